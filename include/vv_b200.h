@@ -1,0 +1,318 @@
+/*
+ * vv_b200.h -- C-ABI of libvv_b200.so: the B200 (sm_100a) implementation of the
+ * temporal-context embedding training hot path of eevignesh/videovector.
+ *
+ * This is the drop-in boundary.  Every entry point takes plain device pointers,
+ * sizes and a CUDA stream, returns an int status (0 = VV_OK, <0 = error, text via
+ * vv_last_error()), and replaces the body of one reference operator.  The
+ * reference has no FFI of its own (it is one C++ binary); the functions here are
+ * what a maintainer would call from the reference's Layer<Dtype>::Forward_gpu /
+ * Backward_gpu / SGDSolver::ComputeUpdateValue bodies, with
+ * `CHECK_EQ(rc, 0)` standing in for the reference's CUDA_CHECK error convention
+ * (include/caffe/util/device_alternate.hpp:48-67).
+ *
+ * Citations "ref:" are file:line in the reference tree.
+ *
+ * Layout conventions (all row-major, fp32 unless stated, like Blob<float>,
+ * ref: include/caffe/blob.hpp:48-59):
+ *   X  [M, K]   bottom of fc7 ("original_feature"), M = R*B rows, row j*B+b is
+ *               slot j of batch item b (block-major, the result of SLICE dim 1 +
+ *               CONCAT dim 0, ref: slice_layer.cu:22-33, concat_layer.cu:13-20)
+ *   W  [N, K]   fc7 weight blob [1,1,N,K] (ref: inner_product_layer.cpp:29)
+ *   Z/H [M, N]  ip1_nonorm / ip2
+ *   slot order inside an item: 0 target, 1..C-1 context, C..C+Nn-1 negatives
+ *               (ref: video_sampled_shots_data_layer.cpp:439-453, 862)
+ *
+ * There is NO CPU fallback anywhere behind this header: every function either
+ * launches sm_100a kernels or returns an error.
+ */
+#ifndef VV_B200_H_
+#define VV_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* vv_stream_t; /* == cudaStream_t; 0 = legacy default stream (stock Caffe) */
+
+enum {
+  VV_OK = 0,
+  VV_ERR_INVALID = -1,     /* bad argument (shape/alignment/null) */
+  VV_ERR_CUDA = -2,        /* CUDA runtime / driver error, see vv_last_error() */
+  VV_ERR_UNSUPPORTED = -3, /* shape not supported by the sm_100a kernels */
+  VV_ERR_NCCL = -4
+};
+
+/* How the projection GEMMs compute (the `dtype` of the path).
+ *   FP32_SIMT : exact fp32 FMA on CUDA cores (validation / odd shapes)
+ *   TF32X3    : tcgen05 kind::tf32, operands split hi+lo, 3 MMAs per product,
+ *               fp32 accumulate in TMEM -> fp32-level accuracy (the 1e-5 parity mode)
+ *   TF32      : tcgen05 kind::tf32, 1 MMA per product (1e-2 loss-curve mode)
+ *   BF16      : tcgen05 kind::f16 with bf16 operands, fp32 accumulate (1e-2 mode) */
+enum vv_precision {
+  VV_PREC_FP32_SIMT = 0,
+  VV_PREC_TF32X3 = 1,
+  VV_PREC_TF32 = 2,
+  VV_PREC_BF16 = 3
+};
+
+/* A GEMM operand as the kernels read it.
+ *   FP32_SIMT / TF32 : hi = the fp32 array itself, lo = NULL
+ *   TF32X3           : hi = round-to-nearest tf32 part, lo = residual (both fp32 arrays)
+ *   BF16             : hi = bf16 array (uint16 storage), lo = NULL
+ * vv_prepare_operand() produces these from an fp32 array; the producer kernels
+ * (gather, rank-loss backward, sgd update) can emit them directly. */
+typedef struct vv_operand {
+  const void* hi;
+  const void* lo;
+} vv_operand_t;
+
+/* ReLU + Dropout spec for the fc7 epilogue.
+ * ref: relu_layer.cu:9-33 (max(x,0)+slope*min(x,0)), dropout_layer.cu:14-41 */
+enum { VV_DROPOUT_NONE = 0, VV_DROPOUT_MASK01 = 1, VV_DROPOUT_MASK_U32 = 2, VV_DROPOUT_PHILOX = 3 };
+typedef struct vv_act {
+  int relu;              /* 0/1 */
+  float negative_slope;  /* relu_param.negative_slope */
+  int dropout_mode;      /* VV_DROPOUT_* */
+  float dropout_ratio;   /* dropout_param.dropout_ratio (threshold_) */
+  const uint32_t* mask;  /* [M,N]: MASK01 -> 0/1 (CPU layer's rand_vec_, dropout_layer.cpp:41);
+                            MASK_U32 -> raw u32, keep iff mask > uint_thres_ (dropout_layer.cu:19) */
+  uint32_t* mask_out;    /* optional [M,N] 0/1 mask written in PHILOX mode (else NULL) */
+  uint64_t seed;         /* PHILOX: key */
+  uint64_t step;         /* PHILOX: iteration, mixed into the counter */
+} vv_act_t;
+
+const char* vv_last_error(void);
+int vv_version(void);
+/* 0 if the current device is sm_100 and the kernels can launch. */
+int vv_device_check(void);
+
+/* ------------------------------------------------------------------------- */
+/* K0: data layer + SLICE(dim1) + CONCAT(dim0) + FLATTEN as one index gather. */
+/* ref: video_sampled_shots_data_layer.cpp:439-453,492-496,856-864 (what is    */
+/* copied where), base_data_layer.cu:7-21, slice_layer.cu:22-33,               */
+/* concat_layer.cu:13-20, flatten_layer.cpp:20-24.                             */
+/* idx   [B,R] int32 bank row per slot (item-major like the data blob [B,R,K]) */
+/* quirk [B,R] int32 or NULL: -2 = full row; >=0 = element K-1 comes from that */
+/*       bank row; -1 = element K-1 is 0.0 (the reference's K-1 copy quirk)    */
+/* Outputs (any may be NULL): X fp32 [R*B,K] bit-exact; Xop.hi/lo operand       */
+/* copies in `prec` layout.  Xblob [B,R,K] = the data blob itself if wanted.    */
+/* ------------------------------------------------------------------------- */
+int vv_gather_rows(const float* bank, int64_t bank_rows, int K,
+                   const int32_t* idx, const int32_t* quirk, int B, int R,
+                   float* X, void* Xop_hi, void* Xop_lo, int prec,
+                   float* Xblob, vv_stream_t stream);
+
+/* fp32 array -> operand copies for `prec` (no-op for FP32_SIMT/TF32). */
+int vv_prepare_operand(const float* src, int64_t count, int prec,
+                       void* hi, void* lo, vv_stream_t stream);
+
+/* ------------------------------------------------------------------------- */
+/* K1: InnerProduct (fc7).  ref: inner_product_layer.cu:12-25 forward,          */
+/* :27-59 backward; CPU restatement inner_product_layer.cpp:61-106.            */
+/* ------------------------------------------------------------------------- */
+/* Forward: Z = X W^T + 1 b^T ; H = dropout(relu(Z)).  act == NULL -> H = Z.    */
+/* Z may be NULL when act != NULL (pre-activation not stored).                  */
+int vv_ip_forward(vv_operand_t X, vv_operand_t W, const float* bias,
+                  int M, int N, int K, int prec, const vv_act_t* act,
+                  float* Z, float* H, vv_stream_t stream);
+
+/* Weight gradient: dW = dZ^T X (overwrite, beta = 0), then dW *= (1+reg/2) if
+ * regularization > 0 (ref: inner_product_layer.cpp:80-90).
+ * nsplit >= 1 slabs are written at dW_parts + s*N*K (split over M); the caller
+ * sums them (vv_sgd_update does, or vv_reduce_parts).  nsplit = 0 lets the
+ * library pick and reduce into dW_parts[0] using `workspace`. */
+int vv_ip_wgrad(vv_operand_t dZ, vv_operand_t X, int M, int N, int K, int prec,
+                float regularization, float* dW_parts, int nsplit,
+                void* workspace, size_t workspace_bytes, vv_stream_t stream);
+size_t vv_ip_wgrad_workspace_bytes(int M, int N, int K, int prec);
+int vv_ip_wgrad_auto_nsplit(int M, int N, int K, int prec);
+
+/* Bias gradient db = dZ^T 1_M (ref: inner_product_layer.cu:48-50). */
+int vv_ip_bias_grad(const float* dZ, int M, int N, float* db, vv_stream_t stream);
+
+/* Bottom gradient dX = dZ W (ref: inner_product_layer.cu:52-58). */
+int vv_ip_dgrad(vv_operand_t dZ, vv_operand_t W, int M, int N, int K, int prec,
+                float* dX, vv_stream_t stream);
+
+/* out[i] = sum_s parts[s*stride + i] */
+int vv_reduce_parts(const float* parts, int nparts, int64_t stride, int64_t count,
+                    float* out, vv_stream_t stream);
+
+/* ------------------------------------------------------------------------- */
+/* K2/K3: slice_emb .. max_margin_loss fused (context mean, 3 L2 normalisations,*/
+/* 1+Nn dot products, hinge loss; and the whole backward down to ip1.diff).     */
+/* ref: eltwise_layer.cpp:67-73,119-143; normalization_layer.cpp:30-112;       */
+/* sum_layer.cpp:32-82; split_layer.cpp:36-51; max_margin_loss_layer.cpp:54-214;*/
+/* dropout_layer.cpp:52-68; relu_layer.cpp:23-36; slice/concat as indexing.     */
+/* ------------------------------------------------------------------------- */
+#define VV_MAX_CONTEXT 64
+typedef struct vv_rank_cfg {
+  int B, C, Nn, N;       /* items, context_size (incl. target), negatives, embedding dim */
+  float coeff[VV_MAX_CONTEXT]; /* eltwise_param.coeff for the C-1 context rows */
+  float margin;          /* max_margin_loss_param.margin */
+  int norm;              /* 1 = L1, 2 = L2 */
+  float eps;             /* 1e-10 (normalization_layer.cpp:36) */
+} vv_rank_cfg_t;
+
+/* floats per item in the `stats` buffer: s_c, then (s_x, p_x) for target, neg_1..Nn */
+static inline int vv_rank_stats_stride(int Nn) { return 1 + 2 * (1 + Nn); }
+
+/* Forward.  H [R*B, N] = ip2 (block-major).  Outputs:
+ *  stats        [B, vv_rank_stats_stride(Nn)]  saved for backward
+ *  target_score [B, Nn] (sum_true with num_output=Nn), neg_score [B, Nn]  (NULL ok)
+ *  item_loss [B], item_viol [B] partial sums (NULL ok) ; loss[0] = mean hinge term,
+ *  violations[0] = #(s+ - s- < 0)  (both device pointers, NULL ok) */
+int vv_rank_loss_forward(const float* H, const vv_rank_cfg_t* cfg, float* stats,
+                         float* target_score, float* neg_score,
+                         float* item_loss, float* item_viol,
+                         float* loss, float* violations, vv_stream_t stream);
+
+/* Backward from saved stats to ip1_nonorm.diff:
+ *  dZ = d(ip2) * dropout_scale * [ip2 > 0]  when act_fused != 0 (ReLU slope 0 and
+ *  dropout folded: ip2 > 0 <=> Z > 0 and mask = 1), else dZ = d(ip2) (then the
+ *  caller runs vv_dropout_backward / vv_relu_backward).
+ *  Any of dZ (fp32), dZop.hi/lo (operand copies for `prec`), db_accum may be NULL.
+ *  db_accum [N] is atomically accumulated with the column sums of dZ (zero it first). */
+int vv_rank_loss_backward(const float* H, const vv_rank_cfg_t* cfg, const float* stats,
+                          float loss_weight, int act_fused, float dropout_scale,
+                          float* dZ, void* dZop_hi, void* dZop_lo, int prec,
+                          float* db_accum, vv_stream_t stream);
+
+/* ------------------------------------------------------------------------- */
+/* K4: SGDSolver::ComputeUpdateValue + Net::Update + Blob::Update in one pass.  */
+/* ref: solver.cpp:486-576, net.cpp:804-839, blob.cpp:113-136.                 */
+/*  g = grad_scale * sum_s grad_parts[s]; g += decay*W (L2) | decay*sign(W) (L1)*/
+/*  hist = momentum*hist + local_rate*g ; diff_out = hist ; W -= hist           */
+/* diff_out may alias grad_parts (slab 0) or be NULL.  Wop_hi/lo: refreshed      */
+/* operand copies of W for `prec` (NULL ok).                                     */
+/* ------------------------------------------------------------------------- */
+int vv_sgd_update(float* W, const float* grad_parts, int nparts, int64_t part_stride,
+                  float* hist, float* diff_out, int64_t count,
+                  float local_rate, float momentum, float local_decay, int reg_type,
+                  float grad_scale, void* Wop_hi, void* Wop_lo, int prec,
+                  vv_stream_t stream);
+/* rate = base_lr * f(iter)  (ref: solver.cpp:441-460), evaluated in float. */
+float vv_learning_rate(const char* policy, float base_lr, float gamma, float power,
+                       int stepsize, int iter);
+
+/* ------------------------------------------------------------------------- */
+/* Standalone layer kernels: exact single-layer semantics for the drop-in Layer */
+/* classes when a net is not fused (ref files as named).                        */
+/* ------------------------------------------------------------------------- */
+int vv_relu_forward(const float* x, int64_t n, float negative_slope, float* y, vv_stream_t s);      /* relu_layer.cu:9-33 */
+int vv_relu_backward(const float* x, const float* dy, int64_t n, float negative_slope, float* dx, vv_stream_t s); /* :35-60 */
+int vv_dropout_forward(const float* x, const uint32_t* mask, int mask_mode, int64_t n, float ratio, float* y, vv_stream_t s); /* dropout_layer.cu:14-41 */
+int vv_dropout_backward(const float* dy, const uint32_t* mask, int mask_mode, int64_t n, float ratio, float* dx, vv_stream_t s); /* :44-70 */
+/* 0/1 mask [rows, cols] drawn from the same Philox stream the fused fc7 epilogue uses (VV_DROPOUT_PHILOX) */
+int vv_dropout_make_mask(uint32_t* mask01, int rows, int cols, float ratio, uint64_t seed, uint64_t step, vv_stream_t s);
+int vv_eltwise_sum_forward(const float* const* bottoms, const float* coeffs, int nb, int64_t n, float* top, vv_stream_t s); /* eltwise_layer.cu:48-54; host arrays of device ptrs */
+int vv_eltwise_prod_forward(const float* a, const float* b, int64_t n, float* top, vv_stream_t s);  /* eltwise_layer.cu:41-47 */
+int vv_axpby(int64_t n, float alpha, const float* x, float beta, float* y, vv_stream_t s);         /* y = alpha*x + beta*y */
+int vv_mul(int64_t n, const float* a, const float* b, float* y, vv_stream_t s);
+int vv_l2norm_forward(const float* x, int num, int dim, float* y, vv_stream_t s);                   /* normalization_layer.cu:10-45 */
+int vv_l2norm_backward(const float* x, const float* dy, int num, int dim, float* dx, vv_stream_t s);/* normalization_layer.cu:47-97 */
+int vv_rowsum_forward(const float* x, int num, int dim, int num_output, float* y, vv_stream_t s);   /* sum_layer.cu:10-31 */
+int vv_rowsum_backward(const float* dy, int num, int dim, int num_output, float* dx, vv_stream_t s);/* sum_layer.cu:33-55 */
+int vv_copy_strided(const float* src, int64_t src_stride, float* dst, int64_t dst_stride,
+                    int64_t rows, int64_t cols, vv_stream_t s);                                     /* slice/concat copies */
+int vv_max_margin_forward(const float* s_true, const float* s_bogus, int count, float margin, int norm,
+                          float* hinge_tmp, float* loss, float* violations, vv_stream_t s);         /* max_margin_loss_layer.cpp:54-127 */
+int vv_max_margin_backward(const float* s_true, const float* s_bogus, int count, float margin, int norm,
+                           float loss_weight, float* d_true, float* d_bogus, vv_stream_t s);        /* :130-214 */
+
+/* ------------------------------------------------------------------------- */
+/* Synthetic feature bank (benchmarks): value(row, col) = relu(approx N(0,1))   */
+/* from an integer hash of (seed,row,col); bit-identical on host and device.    */
+/* ------------------------------------------------------------------------- */
+int vv_fill_bank(float* bank, int64_t rows, int K, uint64_t seed, vv_stream_t stream);
+float vv_bank_value_host(uint64_t seed, int64_t row, int col, int K);
+
+/* ------------------------------------------------------------------------- */
+/* Host sampler: VideoSampledShotsDataLayer's WINDOW sampler as an index stream */
+/* (ref: video_sampled_shots_data_layer.cpp:25-44,245-344,372-507,769-909;     */
+/* util/rng.hpp:43-54).  Self-contained glibc-compatible rand() (TYPE_3, the    */
+/* reference never seeds it -> seed 1), so it is reproducible per rank and does */
+/* not touch process-global state.  No CUDA inside.                             */
+/* ------------------------------------------------------------------------- */
+typedef struct vv_sampler vv_sampler_t;
+vv_sampler_t* vv_sampler_create(int num_videos, const int32_t* video_id,
+                                const int32_t* shot_off /*[V+1]*/, const int32_t* shot_ids,
+                                int batch_size, int context_size, int num_negative_samples,
+                                int max_buffer_size, int negative_swap_percentage,
+                                int max_same_video_negs, int max_tries_for_negs,
+                                unsigned int rand_seed);
+void vv_sampler_destroy(vv_sampler_t* s);
+/* idx, quirk: host [B,R] int32 (see vv_gather_rows).  Returns 0 or <0. */
+int vv_sampler_next(vv_sampler_t* s, int32_t* idx, int32_t* quirk);
+int vv_sampler_cursor(const vv_sampler_t* s);
+/* the generator alone, for tests against libc rand() */
+typedef struct vv_glibc_rand vv_glibc_rand_t;
+vv_glibc_rand_t* vv_glibc_rand_create(unsigned int seed);
+int vv_glibc_rand_next(vv_glibc_rand_t* g);
+void vv_glibc_rand_destroy(vv_glibc_rand_t* g);
+
+/* ------------------------------------------------------------------------- */
+/* Trainer: one data-parallel rank of the fused training step                   */
+/* (gather -> fc7 fwd(+relu+dropout) -> rank loss fwd/bwd -> wgrad -> [allreduce]*/
+/*  -> sgd update), i.e. Solver::Solve's loop body (ref: solver.cpp:177-220)    */
+/* for the shipped net.  One process per GPU; NCCL is loaded at run time.       */
+/* ------------------------------------------------------------------------- */
+typedef struct vv_trainer vv_trainer_t;
+typedef struct vv_trainer_cfg {
+  int B;                 /* items on THIS rank per step */
+  int C, Nn, K, N;
+  float coeff[VV_MAX_CONTEXT]; /* zeros -> 1/(C-1) */
+  float margin; int norm;
+  float dropout_ratio;   /* 0 -> no dropout layer */
+  int dropout_mode;      /* VV_DROPOUT_PHILOX for perf runs, MASK01 for parity */
+  uint64_t dropout_seed;
+  float loss_weight;
+  float regularization;  /* inner_product_param.regularization */
+  /* solver (ref: mednet_embedding_train_solver.prototxt) */
+  char lr_policy[16]; float base_lr, gamma, power; int stepsize;
+  float momentum, weight_decay; int reg_type;  /* 2 = L2, 1 = L1 */
+  float lr_mult[2], decay_mult[2];             /* weight, bias: blobs_lr / weight_decay */
+  int prec;              /* vv_precision */
+  int world_size, rank;  /* data parallel */
+  int compute_dgrad;     /* 0 in the shipped net (net.cpp:68-76) */
+  int keep_blobs;        /* 1: also keep fp32 X / Z / dZ for inspection (parity tests) */
+} vv_trainer_cfg_t;
+
+vv_trainer_t* vv_trainer_create(const vv_trainer_cfg_t* cfg, vv_stream_t stream);
+void vv_trainer_destroy(vv_trainer_t* t);
+/* device pointers owned by the trainer (valid until destroy) */
+float* vv_trainer_weight(vv_trainer_t* t);       /* [N,K] */
+float* vv_trainer_bias(vv_trainer_t* t);         /* [N]   */
+float* vv_trainer_weight_hist(vv_trainer_t* t);
+float* vv_trainer_bias_hist(vv_trainer_t* t);
+float* vv_trainer_weight_diff(vv_trainer_t* t);  /* dW after the step: = hist (reference semantics) */
+float* vv_trainer_bias_diff(vv_trainer_t* t);
+float* vv_trainer_blob(vv_trainer_t* t, const char* name); /* "X","Z","H","dZ","stats","loss","violations","dW_raw","db_raw" */
+/* call after writing weights/bias through the pointers above */
+int vv_trainer_sync_weights(vv_trainer_t* t);
+/* One step.  bank: device feature bank; idx/quirk: DEVICE [B,R] int32 for this
+ * rank's items; mask: explicit dropout mask (MASK01 mode) or NULL; iter: solver
+ * iteration (0-based) used for the learning rate and the Philox stream.
+ * do_update = 0 runs forward/backward only (gradients left in *_diff raw). */
+int vv_trainer_step(vv_trainer_t* t, const float* bank, int64_t bank_rows,
+                    const int32_t* idx, const int32_t* quirk, const uint32_t* mask,
+                    int iter, int do_update);
+/* kernels launched by the last step (for bench.py's gpu_launches claim) */
+int vv_trainer_last_launches(const vv_trainer_t* t);
+/* Inference / extraction: out[rows,N] = relu(F W^T + b) (ref: tools/extract_features.cpp:100-209
+ * reading blob ip2 of videovec_extraction.prototxt:179-205). rows_op = operand copies of F rows. */
+int vv_trainer_extract(vv_trainer_t* t, const float* F, int64_t rows, float* out);
+
+/* Data-parallel plumbing (NCCL over NVLink; ref has none). */
+int vv_dp_unique_id(void* id128 /*128 bytes out*/);
+int vv_dp_init(vv_trainer_t* t, const void* id128);
+int vv_dp_allreduce_inplace(vv_trainer_t* t, float* buf, int64_t count, vv_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VV_B200_H_ */

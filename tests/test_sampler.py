@@ -1,0 +1,97 @@
+"""Row S (sampler): the product's host index sampler reproduces the oracle's (= the reference's
+state machine on the real libc rand()) index stream bit-exactly, and gathering bank rows with
+(idx, quirk) reproduces the materialised data blob, K-1 copy quirk included.
+ref: video_sampled_shots_data_layer.cpp:25-44,245-344,372-507,769-909; util/rng.hpp:43-54."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from videovector_b200 import ops
+
+
+def make_dataset(rng, V, smin, smax, K=None):
+    counts = rng.randint(smin, smax + 1, size=V)
+    video_id = (rng.permutation(V) + 100).astype(np.int32)           # arbitrary, unique ids
+    shot_off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    shot_ids = np.concatenate([np.sort(rng.choice(1000, c, replace=False)) for c in counts]).astype(np.int32)
+    feat = rng.normal(0, 1, (shot_off[-1], K)).astype(np.float32) if K else None
+    return video_id, shot_off, shot_ids, feat
+
+
+def test_glibc_rand_matches_libc(vvlib):
+    libc = ctypes.CDLL("libc.so.6")
+    for seed in (1, 2, 12345, 0, 4294967295):
+        libc.srand(ctypes.c_uint(seed))
+        g = vvlib.vv_glibc_rand_create(seed)
+        a = [libc.rand() for _ in range(5000)]
+        b = [vvlib.vv_glibc_rand_next(g) for _ in range(5000)]
+        vvlib.vv_glibc_rand_destroy(g)
+        assert a == b, "seed %d" % seed
+
+
+CASES = [
+    # V, smin, smax, B, C, Nn, P, swap, max_same
+    (300, 1, 12, 16, 5, 10, 50, 50, 6),     # many records skipped (n < C), ragged shot counts
+    (200, 6, 40, 32, 5, 10, 100, 50, 6),    # the shipped parameters at small buffer
+    (120, 18, 30, 8, 17, 50, 400, 50, 6),   # cfg-4: window +-8, 50 negatives
+    (150, 3, 9, 8, 3, 4, 30, 0, 2),         # no swapping
+    (150, 5, 9, 8, 5, 6, 40, 99, 6),        # n == C records (no same-video negatives), heavy swapping
+    (64, 8, 8, 128, 5, 10, 60, 50, 6),      # cursor wraps several times per batch
+]
+
+
+@pytest.mark.parametrize("V,smin,smax,B,C,Nn,P,swap,max_same", CASES)
+def test_index_stream_matches_oracle(vvlib, oracle, V, smin, smax, B, C, Nn, P, swap, max_same):
+    rng = np.random.RandomState(V + B)
+    video_id, shot_off, shot_ids, _ = make_dataset(rng, V, smin, smax)
+    for seed in (1, 77):
+        osmp = oracle.Sampler(video_id, shot_off, shot_ids, None, 4, B, C, Nn, P, swap, max_same, 100, seed=seed)
+        ostream = [osmp.next()[:2] for _ in range(12)]      # consumes libc rand(): run the oracle to completion first
+        ocur = osmp.cursor
+        osmp.close()
+        psmp = ops.Sampler(video_id, shot_off, shot_ids, B, C, Nn, P, swap, max_same, 100, rand_seed=seed)
+        for it, (oi, oq) in enumerate(ostream):
+            pi, pq = psmp.next()
+            assert np.array_equal(pi, oi), "idx differs at batch %d" % it
+            assert np.array_equal(pq, oq), "quirk differs at batch %d" % it
+        assert psmp.cursor == ocur
+        psmp.close()
+
+
+def test_gather_reproduces_materialised_blob(oracle):
+    """numpy gather of (idx, quirk) == the data blob the reference would have built (incl. K-1 quirk)."""
+    rng = np.random.RandomState(3)
+    K = 12
+    video_id, shot_off, shot_ids, feat = make_dataset(rng, 80, 4, 20, K)
+    smp = oracle.Sampler(video_id, shot_off, shot_ids, feat, K, 16, 5, 10, 60, 50, 6, 100, seed=1)
+    saw_quirk_shot = saw_quirk_zero = False
+    for _ in range(10):
+        idx, quirk, data = smp.next()
+        g = feat[idx]                                           # [B,R,K]
+        q = quirk >= 0
+        g[..., K - 1] = np.where(q, feat[np.maximum(quirk, 0), K - 1], g[..., K - 1])
+        g[..., K - 1] = np.where(quirk == -1, 0.0, g[..., K - 1])
+        assert np.array_equal(g, data)
+        saw_quirk_shot |= bool(q.any()); saw_quirk_zero |= bool((quirk == -1).any())
+    assert saw_quirk_shot and saw_quirk_zero
+    smp.close()
+
+
+def test_sampler_rejects_bad_parameters(vvlib):
+    video_id, shot_off, shot_ids = ops.synthetic_videos(10, 8)
+    with pytest.raises(Exception):
+        ops.Sampler(video_id, shot_off, shot_ids, 4, context_size=4)              # even context (CHECK :435)
+    with pytest.raises(Exception):
+        ops.Sampler(video_id, shot_off, shot_ids, 4, max_buffer_size=5000)        # cannot find 5000 unique shots (CHECK_EQ :346)
+    with pytest.raises(Exception):
+        ops.Sampler(video_id, shot_off, shot_ids, 4, negative_swap_percentage=100, max_buffer_size=20)
+
+
+def test_synthetic_bank_hash_host_matches_numpy(vvlib):
+    b = ops.bank_host(5, 16, 1234)
+    for r in range(5):
+        for c in range(16):
+            assert b[r, c] == vvlib.vv_bank_value_host(1234, r, c, 16)
+    big = ops.bank_host(64, 256, 1234)
+    assert 0.3 < (big > 0).mean() < 0.7 and 0.4 < big.std() < 0.8

@@ -1,0 +1,305 @@
+// vv_trainer.cu -- one data-parallel rank of the fused training step (host C++).
+//
+// The loop body of Solver::Solve for the shipped net (ref: solver.cpp:177-220:
+// ForwardBackward, ComputeUpdateValue, Net::Update) as a fixed kernel sequence:
+//   K0 gather -> K1 fc7 fwd (+ReLU+dropout epilogue) -> K2 rank-loss fwd ->
+//   K3 rank-loss bwd (+ReLU'/dropout', db) -> K1 wgrad (split-K slabs) ->
+//   [K1 dgrad] -> [NCCL allreduce of dW, db, loss] -> K4 fused SGD update
+// One process per GPU; NCCL is dlopen'ed (the copy already loaded by the host
+// process, e.g. torch's, is reused), so the library has no link-time dependency.
+#include <dlfcn.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include "../vv_common.cuh"
+
+using namespace vv;
+
+namespace {
+
+// ---- minimal NCCL binding --------------------------------------------------
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+struct Nccl {
+  void* h = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool load() {
+    if (h) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) { h = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (h) break; }
+    if (!h) { set_error("cannot dlopen libnccl.so.2: %s", dlerror()); return false; }
+    GetUniqueId = (decltype(GetUniqueId))dlsym(h, "ncclGetUniqueId");
+    CommInitRank = (decltype(CommInitRank))dlsym(h, "ncclCommInitRank");
+    AllReduce = (decltype(AllReduce))dlsym(h, "ncclAllReduce");
+    CommDestroy = (decltype(CommDestroy))dlsym(h, "ncclCommDestroy");
+    GetErrorString = (decltype(GetErrorString))dlsym(h, "ncclGetErrorString");
+    if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy) { set_error("libnccl is missing symbols"); return false; }
+    return true;
+  }
+};
+Nccl g_nccl;
+constexpr int kNcclFloat = 7, kNcclSum = 0;
+
+struct DevBuf {
+  void* p = nullptr; size_t bytes = 0;
+  int alloc(size_t n) {
+    bytes = n;
+    if (n == 0) return VV_OK;
+    VV_CUDA(cudaMalloc(&p, n));
+    VV_CUDA(cudaMemset(p, 0, n));      // zero-fill on first touch like SyncedMemory (syncedmem.cpp:24-25)
+    return VV_OK;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; }
+  template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+}  // namespace
+
+struct vv_trainer {
+  vv_trainer_cfg_t cfg;
+  cudaStream_t stream = nullptr;
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_grad = nullptr, ev_comm = nullptr;
+  int R = 0, M = 0, nsplit = 1;
+  vv_rank_cfg_t rank;
+  // parameters
+  DevBuf W, b, Wh, bh, W_hi, W_lo;
+  // activations / gradients
+  DevBuf Xf, X_hi, X_lo, Zf, H, stats, item_loss, item_viol, dZf, dZ_hi, dZ_lo, dW_parts, dbx, dX;
+  ncclComm_t comm = nullptr;
+  int last_launches = 0;
+
+  vv_operand_t opX() const { return op(Xf, X_hi, X_lo); }
+  vv_operand_t opW() const { return op(W, W_hi, W_lo); }
+  vv_operand_t opdZ() const { return op(dZf, dZ_hi, dZ_lo); }
+  vv_operand_t op(const DevBuf& f, const DevBuf& hi, const DevBuf& lo) const {
+    vv_operand_t o;
+    if (cfg.prec == VV_PREC_TF32X3) { o.hi = hi.p; o.lo = lo.p; }
+    else if (cfg.prec == VV_PREC_BF16) { o.hi = hi.p; o.lo = nullptr; }
+    else { o.hi = f.p; o.lo = nullptr; }
+    return o;
+  }
+  bool needs_f32_operand() const { return cfg.prec == VV_PREC_FP32_SIMT || cfg.prec == VV_PREC_TF32; }
+
+  int init() {
+    R = cfg.C + cfg.Nn; M = R * cfg.B;
+    const size_t MK = size_t(M) * cfg.K, MN = size_t(M) * cfg.N, NK = size_t(cfg.N) * cfg.K;
+    const bool f32op = needs_f32_operand();
+    int rc;
+#define A(buf, n) if ((rc = buf.alloc(n))) return rc
+    A(W, NK * 4); A(b, size_t(cfg.N) * 4); A(Wh, NK * 4); A(bh, size_t(cfg.N) * 4);
+    if (cfg.prec == VV_PREC_TF32X3) { A(W_hi, NK * 4); A(W_lo, NK * 4); A(X_hi, MK * 4); A(X_lo, MK * 4); A(dZ_hi, MN * 4); A(dZ_lo, MN * 4); }
+    if (cfg.prec == VV_PREC_BF16) { A(W_hi, NK * 2); A(X_hi, MK * 2); A(dZ_hi, MN * 2); }
+    if (f32op || cfg.keep_blobs) { A(Xf, MK * 4); A(dZf, MN * 4); }
+    if (cfg.keep_blobs) { A(Zf, MN * 4); }
+    A(H, MN * 4);
+    A(stats, size_t(cfg.B) * vv_rank_stats_stride(cfg.Nn) * 4);
+    A(item_loss, size_t(cfg.B) * 4); A(item_viol, size_t(cfg.B) * 4);
+    nsplit = vv_ip_wgrad_auto_nsplit(M, cfg.N, cfg.K, cfg.prec);
+    A(dW_parts, size_t(nsplit) * NK * 4);
+    A(dbx, size_t(cfg.N + 4) * 4);            // db [N] + loss + violations (+pad): one allreduce payload
+    if (cfg.compute_dgrad) { A(dX, MK * 4); }
+#undef A
+    memset(&rank, 0, sizeof(rank));
+    rank.B = cfg.B; rank.C = cfg.C; rank.Nn = cfg.Nn; rank.N = cfg.N;
+    bool any = false;
+    for (int i = 0; i < cfg.C - 1 && i < VV_MAX_CONTEXT; ++i) any = any || cfg.coeff[i] != 0.f;
+    for (int i = 0; i < cfg.C - 1 && i < VV_MAX_CONTEXT; ++i)
+      rank.coeff[i] = any ? cfg.coeff[i] : 1.f / float(cfg.C - 1);
+    rank.margin = cfg.margin; rank.norm = cfg.norm; rank.eps = 1e-10f;
+    if (cfg.world_size > 1) {
+      VV_CUDA(cudaStreamCreateWithFlags(&comm_stream, cudaStreamNonBlocking));
+      VV_CUDA(cudaEventCreateWithFlags(&ev_grad, cudaEventDisableTiming));
+      VV_CUDA(cudaEventCreateWithFlags(&ev_comm, cudaEventDisableTiming));
+    }
+    return VV_OK;
+  }
+  ~vv_trainer() {
+    if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
+    DevBuf* all[] = {&W, &b, &Wh, &bh, &W_hi, &W_lo, &Xf, &X_hi, &X_lo, &Zf, &H, &stats, &item_loss, &item_viol,
+                     &dZf, &dZ_hi, &dZ_lo, &dW_parts, &dbx, &dX};
+    for (DevBuf* d : all) d->release();
+    if (ev_grad) cudaEventDestroy(ev_grad);
+    if (ev_comm) cudaEventDestroy(ev_comm);
+    if (comm_stream) cudaStreamDestroy(comm_stream);
+  }
+  float* loss_ptr() { return dbx.as<float>() + cfg.N; }
+  float* viol_ptr() { return dbx.as<float>() + cfg.N + 1; }
+};
+
+extern "C" vv_trainer_t* vv_trainer_create(const vv_trainer_cfg_t* cfg, vv_stream_t stream) {
+  if (!cfg) { set_error("trainer cfg is NULL"); return nullptr; }
+  if (cfg->B < 1 || cfg->C < 3 || (cfg->C % 2) != 1 || cfg->Nn < 1 || cfg->K < 4 || cfg->N < 4 || (cfg->K % 4) || (cfg->N % 4)) {
+    set_error("bad trainer cfg: B=%d C=%d Nn=%d K=%d N=%d", cfg->B, cfg->C, cfg->Nn, cfg->K, cfg->N); return nullptr;
+  }
+  if (cfg->prec < VV_PREC_FP32_SIMT || cfg->prec > VV_PREC_BF16) { set_error("bad precision %d", cfg->prec); return nullptr; }
+  if (cfg->world_size < 1 || cfg->rank < 0 || cfg->rank >= cfg->world_size) { set_error("bad rank/world_size"); return nullptr; }
+  if (vv_device_check() != VV_OK) return nullptr;
+  vv_trainer* t = new vv_trainer();
+  t->cfg = *cfg;
+  t->stream = reinterpret_cast<cudaStream_t>(stream);
+  if (t->init() != VV_OK) { delete t; return nullptr; }
+  return t;
+}
+extern "C" void vv_trainer_destroy(vv_trainer_t* t) { delete t; }
+extern "C" float* vv_trainer_weight(vv_trainer_t* t) { return t->W.as<float>(); }
+extern "C" float* vv_trainer_bias(vv_trainer_t* t) { return t->b.as<float>(); }
+extern "C" float* vv_trainer_weight_hist(vv_trainer_t* t) { return t->Wh.as<float>(); }
+extern "C" float* vv_trainer_bias_hist(vv_trainer_t* t) { return t->bh.as<float>(); }
+extern "C" float* vv_trainer_weight_diff(vv_trainer_t* t) { return t->dW_parts.as<float>(); }
+extern "C" float* vv_trainer_bias_diff(vv_trainer_t* t) { return t->dbx.as<float>(); }
+extern "C" float* vv_trainer_blob(vv_trainer_t* t, const char* name) {
+  const std::string n(name ? name : "");
+  if (n == "X") return t->Xf.as<float>();
+  if (n == "Z") return t->Zf.as<float>();
+  if (n == "H") return t->H.as<float>();
+  if (n == "dZ") return t->dZf.as<float>();
+  if (n == "stats") return t->stats.as<float>();
+  if (n == "loss") return t->loss_ptr();
+  if (n == "violations") return t->viol_ptr();
+  if (n == "dW_raw") return t->dW_parts.as<float>();
+  if (n == "db_raw") return t->dbx.as<float>();
+  if (n == "dX") return t->dX.as<float>();
+  set_error("unknown trainer blob '%s'", n.c_str());
+  return nullptr;
+}
+extern "C" int vv_trainer_last_launches(const vv_trainer_t* t) { return t->last_launches; }
+
+extern "C" int vv_trainer_sync_weights(vv_trainer_t* t) {
+  const int64_t NK = int64_t(t->cfg.N) * t->cfg.K;
+  return vv_prepare_operand(t->W.as<float>(), NK, t->cfg.prec, t->W_hi.p, t->W_lo.p,
+                            reinterpret_cast<vv_stream_t>(t->stream));
+}
+
+extern "C" int vv_trainer_step(vv_trainer_t* t, const float* bank, int64_t bank_rows, const int32_t* idx,
+                               const int32_t* quirk, const uint32_t* mask, int iter, int do_update) {
+  const vv_trainer_cfg_t& c = t->cfg;
+  vv_stream_t s = reinterpret_cast<vv_stream_t>(t->stream);
+  const int M = t->M, N = c.N, K = c.K;
+  const int64_t NK = int64_t(N) * K;
+  int rc;
+  launches_reset();
+  // K0
+  if ((rc = vv_gather_rows(bank, bank_rows, K, idx, quirk, c.B, t->R, t->Xf.as<float>(), t->X_hi.p, t->X_lo.p, c.prec,
+                           nullptr, s))) return rc;
+  // K1 forward with fused bias + ReLU + dropout
+  vv_act_t act; memset(&act, 0, sizeof(act));
+  act.relu = 1; act.negative_slope = 0.f;
+  const bool has_dropout = c.dropout_ratio > 0.f;
+  act.dropout_mode = has_dropout ? c.dropout_mode : VV_DROPOUT_NONE;
+  act.dropout_ratio = c.dropout_ratio; act.mask = mask; act.seed = c.dropout_seed; act.step = uint64_t(iter);
+  if (has_dropout && (act.dropout_mode == VV_DROPOUT_MASK01 || act.dropout_mode == VV_DROPOUT_MASK_U32) && !mask) {
+    set_error("trainer: dropout mask mode needs a mask"); return VV_ERR_INVALID;
+  }
+  if ((rc = vv_ip_forward(t->opX(), t->opW(), t->b.as<float>(), M, N, K, c.prec, &act, t->Zf.as<float>(),
+                          t->H.as<float>(), s))) return rc;
+  // K2
+  if ((rc = vv_rank_loss_forward(t->H.as<float>(), &t->rank, t->stats.as<float>(), nullptr, nullptr,
+                                 t->item_loss.as<float>(), t->item_viol.as<float>(), t->loss_ptr(), t->viol_ptr(), s))) return rc;
+  // K3 (+ bias gradient)
+  VV_CUDA(cudaMemsetAsync(t->dbx.p, 0, size_t(N) * 4, t->stream));
+  count_launch();
+  const float dscale = has_dropout ? dropout_scale(c.dropout_ratio) : 1.f;
+  if ((rc = vv_rank_loss_backward(t->H.as<float>(), &t->rank, t->stats.as<float>(), c.loss_weight, 1, dscale,
+                                  t->dZf.as<float>(), t->dZ_hi.p, t->dZ_lo.p, c.prec, t->dbx.as<float>(), s))) return rc;
+  // K1 wgrad into split-K slabs
+  if ((rc = vv_ip_wgrad(t->opdZ(), t->opX(), M, N, K, c.prec, c.regularization, t->dW_parts.as<float>(), t->nsplit,
+                        nullptr, 0, s))) return rc;
+  if (c.compute_dgrad) {
+    if ((rc = vv_ip_dgrad(t->opdZ(), t->opW(), M, N, K, c.prec, t->dX.as<float>(), s))) return rc;
+  }
+  int nparts = t->nsplit;
+  float gscale = 1.f;
+  if (c.world_size > 1) {
+    if (!t->comm) { set_error("trainer: world_size > 1 but vv_dp_init was not called"); return VV_ERR_NCCL; }
+    if (nparts > 1) {
+      if ((rc = vv_reduce_parts(t->dW_parts.as<float>(), nparts, NK, NK, t->dW_parts.as<float>(), s))) return rc;
+      nparts = 1;
+    }
+    VV_CUDA(cudaEventRecord(t->ev_grad, t->stream));
+    VV_CUDA(cudaStreamWaitEvent(t->comm_stream, t->ev_grad, 0));
+    ncclResult_t r1 = g_nccl.AllReduce(t->dW_parts.p, t->dW_parts.p, size_t(NK), kNcclFloat, kNcclSum, t->comm, t->comm_stream);
+    ncclResult_t r2 = g_nccl.AllReduce(t->dbx.p, t->dbx.p, size_t(N + 2), kNcclFloat, kNcclSum, t->comm, t->comm_stream);
+    if (r1 != 0 || r2 != 0) { set_error("ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r1 ? r1 : r2) : "?"); return VV_ERR_NCCL; }
+    VV_CUDA(cudaEventRecord(t->ev_comm, t->comm_stream));
+    VV_CUDA(cudaStreamWaitEvent(t->stream, t->ev_comm, 0));
+    count_launch(2);
+    gscale = 1.f / float(c.world_size);
+  }
+  if (do_update) {
+    // ref: solver.cpp:486-576 + net.cpp:804-839; weight then bias (net.params() order)
+    const float rate = vv_learning_rate(c.lr_policy, c.base_lr, c.gamma, c.power, c.stepsize, iter);
+    if (rate < 0.f) return VV_ERR_INVALID;
+    if ((rc = vv_sgd_update(t->W.as<float>(), t->dW_parts.as<float>(), nparts, NK, t->Wh.as<float>(),
+                            t->dW_parts.as<float>(), NK, rate * c.lr_mult[0], c.momentum, c.weight_decay * c.decay_mult[0],
+                            c.reg_type, gscale, t->W_hi.p, t->W_lo.p, c.prec, s))) return rc;
+    if ((rc = vv_sgd_update(t->b.as<float>(), t->dbx.as<float>(), 1, 0, t->bh.as<float>(), t->dbx.as<float>(), N,
+                            rate * c.lr_mult[1], c.momentum, c.weight_decay * c.decay_mult[1], c.reg_type, gscale,
+                            nullptr, nullptr, VV_PREC_FP32_SIMT, s))) return rc;
+    if (c.world_size > 1) {
+      // loss/violations were summed over ranks: loss -> mean over ranks (global-batch mean)
+      if ((rc = vv_axpby(1, gscale, t->loss_ptr(), 0.f, t->loss_ptr(), s))) return rc;
+    }
+  } else if (nparts > 1) {
+    if ((rc = vv_reduce_parts(t->dW_parts.as<float>(), nparts, NK, NK, t->dW_parts.as<float>(), s))) return rc;
+  }
+  t->last_launches = launches_reset();
+  return VV_OK;
+}
+
+extern "C" int vv_trainer_extract(vv_trainer_t* t, const float* F, int64_t rows, float* out) {
+  const vv_trainer_cfg_t& c = t->cfg;
+  vv_stream_t s = reinterpret_cast<vv_stream_t>(t->stream);
+  if (!F || !out || rows <= 0) { set_error("extract: bad arguments"); return VV_ERR_INVALID; }
+  vv_act_t act; memset(&act, 0, sizeof(act));
+  act.relu = 1; act.dropout_mode = VV_DROPOUT_NONE;      // TEST phase: dropout is a copy (dropout_layer.cpp:46-48)
+  int rc;
+  launches_reset();
+  for (int64_t r0 = 0; r0 < rows; r0 += t->M) {
+    const int m = int(rows - r0 < t->M ? rows - r0 : t->M);
+    vv_operand_t x;
+    if (t->needs_f32_operand()) { x.hi = F + r0 * c.K; x.lo = nullptr; }
+    else {
+      if ((rc = vv_prepare_operand(F + r0 * c.K, int64_t(m) * c.K, c.prec, t->X_hi.p, t->X_lo.p, s))) return rc;
+      x.hi = t->X_hi.p; x.lo = t->X_lo.p;
+    }
+    if ((rc = vv_ip_forward(x, t->opW(), t->b.as<float>(), m, c.N, c.K, c.prec, &act, nullptr, out + r0 * c.N, s))) return rc;
+  }
+  t->last_launches = launches_reset();
+  return VV_OK;
+}
+
+// ---- data-parallel plumbing -------------------------------------------------
+extern "C" int vv_dp_unique_id(void* id128) {
+  if (!id128) return VV_ERR_INVALID;
+  if (!g_nccl.load()) return VV_ERR_NCCL;
+  ncclUniqueId id;
+  ncclResult_t r = g_nccl.GetUniqueId(&id);
+  if (r != 0) { set_error("ncclGetUniqueId failed (%d)", r); return VV_ERR_NCCL; }
+  memcpy(id128, &id, 128);
+  return VV_OK;
+}
+extern "C" int vv_dp_init(vv_trainer_t* t, const void* id128) {
+  if (!t || !id128) return VV_ERR_INVALID;
+  if (t->cfg.world_size == 1) return VV_OK;
+  if (!g_nccl.load()) return VV_ERR_NCCL;
+  ncclUniqueId id; memcpy(&id, id128, 128);
+  ncclResult_t r = g_nccl.CommInitRank(&t->comm, t->cfg.world_size, id, t->cfg.rank);
+  if (r != 0) { set_error("ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"); return VV_ERR_NCCL; }
+  return VV_OK;
+}
+extern "C" int vv_dp_allreduce_inplace(vv_trainer_t* t, float* buf, int64_t count, vv_stream_t stream) {
+  if (!t || !buf || count <= 0) return VV_ERR_INVALID;
+  if (t->cfg.world_size == 1) return VV_OK;
+  if (!t->comm) { set_error("vv_dp_init was not called"); return VV_ERR_NCCL; }
+  ncclResult_t r = g_nccl.AllReduce(buf, buf, size_t(count), kNcclFloat, kNcclSum, t->comm, reinterpret_cast<cudaStream_t>(stream));
+  if (r != 0) { set_error("ncclAllReduce failed (%d)", r); return VV_ERR_NCCL; }
+  return VV_OK;
+}

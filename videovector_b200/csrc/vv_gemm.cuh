@@ -1,0 +1,84 @@
+// vv_gemm.cuh -- internal interface of the projection GEMMs (K1).
+#pragma once
+#include "vv_common.cuh"
+
+namespace vv {
+
+// Which contraction of the fc7 layer (ref: inner_product_layer.cu:12-59)
+enum GemmKind {
+  GEMM_FWD = 0,    // D[M,N]  = X[M,K]  . W[N,K]^T     A K-major,  B K-major,  reduce K
+  GEMM_WGRAD = 1,  // D[N,K]  = dZ[M,N]^T . X[M,K]     A MN-major, B MN-major, reduce M
+  GEMM_DGRAD = 2   // D[M,K]  = dZ[M,N] . W[N,K]       A K-major,  B MN-major, reduce N
+};
+
+// Epilogue description (device side copy of vv_act_t plus bias / scaling)
+struct GemmEpilogue {
+  const float* bias;      // per output column, or NULL (FWD only)
+  float* Z;               // optional pre-activation output (FWD only)
+  int has_act;
+  int relu; float negative_slope;
+  int dropout_mode; float dropout_scale; uint32_t dropout_thres;
+  const uint32_t* mask; uint32_t* mask_out;
+  uint64_t seed, step;
+  float out_scale;        // multiplies the accumulator (wgrad regularization), 1 otherwise
+};
+
+// D_rows x D_cols output (row pitch ldd), reduction length red.
+// nsplit slabs (split over the reduction) are written at D + s*slab_stride.
+struct GemmProblem {
+  GemmKind kind;
+  int prec;               // vv_precision
+  vv_operand_t A, B;      // see GemmKind for which arrays these are
+  int M, N, K;            // the fc7 dims (rows, outputs, inputs) -- NOT the tile dims
+  float* D; int64_t slab_stride; int nsplit;
+  GemmEpilogue epi;
+};
+
+int gemm_tc_launch(const GemmProblem& p, cudaStream_t stream);     // tcgen05 path (TF32X3 / TF32 / BF16)
+int gemm_simt_launch(const GemmProblem& p, cudaStream_t stream);   // exact fp32 path
+bool gemm_tc_supported(const GemmProblem& p, const char** why);
+
+// ---- shared epilogue element math (used by both paths) ----------------------
+// Applies bias/ReLU/dropout to 4 consecutive columns [col, col+4) of row `row`.
+__device__ __forceinline__ void epilogue_act4(const GemmEpilogue& e, int N, int row, int col,
+                                              float4& v, float4& z_out) {
+  if (e.bias) {
+    const float4 b = *reinterpret_cast<const float4*>(e.bias + col);
+    v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+  }
+  z_out = v;
+  if (!e.has_act) return;
+  if (e.relu) {
+    const float s = e.negative_slope;
+    v.x = fmaxf(v.x, 0.f) + s * fminf(v.x, 0.f);
+    v.y = fmaxf(v.y, 0.f) + s * fminf(v.y, 0.f);
+    v.z = fmaxf(v.z, 0.f) + s * fminf(v.z, 0.f);
+    v.w = fmaxf(v.w, 0.f) + s * fminf(v.w, 0.f);
+  }
+  if (e.dropout_mode == VV_DROPOUT_NONE) return;
+  uint32_t keep[4];
+  if (e.dropout_mode == VV_DROPOUT_PHILOX) {
+    uint32_t w[4];
+    dropout_words(e.seed, e.step, uint32_t(row), uint32_t(col >> 2), w);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) keep[j] = (w[j] > e.dropout_thres) ? 1u : 0u;
+    if (e.mask_out) {
+      *reinterpret_cast<uint4*>(e.mask_out + size_t(row) * N + col) = make_uint4(keep[0], keep[1], keep[2], keep[3]);
+    }
+  } else {
+    const uint4 m = *reinterpret_cast<const uint4*>(e.mask + size_t(row) * N + col);
+    if (e.dropout_mode == VV_DROPOUT_MASK_U32) {
+      keep[0] = m.x > e.dropout_thres; keep[1] = m.y > e.dropout_thres;
+      keep[2] = m.z > e.dropout_thres; keep[3] = m.w > e.dropout_thres;
+    } else {
+      keep[0] = m.x; keep[1] = m.y; keep[2] = m.z; keep[3] = m.w;
+    }
+  }
+  // reference order: x * mask * scale (dropout_layer.cpp:44)
+  v.x = v.x * float(keep[0]) * e.dropout_scale;
+  v.y = v.y * float(keep[1]) * e.dropout_scale;
+  v.z = v.z * float(keep[2]) * e.dropout_scale;
+  v.w = v.w * float(keep[3]) * e.dropout_scale;
+}
+
+}  // namespace vv

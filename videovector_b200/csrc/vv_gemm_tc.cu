@@ -1,0 +1,369 @@
+// vv_gemm_tc.cu -- K1: the fc7 projection GEMMs on 5th-gen tensor cores.
+//
+// One persistent, warp-specialised kernel template for sm_100a:
+//   warp 0   : TMA producer  (cp.async.bulk.tensor 2D tiles, SWIZZLE_128B, mbarrier tx)
+//   warp 1   : MMA issuer    (tcgen05.mma cta_group::1, 128 x BLOCK_N x (32 B of K), fp32 accum in TMEM)
+//   warp 2   : TMEM allocator
+//   warps 4-7: epilogue      (tcgen05.ld 32x32b -> bias / ReLU / dropout / scale -> global)
+// Two TMEM accumulator buffers (2 x BLOCK_N columns) let the epilogue of tile i
+// overlap the main loop of tile i+1.
+//
+// The three contractions of the reference layer (ref: inner_product_layer.cu:12-59)
+// differ only in operand major-ness, expressed in the UMMA descriptors:
+//   FWD   D[M,N] = X W^T      A = X  [M,K] K-major      B = W [N,K] K-major
+//   WGRAD D[N,K] = dZ^T X     A = dZ [M,N] MN-major     B = X [M,K] MN-major   (reduce M, split-K slabs)
+//   DGRAD D[M,K] = dZ W       A = dZ [M,N] K-major      B = W [N,K] MN-major   (reduce N)
+// Precisions: bf16 (kind::f16), tf32 (kind::tf32), and tf32x3 = hi/lo split operands,
+// three MMAs per k-step (lo*hi + hi*lo + hi*hi) for fp32-level accuracy.
+#include <cuda.h>
+#include "vv_gemm.cuh"
+
+namespace vv {
+
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kRowBytes = 128;            // bytes of the contiguous dim per smem row (= swizzle span)
+constexpr int kNumThreads = 256;
+
+struct TcParams {
+  int d_rows, d_cols, ldd;      // output extent and row pitch
+  int tiles_m, tiles_n, nsplit;
+  int num_kb, kb_per_split;     // k-blocks (of kRowBytes worth of elements)
+  float* D; long long slab_stride;
+  int act_N;                    // row pitch of mask/Z (= N of the layer) for the FWD epilogue
+  GemmEpilogue epi;
+};
+
+template <bool kTF32, bool kAMN, bool kBMN, int kNProd, int kBlockN, int kStages, bool kFwdEpi>
+struct Cfg {
+  static constexpr bool tf32 = kTF32;
+  static constexpr bool a_mn = kAMN, b_mn = kBMN;
+  static constexpr int nprod = kNProd;                 // 1 or 3
+  static constexpr int parts = (kNProd == 3) ? 2 : 1;  // hi (+ lo)
+  static constexpr int block_n = kBlockN;
+  static constexpr int stages = kStages;
+  static constexpr bool fwd_epi = kFwdEpi;
+  static constexpr int elem_bytes = kTF32 ? 4 : 2;
+  static constexpr int bk = kRowBytes / elem_bytes;    // reduction elements per k-block (32 / 64)
+  static constexpr int umma_k = 32 / elem_bytes;       // 8 / 16
+  static constexpr int ksteps = bk / umma_k;           // 4
+  static constexpr int chunk = kRowBytes / elem_bytes; // MN elements per 128B row (MN-major)
+  static constexpr int a_bytes = kBlockM * kRowBytes;  // 16 KB per part
+  static constexpr int b_bytes = kBlockN * kRowBytes;  // 32 KB per part (BLOCK_N = 256)
+  static constexpr int stage_bytes = parts * (a_bytes + b_bytes);
+  static constexpr int tmem_cols = 2 * kBlockN;
+  static constexpr int smem_bytes = stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static_assert(tmem_cols == 256 || tmem_cols == 512, "TMEM allocation must be a power of two");
+  static_assert(smem_bytes <= 232448, "exceeds 227 KB of shared memory");
+};
+
+template <class C>
+__global__ void __launch_bounds__(kNumThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+               const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+               const TcParams p) {
+#if defined(__CUDA_ARCH__)
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::stages * C::stage_bytes);
+  uint64_t* empty_bar = full_bar + C::stages;
+  uint64_t* tmem_full = empty_bar + C::stages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmB_hi);
+    if (C::parts == 2) { tma_prefetch_desc(&tmA_lo); tma_prefetch_desc(&tmB_lo); }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 2) { tmem_alloc(tmem_slot, C::tmem_cols); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_mn = p.tiles_m * p.tiles_n;
+  const int total_units = tiles_mn * p.nsplit;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+        const int split = u / tiles_mn;
+        const int t = u - split * tiles_mn;
+        const int m0 = (t / p.tiles_n) * kBlockM;
+        const int n0 = (t % p.tiles_n) * C::block_n;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          mbar_arrive_expect_tx(&full_bar[stage], C::stage_bytes);
+          uint8_t* sa = smem + stage * C::stage_bytes;
+          uint8_t* sb = sa + C::parts * C::a_bytes;
+          const int k0 = kb * C::bk;
+#pragma unroll
+          for (int part = 0; part < C::parts; ++part) {
+            const CUtensorMap* ta = part ? &tmA_lo : &tmA_hi;
+            const CUtensorMap* tb = part ? &tmB_lo : &tmB_hi;
+            if (!C::a_mn) {
+              tma_load_2d(sa + part * C::a_bytes, ta, &full_bar[stage], k0, m0);
+            } else {
+#pragma unroll
+              for (int c = 0; c < kBlockM / C::chunk; ++c)
+                tma_load_2d(sa + part * C::a_bytes + c * (C::bk * kRowBytes), ta, &full_bar[stage],
+                            m0 + c * C::chunk, k0);
+            }
+            if (!C::b_mn) {
+              tma_load_2d(sb + part * C::b_bytes, tb, &full_bar[stage], k0, n0);
+            } else {
+#pragma unroll
+              for (int c = 0; c < C::block_n / C::chunk; ++c)
+                tma_load_2d(sb + part * C::b_bytes + c * (C::bk * kRowBytes), tb, &full_bar[stage],
+                            n0 + c * C::chunk, k0);
+            }
+          }
+          if (++stage == C::stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(C::tf32 ? 2 : 1, C::a_mn ? 1 : 0, C::b_mn ? 1 : 0, kBlockM, C::block_n);
+      // K-major : rows of 128 B, 8-row atoms 1024 B apart (SBO); LBO unused (1)
+      // MN-major: 128 B of MN contiguous, k-rows 128 B apart, 8-row atoms 1024 B apart (SBO),
+      //           next MN chunk bk*128 B away (LBO)
+      constexpr uint32_t lbo_a = C::a_mn ? C::bk * kRowBytes : 16;
+      constexpr uint32_t lbo_b = C::b_mn ? C::bk * kRowBytes : 16;
+      constexpr uint32_t kadv_a = C::a_mn ? C::umma_k * kRowBytes : 32;   // bytes per k-step
+      constexpr uint32_t kadv_b = C::b_mn ? C::umma_k * kRowBytes : 32;
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+        const int split = u / tiles_mn;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + uint32_t(acc * C::block_n);
+        uint32_t accumulate = 0;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * C::stage_bytes);
+          const uint32_t sb = sa + C::parts * C::a_bytes;
+#pragma unroll
+          for (int k = 0; k < C::ksteps; ++k) {
+            const uint64_t a_hi = make_sw128_desc(sa + k * kadv_a, lbo_a, 1024);
+            const uint64_t b_hi = make_sw128_desc(sb + k * kadv_b, lbo_b, 1024);
+            if (C::nprod == 3) {
+              const uint64_t a_lo = make_sw128_desc(sa + C::a_bytes + k * kadv_a, lbo_a, 1024);
+              const uint64_t b_lo = make_sw128_desc(sb + C::b_bytes + k * kadv_b, lbo_b, 1024);
+              umma_ss<C::tf32>(d_tmem, a_lo, b_hi, idesc, accumulate);
+              umma_ss<C::tf32>(d_tmem, a_hi, b_lo, idesc, 1u);
+              umma_ss<C::tf32>(d_tmem, a_hi, b_hi, idesc, 1u);
+            } else {
+              umma_ss<C::tf32>(d_tmem, a_hi, b_hi, idesc, accumulate);
+            }
+            accumulate = 1u;
+          }
+          umma_commit(&empty_bar[stage]);            // frees the smem stage when these MMAs retire
+          if (kb == kb1 - 1) umma_commit(&tmem_full[acc]);
+          if (++stage == C::stages) { stage = 0; phase ^= 1u; }
+        }
+        acc ^= 1; if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;                          // TMEM lane quarter this warp may touch
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+      const int split = u / tiles_mn;
+      const int t = u - split * tiles_mn;
+      const int m0 = (t / p.tiles_n) * kBlockM;
+      const int n0 = (t % p.tiles_n) * C::block_n;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const int row = m0 + q * 32 + lane;
+      const bool row_ok = row < p.d_rows;
+      float* drow = p.D + (long long)split * p.slab_stride + (long long)row * p.ldd;
+      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * C::block_n);
+#pragma unroll 1
+      for (int c = 0; c < C::block_n / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + c * 32, r);
+        tmem_ld_wait();
+        const int col0 = n0 + c * 32;
+        if (row_ok) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int col = col0 + j * 4;
+            if (col < p.d_cols) {
+              float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                     __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+              if (C::fwd_epi) {
+                float4 z;
+                epilogue_act4(p.epi, p.act_N, row, col, v, z);
+                if (p.epi.Z) *reinterpret_cast<float4*>(p.epi.Z + (long long)row * p.act_N + col) = z;
+              } else {
+                const float s = p.epi.out_scale;
+                v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+              }
+              *reinterpret_cast<float4*>(drow + col) = v;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      acc ^= 1; if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, C::tmem_cols); }
+#endif
+}
+
+// ----------------------------------------------------------------------------
+// host side: tensor maps + dispatch
+// ----------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess || !p) {
+    set_error("cuTensorMapEncodeTiled not available from the driver");
+    return nullptr;
+  }
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+// 2D row-major tensor [outer rows, inner contiguous elems]; box = [box_outer rows, 128 B of inner].
+int make_tmap(CUtensorMap* tm, const void* base, CUtensorMapDataType dt, int elem_bytes, uint64_t inner,
+              uint64_t outer, uint32_t box_outer) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return VV_ERR_CUDA;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || ((inner * elem_bytes) & 15) != 0) {
+    set_error("GEMM operand must be 16-byte aligned with a row pitch that is a multiple of 16 bytes");
+    return VV_ERR_INVALID;
+  }
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {inner * elem_bytes};
+  cuuint32_t box[2] = {uint32_t(kRowBytes / elem_bytes), box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (CUresult %d)", int(r)); return VV_ERR_CUDA; }
+  return VV_OK;
+}
+
+template <class C>
+int launch_cfg(const GemmProblem& g, cudaStream_t stream) {
+  // output extent, reduction length, operand shapes per kind
+  int d_rows, d_cols, red;
+  uint64_t a_inner, a_outer, b_inner, b_outer;
+  switch (g.kind) {
+    case GEMM_FWD:   d_rows = g.M; d_cols = g.N; red = g.K; a_inner = g.K; a_outer = g.M; b_inner = g.K; b_outer = g.N; break;
+    case GEMM_WGRAD: d_rows = g.N; d_cols = g.K; red = g.M; a_inner = g.N; a_outer = g.M; b_inner = g.K; b_outer = g.M; break;
+    default:         d_rows = g.M; d_cols = g.K; red = g.N; a_inner = g.N; a_outer = g.M; b_inner = g.K; b_outer = g.N; break;
+  }
+  const CUtensorMapDataType dt = C::tf32 ? (C::nprod == 3 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32)
+                                         : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUtensorMap tA_hi, tA_lo, tB_hi, tB_lo;
+  const uint32_t a_box = C::a_mn ? C::bk : kBlockM;
+  const uint32_t b_box = C::b_mn ? C::bk : C::block_n;
+  int rc;
+  if ((rc = make_tmap(&tA_hi, g.A.hi, dt, C::elem_bytes, a_inner, a_outer, a_box))) return rc;
+  if ((rc = make_tmap(&tB_hi, g.B.hi, dt, C::elem_bytes, b_inner, b_outer, b_box))) return rc;
+  if (C::parts == 2) {
+    if (!g.A.lo || !g.B.lo) { set_error("TF32X3 needs hi and lo operand arrays"); return VV_ERR_INVALID; }
+    if ((rc = make_tmap(&tA_lo, g.A.lo, dt, C::elem_bytes, a_inner, a_outer, a_box))) return rc;
+    if ((rc = make_tmap(&tB_lo, g.B.lo, dt, C::elem_bytes, b_inner, b_outer, b_box))) return rc;
+  } else {
+    tA_lo = tA_hi; tB_lo = tB_hi;
+  }
+  TcParams p;
+  p.d_rows = d_rows; p.d_cols = d_cols; p.ldd = d_cols;
+  p.tiles_m = (d_rows + kBlockM - 1) / kBlockM;
+  p.tiles_n = (d_cols + C::block_n - 1) / C::block_n;
+  p.num_kb = (red + C::bk - 1) / C::bk;
+  const int nsplit = g.nsplit < 1 ? 1 : g.nsplit;
+  p.kb_per_split = (p.num_kb + nsplit - 1) / nsplit;
+  // every slab must receive at least one k-block, else it would stay unwritten
+  if (nsplit > p.num_kb || (nsplit - 1) * p.kb_per_split >= p.num_kb) {
+    set_error("nsplit=%d leaves an empty split for %d k-blocks", nsplit, p.num_kb);
+    return VV_ERR_INVALID;
+  }
+  p.nsplit = nsplit;
+  p.D = g.D; p.slab_stride = g.slab_stride;
+  p.act_N = g.N;
+  p.epi = g.epi;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VV_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::smem_bytes));
+    attr_set = true;
+  }
+  const int total = p.tiles_m * p.tiles_n * p.nsplit;
+  const int grid = total < num_sms() ? total : num_sms();
+  gemm_tc_kernel<C><<<grid, kNumThreads, C::smem_bytes, stream>>>(tA_hi, tA_lo, tB_hi, tB_lo, p);
+  VV_LAUNCH_CHECK();
+  count_launch();
+  return VV_OK;
+}
+
+}  // namespace
+
+bool gemm_tc_supported(const GemmProblem& g, const char** why) {
+  static const char* w_prec = "precision is not a tensor-core mode";
+  static const char* w_align = "tensor-core path needs N % 8 == 0 and K % 8 == 0";
+  if (g.prec != VV_PREC_TF32X3 && g.prec != VV_PREC_TF32 && g.prec != VV_PREC_BF16) { if (why) *why = w_prec; return false; }
+  if ((g.N % 8) != 0 || (g.K % 8) != 0) { if (why) *why = w_align; return false; }
+  return true;
+}
+
+int gemm_tc_launch(const GemmProblem& g, cudaStream_t stream) {
+  const char* why = nullptr;
+  if (!gemm_tc_supported(g, &why)) { set_error("%s (M=%d N=%d K=%d)", why, g.M, g.N, g.K); return VV_ERR_UNSUPPORTED; }
+  //                 tf32   A-MN   B-MN  nprod  BN  stages fwd-epilogue
+  if (g.prec == VV_PREC_BF16) {
+    switch (g.kind) {
+      case GEMM_FWD:   return launch_cfg<Cfg<false, false, false, 1, 256, 4, true >>(g, stream);
+      case GEMM_WGRAD: return launch_cfg<Cfg<false, true,  true,  1, 256, 4, false>>(g, stream);
+      default:         return launch_cfg<Cfg<false, false, true,  1, 256, 4, false>>(g, stream);
+    }
+  } else if (g.prec == VV_PREC_TF32) {
+    switch (g.kind) {
+      case GEMM_FWD:   return launch_cfg<Cfg<true, false, false, 1, 256, 4, true >>(g, stream);
+      case GEMM_WGRAD: return launch_cfg<Cfg<true, true,  true,  1, 256, 4, false>>(g, stream);
+      default:         return launch_cfg<Cfg<true, false, true,  1, 256, 4, false>>(g, stream);
+    }
+  } else {
+    switch (g.kind) {
+      case GEMM_FWD:   return launch_cfg<Cfg<true, false, false, 3, 256, 2, true >>(g, stream);
+      case GEMM_WGRAD: return launch_cfg<Cfg<true, true,  true,  3, 256, 2, false>>(g, stream);
+      default:         return launch_cfg<Cfg<true, false, true,  3, 256, 2, false>>(g, stream);
+    }
+  }
+}
+
+}  // namespace vv

@@ -1,0 +1,404 @@
+// vv_rank_loss.cu -- K2 / K3: everything between ip2 and the loss, fused.
+//
+// Forward (one pass over the R rows of an item, HBM-bound, R*N*4 bytes/item):
+//   slice_emb -> context_average (ELTWISE SUM, coeff) -> word_embedding_norm ->
+//   concat/pos_neg_normalize/slice -> prod_* + sum_* (1+Nn dot products) ->
+//   concat_negative_scores -> max_margin_loss
+// Backward (read R rows, write R rows: 2*R*N*4 bytes/item): the reverse graph down to
+//   ip1_nonorm.diff including the Split sum, both Normalization backwards, the
+//   Eltwise SUM scale, Dropout and ReLU backward.
+// ref: eltwise_layer.cpp:61-73,119-143; normalization_layer.cpp:30-112;
+//      sum_layer.cpp:32-82; split_layer.cpp:36-51; max_margin_loss_layer.cpp:54-214;
+//      dropout_layer.cpp:52-68; relu_layer.cpp:23-36 (math summarised in SURVEY 8a).
+//
+// Per item the forward saves only scalars: s_c = |cbar|^2 and, for the target and every
+// negative row x, s_x = |x|^2 and p_x = <cbar, x>.  Every reduction the reference's
+// backward performs (a = <x, dy> in Normalization, the row sums in Sum) is a linear
+// combination of these, so the backward needs no reduction at all and streams.
+//
+// Thread mapping: one CTA per item (grid-stride), thread t owns float4 column
+// groups t, t+T, ... ; all rows of the item are read with 128-bit loads.
+#include "vv_common.cuh"
+
+namespace vv {
+namespace {
+
+constexpr int kMaxVec = 4;        // float4 groups per thread: N <= 4 * 256 * kMaxVec = 4096
+constexpr int kRowBatch = 4;      // rows loaded before reducing (memory-level parallelism)
+
+struct RankDev {
+  int B, C, Nn, N, N4, nvec, stride;
+  float margin, eps; int norm;
+  float coeff[VV_MAX_CONTEXT];
+};
+
+__device__ __forceinline__ float4 ld4(const float* p) { return ldg_stream(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float dot4(const float4& a, const float4& b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+
+// c-bar = sum_i coeff_i * ctx_i  (zeroed output, then axpy in bottom order: eltwise_layer.cpp:67-73)
+template <int NVEC>
+__device__ __forceinline__ void context_mean(const float* H, const RankDev& p, int b, int tid, int T, float4 (&cbar)[NVEC]) {
+#pragma unroll
+  for (int v = 0; v < NVEC; ++v) cbar[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i0 = 1; i0 < p.C; i0 += kRowBatch) {
+    float4 x[kRowBatch][NVEC];
+#pragma unroll
+    for (int r = 0; r < kRowBatch; ++r)
+#pragma unroll
+      for (int v = 0; v < NVEC; ++v) {
+        const int c4 = v * T + tid;
+        if (i0 + r < p.C && c4 < p.N4)
+          x[r][v] = ld4(H + (size_t(i0 + r) * p.B + b) * p.N + c4 * 4);
+        else
+          x[r][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+    for (int r = 0; r < kRowBatch; ++r) {
+      if (i0 + r < p.C) {
+        const float a = p.coeff[i0 + r - 1];
+#pragma unroll
+        for (int v = 0; v < NVEC; ++v) {
+          cbar[v].x = fmaf(a, x[r][v].x, cbar[v].x); cbar[v].y = fmaf(a, x[r][v].y, cbar[v].y);
+          cbar[v].z = fmaf(a, x[r][v].z, cbar[v].z); cbar[v].w = fmaf(a, x[r][v].w, cbar[v].w);
+        }
+      }
+    }
+  }
+}
+
+template <int NVEC>
+__global__ void __launch_bounds__(256)
+rank_fwd_kernel(const float* __restrict__ H, const RankDev p, float* __restrict__ stats,
+                float* __restrict__ tscore, float* __restrict__ nscore,
+                float* __restrict__ item_loss, float* __restrict__ item_viol) {
+  extern __shared__ float sm[];
+  const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = T >> 5;
+  const int J = 1 + p.Nn;                 // target + negatives
+  float* part = sm;                       // [J][2][nw]
+  float* part_c = part + J * 2 * nw;      // [nw]
+  float* fin = part_c + nw;               // [J][2] then s_c at fin[2J]
+  for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
+    float4 cbar[NVEC];
+    context_mean<NVEC>(H, p, b, tid, T, cbar);
+    float sc = 0.f;
+#pragma unroll
+    for (int v = 0; v < NVEC; ++v) sc += dot4(cbar[v], cbar[v]);
+    sc = warp_sum(sc);
+    if (lane == 0) part_c[warp] = sc;
+    for (int j0 = 0; j0 < J; j0 += kRowBatch) {
+      float4 x[kRowBatch][NVEC];
+#pragma unroll
+      for (int r = 0; r < kRowBatch; ++r) {
+        const int j = j0 + r;
+        const int row = (j == 0) ? 0 : p.C + j - 1;
+#pragma unroll
+        for (int v = 0; v < NVEC; ++v) {
+          const int c4 = v * T + tid;
+          if (j < J && c4 < p.N4)
+            x[r][v] = ld4(H + (size_t(row) * p.B + b) * p.N + c4 * 4);
+          else
+            x[r][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < kRowBatch; ++r) {
+        const int j = j0 + r;
+        if (j < J) {
+          float sx = 0.f, px = 0.f;
+#pragma unroll
+          for (int v = 0; v < NVEC; ++v) { sx += dot4(x[r][v], x[r][v]); px += dot4(cbar[v], x[r][v]); }
+          sx = warp_sum(sx); px = warp_sum(px);
+          if (lane == 0) { part[(j * 2 + 0) * nw + warp] = sx; part[(j * 2 + 1) * nw + warp] = px; }
+        }
+      }
+    }
+    __syncthreads();
+    for (int e = tid; e < 2 * J + 1; e += T) {
+      float s = 0.f;
+      if (e < 2 * J) { for (int w = 0; w < nw; ++w) s += part[e * nw + w]; }
+      else           { for (int w = 0; w < nw; ++w) s += part_c[w]; }
+      fin[e] = s;
+      // stats layout: [s_c, s_t, p_t, s_n1, p_n1, ...]
+      stats[size_t(b) * p.stride + (e < 2 * J ? 1 + e : 0)] = s;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      // normalisation_layer.cpp:36-59: r = pow(s, .5) + eps ; y = x / r.  scores = <c^, x^>
+      const float nc = sqrtf(fin[2 * J]) + p.eps;
+      const float st = fin[1] / (nc * (sqrtf(fin[0]) + p.eps));
+      float loss = 0.f, viol = 0.f;
+      for (int k = 1; k <= p.Nn; ++k) {
+        const float sn = fin[2 * k + 1] / (nc * (sqrtf(fin[2 * k]) + p.eps));
+        const float delta = st - sn;                       // caffe_sub :69
+        if (delta < 0.f) viol += 1.f;
+        const float h = fmaxf(0.f, p.margin - delta);
+        loss += (p.norm == 2) ? h * h : fabsf(h);
+        if (tscore) tscore[size_t(b) * p.Nn + k - 1] = st;  // sum_true replicates to Nn columns
+        if (nscore) nscore[size_t(b) * p.Nn + k - 1] = sn;
+      }
+      if (item_loss) item_loss[b] = loss;
+      if (item_viol) item_viol[b] = viol;
+    }
+    __syncthreads();
+  }
+}
+
+// loss = sum_b item_loss[b] / (B*Nn) ; violations = sum_b item_viol[b].  Deterministic.
+__global__ void __launch_bounds__(1024)
+rank_loss_reduce_kernel(const float* __restrict__ item_loss, const float* __restrict__ item_viol, int B,
+                        float inv_count, float* __restrict__ loss, float* __restrict__ viol) {
+  __shared__ float s1[32], s2[32];
+  float a = 0.f, c = 0.f;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) { a += item_loss[i]; c += item_viol[i]; }
+  a = warp_sum(a); c = warp_sum(c);
+  if ((threadIdx.x & 31) == 0) { s1[threadIdx.x >> 5] = a; s2[threadIdx.x >> 5] = c; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    a = (threadIdx.x < (blockDim.x >> 5)) ? s1[threadIdx.x] : 0.f;
+    c = (threadIdx.x < (blockDim.x >> 5)) ? s2[threadIdx.x] : 0.f;
+    a = warp_sum(a); c = warp_sum(c);
+    if (threadIdx.x == 0) { if (loss) *loss = a * inv_count; if (viol) *viol = c; }
+  }
+}
+
+struct BwdOut {
+  float* dZ; float* hi; float* lo; uint16_t* bf; int prec;
+};
+
+__device__ __forceinline__ void store_row4(const BwdOut& o, size_t off, const float4& v) {
+  if (o.dZ) stg_stream(reinterpret_cast<float4*>(o.dZ + off), v);
+  if (o.prec == VV_PREC_TF32X3) {
+    float4 h, l;
+    split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+    stg_stream(reinterpret_cast<float4*>(o.hi + off), h);
+    stg_stream(reinterpret_cast<float4*>(o.lo + off), l);
+  } else if (o.prec == VV_PREC_BF16) {
+    uint2 pk = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    *reinterpret_cast<uint2*>(o.bf + off) = pk;
+  }
+}
+
+template <int NVEC>
+__global__ void __launch_bounds__(256)
+rank_bwd_kernel(const float* __restrict__ H, const RankDev p, const float* __restrict__ stats,
+                const float gscale /* lw*2/(B*Nn) for L2, lw/(B*Nn) for L1 */,
+                const int act_fused, const float dscale, const BwdOut out, float* __restrict__ db_accum) {
+  extern __shared__ float sm[];
+  const int T = blockDim.x, tid = threadIdx.x;
+  const int J = 1 + p.Nn;
+  float* s_s = sm;            // [J] |x|^2
+  float* s_p = s_s + J;       // [J] <cbar,x>
+  float* s_w = s_p + J;       // [J] weight of branch j on c^ : w_0 = -sum g, w_k = g_k
+  float* cA = s_w + J;        // [J] coefficient on cbar
+  float* cB = cA + J;         // [J] coefficient on x
+  float* cE = cB + J;         // [J] w_j / n_j   (d c^ = sum_j cE_j x_j)
+  float* sc = cE + J;         // [4] s_c, nc, Fs, Fc
+  float4 dbacc[NVEC];
+#pragma unroll
+  for (int v = 0; v < NVEC; ++v) dbacc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
+    const float* st = stats + size_t(b) * p.stride;
+    // ---- per-item scalar prologue (parallel over the J branches)
+    for (int j = tid; j < J; j += T) { s_s[j] = st[1 + 2 * j]; s_p[j] = st[2 + 2 * j]; }
+    if (tid == 0) { const float s = st[0]; sc[0] = s; sc[1] = sqrtf(s) + p.eps; }
+    __syncthreads();
+    const float nc = sc[1];
+    const float score_t = s_p[0] / (nc * (sqrtf(s_s[0]) + p.eps));
+    for (int k = 1 + tid; k < J; k += T) {
+      const float sn = s_p[k] / (nc * (sqrtf(s_s[k]) + p.eps));
+      const float h = fmaxf(0.f, p.margin - (score_t - sn));
+      // max_margin_loss_layer.cpp:149-192: L2 g = h * (lw*2/count); L1 g = [h>0] * lw/count
+      s_w[k] = (p.norm == 2) ? h * gscale : (h > 0.f ? gscale : 0.f);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      float g = 0.f;                       // sum_layer.cpp:65-68 gemv over the Nn replicated columns;
+      for (int k = 1; k < J; ++k) g += s_w[k];
+      s_w[0] = -g;                         // d s+ = -1 * d s- (axpby, :210-212)
+    }
+    __syncthreads();
+    for (int j = tid; j < J; j += T) {
+      const float s = s_s[j], pj = s_p[j], w = s_w[j];
+      const float nj = sqrtf(s) + p.eps;
+      const float q = powf(s, 1.5f) + p.eps;         // normalization_layer.cpp:101-107
+      const float aj = w * pj / nc;                  // a = <x, w c^>
+      cA[j] = s * w / (nc * q);                      // (s * w c^) / q, c^ = cbar / nc
+      cB[j] = -aj / q;
+      cE[j] = w / nj;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      float ac = 0.f;                                // a_c = <cbar, d c^> = sum_j cE_j p_j (split order: true, neg_1..)
+      for (int j = 0; j < J; ++j) ac += cE[j] * s_p[j];
+      const float s = sc[0];
+      const float q = powf(s, 1.5f) + p.eps;
+      sc[2] = s / q; sc[3] = -ac / q;
+    }
+    // ---- context mean (needed for every output row)
+    float4 cbar[NVEC], D[NVEC];
+    context_mean<NVEC>(H, p, b, tid, T, cbar);
+#pragma unroll
+    for (int v = 0; v < NVEC; ++v) D[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // ---- target + negative rows: dx = cA*cbar + cB*x ; D += cE*x
+    for (int j0 = 0; j0 < J; j0 += kRowBatch) {
+      float4 x[kRowBatch][NVEC];
+#pragma unroll
+      for (int r = 0; r < kRowBatch; ++r) {
+        const int j = j0 + r;
+        const int row = (j == 0) ? 0 : p.C + j - 1;
+#pragma unroll
+        for (int v = 0; v < NVEC; ++v) {
+          const int c4 = v * T + tid;
+          if (j < J && c4 < p.N4) x[r][v] = ld4(H + (size_t(row) * p.B + b) * p.N + c4 * 4);
+          else x[r][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < kRowBatch; ++r) {
+        const int j = j0 + r;
+        if (j < J) {
+          const int row = (j == 0) ? 0 : p.C + j - 1;
+          const float a = cA[j], bb = cB[j], e = cE[j];
+#pragma unroll
+          for (int v = 0; v < NVEC; ++v) {
+            const int c4 = v * T + tid;
+            if (c4 < p.N4) {
+              const float4 xv = x[r][v];
+              float4 o;
+              o.x = fmaf(a, cbar[v].x, bb * xv.x); o.y = fmaf(a, cbar[v].y, bb * xv.y);
+              o.z = fmaf(a, cbar[v].z, bb * xv.z); o.w = fmaf(a, cbar[v].w, bb * xv.w);
+              D[v].x = fmaf(e, xv.x, D[v].x); D[v].y = fmaf(e, xv.y, D[v].y);
+              D[v].z = fmaf(e, xv.z, D[v].z); D[v].w = fmaf(e, xv.w, D[v].w);
+              if (act_fused) {   // dZ = dH * mask*scale * [Z>0]  <=>  dH * scale * [H>0]
+                o.x = xv.x > 0.f ? o.x * dscale : 0.f; o.y = xv.y > 0.f ? o.y * dscale : 0.f;
+                o.z = xv.z > 0.f ? o.z * dscale : 0.f; o.w = xv.w > 0.f ? o.w * dscale : 0.f;
+              }
+              dbacc[v].x += o.x; dbacc[v].y += o.y; dbacc[v].z += o.z; dbacc[v].w += o.w;
+              store_row4(out, (size_t(row) * p.B + b) * p.N + c4 * 4, o);
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();   // sc[2], sc[3] visible
+    // ---- context rows: d cbar = (s_c * d c^ - cbar * a_c) / q_c ; d c_i = coeff_i * d cbar
+    const float Fs = sc[2], Fc = sc[3];
+    float4 dcb[NVEC];
+#pragma unroll
+    for (int v = 0; v < NVEC; ++v) {
+      dcb[v].x = fmaf(Fs, D[v].x, Fc * cbar[v].x); dcb[v].y = fmaf(Fs, D[v].y, Fc * cbar[v].y);
+      dcb[v].z = fmaf(Fs, D[v].z, Fc * cbar[v].z); dcb[v].w = fmaf(Fs, D[v].w, Fc * cbar[v].w);
+    }
+    for (int i = 1; i < p.C; ++i) {
+      const float a = p.coeff[i - 1];
+#pragma unroll
+      for (int v = 0; v < NVEC; ++v) {
+        const int c4 = v * T + tid;
+        if (c4 < p.N4) {
+          const size_t off = (size_t(i) * p.B + b) * p.N + c4 * 4;
+          float4 o = make_float4(a * dcb[v].x, a * dcb[v].y, a * dcb[v].z, a * dcb[v].w);
+          if (act_fused) {
+            const float4 xv = ld4(H + off);     // re-read (L2 hit): the ReLU/dropout gate of this row
+            o.x = xv.x > 0.f ? o.x * dscale : 0.f; o.y = xv.y > 0.f ? o.y * dscale : 0.f;
+            o.z = xv.z > 0.f ? o.z * dscale : 0.f; o.w = xv.w > 0.f ? o.w * dscale : 0.f;
+          }
+          dbacc[v].x += o.x; dbacc[v].y += o.y; dbacc[v].z += o.z; dbacc[v].w += o.w;
+          store_row4(out, off, o);
+        }
+      }
+    }
+    __syncthreads();   // smem coefficients are rewritten by the next item
+  }
+  if (db_accum) {
+#pragma unroll
+    for (int v = 0; v < NVEC; ++v) {
+      const int c4 = v * T + tid;
+      if (c4 < p.N4) {
+        atomicAdd(db_accum + c4 * 4 + 0, dbacc[v].x); atomicAdd(db_accum + c4 * 4 + 1, dbacc[v].y);
+        atomicAdd(db_accum + c4 * 4 + 2, dbacc[v].z); atomicAdd(db_accum + c4 * 4 + 3, dbacc[v].w);
+      }
+    }
+  }
+}
+
+int make_dev(const vv_rank_cfg_t* cfg, RankDev* d, int* threads) {
+  VV_REQUIRE(cfg, "rank cfg is NULL");
+  VV_REQUIRE(cfg->B > 0 && cfg->C >= 2 && cfg->Nn >= 1 && cfg->N > 0, "bad rank cfg B=%d C=%d Nn=%d N=%d", cfg->B, cfg->C, cfg->Nn, cfg->N);
+  VV_REQUIRE(cfg->C - 1 <= VV_MAX_CONTEXT, "context_size-1 = %d exceeds VV_MAX_CONTEXT", cfg->C - 1);
+  VV_REQUIRE(cfg->N % 4 == 0, "embedding dim N=%d must be a multiple of 4", cfg->N);
+  VV_REQUIRE(cfg->N <= 4 * 256 * kMaxVec, "embedding dim N=%d exceeds %d", cfg->N, 4 * 256 * kMaxVec);
+  VV_REQUIRE(cfg->norm == 1 || cfg->norm == 2, "norm must be 1 (L1) or 2 (L2)");
+  d->B = cfg->B; d->C = cfg->C; d->Nn = cfg->Nn; d->N = cfg->N; d->N4 = cfg->N / 4;
+  int T = ((d->N4 + 31) / 32) * 32;
+  if (T > 256) T = 256;
+  d->nvec = (d->N4 + T - 1) / T;
+  d->stride = vv_rank_stats_stride(cfg->Nn);
+  d->margin = cfg->margin; d->eps = cfg->eps; d->norm = cfg->norm;
+  for (int i = 0; i < VV_MAX_CONTEXT; ++i) d->coeff[i] = cfg->coeff[i];
+  *threads = T;
+  return VV_OK;
+}
+
+}  // namespace
+}  // namespace vv
+
+using namespace vv;
+
+extern "C" int vv_rank_loss_forward(const float* H, const vv_rank_cfg_t* cfg, float* stats,
+                                    float* target_score, float* neg_score,
+                                    float* item_loss, float* item_viol,
+                                    float* loss, float* violations, vv_stream_t stream) {
+  RankDev d; int T;
+  int rc = make_dev(cfg, &d, &T);
+  if (rc) return rc;
+  VV_REQUIRE(H && stats, "H and stats must be non-NULL");
+  VV_REQUIRE(!(loss || violations) || (item_loss && item_viol), "loss/violations need item_loss and item_viol scratch [B]");
+  const int J = 1 + d.Nn, nw = T / 32;
+  const size_t smem = sizeof(float) * (J * 2 * nw + nw + 2 * J + 1);
+  const int grid = d.B < num_sms() * 8 ? d.B : num_sms() * 8;
+  switch (d.nvec) {
+    case 1: rank_fwd_kernel<1><<<grid, T, smem, stream>>>(H, d, stats, target_score, neg_score, item_loss, item_viol); break;
+    case 2: rank_fwd_kernel<2><<<grid, T, smem, stream>>>(H, d, stats, target_score, neg_score, item_loss, item_viol); break;
+    default: rank_fwd_kernel<4><<<grid, T, smem, stream>>>(H, d, stats, target_score, neg_score, item_loss, item_viol); break;
+  }
+  VV_LAUNCH_CHECK();
+  count_launch();
+  if (loss || violations) {
+    rank_loss_reduce_kernel<<<1, 1024, 0, stream>>>(item_loss, item_viol, d.B, 1.f / float(d.B * d.Nn), loss, violations);
+    VV_LAUNCH_CHECK();
+    count_launch();
+  }
+  return VV_OK;
+}
+
+extern "C" int vv_rank_loss_backward(const float* H, const vv_rank_cfg_t* cfg, const float* stats,
+                                     float loss_weight, int act_fused, float dropout_scale,
+                                     float* dZ, void* dZop_hi, void* dZop_lo, int prec,
+                                     float* db_accum, vv_stream_t stream) {
+  RankDev d; int T;
+  int rc = make_dev(cfg, &d, &T);
+  if (rc) return rc;
+  VV_REQUIRE(H && stats, "H and stats must be non-NULL");
+  BwdOut o; o.dZ = dZ; o.hi = nullptr; o.lo = nullptr; o.bf = nullptr; o.prec = VV_PREC_FP32_SIMT;
+  if (prec == VV_PREC_TF32X3 && dZop_hi) {
+    VV_REQUIRE(dZop_lo, "TF32X3 operand copy needs hi and lo");
+    o.hi = static_cast<float*>(dZop_hi); o.lo = static_cast<float*>(dZop_lo); o.prec = prec;
+  } else if (prec == VV_PREC_BF16 && dZop_hi) {
+    o.bf = static_cast<uint16_t*>(dZop_hi); o.prec = prec;
+  }
+  VV_REQUIRE(o.dZ || o.prec != VV_PREC_FP32_SIMT, "no output requested");
+  const int count = d.B * d.Nn;
+  const float gscale = (d.norm == 2) ? loss_weight * 2 / count : loss_weight / count;
+  const int J = 1 + d.Nn;
+  const size_t smem = sizeof(float) * (6 * J + 4);
+  const int grid = d.B < num_sms() * 8 ? d.B : num_sms() * 8;
+  switch (d.nvec) {
+    case 1: rank_bwd_kernel<1><<<grid, T, smem, stream>>>(H, d, stats, gscale, act_fused, dropout_scale, o, db_accum); break;
+    case 2: rank_bwd_kernel<2><<<grid, T, smem, stream>>>(H, d, stats, gscale, act_fused, dropout_scale, o, db_accum); break;
+    default: rank_bwd_kernel<4><<<grid, T, smem, stream>>>(H, d, stats, gscale, act_fused, dropout_scale, o, db_accum); break;
+  }
+  VV_LAUNCH_CHECK();
+  count_launch();
+  return VV_OK;
+}

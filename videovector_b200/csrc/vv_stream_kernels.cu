@@ -1,0 +1,468 @@
+// vv_stream_kernels.cu -- the HBM-bound streaming kernels around the GEMMs:
+//   K0 index gather (data layer + slice/concat/flatten), operand preparation,
+//   K4 fused SGD/momentum update, split-K slab reduction, bias gradient,
+//   synthetic feature bank, and the standalone single-layer kernels that give the
+//   drop-in Layer classes exact per-layer semantics when a net is not fused.
+// All are 128-bit vectorised, grid-stride, sized in multiples of the SM count.
+#include "vv_common.cuh"
+#include <string.h>
+
+namespace vv {
+namespace {
+
+inline int stream_grid(long long work_items, int threads) {
+  long long blocks = (work_items + threads - 1) / threads;
+  const long long cap = (long long)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return int(blocks);
+}
+
+// ----------------------------------------------------------------------------
+// K0 gather.  One CTA per output row (grid-stride).  Output row j*B+b <- bank[idx[b*R+j]].
+// quirk: element K-1 replaced (ref: video_sampled_shots_data_layer.cpp:492 copies K-1 floats)
+// ----------------------------------------------------------------------------
+struct GatherOut { float* X; float* hi; float* lo; uint16_t* bf; float* blob; int prec; };
+
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const float* __restrict__ bank, const int* __restrict__ idx, const int* __restrict__ quirk,
+                   int B, int R, int K, const GatherOut o) {
+  const int K4 = K >> 2;
+  const long long M = (long long)B * R;
+  for (long long orow = blockIdx.x; orow < M; orow += gridDim.x) {
+    const int j = int(orow / B), b = int(orow - (long long)j * B);
+    const int slot = b * R + j;
+    const long long src = idx[slot];
+    const int qk = quirk ? quirk[slot] : -2;
+    const float4* s4 = reinterpret_cast<const float4*>(bank + src * K);
+    for (int c = threadIdx.x; c < K4; c += blockDim.x) {
+      float4 v = ldg_stream(s4 + c);
+      if (c == K4 - 1 && qk != -2) v.w = (qk >= 0) ? bank[(long long)qk * K + (K - 1)] : 0.f;
+      const size_t off = size_t(orow) * K + size_t(c) * 4;
+      if (o.X) stg_stream(reinterpret_cast<float4*>(o.X + off), v);
+      if (o.blob) stg_stream(reinterpret_cast<float4*>(o.blob + (size_t(slot) * K + size_t(c) * 4)), v);
+      if (o.prec == VV_PREC_TF32X3) {
+        float4 h, l;
+        split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+        stg_stream(reinterpret_cast<float4*>(o.hi + off), h);
+        stg_stream(reinterpret_cast<float4*>(o.lo + off), l);
+      } else if (o.prec == VV_PREC_BF16) {
+        *reinterpret_cast<uint2*>(o.bf + off) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+      }
+    }
+  }
+}
+
+// fp32 -> operand copies
+__global__ void __launch_bounds__(256)
+prepare_operand_kernel(const float* __restrict__ src, long long n4, int prec, float* hi, float* lo, uint16_t* bf) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = ldg_stream(reinterpret_cast<const float4*>(src) + i);
+    if (prec == VV_PREC_TF32X3) {
+      float4 h, l;
+      split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+      reinterpret_cast<float4*>(hi)[i] = h; reinterpret_cast<float4*>(lo)[i] = l;
+    } else {
+      reinterpret_cast<uint2*>(bf)[i] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------
+// K4 fused update (ref: solver.cpp:534-568, net.cpp:837, blob.cpp:126-128):
+//   g = scale * sum_s parts[s] ; g += decay * W (L2) | decay * sign(W) (L1)
+//   hist = momentum * hist (scal) ; hist += rate * g (axpy) ; diff = hist ; W -= diff
+// ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+sgd_update_kernel(float* W, const float* parts, int nparts, long long stride,
+                  float* hist, float* diff_out, long long n4, float rate, float momentum,
+                  float decay, int reg_type, float gscale, int prec, float* hi, float* lo, uint16_t* bf) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 g = reinterpret_cast<const float4*>(parts)[i];
+    for (int s = 1; s < nparts; ++s) {
+      const float4 t = reinterpret_cast<const float4*>(parts + s * stride)[i];
+      g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+    }
+    if (gscale != 1.f) { g.x *= gscale; g.y *= gscale; g.z *= gscale; g.w *= gscale; }
+    float4 w = reinterpret_cast<float4*>(W)[i];
+    if (decay != 0.f) {
+      if (reg_type == 2) {
+        g.x = fmaf(decay, w.x, g.x); g.y = fmaf(decay, w.y, g.y); g.z = fmaf(decay, w.z, g.z); g.w = fmaf(decay, w.w, g.w);
+      } else {
+        g.x += decay * float((0.f < w.x) - (w.x < 0.f)); g.y += decay * float((0.f < w.y) - (w.y < 0.f));
+        g.z += decay * float((0.f < w.z) - (w.z < 0.f)); g.w += decay * float((0.f < w.w) - (w.w < 0.f));
+      }
+    }
+    float4 h = reinterpret_cast<float4*>(hist)[i];
+    h.x = fmaf(rate, g.x, momentum * h.x); h.y = fmaf(rate, g.y, momentum * h.y);
+    h.z = fmaf(rate, g.z, momentum * h.z); h.w = fmaf(rate, g.w, momentum * h.w);
+    w.x -= h.x; w.y -= h.y; w.z -= h.z; w.w -= h.w;
+    reinterpret_cast<float4*>(hist)[i] = h;
+    reinterpret_cast<float4*>(W)[i] = w;
+    if (diff_out) reinterpret_cast<float4*>(diff_out)[i] = h;
+    if (prec == VV_PREC_TF32X3 && hi) {
+      float4 a, l;
+      split_tf32(w.x, a.x, l.x); split_tf32(w.y, a.y, l.y); split_tf32(w.z, a.z, l.z); split_tf32(w.w, a.w, l.w);
+      reinterpret_cast<float4*>(hi)[i] = a; reinterpret_cast<float4*>(lo)[i] = l;
+    } else if (prec == VV_PREC_BF16 && bf) {
+      reinterpret_cast<uint2*>(bf)[i] = make_uint2(pack_bf16x2(w.x, w.y), pack_bf16x2(w.z, w.w));
+    }
+  }
+}
+// scalar tail / unaligned version (bias blobs whose count is not a multiple of 4)
+__global__ void sgd_update_scalar_kernel(float* W, const float* parts, int nparts, long long stride, float* hist,
+                                         float* diff_out, long long n, float rate, float momentum, float decay,
+                                         int reg_type, float gscale) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float g = parts[i];
+    for (int s = 1; s < nparts; ++s) g += parts[s * stride + i];
+    if (gscale != 1.f) g *= gscale;
+    float w = W[i];
+    if (decay != 0.f) g = (reg_type == 2) ? fmaf(decay, w, g) : g + decay * float((0.f < w) - (w < 0.f));
+    const float h = fmaf(rate, g, momentum * hist[i]);
+    hist[i] = h; W[i] = w - h;
+    if (diff_out) diff_out[i] = h;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+reduce_parts_kernel(const float* parts, int nparts, long long stride, long long n, float* out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float g = parts[i];
+    for (int s = 1; s < nparts; ++s) g += parts[s * stride + i];
+    out[i] = g;
+  }
+}
+
+// db[n] = sum_m dZ[m, n]  (ref: inner_product_layer.cu:48-50, gemv with the ones vector)
+// grid.x covers column groups of 32, grid.y splits rows; partial sums combined with atomics on a zeroed db.
+__global__ void __launch_bounds__(256)
+bias_grad_kernel(const float* __restrict__ dZ, int M, int N, float* __restrict__ db) {
+  __shared__ float sm[8][33];
+  const int col = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int r0 = threadIdx.x >> 5;
+  float acc = 0.f;
+  if (col < N)
+    for (long long m = blockIdx.y * 8 + r0; m < M; m += (long long)gridDim.y * 8) acc += dZ[m * N + col];
+  sm[r0][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float s = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) s += sm[r][threadIdx.x];
+    if (col < N) atomicAdd(db + col, s);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+fill_bank_kernel(float* __restrict__ bank, long long n4, int K, unsigned long long seed) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const unsigned long long e = (unsigned long long)i * 4;
+    float4 v = make_float4(bank_value(seed, e), bank_value(seed, e + 1), bank_value(seed, e + 2), bank_value(seed, e + 3));
+    reinterpret_cast<float4*>(bank)[i] = v;
+  }
+}
+
+// ----------------------------------------------------------------------------
+// standalone layer kernels (scalar grid-stride; these are not on the fused path)
+// ----------------------------------------------------------------------------
+#define GS_LOOP(i, n) for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (n); i += (long long)gridDim.x * blockDim.x)
+
+__global__ void relu_fwd_kernel(const float* x, long long n, float s, float* y) {
+  GS_LOOP(i, n) { const float v = x[i]; y[i] = fmaxf(v, 0.f) + s * fminf(v, 0.f); }
+}
+__global__ void relu_bwd_kernel(const float* x, const float* dy, long long n, float s, float* dx) {
+  GS_LOOP(i, n) { dx[i] = dy[i] * ((x[i] > 0.f) + s * (x[i] <= 0.f)); }
+}
+__global__ void dropout_kernel(const float* x, const unsigned* mask, int mode, unsigned thres, long long n, float scale, float* y) {
+  GS_LOOP(i, n) {
+    const unsigned m = mask[i];
+    const unsigned keep = (mode == VV_DROPOUT_MASK_U32) ? (m > thres) : m;
+    y[i] = x[i] * float(keep) * scale;
+  }
+}
+// same stream as the fused fc7 epilogue: element (row, 4*col4 + j) = word j of dropout_words(seed, step, row, col4)
+__global__ void dropout_make_mask_kernel(unsigned* mask, int rows, int cols4, unsigned thres, unsigned long long seed, unsigned long long step) {
+  GS_LOOP(i, (long long)rows * cols4) {
+    const unsigned row = unsigned(i / cols4), c4 = unsigned(i - (long long)row * cols4);
+    unsigned w[4];
+    dropout_words(seed, step, row, c4, w);
+    reinterpret_cast<uint4*>(mask)[i] = make_uint4(w[0] > thres, w[1] > thres, w[2] > thres, w[3] > thres);
+  }
+}
+__global__ void axpby_kernel(long long n, float a, const float* x, float b, float* y) {
+  GS_LOOP(i, n) { y[i] = (b == 0.f) ? a * x[i] : fmaf(a, x[i], b * y[i]); }
+}
+__global__ void mul_kernel(long long n, const float* a, const float* b, float* y) { GS_LOOP(i, n) { y[i] = a[i] * b[i]; } }
+struct PtrPack { const float* p[VV_MAX_CONTEXT]; float c[VV_MAX_CONTEXT]; int nb; };
+__global__ void eltwise_sum_kernel(const PtrPack pk, long long n, float* top) {
+  GS_LOOP(i, n) {
+    float acc = 0.f;
+    for (int k = 0; k < pk.nb; ++k) acc = fmaf(pk.c[k], pk.p[k][i], acc);
+    top[i] = acc;
+  }
+}
+// one warp per row
+__global__ void l2norm_fwd_kernel(const float* x, int num, int dim, float* y) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int r = warp; r < num; r += nwarps) {
+    const float* xr = x + (size_t)r * dim;
+    float s = 0.f;
+    for (int c = lane; c < dim; c += 32) s = fmaf(xr[c], xr[c], s);
+    s = warp_sum(s);
+    const float d = sqrtf(s) + 1e-10f;           // pow(s,.5) + eps (normalization_layer.cpp:36-50)
+    for (int c = lane; c < dim; c += 32) y[(size_t)r * dim + c] = xr[c] / d;
+  }
+}
+__global__ void l2norm_bwd_kernel(const float* x, const float* dy, int num, int dim, float* dx) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int r = warp; r < num; r += nwarps) {
+    const float* xr = x + (size_t)r * dim; const float* dr = dy + (size_t)r * dim;
+    float a = 0.f, s = 0.f;
+    for (int c = lane; c < dim; c += 32) { a = fmaf(xr[c], dr[c], a); s = fmaf(xr[c], xr[c], s); }
+    a = warp_sum(a); s = warp_sum(s);
+    const float q = powf(s, 1.5f) + 1e-10f;      // normalization_layer.cpp:101-110
+    for (int c = lane; c < dim; c += 32) dx[(size_t)r * dim + c] = (s * dr[c] - xr[c] * a) / q;
+  }
+}
+__global__ void rowsum_fwd_kernel(const float* x, int num, int dim, int nout, float* y) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int r = warp; r < num; r += nwarps) {
+    float s = 0.f;
+    for (int c = lane; c < dim; c += 32) s += x[(size_t)r * dim + c];
+    s = warp_sum(s);
+    for (int o = lane; o < nout; o += 32) y[(size_t)r * nout + o] = s;
+  }
+}
+__global__ void rowsum_bwd_kernel(const float* dy, int num, int dim, int nout, float* dx) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int r = warp; r < num; r += nwarps) {
+    float t = 0.f;
+    for (int o = 0; o < nout; ++o) t += dy[(size_t)r * nout + o];   // gemv with ones (sum_layer.cpp:65-68)
+    for (int c = lane; c < dim; c += 32) dx[(size_t)r * dim + c] = t;
+  }
+}
+__global__ void copy_strided_kernel(const float* src, long long ss, float* dst, long long ds, long long rows, long long cols) {
+  GS_LOOP(i, rows * cols) { const long long r = i / cols, c = i - r * cols; dst[r * ds + c] = src[r * ss + c]; }
+}
+// single block: hinge terms, loss, violations (max_margin_loss_layer.cpp:54-127)
+__global__ void __launch_bounds__(1024)
+max_margin_fwd_kernel(const float* st, const float* sb, int count, float margin, int norm, float* hinge, float* loss, float* viol) {
+  __shared__ float s1[32], s2[32];
+  float a = 0.f, v = 0.f;
+  for (int i = threadIdx.x; i < count; i += blockDim.x) {
+    const float d = st[i] - sb[i];
+    if (d < 0.f) v += 1.f;
+    const float h = fmaxf(0.f, margin - d);
+    if (hinge) hinge[i] = h;
+    a += (norm == 2) ? h * h : fabsf(h);
+  }
+  a = warp_sum(a); v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) { s1[threadIdx.x >> 5] = a; s2[threadIdx.x >> 5] = v; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    a = s1[threadIdx.x]; v = s2[threadIdx.x];
+    a = warp_sum(a); v = warp_sum(v);
+    if (threadIdx.x == 0) { if (loss) *loss = a / count; if (viol) *viol = v; }
+  }
+}
+__global__ void max_margin_bwd_kernel(const float* st, const float* sb, int count, float margin, int norm, float gs, float* dt, float* dbg) {
+  GS_LOOP(i, count) {
+    const float h = fmaxf(0.f, margin - (st[i] - sb[i]));
+    const float g = (norm == 2) ? h * gs : (h > 0.f ? gs : 0.f);
+    if (dbg) dbg[i] = g;
+    if (dt) dt[i] = -1.f * g;
+  }
+}
+
+}  // namespace
+}  // namespace vv
+
+using namespace vv;
+
+#define VV_ALIGNED16(p) ((reinterpret_cast<uintptr_t>(p) & 15) == 0)
+
+extern "C" int vv_gather_rows(const float* bank, int64_t bank_rows, int K, const int32_t* idx, const int32_t* quirk,
+                              int B, int R, float* X, void* Xop_hi, void* Xop_lo, int prec, float* Xblob,
+                              vv_stream_t stream) {
+  VV_REQUIRE(bank && idx && B > 0 && R > 0 && bank_rows > 0, "bad gather arguments");
+  VV_REQUIRE(K > 0 && K % 4 == 0, "K=%d must be a multiple of 4", K);
+  VV_REQUIRE(VV_ALIGNED16(bank) && VV_ALIGNED16(X) && VV_ALIGNED16(Xop_hi) && VV_ALIGNED16(Xop_lo) && VV_ALIGNED16(Xblob),
+             "gather buffers must be 16-byte aligned");
+  GatherOut o; o.X = X; o.blob = Xblob; o.hi = nullptr; o.lo = nullptr; o.bf = nullptr; o.prec = VV_PREC_FP32_SIMT;
+  if (prec == VV_PREC_TF32X3 && Xop_hi) {
+    VV_REQUIRE(Xop_lo, "TF32X3 operand copy needs hi and lo");
+    o.hi = static_cast<float*>(Xop_hi); o.lo = static_cast<float*>(Xop_lo); o.prec = prec;
+  } else if (prec == VV_PREC_BF16 && Xop_hi) {
+    o.bf = static_cast<uint16_t*>(Xop_hi); o.prec = prec;
+  }
+  VV_REQUIRE(o.X || o.blob || o.prec != VV_PREC_FP32_SIMT, "no gather output requested");
+  const long long M = (long long)B * R;
+  const int grid = int(M < (long long)num_sms() * 16 ? M : (long long)num_sms() * 16);
+  gather_rows_kernel<<<grid, 256, 0, stream>>>(bank, idx, quirk, B, R, K, o);
+  VV_LAUNCH_CHECK();
+  count_launch();
+  return VV_OK;
+}
+
+extern "C" int vv_prepare_operand(const float* src, int64_t count, int prec, void* hi, void* lo, vv_stream_t stream) {
+  if (prec == VV_PREC_FP32_SIMT || prec == VV_PREC_TF32) return VV_OK;
+  VV_REQUIRE(src && hi && count > 0 && count % 4 == 0, "prepare_operand: bad arguments (count must be a multiple of 4)");
+  VV_REQUIRE(prec != VV_PREC_TF32X3 || lo, "TF32X3 needs a lo array");
+  VV_REQUIRE(VV_ALIGNED16(src) && VV_ALIGNED16(hi) && VV_ALIGNED16(lo), "operand buffers must be 16-byte aligned");
+  const long long n4 = count / 4;
+  prepare_operand_kernel<<<stream_grid(n4, 256), 256, 0, stream>>>(src, n4, prec, static_cast<float*>(hi),
+                                                                  static_cast<float*>(lo), static_cast<uint16_t*>(hi));
+  VV_LAUNCH_CHECK();
+  count_launch();
+  return VV_OK;
+}
+
+extern "C" int vv_sgd_update(float* W, const float* grad_parts, int nparts, int64_t part_stride, float* hist,
+                             float* diff_out, int64_t count, float local_rate, float momentum, float local_decay,
+                             int reg_type, float grad_scale, void* Wop_hi, void* Wop_lo, int prec, vv_stream_t stream) {
+  VV_REQUIRE(W && grad_parts && hist && count > 0 && nparts >= 1, "sgd_update: bad arguments");
+  VV_REQUIRE(reg_type == 1 || reg_type == 2, "regularization type must be 1 (L1) or 2 (L2)");
+  const bool vec = (count % 4 == 0) && (part_stride % 4 == 0) && VV_ALIGNED16(W) && VV_ALIGNED16(grad_parts) &&
+                   VV_ALIGNED16(hist) && VV_ALIGNED16(diff_out) && VV_ALIGNED16(Wop_hi) && VV_ALIGNED16(Wop_lo);
+  if (vec) {
+    const long long n4 = count / 4;
+    sgd_update_kernel<<<stream_grid(n4, 256), 256, 0, stream>>>(
+        W, grad_parts, nparts, part_stride, hist, diff_out, n4, local_rate, momentum, local_decay, reg_type,
+        grad_scale, prec, static_cast<float*>(Wop_hi), static_cast<float*>(Wop_lo), static_cast<uint16_t*>(Wop_hi));
+  } else {
+    VV_REQUIRE(!Wop_hi, "operand refresh needs a 16-byte aligned blob whose count is a multiple of 4");
+    sgd_update_scalar_kernel<<<stream_grid(count, 256), 256, 0, stream>>>(
+        W, grad_parts, nparts, part_stride, hist, diff_out, count, local_rate, momentum, local_decay, reg_type, grad_scale);
+  }
+  VV_LAUNCH_CHECK();
+  count_launch();
+  return VV_OK;
+}
+
+extern "C" float vv_learning_rate(const char* policy, float base_lr, float gamma, float power, int stepsize, int iter) {
+  // ref: solver.cpp:441-460, evaluated in Dtype = float
+  if (!policy || !strcmp(policy, "fixed")) return base_lr;
+  // pow(float, int) promotes to double in C++11, the product with base_lr is rounded to float once
+  if (!strcmp(policy, "step")) { const int cur = iter / (stepsize > 0 ? stepsize : 1); return float(base_lr * pow(double(gamma), double(cur))); }
+  if (!strcmp(policy, "exp")) return float(base_lr * pow(double(gamma), double(iter)));
+  if (!strcmp(policy, "inv")) return base_lr * powf(float(1) + gamma * iter, -power);
+  set_error("Unknown learning rate policy: %s", policy);
+  return -1.f;
+}
+
+extern "C" int vv_reduce_parts(const float* parts, int nparts, int64_t stride, int64_t count, float* out, vv_stream_t stream) {
+  VV_REQUIRE(parts && out && nparts >= 1 && count > 0, "reduce_parts: bad arguments");
+  reduce_parts_kernel<<<stream_grid(count, 256), 256, 0, stream>>>(parts, nparts, stride, count, out);
+  VV_LAUNCH_CHECK();
+  count_launch();
+  return VV_OK;
+}
+
+extern "C" int vv_ip_bias_grad(const float* dZ, int M, int N, float* db, vv_stream_t stream) {
+  VV_REQUIRE(dZ && db && M > 0 && N > 0, "bias_grad: bad arguments");
+  VV_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * N, stream));
+  int gy = (M + 255) / 256; if (gy > 64) gy = 64; if (gy < 1) gy = 1;
+  bias_grad_kernel<<<dim3((N + 31) / 32, gy), 256, 0, stream>>>(dZ, M, N, db);
+  VV_LAUNCH_CHECK();
+  count_launch(2);
+  return VV_OK;
+}
+
+extern "C" int vv_fill_bank(float* bank, int64_t rows, int K, uint64_t seed, vv_stream_t stream) {
+  VV_REQUIRE(bank && rows > 0 && K > 0 && K % 4 == 0, "fill_bank: bad arguments");
+  const long long n4 = rows * (long long)K / 4;
+  fill_bank_kernel<<<stream_grid(n4, 256), 256, 0, stream>>>(bank, n4, K, seed);
+  VV_LAUNCH_CHECK();
+  count_launch();
+  return VV_OK;
+}
+extern "C" float vv_bank_value_host(uint64_t seed, int64_t row, int col, int K) {
+  return bank_value(seed, uint64_t(row) * uint64_t(K) + uint64_t(col));
+}
+
+// ---- standalone layers -------------------------------------------------------
+#define VV_SIMPLE_LAUNCH(kernel, n, ...)                                         \
+  do {                                                                           \
+    kernel<<<stream_grid((n), 256), 256, 0, s>>>(__VA_ARGS__);                   \
+    VV_LAUNCH_CHECK();                                                           \
+    count_launch();                                                              \
+    return VV_OK;                                                                \
+  } while (0)
+
+extern "C" int vv_relu_forward(const float* x, int64_t n, float slope, float* y, vv_stream_t s) {
+  VV_REQUIRE(x && y && n > 0, "relu_forward: bad arguments");
+  VV_SIMPLE_LAUNCH(relu_fwd_kernel, n, x, n, slope, y);
+}
+extern "C" int vv_relu_backward(const float* x, const float* dy, int64_t n, float slope, float* dx, vv_stream_t s) {
+  VV_REQUIRE(x && dy && dx && n > 0, "relu_backward: bad arguments");
+  VV_SIMPLE_LAUNCH(relu_bwd_kernel, n, x, dy, n, slope, dx);
+}
+extern "C" int vv_dropout_forward(const float* x, const uint32_t* mask, int mode, int64_t n, float ratio, float* y, vv_stream_t s) {
+  VV_REQUIRE(x && y && mask && n > 0 && (mode == VV_DROPOUT_MASK01 || mode == VV_DROPOUT_MASK_U32), "dropout_forward: bad arguments");
+  VV_SIMPLE_LAUNCH(dropout_kernel, n, x, mask, mode, dropout_uint_thres(ratio), n, dropout_scale(ratio), y);
+}
+extern "C" int vv_dropout_backward(const float* dy, const uint32_t* mask, int mode, int64_t n, float ratio, float* dx, vv_stream_t s) {
+  VV_REQUIRE(dy && dx && mask && n > 0 && (mode == VV_DROPOUT_MASK01 || mode == VV_DROPOUT_MASK_U32), "dropout_backward: bad arguments");
+  VV_SIMPLE_LAUNCH(dropout_kernel, n, dy, mask, mode, dropout_uint_thres(ratio), n, dropout_scale(ratio), dx);
+}
+extern "C" int vv_dropout_make_mask(uint32_t* mask01, int rows, int cols, float ratio, uint64_t seed, uint64_t step, vv_stream_t s) {
+  VV_REQUIRE(mask01 && rows > 0 && cols > 0 && cols % 4 == 0 && VV_ALIGNED16(mask01), "dropout_make_mask: cols must be a multiple of 4, mask 16-byte aligned");
+  VV_SIMPLE_LAUNCH(dropout_make_mask_kernel, (long long)rows * (cols / 4), mask01, rows, cols / 4, dropout_uint_thres(ratio), seed, step);
+}
+extern "C" int vv_eltwise_sum_forward(const float* const* bottoms, const float* coeffs, int nb, int64_t n, float* top, vv_stream_t s) {
+  VV_REQUIRE(bottoms && coeffs && top && nb >= 1 && nb <= VV_MAX_CONTEXT && n > 0, "eltwise_sum: bad arguments");
+  PtrPack pk; pk.nb = nb;
+  for (int i = 0; i < nb; ++i) { pk.p[i] = bottoms[i]; pk.c[i] = coeffs[i]; }
+  VV_SIMPLE_LAUNCH(eltwise_sum_kernel, n, pk, n, top);
+}
+extern "C" int vv_eltwise_prod_forward(const float* a, const float* b, int64_t n, float* top, vv_stream_t s) {
+  VV_REQUIRE(a && b && top && n > 0, "eltwise_prod: bad arguments");
+  VV_SIMPLE_LAUNCH(mul_kernel, n, n, a, b, top);
+}
+extern "C" int vv_axpby(int64_t n, float alpha, const float* x, float beta, float* y, vv_stream_t s) {
+  VV_REQUIRE(x && y && n > 0, "axpby: bad arguments");
+  VV_SIMPLE_LAUNCH(axpby_kernel, n, n, alpha, x, beta, y);
+}
+extern "C" int vv_mul(int64_t n, const float* a, const float* b, float* y, vv_stream_t s) {
+  VV_REQUIRE(a && b && y && n > 0, "mul: bad arguments");
+  VV_SIMPLE_LAUNCH(mul_kernel, n, n, a, b, y);
+}
+extern "C" int vv_l2norm_forward(const float* x, int num, int dim, float* y, vv_stream_t s) {
+  VV_REQUIRE(x && y && num > 0 && dim > 0, "l2norm_forward: bad arguments");
+  VV_SIMPLE_LAUNCH(l2norm_fwd_kernel, (long long)num * 32, x, num, dim, y);
+}
+extern "C" int vv_l2norm_backward(const float* x, const float* dy, int num, int dim, float* dx, vv_stream_t s) {
+  VV_REQUIRE(x && dy && dx && num > 0 && dim > 0, "l2norm_backward: bad arguments");
+  VV_SIMPLE_LAUNCH(l2norm_bwd_kernel, (long long)num * 32, x, dy, num, dim, dx);
+}
+extern "C" int vv_rowsum_forward(const float* x, int num, int dim, int nout, float* y, vv_stream_t s) {
+  VV_REQUIRE(x && y && num > 0 && dim > 0 && nout > 0, "rowsum_forward: bad arguments");
+  VV_SIMPLE_LAUNCH(rowsum_fwd_kernel, (long long)num * 32, x, num, dim, nout, y);
+}
+extern "C" int vv_rowsum_backward(const float* dy, int num, int dim, int nout, float* dx, vv_stream_t s) {
+  VV_REQUIRE(dy && dx && num > 0 && dim > 0 && nout > 0, "rowsum_backward: bad arguments");
+  VV_SIMPLE_LAUNCH(rowsum_bwd_kernel, (long long)num * 32, dy, num, dim, nout, dx);
+}
+extern "C" int vv_copy_strided(const float* src, int64_t ss, float* dst, int64_t ds, int64_t rows, int64_t cols, vv_stream_t s) {
+  VV_REQUIRE(src && dst && rows > 0 && cols > 0, "copy_strided: bad arguments");
+  VV_SIMPLE_LAUNCH(copy_strided_kernel, rows * cols, src, ss, dst, ds, rows, cols);
+}
+extern "C" int vv_max_margin_forward(const float* st, const float* sb, int count, float margin, int norm, float* hinge,
+                                     float* loss, float* viol, vv_stream_t s) {
+  VV_REQUIRE(st && sb && count > 0 && (norm == 1 || norm == 2), "max_margin_forward: bad arguments");
+  max_margin_fwd_kernel<<<1, 1024, 0, s>>>(st, sb, count, margin, norm, hinge, loss, viol);
+  VV_LAUNCH_CHECK();
+  count_launch();
+  return VV_OK;
+}
+extern "C" int vv_max_margin_backward(const float* st, const float* sb, int count, float margin, int norm, float lw,
+                                      float* d_true, float* d_bogus, vv_stream_t s) {
+  VV_REQUIRE(st && sb && count > 0 && (norm == 1 || norm == 2), "max_margin_backward: bad arguments");
+  const float gs = (norm == 2) ? lw * 2 / count : lw / count;
+  VV_SIMPLE_LAUNCH(max_margin_bwd_kernel, count, st, sb, count, margin, norm, gs, d_true, d_bogus);
+}

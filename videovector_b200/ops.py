@@ -1,0 +1,373 @@
+"""Thin torch-tensor wrappers over the C-ABI (PyTorch supplies device memory and
+streams only; every op below is one call into libvv_b200.so)."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (Act, Operand, RankCfg, TrainerCfg, PREC, DROPOUT_NONE, DROPOUT_MASK01,
+                   DROPOUT_MASK_U32, DROPOUT_PHILOX, VVError, check)
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    assert t.is_contiguous(), "tensor must be contiguous"
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _prec(p):
+    return PREC[p] if isinstance(p, str) else int(p)
+
+
+class OperandT:
+    """GEMM operand copies of an fp32 tensor for a precision (see vv_operand_t)."""
+
+    def __init__(self, hi, lo=None):
+        self.hi, self.lo = hi, lo
+
+    def c(self):
+        return Operand(_ptr(self.hi), _ptr(self.lo))
+
+
+def alloc_operand(shape, prec, device="cuda"):
+    p = _prec(prec)
+    if p == PREC["tf32x3"]:
+        return OperandT(torch.empty(shape, dtype=torch.float32, device=device),
+                        torch.empty(shape, dtype=torch.float32, device=device))
+    if p == PREC["bf16"]:
+        return OperandT(torch.empty(shape, dtype=torch.bfloat16, device=device))
+    return None
+
+
+def prepare_operand(x, prec):
+    """fp32 tensor -> OperandT for `prec` (FP32_SIMT / TF32 use the tensor itself)."""
+    p = _prec(prec)
+    if p in (PREC["fp32_simt"], PREC["tf32"]):
+        return OperandT(x)
+    op = alloc_operand(x.shape, p, x.device)
+    check(_lib.load().vv_prepare_operand(_ptr(x), x.numel(), p, _ptr(op.hi), _ptr(op.lo), _stream()))
+    return op
+
+
+def gather_rows(bank, idx, quirk, prec="fp32_simt", want_x=True, want_blob=False):
+    """K0.  bank [rows,K] fp32, idx/quirk [B,R] int32 (device).  Returns (X, operand, blob)."""
+    lib = _lib.load()
+    B, R = idx.shape
+    K = bank.shape[1]
+    p = _prec(prec)
+    X = torch.empty((R * B, K), dtype=torch.float32, device=bank.device) if want_x else None
+    op = alloc_operand((R * B, K), p, bank.device)
+    blob = torch.empty((B, R, K), dtype=torch.float32, device=bank.device) if want_blob else None
+    check(lib.vv_gather_rows(_ptr(bank), bank.shape[0], K, _ptr(idx), _ptr(quirk), B, R, _ptr(X),
+                             _ptr(op.hi) if op else None, _ptr(op.lo) if op else None, p, _ptr(blob), _stream()))
+    if op is None and X is not None:
+        op = OperandT(X)
+    return X, op, blob
+
+
+def make_act(relu=True, negative_slope=0.0, dropout_mode=DROPOUT_NONE, ratio=0.0, mask=None, mask_out=None,
+             seed=0, step=0):
+    a = Act()
+    a.relu = int(relu); a.negative_slope = negative_slope; a.dropout_mode = dropout_mode
+    a.dropout_ratio = ratio
+    a.mask = mask.data_ptr() if mask is not None else None
+    a.mask_out = mask_out.data_ptr() if mask_out is not None else None
+    a.seed = seed; a.step = step
+    return a
+
+
+def ip_forward(X, W, bias, M, N, K, prec, act=None, want_z=False):
+    """K1 forward.  X, W are OperandT.  Returns (H, Z)."""
+    dev = W.hi.device
+    H = torch.empty((M, N), dtype=torch.float32, device=dev)
+    Z = torch.empty((M, N), dtype=torch.float32, device=dev) if (want_z and act is not None) else None
+    check(_lib.load().vv_ip_forward(X.c(), W.c(), _ptr(bias), M, N, K, _prec(prec),
+                                    C.byref(act) if act is not None else None, _ptr(Z), _ptr(H), _stream()))
+    return H, Z
+
+
+def ip_wgrad(dZ, X, M, N, K, prec, regularization=0.0, nsplit=0):
+    """K1 wgrad.  Returns dW [N,K] (slabs reduced)."""
+    lib = _lib.load()
+    dev = X.hi.device
+    p = _prec(prec)
+    if nsplit == 0:
+        ws_bytes = lib.vv_ip_wgrad_workspace_bytes(M, N, K, p)
+        ws = torch.empty((max(ws_bytes, 4) // 4,), dtype=torch.float32, device=dev)
+        dW = torch.empty((N, K), dtype=torch.float32, device=dev)
+        check(lib.vv_ip_wgrad(dZ.c(), X.c(), M, N, K, p, regularization, _ptr(dW), 0, _ptr(ws), ws_bytes, _stream()))
+        return dW
+    parts = torch.empty((nsplit, N, K), dtype=torch.float32, device=dev)
+    check(lib.vv_ip_wgrad(dZ.c(), X.c(), M, N, K, p, regularization, _ptr(parts), nsplit, None, 0, _stream()))
+    return parts.sum(0) if nsplit > 1 else parts[0]
+
+
+def ip_bias_grad(dZ):
+    M, N = dZ.shape
+    db = torch.empty((N,), dtype=torch.float32, device=dZ.device)
+    check(_lib.load().vv_ip_bias_grad(_ptr(dZ), M, N, _ptr(db), _stream()))
+    return db
+
+
+def ip_dgrad(dZ, W, M, N, K, prec):
+    dX = torch.empty((M, K), dtype=torch.float32, device=W.hi.device)
+    check(_lib.load().vv_ip_dgrad(dZ.c(), W.c(), M, N, K, _prec(prec), _ptr(dX), _stream()))
+    return dX
+
+
+def rank_cfg(B, Cc, Nn, N, margin=2.0, norm=2, coeff=None, eps=1e-10):
+    c = RankCfg()
+    c.B, c.C, c.Nn, c.N = B, Cc, Nn, N
+    co = coeff if coeff is not None else [1.0 / (Cc - 1)] * (Cc - 1)
+    for i, v in enumerate(co):
+        c.coeff[i] = np.float32(v)
+    c.margin = margin; c.norm = norm; c.eps = eps
+    return c
+
+
+def rank_loss_forward(H, cfg):
+    """K2.  Returns dict(stats, target_score, neg_score, loss, violations)."""
+    dev = H.device
+    B, Nn = cfg.B, cfg.Nn
+    stride = 1 + 2 * (1 + Nn)
+    out = dict(stats=torch.empty((B, stride), dtype=torch.float32, device=dev),
+               target_score=torch.empty((B, Nn), dtype=torch.float32, device=dev),
+               neg_score=torch.empty((B, Nn), dtype=torch.float32, device=dev),
+               item_loss=torch.empty((B,), dtype=torch.float32, device=dev),
+               item_viol=torch.empty((B,), dtype=torch.float32, device=dev),
+               loss=torch.empty((1,), dtype=torch.float32, device=dev),
+               violations=torch.empty((1,), dtype=torch.float32, device=dev))
+    check(_lib.load().vv_rank_loss_forward(_ptr(H), C.byref(cfg), _ptr(out["stats"]), _ptr(out["target_score"]),
+                                           _ptr(out["neg_score"]), _ptr(out["item_loss"]), _ptr(out["item_viol"]),
+                                           _ptr(out["loss"]), _ptr(out["violations"]), _stream()))
+    return out
+
+
+def rank_loss_backward(H, cfg, stats, loss_weight=1.0, act_fused=True, dropout_scale=1.0, prec="fp32_simt",
+                       want_db=True):
+    """K3.  Returns (dZ fp32, operand copies or None, db or None)."""
+    dev = H.device
+    p = _prec(prec)
+    dZ = torch.empty_like(H)
+    op = alloc_operand(H.shape, p, dev)
+    db = torch.zeros((cfg.N,), dtype=torch.float32, device=dev) if want_db else None
+    check(_lib.load().vv_rank_loss_backward(_ptr(H), C.byref(cfg), _ptr(stats), loss_weight, int(act_fused),
+                                            dropout_scale, _ptr(dZ), _ptr(op.hi) if op else None,
+                                            _ptr(op.lo) if op else None, p, _ptr(db), _stream()))
+    return dZ, (op if op is not None else OperandT(dZ)), db
+
+
+def sgd_update(W, grad_parts, hist, local_rate, momentum, local_decay, reg_type=2, grad_scale=1.0, prec="fp32_simt",
+               Wop=None, diff_out=None):
+    """K4 (in place on W, hist).  grad_parts [S, ...] or [...]."""
+    count = W.numel()
+    nparts = grad_parts.numel() // count
+    check(_lib.load().vv_sgd_update(_ptr(W), _ptr(grad_parts), nparts, count, _ptr(hist), _ptr(diff_out), count,
+                                    local_rate, momentum, local_decay, reg_type, grad_scale,
+                                    _ptr(Wop.hi) if Wop is not None else None,
+                                    _ptr(Wop.lo) if (Wop is not None and Wop.lo is not None) else None,
+                                    _prec(prec), _stream()))
+
+
+def learning_rate(policy, base_lr, gamma, power, stepsize, it):
+    return float(_lib.load().vv_learning_rate(policy.encode(), base_lr, gamma, power, stepsize, it))
+
+
+def dropout_make_mask(rows, cols, ratio, seed, step, device="cuda"):
+    m = torch.empty((rows, cols), dtype=torch.int32, device=device)
+    check(_lib.load().vv_dropout_make_mask(_ptr(m), rows, cols, ratio, seed, step, _stream()))
+    return m
+
+
+def fill_bank(rows, K, seed, device="cuda"):
+    bank = torch.empty((rows, K), dtype=torch.float32, device=device)
+    check(_lib.load().vv_fill_bank(_ptr(bank), rows, K, seed, _stream()))
+    return bank
+
+
+def bank_host(rows, K, seed):
+    """numpy restatement of the synthetic bank hash (bit-identical to vv_fill_bank)."""
+    e = np.arange(rows * K, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        x = np.uint64(seed) * np.uint64(0xD1342543DE82EF95) + e
+        x = x + np.uint64(0x9E3779B97F4A7C15)
+        x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        x = x ^ (x >> np.uint64(31))
+    m = np.uint64(0xFFFF)
+    t = ((x & m) + ((x >> np.uint64(16)) & m) + ((x >> np.uint64(32)) & m) + ((x >> np.uint64(48)) & m)).astype(np.int64) - 131070
+    v = t.astype(np.float32) * np.float32(np.float32(1.0) / np.float32(37837.0))
+    return np.maximum(v, np.float32(0)).reshape(rows, K)
+
+
+# ---------------------------------------------------------------------------------
+# host sampler + synthetic dataset description
+# ---------------------------------------------------------------------------------
+def synthetic_videos(V, S):
+    """V videos of S shots each: video_id = v, shot_ids = 0..S-1, bank row = v*S + s."""
+    video_id = np.arange(V, dtype=np.int32)
+    shot_off = (np.arange(V + 1, dtype=np.int64) * S).astype(np.int32)
+    shot_ids = np.tile(np.arange(S, dtype=np.int32), V)
+    return video_id, shot_off, shot_ids
+
+
+class Sampler:
+    """VideoSampledShotsDataLayer's WINDOW sampler as an index stream (host, C++)."""
+
+    def __init__(self, video_id, shot_off, shot_ids, batch_size, context_size=5, num_negative_samples=10,
+                 max_buffer_size=5000, negative_swap_percentage=50, max_same_video_negs=6,
+                 max_tries_for_negs=100, rand_seed=1):
+        self._lib = _lib.load()
+        self.video_id = np.ascontiguousarray(video_id, dtype=np.int32)
+        self.shot_off = np.ascontiguousarray(shot_off, dtype=np.int32)
+        self.shot_ids = np.ascontiguousarray(shot_ids, dtype=np.int32)
+        self.B, self.R = batch_size, context_size + num_negative_samples
+        self._h = self._lib.vv_sampler_create(len(self.video_id), self.video_id.ctypes.data, self.shot_off.ctypes.data,
+                                              self.shot_ids.ctypes.data, batch_size, context_size, num_negative_samples,
+                                              max_buffer_size, negative_swap_percentage, max_same_video_negs,
+                                              max_tries_for_negs, rand_seed)
+        if not self._h:
+            raise VVError("vv_sampler_create failed (bad parameters, or could not fill the negative buffer)")
+
+    def next(self):
+        idx = np.empty((self.B, self.R), dtype=np.int32)
+        quirk = np.empty((self.B, self.R), dtype=np.int32)
+        check(self._lib.vv_sampler_next(self._h, idx.ctypes.data, quirk.ctypes.data))
+        return idx, quirk
+
+    def next_into(self, idx, quirk):
+        check(self._lib.vv_sampler_next(self._h, idx.ctypes.data, quirk.ctypes.data))
+
+    @property
+    def cursor(self):
+        return self._lib.vv_sampler_cursor(self._h)
+
+    def close(self):
+        if self._h:
+            self._lib.vv_sampler_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ---------------------------------------------------------------------------------
+# trainer
+# ---------------------------------------------------------------------------------
+SOLVER_DEFAULTS = dict(lr_policy="inv", base_lr=1e-3, gamma=1e-3, power=0.75, stepsize=1,
+                       momentum=0.9, weight_decay=5e-4, reg_type=2, lr_mult=(1.0, 2.0), decay_mult=(1.0, 0.0))
+
+
+def trainer_cfg(B, C_=5, Nn=10, K=4096, N=512, margin=2.0, norm=2, dropout_ratio=0.9, dropout_mode=DROPOUT_PHILOX,
+                dropout_seed=7, loss_weight=1.0, regularization=0.0, prec="tf32x3", world_size=1, rank=0,
+                compute_dgrad=False, keep_blobs=False, coeff=None, **solver):
+    s = dict(SOLVER_DEFAULTS); s.update(solver)
+    c = TrainerCfg()
+    c.B, c.C, c.Nn, c.K, c.N = B, C_, Nn, K, N
+    if coeff is not None:
+        for i, v in enumerate(coeff):
+            c.coeff[i] = v
+    c.margin, c.norm = margin, norm
+    c.dropout_ratio, c.dropout_mode, c.dropout_seed = dropout_ratio, dropout_mode, dropout_seed
+    c.loss_weight, c.regularization = loss_weight, regularization
+    c.lr_policy = s["lr_policy"].encode()
+    c.base_lr, c.gamma, c.power, c.stepsize = s["base_lr"], s["gamma"], s["power"], s["stepsize"]
+    c.momentum, c.weight_decay, c.reg_type = s["momentum"], s["weight_decay"], s["reg_type"]
+    c.lr_mult[0], c.lr_mult[1] = s["lr_mult"]
+    c.decay_mult[0], c.decay_mult[1] = s["decay_mult"]
+    c.prec = _prec(prec); c.world_size, c.rank = world_size, rank
+    c.compute_dgrad, c.keep_blobs = int(compute_dgrad), int(keep_blobs)
+    return c
+
+
+class Trainer:
+    """One data-parallel rank of the fused training step (C++ object behind the C-ABI)."""
+
+    def __init__(self, cfg, stream=None):
+        self._lib = _lib.load()
+        self.cfg = cfg
+        self.stream = stream if stream is not None else torch.cuda.current_stream()
+        self._h = self._lib.vv_trainer_create(C.byref(cfg), C.c_void_p(self.stream.cuda_stream))
+        if not self._h:
+            raise VVError("vv_trainer_create failed: " + _lib.last_error())
+        self.R = cfg.C + cfg.Nn
+        self.M = self.R * cfg.B
+
+    def tensor(self, which):
+        N, K, B = self.cfg.N, self.cfg.K, self.cfg.B
+        L = self._lib
+        table = {
+            "W": (L.vv_trainer_weight, (N, K)), "b": (L.vv_trainer_bias, (N,)),
+            "W_hist": (L.vv_trainer_weight_hist, (N, K)), "b_hist": (L.vv_trainer_bias_hist, (N,)),
+            "W_diff": (L.vv_trainer_weight_diff, (N, K)), "b_diff": (L.vv_trainer_bias_diff, (N,)),
+        }
+        if which in table:
+            fn, shape = table[which]
+            return _device_view(fn(self._h), shape)
+        shapes = {"X": (self.M, K), "Z": (self.M, N), "H": (self.M, N), "dZ": (self.M, N),
+                  "stats": (B, 1 + 2 * (1 + self.cfg.Nn)), "loss": (1,), "violations": (1,),
+                  "dW_raw": (N, K), "db_raw": (N,), "dX": (self.M, K)}
+        ptr = L.vv_trainer_blob(self._h, which.encode())
+        if not ptr:
+            raise VVError("trainer blob %s is not allocated in this configuration" % which)
+        return _device_view(ptr, shapes[which])
+
+    def set_weights(self, W, b):
+        self.tensor("W").copy_(W)
+        self.tensor("b").copy_(b)
+        check(self._lib.vv_trainer_sync_weights(self._h))
+
+    def step(self, bank, idx, quirk, mask=None, it=0, do_update=True):
+        check(self._lib.vv_trainer_step(self._h, _ptr(bank), bank.shape[0], _ptr(idx), _ptr(quirk), _ptr(mask),
+                                        it, int(do_update)))
+
+    def extract(self, F):
+        out = torch.empty((F.shape[0], self.cfg.N), dtype=torch.float32, device=F.device)
+        check(self._lib.vv_trainer_extract(self._h, _ptr(F), F.shape[0], _ptr(out)))
+        return out
+
+    @property
+    def last_launches(self):
+        return self._lib.vv_trainer_last_launches(self._h)
+
+    def dp_init(self, id_bytes):
+        buf = (C.c_char * 128).from_buffer_copy(id_bytes)
+        check(self._lib.vv_dp_init(self._h, C.addressof(buf)))
+
+    def close(self):
+        if self._h:
+            self._lib.vv_trainer_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def dp_unique_id():
+    buf = (C.c_char * 128)()
+    check(_lib.load().vv_dp_unique_id(C.addressof(buf)))
+    return bytes(buf.raw)
+
+
+class _CudaArrayHolder:
+    def __init__(self, ptr, shape):
+        n = int(np.prod(shape))
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+
+def _device_view(ptr, shape):
+    """Zero-copy torch view of trainer-owned device memory."""
+    t = torch.as_tensor(_CudaArrayHolder(ptr, shape), device="cuda")
+    return t.view(*shape)
