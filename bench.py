@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""bench.py -- training triplets/sec of the temporal-context embedding step on B200.
+
+  python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun, one rank per GPU)
+  python bench.py --impl reference --gpus N --steps K --warmup W    (the reference's CPU path, rank 0 only)
+
+Prints ONE JSON line (rank 0).  Workload (BASELINE.json configs[1] per GPU, weak scaling):
+synthetic post-ReLU 4096-d features resident in HBM, 512-d embedding, window +-2 (C=5),
+10 negatives, B = 4096 triplets per GPU per step, dropout 0.9 (Philox), squared hinge margin 2,
+SGD momentum 0.9 / decay 5e-4 / inv LR policy.  Default precision: tf32x3 (tensor-core hi/lo split,
+fp32 accumulate = the fp32-parity mode config[1] names); --precision bf16|tf32 for config[2]'s mode.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG = dict(C=5, Nn=10, K=4096, N=512, B=4096, V=2048, S=32, P=5000, swap=50, max_same=6)
+CPU_SAMPLE_B = 256          # bounded CPU sample: items per oracle step (same K, N, C, Nn)
+METRIC = "training triplets/sec"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=float(d["hbm_gbs"]), bf16=float(d["bf16_tflops"]), bf16_sus=float(d["bf16_tflops_sustained"]),
+                    src="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sus=1400.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        # "under load" = samples drawing more than half of the peak power seen
+        pmax = max(power)
+        load = [s for s, p in zip(sm, power) if p >= 0.5 * pmax] or sm
+        return {"sm_mhz": float(np.median(load)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons),
+                "power_w_max": pmax, "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the oracle (port of the reference's CPU layers) on the host cores
+# ---------------------------------------------------------------------------------------------------
+def cpu_reference_run(steps, warmup, threads=0):
+    """One 'step' = sampler (materialising the data blob) + whole-net forward/backward + SGD update on a
+    bounded sample of CPU_SAMPLE_B items of the workload.  Returns (triplets/s, ms/step, cores, phase dict)."""
+    from oracle import pyoracle as orc
+    from videovector_b200 import ops
+    c = CFG
+    B = CPU_SAMPLE_B
+    V, S = 512, 16                                       # 8192 shots >= the 5000-entry negative buffer
+    cores = orc.use_openblas(threads)
+    feat = ops.bank_host(V * S, c["K"], 1234)
+    vid, off, sid = ops.synthetic_videos(V, S)
+    smp = orc.Sampler(vid, off, sid, feat, c["K"], B, c["C"], c["Nn"], c["P"], c["swap"], c["max_same"], 100, seed=1)
+    rng = np.random.RandomState(1701)
+    W = rng.normal(0, 0.001, (c["N"], c["K"])).astype(np.float32)
+    b = np.zeros(c["N"], np.float32)
+    hW = np.zeros_like(W); hb = np.zeros_like(b)
+    R = c["C"] + c["Nn"]
+    mrng = np.random.RandomState(7)
+    times, phases = [], np.zeros(8)
+    for it in range(warmup + steps):
+        mask = (mrng.uniform(0, 1, (R * B, c["N"])) > 0.9).astype(np.uint32)   # mask generation not timed
+        t0 = time.perf_counter()
+        idx, quirk, data = smp.next()
+        t1 = time.perf_counter()
+        out = orc.net_forward_backward(data, W, b, mask, B, c["C"], c["Nn"], margin=2.0, norm=2, dropout_ratio=0.9,
+                                       want=("loss", "violations", "dW", "db"))
+        rate = orc.learning_rate("inv", 1e-3, 1e-3, 0.75, 1, it)
+        W, _, hW = orc.sgd_update(W, out["dW"], hW, rate, 0.9, 5e-4)
+        b, _, hb = orc.sgd_update(b, out["db"], hb, rate * 2, 0.9, 0.0)
+        t2 = time.perf_counter()
+        if it >= warmup:
+            times.append(t2 - t0)
+            phases[:5] += out["phase_seconds"][:5]; phases[5] += t1 - t0
+    smp.close()
+    orc.use_builtin_blas()
+    ms = 1e3 * float(np.mean(times))
+    ph = {k: 1e3 * phases[i] / len(times) for i, k in enumerate(["slice_concat", "fc7_forward", "loss_forward",
+                                                                  "loss_backward", "fc7_backward", "sampler"])}
+    return B / (ms * 1e-3), ms, cores, ph
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    val, ms, cores, ph = cpu_reference_run(args.steps, max(args.warmup, 1))
+    sample = "B=%d items per step (1/%d of the %d-item GPU step), same K/N/C/Nn; %d timed steps" % (
+        CPU_SAMPLE_B, CFG["B"] // CPU_SAMPLE_B, CFG["B"], args.steps)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "triplets/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": val, "unit": "triplets/s", "cores": cores, "kind": "port", "sample": sample,
+                         "phase_ms": ph,
+                         "note": "oracle/vv_oracle.cpp = restated reference CPU layers + solver + sampler, OpenBLAS "
+                                 "from the SciPy wheel; the reference itself cannot be built here (glog/boost/protobuf absent)"},
+        "e2e": {"value": val, "unit": "triplets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, world):
+    c = CFG
+    return {"workload": "videovec_embedding context-ranking training step (BASELINE configs[1] per GPU): "
+                        "4096-d features -> %d-d embedding, window +-%d, %d negatives, B=%d triplets/GPU/step, "
+                        "dropout 0.9, squared hinge margin 2, SGD momentum" % (c["N"], c["C"] // 2, c["Nn"], c["B"]),
+            "global_batch": c["B"] * world, "K": c["K"], "N": c["N"], "C": c["C"], "Nn": c["Nn"],
+            "parallelism": "dp%d" % world, "precision": getattr(args, "precision", "tf32x3"),
+            "dgrad": False, "bank_rows": c["V"] * c["S"],
+            "l2": "inputs larger than L2: each step streams a %.2f GB gathered operand (> 126 MB L2)" % (
+                (c["C"] + c["Nn"]) * c["B"] * c["K"] * (8 if getattr(args, "precision", "tf32x3") == "tf32x3" else 4) / 1e9)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# the GPU arm
+# ---------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from videovector_b200 import ops
+    from videovector_b200._lib import DROPOUT_PHILOX
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    c = CFG
+    B, C, Nn, K, N = c["B"], c["C"], c["Nn"], c["K"], c["N"]
+    R = C + Nn
+    prec = args.precision
+    pk = peaks()
+
+    # synthetic feature bank (resident in HBM) and the host sampler.  Data parallel: every rank owns a
+    # shard of the videos and runs its own reference-exact sampler stream over it (no data-path collective).
+    bank = ops.fill_bank(c["V"] * c["S"], K, 1234 + rank)
+    vid, off, sid = ops.synthetic_videos(c["V"], c["S"])
+    smp = ops.Sampler(vid + rank * c["V"], off, sid, B, C, Nn, c["P"], c["swap"], c["max_same"], 100, rand_seed=1 + rank)
+
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        tr = ops.Trainer(ops.trainer_cfg(B, C, Nn, K, N, prec=prec, dropout_ratio=0.9, dropout_mode=DROPOUT_PHILOX,
+                                         dropout_seed=7, world_size=world, rank=rank), stream=stream)
+        g = torch.Generator(device="cuda").manual_seed(1701)
+        W0 = torch.randn(N, K, device="cuda", generator=g) * 0.001          # gaussian filler std 0.001, bias 0
+        tr.set_weights(W0, torch.zeros(N, device="cuda"))
+        if world > 1:
+            idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                idt.copy_(torch.frombuffer(bytearray(ops.dp_unique_id()), dtype=torch.uint8))
+            dist.broadcast(idt, 0)
+            tr.dp_init(bytes(idt.cpu().numpy().tobytes()))
+
+        total = args.warmup + args.steps
+        # ---- leg 1: `value` -- inputs already resident in HBM when the timed region starts
+        idx_host = torch.empty((total, B, R), dtype=torch.int32).pin_memory()
+        qk_host = torch.empty((total, B, R), dtype=torch.int32).pin_memory()
+        for i in range(total):
+            smp.next_into(idx_host[i].numpy(), qk_host[i].numpy())
+        idx_dev = idx_host.cuda(non_blocking=True); qk_dev = qk_host.cuda(non_blocking=True)
+        for i in range(args.warmup):
+            tr.step(bank, idx_dev[i], qk_dev[i], None, it=i)
+        stream.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        clocks = ClockSampler(local); clocks.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(args.warmup, total):
+            tr.step(bank, idx_dev[i], qk_dev[i], None, it=i)
+        e1.record(stream)
+        stream.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        clk = clocks.stop()
+        ms_total = e0.elapsed_time(e1)
+        launches = tr.last_launches * args.steps
+        loss_final = float(tr.tensor("loss").item())
+
+        # ---- leg 2: per-kernel timing inside the step (CUDA events on the launching stream)
+        tr.set_timing(True)
+        nt = min(args.steps, 20)
+        for i in range(nt):
+            tr.step(bank, idx_dev[args.warmup + i % args.steps], qk_dev[args.warmup + i % args.steps], None, it=total + i)
+        phase, _ = tr.phase_ms()
+        tr.set_timing(False)
+
+        # ---- leg 3: `e2e` -- the public API with HOST buffers: sampler (prefetch thread, as the reference's
+        # prefetching data layer) -> pinned host indices -> H2D -> step -> D2H loss, all inside the timed region
+        nbuf = 3
+        hi = [torch.empty((B, R), dtype=torch.int32).pin_memory() for _ in range(nbuf)]
+        hq = [torch.empty((B, R), dtype=torch.int32).pin_memory() for _ in range(nbuf)]
+        di = [torch.empty((B, R), dtype=torch.int32, device="cuda") for _ in range(nbuf)]
+        dq = [torch.empty((B, R), dtype=torch.int32, device="cuda") for _ in range(nbuf)]
+        loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+        ready = [threading.Semaphore(0) for _ in range(nbuf)]
+        free = [threading.Semaphore(1) for _ in range(nbuf)]
+        e2e_steps = args.steps
+
+        def producer():
+            for i in range(args.warmup + e2e_steps):
+                k = i % nbuf
+                free[k].acquire()
+                smp.next_into(hi[k].numpy(), hq[k].numpy())
+                ready[k].release()
+        th = threading.Thread(target=producer, daemon=True); th.start()
+        evs = [torch.cuda.Event() for _ in range(nbuf)]
+
+        def e2e_step(i):
+            k = i % nbuf
+            ready[k].acquire()
+            di[k].copy_(hi[k], non_blocking=True); dq[k].copy_(hq[k], non_blocking=True)
+            evs[k].record(stream)
+            tr.step(bank, di[k], dq[k], None, it=2 * total + i)
+            loss_host.copy_(tr.tensor("db_raw_ext")[N:N + 2], non_blocking=True)      # loss + violations, 8 bytes D2H
+            # a pinned index buffer may be refilled once its H2D copy has completed: release the previous
+            # step's buffer (its copy is long done) so the host never stalls on the step it just launched
+            if i > 0:
+                kp = (i - 1) % nbuf
+                evs[kp].synchronize()
+                free[kp].release()
+        for i in range(args.warmup):
+            e2e_step(i)
+        stream.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for i in range(args.warmup, args.warmup + e2e_steps):
+            e2e_step(i)
+        stream.synchronize()
+        t1 = time.perf_counter()
+        th.join(timeout=10)
+        e2e_ms = 1e3 * (t1 - t0)
+
+    # max over ranks
+    if world > 1:
+        t = torch.tensor([ms_total, e2e_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, e2e_ms = float(t[0]), float(t[1])
+    ms_step = ms_total / args.steps
+    value = world * B / (ms_step * 1e-3)
+    e2e_val = world * B * e2e_steps / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        M = R * B
+        flops = 2.0 * M * N * K
+        tf32_factor = 3 if prec == "tf32x3" else 1
+        # peak for the operand type: bf16 measured (sustained, kernel timed inside a long step); tf32 = half of it
+        tensor_peak = pk["bf16_sus"] if prec == "bf16" else pk["bf16_sus"] / 2
+        kern = {}
+        for name, f in (("fc7_forward", flops), ("wgrad", flops)):
+            ms = phase[name]
+            kern[name] = {"ms": ms, "bound": "tensor", "achieved_tflops": flops / (ms * 1e-3) / 1e12 if ms > 0 else None}
+        bytes_alg = {"gather": M * K * 4 * (1 + (2 if prec == "tf32x3" else (0.5 if prec == "bf16" else 1))),
+                     "rank_loss_forward": M * N * 4,
+                     "rank_loss_backward": M * N * 4 * (1 + (2 if prec == "tf32x3" else (0.5 if prec == "bf16" else 1))),
+                     "sgd_update": N * K * 4 * (5 + tr._lib.vv_ip_wgrad_auto_nsplit(M, N, K, ops.PREC[prec])
+                                                + (2 if prec == "tf32x3" else (0.5 if prec == "bf16" else 0)))}
+        for name, by in bytes_alg.items():
+            ms = phase[name]
+            kern[name] = {"ms": ms, "bound": "hbm", "achieved_gbs": by / (ms * 1e-3) / 1e9 if ms > 0 else None,
+                          "frac": by / (ms * 1e-3) / 1e9 / pk["hbm"] if ms > 0 else None}
+        dom = "wgrad" if phase["wgrad"] >= phase["fc7_forward"] else "fc7_forward"
+        ach = kern[dom]["achieved_tflops"]
+        roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": tensor_peak, "unit": "TFLOP/s",
+                    "frac": ach / tensor_peak if ach else None, "traffic": None,
+                    "peak_source": pk["src"] + ("; tf32 peak taken as half of the measured bf16 sustained peak" if prec != "bf16" else ""),
+                    "mma_per_product": tf32_factor,
+                    "tensor_pipe_frac": ach * tf32_factor / tensor_peak if ach else None,
+                    "note": "achieved = algorithmic 2*M*N*K per launch / mean launch duration (CUDA events around the "
+                            "kernel inside the step); tf32x3 issues 3 MMAs per product, tensor_pipe_frac counts them"}
+        for k in ("fc7_forward", "wgrad"):
+            kern[k]["frac"] = kern[k]["achieved_tflops"] / tensor_peak if kern[k]["achieved_tflops"] else None
+        line = {
+            "metric": METRIC, "value": value, "unit": "triplets/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": {"tf32x3": "f32 (tf32x3 split, fp32 accumulate)", "bf16": "bf16",
+                                           "tf32": "tf32", "fp32_simt": "f32"}[prec],
+            "data": "synthetic", "config": workload_config(args, world),
+            "clocks": clk, "gpu_launches": launches,
+            "e2e": {"value": e2e_val, "unit": "triplets/s", "h2d_bytes_per_step": 2 * B * R * 4, "d2h_bytes_per_step": 8,
+                    "ms_per_step": e2e_ms / e2e_steps,
+                    "note": "host sampler on a prefetch thread -> pinned int32 [B,R] indices -> H2D -> vv_trainer_step -> "
+                            "D2H loss; the feature bank is resident in HBM (uploaded once, like opening the LMDB)"},
+            "roofline": roofline, "kernels": kern, "loss": loss_final,
+            "hinge_terms_per_s": value * Nn,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            val, ms, cores, ph = cpu_reference_run(5, 2)
+            line["cpu_baseline"] = {"value": val, "unit": "triplets/s", "cores": cores, "kind": "port",
+                                    "sample": "B=%d items per step (1/%d of the GPU step), same K/N/C/Nn, 5 timed steps after 2 warm-up"
+                                              % (CPU_SAMPLE_B, B // CPU_SAMPLE_B), "ms_per_step": ms, "phase_ms": ph}
+        print(json.dumps(line))
+    tr.close(); smp.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default="tf32x3", choices=["tf32x3", "tf32", "bf16", "fp32_simt"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

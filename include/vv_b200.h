@@ -303,6 +303,13 @@ int vv_trainer_step(vv_trainer_t* t, const float* bank, int64_t bank_rows,
                     int iter, int do_update);
 /* kernels launched by the last step (for bench.py's gpu_launches claim) */
 int vv_trainer_last_launches(const vv_trainer_t* t);
+/* Per-phase device timing with CUDA events on the trainer's stream (off by default).
+ * Phases: 0 gather, 1 fc7 forward, 2 rank-loss forward, 3 rank-loss backward, 4 wgrad,
+ * 5 dgrad, 6 allreduce (+slab reduce), 7 sgd update.  vv_trainer_phase_ms synchronises the
+ * stream, writes the summed milliseconds per phase and the number of timed steps, and resets. */
+#define VV_NUM_PHASES 8
+int vv_trainer_set_timing(vv_trainer_t* t, int enable);
+int vv_trainer_phase_ms(vv_trainer_t* t, float* ms_out /*[VV_NUM_PHASES]*/, int* steps_out);
 /* Inference / extraction: out[rows,N] = relu(F W^T + b) (ref: tools/extract_features.cpp:100-209
  * reading blob ip2 of videovec_extraction.prototxt:179-205). rows_op = operand copies of F rows. */
 int vv_trainer_extract(vv_trainer_t* t, const float* F, int64_t rows, float* out);

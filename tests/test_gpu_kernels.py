@@ -1,0 +1,342 @@
+"""Parity of the sm_100a kernels (through the C-ABI) against the CPU oracle and float64 references.
+
+Tolerances (north_star): indices / gathers bit-exact; fp32 paths (FP32_SIMT, TF32X3) within 1e-5
+relative of the oracle; TF32 / BF16 tensor-core paths within the stated loose bounds below.
+Relative error is max|a-b| / max|b| over the tensor (BLAS summation order is unspecified)."""
+import numpy as np
+import pytest
+import torch
+
+from videovector_b200 import ops
+from videovector_b200._lib import DROPOUT_MASK01, DROPOUT_MASK_U32, DROPOUT_NONE, DROPOUT_PHILOX
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32_simt": 1e-5, "tf32x3": 1e-5, "tf32": 4e-3, "bf16": 2e-2}
+TC = ["tf32x3", "tf32", "bf16"]
+ALL = ["fp32_simt"] + TC
+
+
+def rel(a, b):
+    a = a.double() if torch.is_tensor(a) else torch.as_tensor(a).double()
+    b = b.double() if torch.is_tensor(b) else torch.as_tensor(b).double()
+    a, b = a.cpu(), b.cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def cuda(a, dtype=None):
+    t = torch.as_tensor(a)
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda().contiguous()
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _device(vvlib):
+    assert vvlib.vv_device_check() == 0, vvlib.vv_last_error()
+    torch.cuda.set_device(0)
+
+
+# ------------------------------------------------------------------------------------------------
+# K0 gather + synthetic bank: bit-exact
+# ------------------------------------------------------------------------------------------------
+def test_bank_fill_bit_exact():
+    bank = ops.fill_bank(257, 64, 1234)
+    assert np.array_equal(bank.cpu().numpy(), ops.bank_host(257, 64, 1234))
+
+
+@pytest.mark.parametrize("prec", ALL)
+def test_gather_rows_bit_exact(oracle, prec):
+    rng = np.random.RandomState(5)
+    K, B, C, Nn = 64, 16, 5, 10
+    from test_sampler import make_dataset
+    video_id, shot_off, shot_ids, feat = make_dataset(rng, 80, 4, 20, K)
+    osmp = oracle.Sampler(video_id, shot_off, shot_ids, feat, K, B, C, Nn, 60, 50, 6, 100, seed=1)
+    batches = [osmp.next() for _ in range(4)]
+    osmp.close()
+    psmp = ops.Sampler(video_id, shot_off, shot_ids, B, C, Nn, 60, 50, 6, 100, rand_seed=1)
+    bank = cuda(feat)
+    for (oi, oq, data) in batches:
+        idx, quirk = psmp.next()
+        assert np.array_equal(idx, oi) and np.array_equal(quirk, oq)          # index stream bit-exact
+        X, op, blob = ops.gather_rows(bank, cuda(idx), cuda(quirk), prec, want_x=True, want_blob=True)
+        assert np.array_equal(blob.cpu().numpy(), data)                       # the data blob, K-1 quirk included
+        Xref = np.ascontiguousarray(data.transpose(1, 0, 2)).reshape((C + Nn) * B, K)   # slice dim1 + concat dim0
+        assert np.array_equal(X.cpu().numpy(), Xref)
+        if prec == "bf16":
+            assert torch.equal(op.hi, X.to(torch.bfloat16))
+        if prec == "tf32x3":
+            assert rel(op.hi.double() + op.lo.double(), X) < 2 ** -21
+            assert torch.equal(op.hi.view(torch.int32) & 0x1FFF, torch.zeros_like(op.hi, dtype=torch.int32))
+    psmp.close()
+
+
+def test_gather_no_quirk_pointer():
+    bank = ops.fill_bank(100, 32, 9)
+    idx = cuda(np.random.RandomState(0).randint(0, 100, (8, 6)).astype(np.int32))
+    X, _, _ = ops.gather_rows(bank, idx, None)
+    ref = bank[idx.long().t().reshape(-1)]
+    assert torch.equal(X, ref)
+
+
+# ------------------------------------------------------------------------------------------------
+# K1 GEMMs
+# ------------------------------------------------------------------------------------------------
+SHAPES = [(1920, 512, 4096),   # cfg-1: B=128, R=15
+          (128, 256, 64),      # exactly one tile, two k-blocks (bf16) / two (tf32)
+          (130, 264, 72),      # ragged M, N, K tails (TMA zero fill + predicated stores)
+          (200, 24, 40),       # smaller than one tile in every dimension
+          (1005, 1024, 512)]   # cfg-4 embedding width
+
+
+def _inputs(M, N, K, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    X = torch.relu(torch.randn(M, K, device="cuda", generator=g))
+    W = torch.randn(N, K, device="cuda", generator=g) * 0.05
+    b = torch.randn(N, device="cuda", generator=g) * 0.1
+    dZ = torch.randn(M, N, device="cuda", generator=g) * 0.01
+    return X, W, b, dZ
+
+
+@pytest.mark.parametrize("prec", ALL)
+@pytest.mark.parametrize("M,N,K", SHAPES)
+def test_ip_forward_plain(prec, M, N, K):
+    X, W, b, _ = _inputs(M, N, K)
+    H, _ = ops.ip_forward(ops.prepare_operand(X, prec), ops.prepare_operand(W, prec), b, M, N, K, prec)
+    ref = X.double() @ W.double().t() + b.double()
+    assert rel(H, ref) < TOL[prec], (prec, rel(H, ref))
+
+
+@pytest.mark.parametrize("prec", ALL)
+def test_ip_forward_matches_oracle_cfg1(oracle, prec):
+    M, N, K = 1920, 512, 4096
+    X, W, b, _ = _inputs(M, N, K, seed=3)
+    oracle.use_openblas(0)
+    ref = oracle.ip_forward(X.cpu().numpy(), W.cpu().numpy(), b.cpu().numpy())
+    oracle.use_builtin_blas()
+    H, _ = ops.ip_forward(ops.prepare_operand(X, prec), ops.prepare_operand(W, prec), b, M, N, K, prec)
+    assert rel(H, ref) < TOL[prec]
+
+
+@pytest.mark.parametrize("prec", ALL)
+@pytest.mark.parametrize("mode", [DROPOUT_NONE, DROPOUT_MASK01, DROPOUT_MASK_U32, DROPOUT_PHILOX])
+def test_ip_forward_fused_relu_dropout(oracle, prec, mode):
+    M, N, K = 256, 264, 96
+    ratio = 0.9
+    X, W, b, _ = _inputs(M, N, K, seed=1)
+    g = torch.Generator(device="cuda").manual_seed(11)
+    raw = torch.randint(0, 2 ** 32, (M, N), device="cuda", generator=g, dtype=torch.int64)   # u32 draws like curandGenerate
+    thres = oracle.lib().orc_dropout_uint_thres(np.float32(ratio))
+    mask = mask_out = None
+    keep = (raw > thres).to(torch.int32).contiguous()
+    if mode == DROPOUT_MASK01:
+        mask = keep
+    elif mode == DROPOUT_MASK_U32:
+        mask = torch.where(raw >= 2 ** 31, raw - 2 ** 32, raw).to(torch.int32).contiguous()   # raw u32 bit patterns
+    elif mode == DROPOUT_PHILOX:
+        mask_out = torch.zeros((M, N), dtype=torch.int32, device="cuda")
+        keep = ops.dropout_make_mask(M, N, ratio, 7, 5)
+    act = ops.make_act(relu=True, dropout_mode=mode, ratio=ratio, mask=mask, mask_out=mask_out, seed=7, step=5)
+    H, Z = ops.ip_forward(ops.prepare_operand(X, prec), ops.prepare_operand(W, prec), b, M, N, K, prec, act=act, want_z=True)
+    Zref = oracle.ip_forward(X.cpu().numpy(), W.cpu().numpy(), b.cpu().numpy())
+    assert rel(Z, Zref) < TOL[prec]
+    # activation applied to the kernel's own Z must follow the reference layers exactly
+    Href = oracle.relu_forward(Z.cpu().numpy())
+    if mode != DROPOUT_NONE:
+        Href = oracle.dropout_forward(Href, keep.cpu().numpy().astype(np.uint32), ratio)
+        if mode == DROPOUT_PHILOX:
+            assert torch.equal(mask_out, keep)
+            frac = keep.float().mean().item()
+            assert abs(frac - (1 - ratio)) < 0.01
+    assert np.array_equal(H.cpu().numpy(), Href)
+
+
+@pytest.mark.parametrize("prec", ALL)
+@pytest.mark.parametrize("M,N,K", SHAPES)
+def test_ip_wgrad(prec, M, N, K):
+    X, W, b, dZ = _inputs(M, N, K, seed=2)
+    dW = ops.ip_wgrad(ops.prepare_operand(dZ, prec), ops.prepare_operand(X, prec), M, N, K, prec)
+    ref = dZ.double().t() @ X.double()
+    assert rel(dW, ref) < TOL[prec], (prec, rel(dW, ref))
+
+
+@pytest.mark.parametrize("prec", ALL)
+@pytest.mark.parametrize("nsplit", [1, 2, 3])
+def test_ip_wgrad_explicit_splits_and_regularization(oracle, prec, nsplit):
+    M, N, K = 1920, 512, 4096
+    X, W, b, dZ = _inputs(M, N, K, seed=4)
+    dW = ops.ip_wgrad(ops.prepare_operand(dZ, prec), ops.prepare_operand(X, prec), M, N, K, prec,
+                      regularization=0.5, nsplit=nsplit)
+    oracle.use_openblas(0)
+    ref, db_ref, _ = oracle.ip_backward(dZ.cpu().numpy(), X.cpu().numpy(), W.cpu().numpy(), regularization=0.5)
+    oracle.use_builtin_blas()
+    assert rel(dW, ref) < TOL[prec]
+    db = ops.ip_bias_grad(dZ)
+    assert rel(db, db_ref) < 1e-5
+
+
+@pytest.mark.parametrize("prec", ALL)
+@pytest.mark.parametrize("M,N,K", SHAPES)
+def test_ip_dgrad(prec, M, N, K):
+    X, W, b, dZ = _inputs(M, N, K, seed=6)
+    dX = ops.ip_dgrad(ops.prepare_operand(dZ, prec), ops.prepare_operand(W, prec), M, N, K, prec)
+    ref = dZ.double() @ W.double()
+    assert rel(dX, ref) < TOL[prec], (prec, rel(dX, ref))
+
+
+def test_gemm_known_answers_on_device():
+    """The reference's GemmTest integers (test_util_blas.cpp:26-29) through the exact fp32 kernel."""
+    A = cuda(np.array([[1, 2, 3], [4, 5, 6]], np.float32))
+    Bm = cuda(np.arange(1, 13, dtype=np.float32).reshape(3, 4))
+    # C = A * B  as  X W^T with W = B^T
+    H, _ = ops.ip_forward(ops.OperandT(A), ops.OperandT(Bm.t().contiguous()), None, 2, 4, 3, "fp32_simt")
+    assert H.flatten().tolist() == [38, 44, 50, 56, 83, 98, 113, 128]
+
+
+# ------------------------------------------------------------------------------------------------
+# K2 / K3 fused rank loss vs the oracle net and vs float64 autograd
+# ------------------------------------------------------------------------------------------------
+def _rank_ref64(H, B, C, Nn, margin, norm, lw, dscale):
+    """float64 autograd on the GPU: d loss / d H and the fused-activation dZ."""
+    R = C + Nn
+    Hd = H.double().clone().requires_grad_(True)
+    Hs = Hd.reshape(R, B, -1)
+    a = float(np.float32(1.0 / (C - 1)))
+    cbar = sum(Hs[i] * a for i in range(1, C))
+
+    def l2n(x):
+        s = x.pow(2).sum(1, keepdim=True)
+        s = torch.where(s > 0, s, torch.ones_like(s))
+        return x / (s.sqrt() + 1e-10)
+    chat = l2n(cbar)
+    st = (chat * l2n(Hs[0])).sum(1, keepdim=True)
+    sn = torch.stack([(chat * l2n(Hs[C + k])).sum(1) for k in range(Nn)], 1)
+    h = torch.clamp(margin - (st - sn), min=0)
+    loss = (h.pow(2) if norm == 2 else h.abs()).sum() / (B * Nn)
+    (loss * lw).backward()
+    dZ = Hd.grad * dscale * (H > 0)
+    return loss.item(), float((st - sn < 0).sum().item()), st.detach(), sn.detach(), Hd.grad, dZ
+
+
+RANK_CASES = [(128, 5, 10, 512, 2), (64, 17, 50, 1024, 2), (37, 3, 4, 64, 1), (16, 5, 10, 4096, 2), (9, 7, 5, 200, 2)]
+
+
+@pytest.mark.parametrize("B,C,Nn,N,norm", RANK_CASES)
+def test_rank_loss_forward_backward(B, C, Nn, N, norm):
+    R = C + Nn
+    g = torch.Generator(device="cuda").manual_seed(B)
+    H = torch.relu(torch.randn(R * B, N, device="cuda", generator=g))
+    H = H * (torch.rand(R * B, N, device="cuda", generator=g) < 0.3) * 3.0      # sparse like dropout
+    H[5] = 0.0                                                                   # an all-zero row
+    H = H.contiguous()
+    cfg = ops.rank_cfg(B, C, Nn, N, margin=2.0, norm=norm)
+    out = ops.rank_loss_forward(H, cfg)
+    loss, viol, st, sn, dH_ref, dZ_ref = _rank_ref64(H, B, C, Nn, 2.0, norm, 1.0, 10.0)
+    assert abs(out["loss"].item() - loss) < 1e-5 * max(1, abs(loss))
+    assert out["violations"].item() == viol
+    assert rel(out["target_score"], st.expand(-1, Nn)) < 1e-5 and rel(out["neg_score"], sn) < 1e-5
+    dH, _, _ = ops.rank_loss_backward(H, cfg, out["stats"], 1.0, act_fused=False, want_db=False)
+    assert rel(dH, dH_ref) < 1e-5, rel(dH, dH_ref)
+    dZ, _, db = ops.rank_loss_backward(H, cfg, out["stats"], 1.0, act_fused=True, dropout_scale=10.0)
+    assert rel(dZ, dZ_ref) < 1e-5
+    assert rel(db, dZ_ref.sum(0)) < 1e-5
+
+
+@pytest.mark.parametrize("prec", ["tf32x3", "bf16"])
+def test_rank_loss_backward_operand_copies(prec):
+    B, C, Nn, N = 32, 5, 10, 512
+    H = torch.relu(torch.randn((C + Nn) * B, N, device="cuda")).contiguous()
+    cfg = ops.rank_cfg(B, C, Nn, N)
+    out = ops.rank_loss_forward(H, cfg)
+    dZ, op, _ = ops.rank_loss_backward(H, cfg, out["stats"], 1.0, True, 10.0, prec=prec)
+    if prec == "bf16":
+        assert torch.equal(op.hi, dZ.to(torch.bfloat16))
+    else:
+        assert rel(op.hi.double() + op.lo.double(), dZ) < 2 ** -21
+
+
+# ------------------------------------------------------------------------------------------------
+# K4 update
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("reg_type", [2, 1])
+@pytest.mark.parametrize("count", [512 * 4096, 515])
+def test_sgd_update_matches_oracle(oracle, reg_type, count):
+    rng = np.random.RandomState(count)
+    W = rng.normal(0, 0.01, count).astype(np.float32)
+    g = rng.normal(0, 0.1, (3, count)).astype(np.float32)
+    h = rng.normal(0, 0.001, count).astype(np.float32)
+    Wd, hd, gd = cuda(W), cuda(h), cuda(g)
+    diff = torch.empty_like(Wd)
+    ops.sgd_update(Wd, gd, hd, 2e-3, 0.9, 5e-4, reg_type=reg_type, grad_scale=0.5, diff_out=diff)
+    Wr, dr, hr = oracle.sgd_update(W, 0.5 * g.sum(0), h, 2e-3, 0.9, 5e-4, reg_type)
+    assert rel(Wd, Wr) < 1e-6 and rel(hd, hr) < 1e-6 and rel(diff, dr) < 1e-6
+
+
+@pytest.mark.parametrize("prec", ["tf32x3", "bf16"])
+def test_sgd_update_refreshes_operand_copies(prec):
+    count = 64 * 128
+    W = torch.randn(count, device="cuda") * 0.01
+    g = torch.randn(count, device="cuda")
+    h = torch.zeros(count, device="cuda")
+    Wop = ops.alloc_operand((count,), prec)
+    ops.sgd_update(W, g, h, 1e-2, 0.9, 0.0, prec=prec, Wop=Wop)
+    if prec == "bf16":
+        assert torch.equal(Wop.hi, W.to(torch.bfloat16))
+    else:
+        assert rel(Wop.hi.double() + Wop.lo.double(), W) < 2 ** -21
+
+
+# ------------------------------------------------------------------------------------------------
+# standalone layer kernels vs the oracle's layer restatements
+# ------------------------------------------------------------------------------------------------
+def test_standalone_layers_match_oracle(vvlib, oracle):
+    from videovector_b200.ops import _ptr, _stream
+    from videovector_b200._lib import check
+    import ctypes as C
+    rng = np.random.RandomState(1)
+    x = rng.normal(0, 1, (33, 77)).astype(np.float32); dy = rng.normal(0, 1, (33, 77)).astype(np.float32)
+    xd, dyd = cuda(x), cuda(dy)
+    y = torch.empty_like(xd)
+    check(vvlib.vv_relu_forward(_ptr(xd), xd.numel(), 0.1, _ptr(y), _stream()))
+    assert np.array_equal(y.cpu().numpy(), oracle.relu_forward(x, 0.1))
+    check(vvlib.vv_relu_backward(_ptr(xd), _ptr(dyd), xd.numel(), 0.1, _ptr(y), _stream()))
+    assert np.allclose(y.cpu().numpy(), oracle.relu_backward(x, dy, 0.1), rtol=1e-7)
+    check(vvlib.vv_l2norm_forward(_ptr(xd), 33, 77, _ptr(y), _stream()))
+    assert rel(y, oracle.normalization_forward(x)) < 1e-6
+    check(vvlib.vv_l2norm_backward(_ptr(xd), _ptr(dyd), 33, 77, _ptr(y), _stream()))
+    assert rel(y, oracle.normalization_backward(x, dy)) < 1e-5
+    s = torch.empty((33, 10), device="cuda")
+    check(vvlib.vv_rowsum_forward(_ptr(xd), 33, 77, 10, _ptr(s), _stream()))
+    assert rel(s, oracle.sum_forward(x, 10)) < 1e-6
+    ds = cuda(rng.normal(0, 1, (33, 10)).astype(np.float32))
+    check(vvlib.vv_rowsum_backward(_ptr(ds), 33, 77, 10, _ptr(y), _stream()))
+    assert rel(y, oracle.sum_backward(ds.cpu().numpy(), 77)) < 1e-6
+    m = (rng.uniform(0, 1, x.shape) < 0.5).astype(np.uint32)
+    md = cuda(m.astype(np.int32))
+    check(vvlib.vv_dropout_forward(_ptr(xd), _ptr(md), DROPOUT_MASK01, xd.numel(), 0.5, _ptr(y), _stream()))
+    assert np.array_equal(y.cpu().numpy(), oracle.dropout_forward(x, m, 0.5))
+    t = cuda(rng.normal(0, 10, (10, 5)).astype(np.float32)); b = cuda(rng.normal(0, 10, (10, 5)).astype(np.float32))
+    loss = torch.zeros(1, device="cuda"); viol = torch.zeros(1, device="cuda"); hinge = torch.zeros(50, device="cuda")
+    for norm in (1, 2):
+        check(vvlib.vv_max_margin_forward(_ptr(t), _ptr(b), 50, 1.0, norm, _ptr(hinge), _ptr(loss), _ptr(viol), _stream()))
+        lr, vr, _ = oracle.max_margin_forward(t.cpu().numpy(), b.cpu().numpy(), 1.0, norm)
+        assert abs(loss.item() - lr) < 1e-5 * max(1, abs(lr)) and viol.item() == vr
+        dt = torch.zeros_like(t); dbg = torch.zeros_like(t)
+        check(vvlib.vv_max_margin_backward(_ptr(t), _ptr(b), 50, 1.0, norm, 1.0, _ptr(dt), _ptr(dbg), _stream()))
+        rt, rb = oracle.max_margin_backward(t.cpu().numpy(), b.cpu().numpy(), 1.0, norm, 1.0)
+        assert rel(dt, rt) < 1e-6 and rel(dbg, rb) < 1e-6
+    bots = [cuda(rng.normal(0, 1, (5, 9)).astype(np.float32)) for _ in range(4)]
+    ptrs = (C.c_void_p * 4)(*[t_.data_ptr() for t_ in bots]); co = (C.c_float * 4)(0.25, 0.25, 0.25, 0.25)
+    top = torch.empty_like(bots[0])
+    check(vvlib.vv_eltwise_sum_forward(ptrs, co, 4, 45, _ptr(top), _stream()))
+    assert rel(top, oracle.eltwise_sum_forward([t_.cpu().numpy() for t_ in bots], [0.25] * 4)) < 1e-6
+
+
+def test_errors_are_loud(vvlib):
+    """Bad arguments return an error code and a message; nothing falls back to the CPU."""
+    X = torch.zeros((8, 12), device="cuda")
+    with pytest.raises(Exception):
+        ops.ip_forward(ops.OperandT(X), ops.OperandT(X), None, 8, 8, 12, "bf16")     # K % 8 != 0 on the TC path
+    assert "K" in vvlib.vv_last_error().decode() or "tensor-core" in vvlib.vv_last_error().decode()
+    with pytest.raises(Exception):
+        ops.rank_loss_forward(torch.zeros((15, 6), device="cuda"), ops.rank_cfg(1, 5, 10, 6))   # N % 4 != 0

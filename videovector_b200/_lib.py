@@ -105,6 +105,8 @@ SIGNATURES = {
     "vv_trainer_sync_weights": (_i, [_P]),
     "vv_trainer_step": (_i, [_P, _P, _i64, _P, _P, _P, _i, _i]),
     "vv_trainer_last_launches": (_i, [_P]),
+    "vv_trainer_set_timing": (_i, [_P, _i]),
+    "vv_trainer_phase_ms": (_i, [_P, _P, _P]),
     "vv_trainer_extract": (_i, [_P, _P, _i64, _P]),
     "vv_dp_unique_id": (_i, [_P]),
     "vv_dp_init": (_i, [_P, _P]),

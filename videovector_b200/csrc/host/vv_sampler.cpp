@@ -19,36 +19,44 @@
 #include <cstdint>
 #include <cstring>
 #include <numeric>
-#include <unordered_set>
+#include <unordered_map>
 #include <vector>
 #include "vv_b200.h"
 
 struct vv_glibc_rand {
-  int32_t state[31];
-  int f, r;
+  // glibc TYPE_3 (random_r): with state r[0..30], fptr = &r[3], rptr = &r[0], draw k does
+  // r[f] += r[q] and returns r[f] >> 1.  Unrolled onto a linear array L with
+  // L[j] = r[(j + 3) % 31] for j < 31 this is  L[i] = L[i-31] + L[i-3]  and draw k = L[31 + k].
+  // srandom_r discards the first 310 draws.  Outputs are produced in blocks so next() is a load.
+  static constexpr int kBlock = 2048;
+  uint32_t buf[31 + kBlock];
+  int pos;
   explicit vv_glibc_rand(unsigned int seed) { reseed(seed); }
   void reseed(unsigned int seed) {
     if (seed == 0) seed = 1;
-    state[0] = int32_t(seed);
-    int32_t word = int32_t(seed);
+    int32_t r[31];
+    r[0] = int32_t(seed);
     for (int i = 1; i < 31; ++i) {
-      // 16807 * word % 2147483647 without overflow (Schrage), as glibc's srandom_r
-      const long hi = word / 127773, lo = word % 127773;
+      // 16807 * r[i-1] % 2147483647 without overflow (Schrage), as glibc's srandom_r
+      const long hi = r[i - 1] / 127773, lo = r[i - 1] % 127773;
       long w = 16807 * lo - 2836 * hi;
       if (w < 0) w += 2147483647;
-      word = int32_t(w);
-      state[i] = word;
+      r[i] = int32_t(w);
     }
-    f = 3; r = 0;
-    for (int k = 0; k < 310; ++k) next();
+    for (int j = 0; j < 31; ++j) buf[j] = uint32_t(r[(j + 3) % 31]);
+    generate();
+    pos = 31 + 310;
+  }
+  void generate() {
+    for (int i = 31; i < 31 + kBlock; ++i) buf[i] = buf[i - 31] + buf[i - 3];
   }
   int next() {
-    const uint32_t val = uint32_t(state[f]) + uint32_t(state[r]);
-    state[f] = int32_t(val);
-    const int result = int(val >> 1);
-    if (++f >= 31) { f = 0; ++r; }
-    else if (++r >= 31) r = 0;
-    return result;
+    if (pos >= 31 + kBlock) {
+      for (int i = 0; i < 31; ++i) buf[i] = buf[kBlock + i];
+      generate();
+      pos = 31;
+    }
+    return int(buf[pos++] >> 1);
   }
 };
 
@@ -56,6 +64,19 @@ namespace {
 inline uint64_t shot_key(int video_id, int shot_id) {
   return (uint64_t(uint32_t(video_id)) << 32) | uint32_t(shot_id);
 }
+// x % d for 32-bit x without a hardware divide (Lemire's fastmod, exact for all 32-bit x, d):
+// the sampler draws ~90 rand() % n per item and the divides dominated its cost.
+struct FastMod {
+  std::vector<uint64_t> magic;   // magic[d] = 2^64 / d + 1 for d < size
+  explicit FastMod(int max_d) : magic(size_t(max_d) + 1, 0) {
+    for (int d = 1; d <= max_d; ++d) magic[d] = ~uint64_t(0) / uint64_t(d) + 1;
+  }
+  inline int mod(int x, int d) const {
+    if (size_t(d) >= magic.size()) return x % d;
+    const uint64_t low = magic[d] * uint64_t(uint32_t(x));
+    return int((static_cast<unsigned __int128>(low) * uint64_t(d)) >> 64);
+  }
+};
 }  // namespace
 
 struct vv_sampler {
@@ -65,16 +86,20 @@ struct vv_sampler {
   int cursor;
   std::vector<float> buffer_ids;          // persistent permutation, float like the reference (:81-83)
   std::vector<int32_t> neg_row;           // buffer slot -> bank row currently held
-  std::vector<uint64_t> slot_key;         // negative_id_to_key_
-  std::unordered_set<uint64_t> key_set;   // negative_keys_set_
+  // "video_id:shot_id" keys (negative_id_to_key_ / negative_keys_set_) as dense ids:
+  // key_of[g] = id of the key of global shot g (equal keys share an id), so the set is a bitmap.
+  std::vector<int32_t> key_of;            // [num_shots]
+  std::vector<int32_t> slot_key;          // buffer slot -> key id
+  std::vector<uint8_t> in_set;            // [num_keys] membership
   std::vector<int32_t> last_full;         // [B,R] bank row of the last full-row write per slot, -1 = none
-  vv_sampler(unsigned seed) : rng(seed), cursor(0) {}
+  FastMod fm;
+  vv_sampler(unsigned seed, int max_d) : rng(seed), cursor(0), fm(max_d) {}
 
   // random_unique over a range (rng.hpp:43-54)
   template <class T> void random_unique(T* first, int n, int num_random) {
     int left = n;
     while (num_random--) {
-      std::swap(*first, first[rng.next() % left]);
+      std::swap(*first, first[fm.mod(rng.next(), left)]);
       ++first; --left;
     }
   }
@@ -85,9 +110,10 @@ struct vv_sampler {
       cursor = (cursor + 1) % V;
       const int n = shot_off[v + 1] - shot_off[v];
       if (n <= 0) return false;
-      const int s = rng.next() % n;
-      const uint64_t key = shot_key(video_id[v], shot_ids[shot_off[v] + s]);
-      if (key_set.insert(key).second) {
+      const int s = fm.mod(rng.next(), n);
+      const int32_t key = key_of[shot_off[v] + s];
+      if (!in_set[key]) {
+        in_set[key] = 1;
         neg_row[added] = shot_off[v] + s;
         slot_key[added] = key;
         ++added;
@@ -122,7 +148,7 @@ struct vv_sampler {
       int added = 0;
       if (Nn > 0 && n > C) {                              // same-video negatives :479-503
         for (int i = C + 1; i < n; ++i) {                 // std::random_shuffle(ids+C, end)
-          const int j = C + rng.next() % (i - C + 1);
+          const int j = C + fm.mod(rng.next(), i - C + 1);
           if (i != j) std::swap(ids[i], ids[j]);
         }
         for (int nid = C; nid < n && added < max_same; ++nid) {
@@ -144,14 +170,14 @@ struct vv_sampler {
       ++item;
       if (Nn > 0 && swap_pct > 0) {                       // swap this record's shots into the buffer :888-906
         for (int j = 0; j < n; ++j) {
-          const uint64_t key = shot_key(video_id[v], shot_ids[off + j]);
-          if (key_set.find(key) == key_set.end()) {
-            if ((rng.next() % 100) < swap_pct) {          // AddToBuffer :25-37
-              const int pos = rng.next() % P;
+          const int32_t key = key_of[off + j];
+          if (!in_set[key]) {
+            if (fm.mod(rng.next(), 100) < swap_pct) {          // AddToBuffer :25-37
+              const int pos = fm.mod(rng.next(), P);
               neg_row[pos] = off + j;
-              key_set.erase(slot_key[pos]);
+              in_set[slot_key[pos]] = 0;
               slot_key[pos] = key;
-              key_set.insert(key);
+              in_set[key] = 1;
             }
           }
         }
@@ -170,7 +196,10 @@ extern "C" vv_sampler_t* vv_sampler_create(int num_videos, const int32_t* video_
       (context_size % 2) != 1 || num_negative_samples < 0 || negative_swap_percentage < 0 ||
       negative_swap_percentage > 99 || (num_negative_samples > 0 && max_buffer_size < num_negative_samples))
     return nullptr;
-  vv_sampler* s = new vv_sampler(rand_seed);
+  int max_d = max_buffer_size > 100 ? max_buffer_size : 100;
+  for (int v = 0; v < num_videos; ++v) max_d = std::max(max_d, shot_off[v + 1] - shot_off[v]);
+  if (max_d > (1 << 20)) max_d = 1 << 20;
+  vv_sampler* s = new vv_sampler(rand_seed, max_d);
   s->V = num_videos; s->B = batch_size; s->C = context_size; s->Nn = num_negative_samples;
   s->P = num_negative_samples > 0 ? max_buffer_size : 0;
   s->swap_pct = negative_swap_percentage; s->max_same = max_same_video_negs;
@@ -181,6 +210,18 @@ extern "C" vv_sampler_t* vv_sampler_create(int num_videos, const int32_t* video_
   for (int i = 0; i < s->P; ++i) s->buffer_ids[i] = float(i);
   s->neg_row.assign(s->P, -1);
   s->slot_key.assign(s->P, 0);
+  {
+    const int total = shot_off[num_videos];
+    std::unordered_map<uint64_t, int32_t> ids;
+    ids.reserve(size_t(total) * 2);
+    s->key_of.resize(total);
+    for (int v = 0; v < num_videos; ++v)
+      for (int g = shot_off[v]; g < shot_off[v + 1]; ++g) {
+        auto it = ids.emplace(shot_key(video_id[v], shot_ids[g]), int32_t(ids.size()));
+        s->key_of[g] = it.first->second;
+      }
+    s->in_set.assign(ids.size(), 0);
+  }
   s->last_full.assign((size_t)batch_size * (context_size + num_negative_samples), -1);
   if (s->P > 0 && !s->init(max_tries_for_negs)) { delete s; return nullptr; }
   return s;

@@ -75,6 +75,17 @@ struct vv_trainer {
   DevBuf Xf, X_hi, X_lo, Zf, H, stats, item_loss, item_viol, dZf, dZ_hi, dZ_lo, dW_parts, dbx, dX;
   ncclComm_t comm = nullptr;
   int last_launches = 0;
+  // optional per-phase timing
+  bool timing = false;
+  std::vector<cudaEvent_t> ev_pool;      // [step][phase][2]
+  int timed_steps = 0;
+  cudaEvent_t* phase_events(int phase) {
+    const size_t base = (size_t(timed_steps) * VV_NUM_PHASES + phase) * 2;
+    while (ev_pool.size() < base + 2) { cudaEvent_t e; cudaEventCreate(&e); ev_pool.push_back(e); }
+    return &ev_pool[base];
+  }
+  void tic(int phase) { if (timing) cudaEventRecord(phase_events(phase)[0], stream); }
+  void toc(int phase) { if (timing) cudaEventRecord(phase_events(phase)[1], stream); }
 
   vv_operand_t opX() const { return op(Xf, X_hi, X_lo); }
   vv_operand_t opW() const { return op(W, W_hi, W_lo); }
@@ -126,6 +137,7 @@ struct vv_trainer {
     DevBuf* all[] = {&W, &b, &Wh, &bh, &W_hi, &W_lo, &Xf, &X_hi, &X_lo, &Zf, &H, &stats, &item_loss, &item_viol,
                      &dZf, &dZ_hi, &dZ_lo, &dW_parts, &dbx, &dX};
     for (DevBuf* d : all) d->release();
+    for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
     if (ev_grad) cudaEventDestroy(ev_grad);
     if (ev_comm) cudaEventDestroy(ev_comm);
     if (comm_stream) cudaStreamDestroy(comm_stream);
@@ -186,9 +198,12 @@ extern "C" int vv_trainer_step(vv_trainer_t* t, const float* bank, int64_t bank_
   const int64_t NK = int64_t(N) * K;
   int rc;
   launches_reset();
+  if (t->timing && t->timed_steps >= 256) { set_error("timing: read vv_trainer_phase_ms at least every 256 steps"); return VV_ERR_INVALID; }
   // K0
+  t->tic(0);
   if ((rc = vv_gather_rows(bank, bank_rows, K, idx, quirk, c.B, t->R, t->Xf.as<float>(), t->X_hi.p, t->X_lo.p, c.prec,
                            nullptr, s))) return rc;
+  t->toc(0);
   // K1 forward with fused bias + ReLU + dropout
   vv_act_t act; memset(&act, 0, sizeof(act));
   act.relu = 1; act.negative_slope = 0.f;
@@ -198,26 +213,37 @@ extern "C" int vv_trainer_step(vv_trainer_t* t, const float* bank, int64_t bank_
   if (has_dropout && (act.dropout_mode == VV_DROPOUT_MASK01 || act.dropout_mode == VV_DROPOUT_MASK_U32) && !mask) {
     set_error("trainer: dropout mask mode needs a mask"); return VV_ERR_INVALID;
   }
+  t->tic(1);
   if ((rc = vv_ip_forward(t->opX(), t->opW(), t->b.as<float>(), M, N, K, c.prec, &act, t->Zf.as<float>(),
                           t->H.as<float>(), s))) return rc;
+  t->toc(1);
   // K2
+  t->tic(2);
   if ((rc = vv_rank_loss_forward(t->H.as<float>(), &t->rank, t->stats.as<float>(), nullptr, nullptr,
                                  t->item_loss.as<float>(), t->item_viol.as<float>(), t->loss_ptr(), t->viol_ptr(), s))) return rc;
+  t->toc(2);
   // K3 (+ bias gradient)
+  t->tic(3);
   VV_CUDA(cudaMemsetAsync(t->dbx.p, 0, size_t(N) * 4, t->stream));
   count_launch();
   const float dscale = has_dropout ? dropout_scale(c.dropout_ratio) : 1.f;
   if ((rc = vv_rank_loss_backward(t->H.as<float>(), &t->rank, t->stats.as<float>(), c.loss_weight, 1, dscale,
                                   t->dZf.as<float>(), t->dZ_hi.p, t->dZ_lo.p, c.prec, t->dbx.as<float>(), s))) return rc;
+  t->toc(3);
   // K1 wgrad into split-K slabs
+  t->tic(4);
   if ((rc = vv_ip_wgrad(t->opdZ(), t->opX(), M, N, K, c.prec, c.regularization, t->dW_parts.as<float>(), t->nsplit,
                         nullptr, 0, s))) return rc;
+  t->toc(4);
   if (c.compute_dgrad) {
+    t->tic(5);
     if ((rc = vv_ip_dgrad(t->opdZ(), t->opW(), M, N, K, c.prec, t->dX.as<float>(), s))) return rc;
+    t->toc(5);
   }
   int nparts = t->nsplit;
   float gscale = 1.f;
   if (c.world_size > 1) {
+    t->tic(6);
     if (!t->comm) { set_error("trainer: world_size > 1 but vv_dp_init was not called"); return VV_ERR_NCCL; }
     if (nparts > 1) {
       if ((rc = vv_reduce_parts(t->dW_parts.as<float>(), nparts, NK, NK, t->dW_parts.as<float>(), s))) return rc;
@@ -232,8 +258,10 @@ extern "C" int vv_trainer_step(vv_trainer_t* t, const float* bank, int64_t bank_
     VV_CUDA(cudaStreamWaitEvent(t->stream, t->ev_comm, 0));
     count_launch(2);
     gscale = 1.f / float(c.world_size);
+    t->toc(6);
   }
   if (do_update) {
+    t->tic(7);
     // ref: solver.cpp:486-576 + net.cpp:804-839; weight then bias (net.params() order)
     const float rate = vv_learning_rate(c.lr_policy, c.base_lr, c.gamma, c.power, c.stepsize, iter);
     if (rate < 0.f) return VV_ERR_INVALID;
@@ -247,10 +275,36 @@ extern "C" int vv_trainer_step(vv_trainer_t* t, const float* bank, int64_t bank_
       // loss/violations were summed over ranks: loss -> mean over ranks (global-batch mean)
       if ((rc = vv_axpby(1, gscale, t->loss_ptr(), 0.f, t->loss_ptr(), s))) return rc;
     }
+    t->toc(7);
   } else if (nparts > 1) {
     if ((rc = vv_reduce_parts(t->dW_parts.as<float>(), nparts, NK, NK, t->dW_parts.as<float>(), s))) return rc;
   }
   t->last_launches = launches_reset();
+  if (t->timing) ++t->timed_steps;
+  return VV_OK;
+}
+
+extern "C" int vv_trainer_set_timing(vv_trainer_t* t, int enable) {
+  if (!t) return VV_ERR_INVALID;
+  t->timing = enable != 0; t->timed_steps = 0;
+  return VV_OK;
+}
+extern "C" int vv_trainer_phase_ms(vv_trainer_t* t, float* ms_out, int* steps_out) {
+  if (!t || !ms_out) return VV_ERR_INVALID;
+  VV_CUDA(cudaStreamSynchronize(t->stream));
+  for (int p = 0; p < VV_NUM_PHASES; ++p) ms_out[p] = 0.f;
+  const bool has_dgrad = t->cfg.compute_dgrad != 0, has_comm = t->cfg.world_size > 1;
+  for (int sidx = 0; sidx < t->timed_steps; ++sidx)
+    for (int p = 0; p < VV_NUM_PHASES; ++p) {
+      if ((p == 5 && !has_dgrad) || (p == 6 && !has_comm)) continue;
+      const size_t base = (size_t(sidx) * VV_NUM_PHASES + p) * 2;
+      if (base + 1 >= t->ev_pool.size()) continue;
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, t->ev_pool[base], t->ev_pool[base + 1]) == cudaSuccess) ms_out[p] += ms;
+      else cudaGetLastError();
+    }
+  if (steps_out) *steps_out = t->timed_steps;
+  t->timed_steps = 0;
   return VV_OK;
 }
 

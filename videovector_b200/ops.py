@@ -315,8 +315,8 @@ class Trainer:
             return _device_view(fn(self._h), shape)
         shapes = {"X": (self.M, K), "Z": (self.M, N), "H": (self.M, N), "dZ": (self.M, N),
                   "stats": (B, 1 + 2 * (1 + self.cfg.Nn)), "loss": (1,), "violations": (1,),
-                  "dW_raw": (N, K), "db_raw": (N,), "dX": (self.M, K)}
-        ptr = L.vv_trainer_blob(self._h, which.encode())
+                  "dW_raw": (N, K), "db_raw": (N,), "dX": (self.M, K), "db_raw_ext": (N + 2,)}
+        ptr = L.vv_trainer_blob(self._h, (b"db_raw" if which == "db_raw_ext" else which.encode()))
         if not ptr:
             raise VVError("trainer blob %s is not allocated in this configuration" % which)
         return _device_view(ptr, shapes[which])
@@ -338,6 +338,20 @@ class Trainer:
     @property
     def last_launches(self):
         return self._lib.vv_trainer_last_launches(self._h)
+
+    PHASES = ("gather", "fc7_forward", "rank_loss_forward", "rank_loss_backward", "wgrad", "dgrad", "allreduce",
+              "sgd_update")
+
+    def set_timing(self, enable):
+        check(self._lib.vv_trainer_set_timing(self._h, int(enable)))
+
+    def phase_ms(self):
+        """(dict phase -> mean ms per step, number of timed steps) since the last call."""
+        ms = (C.c_float * 8)()
+        n = C.c_int(0)
+        check(self._lib.vv_trainer_phase_ms(self._h, C.addressof(ms), C.addressof(n)))
+        steps = max(n.value, 1)
+        return {name: ms[i] / steps for i, name in enumerate(self.PHASES)}, n.value
 
     def dp_init(self, id_bytes):
         buf = (C.c_char * 128).from_buffer_copy(id_bytes)
