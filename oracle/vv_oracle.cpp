@@ -675,6 +675,7 @@ void* orc_sampler_create(int V, int K, const int* video_id, const int* shot_off,
                          int batch_size, int context_size, int num_negative_samples,
                          int max_buffer_size, int negative_swap_percentage,
                          int max_same_video_negs, int max_tries_for_negs) {
+  if (max_same_video_negs > num_negative_samples) return nullptr;   // undefined in the reference (slot overflow)
   OrcSampler* s = new OrcSampler();
   s->V = V; s->K = K; s->B = batch_size; s->C = context_size; s->Nn = num_negative_samples;
   s->P = num_negative_samples > 0 ? max_buffer_size : 0;

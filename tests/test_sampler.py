@@ -35,7 +35,7 @@ CASES = [
     (300, 1, 12, 16, 5, 10, 50, 50, 6),     # many records skipped (n < C), ragged shot counts
     (200, 6, 40, 32, 5, 10, 100, 50, 6),    # the shipped parameters at small buffer
     (120, 18, 30, 8, 17, 50, 400, 50, 6),   # cfg-4: window +-8, 50 negatives
-    (150, 3, 9, 8, 3, 4, 30, 0, 2),         # no swapping
+    (150, 3, 9, 8, 3, 4, 30, 0, 2),         # no swapping, max_same < default
     (150, 5, 9, 8, 5, 6, 40, 99, 6),        # n == C records (no same-video negatives), heavy swapping
     (64, 8, 8, 128, 5, 10, 60, 50, 6),      # cursor wraps several times per batch
 ]
@@ -86,6 +86,8 @@ def test_sampler_rejects_bad_parameters(vvlib):
         ops.Sampler(video_id, shot_off, shot_ids, 4, max_buffer_size=5000)        # cannot find 5000 unique shots (CHECK_EQ :346)
     with pytest.raises(Exception):
         ops.Sampler(video_id, shot_off, shot_ids, 4, negative_swap_percentage=100, max_buffer_size=20)
+    with pytest.raises(Exception):   # more same-video negatives than negative slots: slot overflow in the reference
+        ops.Sampler(video_id, shot_off, shot_ids, 4, num_negative_samples=4, max_same_video_negs=6, max_buffer_size=20)
 
 
 def test_synthetic_bank_hash_host_matches_numpy(vvlib):

@@ -194,7 +194,10 @@ extern "C" vv_sampler_t* vv_sampler_create(int num_videos, const int32_t* video_
                                            int max_tries_for_negs, unsigned int rand_seed) {
   if (num_videos <= 0 || !video_id || !shot_off || !shot_ids || batch_size < 1 || context_size < 2 ||
       (context_size % 2) != 1 || num_negative_samples < 0 || negative_swap_percentage < 0 ||
-      negative_swap_percentage > 99 || (num_negative_samples > 0 && max_buffer_size < num_negative_samples))
+      negative_swap_percentage > 99 || (num_negative_samples > 0 && max_buffer_size < num_negative_samples) ||
+      // the reference writes max_same_video_negs slots unconditionally (:483-499) and then draws
+      // Nn - added buffer negatives; more same-video negatives than slots is undefined there, an error here
+      max_same_video_negs < 0 || max_same_video_negs > num_negative_samples)
     return nullptr;
   int max_d = max_buffer_size > 100 ? max_buffer_size : 100;
   for (int v = 0; v < num_videos; ++v) max_d = std::max(max_d, shot_off[v + 1] - shot_off[v]);

@@ -4,7 +4,7 @@
 //   warp 0   : TMA producer  (cp.async.bulk.tensor 2D tiles, SWIZZLE_128B, mbarrier tx)
 //   warp 1   : MMA issuer    (tcgen05.mma cta_group::1, 128 x BLOCK_N x (32 B of K), fp32 accum in TMEM)
 //   warp 2   : TMEM allocator
-//   warps 4-7: epilogue      (tcgen05.ld 32x32b -> bias / ReLU / dropout / scale -> global)
+//   warps 4-11: epilogue     (tcgen05.ld 32x32b -> bias / ReLU / dropout / scale -> global)
 // Two TMEM accumulator buffers (2 x BLOCK_N columns) let the epilogue of tile i
 // overlap the main loop of tile i+1.
 //
@@ -24,12 +24,13 @@ namespace {
 
 constexpr int kBlockM = 128;
 constexpr int kRowBytes = 128;            // bytes of the contiguous dim per smem row (= swizzle span)
-constexpr int kNumThreads = 256;
+constexpr int kNumThreads = 384;          // 4 control warps + 8 epilogue warps
 
 struct TcParams {
   int d_rows, d_cols, ldd;      // output extent and row pitch
   int tiles_m, tiles_n, nsplit;
   int num_kb, kb_per_split;     // k-blocks (of kRowBytes worth of elements)
+  int chunk_kb;                 // k-blocks accumulated in TMEM before promotion to fp32 registers
   float* D; long long slab_stride;
   int act_N;                    // row pitch of mask/Z (= N of the layer) for the FWD epilogue
   GemmEpilogue epi;
@@ -40,6 +41,7 @@ struct Cfg {
   static constexpr bool tf32 = kTF32;
   static constexpr bool a_mn = kAMN, b_mn = kBMN;
   static constexpr int nprod = kNProd;                 // 1 or 3
+  static constexpr bool promote = (kNProd == 3);        // chunked TMEM accumulation + fp32 register sums
   static constexpr int parts = (kNProd == 3) ? 2 : 1;  // hi (+ lo)
   static constexpr int block_n = kBlockN;
   static constexpr int stages = kStages;
@@ -81,7 +83,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 8); }
     fence_barrier_init();
   }
   if (warp == 2) { tmem_alloc(tmem_slot, C::tmem_cols); tmem_relinquish(); }
@@ -146,71 +148,100 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       constexpr uint32_t lbo_b = C::b_mn ? C::bk * kRowBytes : 16;
       constexpr uint32_t kadv_a = C::a_mn ? C::umma_k * kRowBytes : 32;   // bytes per k-step
       constexpr uint32_t kadv_b = C::b_mn ? C::umma_k * kRowBytes : 32;
+      // MN-major tf32 must use the 32-byte-chunk swizzle: atoms of 4 k-rows (512 B) instead of 8 (1024 B)
+      constexpr uint32_t lay_a = (C::tf32 && C::a_mn) ? kLayoutSw128Base32 : kLayoutSw128;
+      constexpr uint32_t lay_b = (C::tf32 && C::b_mn) ? kLayoutSw128Base32 : kLayoutSw128;
+      constexpr uint32_t sbo_a = (C::tf32 && C::a_mn) ? 512 : 1024;
+      constexpr uint32_t sbo_b = (C::tf32 && C::b_mn) ? 512 : 1024;
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
         const int split = u / tiles_mn;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + uint32_t(acc * C::block_n);
-        uint32_t accumulate = 0;
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+        // The k-range is issued in chunks of p.chunk_kb k-blocks, each into its own TMEM buffer
+        // (accumulate = 0 at the chunk start): the epilogue warps sum the chunks in fp32 registers.
+        // Non-promoting configurations use one chunk per unit.
+        for (int c0 = kb0; c0 < kb1; c0 += p.chunk_kb) {
+          const int c1 = min(c0 + p.chunk_kb, kb1);
+          mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * C::stage_bytes);
-          const uint32_t sb = sa + C::parts * C::a_bytes;
+          const uint32_t d_tmem = tmem_base + uint32_t(acc * C::block_n);
+          uint32_t accumulate = 0;
+          for (int kb = c0; kb < c1; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * C::stage_bytes);
+            const uint32_t sb = sa + C::parts * C::a_bytes;
 #pragma unroll
-          for (int k = 0; k < C::ksteps; ++k) {
-            const uint64_t a_hi = make_sw128_desc(sa + k * kadv_a, lbo_a, 1024);
-            const uint64_t b_hi = make_sw128_desc(sb + k * kadv_b, lbo_b, 1024);
-            if (C::nprod == 3) {
-              const uint64_t a_lo = make_sw128_desc(sa + C::a_bytes + k * kadv_a, lbo_a, 1024);
-              const uint64_t b_lo = make_sw128_desc(sb + C::b_bytes + k * kadv_b, lbo_b, 1024);
-              umma_ss<C::tf32>(d_tmem, a_lo, b_hi, idesc, accumulate);
-              umma_ss<C::tf32>(d_tmem, a_hi, b_lo, idesc, 1u);
-              umma_ss<C::tf32>(d_tmem, a_hi, b_hi, idesc, 1u);
-            } else {
-              umma_ss<C::tf32>(d_tmem, a_hi, b_hi, idesc, accumulate);
+            for (int k = 0; k < C::ksteps; ++k) {
+              const uint64_t a_hi = make_smem_desc(sa + k * kadv_a, lbo_a, sbo_a, lay_a);
+              const uint64_t b_hi = make_smem_desc(sb + k * kadv_b, lbo_b, sbo_b, lay_b);
+              if (C::nprod == 3) {
+                const uint64_t a_lo = make_smem_desc(sa + C::a_bytes + k * kadv_a, lbo_a, sbo_a, lay_a);
+                const uint64_t b_lo = make_smem_desc(sb + C::b_bytes + k * kadv_b, lbo_b, sbo_b, lay_b);
+                umma_ss<C::tf32>(d_tmem, a_lo, b_hi, idesc, accumulate);
+                umma_ss<C::tf32>(d_tmem, a_hi, b_lo, idesc, 1u);
+                umma_ss<C::tf32>(d_tmem, a_hi, b_hi, idesc, 1u);
+              } else {
+                umma_ss<C::tf32>(d_tmem, a_hi, b_hi, idesc, accumulate);
+              }
+              accumulate = 1u;
             }
-            accumulate = 1u;
+            umma_commit(&empty_bar[stage]);            // frees the smem stage when these MMAs retire
+            if (kb == c1 - 1) umma_commit(&tmem_full[acc]);
+            if (++stage == C::stages) { stage = 0; phase ^= 1u; }
           }
-          umma_commit(&empty_bar[stage]);            // frees the smem stage when these MMAs retire
-          if (kb == kb1 - 1) umma_commit(&tmem_full[acc]);
-          if (++stage == C::stages) { stage = 0; phase ^= 1u; }
+          acc ^= 1; if (acc == 0) acc_phase ^= 1u;
         }
-        acc ^= 1; if (acc == 0) acc_phase ^= 1u;
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue =====================
-    const int q = warp & 3;                          // TMEM lane quarter this warp may touch
+    // ===================== epilogue (8 warps) =====================
+    // warp w may touch TMEM lanes [32*(w%4), +32); the two warps of a lane quarter split the columns.
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
+    constexpr int kColsPerWarp = C::block_n / 2;
     int acc = 0; uint32_t acc_phase = 0;
     for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
       const int split = u / tiles_mn;
       const int t = u - split * tiles_mn;
       const int m0 = (t / p.tiles_n) * kBlockM;
-      const int n0 = (t % p.tiles_n) * C::block_n;
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
+      const int n0 = (t % p.tiles_n) * C::block_n + half * kColsPerWarp;
+      const int kb0 = split * p.kb_per_split;
+      const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
       const int row = m0 + q * 32 + lane;
       const bool row_ok = row < p.d_rows;
       float* drow = p.D + (long long)split * p.slab_stride + (long long)row * p.ldd;
-      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * C::block_n);
-#pragma unroll 1
-      for (int c = 0; c < C::block_n / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(taddr + c * 32, r);
-        tmem_ld_wait();
-        const int col0 = n0 + c * 32;
+      if (C::promote) {
+        // fp32 register accumulation of the chunk partial sums (round-to-nearest adds): the tensor
+        // core's own accumulator truncates, which biases long tf32x3 chains ("tf32x3").
+        float accr[kColsPerWarp];
+#pragma unroll
+        for (int j = 0; j < kColsPerWarp; ++j) accr[j] = 0.f;
+        for (int c0 = kb0; c0 < kb1; c0 += p.chunk_kb) {
+          mbar_wait(&tmem_full[acc], acc_phase);
+          tc_fence_after();
+          const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * C::block_n + half * kColsPerWarp);
+#pragma unroll
+          for (int c = 0; c < kColsPerWarp / 16; ++c) {
+            uint32_t r[16];
+            tmem_ld_32x16(taddr + c * 16, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) accr[c * 16 + j] += __uint_as_float(r[j]);
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          acc ^= 1; if (acc == 0) acc_phase ^= 1u;
+        }
         if (row_ok) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int col = col0 + j * 4;
+          for (int j = 0; j < kColsPerWarp / 4; ++j) {
+            const int col = n0 + j * 4;
             if (col < p.d_cols) {
-              float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                                     __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+              float4 v = make_float4(accr[4 * j], accr[4 * j + 1], accr[4 * j + 2], accr[4 * j + 3]);
               if (C::fwd_epi) {
                 float4 z;
                 epilogue_act4(p.epi, p.act_N, row, col, v, z);
@@ -223,11 +254,41 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             }
           }
         }
+      } else {
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * C::block_n + half * kColsPerWarp);
+#pragma unroll 1
+        for (int c = 0; c < kColsPerWarp / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c * 32, r);
+          tmem_ld_wait();
+          const int col0 = n0 + c * 32;
+          if (row_ok) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int col = col0 + j * 4;
+              if (col < p.d_cols) {
+                float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                       __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+                if (C::fwd_epi) {
+                  float4 z;
+                  epilogue_act4(p.epi, p.act_N, row, col, v, z);
+                  if (p.epi.Z) *reinterpret_cast<float4*>(p.epi.Z + (long long)row * p.act_N + col) = z;
+                } else {
+                  const float s = p.epi.out_scale;
+                  v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+                }
+                *reinterpret_cast<float4*>(drow + col) = v;
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        acc ^= 1; if (acc == 0) acc_phase ^= 1u;
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-      acc ^= 1; if (acc == 0) acc_phase ^= 1u;
     }
   }
 
@@ -260,7 +321,7 @@ EncodeTiledFn get_encode() {
 
 // 2D row-major tensor [outer rows, inner contiguous elems]; box = [box_outer rows, 128 B of inner].
 int make_tmap(CUtensorMap* tm, const void* base, CUtensorMapDataType dt, int elem_bytes, uint64_t inner,
-              uint64_t outer, uint32_t box_outer) {
+              uint64_t outer, uint32_t box_outer, CUtensorMapSwizzle swizzle) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return VV_ERR_CUDA;
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || ((inner * elem_bytes) & 15) != 0) {
@@ -272,7 +333,7 @@ int make_tmap(CUtensorMap* tm, const void* base, CUtensorMapDataType dt, int ele
   cuuint32_t box[2] = {uint32_t(kRowBytes / elem_bytes), box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(tm, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (CUresult %d)", int(r)); return VV_ERR_CUDA; }
   return VV_OK;
 }
@@ -292,13 +353,15 @@ int launch_cfg(const GemmProblem& g, cudaStream_t stream) {
   CUtensorMap tA_hi, tA_lo, tB_hi, tB_lo;
   const uint32_t a_box = C::a_mn ? C::bk : kBlockM;
   const uint32_t b_box = C::b_mn ? C::bk : C::block_n;
+  const CUtensorMapSwizzle sw_a = (C::tf32 && C::a_mn) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
+  const CUtensorMapSwizzle sw_b = (C::tf32 && C::b_mn) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
   int rc;
-  if ((rc = make_tmap(&tA_hi, g.A.hi, dt, C::elem_bytes, a_inner, a_outer, a_box))) return rc;
-  if ((rc = make_tmap(&tB_hi, g.B.hi, dt, C::elem_bytes, b_inner, b_outer, b_box))) return rc;
+  if ((rc = make_tmap(&tA_hi, g.A.hi, dt, C::elem_bytes, a_inner, a_outer, a_box, sw_a))) return rc;
+  if ((rc = make_tmap(&tB_hi, g.B.hi, dt, C::elem_bytes, b_inner, b_outer, b_box, sw_b))) return rc;
   if (C::parts == 2) {
     if (!g.A.lo || !g.B.lo) { set_error("TF32X3 needs hi and lo operand arrays"); return VV_ERR_INVALID; }
-    if ((rc = make_tmap(&tA_lo, g.A.lo, dt, C::elem_bytes, a_inner, a_outer, a_box))) return rc;
-    if ((rc = make_tmap(&tB_lo, g.B.lo, dt, C::elem_bytes, b_inner, b_outer, b_box))) return rc;
+    if ((rc = make_tmap(&tA_lo, g.A.lo, dt, C::elem_bytes, a_inner, a_outer, a_box, sw_a))) return rc;
+    if ((rc = make_tmap(&tB_lo, g.B.lo, dt, C::elem_bytes, b_inner, b_outer, b_box, sw_b))) return rc;
   } else {
     tA_lo = tA_hi; tB_lo = tB_hi;
   }
@@ -315,6 +378,8 @@ int launch_cfg(const GemmProblem& g, cudaStream_t stream) {
     return VV_ERR_INVALID;
   }
   p.nsplit = nsplit;
+  // tf32x3: promote every 512 reduction elements (16 k-blocks of 32) -> truncation bias < 4e-6 relative
+  p.chunk_kb = C::promote ? 16 : p.kb_per_split;
   p.D = g.D; p.slab_stride = g.slab_stride;
   p.act_N = g.N;
   p.epi = g.epi;
