@@ -10,10 +10,10 @@ NVFLAGS   := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -Wall 
 LIBDIR    := videovector_b200/lib
 OBJDIR    := build/obj
 CU_SRCS   := $(wildcard videovector_b200/csrc/*.cu) $(wildcard videovector_b200/csrc/host/*.cu)
-CPP_SRCS  := $(wildcard videovector_b200/csrc/host/*.cpp)
+CPP_SRCS  := $(wildcard videovector_b200/csrc/host/*.cpp) $(wildcard videovector_b200/csrc/host/caffe_compat/*.cpp)
 CU_OBJS   := $(patsubst %.cu,$(OBJDIR)/%.o,$(CU_SRCS))
 CPP_OBJS  := $(patsubst %.cpp,$(OBJDIR)/%.o,$(CPP_SRCS))
-HDRS      := include/vv_b200.h $(wildcard videovector_b200/csrc/*.cuh) $(wildcard videovector_b200/csrc/host/*.h) $(wildcard videovector_b200/csrc/host/*.hpp)
+HDRS      := include/vv_b200.h $(wildcard videovector_b200/csrc/host/caffe_compat/caffe/*.hpp) $(wildcard videovector_b200/csrc/host/caffe_compat/caffe/proto/*.hpp) $(wildcard videovector_b200/csrc/*.cuh) $(wildcard videovector_b200/csrc/host/*.h) $(wildcard videovector_b200/csrc/host/*.hpp)
 
 all: $(LIBDIR)/libvv_b200.so
 
@@ -23,11 +23,15 @@ $(OBJDIR)/%.o: %.cu $(HDRS)
 
 $(OBJDIR)/%.o: %.cpp $(HDRS)
 	@mkdir -p $(dir $@)
-	$(CXX) -O2 -std=c++17 -fPIC -Wall -Iinclude -Ivideovector_b200/csrc -I/usr/local/cuda/include -c $< -o $@
+	$(CXX) -O2 -std=c++17 -fPIC -Wall -Iinclude -Ivideovector_b200/csrc -Ivideovector_b200/csrc/host/caffe_compat -I/usr/local/cuda/include -c $< -o $@
 
 $(LIBDIR)/libvv_b200.so: $(CU_OBJS) $(CPP_OBJS)
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(ARCH) -shared -o $@ $^ -ldl
+
+tools: build/vv_caffe
+build/vv_caffe: tools/vv_caffe.cpp $(LIBDIR)/libvv_b200.so
+	$(CXX) -O2 -std=c++17 -Iinclude -Ivideovector_b200/csrc/host/caffe_compat -I/usr/local/cuda/include $< -o $@ -L$(LIBDIR) -lvv_b200 -Wl,-rpath,'$$ORIGIN/../$(LIBDIR)'
 
 oracle: oracle/_build/libvv_oracle.so
 oracle/_build/libvv_oracle.so: oracle/vv_oracle.cpp
@@ -40,4 +44,4 @@ ref:
 clean:
 	rm -rf build $(LIBDIR)/libvv_b200.so oracle/_build
 
-.PHONY: all oracle ref clean
+.PHONY: all oracle ref clean tools

@@ -1,0 +1,153 @@
+"""The drop-in boundary: the reference's operator interface (Blob / Layer<Dtype> / Net / SGDSolver, built from a
+prototxt with the shipped net's structure) running layer by layer on the C-ABI kernels, and the same net fused;
+both against the oracle.  These read like the reference's net / solver tests (test_net.cpp, test_gradient_based_solver.cpp)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+from videovector_b200 import caffe_host, prototxt
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+CFG = dict(B=16, C=5, Nn=10, K=256, N=64, dropout=0.5, videos=64, shots=24, max_buffer_size=200)
+
+
+def make_net(prec, fuse, W0, b0, mask):
+    caffe_host.set_device(0)
+    caffe_host.set_precision(prec)
+    net = caffe_host.Net(prototxt.train_net(**CFG))
+    net.set_param(0, W0); net.set_param(1, b0)
+    net.set_dropout_mask(mask)
+    if fuse:
+        ok, why = net.enable_fusion()
+        assert ok, why
+    return net
+
+
+def problem():
+    rng = np.random.RandomState(1701)
+    R = CFG["C"] + CFG["Nn"]
+    W0 = rng.normal(0, 0.02, (CFG["N"], CFG["K"])).astype(np.float32)
+    b0 = rng.normal(0, 0.01, CFG["N"]).astype(np.float32)
+    mask = (rng.uniform(0, 1, (R * CFG["B"], CFG["N"])) > 0.5).astype(np.uint32)
+    return W0, b0, mask, torch.as_tensor(mask.astype(np.int32)).cuda()
+
+
+@pytest.mark.parametrize("prec,tol", [("fp32_simt", 1e-5), ("tf32x3", 1e-5)])
+def test_layer_by_layer_net_matches_oracle(oracle, prec, tol):
+    W0, b0, mask, mask_dev = problem()
+    net = make_net(prec, False, W0, b0, mask_dev)
+    B, C, Nn, K, N = CFG["B"], CFG["C"], CFG["Nn"], CFG["K"], CFG["N"]
+    # net structure the reference's Net::Init would produce
+    assert net.num_params == 2
+    nb = dict(zip(net.layer_names, net.layer_need_backward))
+    assert not nb["shot_windows"] and not nb["slice_input_data"] and not nb["batch_concat_input"] and not nb["flatten_input"]
+    assert nb["fc7"] and nb["max_margin_loss"] and nb["context_feature_word_embedding_norm_0_split"]
+    for it in range(2):
+        loss = net.forward_backward()
+        data = net.blob("data").reshape(B, C + Nn, K)
+        ref = oracle.net_forward_backward(data, W0, b0, mask, B, C, Nn, margin=2.0, norm=2, dropout_ratio=0.5,
+                                          want=("loss", "violations", "dW", "db", "X", "Z", "H", "target_score", "neg_score", "dZ"))
+        assert abs(loss - ref["loss"][0]) < tol * max(1, ref["loss"][0])
+        assert np.array_equal(net.blob("original_feature").reshape(-1, K), ref["X"])          # slice + concat + flatten: bit-exact
+        assert rel(net.blob("ip1_nonorm").reshape(-1, N), ref["Z"]) < tol
+        assert rel(net.blob("ip2").reshape(-1, N), ref["H"]) < tol
+        assert rel(net.blob("target_score").reshape(B, Nn), ref["target_score"]) < tol
+        assert rel(net.blob("negative_score").reshape(B, Nn), ref["neg_score"]) < tol
+        assert net.blob("train_violations").item() == ref["violations"][0]
+        assert net.blob("loss_output", diff=True).item() == 1.0                              # the loss weight lives in top.diff
+        assert rel(net.blob("ip1_nonorm", diff=True).reshape(-1, N), ref["dZ"]) < 2 * tol
+        assert rel(net.param(0, diff=True).reshape(N, K), ref["dW"]) < 2 * tol
+        assert rel(net.param(1, diff=True), ref["db"]) < 2 * tol
+    net.close()
+
+
+@pytest.mark.parametrize("prec,tol", [("tf32x3", 1e-5), ("bf16", 5e-2)])
+def test_fused_net_matches_layer_by_layer_and_oracle(oracle, prec, tol):
+    W0, b0, mask, mask_dev = problem()
+    B, C, Nn, K, N = CFG["B"], CFG["C"], CFG["Nn"], CFG["K"], CFG["N"]
+    plain = make_net("fp32_simt", False, W0, b0, mask_dev)
+    fused = make_net(prec, True, W0, b0, mask_dev)
+    for it in range(2):                     # both data layers replay the same sampler stream
+        l_plain = plain.forward_backward()
+        l_fused = fused.forward_backward()
+        data = plain.blob("data").reshape(B, C + Nn, K)
+        ref = oracle.net_forward_backward(data, W0, b0, mask, B, C, Nn, dropout_ratio=0.5)
+        assert abs(l_fused - ref["loss"][0]) < tol * max(1, ref["loss"][0]) and abs(l_fused - l_plain) < tol * max(1, l_plain)
+        assert fused.blob("train_violations").item() == plain.blob("train_violations").item() or tol > 1e-5
+        if tol <= 1e-5:
+            assert rel(fused.param(0, diff=True), ref["dW"].reshape(-1)) < 2 * tol
+            assert rel(fused.param(1, diff=True), ref["db"]) < 2 * tol
+        else:
+            d = fused.param(0, diff=True).astype(np.float64) - ref["dW"].reshape(-1)
+            assert np.linalg.norm(d) / np.linalg.norm(ref["dW"]) < 10 * tol
+    plain.close(); fused.close()
+
+
+def test_fusion_refuses_other_graphs():
+    caffe_host.set_device(0)
+    txt = prototxt.train_net(**CFG).replace("slice_dim: 0", "slice_dim: 1", 1) if False else prototxt.train_net(**CFG)
+    # a leaky ReLU is not what the fused kernels compute: the pass must decline and say why
+    leaky = txt.replace('type: RELU\n  top: "ip2"\n  bottom: "ip1_nonorm"\n', 'type: RELU\n  top: "ip2"\n  bottom: "ip1_nonorm"\n  relu_param { negative_slope: 0.1 }\n')
+    net = caffe_host.Net(leaky)
+    ok, why = net.enable_fusion()
+    assert not ok and "ReLU" in why
+    net.close()
+
+
+@pytest.mark.parametrize("fuse", [False, True])
+def test_solver_trajectory(oracle, fuse, monkeypatch):
+    """SGDSolver::Solve's loop body through the reference interface: 4 iterations, layer by layer and fused,
+    against the oracle's update (ref: test_gradient_based_solver.cpp checks weights AND history)."""
+    monkeypatch.setenv("VV_FUSE", "1" if fuse else "0")
+    W0, b0, mask, mask_dev = problem()
+    B, C, Nn, K, N = CFG["B"], CFG["C"], CFG["Nn"], CFG["K"], CFG["N"]
+    caffe_host.set_device(0); caffe_host.set_precision("tf32x3")
+    sol = caffe_host.Solver(prototxt.solver(base_lr=0.05, display=0), prototxt.train_net(**CFG))
+    sol.net.set_param(0, W0); sol.net.set_param(1, b0); sol.net.set_dropout_mask(mask_dev)
+    twin = make_net("fp32_simt", False, W0, b0, mask_dev)         # same sampler stream, only used to read the data blob
+    W, b = W0.copy(), b0.copy(); hW = np.zeros_like(W); hb = np.zeros_like(b)
+    for it in range(4):
+        assert abs(sol.learning_rate() - oracle.learning_rate("inv", 0.05, 1e-3, 0.75, 1, it)) < 1e-12
+        loss = sol.step()
+        twin.forward()
+        data = twin.blob("data").reshape(B, C + Nn, K)
+        ref = oracle.net_forward_backward(data, W, b, mask, B, C, Nn, dropout_ratio=0.5)
+        rate = oracle.learning_rate("inv", 0.05, 1e-3, 0.75, 1, it)
+        W, dWo, hW = oracle.sgd_update(W, ref["dW"], hW, rate * 1.0, 0.9, 5e-4 * 1.0)
+        b, dbo, hb = oracle.sgd_update(b, ref["db"], hb, rate * 2.0, 0.9, 0.0)
+        assert abs(loss - ref["loss"][0]) < 1e-5 * max(1, ref["loss"][0])
+        assert rel(sol.net.param(0), W.reshape(-1)) < 1e-5 and rel(sol.net.param(1), b) < 1e-5
+        assert rel(sol.history(0), hW.reshape(-1)) < 3e-5 and rel(sol.history(1), hb) < 3e-5
+        assert rel(sol.net.param(0, diff=True), dWo.reshape(-1)) < 3e-5                    # diff := history
+    assert sol.iter == 4
+    sol.close(); twin.close()
+
+
+def test_cli_train_log_format(tmp_path):
+    """`vv_caffe train` prints the fork's log lines (solver.cpp:195-217) that parse_log.sh / plot_training_stats.py scrape."""
+    exe = os.path.join(ROOT, "build", "vv_caffe")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "tools"], cwd=ROOT)
+    netp = tmp_path / "net.prototxt"; solp = tmp_path / "solver.prototxt"
+    netp.write_text(prototxt.train_net(**CFG))
+    solp.write_text(prototxt.solver(str(netp), display=1, max_iter=3))
+    r = subprocess.run([exe, "train", "--solver=%s" % solp], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert "Iteration 0, loss = " in r.stderr and "Iteration 2, lr = " in r.stderr
+    assert "Train net output #0: loss_output = iter = 0 value = " in r.stderr
+    assert "Train net output #1: train_violations = iter = 2 value = " in r.stderr
+    # a CPU solver must fail loudly: there is no CPU fallback
+    solp.write_text(prototxt.solver(str(netp), display=1, max_iter=1).replace("solver_mode: GPU", "solver_mode: CPU"))
+    r = subprocess.run([exe, "train", "--solver=%s" % solp], capture_output=True, text=True, timeout=120)
+    assert r.returncode != 0 and "no CPU fallback" in r.stderr

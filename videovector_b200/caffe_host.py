@@ -1,0 +1,190 @@
+"""ctypes wrapper over the caffe_compat host (csrc/host/caffe_compat/): Net / SGDSolver with the reference's
+interface, built from prototxt text.  Used by the tests; the C++ CLI is build/vv_caffe."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import VVError, PREC
+
+_P = C.c_void_p
+
+
+def _l():
+    lib = _lib.load()
+    if getattr(lib, "_vvc_ready", False):
+        return lib
+    lib.vvc_last_error.restype = C.c_char_p
+    lib.vvc_net_create.restype = _P; lib.vvc_net_create.argtypes = [C.c_char_p, C.c_int]
+    lib.vvc_solver_create.restype = _P; lib.vvc_solver_create.argtypes = [C.c_char_p, C.c_char_p]
+    lib.vvc_solver_net.restype = _P; lib.vvc_solver_net.argtypes = [_P]
+    lib.vvc_net_layer_name.restype = C.c_char_p; lib.vvc_net_layer_name.argtypes = [_P, C.c_int]
+    lib.vvc_net_blob_name.restype = C.c_char_p; lib.vvc_net_blob_name.argtypes = [_P, C.c_int]
+    lib.vvc_solver_learning_rate.restype = C.c_float; lib.vvc_solver_learning_rate.argtypes = [_P]
+    for name in ("vvc_net_destroy", "vvc_solver_destroy"):
+        getattr(lib, name).argtypes = [_P]; getattr(lib, name).restype = None
+    for name in ("vvc_net_num_layers", "vvc_net_num_blobs", "vvc_net_num_params", "vvc_solver_iter"):
+        getattr(lib, name).argtypes = [_P]
+    for name in ("vvc_net_layer_type", "vvc_net_layer_need_backward", "vvc_net_param_count"):
+        getattr(lib, name).argtypes = [_P, C.c_int]
+    lib.vvc_net_blob_shape.argtypes = [_P, C.c_char_p, _P]
+    lib.vvc_net_blob_read.argtypes = [_P, C.c_char_p, C.c_int, _P]
+    lib.vvc_net_param_read.argtypes = [_P, C.c_int, C.c_int, _P]
+    lib.vvc_net_param_write.argtypes = [_P, C.c_int, _P]
+    lib.vvc_net_set_dropout_mask.argtypes = [_P, _P]
+    lib.vvc_net_enable_fusion.argtypes = [_P, _P, C.c_int]
+    lib.vvc_net_forward_backward.argtypes = [_P, _P]
+    lib.vvc_net_forward.argtypes = [_P, _P]
+    lib.vvc_solver_step.argtypes = [_P, _P]
+    lib.vvc_solver_solve.argtypes = [_P, C.c_int]
+    lib.vvc_solver_history_read.argtypes = [_P, C.c_int, _P]
+    lib.vvc_transform_net.argtypes = [C.c_char_p, C.c_int, _P, C.c_int]
+    lib.vvc_set_stream.argtypes = [_P]
+    lib._vvc_ready = True
+    return lib
+
+
+def _check(rc):
+    if rc < 0:
+        raise VVError("caffe host: " + _l().vvc_last_error().decode())
+    return rc
+
+
+def set_device(dev=0):
+    _check(_l().vvc_set_device(dev))
+
+
+def set_seed(seed):
+    _l().vvc_set_seed(seed)
+
+
+def set_precision(prec):
+    _l().vvc_set_precision(PREC[prec] if isinstance(prec, str) else prec)
+
+
+def transform_net(prototxt, phase="TRAIN"):
+    """FilterNet(phase) + InsertSplits on prototxt text (host only, no GPU needed)."""
+    buf = C.create_string_buffer(1 << 22)
+    _check(_l().vvc_transform_net(prototxt.encode(), 1 if phase == "TEST" else 0, buf, len(buf)))
+    return buf.value.decode()
+
+
+class Net:
+    def __init__(self, prototxt=None, phase="TRAIN", handle=None, owner=None):
+        self._lib = _l()
+        self._owner = owner
+        if handle is None:
+            handle = self._lib.vvc_net_create(prototxt.encode(), 1 if phase == "TEST" else 0)
+            if not handle:
+                raise VVError("caffe host: " + self._lib.vvc_last_error().decode())
+            self._own = True
+        else:
+            self._own = False
+        self._h = handle
+
+    @property
+    def layer_names(self):
+        return [self._lib.vvc_net_layer_name(self._h, i).decode() for i in range(self._lib.vvc_net_num_layers(self._h))]
+
+    @property
+    def layer_types(self):
+        return [self._lib.vvc_net_layer_type(self._h, i) for i in range(self._lib.vvc_net_num_layers(self._h))]
+
+    @property
+    def layer_need_backward(self):
+        return [bool(self._lib.vvc_net_layer_need_backward(self._h, i)) for i in range(self._lib.vvc_net_num_layers(self._h))]
+
+    @property
+    def blob_names(self):
+        return [self._lib.vvc_net_blob_name(self._h, i).decode() for i in range(self._lib.vvc_net_num_blobs(self._h))]
+
+    @property
+    def num_params(self):
+        return self._lib.vvc_net_num_params(self._h)
+
+    def blob(self, name, diff=False):
+        shape = (C.c_int * 4)()
+        n = _check(self._lib.vvc_net_blob_shape(self._h, name.encode(), shape))
+        out = np.empty(n, np.float32)
+        _check(self._lib.vvc_net_blob_read(self._h, name.encode(), int(diff), out.ctypes.data))
+        return out.reshape([s for s in shape])
+
+    def param(self, i, diff=False):
+        out = np.empty(self._lib.vvc_net_param_count(self._h, i), np.float32)
+        _check(self._lib.vvc_net_param_read(self._h, i, int(diff), out.ctypes.data))
+        return out
+
+    def set_param(self, i, value):
+        v = np.ascontiguousarray(value, np.float32).reshape(-1)
+        assert v.size == self._lib.vvc_net_param_count(self._h, i)
+        _check(self._lib.vvc_net_param_write(self._h, i, v.ctypes.data))
+
+    def set_dropout_mask(self, mask_dev):
+        self._mask = mask_dev            # keep the tensor alive
+        _check(self._lib.vvc_net_set_dropout_mask(self._h, C.c_void_p(mask_dev.data_ptr())))
+
+    def enable_fusion(self):
+        why = C.create_string_buffer(512)
+        ok = _check(self._lib.vvc_net_enable_fusion(self._h, why, 512))
+        return bool(ok), why.value.decode()
+
+    def forward_backward(self):
+        loss = C.c_float(0)
+        _check(self._lib.vvc_net_forward_backward(self._h, C.byref(loss)))
+        return loss.value
+
+    def forward(self):
+        loss = C.c_float(0)
+        _check(self._lib.vvc_net_forward(self._h, C.byref(loss)))
+        return loss.value
+
+    def close(self):
+        if self._h and self._own:
+            self._lib.vvc_net_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Solver:
+    def __init__(self, solver_prototxt, net_prototxt):
+        self._lib = _l()
+        self._h = self._lib.vvc_solver_create(solver_prototxt.encode(), net_prototxt.encode())
+        if not self._h:
+            raise VVError("caffe host: " + self._lib.vvc_last_error().decode())
+        self.net = Net(handle=self._lib.vvc_solver_net(self._h), owner=self)
+
+    def step(self):
+        loss = C.c_float(0)
+        _check(self._lib.vvc_solver_step(self._h, C.byref(loss)))
+        return loss.value
+
+    def solve(self, max_iter):
+        _check(self._lib.vvc_solver_solve(self._h, max_iter))
+
+    @property
+    def iter(self):
+        return self._lib.vvc_solver_iter(self._h)
+
+    def learning_rate(self):
+        return float(self._lib.vvc_solver_learning_rate(self._h))
+
+    def history(self, i):
+        out = np.empty(self._lib.vvc_net_param_count(self.net._h, i), np.float32)
+        _check(self._lib.vvc_solver_history_read(self._h, i, out.ctypes.data))
+        return out
+
+    def close(self):
+        if self._h:
+            self._lib.vvc_solver_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,45 @@
+// Solver / SGDSolver (ref: include/caffe/solver.hpp:17-143, src/caffe/solver.cpp:160-240 Solve,
+// :441-460 GetLearningRate, :464-482 PreSolve, :486-576 ComputeUpdateValue).
+#pragma once
+#include "caffe/net.hpp"
+
+namespace caffe {
+
+template <typename Dtype>
+class Solver {
+ public:
+  explicit Solver(const SolverParameter& param) : param_(param), iter_(0) { Init(param); }
+  virtual ~Solver() {}
+  void Init(const SolverParameter& param);
+  virtual void Solve(int max_iter = -1);
+  // one iteration: ForwardBackward + ComputeUpdateValue + Update (fused into one kernel sequence when the net is fused)
+  Dtype Step();
+  inline shared_ptr<Net<Dtype> > net() { return net_; }
+  int iter() const { return iter_; }
+  const SolverParameter& param() const { return param_; }
+ protected:
+  virtual void PreSolve() {}
+  virtual void ComputeUpdateValue() = 0;
+  virtual void FillFusedSolverCfg(vv_trainer_cfg_t* cfg) = 0;
+  SolverParameter param_;
+  int iter_;
+  shared_ptr<Net<Dtype> > net_;
+  bool presolved_ = false;
+};
+
+template <typename Dtype>
+class SGDSolver : public Solver<Dtype> {
+ public:
+  explicit SGDSolver(const SolverParameter& param) : Solver<Dtype>(param) {}
+  const vector<shared_ptr<Blob<Dtype> > >& history() { return history_; }
+  Dtype GetLearningRate();
+ protected:
+  virtual void PreSolve();
+  virtual void ComputeUpdateValue();
+  virtual void FillFusedSolverCfg(vv_trainer_cfg_t* cfg);
+  vector<shared_ptr<Blob<Dtype> > > history_, update_, temp_;
+};
+
+template <typename Dtype> Solver<Dtype>* GetSolver(const SolverParameter& param);
+
+}  // namespace caffe

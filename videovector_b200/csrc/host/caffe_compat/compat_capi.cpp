@@ -1,0 +1,111 @@
+// C entry points over the caffe_compat host for the Python tests: build a net / solver from prototxt text,
+// run it layer by layer or fused, read blobs by name.  Errors (failed CHECKs) come back as -1 + message.
+#include <cuda_runtime_api.h>
+#include <cstring>
+#include "caffe/solver.hpp"
+
+using namespace caffe;
+
+static thread_local string g_err;
+#define GUARD(body) try { body } catch (const std::exception& e) { g_err = e.what(); return -1; }
+#define GUARDP(body) try { body } catch (const std::exception& e) { g_err = e.what(); return nullptr; }
+
+extern "C" {
+
+const char* vvc_last_error() { return g_err.c_str(); }
+int vvc_set_device(int dev) { GUARD(Caffe::SetDevice(dev); return 0;) }
+int vvc_device_synchronize() { return int(cudaDeviceSynchronize()); }
+int vvc_set_seed(unsigned seed) { Caffe::set_random_seed(seed); return 0; }
+int vvc_set_precision(int prec) { Caffe::set_precision(prec); return 0; }
+int vvc_set_stream(void* s) { Caffe::set_stream(reinterpret_cast<vv_stream_t>(s)); return 0; }
+
+// FilterNet(phase) + InsertSplits on prototxt text (no device needed); result written to out (NUL-terminated)
+int vvc_transform_net(const char* prototxt_text, int phase, char* out, int out_len) {
+  GUARD(const NetParameter p = InsertSplits(FilterNet(NetParameter(ParseTextFormat(prototxt_text)), phase == 1 ? Caffe::TEST : Caffe::TRAIN));
+        const string s = PrintTextFormat(*p.m);
+        CHECK_LT(int(s.size()), out_len) << "output buffer too small";
+        memcpy(out, s.c_str(), s.size() + 1); return int(s.size());)
+}
+
+void* vvc_net_create(const char* prototxt_text, int phase) {
+  GUARDP(return new Net<float>(NetParameter(ParseTextFormat(prototxt_text)), phase == 1 ? Caffe::TEST : Caffe::TRAIN);)
+}
+void vvc_net_destroy(void* n) { delete static_cast<Net<float>*>(n); }
+int vvc_net_num_layers(void* n) { return static_cast<Net<float>*>(n)->layers().size(); }
+const char* vvc_net_layer_name(void* n, int i) { return static_cast<Net<float>*>(n)->layer_names()[i].c_str(); }
+int vvc_net_layer_type(void* n, int i) { return int(static_cast<Net<float>*>(n)->layers()[i]->type()); }
+int vvc_net_layer_need_backward(void* n, int i) { return static_cast<Net<float>*>(n)->layer_need_backward()[i] ? 1 : 0; }
+int vvc_net_num_blobs(void* n) { return static_cast<Net<float>*>(n)->blobs().size(); }
+const char* vvc_net_blob_name(void* n, int i) { return static_cast<Net<float>*>(n)->blob_names()[i].c_str(); }
+int vvc_net_num_params(void* n) { return static_cast<Net<float>*>(n)->params().size(); }
+
+// shape[4] out; returns count or -1
+int vvc_net_blob_shape(void* n, const char* name, int* shape) {
+  GUARD(auto b = static_cast<Net<float>*>(n)->blob_by_name(name);
+        shape[0] = b->num(); shape[1] = b->channels(); shape[2] = b->height(); shape[3] = b->width(); return b->count();)
+}
+// copies data (which = 0) or diff (which = 1) of a named blob to host memory
+int vvc_net_blob_read(void* n, const char* name, int which, float* out) {
+  GUARD(auto b = static_cast<Net<float>*>(n)->blob_by_name(name);
+        memcpy(out, which ? b->cpu_diff() : b->cpu_data(), sizeof(float) * b->count()); return 0;)
+}
+int vvc_net_param_count(void* n, int i) { return static_cast<Net<float>*>(n)->params()[i]->count(); }
+int vvc_net_param_read(void* n, int i, int which, float* out) {
+  GUARD(auto b = static_cast<Net<float>*>(n)->params()[i];
+        memcpy(out, which ? b->cpu_diff() : b->cpu_data(), sizeof(float) * b->count()); return 0;)
+}
+int vvc_net_param_write(void* n, int i, const float* in) {
+  GUARD(auto b = static_cast<Net<float>*>(n)->params()[i];
+        CHECK(!static_cast<Net<float>*>(n)->trainer()) << "write parameters before the first fused step";
+        memcpy(b->mutable_cpu_data(), in, sizeof(float) * b->count()); return 0;)
+}
+// explicit dropout mask (device, 0/1 uint32 [R*B, N]) for parity runs: applies to the DROPOUT layer and the fused path
+int vvc_net_set_dropout_mask(void* n, const void* device_mask01) {
+  GUARD(Net<float>* net = static_cast<Net<float>*>(n);
+        for (auto& l : net->layers())
+          if (auto* d = dynamic_cast<DropoutLayer<float>*>(l.get())) d->set_fixed_mask(static_cast<const uint32_t*>(device_mask01));
+        net->set_fixed_dropout_mask(static_cast<const uint32_t*>(device_mask01)); return 0;)
+}
+int vvc_net_enable_fusion(void* n, char* why, int why_len) {
+  GUARD(string w; const bool ok = static_cast<Net<float>*>(n)->EnableFusion(&w);
+        if (why && why_len > 0) { strncpy(why, w.c_str(), why_len - 1); why[why_len - 1] = 0; }
+        return ok ? 1 : 0;)
+}
+int vvc_net_forward_backward(void* n, float* loss) {
+  GUARD(*loss = static_cast<Net<float>*>(n)->ForwardBackward(); cudaDeviceSynchronize(); return 0;)
+}
+int vvc_net_forward(void* n, float* loss) {
+  GUARD(static_cast<Net<float>*>(n)->ForwardPrefilled(loss); cudaDeviceSynchronize(); return 0;)
+}
+
+void* vvc_solver_create(const char* solver_text, const char* net_text) {
+  // `net:` may name a file, or the net prototxt is given inline (written to a temp file next to nothing: kept in memory)
+  GUARDP(
+    auto sp = ParseTextFormat(solver_text);
+    if (net_text && *net_text) {
+      char path[] = "/tmp/vvc_net_XXXXXX";
+      int fd = mkstemp(path); CHECK_GE(fd, 0) << "mkstemp failed";
+      FILE* f = fdopen(fd, "w"); fputs(net_text, f); fclose(f);
+      sp->set_scalar("net", path);
+      Solver<float>* s = GetSolver<float>(SolverParameter(sp));
+      remove(path);
+      return s;
+    }
+    return GetSolver<float>(SolverParameter(sp));)
+}
+void vvc_solver_destroy(void* s) { delete static_cast<Solver<float>*>(s); }
+void* vvc_solver_net(void* s) { return static_cast<Solver<float>*>(s)->net().get(); }
+int vvc_solver_step(void* s, float* loss) { GUARD(*loss = static_cast<Solver<float>*>(s)->Step(); cudaDeviceSynchronize(); return 0;) }
+int vvc_solver_solve(void* s, int max_iter) { GUARD(static_cast<Solver<float>*>(s)->Solve(max_iter); cudaDeviceSynchronize(); return 0;) }
+int vvc_solver_iter(void* s) { return static_cast<Solver<float>*>(s)->iter(); }
+int vvc_solver_history_read(void* s, int i, float* out) {
+  GUARD(auto* sg = dynamic_cast<SGDSolver<float>*>(static_cast<Solver<float>*>(s)); CHECK(sg);
+        CHECK_LT(i, int(sg->history().size())) << "history is allocated by the first step";
+        memcpy(out, sg->history()[i]->cpu_data(), sizeof(float) * sg->history()[i]->count()); return 0;)
+}
+float vvc_solver_learning_rate(void* s) {
+  try { auto* sg = dynamic_cast<SGDSolver<float>*>(static_cast<Solver<float>*>(s)); return sg->GetLearningRate(); }
+  catch (const std::exception& e) { g_err = e.what(); return -1.f; }
+}
+
+}  // extern "C"

@@ -1,0 +1,126 @@
+// Solver / SGDSolver (see caffe/solver.hpp for the reference lines mirrored here).
+#include <cmath>
+#include <cstring>
+#include "caffe/solver.hpp"
+
+namespace caffe {
+
+template <typename Dtype>
+void Solver<Dtype>::Init(const SolverParameter& param) {
+  param_ = param;
+  if (param_.random_seed() >= 0) Caffe::set_random_seed(unsigned(param_.random_seed()));
+  CHECK(param_.solver_mode() == "GPU") << "solver_mode: CPU is not available in the B200 build (no CPU fallback)";
+  const string net_file = param_.net().empty() ? param_.train_net() : param_.net();
+  CHECK(!net_file.empty()) << "SolverParameter must specify a net";
+  LogInfo("Creating training net from net file: " + net_file);
+  net_.reset(new Net<Dtype>(net_file, Caffe::TRAIN));
+  const char* fuse = getenv("VV_FUSE");
+  if (!fuse || strcmp(fuse, "0") != 0) {
+    string why;
+    if (!net_->EnableFusion(&why)) LogInfo("net not fused (" + why + "): running layer by layer");
+  }
+  iter_ = 0;
+}
+
+template <typename Dtype>
+Dtype Solver<Dtype>::Step() {
+  if (!presolved_) { PreSolve(); presolved_ = true; }
+  Dtype loss;
+  if (net_->fused()) {
+    vv_trainer_cfg_t sc; memset(&sc, 0, sizeof(sc));
+    FillFusedSolverCfg(&sc);
+    loss = net_->FusedStep(iter_, true, &sc);        // forward + backward + ComputeUpdateValue + Update
+  } else {
+    loss = net_->ForwardBackward();
+    ComputeUpdateValue();
+    net_->Update();
+  }
+  ++iter_;
+  return loss;
+}
+
+// ref: solver.cpp:160-240 (test / snapshot hooks are outside the path)
+template <typename Dtype>
+void Solver<Dtype>::Solve(int max_iter) {
+  const int stop = max_iter >= 0 ? max_iter : param_.max_iter();
+  for (; iter_ < stop;) {
+    const int it = iter_;
+    const Dtype loss = Step();
+    if (param_.display() && it % param_.display() == 0) {
+      // the fork's log format (solver.cpp:195-217): scrapers (parse_log.sh, plot_training_stats.py) key on it
+      fprintf(stderr, "Iteration %d, loss = %g\n", it, double(loss));
+      const vector<Blob<Dtype>*>& result = net_->output_blobs();
+      int score_index = 0;
+      for (size_t j = 0; j < result.size(); ++j) {
+        const Dtype* v = result[j]->cpu_data();
+        const string& name = net_->blob_names()[net_->output_blob_indices()[j]];
+        for (int k = 0; k < result[j]->count(); ++k)
+          fprintf(stderr, "    Train net output #%d: %s = iter = %d value = %g\n", score_index++, name.c_str(), it, double(v[k]));
+      }
+    }
+  }
+}
+
+template <typename Dtype>
+Dtype SGDSolver<Dtype>::GetLearningRate() {
+  // evaluated through the C-ABI so the host-side rate is the one the fused kernels use (ref: solver.cpp:441-460)
+  const float r = vv_learning_rate(this->param_.lr_policy().c_str(), this->param_.base_lr(), this->param_.gamma(),
+                                   this->param_.power(), this->param_.stepsize(), this->iter_);
+  CHECK_GE(r, 0.f) << "Unknown learning rate policy: " << this->param_.lr_policy();
+  return r;
+}
+template <typename Dtype>
+void SGDSolver<Dtype>::PreSolve() {
+  history_.clear(); update_.clear(); temp_.clear();
+  vector<shared_ptr<Blob<Dtype> > >& net_params = this->net_->params();
+  for (size_t i = 0; i < net_params.size(); ++i) {
+    const Blob<Dtype>* p = net_params[i].get();
+    history_.push_back(shared_ptr<Blob<Dtype> >(new Blob<Dtype>(p->num(), p->channels(), p->height(), p->width())));
+  }
+}
+template <typename Dtype>
+void SGDSolver<Dtype>::FillFusedSolverCfg(vv_trainer_cfg_t* c) {
+  strncpy(c->lr_policy, this->param_.lr_policy().c_str(), sizeof(c->lr_policy) - 1);
+  c->base_lr = this->param_.base_lr(); c->gamma = this->param_.gamma(); c->power = this->param_.power();
+  c->stepsize = this->param_.stepsize(); c->momentum = this->param_.momentum(); c->weight_decay = this->param_.weight_decay();
+  const string rt = this->param_.regularization_type();
+  CHECK(rt == "L2" || rt == "L1") << "Unknown regularization type: " << rt;
+  c->reg_type = rt == "L2" ? 2 : 1;
+  // after the trainer exists the momentum history lives in its buffers
+  if (this->net_->trainer() && history_.size() == 2 && history_[0]->gpu_data() != vv_trainer_weight_hist(this->net_->trainer())) {
+    history_[0]->set_gpu_data(vv_trainer_weight_hist(this->net_->trainer()));
+    history_[1]->set_gpu_data(vv_trainer_bias_hist(this->net_->trainer()));
+  }
+}
+// Layer-by-layer mode: the reference's own sequence on the device (ref: solver.cpp:534-568):
+//   diff += decay * data ; hist = rate * diff + momentum * hist ; diff = hist ; then Net::Update: data -= diff.
+// (The fused net does all of it, plus the split-K slab sum, in one pass: vv_sgd_update inside vv_trainer_step.)
+template <typename Dtype>
+void SGDSolver<Dtype>::ComputeUpdateValue() {
+  vector<shared_ptr<Blob<Dtype> > >& net_params = this->net_->params();
+  vector<float>& lr = this->net_->params_lr();
+  vector<float>& wd = this->net_->params_weight_decay();
+  const Dtype rate = GetLearningRate();
+  if (this->param_.display() && this->iter_ % this->param_.display() == 0) fprintf(stderr, "Iteration %d, lr = %g\n", this->iter_, double(rate));
+  const Dtype momentum = this->param_.momentum();
+  const Dtype weight_decay = this->param_.weight_decay();
+  const string rt = this->param_.regularization_type();
+  for (size_t i = 0; i < net_params.size(); ++i) {
+    Blob<Dtype>* p = net_params[i].get();
+    const Dtype local_rate = rate * lr[i], local_decay = weight_decay * wd[i];
+    if (local_decay) {
+      CHECK(rt == "L2") << "regularization_type " << rt << " is only built in the fused update kernel";
+      VV_CHECK(vv_axpby(p->count(), local_decay, p->gpu_data(), 1.f, p->mutable_gpu_diff(), Caffe::stream()));
+    }
+    VV_CHECK(vv_axpby(p->count(), local_rate, p->gpu_diff(), momentum, history_[i]->mutable_gpu_data(), Caffe::stream()));
+    VV_CHECK(vv_axpby(p->count(), 1.f, history_[i]->gpu_data(), 0.f, p->mutable_gpu_diff(), Caffe::stream()));
+  }
+}
+
+template <typename Dtype>
+Solver<Dtype>* GetSolver(const SolverParameter& param) { return new SGDSolver<Dtype>(param); }
+template Solver<float>* GetSolver(const SolverParameter& param);
+template class Solver<float>;
+template class SGDSolver<float>;
+
+}  // namespace caffe

@@ -1,0 +1,64 @@
+"""Writer of V1 `layers {}` prototxts with the structure and layer/blob names of the reference project
+(projects/videovec_embedding/mednet_embedding_train.prototxt:2-671 and ..._solver.prototxt), parameterised on
+batch, window, negatives and dimensions (BASELINE configs 1-4).  The data layer's `source` is a synthetic://
+feature bank because the LMDB reader is out of scope."""
+
+
+def train_net(B=128, C=5, Nn=10, K=4096, N=512, dropout=0.9, margin=2.0, norm="L2", videos=2048, shots=32, seed=1234,
+              max_buffer_size=5000, swap=50, max_same=6, name="med_embedding"):
+    L = []
+
+    def layer(s, both_phases=False):
+        # fc7 / fc7_relu carry no include rule in the shipped file (used by TRAIN and TEST), all others are TRAIN-only
+        L.append("layers {\n" + s.rstrip() + ("\n" if both_phases else "\n  include: { phase: TRAIN }\n") + "}\n")
+    ctx = ["context_window_emb_%d_nonorm" % i for i in range(1, C)]
+    neg = ["negative_emb_%d" % k for k in range(1, Nn + 1)]
+    raw = ["target"] + ["context_window_%d" % i for i in range(1, C)] + ["negative_%d" % k for k in range(1, Nn + 1)]
+
+    def tops(names, key="top"):
+        return "".join('  %s: "%s"\n' % (key, n) for n in names)
+    layer('  name: "shot_windows"\n  type: VIDEO_SAMPLED_SHOTS_DATA\n  top: "data"\n  video_sampled_shots_data_param {\n'
+          '    source: "synthetic://videos=%d&shots=%d&dim=%d&seed=%d"\n    backend: LMDB\n    batch_size: %d\n'
+          '    num_negative_samples: %d\n    max_buffer_size: %d\n    negative_swap_percentage: %d\n    max_same_video_negs: %d\n'
+          '    context_type: WINDOW\n    context_size: %d\n  }\n' % (videos, shots, K, seed, B, Nn, max_buffer_size, swap, max_same, C))
+    layer('  name: "slice_input_data"\n  type: SLICE\n  bottom: "data"\n' + tops(raw) + '  slice_param {\n    slice_dim: 1\n  }\n')
+    layer('  name: "batch_concat_input"\n  type: CONCAT\n  top: "batch_concat"\n' + tops(raw, "bottom") + '  concat_param {\n    concat_dim: 0\n  }\n')
+    layer('  name: "flatten_input"\n  type: FLATTEN\n  bottom: "batch_concat"\n  top: "original_feature"\n')
+    layer('  name: "fc7"\n  type: INNER_PRODUCT\n  bottom: "original_feature"\n  top: "ip1_nonorm"\n  blobs_lr: 1\n  blobs_lr: 2\n'
+          '  weight_decay: 1\n  weight_decay: 0\n  inner_product_param {\n    num_output: %d\n    weight_filler {\n      type: "gaussian"\n'
+          '      std: 0.001\n    }\n    bias_filler {\n      type: "constant"\n    }\n  }\n' % N, both_phases=True)
+    layer('  name: "fc7_relu"\n  type: RELU\n  top: "ip2"\n  bottom: "ip1_nonorm"\n', both_phases=True)
+    if dropout and dropout > 0:
+        layer('  name: "drop2"\n  type: DROPOUT\n  bottom: "ip2"\n  top: "ip2"\n  dropout_param {\n    dropout_ratio: %g\n  }\n' % dropout)
+    layer('  name: "slice_emb"\n  type: SLICE\n  bottom: "ip2"\n' + tops(["target_emb_nonorm"] + ctx + [n + "_nonorm" for n in neg]) +
+          '  slice_param {\n    slice_dim: 0\n  }\n')
+    layer('  name: "context_average"\n  type: ELTWISE\n' + tops(ctx, "bottom") + '  top: "context_feature_nonorm"\n  eltwise_param {\n'
+          '    operation: SUM\n' + "".join("    coeff: %.10g\n" % (1.0 / (C - 1)) for _ in ctx) + '  }\n')
+    layer('  name: "word_embedding_norm"\n  type: NORMALIZATION\n  bottom: "context_feature_nonorm"\n  top: "context_feature"\n')
+    layer('  name: "concat_pos_neg_nonorm"\n  type: CONCAT\n  top: "pos_neg_nonorm"\n' + tops(["target_emb_nonorm"] + [n + "_nonorm" for n in neg], "bottom") +
+          '  concat_param {\n    concat_dim: 0\n  }\n')
+    layer('  name: "pos_neg_normalize"\n  type: NORMALIZATION\n  bottom: "pos_neg_nonorm"\n  top: "pos_neg_norm"\n')
+    layer('  name: "slice_pos_neg_norm"\n  type: SLICE\n  bottom: "pos_neg_norm"\n' + tops(["target_emb"] + neg) + '  slice_param {\n    slice_dim: 0\n  }\n')
+    layer('  name: "prod_true"\n  type: ELTWISE\n  bottom: "context_feature"\n  bottom: "target_emb"\n  top: "target_prod"\n  eltwise_param {\n    operation: PROD\n  }\n')
+    layer('  name: "sum_true"\n  type: SUM\n  bottom: "target_prod"\n  top: "target_score"\n  sum_param {\n    num_output: %d\n  }\n' % Nn)
+    for k in range(1, Nn + 1):
+        layer('  name: "prod_neg_%d"\n  type: ELTWISE\n  bottom: "context_feature"\n  bottom: "negative_emb_%d"\n  top: "negative_emb_%d_prod"\n'
+              '  eltwise_param {\n    operation: PROD\n  }\n' % (k, k, k))
+        layer('  name: "sum_neg_%d"\n  type: SUM\n  bottom: "negative_emb_%d_prod"\n  top: "neg_score_%d"\n' % (k, k, k))
+    layer('  name: "concat_negative_scores"\n  type: CONCAT\n' + tops(["neg_score_%d" % k for k in range(1, Nn + 1)], "bottom") +
+          '  top: "negative_score"\n  concat_param {\n    concat_dim: 1\n  }\n')
+    layer('  name: "max_margin_loss"\n  type: MAX_MARGIN_LOSS\n  bottom: "target_score"\n  bottom: "negative_score"\n  top: "loss_output"\n'
+          '  top: "train_violations"\n  loss_weight: 1\n  loss_weight: 0\n  max_margin_loss_param {\n    norm: %s\n    margin: %g\n  }\n' % (norm, margin))
+    # one TEST-only layer like the shipped file, to exercise phase filtering
+    test = ('layers {\n  name: "test_norm"\n  type: NORMALIZATION\n  bottom: "ip2"\n  top: "ip2_norm"\n  include: { phase: TEST }\n}\n')
+    return 'name: "%s"\n' % name + "".join(L[:7]) + test + "".join(L[7:])
+
+
+def solver(net_path="", base_lr=0.001, momentum=0.9, weight_decay=0.0005, lr_policy="inv", gamma=0.001, power=0.75,
+           max_iter=200000, display=10, random_seed=None):
+    s = ('net: "%s"\n' % net_path if net_path else "") + (
+        "base_lr: %g\nmomentum: %g\nweight_decay: %g\nlr_policy: \"%s\"\ngamma: %g\npower: %g\n"
+        "display: %d\nmax_iter: %d\nsnapshot: 2000\nsolver_mode: GPU\n" % (base_lr, momentum, weight_decay, lr_policy, gamma, power, display, max_iter))
+    if random_seed is not None:
+        s += "random_seed: %d\n" % random_seed
+    return s
