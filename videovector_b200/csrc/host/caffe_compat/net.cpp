@@ -333,6 +333,8 @@ Dtype Net<Dtype>::FusedStep(int iter, bool do_update, const vv_trainer_cfg_t* so
   const int32_t* dq = nullptr;
   const int32_t* di = fused_data_->NextIndices(&dq);
   VV_CHECK(vv_trainer_step(trainer_, fused_data_->bank(), fused_data_->bank_rows(), di, dq, fixed_mask_, iter, do_update ? 1 : 0));
+  // the trainer wrote the aliased parameter buffers behind the blobs' back: move their heads to the device
+  for (auto& pb : fused_ip_->blobs()) { pb->mutable_gpu_data(); pb->mutable_gpu_diff(); }
   // populate the net outputs other code reads (display, tests)
   cudaStream_t s = reinterpret_cast<cudaStream_t>(Caffe::stream());
   CHECK_EQ(int(cudaMemcpyAsync(fused_loss_->mutable_gpu_data(), vv_trainer_blob(trainer_, "loss"), sizeof(Dtype), cudaMemcpyDeviceToDevice, s)), 0);

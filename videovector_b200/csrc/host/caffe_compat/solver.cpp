@@ -29,7 +29,11 @@ Dtype Solver<Dtype>::Step() {
   if (net_->fused()) {
     vv_trainer_cfg_t sc; memset(&sc, 0, sizeof(sc));
     FillFusedSolverCfg(&sc);
+    if (param_.display() && iter_ % param_.display() == 0)        // same line ComputeUpdateValue prints (solver.cpp:492-494)
+      fprintf(stderr, "Iteration %d, lr = %g\n", iter_,
+              double(vv_learning_rate(sc.lr_policy, sc.base_lr, sc.gamma, sc.power, sc.stepsize, iter_)));
     loss = net_->FusedStep(iter_, true, &sc);        // forward + backward + ComputeUpdateValue + Update
+    FillFusedSolverCfg(&sc);                         // (re)alias the momentum history to the trainer's buffers
   } else {
     loss = net_->ForwardBackward();
     ComputeUpdateValue();
@@ -87,8 +91,8 @@ void SGDSolver<Dtype>::FillFusedSolverCfg(vv_trainer_cfg_t* c) {
   CHECK(rt == "L2" || rt == "L1") << "Unknown regularization type: " << rt;
   c->reg_type = rt == "L2" ? 2 : 1;
   // after the trainer exists the momentum history lives in its buffers
-  if (this->net_->trainer() && history_.size() == 2 && history_[0]->gpu_data() != vv_trainer_weight_hist(this->net_->trainer())) {
-    history_[0]->set_gpu_data(vv_trainer_weight_hist(this->net_->trainer()));
+  if (this->net_->trainer() && history_.size() == 2) {
+    history_[0]->set_gpu_data(vv_trainer_weight_hist(this->net_->trainer()));   // also moves the head to the device
     history_[1]->set_gpu_data(vv_trainer_bias_hist(this->net_->trainer()));
   }
 }
