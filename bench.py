@@ -26,6 +26,11 @@ sys.path.insert(0, ROOT)
 CFG = dict(C=5, Nn=10, K=4096, N=512, B=4096, V=2048, S=32, P=5000, swap=50, max_same=6)
 CPU_SAMPLE_B = 256          # bounded CPU sample: items per oracle step (same K, N, C, Nn)
 METRIC = "training triplets/sec"
+CPU_NOTE = {
+    "reference": "layers = the reference's own src/caffe/layers/*.cpp compiled unmodified against shim headers (oracle/_ref, "
+                 "Caffe CPU mode, OpenBLAS from the SciPy wheel); sampler and solver update = oracle restatements",
+    "port": "oracle/vv_oracle.cpp = restated reference CPU layers + solver + sampler, OpenBLAS from the SciPy wheel "
+            "(oracle/_ref was not built on this machine)"}
 
 
 def peaks():
@@ -93,14 +98,19 @@ class ClockSampler:
 # CPU baseline / reference arm: the oracle (port of the reference's CPU layers) on the host cores
 # ---------------------------------------------------------------------------------------------------
 def cpu_reference_run(steps, warmup, threads=0):
-    """One 'step' = sampler (materialising the data blob) + whole-net forward/backward + SGD update on a
-    bounded sample of CPU_SAMPLE_B items of the workload.  Returns (triplets/s, ms/step, cores, phase dict)."""
+    """One 'step' = sampler (materialising the data blob) + whole-net forward/backward + SGD update on a bounded
+    sample of CPU_SAMPLE_B items of the workload, on the host cores.  The layers run through oracle/_ref (the
+    reference's own layer sources, shim-compiled) when that library exists -- kind "reference" -- else through the
+    oracle port; the sampler and the solver update are the oracle's restatements in both cases (the reference's
+    data layer and solver.cpp need LMDB / protobuf).  Returns (triplets/s, ms/step, cores, phase dict, kind)."""
     from oracle import pyoracle as orc
+    from oracle import pyref
     from videovector_b200 import ops
     c = CFG
     B = CPU_SAMPLE_B
     V, S = 512, 16                                       # 8192 shots >= the 5000-entry negative buffer
-    cores = orc.use_openblas(threads)
+    cores = orc.use_openblas(threads)                    # same OpenBLAS instance the reference library links
+    use_ref = pyref.available()
     feat = ops.bank_host(V * S, c["K"], 1234)
     vid, off, sid = ops.synthetic_videos(V, S)
     smp = orc.Sampler(vid, off, sid, feat, c["K"], B, c["C"], c["Nn"], c["P"], c["swap"], c["max_same"], 100, seed=1)
@@ -112,32 +122,43 @@ def cpu_reference_run(steps, warmup, threads=0):
     mrng = np.random.RandomState(7)
     times, phases = [], np.zeros(8)
     for it in range(warmup + steps):
-        mask = (mrng.uniform(0, 1, (R * B, c["N"])) > 0.9).astype(np.uint32)   # mask generation not timed
+        mask = None if use_ref else (mrng.uniform(0, 1, (R * B, c["N"])) > 0.9).astype(np.uint32)   # mask generation not timed
         t0 = time.perf_counter()
         idx, quirk, data = smp.next()
         t1 = time.perf_counter()
-        out = orc.net_forward_backward(data, W, b, mask, B, c["C"], c["Nn"], margin=2.0, norm=2, dropout_ratio=0.9,
-                                       want=("loss", "violations", "dW", "db"))
+        if use_ref:
+            out = pyref.net_forward_backward(data, W, b, B, c["C"], c["Nn"], margin=2.0, norm=2, dropout_ratio=0.9, seed=it)
+            net_s = float(out["seconds"][1] + out["seconds"][2])      # Forward + Backward of the built net (setup excluded)
+        else:
+            out = orc.net_forward_backward(data, W, b, mask, B, c["C"], c["Nn"], margin=2.0, norm=2, dropout_ratio=0.9,
+                                           want=("loss", "violations", "dW", "db"))
+            net_s = None
+        t2 = time.perf_counter()
         rate = orc.learning_rate("inv", 1e-3, 1e-3, 0.75, 1, it)
         W, _, hW = orc.sgd_update(W, out["dW"], hW, rate, 0.9, 5e-4)
         b, _, hb = orc.sgd_update(b, out["db"], hb, rate * 2, 0.9, 0.0)
-        t2 = time.perf_counter()
+        t3 = time.perf_counter()
         if it >= warmup:
-            times.append(t2 - t0)
-            phases[:5] += out["phase_seconds"][:5]; phases[5] += t1 - t0
+            step_s = (t1 - t0) + (net_s if net_s is not None else (t2 - t1)) + (t3 - t2)
+            times.append(step_s)
+            if use_ref:
+                phases[1] += out["seconds"][1]; phases[3] += out["seconds"][2]
+            else:
+                phases[:5] += out["phase_seconds"][:5]
+            phases[5] += t1 - t0; phases[6] += t3 - t2
     smp.close()
     orc.use_builtin_blas()
     ms = 1e3 * float(np.mean(times))
-    ph = {k: 1e3 * phases[i] / len(times) for i, k in enumerate(["slice_concat", "fc7_forward", "loss_forward",
-                                                                  "loss_backward", "fc7_backward", "sampler"])}
-    return B / (ms * 1e-3), ms, cores, ph
+    names = ["slice_concat", "forward", "loss_forward", "backward", "fc7_backward", "sampler", "sgd_update"]
+    ph = {k: 1e3 * phases[i] / len(times) for i, k in enumerate(names) if phases[i] > 0}
+    return B / (ms * 1e-3), ms, cores, ph, ("reference" if use_ref else "port")
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    val, ms, cores, ph = cpu_reference_run(args.steps, max(args.warmup, 1))
+    val, ms, cores, ph, kind = cpu_reference_run(args.steps, max(args.warmup, 1))
     sample = "B=%d items per step (1/%d of the %d-item GPU step), same K/N/C/Nn; %d timed steps" % (
         CPU_SAMPLE_B, CFG["B"] // CPU_SAMPLE_B, CFG["B"], args.steps)
     line = {
@@ -145,10 +166,8 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, 1),
-        "cpu_baseline": {"value": val, "unit": "triplets/s", "cores": cores, "kind": "port", "sample": sample,
-                         "phase_ms": ph,
-                         "note": "oracle/vv_oracle.cpp = restated reference CPU layers + solver + sampler, OpenBLAS "
-                                 "from the SciPy wheel; the reference itself cannot be built here (glog/boost/protobuf absent)"},
+        "cpu_baseline": {"value": val, "unit": "triplets/s", "cores": cores, "kind": kind, "sample": sample,
+                         "phase_ms": ph, "note": CPU_NOTE[kind]},
         "e2e": {"value": val, "unit": "triplets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -345,8 +364,8 @@ def run_gpu(args):
             "hinge_terms_per_s": value * Nn,
         }
         if world == 1 and not args.no_cpu_baseline:
-            val, ms, cores, ph = cpu_reference_run(5, 2)
-            line["cpu_baseline"] = {"value": val, "unit": "triplets/s", "cores": cores, "kind": "port",
+            val, ms, cores, ph, kind = cpu_reference_run(5, 2)
+            line["cpu_baseline"] = {"value": val, "unit": "triplets/s", "cores": cores, "kind": kind, "note": CPU_NOTE[kind],
                                     "sample": "B=%d items per step (1/%d of the GPU step), same K/N/C/Nn, 5 timed steps after 2 warm-up"
                                               % (CPU_SAMPLE_B, B // CPU_SAMPLE_B), "ms_per_step": ms, "phase_ms": ph}
         print(json.dumps(line))

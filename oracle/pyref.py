@@ -1,0 +1,70 @@
+"""ctypes wrapper of oracle/_ref/libvv_ref.so: the REFERENCE's own layer classes compiled unmodified against shim
+headers (oracle/ref_shim/).  TEST INFRASTRUCTURE ONLY.  available() is False where the library was not built
+(e.g. a checkout without /root/reference): callers then fall back to the oracle port and say so."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(_HERE, "_ref", "libvv_ref.so")
+_lib = None
+
+
+def available():
+    return os.path.exists(SO)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(SO)
+        _lib.ref_describe.restype = C.c_char_p
+    return _lib
+
+
+def _p(a):
+    return C.c_void_p(a.ctypes.data) if a is not None else None
+
+
+def f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def net_forward_backward(data, W, b, B, Cc, Nn, margin=2.0, norm=2, dropout_ratio=0.9, seed=1701):
+    """Whole TRAIN net through the reference's layer classes.  Returns a dict incl. the dropout mask it drew."""
+    data, W, b = f32(data), f32(W), f32(b)
+    K = data.shape[-1]; N = W.shape[0]; R = Cc + Nn; M = R * B
+    out = dict(loss=np.zeros(1, np.float32), violations=np.zeros(1, np.float32), dW=np.zeros((N, K), np.float32),
+               db=np.zeros(N, np.float32), mask=np.ones((M, N), np.uint32), H=np.zeros((M, N), np.float32),
+               dZ=np.zeros((M, N), np.float32), target_score=np.zeros((B, Nn), np.float32),
+               neg_score=np.zeros((B, Nn), np.float32), seconds=np.zeros(3, np.float64))
+    rc = lib().ref_net_forward_backward(B, Cc, Nn, K, N, C.c_float(margin), norm, C.c_float(dropout_ratio), _p(data), _p(W), _p(b),
+                                        C.c_uint(seed), _p(out["loss"]), _p(out["violations"]), _p(out["dW"]), _p(out["db"]),
+                                        _p(out["mask"]), _p(out["H"]), _p(out["dZ"]), _p(out["target_score"]), _p(out["neg_score"]),
+                                        _p(out["seconds"]))
+    if rc != 0:
+        raise RuntimeError("reference net failed")
+    return out
+
+
+def normalization(x, dy):
+    x, dy = f32(x), f32(dy); y = np.empty_like(x); dx = np.empty_like(x)
+    assert lib().ref_normalization(x.shape[0], x.size // x.shape[0], _p(x), _p(dy), _p(y), _p(dx)) == 0
+    return y, dx
+
+
+def max_margin(s_true, s_bogus, margin=1.0, norm=1, loss_weight=1.0):
+    a, b = f32(s_true), f32(s_bogus)
+    loss = np.zeros(1, np.float32); viol = np.zeros(1, np.float32); dt = np.empty_like(a); dbg = np.empty_like(a)
+    assert lib().ref_max_margin(a.shape[0], a.size // a.shape[0], _p(a), _p(b), C.c_float(margin), norm, C.c_float(loss_weight),
+                                _p(loss), _p(viol), _p(dt), _p(dbg)) == 0
+    return float(loss[0]), float(viol[0]), dt, dbg
+
+
+def inner_product(X, W, b, dZ, regularization=0.0):
+    X, W, b, dZ = f32(X), f32(W), f32(b), f32(dZ)
+    M, K = X.shape; N = W.shape[0]
+    Z = np.empty((M, N), np.float32); dW = np.empty((N, K), np.float32); db = np.empty(N, np.float32); dX = np.empty((M, K), np.float32)
+    assert lib().ref_inner_product(M, N, K, _p(X), _p(W), _p(b), _p(dZ), C.c_float(regularization), _p(Z), _p(dW), _p(db), _p(dX)) == 0
+    return Z, dW, db, dX

@@ -1,0 +1,34 @@
+#!/bin/bash
+# Build oracle/_ref/libvv_ref.so: the reference's OWN layer sources, compiled where they lie under
+# /root/reference (never copied), against the shim headers in oracle/ref_shim/include and accessor classes
+# generated from the reference's .proto files.  Outputs only into oracle/_ref/ (git-ignored).
+# The reference's build system is not used (it needs glog/gflags/boost/protobuf/lmdb/leveldb/hdf5, all absent).
+set -e
+HERE="$(cd "$(dirname "$0")" && pwd)"
+ROOT="$(cd "$HERE/../.." && pwd)"
+REF="${VV_REFERENCE:-/root/reference}"
+OUT="$ROOT/oracle/_ref"
+[ -d "$REF/src/caffe" ] || { echo "no reference tree at $REF: keeping any prebuilt oracle/_ref"; exit 0; }
+mkdir -p "$OUT/obj"
+python "$HERE/gen_pb_shim.py" "$REF" "$OUT/gen" > /dev/null
+BLAS="$(python - <<'PY'
+import glob, os, scipy
+c = glob.glob(os.path.join(os.path.dirname(os.path.dirname(scipy.__file__)), "scipy.libs", "libscipy_openblas*.so"))
+print(c[0] if c else "")
+PY
+)"
+[ -n "$BLAS" ] || { echo "no OpenBLAS found"; exit 1; }
+CXXFLAGS="-std=c++14 -O2 -fPIC -DCPU_ONLY -w -include cstring -include climits -include unistd.h -include cstdlib -I$HERE/include -I$OUT/gen -I$REF/include"
+SRCS="blob syncedmem common util/math_functions layers/inner_product_layer layers/relu_layer layers/dropout_layer layers/eltwise_layer
+      layers/normalization_layer layers/sum_layer layers/split_layer layers/slice_layer layers/concat_layer layers/flatten_layer
+      layers/max_margin_loss_layer layers/loss_layer layers/neuron_layer"
+OBJS=""
+for s in $SRCS; do
+  o="$OUT/obj/$(basename $s).o"
+  if [ ! -f "$o" ] || [ "$REF/src/caffe/$s.cpp" -nt "$o" ]; then g++ $CXXFLAGS -c "$REF/src/caffe/$s.cpp" -o "$o"; fi
+  OBJS="$OBJS $o"
+done
+g++ $CXXFLAGS -c "$HERE/ref_driver.cpp" -o "$OUT/obj/ref_driver.o"
+# link the SciPy wheel's OpenBLAS in place (same image, hence same path, on the GPU box)
+g++ -shared -o "$OUT/libvv_ref.so" $OBJS "$OUT/obj/ref_driver.o" "$BLAS" -Wl,-rpath,"$(dirname "$BLAS")" -lpthread
+echo "built $OUT/libvv_ref.so"

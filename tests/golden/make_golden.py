@@ -1,0 +1,50 @@
+#!/usr/bin/env python
+"""Generate the golden vectors under tests/golden/ by running the REFERENCE's own layer code
+(oracle/_ref/libvv_ref.so, built by oracle/ref_shim/build_ref.sh from /root/reference) on seeded inputs.
+Run in the build container (the reference cannot travel): python tests/golden/make_golden.py
+Inputs are stored with the outputs so every consumer (oracle, CUDA path) replays exactly the same case;
+the dropout mask is the one the reference's DropoutLayer drew."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import pyref  # noqa: E402
+
+assert pyref.available(), "build oracle/_ref first: bash oracle/ref_shim/build_ref.sh"
+OUT = os.path.dirname(os.path.abspath(__file__))
+CASES = {            # name: B, C, Nn, K, N, norm, dropout
+    "net_cfg1_small": (8, 5, 10, 256, 64, 2, 0.9),      # the shipped structure (window +-2, 10 negatives, dropout 0.9, L2 margin 2)
+    "net_cfg4_small": (3, 17, 50, 128, 128, 2, 0.9),    # large-window variant
+    "net_l1_nodrop": (5, 3, 4, 64, 32, 1, 0.0),         # L1 hinge, no dropout layer
+}
+for name, (B, C, Nn, K, N, norm, ratio) in CASES.items():
+    rng = np.random.RandomState(abs(hash(name)) % (2 ** 31))
+    rng = np.random.RandomState(sum(map(ord, name)))
+    R = C + Nn
+    data = np.maximum(rng.normal(0, 1, (B, R, K)), 0).astype(np.float32)
+    data[0, 0] = 0.0                                   # an all-zero target row (dropout can do this too)
+    W = rng.normal(0, 0.05, (N, K)).astype(np.float32)
+    b = rng.normal(0, 0.05, N).astype(np.float32)
+    r = pyref.net_forward_backward(data, W, b, B, C, Nn, margin=2.0, norm=norm, dropout_ratio=ratio, seed=1701)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), B=B, C=C, Nn=Nn, K=K, N=N, norm=norm, dropout_ratio=ratio, margin=2.0,
+                        data=data, W=W, b=b, mask=r["mask"].astype(np.uint8), loss=r["loss"], violations=r["violations"],
+                        dW=r["dW"], db=r["db"], H=r["H"], dZ=r["dZ"], target_score=r["target_score"], neg_score=r["neg_score"])
+    print(name, "loss", r["loss"][0], "violations", r["violations"][0], "kept", r["mask"].mean())
+# single layers
+rng = np.random.RandomState(1701)
+x = rng.normal(0, 1, (6, 40)).astype(np.float32); x[2] = 0; dy = rng.normal(0, 1, (6, 40)).astype(np.float32)
+y, dx = pyref.normalization(x, dy)
+t = rng.normal(0, 10, (10, 5)).astype(np.float32); s = rng.normal(0, 10, (10, 5)).astype(np.float32)
+mm = {}
+for norm in (1, 2):
+    loss, viol, dt, dbg = pyref.max_margin(t, s, margin=1.0, norm=norm, loss_weight=1.0)
+    mm["loss%d" % norm] = loss; mm["viol%d" % norm] = viol; mm["dt%d" % norm] = dt; mm["db%d" % norm] = dbg
+X = rng.uniform(0, 1, (7, 60)).astype(np.float32); W = rng.uniform(-1, 1, (10, 60)).astype(np.float32)
+bb = rng.uniform(1, 2, 10).astype(np.float32); dZ = rng.normal(0, 1, (7, 10)).astype(np.float32)
+Z, dW, db, dX = pyref.inner_product(X, W, bb, dZ, regularization=0.5)
+np.savez_compressed(os.path.join(OUT, "layers.npz"), norm_x=x, norm_dy=dy, norm_y=y, norm_dx=dx, mm_t=t, mm_s=s,
+                    ip_X=X, ip_W=W, ip_b=bb, ip_dZ=dZ, ip_Z=Z, ip_dW=dW, ip_db=db, ip_dX=dX, **mm)
+print("layers.npz written")

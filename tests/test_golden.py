@@ -1,0 +1,74 @@
+"""Golden vectors produced by the REFERENCE's own layer code (tests/golden/make_golden.py, via oracle/_ref):
+the oracle must reproduce them; where oracle/_ref is present (build container) the reference is also run live."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+NETS = sorted(glob.glob(os.path.join(GOLD, "net_*.npz")))
+
+
+def rel(a, b):
+    return float(np.abs(np.asarray(a, np.float64) - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def test_fixtures_present():
+    assert len(NETS) >= 3 and os.path.exists(os.path.join(GOLD, "layers.npz")) and os.path.exists(os.path.join(GOLD, "make_golden.py"))
+
+
+@pytest.mark.parametrize("path", NETS, ids=[os.path.basename(p)[:-4] for p in NETS])
+def test_oracle_reproduces_reference_net(oracle, path):
+    g = np.load(path)
+    B, C, Nn = int(g["B"]), int(g["C"]), int(g["Nn"])
+    ratio = float(g["dropout_ratio"])
+    mask = g["mask"].astype(np.uint32) if ratio > 0 else None
+    for blas in ("builtin", "openblas"):
+        if blas == "openblas":
+            oracle.use_openblas(0)
+        o = oracle.net_forward_backward(g["data"], g["W"], g["b"], mask, B, C, Nn, margin=float(g["margin"]), norm=int(g["norm"]),
+                                        dropout_ratio=ratio if ratio > 0 else 0.5,
+                                        want=("loss", "violations", "dW", "db", "H", "dZ", "target_score", "neg_score"))
+        oracle.use_builtin_blas()
+        assert abs(o["loss"][0] - g["loss"][0]) <= 2e-6 * max(1, abs(g["loss"][0]))
+        assert o["violations"][0] == g["violations"][0]
+        for k in ("H", "target_score", "neg_score", "dZ", "dW", "db"):
+            assert rel(o[k], g[k]) < 2e-6, (k, rel(o[k], g[k]))
+
+
+def test_oracle_reproduces_reference_layers(oracle):
+    g = np.load(os.path.join(GOLD, "layers.npz"))
+    assert rel(oracle.normalization_forward(g["norm_x"]), g["norm_y"]) < 1e-6
+    assert rel(oracle.normalization_backward(g["norm_x"], g["norm_dy"]), g["norm_dx"]) < 2e-6
+    assert np.array_equal(oracle.normalization_forward(g["norm_x"])[2], np.zeros(40, np.float32))      # zero row -> zeros
+    for norm in (1, 2):
+        loss, viol, _ = oracle.max_margin_forward(g["mm_t"], g["mm_s"], margin=1.0, norm=norm)
+        dt, dbg = oracle.max_margin_backward(g["mm_t"], g["mm_s"], margin=1.0, norm=norm, loss_weight=1.0)
+        assert abs(loss - float(g["loss%d" % norm])) < 1e-6 * max(1, loss) and viol == float(g["viol%d" % norm])
+        assert rel(dt, g["dt%d" % norm]) < 1e-6 and rel(dbg, g["db%d" % norm]) < 1e-6
+    Z = oracle.ip_forward(g["ip_X"], g["ip_W"], g["ip_b"])
+    dW, db, dX = oracle.ip_backward(g["ip_dZ"], g["ip_X"], g["ip_W"], regularization=0.5, want_dx=True)
+    assert rel(Z, g["ip_Z"]) < 1e-6 and rel(dW, g["ip_dW"]) < 1e-6 and rel(db, g["ip_db"]) < 1e-6 and rel(dX, g["ip_dX"]) < 1e-6
+
+
+def test_live_reference_agrees_with_fixtures_and_oracle(oracle):
+    """Only where oracle/_ref was built (needs /root/reference at build time)."""
+    from oracle import pyref
+    if not pyref.available():
+        pytest.skip("oracle/_ref not built on this machine")
+    g = np.load(NETS[0])
+    r = pyref.net_forward_backward(g["data"], g["W"], g["b"], int(g["B"]), int(g["C"]), int(g["Nn"]), margin=2.0, norm=int(g["norm"]),
+                                   dropout_ratio=float(g["dropout_ratio"]), seed=1701)
+    assert np.array_equal(r["mask"].astype(np.uint8), g["mask"]) and rel(r["dW"], g["dW"]) < 1e-6   # fixtures are reproducible
+    # fresh random cases at the shipped widths: reference vs oracle
+    rng = np.random.RandomState(11)
+    for (B, C, Nn, K, N) in [(16, 5, 10, 4096, 512), (4, 17, 50, 512, 1024)]:
+        data = np.maximum(rng.normal(0, 1, (B, C + Nn, K)), 0).astype(np.float32)
+        W = rng.normal(0, 0.01, (N, K)).astype(np.float32); b = rng.normal(0, 0.01, N).astype(np.float32)
+        r = pyref.net_forward_backward(data, W, b, B, C, Nn, dropout_ratio=0.9, seed=3)
+        oracle.use_openblas(0)
+        o = oracle.net_forward_backward(data, W, b, r["mask"], B, C, Nn, dropout_ratio=0.9, want=("loss", "violations", "dW", "db", "dZ"))
+        oracle.use_builtin_blas()
+        assert abs(o["loss"][0] - r["loss"][0]) < 2e-6 * max(1, r["loss"][0]) and o["violations"][0] == r["violations"][0]
+        assert rel(o["dW"], r["dW"]) < 5e-6 and rel(o["db"], r["db"]) < 5e-6 and rel(o["dZ"], r["dZ"]) < 5e-6
