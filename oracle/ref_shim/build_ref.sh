@@ -18,7 +18,9 @@ print(c[0] if c else "")
 PY
 )"
 [ -n "$BLAS" ] || { echo "no OpenBLAS found"; exit 1; }
-CXXFLAGS="-std=c++14 -O2 -fPIC -DCPU_ONLY -w -include cstring -include climits -include unistd.h -include cstdlib -I$HERE/include -I$OUT/gen -I$REF/include"
+# hidden visibility: the reference's caffe:: symbols must not interpose with (or be interposed by) the product's
+# caffe_compat classes of the same names when both libraries are loaded into one process (bench.py)
+CXXFLAGS="-std=c++14 -O2 -fPIC -fvisibility=hidden -fvisibility-inlines-hidden -DCPU_ONLY -w -include cstring -include climits -include unistd.h -include cstdlib -I$HERE/include -I$OUT/gen -I$REF/include"
 SRCS="blob syncedmem common util/math_functions layers/inner_product_layer layers/relu_layer layers/dropout_layer layers/eltwise_layer
       layers/normalization_layer layers/sum_layer layers/split_layer layers/slice_layer layers/concat_layer layers/flatten_layer
       layers/max_margin_loss_layer layers/loss_layer layers/neuron_layer"
@@ -30,5 +32,5 @@ for s in $SRCS; do
 done
 g++ $CXXFLAGS -c "$HERE/ref_driver.cpp" -o "$OUT/obj/ref_driver.o"
 # link the SciPy wheel's OpenBLAS in place (same image, hence same path, on the GPU box)
-g++ -shared -o "$OUT/libvv_ref.so" $OBJS "$OUT/obj/ref_driver.o" "$BLAS" -Wl,-rpath,"$(dirname "$BLAS")" -lpthread
+g++ -shared -o "$OUT/libvv_ref.so" $OBJS "$OUT/obj/ref_driver.o" "$BLAS" -Wl,-Bsymbolic -Wl,-rpath,"$(dirname "$BLAS")" -lpthread
 echo "built $OUT/libvv_ref.so"

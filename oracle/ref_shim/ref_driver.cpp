@@ -24,13 +24,14 @@ double now() { return std::chrono::duration<double>(std::chrono::steady_clock::n
 std::unique_ptr<Blob<float> > nb() { return std::unique_ptr<Blob<float> >(new Blob<float>()); }
 }  // namespace
 
+#define REF_API __attribute__((visibility("default")))
 extern "C" {
 
-const char* ref_describe() { return "reference layer classes (eevignesh/videovector src/caffe/layers/*.cpp), CPU mode, shim-compiled"; }
+REF_API const char* ref_describe() { return "reference layer classes (eevignesh/videovector src/caffe/layers/*.cpp), CPU mode, shim-compiled"; }
 
 // Whole TRAIN net forward + backward.  data [B,R,K]; outputs may be NULL.  mask_out receives the 0/1 mask the
 // reference's DropoutLayer drew (caffe_rng_bernoulli) so the other implementations can replay it.
-int ref_net_forward_backward(int B, int C, int Nn, int K, int N, float margin, int norm, float dropout_ratio,
+REF_API int ref_net_forward_backward(int B, int C, int Nn, int K, int N, float margin, int norm, float dropout_ratio,
                              const float* data, const float* W, const float* bias, unsigned seed,
                              float* loss_out, float* viol_out, float* dW, float* db, unsigned* mask_out,
                              float* H_out, float* dZ_out, float* tscore_out, float* nscore_out, double* seconds) {
@@ -137,7 +138,7 @@ int ref_net_forward_backward(int B, int C, int Nn, int K, int N, float margin, i
 }
 
 // Single layers, for pinning the oracle's restatements one by one.
-int ref_normalization(int num, int dim, const float* x, const float* dy, float* y, float* dx) {
+REF_API int ref_normalization(int num, int dim, const float* x, const float* dy, float* y, float* dx) {
   try {
     Caffe::set_mode(Caffe::CPU);
     Blob<float> b(num, dim, 1, 1), t;
@@ -154,7 +155,7 @@ int ref_normalization(int num, int dim, const float* x, const float* dy, float* 
     return 0;
   } catch (const std::exception& e) { fprintf(stderr, "ref_driver: %s\n", e.what()); return -1; }
 }
-int ref_max_margin(int num, int ch, const float* s_true, const float* s_bogus, float margin, int norm, float loss_weight,
+REF_API int ref_max_margin(int num, int ch, const float* s_true, const float* s_bogus, float margin, int norm, float loss_weight,
                    float* loss, float* viol, float* d_true, float* d_bogus) {
   try {
     Caffe::set_mode(Caffe::CPU);
@@ -175,7 +176,7 @@ int ref_max_margin(int num, int ch, const float* s_true, const float* s_bogus, f
     return 0;
   } catch (const std::exception& e) { fprintf(stderr, "ref_driver: %s\n", e.what()); return -1; }
 }
-int ref_inner_product(int M, int N, int K, const float* X, const float* W, const float* bias, const float* dZ, float reg,
+REF_API int ref_inner_product(int M, int N, int K, const float* X, const float* W, const float* bias, const float* dZ, float reg,
                       float* Z, float* dW, float* db, float* dX) {
   try {
     Caffe::set_mode(Caffe::CPU);
@@ -201,6 +202,5 @@ int ref_inner_product(int M, int N, int K, const float* X, const float* W, const
     return 0;
   } catch (const std::exception& e) { fprintf(stderr, "ref_driver: %s\n", e.what()); return -1; }
 }
-void ref_set_blas_threads(int n);
 
 }  // extern "C"

@@ -123,7 +123,7 @@ def load():
         return _lib
     if not os.path.exists(LIB_PATH):
         raise VVError("libvv_b200.so not found at %s -- run `make` (or __graft_entry__.build())" % LIB_PATH)
-    lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    lib = C.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = res
