@@ -181,6 +181,7 @@ def workload_config(args, world):
             "global_batch": c["B"] * world, "K": c["K"], "N": c["N"], "C": c["C"], "Nn": c["Nn"],
             "parallelism": "dp%d" % world, "precision": getattr(args, "precision", "tf32x3"),
             "dgrad": False, "bank_rows": c["V"] * c["S"],
+            "gather": "fused into the GEMM TMA producer (gather4)" if getattr(args, "fused_gather", False) else "materialised X (K0 kernel)",
             "l2": "inputs larger than L2: each step streams a %.2f GB gathered operand (> 126 MB L2)" % (
                 (c["C"] + c["Nn"]) * c["B"] * c["K"] * (8 if getattr(args, "precision", "tf32x3") == "tf32x3" else 4) / 1e9)}
 
@@ -220,6 +221,8 @@ def run_gpu(args):
         g = torch.Generator(device="cuda").manual_seed(1701)
         W0 = torch.randn(N, K, device="cuda", generator=g) * 0.001          # gaussian filler std 0.001, bias 0
         tr.set_weights(W0, torch.zeros(N, device="cuda"))
+        if args.fused_gather:
+            tr.set_bank(bank)          # gather-fused GEMMs (TMA gather4): correct but measured 2-4x slower, see DESIGN.md
         if world > 1:
             idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
             if rank == 0:
@@ -329,7 +332,8 @@ def run_gpu(args):
         for name, f in (("fc7_forward", flops), ("wgrad", flops)):
             ms = phase[name]
             kern[name] = {"ms": ms, "bound": "tensor", "achieved_tflops": flops / (ms * 1e-3) / 1e12 if ms > 0 else None}
-        bytes_alg = {"gather": M * K * 4 * (1 + (2 if prec == "tf32x3" else (0.5 if prec == "bf16" else 1))),
+        bytes_alg = {"gather": (M * K * 4 * (1 + (2 if prec == "tf32x3" else (0.5 if prec == "bf16" else 1)))) if not args.fused_gather
+                     else ((M + 127) // 128 * 128) * 8 + M * 8,
                      "rank_loss_forward": M * N * 4,
                      "rank_loss_backward": M * N * 4 * (1 + (2 if prec == "tf32x3" else (0.5 if prec == "bf16" else 1))),
                      "sgd_update": N * K * 4 * (5 + tr._lib.vv_ip_wgrad_auto_nsplit(M, N, K, ops.PREC[prec])
@@ -383,6 +387,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="tf32x3", choices=["tf32x3", "tf32", "bf16", "fp32_simt"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fused-gather", action="store_true", help="fold K0 into the GEMM TMA producer (gather4) instead of materialising X")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

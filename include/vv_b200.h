@@ -138,6 +138,25 @@ int vv_ip_bias_grad(const float* dZ, int M, int N, float* db, vv_stream_t stream
 int vv_ip_dgrad(vv_operand_t dZ, vv_operand_t W, int M, int N, int K, int prec,
                 float* dX, vv_stream_t stream);
 
+/* ---- gather-fused variants: K0 folded into K1's TMA producer (cp.async.bulk.tensor tile::gather4). ----
+ * The X operand is never materialised: `bank` is the operand copy of the whole resident feature bank
+ * (vv_prepare_operand of the bank, made once) and rowmap/delta come from vv_gather_plan:
+ *   rowmap [round_up(R*B,128)] int32 : bank row of X row j*B+b
+ *   delta  [round_up(R*B,128)] fp32  : correction of feature K-1 for rows hit by the K-1 copy quirk
+ * forward : Z = bank[rowmap] W^T + delta (x) W[:,K-1] + bias      (wlast [N] = W[:,K-1], fp32)
+ * wgrad   : dW = dZ^T bank[rowmap]; the quirk's contribution to dW[:,K-1] is sum_m delta[m] dZ[m,:], which
+ *           vv_rank_loss_backward_ex accumulates (dq_accum) and vv_add_column adds.  Tensor-core precisions only. */
+int vv_gather_plan(const float* bank, int K, const int32_t* idx, const int32_t* quirk, int B, int R,
+                   int32_t* rowmap, float* delta, vv_stream_t stream);
+int vv_ip_forward_gathered(vv_operand_t bank, int64_t bank_rows, const int32_t* rowmap, const float* delta,
+                           const float* wlast, vv_operand_t W, const float* bias, int M, int N, int K, int prec,
+                           const vv_act_t* act, float* Z, float* H, vv_stream_t stream);
+int vv_ip_wgrad_gathered(vv_operand_t dZ, vv_operand_t bank, int64_t bank_rows, const int32_t* rowmap,
+                         int M, int N, int K, int prec, float regularization, float* dW_parts, int nsplit,
+                         vv_stream_t stream);
+/* A[i*ld + col] += v[i], i < n */
+int vv_add_column(float* A, int64_t ld, int col, const float* v, int n, vv_stream_t stream);
+
 /* out[i] = sum_s parts[s*stride + i] */
 int vv_reduce_parts(const float* parts, int nparts, int64_t stride, int64_t count,
                     float* out, vv_stream_t stream);
@@ -181,6 +200,11 @@ int vv_rank_loss_backward(const float* H, const vv_rank_cfg_t* cfg, const float*
                           float loss_weight, int act_fused, float dropout_scale,
                           float* dZ, void* dZop_hi, void* dZop_lo, int prec,
                           float* db_accum, vv_stream_t stream);
+/* same, plus dq_accum [N] += sum_m delta[m] * dZ[m,:] (zero it first; see the gather-fused wgrad) */
+int vv_rank_loss_backward_ex(const float* H, const vv_rank_cfg_t* cfg, const float* stats,
+                             float loss_weight, int act_fused, float dropout_scale,
+                             float* dZ, void* dZop_hi, void* dZop_lo, int prec,
+                             float* db_accum, const float* delta, float* dq_accum, vv_stream_t stream);
 
 /* ------------------------------------------------------------------------- */
 /* K4: SGDSolver::ComputeUpdateValue + Net::Update + Blob::Update in one pass.  */
@@ -292,6 +316,9 @@ float* vv_trainer_bias_hist(vv_trainer_t* t);
 float* vv_trainer_weight_diff(vv_trainer_t* t);  /* dW after the step: = hist (reference semantics) */
 float* vv_trainer_bias_diff(vv_trainer_t* t);
 float* vv_trainer_blob(vv_trainer_t* t, const char* name); /* "X","Z","H","dZ","stats","loss","violations","dW_raw","db_raw" */
+/* Register the resident feature bank: builds its operand copies once (tf32x3: hi+lo, bf16: bf16) so that
+ * vv_trainer_step on this bank runs the gather-fused GEMMs (no materialised X).  Not used in keep_blobs mode. */
+int vv_trainer_set_bank(vv_trainer_t* t, const float* bank, int64_t bank_rows);
 /* call after writing weights/bias through the pointers above */
 int vv_trainer_sync_weights(vv_trainer_t* t);
 /* One step.  bank: device feature bank; idx/quirk: DEVICE [B,R] int32 for this

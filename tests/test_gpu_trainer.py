@@ -108,6 +108,62 @@ def test_solver_trajectory_matches_oracle(oracle, prec):
     tr.close(); smp.close()
 
 
+@pytest.mark.parametrize("prec,tol", [("tf32x3", 1e-5), ("tf32", 2e-2), ("bf16", 5e-2)])
+@pytest.mark.parametrize("B,C,Nn,K,N", [(128, 5, 10, 4096, 512), (24, 17, 50, 512, 1024), (8, 3, 4, 64, 32)])
+def test_gather_fused_step_matches_oracle(oracle, prec, tol, B, C, Nn, K, N):
+    """K0 folded into the GEMMs' TMA producer (gather4 from the registered bank): same results as the oracle,
+    including rows hit by the K-1 copy quirk (handled as a rank-1 correction in the fc7 epilogue / dW[:,K-1])."""
+    bank, smp, W0, b0 = setup_problem(B, C, Nn, K, N)
+    bank_np = bank.cpu().numpy()
+    ratio = 0.9 if N >= 512 else 0.5
+    tr = ops.Trainer(ops.trainer_cfg(B, C, Nn, K, N, dropout_ratio=ratio, dropout_mode=DROPOUT_MASK01, prec=prec))
+    tr.set_weights(torch.as_tensor(W0).cuda(), torch.as_tensor(b0).cuda())
+    tr.set_bank(bank)
+    rng = np.random.RandomState(3)
+    oracle.use_openblas(0)
+    saw_quirk = False
+    for it in range(3):
+        idx, quirk = smp.next()
+        saw_quirk |= bool((quirk != -2).any())
+        mask = (rng.uniform(0, 1, ((C + Nn) * B, N)) > ratio).astype(np.uint32)
+        tr.step(bank, torch.as_tensor(idx).cuda(), torch.as_tensor(quirk).cuda(),
+                torch.as_tensor(mask.astype(np.int32)).cuda(), it=it, do_update=False)
+        ref = oracle.net_forward_backward(oracle_data_blob(bank_np, idx, quirk), W0, b0, mask, B, C, Nn, margin=2.0,
+                                          norm=2, dropout_ratio=ratio, want=("loss", "violations", "dW", "db", "H"))
+        loss = tr.tensor("loss").item()
+        assert abs(loss - ref["loss"][0]) <= tol * max(1.0, abs(ref["loss"][0])), (loss, ref["loss"][0])
+        assert rel(tr.tensor("H"), ref["H"]) < tol
+        if tol <= 1e-5:
+            assert tr.tensor("violations").item() == ref["violations"][0]
+            assert rel(tr.tensor("dW_raw"), ref["dW"]) < 2e-5, rel(tr.tensor("dW_raw"), ref["dW"])
+            # the quirk column specifically
+            assert rel(tr.tensor("dW_raw")[:, K - 1], ref["dW"][:, K - 1]) < 2e-5
+            assert rel(tr.tensor("db_raw"), ref["db"]) < 2e-5
+        else:
+            assert rel_l2(tr.tensor("dW_raw"), ref["dW"]) < 10 * tol
+    assert saw_quirk
+    oracle.use_builtin_blas()
+    tr.close(); smp.close()
+
+
+def test_gather_fused_training_equals_materialised_path():
+    """Same trainer, same stream, with and without the registered bank: weights track each other."""
+    B, C, Nn, K, N = 64, 5, 10, 1024, 256
+    res = []
+    for fused in (False, True):
+        bank, smp, W0, b0 = setup_problem(B, C, Nn, K, N, V=128, S=16, P=500)
+        tr = ops.Trainer(ops.trainer_cfg(B, C, Nn, K, N, dropout_ratio=0.9, dropout_mode=DROPOUT_PHILOX, prec="tf32x3", base_lr=0.01))
+        tr.set_weights(torch.as_tensor(W0).cuda(), torch.as_tensor(b0).cuda())
+        if fused:
+            tr.set_bank(bank)
+        for it in range(20):
+            idx, quirk = smp.next()
+            tr.step(bank, torch.as_tensor(idx).cuda(), torch.as_tensor(quirk).cuda(), None, it=it)
+        res.append((tr.tensor("W").clone(), tr.tensor("b").clone(), tr.tensor("loss").item()))
+        tr.close(); smp.close()
+    assert rel(res[1][0], res[0][0]) < 1e-5 and rel(res[1][1], res[0][1]) < 1e-5 and abs(res[1][2] - res[0][2]) < 1e-5
+
+
 def test_dgrad_in_trainer_matches_oracle(oracle):
     B, C, Nn, K, N = 16, 5, 10, 256, 64
     bank, smp, W0, b0 = setup_problem(B, C, Nn, K, N)

@@ -73,6 +73,10 @@ struct vv_trainer {
   DevBuf W, b, Wh, bh, W_hi, W_lo;
   // activations / gradients
   DevBuf Xf, X_hi, X_lo, Zf, H, stats, item_loss, item_viol, dZf, dZ_hi, dZ_lo, dW_parts, dbx, dX;
+  // gather-fused path: operand copies of the registered bank, per-step gather plan, quirk corrections
+  DevBuf bank_hi, bank_lo, rowmap, delta, wlast, dq;
+  const float* bank_reg = nullptr; int64_t bank_reg_rows = 0;
+  bool x_allocated = false;
   ncclComm_t comm = nullptr;
   int last_launches = 0;
   // optional per-phase timing
@@ -106,9 +110,12 @@ struct vv_trainer {
     int rc;
 #define A(buf, n) if ((rc = buf.alloc(n))) return rc
     A(W, NK * 4); A(b, size_t(cfg.N) * 4); A(Wh, NK * 4); A(bh, size_t(cfg.N) * 4);
-    if (cfg.prec == VV_PREC_TF32X3) { A(W_hi, NK * 4); A(W_lo, NK * 4); A(X_hi, MK * 4); A(X_lo, MK * 4); A(dZ_hi, MN * 4); A(dZ_lo, MN * 4); }
-    if (cfg.prec == VV_PREC_BF16) { A(W_hi, NK * 2); A(X_hi, MK * 2); A(dZ_hi, MN * 2); }
-    if (f32op || cfg.keep_blobs) { A(Xf, MK * 4); A(dZf, MN * 4); }
+    // the materialised X operand (1-2 GB at B=4096) is allocated on first use: the gather-fused path never needs it
+    if (cfg.prec == VV_PREC_TF32X3) { A(W_hi, NK * 4); A(W_lo, NK * 4); A(dZ_hi, MN * 4); A(dZ_lo, MN * 4); }
+    if (cfg.prec == VV_PREC_BF16) { A(W_hi, NK * 2); A(dZ_hi, MN * 2); }
+    if (f32op || cfg.keep_blobs) { A(dZf, MN * 4); }
+    A(wlast, size_t(cfg.N) * 4); A(dq, size_t(cfg.N) * 4);
+    A(rowmap, size_t((M + 127) / 128 * 128) * 4); A(delta, size_t((M + 127) / 128 * 128) * 4);
     if (cfg.keep_blobs) { A(Zf, MN * 4); }
     A(H, MN * 4);
     A(stats, size_t(cfg.B) * vv_rank_stats_stride(cfg.Nn) * 4);
@@ -132,10 +139,27 @@ struct vv_trainer {
     }
     return VV_OK;
   }
+  int alloc_x() {
+    if (x_allocated) return VV_OK;
+    const size_t MK = size_t(M) * cfg.K;
+    int rc;
+    if (cfg.prec == VV_PREC_TF32X3) { if ((rc = X_hi.alloc(MK * 4))) return rc; if ((rc = X_lo.alloc(MK * 4))) return rc; }
+    if (cfg.prec == VV_PREC_BF16) { if ((rc = X_hi.alloc(MK * 2))) return rc; }
+    if (needs_f32_operand() || cfg.keep_blobs) { if ((rc = Xf.alloc(MK * 4))) return rc; }
+    x_allocated = true;
+    return VV_OK;
+  }
+  vv_operand_t opBank() const {
+    vv_operand_t o;
+    if (cfg.prec == VV_PREC_TF32X3) { o.hi = bank_hi.p; o.lo = bank_lo.p; }
+    else if (cfg.prec == VV_PREC_BF16) { o.hi = bank_hi.p; o.lo = nullptr; }
+    else { o.hi = bank_reg; o.lo = nullptr; }      // TF32: TMA reads the fp32 bank itself
+    return o;
+  }
   ~vv_trainer() {
     if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
     DevBuf* all[] = {&W, &b, &Wh, &bh, &W_hi, &W_lo, &Xf, &X_hi, &X_lo, &Zf, &H, &stats, &item_loss, &item_viol,
-                     &dZf, &dZ_hi, &dZ_lo, &dW_parts, &dbx, &dX};
+                     &dZf, &dZ_hi, &dZ_lo, &dW_parts, &dbx, &dX, &bank_hi, &bank_lo, &rowmap, &delta, &wlast, &dq};
     for (DevBuf* d : all) d->release();
     for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
     if (ev_grad) cudaEventDestroy(ev_grad);
@@ -186,8 +210,25 @@ extern "C" int vv_trainer_last_launches(const vv_trainer_t* t) { return t->last_
 
 extern "C" int vv_trainer_sync_weights(vv_trainer_t* t) {
   const int64_t NK = int64_t(t->cfg.N) * t->cfg.K;
-  return vv_prepare_operand(t->W.as<float>(), NK, t->cfg.prec, t->W_hi.p, t->W_lo.p,
-                            reinterpret_cast<vv_stream_t>(t->stream));
+  vv_stream_t s = reinterpret_cast<vv_stream_t>(t->stream);
+  int rc = vv_copy_strided(t->W.as<float>() + (t->cfg.K - 1), t->cfg.K, t->wlast.as<float>(), 1, t->cfg.N, 1, s);   // wlast = W[:, K-1]
+  if (rc) return rc;
+  return vv_prepare_operand(t->W.as<float>(), NK, t->cfg.prec, t->W_hi.p, t->W_lo.p, s);
+}
+
+extern "C" int vv_trainer_set_bank(vv_trainer_t* t, const float* bank, int64_t bank_rows) {
+  if (!t || !bank || bank_rows <= 0) { set_error("set_bank: bad arguments"); return VV_ERR_INVALID; }
+  const vv_trainer_cfg_t& c = t->cfg;
+  if (c.prec == VV_PREC_FP32_SIMT || c.keep_blobs) { t->bank_reg = nullptr; return VV_OK; }   // materialised path
+  vv_stream_t s = reinterpret_cast<vv_stream_t>(t->stream);
+  const int64_t n = bank_rows * c.K;
+  int rc;
+  t->bank_hi.release(); t->bank_lo.release();
+  if (c.prec == VV_PREC_TF32X3) { if ((rc = t->bank_hi.alloc(size_t(n) * 4))) return rc; if ((rc = t->bank_lo.alloc(size_t(n) * 4))) return rc; }
+  if (c.prec == VV_PREC_BF16) { if ((rc = t->bank_hi.alloc(size_t(n) * 2))) return rc; }
+  if ((rc = vv_prepare_operand(bank, n, c.prec, t->bank_hi.p, t->bank_lo.p, s))) return rc;
+  t->bank_reg = bank; t->bank_reg_rows = bank_rows;
+  return VV_OK;
 }
 
 extern "C" int vv_trainer_step(vv_trainer_t* t, const float* bank, int64_t bank_rows, const int32_t* idx,
@@ -199,10 +240,16 @@ extern "C" int vv_trainer_step(vv_trainer_t* t, const float* bank, int64_t bank_
   int rc;
   launches_reset();
   if (t->timing && t->timed_steps >= 256) { set_error("timing: read vv_trainer_phase_ms at least every 256 steps"); return VV_ERR_INVALID; }
-  // K0
+  // K0: either a gather plan (fused path: the GEMMs fetch the bank rows themselves) or the materialised X
+  const bool fused_gather = t->bank_reg != nullptr && bank == t->bank_reg && bank_rows == t->bank_reg_rows;
   t->tic(0);
-  if ((rc = vv_gather_rows(bank, bank_rows, K, idx, quirk, c.B, t->R, t->Xf.as<float>(), t->X_hi.p, t->X_lo.p, c.prec,
-                           nullptr, s))) return rc;
+  if (fused_gather) {
+    if ((rc = vv_gather_plan(bank, K, idx, quirk, c.B, t->R, t->rowmap.as<int32_t>(), t->delta.as<float>(), s))) return rc;
+  } else {
+    if ((rc = t->alloc_x())) return rc;
+    if ((rc = vv_gather_rows(bank, bank_rows, K, idx, quirk, c.B, t->R, t->Xf.as<float>(), t->X_hi.p, t->X_lo.p, c.prec,
+                             nullptr, s))) return rc;
+  }
   t->toc(0);
   // K1 forward with fused bias + ReLU + dropout
   vv_act_t act; memset(&act, 0, sizeof(act));
@@ -214,8 +261,13 @@ extern "C" int vv_trainer_step(vv_trainer_t* t, const float* bank, int64_t bank_
     set_error("trainer: dropout mask mode needs a mask"); return VV_ERR_INVALID;
   }
   t->tic(1);
-  if ((rc = vv_ip_forward(t->opX(), t->opW(), t->b.as<float>(), M, N, K, c.prec, &act, t->Zf.as<float>(),
-                          t->H.as<float>(), s))) return rc;
+  if (fused_gather) {
+    if ((rc = vv_ip_forward_gathered(t->opBank(), bank_rows, t->rowmap.as<int32_t>(), t->delta.as<float>(), t->wlast.as<float>(),
+                                     t->opW(), t->b.as<float>(), M, N, K, c.prec, &act, nullptr, t->H.as<float>(), s))) return rc;
+  } else {
+    if ((rc = vv_ip_forward(t->opX(), t->opW(), t->b.as<float>(), M, N, K, c.prec, &act, t->Zf.as<float>(),
+                            t->H.as<float>(), s))) return rc;
+  }
   t->toc(1);
   // K2
   t->tic(2);
@@ -225,15 +277,26 @@ extern "C" int vv_trainer_step(vv_trainer_t* t, const float* bank, int64_t bank_
   // K3 (+ bias gradient)
   t->tic(3);
   VV_CUDA(cudaMemsetAsync(t->dbx.p, 0, size_t(N) * 4, t->stream));
+  if (fused_gather) VV_CUDA(cudaMemsetAsync(t->dq.p, 0, size_t(N) * 4, t->stream));
   count_launch();
   const float dscale = has_dropout ? dropout_scale(c.dropout_ratio) : 1.f;
-  if ((rc = vv_rank_loss_backward(t->H.as<float>(), &t->rank, t->stats.as<float>(), c.loss_weight, 1, dscale,
-                                  t->dZf.as<float>(), t->dZ_hi.p, t->dZ_lo.p, c.prec, t->dbx.as<float>(), s))) return rc;
+  if ((rc = vv_rank_loss_backward_ex(t->H.as<float>(), &t->rank, t->stats.as<float>(), c.loss_weight, 1, dscale,
+                                     t->dZf.as<float>(), t->dZ_hi.p, t->dZ_lo.p, c.prec, t->dbx.as<float>(),
+                                     fused_gather ? t->delta.as<float>() : nullptr, fused_gather ? t->dq.as<float>() : nullptr, s))) return rc;
   t->toc(3);
   // K1 wgrad into split-K slabs
   t->tic(4);
-  if ((rc = vv_ip_wgrad(t->opdZ(), t->opX(), M, N, K, c.prec, c.regularization, t->dW_parts.as<float>(), t->nsplit,
-                        nullptr, 0, s))) return rc;
+  if (fused_gather) {
+    if ((rc = vv_ip_wgrad_gathered(t->opdZ(), t->opBank(), bank_rows, t->rowmap.as<int32_t>(), M, N, K, c.prec, c.regularization,
+                                   t->dW_parts.as<float>(), t->nsplit, s))) return rc;
+    // the K-1 copy quirk's share of dW[:, K-1] (scaled like the GEMM output)
+    const double reg = double(c.regularization) / 2;
+    if (reg > 0) { if ((rc = vv_axpby(N, float(1.0 + reg), t->dq.as<float>(), 0.f, t->dq.as<float>(), s))) return rc; }
+    if ((rc = vv_add_column(t->dW_parts.as<float>(), K, K - 1, t->dq.as<float>(), N, s))) return rc;
+  } else {
+    if ((rc = vv_ip_wgrad(t->opdZ(), t->opX(), M, N, K, c.prec, c.regularization, t->dW_parts.as<float>(), t->nsplit,
+                          nullptr, 0, s))) return rc;
+  }
   t->toc(4);
   if (c.compute_dgrad) {
     t->tic(5);
@@ -268,6 +331,7 @@ extern "C" int vv_trainer_step(vv_trainer_t* t, const float* bank, int64_t bank_
     if ((rc = vv_sgd_update(t->W.as<float>(), t->dW_parts.as<float>(), nparts, NK, t->Wh.as<float>(),
                             t->dW_parts.as<float>(), NK, rate * c.lr_mult[0], c.momentum, c.weight_decay * c.decay_mult[0],
                             c.reg_type, gscale, t->W_hi.p, t->W_lo.p, c.prec, s))) return rc;
+    if ((rc = vv_copy_strided(t->W.as<float>() + (K - 1), K, t->wlast.as<float>(), 1, N, 1, s))) return rc;
     if ((rc = vv_sgd_update(t->b.as<float>(), t->dbx.as<float>(), 1, 0, t->bh.as<float>(), t->dbx.as<float>(), N,
                             rate * c.lr_mult[1], c.momentum, c.weight_decay * c.decay_mult[1], c.reg_type, gscale,
                             nullptr, nullptr, VV_PREC_FP32_SIMT, s))) return rc;
@@ -315,6 +379,7 @@ extern "C" int vv_trainer_extract(vv_trainer_t* t, const float* F, int64_t rows,
   vv_act_t act; memset(&act, 0, sizeof(act));
   act.relu = 1; act.dropout_mode = VV_DROPOUT_NONE;      // TEST phase: dropout is a copy (dropout_layer.cpp:46-48)
   int rc;
+  if ((rc = t->alloc_x())) return rc;
   launches_reset();
   for (int64_t r0 = 0; r0 < rows; r0 += t->M) {
     const int m = int(rows - r0 < t->M ? rows - r0 : t->M);

@@ -35,6 +35,7 @@ static int fill_epilogue(const vv_act_t* act, const float* bias, float* Z, GemmE
   e->bias = bias; e->Z = Z; e->has_act = act ? 1 : 0; e->out_scale = 1.f;
   e->relu = 0; e->negative_slope = 0.f; e->dropout_mode = VV_DROPOUT_NONE; e->dropout_scale = 1.f;
   e->dropout_thres = 0; e->mask = nullptr; e->mask_out = nullptr; e->seed = 0; e->step = 0;
+  e->delta = nullptr; e->wlast = nullptr;
   if (!act) return VV_OK;
   e->relu = act->relu; e->negative_slope = act->negative_slope;
   e->dropout_mode = act->dropout_mode;
@@ -74,7 +75,7 @@ extern "C" int vv_ip_forward(vv_operand_t X, vv_operand_t W, const float* bias, 
   VV_REQUIRE(X.hi && W.hi && H && M > 0 && N > 0 && K > 0, "ip_forward: bad arguments");
   GemmProblem g;
   g.kind = GEMM_FWD; g.prec = prec; g.A = X; g.B = W; g.M = M; g.N = N; g.K = K;
-  g.D = H; g.slab_stride = 0; g.nsplit = 1;
+  g.D = H; g.slab_stride = 0; g.nsplit = 1; g.rowmap = nullptr; g.bank_rows = 0;
   int rc = fill_epilogue(act, bias, Z, &g.epi);
   if (rc) return rc;
   if (!act && Z && Z != H) { set_error("ip_forward: without an activation pass H only (Z == NULL)"); return VV_ERR_INVALID; }
@@ -112,7 +113,7 @@ extern "C" int vv_ip_wgrad(vv_operand_t dZ, vv_operand_t X, int M, int N, int K,
                            float* dW_parts, int nsplit, void* workspace, size_t workspace_bytes, vv_stream_t stream) {
   VV_REQUIRE(dZ.hi && X.hi && dW_parts && M > 0 && N > 0 && K > 0 && nsplit >= 0, "ip_wgrad: bad arguments");
   GemmProblem g;
-  g.kind = GEMM_WGRAD; g.prec = prec; g.A = dZ; g.B = X; g.M = M; g.N = N; g.K = K;
+  g.kind = GEMM_WGRAD; g.prec = prec; g.A = dZ; g.B = X; g.M = M; g.N = N; g.K = K; g.rowmap = nullptr; g.bank_rows = 0;
   int rc = fill_epilogue(nullptr, nullptr, nullptr, &g.epi);
   if (rc) return rc;
   // ref: inner_product_layer.cpp:80,88-91  dW *= (1 + regularization/2) when regularization/2 > 0
@@ -137,8 +138,41 @@ extern "C" int vv_ip_dgrad(vv_operand_t dZ, vv_operand_t W, int M, int N, int K,
   VV_REQUIRE(dZ.hi && W.hi && dX && M > 0 && N > 0 && K > 0, "ip_dgrad: bad arguments");
   GemmProblem g;
   g.kind = GEMM_DGRAD; g.prec = prec; g.A = dZ; g.B = W; g.M = M; g.N = N; g.K = K;
-  g.D = dX; g.slab_stride = 0; g.nsplit = 1;
+  g.D = dX; g.slab_stride = 0; g.nsplit = 1; g.rowmap = nullptr; g.bank_rows = 0;
   int rc = fill_epilogue(nullptr, nullptr, nullptr, &g.epi);
   if (rc) return rc;
   return run_gemm(g, stream);
+}
+
+// ---- gather-fused variants (K0 folded into K1's TMA producer) --------------------------------------------
+extern "C" int vv_ip_forward_gathered(vv_operand_t bank, int64_t bank_rows, const int32_t* rowmap, const float* delta,
+                                      const float* wlast, vv_operand_t W, const float* bias, int M, int N, int K, int prec,
+                                      const vv_act_t* act, float* Z, float* H, vv_stream_t stream) {
+  VV_REQUIRE(bank.hi && rowmap && W.hi && H && M > 0 && N > 0 && K > 0 && bank_rows > 0, "ip_forward_gathered: bad arguments");
+  VV_REQUIRE(prec != VV_PREC_FP32_SIMT, "ip_forward_gathered needs a tensor-core precision");
+  VV_REQUIRE(!delta || wlast, "ip_forward_gathered: delta needs wlast");
+  GemmProblem g;
+  g.kind = GEMM_FWD; g.prec = prec; g.A = bank; g.B = W; g.M = M; g.N = N; g.K = K;
+  g.D = H; g.slab_stride = 0; g.nsplit = 1; g.rowmap = rowmap; g.bank_rows = bank_rows;
+  int rc = fill_epilogue(act, bias, Z, &g.epi);
+  if (rc) return rc;
+  if (!act) g.epi.Z = nullptr;
+  g.epi.delta = delta; g.epi.wlast = wlast;
+  return gemm_tc_launch(g, stream);
+}
+
+extern "C" int vv_ip_wgrad_gathered(vv_operand_t dZ, vv_operand_t bank, int64_t bank_rows, const int32_t* rowmap, int M, int N,
+                                    int K, int prec, float regularization, float* dW_parts, int nsplit, vv_stream_t stream) {
+  VV_REQUIRE(dZ.hi && bank.hi && rowmap && dW_parts && M > 0 && N > 0 && K > 0 && nsplit >= 1 && bank_rows > 0,
+             "ip_wgrad_gathered: bad arguments");
+  VV_REQUIRE(prec != VV_PREC_FP32_SIMT, "ip_wgrad_gathered needs a tensor-core precision");
+  GemmProblem g;
+  g.kind = GEMM_WGRAD; g.prec = prec; g.A = dZ; g.B = bank; g.M = M; g.N = N; g.K = K;
+  g.rowmap = rowmap; g.bank_rows = bank_rows;
+  int rc = fill_epilogue(nullptr, nullptr, nullptr, &g.epi);
+  if (rc) return rc;
+  const double reg = double(regularization) / 2;
+  g.epi.out_scale = reg > 0 ? float(1.0 + reg) : 1.f;
+  g.slab_stride = (long long)N * K; g.D = dW_parts; g.nsplit = nsplit;
+  return gemm_tc_launch(g, stream);
 }

@@ -21,6 +21,9 @@ struct GemmEpilogue {
   const uint32_t* mask; uint32_t* mask_out;
   uint64_t seed, step;
   float out_scale;        // multiplies the accumulator (wgrad regularization), 1 otherwise
+  // gather-fused forward: Z[m,:] += delta[m] * wlast[:]  (the K-1 copy quirk as a rank-1 correction)
+  const float* delta;     // [M] or NULL
+  const float* wlast;     // [N] = W[:, K-1]
 };
 
 // D_rows x D_cols output (row pitch ldd), reduction length red.
@@ -32,6 +35,10 @@ struct GemmProblem {
   int M, N, K;            // the fc7 dims (rows, outputs, inputs) -- NOT the tile dims
   float* D; int64_t slab_stride; int nsplit;
   GemmEpilogue epi;
+  // gather-fused variants: the X operand (A of FWD, B of WGRAD) is the resident bank's operand copy and its
+  // rows are fetched by index with TMA gather4; rowmap[m] = bank row of X row m (padded to a multiple of 128)
+  const int32_t* rowmap;  // NULL = X is materialised
+  int64_t bank_rows;
 };
 
 int gemm_tc_launch(const GemmProblem& p, cudaStream_t stream);     // tcgen05 path (TF32X3 / TF32 / BF16)
@@ -42,6 +49,13 @@ bool gemm_tc_supported(const GemmProblem& p, const char** why);
 // Applies bias/ReLU/dropout to 4 consecutive columns [col, col+4) of row `row`.
 __device__ __forceinline__ void epilogue_act4(const GemmEpilogue& e, int N, int row, int col,
                                               float4& v, float4& z_out) {
+  if (e.delta) {
+    const float d = e.delta[row];
+    if (d != 0.f) {
+      const float4 w = *reinterpret_cast<const float4*>(e.wlast + col);
+      v.x = fmaf(d, w.x, v.x); v.y = fmaf(d, w.y, v.y); v.z = fmaf(d, w.z, v.z); v.w = fmaf(d, w.w, v.w);
+    }
+  }
   if (e.bias) {
     const float4 b = *reinterpret_cast<const float4*>(e.bias + col);
     v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;

@@ -33,11 +33,16 @@ struct TcParams {
   int chunk_kb;                 // k-blocks accumulated in TMEM before promotion to fp32 registers
   float* D; long long slab_stride;
   int act_N;                    // row pitch of mask/Z (= N of the layer) for the FWD epilogue
+  const int* rowmap;            // gather variants: bank row of every X row (padded to a multiple of 128)
   GemmEpilogue epi;
 };
 
-template <bool kTF32, bool kAMN, bool kBMN, int kNProd, int kBlockN, int kStages, bool kFwdEpi>
+template <bool kTF32, bool kAMN, bool kBMN, int kNProd, int kBlockN, int kStages, bool kFwdEpi, bool kGather = false>
 struct Cfg {
+  // kGather: the X operand (A when K-major = FWD, B when MN-major = WGRAD) is gathered row-wise from the bank
+  static constexpr bool gather = kGather;
+  static constexpr bool gather_a = kGather && !kAMN;   // FWD : A rows = X rows
+  static constexpr bool gather_b = kGather && kAMN;    // WGRAD: B k-rows = X rows
   static constexpr bool tf32 = kTF32;
   static constexpr bool a_mn = kAMN, b_mn = kBMN;
   static constexpr int nprod = kNProd;                 // 1 or 3
@@ -97,7 +102,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    // Lane 0 issues the tiled loads; in the gather variants all 32 lanes issue gather4 loads (4 rows each)
+    // of the bank rows named by rowmap, so the gathered operand never exists in HBM.
+    if (lane == 0 || C::gather) {
       int stage = 0; uint32_t phase = 0;
       for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
         const int split = u / tiles_mn;
@@ -106,9 +113,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const int n0 = (t % p.tiles_n) * C::block_n;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
+        int4 arow = make_int4(0, 0, 0, 0);
+        if (C::gather_a) arow = *reinterpret_cast<const int4*>(p.rowmap + m0 + 4 * lane);   // this lane's 4 A rows
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1u);
-          mbar_arrive_expect_tx(&full_bar[stage], C::stage_bytes);
+          if (lane == 0) {
+            mbar_wait(&empty_bar[stage], phase ^ 1u);
+            mbar_arrive_expect_tx(&full_bar[stage], C::stage_bytes);
+          }
+          if (C::gather) __syncwarp();
           uint8_t* sa = smem + stage * C::stage_bytes;
           uint8_t* sb = sa + C::parts * C::a_bytes;
           const int k0 = kb * C::bk;
@@ -116,21 +128,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           for (int part = 0; part < C::parts; ++part) {
             const CUtensorMap* ta = part ? &tmA_lo : &tmA_hi;
             const CUtensorMap* tb = part ? &tmB_lo : &tmB_hi;
-            if (!C::a_mn) {
-              tma_load_2d(sa + part * C::a_bytes, ta, &full_bar[stage], k0, m0);
-            } else {
+            if (C::gather_a) {
+              // A tile [128 rows x 128 B]: lane l fills rows 4l..4l+3 (512 B, inside one swizzle atom)
+              tma_gather4(sa + part * C::a_bytes + lane * 512, ta, &full_bar[stage], k0, arow.x, arow.y, arow.z, arow.w);
+            } else if (lane == 0) {
+              if (!C::a_mn) {
+                tma_load_2d(sa + part * C::a_bytes, ta, &full_bar[stage], k0, m0);
+              } else {
 #pragma unroll
-              for (int c = 0; c < kBlockM / C::chunk; ++c)
-                tma_load_2d(sa + part * C::a_bytes + c * (C::bk * kRowBytes), ta, &full_bar[stage],
-                            m0 + c * C::chunk, k0);
+                for (int c = 0; c < kBlockM / C::chunk; ++c)
+                  tma_load_2d(sa + part * C::a_bytes + c * (C::bk * kRowBytes), ta, &full_bar[stage],
+                              m0 + c * C::chunk, k0);
+              }
             }
-            if (!C::b_mn) {
-              tma_load_2d(sb + part * C::b_bytes, tb, &full_bar[stage], k0, n0);
-            } else {
+            if (C::gather_b) {
+              // B tile = chunks of [bk k-rows x 128 B]; a gather4 fills 4 k-rows of one chunk.
+              constexpr int kGroups = C::bk / 4;                 // row groups per chunk (16 bf16 / 8 tf32)
+              constexpr int kChunks = C::block_n / C::chunk;     // 4 bf16 / 8 tf32
+              const int grp = lane % kGroups;
+              const int4 r = *reinterpret_cast<const int4*>(p.rowmap + k0 + 4 * grp);
 #pragma unroll
-              for (int c = 0; c < C::block_n / C::chunk; ++c)
-                tma_load_2d(sb + part * C::b_bytes + c * (C::bk * kRowBytes), tb, &full_bar[stage],
-                            n0 + c * C::chunk, k0);
+              for (int c = lane / kGroups; c < kChunks; c += 32 / kGroups)
+                tma_gather4(sb + part * C::b_bytes + c * (C::bk * kRowBytes) + grp * 512, tb, &full_bar[stage],
+                            n0 + c * C::chunk, r.x, r.y, r.z, r.w);
+            } else if (lane == 0) {
+              if (!C::b_mn) {
+                tma_load_2d(sb + part * C::b_bytes, tb, &full_bar[stage], k0, n0);
+              } else {
+#pragma unroll
+                for (int c = 0; c < C::block_n / C::chunk; ++c)
+                  tma_load_2d(sb + part * C::b_bytes + c * (C::bk * kRowBytes), tb, &full_bar[stage],
+                              n0 + c * C::chunk, k0);
+              }
             }
           }
           if (++stage == C::stages) { stage = 0; phase ^= 1u; }
@@ -351,8 +380,13 @@ int launch_cfg(const GemmProblem& g, cudaStream_t stream) {
   const CUtensorMapDataType dt = C::tf32 ? (C::nprod == 3 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32)
                                          : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   CUtensorMap tA_hi, tA_lo, tB_hi, tB_lo;
-  const uint32_t a_box = C::a_mn ? C::bk : kBlockM;
-  const uint32_t b_box = C::b_mn ? C::bk : C::block_n;
+  // gathered operands: the tensor is the whole bank and the box is one row (gather4 fetches 4 of them)
+  if (C::gather) {
+    if (!g.rowmap || g.bank_rows <= 0) { set_error("gather variant without a rowmap"); return VV_ERR_INVALID; }
+    if (C::gather_a) a_outer = uint64_t(g.bank_rows); else b_outer = uint64_t(g.bank_rows);
+  }
+  const uint32_t a_box = C::gather_a ? 1 : (C::a_mn ? C::bk : kBlockM);
+  const uint32_t b_box = C::gather_b ? 1 : (C::b_mn ? C::bk : C::block_n);
   const CUtensorMapSwizzle sw_a = (C::tf32 && C::a_mn) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
   const CUtensorMapSwizzle sw_b = (C::tf32 && C::b_mn) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
   int rc;
@@ -383,6 +417,7 @@ int launch_cfg(const GemmProblem& g, cudaStream_t stream) {
   p.D = g.D; p.slab_stride = g.slab_stride;
   p.act_N = g.N;
   p.epi = g.epi;
+  p.rowmap = g.rowmap;
   static bool attr_set = false;
   if (!attr_set) {
     VV_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::smem_bytes));
@@ -409,23 +444,31 @@ bool gemm_tc_supported(const GemmProblem& g, const char** why) {
 int gemm_tc_launch(const GemmProblem& g, cudaStream_t stream) {
   const char* why = nullptr;
   if (!gemm_tc_supported(g, &why)) { set_error("%s (M=%d N=%d K=%d)", why, g.M, g.N, g.K); return VV_ERR_UNSUPPORTED; }
-  //                 tf32   A-MN   B-MN  nprod  BN  stages fwd-epilogue
+  //                 tf32   A-MN   B-MN  nprod  BN  stages fwd-epilogue gather
+  const bool gat = g.rowmap != nullptr;
+  if (gat && g.kind == GEMM_DGRAD) { set_error("dgrad has no gathered operand"); return VV_ERR_INVALID; }
   if (g.prec == VV_PREC_BF16) {
     switch (g.kind) {
-      case GEMM_FWD:   return launch_cfg<Cfg<false, false, false, 1, 256, 4, true >>(g, stream);
-      case GEMM_WGRAD: return launch_cfg<Cfg<false, true,  true,  1, 256, 4, false>>(g, stream);
+      case GEMM_FWD:   return gat ? launch_cfg<Cfg<false, false, false, 1, 256, 4, true,  true>>(g, stream)
+                                  : launch_cfg<Cfg<false, false, false, 1, 256, 4, true >>(g, stream);
+      case GEMM_WGRAD: return gat ? launch_cfg<Cfg<false, true,  true,  1, 256, 4, false, true>>(g, stream)
+                                  : launch_cfg<Cfg<false, true,  true,  1, 256, 4, false>>(g, stream);
       default:         return launch_cfg<Cfg<false, false, true,  1, 256, 4, false>>(g, stream);
     }
   } else if (g.prec == VV_PREC_TF32) {
     switch (g.kind) {
-      case GEMM_FWD:   return launch_cfg<Cfg<true, false, false, 1, 256, 4, true >>(g, stream);
-      case GEMM_WGRAD: return launch_cfg<Cfg<true, true,  true,  1, 256, 4, false>>(g, stream);
+      case GEMM_FWD:   return gat ? launch_cfg<Cfg<true, false, false, 1, 256, 4, true,  true>>(g, stream)
+                                  : launch_cfg<Cfg<true, false, false, 1, 256, 4, true >>(g, stream);
+      case GEMM_WGRAD: return gat ? launch_cfg<Cfg<true, true,  true,  1, 256, 4, false, true>>(g, stream)
+                                  : launch_cfg<Cfg<true, true,  true,  1, 256, 4, false>>(g, stream);
       default:         return launch_cfg<Cfg<true, false, true,  1, 256, 4, false>>(g, stream);
     }
   } else {
     switch (g.kind) {
-      case GEMM_FWD:   return launch_cfg<Cfg<true, false, false, 3, 256, 2, true >>(g, stream);
-      case GEMM_WGRAD: return launch_cfg<Cfg<true, true,  true,  3, 256, 2, false>>(g, stream);
+      case GEMM_FWD:   return gat ? launch_cfg<Cfg<true, false, false, 3, 256, 2, true,  true>>(g, stream)
+                                  : launch_cfg<Cfg<true, false, false, 3, 256, 2, true >>(g, stream);
+      case GEMM_WGRAD: return gat ? launch_cfg<Cfg<true, true,  true,  3, 256, 2, false, true>>(g, stream)
+                                  : launch_cfg<Cfg<true, true,  true,  3, 256, 2, false>>(g, stream);
       default:         return launch_cfg<Cfg<true, false, true,  3, 256, 2, false>>(g, stream);
     }
   }

@@ -182,7 +182,8 @@ template <int NVEC>
 __global__ void __launch_bounds__(256)
 rank_bwd_kernel(const float* __restrict__ H, const RankDev p, const float* __restrict__ stats,
                 const float gscale /* lw*2/(B*Nn) for L2, lw/(B*Nn) for L1 */,
-                const int act_fused, const float dscale, const BwdOut out, float* __restrict__ db_accum) {
+                const int act_fused, const float dscale, const BwdOut out, float* __restrict__ db_accum,
+                const float* __restrict__ delta, float* __restrict__ dq_accum) {
   extern __shared__ float sm[];
   const int T = blockDim.x, tid = threadIdx.x;
   const int J = 1 + p.Nn;
@@ -193,9 +194,11 @@ rank_bwd_kernel(const float* __restrict__ H, const RankDev p, const float* __res
   float* cB = cA + J;         // [J] coefficient on x
   float* cE = cB + J;         // [J] w_j / n_j   (d c^ = sum_j cE_j x_j)
   float* sc = cE + J;         // [4] s_c, nc, Fs, Fc
-  float4 dbacc[NVEC];
+  // dbacc: column sums of dZ (bias gradient); dqacc: sum_m delta[m] * dZ[m,:] (the gather-fused wgrad's
+  // correction of dW[:, K-1] for the K-1 copy quirk; delta is non-zero on same-video negative rows only)
+  float4 dbacc[NVEC], dqacc[NVEC];
 #pragma unroll
-  for (int v = 0; v < NVEC; ++v) dbacc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int v = 0; v < NVEC; ++v) { dbacc[v] = make_float4(0.f, 0.f, 0.f, 0.f); dqacc[v] = make_float4(0.f, 0.f, 0.f, 0.f); }
 
   for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
     const float* st = stats + size_t(b) * p.stride;
@@ -260,6 +263,7 @@ rank_bwd_kernel(const float* __restrict__ H, const RankDev p, const float* __res
         if (j < J) {
           const int row = (j == 0) ? 0 : p.C + j - 1;
           const float a = cA[j], bb = cB[j], e = cE[j];
+          const float dl = delta ? delta[size_t(row) * p.B + b] : 0.f;
 #pragma unroll
           for (int v = 0; v < NVEC; ++v) {
             const int c4 = v * T + tid;
@@ -275,6 +279,8 @@ rank_bwd_kernel(const float* __restrict__ H, const RankDev p, const float* __res
                 o.z = xv.z > 0.f ? o.z * dscale : 0.f; o.w = xv.w > 0.f ? o.w * dscale : 0.f;
               }
               dbacc[v].x += o.x; dbacc[v].y += o.y; dbacc[v].z += o.z; dbacc[v].w += o.w;
+              dqacc[v].x = fmaf(dl, o.x, dqacc[v].x); dqacc[v].y = fmaf(dl, o.y, dqacc[v].y);
+              dqacc[v].z = fmaf(dl, o.z, dqacc[v].z); dqacc[v].w = fmaf(dl, o.w, dqacc[v].w);
               store_row4(out, (size_t(row) * p.B + b) * p.N + c4 * 4, o);
             }
           }
@@ -317,6 +323,16 @@ rank_bwd_kernel(const float* __restrict__ H, const RankDev p, const float* __res
       if (c4 < p.N4) {
         atomicAdd(db_accum + c4 * 4 + 0, dbacc[v].x); atomicAdd(db_accum + c4 * 4 + 1, dbacc[v].y);
         atomicAdd(db_accum + c4 * 4 + 2, dbacc[v].z); atomicAdd(db_accum + c4 * 4 + 3, dbacc[v].w);
+      }
+    }
+  }
+  if (dq_accum) {
+#pragma unroll
+    for (int v = 0; v < NVEC; ++v) {
+      const int c4 = v * T + tid;
+      if (c4 < p.N4) {
+        atomicAdd(dq_accum + c4 * 4 + 0, dqacc[v].x); atomicAdd(dq_accum + c4 * 4 + 1, dqacc[v].y);
+        atomicAdd(dq_accum + c4 * 4 + 2, dqacc[v].z); atomicAdd(dq_accum + c4 * 4 + 3, dqacc[v].w);
       }
     }
   }
@@ -376,6 +392,14 @@ extern "C" int vv_rank_loss_backward(const float* H, const vv_rank_cfg_t* cfg, c
                                      float loss_weight, int act_fused, float dropout_scale,
                                      float* dZ, void* dZop_hi, void* dZop_lo, int prec,
                                      float* db_accum, vv_stream_t stream) {
+  return vv_rank_loss_backward_ex(H, cfg, stats, loss_weight, act_fused, dropout_scale, dZ, dZop_hi, dZop_lo, prec,
+                                  db_accum, nullptr, nullptr, stream);
+}
+
+extern "C" int vv_rank_loss_backward_ex(const float* H, const vv_rank_cfg_t* cfg, const float* stats,
+                                        float loss_weight, int act_fused, float dropout_scale,
+                                        float* dZ, void* dZop_hi, void* dZop_lo, int prec,
+                                        float* db_accum, const float* delta, float* dq_accum, vv_stream_t stream) {
   RankDev d; int T;
   int rc = make_dev(cfg, &d, &T);
   if (rc) return rc;
@@ -388,15 +412,16 @@ extern "C" int vv_rank_loss_backward(const float* H, const vv_rank_cfg_t* cfg, c
     o.bf = static_cast<uint16_t*>(dZop_hi); o.prec = prec;
   }
   VV_REQUIRE(o.dZ || o.prec != VV_PREC_FP32_SIMT, "no output requested");
+  VV_REQUIRE(!dq_accum || delta, "dq_accum needs delta");
   const int count = d.B * d.Nn;
   const float gscale = (d.norm == 2) ? loss_weight * 2 / count : loss_weight / count;
   const int J = 1 + d.Nn;
   const size_t smem = sizeof(float) * (6 * J + 4);
   const int grid = d.B < num_sms() * 8 ? d.B : num_sms() * 8;
   switch (d.nvec) {
-    case 1: rank_bwd_kernel<1><<<grid, T, smem, stream>>>(H, d, stats, gscale, act_fused, dropout_scale, o, db_accum); break;
-    case 2: rank_bwd_kernel<2><<<grid, T, smem, stream>>>(H, d, stats, gscale, act_fused, dropout_scale, o, db_accum); break;
-    default: rank_bwd_kernel<4><<<grid, T, smem, stream>>>(H, d, stats, gscale, act_fused, dropout_scale, o, db_accum); break;
+    case 1: rank_bwd_kernel<1><<<grid, T, smem, stream>>>(H, d, stats, gscale, act_fused, dropout_scale, o, db_accum, delta, dq_accum); break;
+    case 2: rank_bwd_kernel<2><<<grid, T, smem, stream>>>(H, d, stats, gscale, act_fused, dropout_scale, o, db_accum, delta, dq_accum); break;
+    default: rank_bwd_kernel<4><<<grid, T, smem, stream>>>(H, d, stats, gscale, act_fused, dropout_scale, o, db_accum, delta, dq_accum); break;
   }
   VV_LAUNCH_CHECK();
   count_launch();

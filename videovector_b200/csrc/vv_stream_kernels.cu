@@ -53,6 +53,30 @@ gather_rows_kernel(const float* __restrict__ bank, const int* __restrict__ idx, 
   }
 }
 
+// Gather plan for the gather-fused GEMMs: rowmap[m] = bank row of X row m = j*B+b (0 in the padding), and
+// delta[m] = (value element K-1 should have) - (value the bank row has there): the K-1 copy quirk
+// (ref: video_sampled_shots_data_layer.cpp:492) expressed as a correction of the last feature only.
+__global__ void __launch_bounds__(256)
+gather_plan_kernel(const float* __restrict__ bank, const int* __restrict__ idx, const int* __restrict__ quirk,
+                   int B, int R, int K, int Mpad, int* __restrict__ rowmap, float* __restrict__ delta) {
+  const int M = B * R;
+  for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < Mpad; m += gridDim.x * blockDim.x) {
+    int row = 0; float d = 0.f;
+    if (m < M) {
+      const int j = m / B, b = m - j * B;
+      const int slot = b * R + j;
+      row = idx[slot];
+      const int qk = quirk ? quirk[slot] : -2;
+      if (qk != -2) d = (qk >= 0 ? bank[(long long)qk * K + (K - 1)] : 0.f) - bank[(long long)row * K + (K - 1)];
+    }
+    rowmap[m] = row;
+    if (delta) delta[m] = d;
+  }
+}
+__global__ void add_column_kernel(float* A, long long ld, int col, const float* v, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) A[(long long)i * ld + col] += v[i];
+}
+
 // fp32 -> operand copies
 __global__ void __launch_bounds__(256)
 prepare_operand_kernel(const float* __restrict__ src, long long n4, int prec, float* hi, float* lo, uint16_t* bf) {
@@ -304,6 +328,23 @@ extern "C" int vv_gather_rows(const float* bank, int64_t bank_rows, int K, const
   const long long M = (long long)B * R;
   const int grid = int(M < (long long)num_sms() * 16 ? M : (long long)num_sms() * 16);
   gather_rows_kernel<<<grid, 256, 0, stream>>>(bank, idx, quirk, B, R, K, o);
+  VV_LAUNCH_CHECK();
+  count_launch();
+  return VV_OK;
+}
+
+extern "C" int vv_gather_plan(const float* bank, int K, const int32_t* idx, const int32_t* quirk, int B, int R,
+                              int32_t* rowmap, float* delta, vv_stream_t stream) {
+  VV_REQUIRE(bank && idx && rowmap && B > 0 && R > 0 && K > 0, "gather_plan: bad arguments");
+  const int M = B * R, Mpad = ((M + 127) / 128) * 128;
+  gather_plan_kernel<<<stream_grid(Mpad, 256), 256, 0, stream>>>(bank, idx, quirk, B, R, K, Mpad, rowmap, delta);
+  VV_LAUNCH_CHECK();
+  count_launch();
+  return VV_OK;
+}
+extern "C" int vv_add_column(float* A, int64_t ld, int col, const float* v, int n, vv_stream_t stream) {
+  VV_REQUIRE(A && v && n > 0 && ld > 0 && col >= 0 && col < ld, "add_column: bad arguments");
+  add_column_kernel<<<stream_grid(n, 256), 256, 0, stream>>>(A, ld, col, v, n);
   VV_LAUNCH_CHECK();
   count_launch();
   return VV_OK;

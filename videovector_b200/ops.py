@@ -326,6 +326,11 @@ class Trainer:
         self.tensor("b").copy_(b)
         check(self._lib.vv_trainer_sync_weights(self._h))
 
+    def set_bank(self, bank):
+        """Register the resident bank: later steps on it use the gather-fused GEMMs (no materialised X)."""
+        self._bank = bank
+        check(self._lib.vv_trainer_set_bank(self._h, _ptr(bank), bank.shape[0]))
+
     def step(self, bank, idx, quirk, mask=None, it=0, do_update=True):
         check(self._lib.vv_trainer_step(self._h, _ptr(bank), bank.shape[0], _ptr(idx), _ptr(quirk), _ptr(mask),
                                         it, int(do_update)))
