@@ -48,8 +48,9 @@ enum {
 
 /* How the projection GEMMs compute (the `dtype` of the path).
  *   FP32_SIMT : exact fp32 FMA on CUDA cores (validation / odd shapes)
- *   TF32X3    : tcgen05 kind::tf32, operands split hi+lo, 3 MMAs per product,
- *               fp32 accumulate in TMEM -> fp32-level accuracy (the 1e-5 parity mode)
+ *   TF32X3    : split operands x = hi + lo, three products per element pair: hi*hi on the tf32 tensor
+ *               pipe, the cross terms bf16(x)*bf16(lo) on the bf16 pipe, fp32 accumulate in TMEM with
+ *               periodic promotion to fp32 registers -> fp32-level accuracy (the 1e-5 parity mode)
  *   TF32      : tcgen05 kind::tf32, 1 MMA per product (1e-2 loss-curve mode)
  *   BF16      : tcgen05 kind::f16 with bf16 operands, fp32 accumulate (1e-2 mode) */
 enum vv_precision {
@@ -61,7 +62,8 @@ enum vv_precision {
 
 /* A GEMM operand as the kernels read it.
  *   FP32_SIMT / TF32 : hi = the fp32 array itself, lo = NULL
- *   TF32X3           : hi = round-to-nearest tf32 part, lo = residual (both fp32 arrays)
+ *   TF32X3           : hi = round-to-nearest tf32 part (fp32 array, `count` elements); lo = an array of
+ *                      the same byte size holding two bf16 planes of `count` elements: bf16(x), bf16(x - hi)
  *   BF16             : hi = bf16 array (uint16 storage), lo = NULL
  * vv_prepare_operand() produces these from an fp32 array; the producer kernels
  * (gather, rank-loss backward, sgd update) can emit them directly. */

@@ -24,6 +24,18 @@ def rel(a, b):
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
 
 
+def check_x3_operand(op, x):
+    """TF32X3 operand format: hi = tf32(x) (13 low mantissa bits clear); lo = two bf16 planes [bf16(x) | bf16(x - hi)]."""
+    n = x.numel()
+    assert torch.equal(op.hi.view(torch.int32) & 0x1FFF, torch.zeros_like(op.hi, dtype=torch.int32))
+    assert rel(op.hi, x) < 2 ** -11
+    planes = op.lo.reshape(-1).view(torch.bfloat16)
+    assert planes.numel() == 2 * n
+    assert torch.equal(planes[:n], x.reshape(-1).to(torch.bfloat16))
+    assert torch.equal(planes[n:], (x - op.hi).reshape(-1).to(torch.bfloat16))
+    assert rel(op.hi.double().reshape(-1) + planes[n:].double(), x.reshape(-1)) < 2 ** -19
+
+
 def cuda(a, dtype=None):
     t = torch.as_tensor(a)
     if dtype is not None:
@@ -66,8 +78,7 @@ def test_gather_rows_bit_exact(oracle, prec):
         if prec == "bf16":
             assert torch.equal(op.hi, X.to(torch.bfloat16))
         if prec == "tf32x3":
-            assert rel(op.hi.double() + op.lo.double(), X) < 2 ** -21
-            assert torch.equal(op.hi.view(torch.int32) & 0x1FFF, torch.zeros_like(op.hi, dtype=torch.int32))
+            check_x3_operand(op, X)
     psmp.close()
 
 
@@ -256,7 +267,7 @@ def test_rank_loss_backward_operand_copies(prec):
     if prec == "bf16":
         assert torch.equal(op.hi, dZ.to(torch.bfloat16))
     else:
-        assert rel(op.hi.double() + op.lo.double(), dZ) < 2 ** -21
+        check_x3_operand(op, dZ)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -287,7 +298,7 @@ def test_sgd_update_refreshes_operand_copies(prec):
     if prec == "bf16":
         assert torch.equal(Wop.hi, W.to(torch.bfloat16))
     else:
-        assert rel(Wop.hi.double() + Wop.lo.double(), W) < 2 ** -21
+        check_x3_operand(Wop, W)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -65,6 +65,17 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+// The TF32X3 operand format of 4 consecutive elements: hi = tf32(x) (fp32 array), and in the `lo` array two
+// bf16 planes of `count` elements each: plane 0 = bf16(x), plane 1 = bf16(x - hi)  (the cross-term operands).
+__device__ __forceinline__ void store_x3(float* hi, void* lo, size_t count, size_t off, const float4& v) {
+  float4 h;
+  h.x = to_tf32_rna(v.x); h.y = to_tf32_rna(v.y); h.z = to_tf32_rna(v.z); h.w = to_tf32_rna(v.w);
+  *reinterpret_cast<float4*>(hi + off) = h;
+  uint16_t* planes = static_cast<uint16_t*>(lo);
+  *reinterpret_cast<uint2*>(planes + off) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  *reinterpret_cast<uint2*>(planes + count + off) =
+      make_uint2(pack_bf16x2(v.x - h.x, v.y - h.y), pack_bf16x2(v.z - h.z, v.w - h.w));
+}
 
 // ----------------------------------------------------------------------------
 // counter-based RNGs
@@ -275,7 +286,7 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 //  start address >>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout type [61,64)
 //  layout type: 2 = SWIZZLE_128B (16-byte chunks), 1 = SWIZZLE_128B_BASE32B (32-byte chunks; the only
 //  layout the hardware accepts for MN-major 32-bit (tf32) operands)
-constexpr uint32_t kLayoutSw128 = 2, kLayoutSw128Base32 = 1;
+constexpr uint32_t kLayoutSw128 = 2, kLayoutSw128Base32 = 1, kLayoutSw64 = 4;
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
                                                    uint32_t layout_type) {
   uint64_t d = 0;

@@ -13,8 +13,9 @@
 //   FWD   D[M,N] = X W^T      A = X  [M,K] K-major      B = W [N,K] K-major
 //   WGRAD D[N,K] = dZ^T X     A = dZ [M,N] MN-major     B = X [M,K] MN-major   (reduce M, split-K slabs)
 //   DGRAD D[M,K] = dZ W       A = dZ [M,N] K-major      B = W [N,K] MN-major   (reduce N)
-// Precisions: bf16 (kind::f16), tf32 (kind::tf32), and tf32x3 = hi/lo split operands,
-// three MMAs per k-step (lo*hi + hi*lo + hi*hi) for fp32-level accuracy.
+// Precisions: bf16 (kind::f16), tf32 (kind::tf32), and tf32x3 = split operands x = hi + lo with three products
+// per element pair: hi*hi on the tf32 pipe and the two cross terms bf16(x)*bf16(lo) on the (2x faster) bf16
+// pipe, all accumulated in the same fp32 TMEM tile -> fp32-level accuracy at 4 instead of 6 MMA units.
 #include <cuda.h>
 #include "vv_gemm.cuh"
 
@@ -46,8 +47,8 @@ struct Cfg {
   static constexpr bool tf32 = kTF32;
   static constexpr bool a_mn = kAMN, b_mn = kBMN;
   static constexpr int nprod = kNProd;                 // 1 or 3
+  static constexpr bool mixed = (kNProd == 3);          // tf32 hi*hi + bf16 cross terms
   static constexpr bool promote = (kNProd == 3);        // chunked TMEM accumulation + fp32 register sums
-  static constexpr int parts = (kNProd == 3) ? 2 : 1;  // hi (+ lo)
   static constexpr int block_n = kBlockN;
   static constexpr int stages = kStages;
   static constexpr bool fwd_epi = kFwdEpi;
@@ -56,9 +57,12 @@ struct Cfg {
   static constexpr int umma_k = 32 / elem_bytes;       // 8 / 16
   static constexpr int ksteps = bk / umma_k;           // 4
   static constexpr int chunk = kRowBytes / elem_bytes; // MN elements per 128B row (MN-major)
-  static constexpr int a_bytes = kBlockM * kRowBytes;  // 16 KB per part
-  static constexpr int b_bytes = kBlockN * kRowBytes;  // 32 KB per part (BLOCK_N = 256)
-  static constexpr int stage_bytes = parts * (a_bytes + b_bytes);
+  static constexpr int a_bytes = kBlockM * kRowBytes;  // 16 KB: the main (hi) tile
+  static constexpr int b_bytes = kBlockN * kRowBytes;  // 32 KB (BLOCK_N = 256)
+  // mixed mode: two extra bf16 tiles per operand (bf16(x) and bf16(lo)) covering the same bk = 32 reduction
+  // elements: K-major = rows of 64 B (SWIZZLE_64B); MN-major = 64-element chunks of [32 k-rows x 128 B] (SWIZZLE_128B)
+  static constexpr int a_half = a_bytes / 2, b_half = b_bytes / 2;
+  static constexpr int stage_bytes = mixed ? 2 * (a_bytes + b_bytes) : (a_bytes + b_bytes);
   static constexpr int tmem_cols = 2 * kBlockN;
   static constexpr int smem_bytes = stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
   static_assert(tmem_cols == 256 || tmem_cols == 512, "TMEM allocation must be a power of two");
@@ -67,8 +71,9 @@ struct Cfg {
 
 template <class C>
 __global__ void __launch_bounds__(kNumThreads, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-               const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_hb,
+               const __grid_constant__ CUtensorMap tmA_lb, const __grid_constant__ CUtensorMap tmB_hi,
+               const __grid_constant__ CUtensorMap tmB_hb, const __grid_constant__ CUtensorMap tmB_lb,
                const TcParams p) {
 #if defined(__CUDA_ARCH__)
   extern __shared__ uint8_t smem_raw[];
@@ -84,7 +89,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmB_hi);
-    if (C::parts == 2) { tma_prefetch_desc(&tmA_lo); tma_prefetch_desc(&tmB_lo); }
+    if (C::mixed) { tma_prefetch_desc(&tmA_hb); tma_prefetch_desc(&tmA_lb); tma_prefetch_desc(&tmB_hb); tma_prefetch_desc(&tmB_lb); }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -121,44 +126,62 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             mbar_arrive_expect_tx(&full_bar[stage], C::stage_bytes);
           }
           if (C::gather) __syncwarp();
+          // stage layout: [A_hi][A_hb][A_lb][B_hi][B_hb][B_lb]  (the bf16 tiles only in mixed mode)
           uint8_t* sa = smem + stage * C::stage_bytes;
-          uint8_t* sb = sa + C::parts * C::a_bytes;
+          uint8_t* sb = sa + (C::mixed ? 2 * C::a_bytes : C::a_bytes);
           const int k0 = kb * C::bk;
+          if (C::gather_a) {
+            // A tile [128 rows x 128 B]: lane l fills rows 4l..4l+3 (512 B, inside one swizzle atom)
+            tma_gather4(sa + lane * 512, &tmA_hi, &full_bar[stage], k0, arow.x, arow.y, arow.z, arow.w);
+          } else if (lane == 0) {
+            if (!C::a_mn) {
+              tma_load_2d(sa, &tmA_hi, &full_bar[stage], k0, m0);
+            } else {
 #pragma unroll
-          for (int part = 0; part < C::parts; ++part) {
-            const CUtensorMap* ta = part ? &tmA_lo : &tmA_hi;
-            const CUtensorMap* tb = part ? &tmB_lo : &tmB_hi;
-            if (C::gather_a) {
-              // A tile [128 rows x 128 B]: lane l fills rows 4l..4l+3 (512 B, inside one swizzle atom)
-              tma_gather4(sa + part * C::a_bytes + lane * 512, ta, &full_bar[stage], k0, arow.x, arow.y, arow.z, arow.w);
-            } else if (lane == 0) {
-              if (!C::a_mn) {
-                tma_load_2d(sa + part * C::a_bytes, ta, &full_bar[stage], k0, m0);
-              } else {
-#pragma unroll
-                for (int c = 0; c < kBlockM / C::chunk; ++c)
-                  tma_load_2d(sa + part * C::a_bytes + c * (C::bk * kRowBytes), ta, &full_bar[stage],
-                              m0 + c * C::chunk, k0);
-              }
+              for (int c = 0; c < kBlockM / C::chunk; ++c)
+                tma_load_2d(sa + c * (C::bk * kRowBytes), &tmA_hi, &full_bar[stage], m0 + c * C::chunk, k0);
             }
-            if (C::gather_b) {
-              // B tile = chunks of [bk k-rows x 128 B]; a gather4 fills 4 k-rows of one chunk.
-              constexpr int kGroups = C::bk / 4;                 // row groups per chunk (16 bf16 / 8 tf32)
-              constexpr int kChunks = C::block_n / C::chunk;     // 4 bf16 / 8 tf32
-              const int grp = lane % kGroups;
-              const int4 r = *reinterpret_cast<const int4*>(p.rowmap + k0 + 4 * grp);
+          }
+          if (C::gather_b) {
+            // B tile = chunks of [bk k-rows x 128 B]; a gather4 fills 4 k-rows of one chunk.
+            constexpr int kGroups = C::bk / 4;                 // row groups per chunk (16 bf16 / 8 tf32)
+            constexpr int kChunks = C::block_n / C::chunk;     // 4 bf16 / 8 tf32
+            const int grp = lane % kGroups;
+            const int4 r = *reinterpret_cast<const int4*>(p.rowmap + k0 + 4 * grp);
 #pragma unroll
-              for (int c = lane / kGroups; c < kChunks; c += 32 / kGroups)
-                tma_gather4(sb + part * C::b_bytes + c * (C::bk * kRowBytes) + grp * 512, tb, &full_bar[stage],
-                            n0 + c * C::chunk, r.x, r.y, r.z, r.w);
-            } else if (lane == 0) {
-              if (!C::b_mn) {
-                tma_load_2d(sb + part * C::b_bytes, tb, &full_bar[stage], k0, n0);
+            for (int c = lane / kGroups; c < kChunks; c += 32 / kGroups)
+              tma_gather4(sb + c * (C::bk * kRowBytes) + grp * 512, &tmB_hi, &full_bar[stage],
+                          n0 + c * C::chunk, r.x, r.y, r.z, r.w);
+          } else if (lane == 0) {
+            if (!C::b_mn) {
+              tma_load_2d(sb, &tmB_hi, &full_bar[stage], k0, n0);
+            } else {
+#pragma unroll
+              for (int c = 0; c < C::block_n / C::chunk; ++c)
+                tma_load_2d(sb + c * (C::bk * kRowBytes), &tmB_hi, &full_bar[stage], n0 + c * C::chunk, k0);
+            }
+          }
+          if (C::mixed && lane == 0) {
+            // the two bf16 tiles of each operand for the cross terms
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const CUtensorMap* ta = h ? &tmA_lb : &tmA_hb;
+              const CUtensorMap* tb = h ? &tmB_lb : &tmB_hb;
+              uint8_t* da = sa + C::a_bytes + h * C::a_half;
+              uint8_t* db = sb + C::b_bytes + h * C::b_half;
+              if (!C::a_mn) {
+                tma_load_2d(da, ta, &full_bar[stage], k0, m0);                       // [128 rows x 64 B], SWIZZLE_64B
               } else {
 #pragma unroll
-                for (int c = 0; c < C::block_n / C::chunk; ++c)
-                  tma_load_2d(sb + part * C::b_bytes + c * (C::bk * kRowBytes), tb, &full_bar[stage],
-                              n0 + c * C::chunk, k0);
+                for (int c = 0; c < kBlockM / 64; ++c)                               // 64 bf16 of MN per 128 B row
+                  tma_load_2d(da + c * (C::bk * kRowBytes), ta, &full_bar[stage], m0 + c * 64, k0);
+              }
+              if (!C::b_mn) {
+                tma_load_2d(db, tb, &full_bar[stage], k0, n0);
+              } else {
+#pragma unroll
+                for (int c = 0; c < C::block_n / 64; ++c)
+                  tma_load_2d(db + c * (C::bk * kRowBytes), tb, &full_bar[stage], n0 + c * 64, k0);
               }
             }
           }
@@ -201,20 +224,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
             const uint32_t sa = smem_u32(smem + stage * C::stage_bytes);
-            const uint32_t sb = sa + C::parts * C::a_bytes;
+            const uint32_t sb = sa + (C::mixed ? 2 * C::a_bytes : C::a_bytes);
+            if (C::mixed) {
+              // cross terms first (small magnitude), on the bf16 pipe: bf16(a)*bf16(b_lo) + bf16(a_lo)*bf16(b)
+              constexpr uint32_t idesc16 = make_idesc(1, C::a_mn ? 1 : 0, C::b_mn ? 1 : 0, kBlockM, C::block_n);
+              constexpr uint32_t lay16_a = C::a_mn ? kLayoutSw128 : kLayoutSw64, lay16_b = C::b_mn ? kLayoutSw128 : kLayoutSw64;
+              constexpr uint32_t sbo16_a = C::a_mn ? 1024 : 512, sbo16_b = C::b_mn ? 1024 : 512;
+              constexpr uint32_t kadv16_a = C::a_mn ? 16 * kRowBytes : 32, kadv16_b = C::b_mn ? 16 * kRowBytes : 32;
+              const uint32_t a_hb = sa + C::a_bytes, a_lb = a_hb + C::a_half;
+              const uint32_t b_hb = sb + C::b_bytes, b_lb = b_hb + C::b_half;
+#pragma unroll
+              for (int k = 0; k < 2; ++k) {      // 32 reduction elements = 2 bf16 k-steps of 16
+                const uint64_t d_ahb = make_smem_desc(a_hb + k * kadv16_a, lbo_a, sbo16_a, lay16_a);
+                const uint64_t d_alb = make_smem_desc(a_lb + k * kadv16_a, lbo_a, sbo16_a, lay16_a);
+                const uint64_t d_bhb = make_smem_desc(b_hb + k * kadv16_b, lbo_b, sbo16_b, lay16_b);
+                const uint64_t d_blb = make_smem_desc(b_lb + k * kadv16_b, lbo_b, sbo16_b, lay16_b);
+                umma_ss<false>(d_tmem, d_alb, d_bhb, idesc16, accumulate);
+                umma_ss<false>(d_tmem, d_ahb, d_blb, idesc16, 1u);
+                accumulate = 1u;
+              }
+            }
 #pragma unroll
             for (int k = 0; k < C::ksteps; ++k) {
               const uint64_t a_hi = make_smem_desc(sa + k * kadv_a, lbo_a, sbo_a, lay_a);
               const uint64_t b_hi = make_smem_desc(sb + k * kadv_b, lbo_b, sbo_b, lay_b);
-              if (C::nprod == 3) {
-                const uint64_t a_lo = make_smem_desc(sa + C::a_bytes + k * kadv_a, lbo_a, sbo_a, lay_a);
-                const uint64_t b_lo = make_smem_desc(sb + C::b_bytes + k * kadv_b, lbo_b, sbo_b, lay_b);
-                umma_ss<C::tf32>(d_tmem, a_lo, b_hi, idesc, accumulate);
-                umma_ss<C::tf32>(d_tmem, a_hi, b_lo, idesc, 1u);
-                umma_ss<C::tf32>(d_tmem, a_hi, b_hi, idesc, 1u);
-              } else {
-                umma_ss<C::tf32>(d_tmem, a_hi, b_hi, idesc, accumulate);
-              }
+              umma_ss<C::tf32>(d_tmem, a_hi, b_hi, idesc, accumulate);
               accumulate = 1u;
             }
             umma_commit(&empty_bar[stage]);            // frees the smem stage when these MMAs retire
@@ -348,9 +382,9 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-// 2D row-major tensor [outer rows, inner contiguous elems]; box = [box_outer rows, 128 B of inner].
+// 2D row-major tensor [outer rows, inner contiguous elems]; box = [box_outer rows, box_bytes of inner].
 int make_tmap(CUtensorMap* tm, const void* base, CUtensorMapDataType dt, int elem_bytes, uint64_t inner,
-              uint64_t outer, uint32_t box_outer, CUtensorMapSwizzle swizzle) {
+              uint64_t outer, uint32_t box_outer, CUtensorMapSwizzle swizzle, int box_bytes = kRowBytes) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return VV_ERR_CUDA;
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || ((inner * elem_bytes) & 15) != 0) {
@@ -359,7 +393,7 @@ int make_tmap(CUtensorMap* tm, const void* base, CUtensorMapDataType dt, int ele
   }
   cuuint64_t dims[2] = {inner, outer};
   cuuint64_t strides[1] = {inner * elem_bytes};
-  cuuint32_t box[2] = {uint32_t(kRowBytes / elem_bytes), box_outer};
+  cuuint32_t box[2] = {uint32_t(box_bytes / elem_bytes), box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(tm, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -379,7 +413,7 @@ int launch_cfg(const GemmProblem& g, cudaStream_t stream) {
   }
   const CUtensorMapDataType dt = C::tf32 ? (C::nprod == 3 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32)
                                          : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
-  CUtensorMap tA_hi, tA_lo, tB_hi, tB_lo;
+  CUtensorMap tA_hi, tA_hb, tA_lb, tB_hi, tB_hb, tB_lb;
   // gathered operands: the tensor is the whole bank and the box is one row (gather4 fetches 4 of them)
   if (C::gather) {
     if (!g.rowmap || g.bank_rows <= 0) { set_error("gather variant without a rowmap"); return VV_ERR_INVALID; }
@@ -392,12 +426,23 @@ int launch_cfg(const GemmProblem& g, cudaStream_t stream) {
   int rc;
   if ((rc = make_tmap(&tA_hi, g.A.hi, dt, C::elem_bytes, a_inner, a_outer, a_box, sw_a))) return rc;
   if ((rc = make_tmap(&tB_hi, g.B.hi, dt, C::elem_bytes, b_inner, b_outer, b_box, sw_b))) return rc;
-  if (C::parts == 2) {
-    if (!g.A.lo || !g.B.lo) { set_error("TF32X3 needs hi and lo operand arrays"); return VV_ERR_INVALID; }
-    if ((rc = make_tmap(&tA_lo, g.A.lo, dt, C::elem_bytes, a_inner, a_outer, a_box, sw_a))) return rc;
-    if ((rc = make_tmap(&tB_lo, g.B.lo, dt, C::elem_bytes, b_inner, b_outer, b_box, sw_b))) return rc;
+  if (C::mixed) {
+    // lo = two bf16 planes [bf16(x) | bf16(x - hi)], each the shape of the operand
+    if (!g.A.lo || !g.B.lo) { set_error("TF32X3 needs the hi array and the two-plane bf16 lo array of every operand"); return VV_ERR_INVALID; }
+    const uint16_t* a_planes = static_cast<const uint16_t*>(g.A.lo);
+    const uint16_t* b_planes = static_cast<const uint16_t*>(g.B.lo);
+    const uint64_t a_count = a_inner * a_outer, b_count = b_inner * b_outer;
+    const CUtensorMapDataType bf = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    // K-major: [rows x 64 B] tiles, SWIZZLE_64B; MN-major: [32 k-rows x 128 B] chunks, SWIZZLE_128B
+    const CUtensorMapSwizzle s16a = C::a_mn ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    const CUtensorMapSwizzle s16b = C::b_mn ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    const int bba = C::a_mn ? 128 : 64, bbb = C::b_mn ? 128 : 64;
+    if ((rc = make_tmap(&tA_hb, a_planes, bf, 2, a_inner, a_outer, a_box, s16a, bba))) return rc;
+    if ((rc = make_tmap(&tA_lb, a_planes + a_count, bf, 2, a_inner, a_outer, a_box, s16a, bba))) return rc;
+    if ((rc = make_tmap(&tB_hb, b_planes, bf, 2, b_inner, b_outer, b_box, s16b, bbb))) return rc;
+    if ((rc = make_tmap(&tB_lb, b_planes + b_count, bf, 2, b_inner, b_outer, b_box, s16b, bbb))) return rc;
   } else {
-    tA_lo = tA_hi; tB_lo = tB_hi;
+    tA_hb = tA_hi; tA_lb = tA_hi; tB_hb = tB_hi; tB_lb = tB_hi;
   }
   TcParams p;
   p.d_rows = d_rows; p.d_cols = d_cols; p.ldd = d_cols;
@@ -425,7 +470,7 @@ int launch_cfg(const GemmProblem& g, cudaStream_t stream) {
   }
   const int total = p.tiles_m * p.tiles_n * p.nsplit;
   const int grid = total < num_sms() ? total : num_sms();
-  gemm_tc_kernel<C><<<grid, kNumThreads, C::smem_bytes, stream>>>(tA_hi, tA_lo, tB_hi, tB_lo, p);
+  gemm_tc_kernel<C><<<grid, kNumThreads, C::smem_bytes, stream>>>(tA_hi, tA_hb, tA_lb, tB_hi, tB_hb, tB_lb, p);
   VV_LAUNCH_CHECK();
   count_launch();
   return VV_OK;
@@ -465,10 +510,10 @@ int gemm_tc_launch(const GemmProblem& g, cudaStream_t stream) {
     }
   } else {
     switch (g.kind) {
-      case GEMM_FWD:   return gat ? launch_cfg<Cfg<true, false, false, 3, 256, 2, true,  true>>(g, stream)
-                                  : launch_cfg<Cfg<true, false, false, 3, 256, 2, true >>(g, stream);
-      case GEMM_WGRAD: return gat ? launch_cfg<Cfg<true, true,  true,  3, 256, 2, false, true>>(g, stream)
-                                  : launch_cfg<Cfg<true, true,  true,  3, 256, 2, false>>(g, stream);
+      case GEMM_FWD:   if (gat) { set_error("the gather-fused variants are built for bf16 / tf32 only"); return VV_ERR_UNSUPPORTED; }
+                       return launch_cfg<Cfg<true, false, false, 3, 256, 2, true >>(g, stream);
+      case GEMM_WGRAD: if (gat) { set_error("the gather-fused variants are built for bf16 / tf32 only"); return VV_ERR_UNSUPPORTED; }
+                       return launch_cfg<Cfg<true, true,  true,  3, 256, 2, false>>(g, stream);
       default:         return launch_cfg<Cfg<true, false, true,  3, 256, 2, false>>(g, stream);
     }
   }

@@ -162,16 +162,13 @@ rank_loss_reduce_kernel(const float* __restrict__ item_loss, const float* __rest
 }
 
 struct BwdOut {
-  float* dZ; float* hi; float* lo; uint16_t* bf; int prec;
+  float* dZ; float* hi; float* lo; uint16_t* bf; int prec; size_t count;
 };
 
 __device__ __forceinline__ void store_row4(const BwdOut& o, size_t off, const float4& v) {
   if (o.dZ) stg_stream(reinterpret_cast<float4*>(o.dZ + off), v);
   if (o.prec == VV_PREC_TF32X3) {
-    float4 h, l;
-    split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
-    stg_stream(reinterpret_cast<float4*>(o.hi + off), h);
-    stg_stream(reinterpret_cast<float4*>(o.lo + off), l);
+    store_x3(o.hi, o.lo, o.count, off, v);
   } else if (o.prec == VV_PREC_BF16) {
     uint2 pk = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
     *reinterpret_cast<uint2*>(o.bf + off) = pk;
@@ -405,6 +402,7 @@ extern "C" int vv_rank_loss_backward_ex(const float* H, const vv_rank_cfg_t* cfg
   if (rc) return rc;
   VV_REQUIRE(H && stats, "H and stats must be non-NULL");
   BwdOut o; o.dZ = dZ; o.hi = nullptr; o.lo = nullptr; o.bf = nullptr; o.prec = VV_PREC_FP32_SIMT;
+  o.count = size_t(d.B) * (d.C + d.Nn) * d.N;
   if (prec == VV_PREC_TF32X3 && dZop_hi) {
     VV_REQUIRE(dZop_lo, "TF32X3 operand copy needs hi and lo");
     o.hi = static_cast<float*>(dZop_hi); o.lo = static_cast<float*>(dZop_lo); o.prec = prec;

@@ -42,10 +42,7 @@ gather_rows_kernel(const float* __restrict__ bank, const int* __restrict__ idx, 
       if (o.X) stg_stream(reinterpret_cast<float4*>(o.X + off), v);
       if (o.blob) stg_stream(reinterpret_cast<float4*>(o.blob + (size_t(slot) * K + size_t(c) * 4)), v);
       if (o.prec == VV_PREC_TF32X3) {
-        float4 h, l;
-        split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
-        stg_stream(reinterpret_cast<float4*>(o.hi + off), h);
-        stg_stream(reinterpret_cast<float4*>(o.lo + off), l);
+        store_x3(o.hi, o.lo, size_t(M) * K, off, v);
       } else if (o.prec == VV_PREC_BF16) {
         *reinterpret_cast<uint2*>(o.bf + off) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
       }
@@ -83,9 +80,7 @@ prepare_operand_kernel(const float* __restrict__ src, long long n4, int prec, fl
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const float4 v = ldg_stream(reinterpret_cast<const float4*>(src) + i);
     if (prec == VV_PREC_TF32X3) {
-      float4 h, l;
-      split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
-      reinterpret_cast<float4*>(hi)[i] = h; reinterpret_cast<float4*>(lo)[i] = l;
+      store_x3(hi, lo, size_t(n4) * 4, size_t(i) * 4, v);
     } else {
       reinterpret_cast<uint2*>(bf)[i] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
     }
@@ -125,9 +120,7 @@ sgd_update_kernel(float* W, const float* parts, int nparts, long long stride,
     reinterpret_cast<float4*>(W)[i] = w;
     if (diff_out) reinterpret_cast<float4*>(diff_out)[i] = h;
     if (prec == VV_PREC_TF32X3 && hi) {
-      float4 a, l;
-      split_tf32(w.x, a.x, l.x); split_tf32(w.y, a.y, l.y); split_tf32(w.z, a.z, l.z); split_tf32(w.w, a.w, l.w);
-      reinterpret_cast<float4*>(hi)[i] = a; reinterpret_cast<float4*>(lo)[i] = l;
+      store_x3(hi, lo, size_t(n4) * 4, size_t(i) * 4, w);
     } else if (prec == VV_PREC_BF16 && bf) {
       reinterpret_cast<uint2*>(bf)[i] = make_uint2(pack_bf16x2(w.x, w.y), pack_bf16x2(w.z, w.w));
     }
