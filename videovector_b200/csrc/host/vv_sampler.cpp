@@ -50,14 +50,20 @@ struct vv_glibc_rand {
   void generate() {
     for (int i = 31; i < 31 + kBlock; ++i) buf[i] = buf[i - 31] + buf[i - 3];
   }
+  void refill() {
+    for (int i = 0; i < 31; ++i) buf[i] = buf[kBlock + i];
+    generate();
+    pos = 31;
+  }
   int next() {
-    if (pos >= 31 + kBlock) {
-      for (int i = 0; i < 31; ++i) buf[i] = buf[kBlock + i];
-      generate();
-      pos = 31;
-    }
+    if (pos >= 31 + kBlock) refill();
     return int(buf[pos++] >> 1);
   }
+  int peek() {                      // the next draw, not consumed
+    if (pos >= 31 + kBlock) refill();
+    return int(buf[pos] >> 1);
+  }
+  void skip(int n) { pos += n; }    // consume n (0 or 1) peeked draws
 };
 
 namespace {
@@ -149,7 +155,7 @@ struct vv_sampler {
       if (Nn > 0 && n > C) {                              // same-video negatives :479-503
         for (int i = C + 1; i < n; ++i) {                 // std::random_shuffle(ids+C, end)
           const int j = C + fm.mod(rng.next(), i - C + 1);
-          if (i != j) std::swap(ids[i], ids[j]);
+          std::swap(ids[i], ids[j]);                      // (i == j is a no-op: no branch needed)
         }
         for (int nid = C; nid < n && added < max_same; ++nid) {
           if (ids[nid] < ids[half - 1] || ids[nid] > ids[half + 1]) {
@@ -169,17 +175,21 @@ struct vv_sampler {
       }
       ++item;
       if (Nn > 0 && swap_pct > 0) {                       // swap this record's shots into the buffer :888-906
+        // AddToBuffer (:25-37) draws rand()%100 and, only if that is below the swap percentage, a second
+        // rand()%P.  The second draw is peeked and consumed conditionally (rng.pos += take) and the buffer
+        // update is made branch-free through a dummy slot P / dummy key, because the 50/50 decision is
+        // unpredictable and the mispredictions dominated the sampler's cost.
+        const int32_t dummy_key = int32_t(in_set.size()) - 1;
         for (int j = 0; j < n; ++j) {
           const int32_t key = key_of[off + j];
-          if (!in_set[key]) {
-            if (fm.mod(rng.next(), 100) < swap_pct) {          // AddToBuffer :25-37
-              const int pos = fm.mod(rng.next(), P);
-              neg_row[pos] = off + j;
-              in_set[slot_key[pos]] = 0;
-              slot_key[pos] = key;
-              in_set[key] = 1;
-            }
-          }
+          if (in_set[key]) continue;                       // rare (the buffer holds P of all shots): well predicted
+          const int take = fm.mod(rng.next(), 100) < swap_pct;
+          const int pos = take ? fm.mod(rng.peek(), P) : P;
+          rng.skip(take);
+          in_set[slot_key[pos]] = 0;                       // slot P / dummy key absorb the not-taken case
+          neg_row[pos] = off + j;
+          slot_key[pos] = take ? key : dummy_key;
+          in_set[take ? key : dummy_key] = uint8_t(take);
         }
       }
     }
@@ -211,8 +221,8 @@ extern "C" vv_sampler_t* vv_sampler_create(int num_videos, const int32_t* video_
   s->shot_ids.assign(shot_ids, shot_ids + shot_off[num_videos]);
   s->buffer_ids.resize(s->P);
   for (int i = 0; i < s->P; ++i) s->buffer_ids[i] = float(i);
-  s->neg_row.assign(s->P, -1);
-  s->slot_key.assign(s->P, 0);
+  s->neg_row.assign(s->P + 1, -1);           // + one dummy slot
+  s->slot_key.assign(s->P + 1, 0);
   {
     const int total = shot_off[num_videos];
     std::unordered_map<uint64_t, int32_t> ids;
@@ -223,7 +233,7 @@ extern "C" vv_sampler_t* vv_sampler_create(int num_videos, const int32_t* video_
         auto it = ids.emplace(shot_key(video_id[v], shot_ids[g]), int32_t(ids.size()));
         s->key_of[g] = it.first->second;
       }
-    s->in_set.assign(ids.size(), 0);
+    s->in_set.assign(ids.size() + 1, 0);     // + one dummy key for the branch-free swap loop
   }
   s->last_full.assign((size_t)batch_size * (context_size + num_negative_samples), -1);
   if (s->P > 0 && !s->init(max_tries_for_negs)) { delete s; return nullptr; }
