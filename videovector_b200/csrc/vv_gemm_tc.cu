@@ -44,6 +44,9 @@ struct Cfg {
   static constexpr bool gather = kGather;
   static constexpr bool gather_a = kGather && !kAMN;   // FWD : A rows = X rows
   static constexpr bool gather_b = kGather && kAMN;    // WGRAD: B k-rows = X rows
+  // 2-CTA clusters share the B tile: each CTA loads half of it with TMA multicast, which cuts the L2->smem
+  // fill per CTA from A+B to A+B/2 (the kernels are L2-bandwidth bound at ~12 TB/s, not MMA bound)
+  static constexpr int cluster = kGather ? 1 : 2;
   static constexpr bool tf32 = kTF32;
   static constexpr bool a_mn = kAMN, b_mn = kBMN;
   static constexpr int nprod = kNProd;                 // 1 or 3
@@ -92,18 +95,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     if (C::mixed) { tma_prefetch_desc(&tmA_hb); tma_prefetch_desc(&tmA_lb); tma_prefetch_desc(&tmB_hb); tma_prefetch_desc(&tmB_lb); }
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < C::stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < C::stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], C::cluster); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 8); }
     fence_barrier_init();
   }
   if (warp == 2) { tmem_alloc(tmem_slot, C::tmem_cols); tmem_relinquish(); }
   tc_fence_before();
-  __syncthreads();
+  if (C::cluster > 1) cluster_sync_all(); else __syncthreads();   // barrier inits visible to the peer before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int tiles_mn = p.tiles_m * p.tiles_n;
+  // Work units.  Without clusters: unit = (split, m-tile, n-tile), CTAs stride over units.  With 2-CTA clusters:
+  // unit = (split, PAIR of adjacent m-tiles, n-tile), clusters stride over units and CTA `rank` takes m-tile 2*pair+rank.
+  const int cta_rank = (C::cluster > 1) ? int(cluster_ctarank()) : 0;
+  const int tiles_mp = (p.tiles_m + C::cluster - 1) / C::cluster;
+  const int tiles_mn = tiles_mp * p.tiles_n;
   const int total_units = tiles_mn * p.nsplit;
+  const int unit0 = blockIdx.x / C::cluster, unit_stride = gridDim.x / C::cluster;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -111,10 +119,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     // of the bank rows named by rowmap, so the gathered operand never exists in HBM.
     if (lane == 0 || C::gather) {
       int stage = 0; uint32_t phase = 0;
-      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+      for (int u = unit0; u < total_units; u += unit_stride) {
         const int split = u / tiles_mn;
         const int t = u - split * tiles_mn;
-        const int m0 = (t / p.tiles_n) * kBlockM;
+        const int m0 = ((t / p.tiles_n) * C::cluster + cta_rank) * kBlockM;
         const int n0 = (t % p.tiles_n) * C::block_n;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
@@ -153,7 +161,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
               tma_gather4(sb + c * (C::bk * kRowBytes) + grp * 512, &tmB_hi, &full_bar[stage],
                           n0 + c * C::chunk, r.x, r.y, r.z, r.w);
           } else if (lane == 0) {
-            if (!C::b_mn) {
+            if (C::cluster > 1) {
+              // this CTA fetches half of the shared B tile and multicasts it to both CTAs of the cluster
+              if (!C::b_mn) {
+                tma_load_2d_mc(sb + cta_rank * (C::b_bytes / 2), &tmB_hi, &full_bar[stage], k0, n0 + cta_rank * (C::block_n / 2), 0x3);
+              } else {
+                constexpr int kHalf = C::block_n / C::chunk / 2;
+#pragma unroll
+                for (int c = 0; c < kHalf; ++c)
+                  tma_load_2d_mc(sb + (cta_rank * kHalf + c) * (C::bk * kRowBytes), &tmB_hi, &full_bar[stage],
+                                 n0 + (cta_rank * kHalf + c) * C::chunk, k0, 0x3);
+              }
+            } else if (!C::b_mn) {
               tma_load_2d(sb, &tmB_hi, &full_bar[stage], k0, n0);
             } else {
 #pragma unroll
@@ -176,7 +195,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 for (int c = 0; c < kBlockM / 64; ++c)                               // 64 bf16 of MN per 128 B row
                   tma_load_2d(da + c * (C::bk * kRowBytes), ta, &full_bar[stage], m0 + c * 64, k0);
               }
-              if (!C::b_mn) {
+              if (C::cluster > 1) {
+                if (!C::b_mn) {
+                  tma_load_2d_mc(db + cta_rank * (C::b_half / 2), tb, &full_bar[stage], k0, n0 + cta_rank * (C::block_n / 2), 0x3);
+                } else {
+                  constexpr int kHalf16 = C::block_n / 64 / 2;
+#pragma unroll
+                  for (int c = 0; c < kHalf16; ++c)
+                    tma_load_2d_mc(db + (cta_rank * kHalf16 + c) * (C::bk * kRowBytes), tb, &full_bar[stage],
+                                   n0 + (cta_rank * kHalf16 + c) * 64, k0, 0x3);
+                }
+              } else if (!C::b_mn) {
                 tma_load_2d(db, tb, &full_bar[stage], k0, n0);
               } else {
 #pragma unroll
@@ -207,7 +236,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       constexpr uint32_t sbo_b = (C::tf32 && C::b_mn) ? 512 : 1024;
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+      for (int u = unit0; u < total_units; u += unit_stride) {
         const int split = u / tiles_mn;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
@@ -251,7 +280,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
               umma_ss<C::tf32>(d_tmem, a_hi, b_hi, idesc, accumulate);
               accumulate = 1u;
             }
-            umma_commit(&empty_bar[stage]);            // frees the smem stage when these MMAs retire
+            // frees the smem stage when these MMAs retire -- in BOTH CTAs of a cluster (the peer multicasts into it)
+            if (C::cluster > 1) umma_commit_mc(&empty_bar[stage], 0x3); else umma_commit(&empty_bar[stage]);
             if (kb == c1 - 1) umma_commit(&tmem_full[acc]);
             if (++stage == C::stages) { stage = 0; phase ^= 1u; }
           }
@@ -266,10 +296,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     const int half = (warp - 4) >> 2;
     constexpr int kColsPerWarp = C::block_n / 2;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+    for (int u = unit0; u < total_units; u += unit_stride) {
       const int split = u / tiles_mn;
       const int t = u - split * tiles_mn;
-      const int m0 = (t / p.tiles_n) * kBlockM;
+      const int m0 = ((t / p.tiles_n) * C::cluster + cta_rank) * kBlockM;
       const int n0 = (t % p.tiles_n) * C::block_n + half * kColsPerWarp;
       const int kb0 = split * p.kb_per_split;
       const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
@@ -356,7 +386,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (C::cluster > 1) cluster_sync_all(); else __syncthreads();   // the peer may still arrive on / multicast into this CTA
   if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, C::tmem_cols); }
 #endif
 }
@@ -468,9 +498,17 @@ int launch_cfg(const GemmProblem& g, cudaStream_t stream) {
     VV_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::smem_bytes));
     attr_set = true;
   }
-  const int total = p.tiles_m * p.tiles_n * p.nsplit;
-  const int grid = total < num_sms() ? total : num_sms();
-  gemm_tc_kernel<C><<<grid, kNumThreads, C::smem_bytes, stream>>>(tA_hi, tA_hb, tA_lb, tB_hi, tB_hb, tB_lb, p);
+  const int total = ((p.tiles_m + C::cluster - 1) / C::cluster) * p.tiles_n * p.nsplit;     // units (per cluster)
+  int nclusters = num_sms() / C::cluster;
+  if (total < nclusters) nclusters = total;
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3(nclusters * C::cluster); lc.blockDim = dim3(kNumThreads);
+  lc.dynamicSmemBytes = C::smem_bytes; lc.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = C::cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  lc.attrs = attr; lc.numAttrs = 1;
+  VV_CUDA(cudaLaunchKernelEx(&lc, gemm_tc_kernel<C>, tA_hi, tA_hb, tA_lb, tB_hi, tB_hb, tB_lb, p));
   VV_LAUNCH_CHECK();
   count_launch();
   return VV_OK;
