@@ -450,7 +450,8 @@ int launch_cfg(const GemmProblem& g, cudaStream_t stream) {
     if (C::gather_a) a_outer = uint64_t(g.bank_rows); else b_outer = uint64_t(g.bank_rows);
   }
   const uint32_t a_box = C::gather_a ? 1 : (C::a_mn ? C::bk : kBlockM);
-  const uint32_t b_box = C::gather_b ? 1 : (C::b_mn ? C::bk : C::block_n);
+  // K-major B: with 2-CTA clusters each CTA fetches (and multicasts) half of the tile's rows
+  const uint32_t b_box = C::gather_b ? 1 : (C::b_mn ? C::bk : C::block_n / C::cluster);
   const CUtensorMapSwizzle sw_a = (C::tf32 && C::a_mn) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
   const CUtensorMapSwizzle sw_b = (C::tf32 && C::b_mn) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
   int rc;
