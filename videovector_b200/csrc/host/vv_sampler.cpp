@@ -27,13 +27,19 @@ struct vv_glibc_rand {
   // glibc TYPE_3 (random_r): with state r[0..30], fptr = &r[3], rptr = &r[0], draw k does
   // r[f] += r[q] and returns r[f] >> 1.  Unrolled onto a linear array L with
   // L[j] = r[(j + 3) % 31] for j < 31 this is  L[i] = L[i-31] + L[i-3]  and draw k = L[31 + k].
-  // srandom_r discards the first 310 draws.  Outputs are produced in blocks so next() is a load.
-  static constexpr int kBlock = 2048;
-  uint32_t buf[31 + kBlock];
-  int pos;
-  explicit vv_glibc_rand(unsigned int seed) { reseed(seed); }
+  // srandom_r discards the first 310 draws.
+  //
+  // The words are produced ahead of use into a window [pos, end) so that a consumer can reserve() all the
+  // draws of one record and then index them directly (draw k = word(k) >> 1): the sampler's loops then carry
+  // no dependency through the generator.  take[i] caches (draw_i % 100 < pct), the AddToBuffer coin of the
+  // reference, computed vectorised for every word (it is the only draw whose value decides how many draws follow).
+  std::vector<uint32_t> buf;        // 31 words of history + window
+  std::vector<uint8_t> take;
+  int pos, end, cap, pct;
+  explicit vv_glibc_rand(unsigned int seed, int pct_ = 0, int cap_ = 8192) : pos(0), end(0), cap(cap_), pct(pct_) { reseed(seed); }
   void reseed(unsigned int seed) {
     if (seed == 0) seed = 1;
+    buf.assign(size_t(31 + cap), 0u); take.assign(size_t(31 + cap), 0);
     int32_t r[31];
     r[0] = int32_t(seed);
     for (int i = 1; i < 31; ++i) {
@@ -44,26 +50,41 @@ struct vv_glibc_rand {
       r[i] = int32_t(w);
     }
     for (int j = 0; j < 31; ++j) buf[j] = uint32_t(r[(j + 3) % 31]);
-    generate();
+    end = 31;
+    generate_to(31 + cap);
     pos = 31 + 310;
   }
-  void generate() {
-    for (int i = 31; i < 31 + kBlock; ++i) buf[i] = buf[i - 31] + buf[i - 3];
+  __attribute__((target_clones("avx2", "default")))
+  void generate_to(int new_end) {
+    uint32_t* __restrict L = buf.data();
+    int i = end;
+    // three interleaved chains (the lag-3 term) kept in registers: one add per word
+    uint32_t a = L[i - 3], b = L[i - 2], c = L[i - 1];
+    for (; i + 3 <= new_end; i += 3) {
+      a += L[i - 31]; L[i] = a;
+      b += L[i - 30]; L[i + 1] = b;
+      c += L[i - 29]; L[i + 2] = c;
+    }
+    for (; i < new_end; ++i) L[i] = L[i - 31] + L[i - 3];
+    uint8_t* __restrict T = take.data();
+    const uint32_t p = uint32_t(pct);
+    for (int k = end; k < new_end; ++k) T[k] = uint8_t(((L[k] >> 1) % 100u) < p);
+    end = new_end;
   }
-  void refill() {
-    for (int i = 0; i < 31; ++i) buf[i] = buf[kBlock + i];
-    generate();
-    pos = 31;
+  // make draws [pos, pos + need) addressable
+  void reserve(int need) {
+    if (pos + need <= end) return;
+    const int from = pos - 31, tail = end - from;
+    std::memmove(buf.data(), buf.data() + from, size_t(tail) * sizeof(uint32_t));
+    std::memmove(take.data(), take.data() + from, size_t(tail));
+    pos = 31; end = tail;
+    if (need > cap) { cap = 2 * need; buf.resize(size_t(31 + cap)); take.resize(size_t(31 + cap)); }
+    generate_to(31 + cap);
   }
   int next() {
-    if (pos >= 31 + kBlock) refill();
+    reserve(1);
     return int(buf[pos++] >> 1);
   }
-  int peek() {                      // the next draw, not consumed
-    if (pos >= 31 + kBlock) refill();
-    return int(buf[pos] >> 1);
-  }
-  void skip(int n) { pos += n; }    // consume n (0 or 1) peeked draws
 };
 
 namespace {
@@ -99,15 +120,17 @@ struct vv_sampler {
   std::vector<uint8_t> in_set;            // [num_keys] membership
   std::vector<int32_t> last_full;         // [B,R] bank row of the last full-row write per slot, -1 = none
   FastMod fm;
-  vv_sampler(unsigned seed, int max_d) : rng(seed), cursor(0), fm(max_d) {}
+  std::vector<int> ids, js;
+  vv_sampler(unsigned seed, int max_d, int pct) : rng(seed, pct), cursor(0), fm(max_d) {}
 
-  // random_unique over a range (rng.hpp:43-54)
-  template <class T> void random_unique(T* first, int n, int num_random) {
-    int left = n;
-    while (num_random--) {
-      std::swap(*first, first[fm.mod(rng.next(), left)]);
-      ++first; --left;
-    }
+  // random_unique over a range (rng.hpp:43-54) from `count` reserved draws d[0..count):
+  // for k < count: swap(a[k], a[k + draw_k % (n - k)]).  The targets are computed first and the swaps done in a
+  // second pass: with the swap address hanging off the multiply chain the CPU mis-speculated the ids[] loads
+  // against in-flight stores (memory-order machine clears) on most iterations.
+  template <class T> void random_unique(T* a, int n, int count, const uint32_t* d) {
+    int* __restrict J = js.data();
+    for (int k = 0; k < count; ++k) J[k] = k + fm.mod(int(d[k] >> 1), n - k);
+    for (int k = 0; k < count; ++k) std::swap(a[k], a[J[k]]);
   }
   bool init(int max_tries) {
     int added = 0;
@@ -131,17 +154,28 @@ struct vv_sampler {
   int next(int32_t* idx, int32_t* quirk) {
     const int R = C + Nn;
     int item = 0; long guard = 0;
-    std::vector<int> ids;
+    // raw pointers in locals: the byte stores to in_set may alias anything, members would be reloaded after each
+    const int32_t* __restrict keyof = key_of.data();
+    int32_t* __restrict negrow = neg_row.data();
+    int32_t* __restrict slotkey = slot_key.data();
+    uint8_t* inset = in_set.data();
+    const int32_t dummy_key = int32_t(in_set.size()) - 1;
     while (item < B) {
       if (++guard > 100L * (B + V)) return VV_ERR_INVALID;
       const int v = cursor;
       cursor = (cursor + 1) % V;
       const int off = shot_off[v], n = shot_off[v + 1] - off;
       if (n < 2 || n < C) continue;                       // :387-389, :427-429 (no rand consumed)
-      ids.resize(n);
-      std::iota(ids.begin(), ids.end(), 0);
-      random_unique(ids.data(), n, C);                    // :432
-      std::sort(ids.begin(), ids.begin() + C);            // :437
+      if (int(ids.size()) < n) { ids.resize(n); js.resize(std::max(n, Nn) + 1); }
+      // every draw this record can consume: C (window) + n-C-1 (shuffle) + Nn (buffer) + 2n (swap)
+      rng.reserve(3 * n + Nn + 8);
+      const uint32_t* __restrict d = rng.buf.data() + rng.pos;
+      const uint8_t* __restrict tk = rng.take.data() + rng.pos;
+      int used = 0;
+      int* __restrict id = ids.data();
+      for (int i = 0; i < n; ++i) id[i] = i;
+      random_unique(id, n, C, d); used += C;              // :432
+      std::sort(id, id + C);                              // :437
       const int half = C / 2;
       int32_t* I = idx + (size_t)item * R;
       int32_t* Q = quirk + (size_t)item * R;
@@ -149,49 +183,54 @@ struct vv_sampler {
       int ctx = 0;
       for (int i = 0; i < C; ++i) {
         const int slot = (i == half) ? 0 : ++ctx;         // target -> slot 0, others in temporal order
-        I[slot] = off + ids[i]; Q[slot] = -2; L[slot] = off + ids[i];
+        I[slot] = off + id[i]; Q[slot] = -2; L[slot] = off + id[i];
       }
       int added = 0;
       if (Nn > 0 && n > C) {                              // same-video negatives :479-503
-        for (int i = C + 1; i < n; ++i) {                 // std::random_shuffle(ids+C, end)
-          const int j = C + fm.mod(rng.next(), i - C + 1);
-          std::swap(ids[i], ids[j]);                      // (i == j is a no-op: no branch needed)
-        }
+        // std::random_shuffle(ids+C, end): for i in C+1..n-1 swap(ids[i], ids[C + rand() % (i-C+1)])
+        int* __restrict J = js.data();
+        const int cnt = n - C - 1;
+        for (int k = 0; k < cnt; ++k) J[k] = C + fm.mod(int(d[used + k] >> 1), k + 2);
+        for (int k = 0; k < cnt; ++k) std::swap(id[C + 1 + k], id[J[k]]);
+        used += cnt > 0 ? cnt : 0;
+        const int lo = id[half - 1], hi = id[half + 1];
+        // branch-free filter: the candidate is written every time and kept by advancing `added`; a rejected
+        // candidate's slot is overwritten by the next one or by the buffer negatives below
         for (int nid = C; nid < n && added < max_same; ++nid) {
-          if (ids[nid] < ids[half - 1] || ids[nid] > ids[half + 1]) {
-            const int slot = C + added;
-            I[slot] = off + ids[nid];
-            Q[slot] = L[slot];                            // K-1 floats copied (:492): element K-1 keeps the old value
-            ++added;
-          }
+          const int slot = C + added;
+          I[slot] = off + id[nid];
+          Q[slot] = L[slot];                              // K-1 floats copied (:492): element K-1 keeps the old value
+          added += int(id[nid] < lo) | int(id[nid] > hi);
         }
       }
       if (Nn > 0) {                                       // buffer negatives :852-874
-        random_unique(buffer_ids.data(), P, Nn - added);
+        random_unique(buffer_ids.data(), P, Nn - added, d + used); used += Nn - added;
         for (int s = C + added; s < C + Nn; ++s) {
           const int neg_id = static_cast<int>(buffer_ids[s - C - added]);
-          I[s] = neg_row[neg_id]; Q[s] = -2; L[s] = neg_row[neg_id];
+          I[s] = negrow[neg_id]; Q[s] = -2; L[s] = negrow[neg_id];
         }
       }
       ++item;
       if (Nn > 0 && swap_pct > 0) {                       // swap this record's shots into the buffer :888-906
         // AddToBuffer (:25-37) draws rand()%100 and, only if that is below the swap percentage, a second
-        // rand()%P.  The second draw is peeked and consumed conditionally (rng.pos += take) and the buffer
-        // update is made branch-free through a dummy slot P / dummy key, because the 50/50 decision is
-        // unpredictable and the mispredictions dominated the sampler's cost.
-        const int32_t dummy_key = int32_t(in_set.size()) - 1;
+        // rand()%P.  The coin is read from the generator's precomputed take[] so the loop-carried chain is one
+        // byte load + add; the buffer update is branch-free through a dummy slot P / dummy key (the 50/50
+        // decision is unpredictable and the mispredictions dominated the sampler's cost).
         for (int j = 0; j < n; ++j) {
-          const int32_t key = key_of[off + j];
-          if (in_set[key]) continue;                       // rare (the buffer holds P of all shots): well predicted
-          const int take = fm.mod(rng.next(), 100) < swap_pct;
-          const int pos = take ? fm.mod(rng.peek(), P) : P;
-          rng.skip(take);
-          in_set[slot_key[pos]] = 0;                       // slot P / dummy key absorb the not-taken case
-          neg_row[pos] = off + j;
-          slot_key[pos] = take ? key : dummy_key;
-          in_set[take ? key : dummy_key] = uint8_t(take);
+          const int32_t key = keyof[off + j];
+          if (inset[key]) continue;                        // rare (the buffer holds P of all shots): well predicted
+          const int take = tk[used];                       // 0 / 1
+          const int m = fm.mod(int(d[used + 1] >> 1), P);  // computed either way: selects below are arithmetic, not branches
+          const int pos = P + ((m - P) & -take);
+          const int32_t nk = dummy_key + ((key - dummy_key) & -take);
+          used += 1 + take;
+          inset[slotkey[pos]] = 0;                         // slot P / dummy key absorb the not-taken case
+          negrow[pos] = off + j;
+          slotkey[pos] = nk;
+          inset[nk] = uint8_t(take);
         }
       }
+      rng.pos += used;
     }
     return VV_OK;
   }
@@ -212,7 +251,7 @@ extern "C" vv_sampler_t* vv_sampler_create(int num_videos, const int32_t* video_
   int max_d = max_buffer_size > 100 ? max_buffer_size : 100;
   for (int v = 0; v < num_videos; ++v) max_d = std::max(max_d, shot_off[v + 1] - shot_off[v]);
   if (max_d > (1 << 20)) max_d = 1 << 20;
-  vv_sampler* s = new vv_sampler(rand_seed, max_d);
+  vv_sampler* s = new vv_sampler(rand_seed, max_d, negative_swap_percentage);
   s->V = num_videos; s->B = batch_size; s->C = context_size; s->Nn = num_negative_samples;
   s->P = num_negative_samples > 0 ? max_buffer_size : 0;
   s->swap_pct = negative_swap_percentage; s->max_same = max_same_video_negs;
