@@ -198,11 +198,6 @@ __device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const void* tma
          "r"(c0), "r"(c1), "l"(policy)
       : "memory");
 }
-// L2 prefetch of a tile (no smem, no barrier): hides the DRAM->L2 part of the load latency
-__device__ __forceinline__ void tma_prefetch_2d(const void* tmap, int c0, int c1) {
-  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
-               :: "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1) : "memory");
-}
 // multicast: the tile lands at the same smem offset in every CTA of `mask` and completes tx on each one's mbarrier
 __device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1, uint16_t mask) {
   asm volatile(

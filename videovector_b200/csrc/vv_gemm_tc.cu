@@ -17,7 +17,6 @@
 // per element pair: hi*hi on the tf32 pipe and the two cross terms bf16(x)*bf16(lo) on the (2x faster) bf16
 // pipe, all accumulated in the same fp32 TMEM tile -> fp32-level accuracy at 4 instead of 6 MMA units.
 #include <cuda.h>
-#include <stdlib.h>
 #include "vv_gemm.cuh"
 
 namespace vv {
@@ -33,7 +32,6 @@ struct TcParams {
   int tiles_m, tiles_n, nsplit;
   int num_kb, kb_per_split;     // k-blocks (of kRowBytes worth of elements)
   int chunk_kb;                 // k-blocks accumulated in TMEM before promotion to fp32 registers
-  int prefetch_kb;              // L2 prefetch distance in k-blocks (0 = off)
   float* D; long long slab_stride;
   int act_N;                    // row pitch of mask/Z (= N of the layer) for the FWD epilogue
   const int* rowmap;            // gather variants: bank row of every X row (padded to a multiple of 128)
@@ -132,26 +130,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         if (C::gather_a) arow = *reinterpret_cast<const int4*>(p.rowmap + m0 + 4 * lane);   // this lane's 4 A rows
         for (int kb = kb0; kb < kb1; ++kb) {
           if (lane == 0) {
-            // The pipeline is latency bound (measured: ~2 us from a freed stage to landed data, smem holds only
-            // 3 stages in flight), so pull the tiles of a later k-block into L2 now: the eventual TMA then only
-            // pays the L2->smem leg.  Only the hi tiles (the bulk of the bytes) and only tiled (non-gather) loads.
-            const int kpf = kb + p.prefetch_kb;
-            if (p.prefetch_kb > 0 && kpf < kb1) {
-              const int kp0 = kpf * C::bk;
-              if (!C::gather_a) {
-                if (!C::a_mn) tma_prefetch_2d(&tmA_hi, kp0, m0);
-                else { for (int c = 0; c < kBlockM / C::chunk; ++c) tma_prefetch_2d(&tmA_hi, m0 + c * C::chunk, kp0); }
-              }
-              if (!C::gather_b) {
-                if (C::cluster > 1) {
-                  if (!C::b_mn) tma_prefetch_2d(&tmB_hi, kp0, n0 + cta_rank * (C::block_n / 2));
-                  else { for (int c = 0; c < C::block_n / C::chunk / 2; ++c) tma_prefetch_2d(&tmB_hi, n0 + (cta_rank * (C::block_n / C::chunk / 2) + c) * C::chunk, kp0); }
-                } else {
-                  if (!C::b_mn) tma_prefetch_2d(&tmB_hi, kp0, n0);
-                  else { for (int c = 0; c < C::block_n / C::chunk; ++c) tma_prefetch_2d(&tmB_hi, n0 + c * C::chunk, kp0); }
-                }
-              }
-            }
             mbar_wait(&empty_bar[stage], phase ^ 1u);
             mbar_arrive_expect_tx(&full_bar[stage], C::stage_bytes);
           }
@@ -512,11 +490,6 @@ int launch_cfg(const GemmProblem& g, cudaStream_t stream) {
   p.nsplit = nsplit;
   // tf32x3: promote every 512 reduction elements (16 k-blocks of 32) -> truncation bias < 4e-6 relative
   p.chunk_kb = C::promote ? 16 : p.kb_per_split;
-  {
-    static int pf = -1;
-    if (pf < 0) { const char* e = getenv("VV_GEMM_PREFETCH"); pf = e ? atoi(e) : 2 * C::stages; }
-    p.prefetch_kb = pf;
-  }
   p.D = g.D; p.slab_stride = g.slab_stride;
   p.act_N = g.N;
   p.epi = g.epi;
