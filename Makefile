@@ -15,7 +15,7 @@ CU_OBJS   := $(patsubst %.cu,$(OBJDIR)/%.o,$(CU_SRCS))
 CPP_OBJS  := $(patsubst %.cpp,$(OBJDIR)/%.o,$(CPP_SRCS))
 HDRS      := include/vv_b200.h $(wildcard videovector_b200/csrc/host/caffe_compat/caffe/*.hpp) $(wildcard videovector_b200/csrc/host/caffe_compat/caffe/proto/*.hpp) $(wildcard videovector_b200/csrc/*.cuh) $(wildcard videovector_b200/csrc/host/*.h) $(wildcard videovector_b200/csrc/host/*.hpp)
 
-all: $(LIBDIR)/libvv_b200.so
+all: $(LIBDIR)/libvv_b200.so build/vv_caffe
 
 $(OBJDIR)/%.o: %.cu $(HDRS)
 	@mkdir -p $(dir $@)

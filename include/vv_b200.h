@@ -208,6 +208,16 @@ int vv_rank_loss_backward_ex(const float* H, const vv_rank_cfg_t* cfg, const flo
                              float* dZ, void* dZop_hi, void* dZop_lo, int prec,
                              float* db_accum, const float* delta, float* dq_accum, vv_stream_t stream);
 
+/* K2 + K3 in one pass over H (the rows of an item stay in registers between the forward reductions and the
+ * gradient rows): same outputs as vv_rank_loss_forward followed by vv_rank_loss_backward_ex, bit for bit; every
+ * forward output may be NULL.  Supported when vv_rank_loss_fused_supported(cfg) (N <= 1024, C + Nn <= 32). */
+int vv_rank_loss_fused_supported(const vv_rank_cfg_t* cfg);
+int vv_rank_loss_fused(const float* H, const vv_rank_cfg_t* cfg, float loss_weight, int act_fused,
+                       float dropout_scale, float* stats, float* target_score, float* neg_score,
+                       float* item_loss, float* item_viol, float* loss, float* violations,
+                       float* dZ, void* dZop_hi, void* dZop_lo, int prec, float* db_accum,
+                       const float* delta, float* dq_accum, vv_stream_t stream);
+
 /* ------------------------------------------------------------------------- */
 /* K4: SGDSolver::ComputeUpdateValue + Net::Update + Blob::Update in one pass.  */
 /* ref: solver.cpp:486-576, net.cpp:804-839, blob.cpp:113-136.                 */
@@ -306,6 +316,7 @@ typedef struct vv_trainer_cfg {
   int world_size, rank;  /* data parallel */
   int compute_dgrad;     /* 0 in the shipped net (net.cpp:68-76) */
   int keep_blobs;        /* 1: also keep fp32 X / Z / dZ for inspection (parity tests) */
+  int split_rank_loss;   /* 1: run K2 and K3 as two kernels even where the fused one applies (A/B timing, tests) */
 } vv_trainer_cfg_t;
 
 vv_trainer_t* vv_trainer_create(const vv_trainer_cfg_t* cfg, vv_stream_t stream);

@@ -257,6 +257,38 @@ def test_rank_loss_forward_backward(B, C, Nn, N, norm):
     assert rel(db, dZ_ref.sum(0)) < 1e-5
 
 
+@pytest.mark.parametrize("B,C,Nn,N,norm", [(64, 5, 10, 512, 2), (33, 3, 4, 64, 1), (7, 5, 10, 1000, 2), (300, 7, 20, 256, 2),
+                                            (1, 5, 10, 512, 2)])
+@pytest.mark.parametrize("prec", ["fp32_simt", "tf32x3", "bf16"])
+def test_rank_loss_fused_equals_two_kernel_path(B, C, Nn, N, norm, prec):
+    """K2+K3 fused (rows in registers) against the forward + backward kernels: same reductions and formulas."""
+    R = C + Nn
+    g = torch.Generator(device="cuda").manual_seed(B + N)
+    H = torch.relu(torch.randn(R * B, N, device="cuda", generator=g))
+    H = (H * (torch.rand(R * B, N, device="cuda", generator=g) < 0.3) * 3.0).contiguous()
+    H[min(5, R * B - 1)] = 0.0
+    cfg = ops.rank_cfg(B, C, Nn, N, margin=2.0, norm=norm)
+    assert ops.rank_loss_fused_supported(cfg)
+    a = ops.rank_loss_forward(H, cfg)
+    dZ_a, op_a, db_a = ops.rank_loss_backward(H, cfg, a["stats"], 0.7, True, 10.0, prec=prec)
+    b, dZ_b, op_b, db_b = ops.rank_loss_fused(H, cfg, 0.7, True, 10.0, prec=prec)
+    for k in ("stats", "target_score", "neg_score", "item_viol", "violations"):
+        assert torch.equal(a[k], b[k]), k
+    assert rel(b["item_loss"], a["item_loss"]) < 1e-6 and rel(b["loss"], a["loss"]) < 1e-6
+    assert rel(dZ_b, dZ_a) < 1e-6
+    assert rel(db_b, db_a) < 1e-5                      # atomics: order differs
+    if torch.equal(dZ_a, dZ_b) and prec != "fp32_simt":
+        assert torch.equal(op_a.hi, op_b.hi) and (op_a.lo is None or torch.equal(op_a.lo, op_b.lo))
+    loss, viol, st, sn, dH_ref, dZ_ref = _rank_ref64(H, B, C, Nn, 2.0, norm, 0.7, 10.0)
+    assert abs(b["loss"].item() - loss) < 1e-5 * max(1, abs(loss)) and b["violations"].item() == viol
+    assert rel(dZ_b, dZ_ref) < 1e-5
+
+
+def test_rank_loss_fused_unsupported_shapes():
+    assert not ops.rank_loss_fused_supported(ops.rank_cfg(8, 5, 30, 512))     # R > 32
+    assert not ops.rank_loss_fused_supported(ops.rank_cfg(8, 5, 10, 2048))    # N > 1024
+
+
 @pytest.mark.parametrize("prec", ["tf32x3", "bf16"])
 def test_rank_loss_backward_operand_copies(prec):
     B, C, Nn, N = 32, 5, 10, 512

@@ -44,7 +44,7 @@ class TrainerCfg(C.Structure):
                 ("momentum", C.c_float), ("weight_decay", C.c_float), ("reg_type", C.c_int),
                 ("lr_mult", C.c_float * 2), ("decay_mult", C.c_float * 2),
                 ("prec", C.c_int), ("world_size", C.c_int), ("rank", C.c_int),
-                ("compute_dgrad", C.c_int), ("keep_blobs", C.c_int)]
+                ("compute_dgrad", C.c_int), ("keep_blobs", C.c_int), ("split_rank_loss", C.c_int)]
 
 
 _P = C.c_void_p
@@ -70,6 +70,8 @@ SIGNATURES = {
     "vv_add_column": (_i, [_P, _i64, _i, _P, _i, _P]),
     "vv_rank_loss_backward_ex": (_i, [_P, C.POINTER(RankCfg), _P, _f, _i, _f, _P, _P, _P, _i, _P, _P, _P, _P]),
     "vv_trainer_set_bank": (_i, [_P, _P, _i64]),
+    "vv_rank_loss_fused_supported": (_i, [C.POINTER(RankCfg)]),
+    "vv_rank_loss_fused": (_i, [_P, C.POINTER(RankCfg), _f, _i, _f, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _i, _P, _P, _P, _P]),
     "vv_rank_loss_forward": (_i, [_P, C.POINTER(RankCfg), _P, _P, _P, _P, _P, _P, _P, _P]),
     "vv_rank_loss_backward": (_i, [_P, C.POINTER(RankCfg), _P, _f, _i, _f, _P, _P, _P, _i, _P, _P]),
     "vv_sgd_update": (_i, [_P, _P, _i, _i64, _P, _P, _i64, _f, _f, _f, _i, _f, _P, _P, _i, _P]),

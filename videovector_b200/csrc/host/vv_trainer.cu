@@ -270,20 +270,32 @@ extern "C" int vv_trainer_step(vv_trainer_t* t, const float* bank, int64_t bank_
                             t->H.as<float>(), s))) return rc;
   }
   t->toc(1);
-  // K2
-  t->tic(2);
-  if ((rc = vv_rank_loss_forward(t->H.as<float>(), &t->rank, t->stats.as<float>(), nullptr, nullptr,
-                                 t->item_loss.as<float>(), t->item_viol.as<float>(), t->loss_ptr(), t->viol_ptr(), s))) return rc;
-  t->toc(2);
-  // K3 (+ bias gradient)
-  t->tic(3);
-  VV_CUDA(cudaMemsetAsync(t->dbx.p, 0, size_t(N) * 4, t->stream));
-  if (fused_gather) VV_CUDA(cudaMemsetAsync(t->dq.p, 0, size_t(N) * 4, t->stream));
-  count_launch();
   const float dscale = has_dropout ? dropout_scale(c.dropout_ratio) : 1.f;
-  if ((rc = vv_rank_loss_backward_ex(t->H.as<float>(), &t->rank, t->stats.as<float>(), c.loss_weight, 1, dscale,
-                                     t->dZf.as<float>(), t->dZ_hi.p, t->dZ_lo.p, c.prec, t->dbx.as<float>(),
-                                     fused_gather ? t->delta.as<float>() : nullptr, fused_gather ? t->dq.as<float>() : nullptr, s))) return rc;
+  if (vv_rank_loss_fused_supported(&t->rank) && !c.split_rank_loss) {
+    // K2 + K3 in one pass over H (+ bias gradient); timed as phase 3, phase 2 stays 0
+    t->tic(3);
+    VV_CUDA(cudaMemsetAsync(t->dbx.p, 0, size_t(N) * 4, t->stream));
+    if (fused_gather) VV_CUDA(cudaMemsetAsync(t->dq.p, 0, size_t(N) * 4, t->stream));
+    count_launch();
+    if ((rc = vv_rank_loss_fused(t->H.as<float>(), &t->rank, c.loss_weight, 1, dscale, t->stats.as<float>(), nullptr, nullptr,
+                                 t->item_loss.as<float>(), t->item_viol.as<float>(), t->loss_ptr(), t->viol_ptr(),
+                                 t->dZf.as<float>(), t->dZ_hi.p, t->dZ_lo.p, c.prec, t->dbx.as<float>(),
+                                 fused_gather ? t->delta.as<float>() : nullptr, fused_gather ? t->dq.as<float>() : nullptr, s))) return rc;
+  } else {
+    // K2
+    t->tic(2);
+    if ((rc = vv_rank_loss_forward(t->H.as<float>(), &t->rank, t->stats.as<float>(), nullptr, nullptr,
+                                   t->item_loss.as<float>(), t->item_viol.as<float>(), t->loss_ptr(), t->viol_ptr(), s))) return rc;
+    t->toc(2);
+    // K3 (+ bias gradient)
+    t->tic(3);
+    VV_CUDA(cudaMemsetAsync(t->dbx.p, 0, size_t(N) * 4, t->stream));
+    if (fused_gather) VV_CUDA(cudaMemsetAsync(t->dq.p, 0, size_t(N) * 4, t->stream));
+    count_launch();
+    if ((rc = vv_rank_loss_backward_ex(t->H.as<float>(), &t->rank, t->stats.as<float>(), c.loss_weight, 1, dscale,
+                                       t->dZf.as<float>(), t->dZ_hi.p, t->dZ_lo.p, c.prec, t->dbx.as<float>(),
+                                       fused_gather ? t->delta.as<float>() : nullptr, fused_gather ? t->dq.as<float>() : nullptr, s))) return rc;
+  }
   t->toc(3);
   // K1 wgrad into split-K slabs
   t->tic(4);

@@ -175,6 +175,18 @@ __device__ __forceinline__ void store_row4(const BwdOut& o, size_t off, const fl
   }
 }
 
+// OUT bit 0: fp32 dZ, bits 1..: 0 none, 2 = TF32X3 operand copy, 4 = BF16 operand copy; OUT < 0: decide at run time
+template <int OUT>
+__device__ __forceinline__ void store_row4_t(const BwdOut& o, size_t off, const float4& v) {
+  if (OUT < 0) { store_row4(o, off, v); return; }
+  if (OUT & 1) stg_stream(reinterpret_cast<float4*>(o.dZ + off), v);
+  if (OUT & 2) store_x3(o.hi, o.lo, o.count, off, v);
+  if (OUT & 4) {
+    uint2 pk = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    *reinterpret_cast<uint2*>(o.bf + off) = pk;
+  }
+}
+
 template <int NVEC>
 __global__ void __launch_bounds__(256)
 rank_bwd_kernel(const float* __restrict__ H, const RankDev p, const float* __restrict__ stats,
@@ -335,6 +347,214 @@ rank_bwd_kernel(const float* __restrict__ H, const RankDev p, const float* __res
   }
 }
 
+// Sums NV values across the warp with NV + NV/2 + ... shuffles instead of 5 * NV: at each xor distance a lane keeps
+// one half of the (remaining) values and hands the other half to its partner.  The addition tree per value is the
+// xor butterfly of warp_sum, so the totals are bit-identical.  On return v[0] of lane l is the warp total of value
+// `index` (valid lanes only; every value ends up in exactly one lane).
+template <int NV, int N, int OFF>
+__device__ __forceinline__ void warp_multi_sum_step(float (&v)[NV], int lane, int& base, int& nvalid) {
+  constexpr int half = (N + 1) / 2;
+  const bool up = (lane & OFF) != 0;
+#pragma unroll
+  for (int i = 0; i < half; ++i) {
+    const float a = v[i];
+    const float b = (i + half < N) ? v[i + half] : 0.f;
+    const float recv = __shfl_xor_sync(0xffffffffu, up ? a : b, OFF);
+    v[i] = (up ? b : a) + recv;
+  }
+  const int live = nvalid < N ? nvalid : N;
+  if (up) { base += half; nvalid = live > half ? live - half : 0; }
+  else    { nvalid = live < half ? live : half; }
+  if constexpr (OFF > 1) warp_multi_sum_step<NV, half, OFF / 2>(v, lane, base, nvalid);
+}
+template <int NV>
+__device__ __forceinline__ void warp_multi_sum(float (&v)[NV], int lane, int& index, bool& valid) {
+  int base = 0, nvalid = NV;
+  warp_multi_sum_step<NV, NV, 16>(v, lane, base, nvalid);
+  index = base; valid = nvalid >= 1;
+}
+
+// ---- K2+K3 in one pass -------------------------------------------------------------------------------------
+// All R rows of an item live in registers (R*N*4 bytes are read from HBM exactly once), the 2J+1 dot products
+// are reduced through shared memory, warp 0 evaluates the per-item scalar chain (scores, hinge, every backward
+// coefficient) with one lane per branch, and the gradient rows are produced from the registers: algorithmic
+// traffic = R*N*4 read + the dZ operand write.  The reduction trees, accumulation orders and formulas are the
+// same as rank_fwd_kernel / rank_bwd_kernel above, so the results are bit-identical to the two-kernel path.
+// Needs nvec == 1 (N <= 1024), R <= RMAX and J <= 32; otherwise the two-kernel path runs.
+// CT / NNT > 0: context size / negatives fixed at compile time (the per-row role tests fold away); OUT: store mode.
+template <int RMAX, int CT, int NNT, int OUT>
+__global__ void __launch_bounds__(256)
+rank_fused_kernel(const float* __restrict__ H, const RankDev p, const float gscale, const int act_fused,
+                  const float dscale, const BwdOut out, float* __restrict__ db_accum,
+                  const float* __restrict__ delta, float* __restrict__ dq_accum,
+                  float* __restrict__ stats, float* __restrict__ tscore, float* __restrict__ nscore,
+                  float* __restrict__ item_loss, float* __restrict__ item_viol) {
+  extern __shared__ float sm[];
+  const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = T >> 5;
+  const int Cc = CT > 0 ? CT : p.C, Nn = NNT > 0 ? NNT : p.Nn;
+  const int J = 1 + Nn, R = Cc + Nn;
+  const int per = (2 * J + 1) * nw + 3 * J + 2;        // floats per smem buffer (double buffered by item parity)
+  const bool col_ok = tid < p.N4;
+  float4 dbacc = make_float4(0.f, 0.f, 0.f, 0.f), dqacc = make_float4(0.f, 0.f, 0.f, 0.f);
+  int parity = 0;
+  for (int b = blockIdx.x; b < p.B; b += gridDim.x, parity ^= 1) {
+    float* part = sm + parity * per;                   // [2J+1][nw]: (s_x, p_x) per branch, then s_c
+    float* cA = part + (2 * J + 1) * nw;               // [J] coefficient on cbar
+    float* cB = cA + J;                                // [J] coefficient on x
+    float* cE = cB + J;                                // [J] w_j / n_j
+    float* sc = cE + J;                                // Fs, Fc
+    // ---- one load phase: R independent 128-bit loads per thread
+    float4 x[RMAX];
+#pragma unroll
+    for (int r = 0; r < RMAX; ++r)
+      x[r] = (r < R && col_ok) ? ld4(H + (size_t(r) * p.B + b) * p.N + tid * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    // ---- context mean, bottom order (eltwise_layer.cpp:67-73)
+    float4 cbar = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int r = 1; r < RMAX; ++r) {
+      if (r < Cc) {
+        const float a = p.coeff[r - 1];
+        cbar.x = fmaf(a, x[r].x, cbar.x); cbar.y = fmaf(a, x[r].y, cbar.y);
+        cbar.z = fmaf(a, x[r].z, cbar.z); cbar.w = fmaf(a, x[r].w, cbar.w);
+      }
+    }
+    if (NNT > 0) {
+      constexpr int NV = 2 * (NNT > 0 ? 1 + NNT : 1) + 1;
+      float v[NV];
+#pragma unroll
+      for (int r = 0; r < RMAX; ++r) {
+        if (r < R && (r == 0 || r >= Cc)) {
+          const int j = (r == 0) ? 0 : r - Cc + 1;
+          v[2 * j] = dot4(x[r], x[r]); v[2 * j + 1] = dot4(cbar, x[r]);
+        }
+      }
+      v[NV - 1] = dot4(cbar, cbar);
+      int e; bool ok;
+      warp_multi_sum<NV>(v, lane, e, ok);
+      if (ok) part[e * nw + warp] = v[0];
+    } else {
+      {
+        float s = warp_sum(dot4(cbar, cbar));
+        if (lane == 0) part[2 * J * nw + warp] = s;
+      }
+#pragma unroll
+      for (int r = 0; r < RMAX; ++r) {
+        if (r < R && (r == 0 || r >= Cc)) {             // uniform branch
+          const int j = (r == 0) ? 0 : r - Cc + 1;
+          float sx = warp_sum(dot4(x[r], x[r])), px = warp_sum(dot4(cbar, x[r]));
+          if (lane == 0) { part[(j * 2 + 0) * nw + warp] = sx; part[(j * 2 + 1) * nw + warp] = px; }
+        }
+      }
+    }
+    __syncthreads();
+    // ---- per-item scalars on warp 0, lane j = branch j
+    if (warp == 0) {
+      float s_c = 0.f;
+      for (int w = 0; w < nw; ++w) s_c += part[2 * J * nw + w];
+      float sj = 0.f, pj = 0.f;
+      if (lane < J) {
+        for (int w = 0; w < nw; ++w) sj += part[(lane * 2 + 0) * nw + w];
+        for (int w = 0; w < nw; ++w) pj += part[(lane * 2 + 1) * nw + w];
+      }
+      if (stats) {
+        float* st = stats + size_t(b) * p.stride;
+        if (lane == 0) st[0] = s_c;
+        if (lane < J) { st[1 + 2 * lane] = sj; st[2 + 2 * lane] = pj; }
+      }
+      // normalization_layer.cpp:36-59: r = pow(s, .5) + eps ; y = x / r.  scores = <c^, x^>
+      const float nc = sqrtf(s_c) + p.eps;
+      const float nj = sqrtf(sj) + p.eps;
+      const float score = pj / (nc * nj);
+      const float score_t = __shfl_sync(0xffffffffu, score, 0);
+      const float dlt = score_t - score;                                  // caffe_sub :69
+      const float h = fmaxf(0.f, p.margin - dlt);
+      const bool neg = lane >= 1 && lane < J;
+      // max_margin_loss_layer.cpp:149-192: L2 g = h * (lw*2/count); L1 g = [h>0] * lw/count
+      float w = neg ? ((p.norm == 2) ? h * gscale : (h > 0.f ? gscale : 0.f)) : 0.f;
+      const float vterm = (neg && dlt < 0.f) ? 1.f : 0.f;
+      float loss = 0.f, viol = 0.f, g = 0.f;
+      for (int k = 1; k < J; ++k) {                                       // serial order of the reference loops
+        const float hk = __shfl_sync(0xffffffffu, h, k);
+        loss += (p.norm == 2) ? hk * hk : fabsf(hk);
+        viol += __shfl_sync(0xffffffffu, vterm, k);
+        g += __shfl_sync(0xffffffffu, w, k);
+      }
+      if (lane == 0) w = -g;                                              // d s+ = -1 * d s- (axpby, :210-212)
+      if (neg) {
+        if (tscore) tscore[size_t(b) * Nn + lane - 1] = score_t;        // sum_true replicates to Nn columns
+        if (nscore) nscore[size_t(b) * Nn + lane - 1] = score;
+      }
+      if (lane == 0) { if (item_loss) item_loss[b] = loss; if (item_viol) item_viol[b] = viol; }
+      const float q = powf(sj, 1.5f) + p.eps;                             // normalization_layer.cpp:101-107
+      const float aj = w * pj / nc;
+      const float e = w / nj;
+      if (lane < J) { cA[lane] = sj * w / (nc * q); cB[lane] = -aj / q; cE[lane] = e; }
+      float ac = 0.f;                                                     // a_c = <cbar, d c^>, split order
+      for (int j = 0; j < J; ++j) ac += __shfl_sync(0xffffffffu, e, j) * __shfl_sync(0xffffffffu, pj, j);
+      if (lane == 0) { const float qc = powf(s_c, 1.5f) + p.eps; sc[0] = s_c / qc; sc[1] = -ac / qc; }
+    }
+    __syncthreads();
+    // ---- target + negative rows: dx = cA*cbar + cB*x ; D += cE*x
+    float4 D = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < RMAX; ++r) {
+      if (r < R && (r == 0 || r >= Cc)) {
+        const int j = (r == 0) ? 0 : r - Cc + 1;
+        const float a = cA[j], bb = cB[j], e = cE[j];
+        if (col_ok) {
+          const float4 xv = x[r];
+          float4 o;
+          o.x = fmaf(a, cbar.x, bb * xv.x); o.y = fmaf(a, cbar.y, bb * xv.y);
+          o.z = fmaf(a, cbar.z, bb * xv.z); o.w = fmaf(a, cbar.w, bb * xv.w);
+          D.x = fmaf(e, xv.x, D.x); D.y = fmaf(e, xv.y, D.y); D.z = fmaf(e, xv.z, D.z); D.w = fmaf(e, xv.w, D.w);
+          if (act_fused) {   // dZ = dH * mask*scale * [Z>0]  <=>  dH * scale * [H>0]
+            o.x = xv.x > 0.f ? o.x * dscale : 0.f; o.y = xv.y > 0.f ? o.y * dscale : 0.f;
+            o.z = xv.z > 0.f ? o.z * dscale : 0.f; o.w = xv.w > 0.f ? o.w * dscale : 0.f;
+          }
+          dbacc.x += o.x; dbacc.y += o.y; dbacc.z += o.z; dbacc.w += o.w;
+          if (delta) {                                                    // uniform
+            const float dl = delta[size_t(r) * p.B + b];
+            dqacc.x = fmaf(dl, o.x, dqacc.x); dqacc.y = fmaf(dl, o.y, dqacc.y);
+            dqacc.z = fmaf(dl, o.z, dqacc.z); dqacc.w = fmaf(dl, o.w, dqacc.w);
+          }
+          store_row4_t<OUT>(out, (size_t(r) * p.B + b) * p.N + tid * 4, o);
+        }
+      }
+    }
+    // ---- context rows: d cbar = (s_c * d c^ - cbar * a_c) / q_c ; d c_i = coeff_i * d cbar
+    const float Fs = sc[0], Fc = sc[1];
+    float4 dcb;
+    dcb.x = fmaf(Fs, D.x, Fc * cbar.x); dcb.y = fmaf(Fs, D.y, Fc * cbar.y);
+    dcb.z = fmaf(Fs, D.z, Fc * cbar.z); dcb.w = fmaf(Fs, D.w, Fc * cbar.w);
+#pragma unroll
+    for (int r = 1; r < RMAX; ++r) {
+      if (r < Cc && col_ok) {
+        const float a = p.coeff[r - 1];
+        float4 o = make_float4(a * dcb.x, a * dcb.y, a * dcb.z, a * dcb.w);
+        if (act_fused) {
+          const float4 xv = x[r];
+          o.x = xv.x > 0.f ? o.x * dscale : 0.f; o.y = xv.y > 0.f ? o.y * dscale : 0.f;
+          o.z = xv.z > 0.f ? o.z * dscale : 0.f; o.w = xv.w > 0.f ? o.w * dscale : 0.f;
+        }
+        dbacc.x += o.x; dbacc.y += o.y; dbacc.z += o.z; dbacc.w += o.w;
+        store_row4_t<OUT>(out, (size_t(r) * p.B + b) * p.N + tid * 4, o);
+      }
+    }
+    // no trailing barrier: the next item uses the other smem buffer, and the barrier after its reductions
+    // orders this item's coefficient reads before the buffer is written again two items later
+  }
+  if (col_ok) {
+    if (db_accum) {
+      atomicAdd(db_accum + tid * 4 + 0, dbacc.x); atomicAdd(db_accum + tid * 4 + 1, dbacc.y);
+      atomicAdd(db_accum + tid * 4 + 2, dbacc.z); atomicAdd(db_accum + tid * 4 + 3, dbacc.w);
+    }
+    if (dq_accum) {
+      atomicAdd(dq_accum + tid * 4 + 0, dqacc.x); atomicAdd(dq_accum + tid * 4 + 1, dqacc.y);
+      atomicAdd(dq_accum + tid * 4 + 2, dqacc.z); atomicAdd(dq_accum + tid * 4 + 3, dqacc.w);
+    }
+  }
+}
+
 int make_dev(const vv_rank_cfg_t* cfg, RankDev* d, int* threads) {
   VV_REQUIRE(cfg, "rank cfg is NULL");
   VV_REQUIRE(cfg->B > 0 && cfg->C >= 2 && cfg->Nn >= 1 && cfg->N > 0, "bad rank cfg B=%d C=%d Nn=%d N=%d", cfg->B, cfg->C, cfg->Nn, cfg->N);
@@ -423,5 +643,56 @@ extern "C" int vv_rank_loss_backward_ex(const float* H, const vv_rank_cfg_t* cfg
   }
   VV_LAUNCH_CHECK();
   count_launch();
+  return VV_OK;
+}
+
+extern "C" int vv_rank_loss_fused_supported(const vv_rank_cfg_t* cfg) {
+  return cfg && cfg->N % 4 == 0 && cfg->N <= 1024 && cfg->C + cfg->Nn <= 32 && 1 + cfg->Nn <= 32 && cfg->Nn >= 1 && cfg->C >= 2;
+}
+
+extern "C" int vv_rank_loss_fused(const float* H, const vv_rank_cfg_t* cfg, float loss_weight, int act_fused,
+                                  float dropout_scale, float* stats, float* target_score, float* neg_score,
+                                  float* item_loss, float* item_viol, float* loss, float* violations,
+                                  float* dZ, void* dZop_hi, void* dZop_lo, int prec, float* db_accum,
+                                  const float* delta, float* dq_accum, vv_stream_t stream) {
+  RankDev d; int T;
+  int rc = make_dev(cfg, &d, &T);
+  if (rc) return rc;
+  VV_REQUIRE(vv_rank_loss_fused_supported(cfg), "rank_loss_fused: needs N <= 1024, C + Nn <= 32 (use forward + backward)");
+  VV_REQUIRE(H, "H must be non-NULL");
+  VV_REQUIRE(!(loss || violations) || (item_loss && item_viol), "loss/violations need item_loss and item_viol scratch [B]");
+  BwdOut o; o.dZ = dZ; o.hi = nullptr; o.lo = nullptr; o.bf = nullptr; o.prec = VV_PREC_FP32_SIMT;
+  o.count = size_t(d.B) * (d.C + d.Nn) * d.N;
+  if (prec == VV_PREC_TF32X3 && dZop_hi) {
+    VV_REQUIRE(dZop_lo, "TF32X3 operand copy needs hi and lo");
+    o.hi = static_cast<float*>(dZop_hi); o.lo = static_cast<float*>(dZop_lo); o.prec = prec;
+  } else if (prec == VV_PREC_BF16 && dZop_hi) {
+    o.bf = static_cast<uint16_t*>(dZop_hi); o.prec = prec;
+  }
+  VV_REQUIRE(o.dZ || o.prec != VV_PREC_FP32_SIMT, "no output requested");
+  VV_REQUIRE(!dq_accum || delta, "dq_accum needs delta");
+  const int count = d.B * d.Nn;
+  const float gscale = (d.norm == 2) ? loss_weight * 2 / count : loss_weight / count;
+  const int J = 1 + d.Nn, nw = T / 32, R = d.C + d.Nn;
+  const size_t smem = sizeof(float) * 2 * ((2 * J + 1) * nw + 3 * J + 2);
+  const int per_sm = (R <= 16) ? 4 : 2;         // resident CTAs per SM at the kernels' register counts x T threads
+  const int grid = d.B < num_sms() * per_sm ? d.B : num_sms() * per_sm;
+  const int mode = (o.dZ ? 1 : 0) | (o.prec == VV_PREC_TF32X3 ? 2 : 0) | (o.prec == VV_PREC_BF16 ? 4 : 0);
+#define VV_RANK_FUSED(RM, CT, NNT, OUT)                                                                              \
+  rank_fused_kernel<RM, CT, NNT, OUT><<<grid, T, smem, stream>>>(H, d, gscale, act_fused, dropout_scale, o, db_accum, \
+      delta, dq_accum, stats, target_score, neg_score, item_loss, item_viol)
+  if (d.C == 5 && d.Nn == 10 && mode == 2) VV_RANK_FUSED(16, 5, 10, 2);        // the shipped net (C=5, Nn=10), training modes
+  else if (d.C == 5 && d.Nn == 10 && mode == 4) VV_RANK_FUSED(16, 5, 10, 4);
+  else if (d.C == 5 && d.Nn == 10 && mode == 1) VV_RANK_FUSED(16, 5, 10, 1);
+  else if (R <= 16) VV_RANK_FUSED(16, 0, 0, -1);
+  else VV_RANK_FUSED(32, 0, 0, -1);
+#undef VV_RANK_FUSED
+  VV_LAUNCH_CHECK();
+  count_launch();
+  if (loss || violations) {
+    rank_loss_reduce_kernel<<<1, 1024, 0, stream>>>(item_loss, item_viol, d.B, 1.f / float(d.B * d.Nn), loss, violations);
+    VV_LAUNCH_CHECK();
+    count_launch();
+  }
   return VV_OK;
 }

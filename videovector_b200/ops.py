@@ -163,6 +163,33 @@ def rank_loss_backward(H, cfg, stats, loss_weight=1.0, act_fused=True, dropout_s
     return dZ, (op if op is not None else OperandT(dZ)), db
 
 
+def rank_loss_fused_supported(cfg):
+    return bool(_lib.load().vv_rank_loss_fused_supported(C.byref(cfg)))
+
+
+def rank_loss_fused(H, cfg, loss_weight=1.0, act_fused=True, dropout_scale=1.0, prec="fp32_simt", want_db=True):
+    """K2 + K3 in one pass.  Returns (forward dict as rank_loss_forward, dZ fp32, operand copies, db)."""
+    dev = H.device
+    B, Nn = cfg.B, cfg.Nn
+    p = _prec(prec)
+    out = dict(stats=torch.empty((B, 1 + 2 * (1 + Nn)), dtype=torch.float32, device=dev),
+               target_score=torch.empty((B, Nn), dtype=torch.float32, device=dev),
+               neg_score=torch.empty((B, Nn), dtype=torch.float32, device=dev),
+               item_loss=torch.empty((B,), dtype=torch.float32, device=dev),
+               item_viol=torch.empty((B,), dtype=torch.float32, device=dev),
+               loss=torch.empty((1,), dtype=torch.float32, device=dev),
+               violations=torch.empty((1,), dtype=torch.float32, device=dev))
+    dZ = torch.empty_like(H)
+    op = alloc_operand(H.shape, p, dev)
+    db = torch.zeros((cfg.N,), dtype=torch.float32, device=dev) if want_db else None
+    check(_lib.load().vv_rank_loss_fused(_ptr(H), C.byref(cfg), loss_weight, int(act_fused), dropout_scale,
+                                         _ptr(out["stats"]), _ptr(out["target_score"]), _ptr(out["neg_score"]),
+                                         _ptr(out["item_loss"]), _ptr(out["item_viol"]), _ptr(out["loss"]),
+                                         _ptr(out["violations"]), _ptr(dZ), _ptr(op.hi) if op else None,
+                                         _ptr(op.lo) if op else None, p, _ptr(db), None, None, _stream()))
+    return out, dZ, (op if op is not None else OperandT(dZ)), db
+
+
 def sgd_update(W, grad_parts, hist, local_rate, momentum, local_decay, reg_type=2, grad_scale=1.0, prec="fp32_simt",
                Wop=None, diff_out=None):
     """K4 (in place on W, hist).  grad_parts [S, ...] or [...]."""
@@ -269,7 +296,7 @@ SOLVER_DEFAULTS = dict(lr_policy="inv", base_lr=1e-3, gamma=1e-3, power=0.75, st
 
 def trainer_cfg(B, C_=5, Nn=10, K=4096, N=512, margin=2.0, norm=2, dropout_ratio=0.9, dropout_mode=DROPOUT_PHILOX,
                 dropout_seed=7, loss_weight=1.0, regularization=0.0, prec="tf32x3", world_size=1, rank=0,
-                compute_dgrad=False, keep_blobs=False, coeff=None, **solver):
+                compute_dgrad=False, keep_blobs=False, coeff=None, split_rank_loss=False, **solver):
     s = dict(SOLVER_DEFAULTS); s.update(solver)
     c = TrainerCfg()
     c.B, c.C, c.Nn, c.K, c.N = B, C_, Nn, K, N
@@ -286,6 +313,7 @@ def trainer_cfg(B, C_=5, Nn=10, K=4096, N=512, margin=2.0, norm=2, dropout_ratio
     c.decay_mult[0], c.decay_mult[1] = s["decay_mult"]
     c.prec = _prec(prec); c.world_size, c.rank = world_size, rank
     c.compute_dgrad, c.keep_blobs = int(compute_dgrad), int(keep_blobs)
+    c.split_rank_loss = int(split_rank_loss)
     return c
 
 
