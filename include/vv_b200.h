@@ -209,7 +209,7 @@ int vv_rank_loss_backward_ex(const float* H, const vv_rank_cfg_t* cfg, const flo
                              float* db_accum, const float* delta, float* dq_accum, vv_stream_t stream);
 
 /* K2 + K3 in one pass over H (the rows of an item stay in registers between the forward reductions and the
- * gradient rows): same outputs as vv_rank_loss_forward followed by vv_rank_loss_backward_ex, bit for bit; every
+ * gradient rows): same outputs as vv_rank_loss_forward followed by vv_rank_loss_backward_ex (to rounding); every
  * forward output may be NULL.  Supported when vv_rank_loss_fused_supported(cfg) (N <= 1024, C + Nn <= 32). */
 int vv_rank_loss_fused_supported(const vv_rank_cfg_t* cfg);
 int vv_rank_loss_fused(const float* H, const vv_rank_cfg_t* cfg, float loss_weight, int act_fused,

@@ -261,7 +261,8 @@ def test_rank_loss_forward_backward(B, C, Nn, N, norm):
                                             (1, 5, 10, 512, 2)])
 @pytest.mark.parametrize("prec", ["fp32_simt", "tf32x3", "bf16"])
 def test_rank_loss_fused_equals_two_kernel_path(B, C, Nn, N, norm, prec):
-    """K2+K3 fused (rows in registers) against the forward + backward kernels: same reductions and formulas."""
+    """K2+K3 fused (rows in registers) against the forward + backward kernels: same formulas, reductions equal up to
+    FMA contraction / summation order (1e-6)."""
     R = C + Nn
     g = torch.Generator(device="cuda").manual_seed(B + N)
     H = torch.relu(torch.randn(R * B, N, device="cuda", generator=g))
@@ -272,7 +273,9 @@ def test_rank_loss_fused_equals_two_kernel_path(B, C, Nn, N, norm, prec):
     a = ops.rank_loss_forward(H, cfg)
     dZ_a, op_a, db_a = ops.rank_loss_backward(H, cfg, a["stats"], 0.7, True, 10.0, prec=prec)
     b, dZ_b, op_b, db_b = ops.rank_loss_fused(H, cfg, 0.7, True, 10.0, prec=prec)
-    for k in ("stats", "target_score", "neg_score", "item_viol", "violations"):
+    for k in ("stats", "target_score", "neg_score"):
+        assert rel(b[k], a[k]) < 1e-6, k
+    for k in ("item_viol", "violations"):
         assert torch.equal(a[k], b[k]), k
     assert rel(b["item_loss"], a["item_loss"]) < 1e-6 and rel(b["loss"], a["loss"]) < 1e-6
     assert rel(dZ_b, dZ_a) < 1e-6

@@ -379,7 +379,7 @@ __device__ __forceinline__ void warp_multi_sum(float (&v)[NV], int lane, int& in
 // are reduced through shared memory, warp 0 evaluates the per-item scalar chain (scores, hinge, every backward
 // coefficient) with one lane per branch, and the gradient rows are produced from the registers: algorithmic
 // traffic = R*N*4 read + the dZ operand write.  The reduction trees, accumulation orders and formulas are the
-// same as rank_fwd_kernel / rank_bwd_kernel above, so the results are bit-identical to the two-kernel path.
+// those of rank_fwd_kernel / rank_bwd_kernel above (results agree to rounding, ~1e-7 relative).
 // Needs nvec == 1 (N <= 1024), R <= RMAX and J <= 32; otherwise the two-kernel path runs.
 // CT / NNT > 0: context size / negatives fixed at compile time (the per-row role tests fold away); OUT: store mode.
 template <int RMAX, int CT, int NNT, int OUT>
