@@ -23,7 +23,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-CFG = dict(C=5, Nn=10, K=4096, N=512, B=4096, V=2048, S=32, P=5000, swap=50, max_same=6)
+CFG = dict(C=5, Nn=10, K=4096, N=512, B=4096, V=8192, S=32, P=5000, swap=50, max_same=6)
 CPU_SAMPLE_B = 256          # bounded CPU sample: items per oracle step (same K, N, C, Nn)
 METRIC = "training triplets/sec"
 CPU_NOTE = {

@@ -15,7 +15,7 @@ ap.add_argument("--N", type=int, default=512)
 a = ap.parse_args()
 torch.cuda.set_device(0)
 B, C, Nn, K, N = a.B, a.C, a.Nn, 4096, a.N
-V, S = 2048, 32
+V, S = 8192, 32
 bank = ops.fill_bank(V * S, K, 1234)
 vid, off, sid = ops.synthetic_videos(V, S)
 smp = ops.Sampler(vid, off, sid, B, C, Nn, 5000, 50, 6, 100, rand_seed=1)

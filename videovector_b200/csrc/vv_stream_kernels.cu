@@ -24,27 +24,56 @@ inline int stream_grid(long long work_items, int threads) {
 // ----------------------------------------------------------------------------
 struct GatherOut { float* X; float* hi; float* lo; uint16_t* bf; float* blob; int prec; };
 
+constexpr int kGatherUnroll = 4;   // 128-bit loads in flight per thread before the first store
+
+__device__ __forceinline__ void gather_store(const GatherOut& o, size_t total, size_t off, size_t blob_off, const float4& v) {
+  if (o.X) stg_stream(reinterpret_cast<float4*>(o.X + off), v);
+  if (o.blob) stg_stream(reinterpret_cast<float4*>(o.blob + blob_off), v);
+  if (o.prec == VV_PREC_TF32X3) {
+    store_x3(o.hi, o.lo, total, off, v);
+  } else if (o.prec == VV_PREC_BF16) {
+    *reinterpret_cast<uint2*>(o.bf + off) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  }
+}
+
 __global__ void __launch_bounds__(256)
 gather_rows_kernel(const float* __restrict__ bank, const int* __restrict__ idx, const int* __restrict__ quirk,
                    int B, int R, int K, const GatherOut o) {
   const int K4 = K >> 2;
   const long long M = (long long)B * R;
-  for (long long orow = blockIdx.x; orow < M; orow += gridDim.x) {
+  const int T = blockDim.x;
+  // the row index of the NEXT row is fetched while this row streams (it heads a dependent chain of two DRAM trips)
+  long long orow = blockIdx.x;
+  int slot = 0; long long src = 0; int qk = -2;
+  if (orow < M) {
     const int j = int(orow / B), b = int(orow - (long long)j * B);
-    const int slot = b * R + j;
-    const long long src = idx[slot];
-    const int qk = quirk ? quirk[slot] : -2;
+    slot = b * R + j; src = idx[slot]; qk = quirk ? quirk[slot] : -2;
+  }
+  for (; orow < M; orow += gridDim.x) {
+    const int cur_slot = slot; const int cur_qk = qk;
     const float4* s4 = reinterpret_cast<const float4*>(bank + src * K);
-    for (int c = threadIdx.x; c < K4; c += blockDim.x) {
-      float4 v = ldg_stream(s4 + c);
-      if (c == K4 - 1 && qk != -2) v.w = (qk >= 0) ? bank[(long long)qk * K + (K - 1)] : 0.f;
-      const size_t off = size_t(orow) * K + size_t(c) * 4;
-      if (o.X) stg_stream(reinterpret_cast<float4*>(o.X + off), v);
-      if (o.blob) stg_stream(reinterpret_cast<float4*>(o.blob + (size_t(slot) * K + size_t(c) * 4)), v);
-      if (o.prec == VV_PREC_TF32X3) {
-        store_x3(o.hi, o.lo, size_t(M) * K, off, v);
-      } else if (o.prec == VV_PREC_BF16) {
-        *reinterpret_cast<uint2*>(o.bf + off) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    const long long nrow = orow + gridDim.x;
+    if (nrow < M) {
+      const int j = int(nrow / B), b = int(nrow - (long long)j * B);
+      slot = b * R + j; src = idx[slot]; qk = quirk ? quirk[slot] : -2;
+    }
+    // the K-1 copy quirk touches one element of the row: fetch its replacement once, up front
+    float last = 0.f;
+    if (cur_qk >= 0 && threadIdx.x == ((K4 - 1) % T)) last = bank[(long long)cur_qk * K + (K - 1)];
+    for (int c0 = 0; c0 < K4; c0 += T * kGatherUnroll) {
+      float4 v[kGatherUnroll];
+#pragma unroll
+      for (int u = 0; u < kGatherUnroll; ++u) {           // all loads of the batch are issued before any store
+        const int c = c0 + u * T + threadIdx.x;
+        if (c < K4) v[u] = ldg_stream(s4 + c);
+      }
+#pragma unroll
+      for (int u = 0; u < kGatherUnroll; ++u) {
+        const int c = c0 + u * T + threadIdx.x;
+        if (c < K4) {
+          if (c == K4 - 1 && cur_qk != -2) v[u].w = last;
+          gather_store(o, size_t(M) * K, size_t(orow) * K + size_t(c) * 4, size_t(cur_slot) * K + size_t(c) * 4, v[u]);
+        }
       }
     }
   }
