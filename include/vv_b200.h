@@ -52,12 +52,18 @@ enum {
  *               pipe, the cross terms bf16(x)*bf16(lo) on the bf16 pipe, fp32 accumulate in TMEM with
  *               periodic promotion to fp32 registers -> fp32-level accuracy (the 1e-5 parity mode)
  *   TF32      : tcgen05 kind::tf32, 1 MMA per product (1e-2 loss-curve mode)
- *   BF16      : tcgen05 kind::f16 with bf16 operands, fp32 accumulate (1e-2 mode) */
+ *   BF16      : tcgen05 kind::f16 with bf16 operands, fp32 accumulate (1e-2 mode)
+ *   F16X3     : split operands s*x = h0 + h1 in fp16 (22 significant bits) under a per-tensor power-of-two
+ *               scale s, three fp16 products h1*h0' + h0*h1' + h0*h0' on the full-rate f16 pipe, the same
+ *               chunked fp32 promotion as TF32X3 -> fp32-level accuracy at 3 MMA units and 4 bytes/element
+ *               (TF32X3: 4 units, 8 bytes/element).  The scale follows the tensor's largest magnitude
+ *               (vv_operand_rescale); conversions saturate instead of overflowing. */
 enum vv_precision {
   VV_PREC_FP32_SIMT = 0,
   VV_PREC_TF32X3 = 1,
   VV_PREC_TF32 = 2,
-  VV_PREC_BF16 = 3
+  VV_PREC_BF16 = 3,
+  VV_PREC_F16X3 = 4
 };
 
 /* A GEMM operand as the kernels read it.
@@ -65,8 +71,14 @@ enum vv_precision {
  *   TF32X3           : hi = round-to-nearest tf32 part (fp32 array, `count` elements); lo = an array of
  *                      the same byte size holding two bf16 planes of `count` elements: bf16(x), bf16(x - hi)
  *   BF16             : hi = bf16 array (uint16 storage), lo = NULL
+ *   F16X3            : hi = fp16 plane h0, lo = fp16 plane h1 (`count` elements each), and the
+ *                      VV_F16X3_HEADER_BYTES bytes immediately BEFORE hi are the operand's header
+ *                      {float scale, float 1/scale, uint32 bits of max|x| seen by the last producer, pad}:
+ *                      allocate header + planes as one block (vv_operand_bytes), zero the header or call
+ *                      vv_operand_set_scale once, and call vv_operand_rescale before each re-production.
  * vv_prepare_operand() produces these from an fp32 array; the producer kernels
  * (gather, rank-loss backward, sgd update) can emit them directly. */
+#define VV_F16X3_HEADER_BYTES 128
 typedef struct vv_operand {
   const void* hi;
   const void* lo;
@@ -108,9 +120,22 @@ int vv_gather_rows(const float* bank, int64_t bank_rows, int K,
                    float* X, void* Xop_hi, void* Xop_lo, int prec,
                    float* Xblob, vv_stream_t stream);
 
-/* fp32 array -> operand copies for `prec` (no-op for FP32_SIMT/TF32). */
+/* fp32 array -> operand copies for `prec` (no-op for FP32_SIMT/TF32).  F16X3: measures max|src| first and
+ * sets the header's scale from it. */
 int vv_prepare_operand(const float* src, int64_t count, int prec,
                        void* hi, void* lo, vv_stream_t stream);
+/* Bytes of one operand allocation for `count` elements and the offsets of hi / lo inside it (lo_offset = 0
+ * when the format has no lo array; FP32_SIMT / TF32 read the fp32 array itself: returns 0). */
+size_t vv_operand_bytes(int64_t count, int prec, size_t* hi_offset, size_t* lo_offset);
+/* F16X3 header maintenance (no-ops for the other precisions).
+ *  set_scale : scale = 2^log2_scale, forget the recorded maximum
+ *  rescale   : scale = 2^(target_log2 - exponent of the recorded max|x|) when a maximum was recorded (else
+ *              unchanged; 1 if never set), then forget the maximum.  target_log2 = 10 leaves a factor 64 of
+ *              growth before fp16 saturates.
+ *  measure   : record max|src| (use before rescale to initialise from data, e.g. the feature bank) */
+int vv_operand_set_scale(void* hi, int prec, int log2_scale, vv_stream_t stream);
+int vv_operand_rescale(void* hi, int prec, int target_log2, vv_stream_t stream);
+int vv_operand_measure(void* hi, int prec, const float* src, int64_t count, vv_stream_t stream);
 
 /* ------------------------------------------------------------------------- */
 /* K1: InnerProduct (fc7).  ref: inner_product_layer.cu:12-25 forward,          */

@@ -43,7 +43,7 @@ def problem():
     return W0, b0, mask, torch.as_tensor(mask.astype(np.int32)).cuda()
 
 
-@pytest.mark.parametrize("prec,tol", [("fp32_simt", 1e-5), ("tf32x3", 1e-5)])
+@pytest.mark.parametrize("prec,tol", [("fp32_simt", 1e-5), ("tf32x3", 1e-5), ("f16x3", 1e-5)])
 def test_layer_by_layer_net_matches_oracle(oracle, prec, tol):
     W0, b0, mask, mask_dev = problem()
     net = make_net(prec, False, W0, b0, mask_dev)
@@ -72,7 +72,7 @@ def test_layer_by_layer_net_matches_oracle(oracle, prec, tol):
     net.close()
 
 
-@pytest.mark.parametrize("prec,tol", [("tf32x3", 1e-5), ("bf16", 5e-2)])
+@pytest.mark.parametrize("prec,tol", [("tf32x3", 1e-5), ("f16x3", 1e-5), ("bf16", 5e-2)])
 def test_fused_net_matches_layer_by_layer_and_oracle(oracle, prec, tol):
     W0, b0, mask, mask_dev = problem()
     B, C, Nn, K, N = CFG["B"], CFG["C"], CFG["Nn"], CFG["K"], CFG["N"]

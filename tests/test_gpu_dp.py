@@ -12,7 +12,7 @@ from conftest import ROOT
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("prec", ["tf32x3"])
+@pytest.mark.parametrize("prec", ["tf32x3", "f16x3"])
 def test_two_rank_nccl_matches_single_rank(prec):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")

@@ -19,7 +19,7 @@ def rel(a, b):
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
 
 
-@pytest.mark.parametrize("prec,tol", [("fp32_simt", 1e-5), ("tf32x3", 1e-5)])
+@pytest.mark.parametrize("prec,tol", [("fp32_simt", 1e-5), ("tf32x3", 1e-5), ("f16x3", 1e-5)])
 @pytest.mark.parametrize("path", NETS, ids=[os.path.basename(p)[:-4] for p in NETS])
 def test_fused_step_reproduces_reference(path, prec, tol):
     g = np.load(path)
@@ -53,7 +53,7 @@ def test_layer_kernels_reproduce_reference(vvlib):
     assert rel(y, g["norm_y"]) < 1e-6
     check(vvlib.vv_l2norm_backward(_ptr(x), _ptr(dy), x.shape[0], x.shape[1], _ptr(y), _stream()))
     assert rel(y, g["norm_dx"]) < 1e-5
-    for prec, tol in (("fp32_simt", 1e-6), ("tf32x3", 1e-5)):
+    for prec, tol in (("fp32_simt", 1e-6), ("tf32x3", 1e-5), ("f16x3", 1e-5)):
         X = torch.as_tensor(np.pad(g["ip_X"], ((0, 0), (0, 4)))).cuda().contiguous()     # K 60 -> 64 (tensor-core path needs K % 8)
         W = torch.as_tensor(np.pad(g["ip_W"], ((0, 6), (0, 4)))).cuda().contiguous()     # N 10 -> 16
         b = torch.as_tensor(np.pad(g["ip_b"], (0, 6))).cuda()

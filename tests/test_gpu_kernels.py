@@ -12,8 +12,8 @@ from videovector_b200._lib import DROPOUT_MASK01, DROPOUT_MASK_U32, DROPOUT_NONE
 
 pytestmark = pytest.mark.gpu
 
-TOL = {"fp32_simt": 1e-5, "tf32x3": 1e-5, "tf32": 4e-3, "bf16": 2e-2}
-TC = ["tf32x3", "tf32", "bf16"]
+TOL = {"fp32_simt": 1e-5, "tf32x3": 1e-5, "f16x3": 1e-5, "tf32": 4e-3, "bf16": 2e-2}
+TC = ["tf32x3", "f16x3", "tf32", "bf16"]
 ALL = ["fp32_simt"] + TC
 
 
@@ -34,6 +34,21 @@ def check_x3_operand(op, x):
     assert torch.equal(planes[:n], x.reshape(-1).to(torch.bfloat16))
     assert torch.equal(planes[n:], (x - op.hi).reshape(-1).to(torch.bfloat16))
     assert rel(op.hi.double().reshape(-1) + planes[n:].double(), x.reshape(-1)) < 2 ** -19
+
+
+def check_f16x3_operand(op, x):
+    """F16X3 operand: fp16 planes h0 = fp16(s*x), h1 = fp16(s*x - h0) under the header's power-of-two scale s; the
+    producer records max|x|; h0 + h1 carries ~22 significant bits (less only for elements far below the maximum)."""
+    s = op.scale
+    assert s > 0 and np.log2(s) == int(np.log2(s))
+    assert op.absmax == float(x.abs().max().item())
+    xs = x.double() * s
+    assert float(xs.abs().max()) < 65504                                    # nothing saturates
+    assert torch.equal(op.hi, (x * s).to(torch.float16))
+    assert torch.equal(op.lo, (x * s - op.hi.float()).to(torch.float16))
+    err = (op.hi.double() + op.lo.double() - xs).abs()
+    # 22 significant bits, down to an absolute floor where h1 turns subnormal (2^-25 in scaled units)
+    assert bool((err <= torch.clamp(xs.abs() * 2.0 ** -21.9, min=2.0 ** -25)).all())
 
 
 def cuda(a, dtype=None):
@@ -79,6 +94,11 @@ def test_gather_rows_bit_exact(oracle, prec):
             assert torch.equal(op.hi, X.to(torch.bfloat16))
         if prec == "tf32x3":
             check_x3_operand(op, X)
+        if prec == "f16x3":
+            assert op.absmax == float(X.abs().max().item())     # recorded by the gather; the scale came from max|bank|
+            s = op.scale
+            assert float(bank.abs().max()) * s < 65504 and torch.equal(op.hi, (X * s).to(torch.float16))
+            assert torch.equal(op.lo, (X * s - op.hi.float()).to(torch.float16))
     psmp.close()
 
 
@@ -259,7 +279,7 @@ def test_rank_loss_forward_backward(B, C, Nn, N, norm):
 
 @pytest.mark.parametrize("B,C,Nn,N,norm", [(64, 5, 10, 512, 2), (33, 3, 4, 64, 1), (7, 5, 10, 1000, 2), (300, 7, 20, 256, 2),
                                             (1, 5, 10, 512, 2)])
-@pytest.mark.parametrize("prec", ["fp32_simt", "tf32x3", "bf16"])
+@pytest.mark.parametrize("prec", ["fp32_simt", "tf32x3", "f16x3", "bf16"])
 def test_rank_loss_fused_equals_two_kernel_path(B, C, Nn, N, norm, prec):
     """K2+K3 fused (rows in registers) against the forward + backward kernels: same formulas, reductions equal up to
     FMA contraction / summation order (1e-6)."""
@@ -292,7 +312,7 @@ def test_rank_loss_fused_unsupported_shapes():
     assert not ops.rank_loss_fused_supported(ops.rank_cfg(8, 5, 10, 2048))    # N > 1024
 
 
-@pytest.mark.parametrize("prec", ["tf32x3", "bf16"])
+@pytest.mark.parametrize("prec", ["tf32x3", "f16x3", "bf16"])
 def test_rank_loss_backward_operand_copies(prec):
     B, C, Nn, N = 32, 5, 10, 512
     H = torch.relu(torch.randn((C + Nn) * B, N, device="cuda")).contiguous()
@@ -301,6 +321,8 @@ def test_rank_loss_backward_operand_copies(prec):
     dZ, op, _ = ops.rank_loss_backward(H, cfg, out["stats"], 1.0, True, 10.0, prec=prec)
     if prec == "bf16":
         assert torch.equal(op.hi, dZ.to(torch.bfloat16))
+    elif prec == "f16x3":
+        check_f16x3_operand(op, dZ)
     else:
         check_x3_operand(op, dZ)
 
@@ -322,18 +344,42 @@ def test_sgd_update_matches_oracle(oracle, reg_type, count):
     assert rel(Wd, Wr) < 1e-6 and rel(hd, hr) < 1e-6 and rel(diff, dr) < 1e-6
 
 
-@pytest.mark.parametrize("prec", ["tf32x3", "bf16"])
+@pytest.mark.parametrize("prec", ["tf32x3", "f16x3", "bf16"])
 def test_sgd_update_refreshes_operand_copies(prec):
     count = 64 * 128
     W = torch.randn(count, device="cuda") * 0.01
     g = torch.randn(count, device="cuda")
     h = torch.zeros(count, device="cuda")
-    Wop = ops.alloc_operand((count,), prec)
+    Wop = ops.prepare_operand(W, prec)                 # f16x3: also records max|W|, from which the update rescales
     ops.sgd_update(W, g, h, 1e-2, 0.9, 0.0, prec=prec, Wop=Wop)
     if prec == "bf16":
         assert torch.equal(Wop.hi, W.to(torch.bfloat16))
+    elif prec == "f16x3":
+        check_f16x3_operand(Wop, W)
     else:
         check_x3_operand(Wop, W)
+
+
+def test_f16x3_operand_scale_tracks_and_saturates():
+    """The header protocol: prepare measures, rescale maps max|x| to ~2^target, a stale scale saturates instead of
+    overflowing, and the next rescale recovers."""
+    x = torch.randn(4096, device="cuda") * 3e-4
+    op = ops.prepare_operand(x, "f16x3")
+    check_f16x3_operand(op, x)
+    assert 2 ** 9 <= float(x.abs().max()) * op.scale < 2 ** 10
+    # the tensor grows 1000x under the old scale: conversions clamp to +-65504 (no inf), the maximum is recorded
+    big = x * 1000.0
+    W = big.clone(); h = torch.zeros_like(W); g = torch.zeros_like(W)
+    s_old = op.scale
+    from videovector_b200._lib import check
+    check(ops._lib.load().vv_sgd_update(ops._ptr(W), ops._ptr(g), 1, W.numel(), ops._ptr(h), None, W.numel(), 0.0, 0.0, 0.0, 2, 1.0,
+                                        ops._ptr(op.hi), ops._ptr(op.lo), ops.PREC["f16x3"], ops._stream()))
+    assert op.scale == s_old and bool(torch.isfinite(op.hi.float()).all()) and float(op.hi.float().abs().max()) == 65504.0
+    assert op.absmax == float(big.abs().max().item())
+    ops.operand_rescale(op, "f16x3")
+    check(ops._lib.load().vv_sgd_update(ops._ptr(W), ops._ptr(g), 1, W.numel(), ops._ptr(h), None, W.numel(), 0.0, 0.0, 0.0, 2, 1.0,
+                                        ops._ptr(op.hi), ops._ptr(op.lo), ops.PREC["f16x3"], ops._stream()))
+    check_f16x3_operand(op, big)
 
 
 # ------------------------------------------------------------------------------------------------

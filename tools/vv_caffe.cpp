@@ -2,7 +2,7 @@
 // :194-266 time) on the caffe_compat host.  Usage:
 //   vv_caffe train --solver=solver.prototxt [--gpu=0] [--iterations=N]
 //   vv_caffe time  --model=net.prototxt [--iterations=50] [--gpu=0]
-// Environment: VV_PRECISION=tf32x3|tf32|bf16|fp32_simt, VV_FUSE=0 to run layer by layer.
+// Environment: VV_PRECISION=tf32x3|f16x3|tf32|bf16|fp32_simt, VV_FUSE=0 to run layer by layer.
 #include <chrono>
 #include <cstdio>
 #include <cstring>

@@ -10,7 +10,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libvv_b200.so")
 
 VV_MAX_CONTEXT = 64
-PREC = {"fp32_simt": 0, "tf32x3": 1, "tf32": 2, "bf16": 3}
+PREC = {"fp32_simt": 0, "tf32x3": 1, "tf32": 2, "bf16": 3, "f16x3": 4}
+F16X3_HEADER_BYTES = 128
 DROPOUT_NONE, DROPOUT_MASK01, DROPOUT_MASK_U32, DROPOUT_PHILOX = 0, 1, 2, 3
 
 
@@ -57,6 +58,10 @@ SIGNATURES = {
     "vv_device_check": (_i, []),
     "vv_gather_rows": (_i, [_P, _i64, _i, _P, _P, _i, _i, _P, _P, _P, _i, _P, _P]),
     "vv_prepare_operand": (_i, [_P, _i64, _i, _P, _P, _P]),
+    "vv_operand_bytes": (C.c_size_t, [_i64, _i, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "vv_operand_set_scale": (_i, [_P, _i, _i, _P]),
+    "vv_operand_rescale": (_i, [_P, _i, _i, _P]),
+    "vv_operand_measure": (_i, [_P, _i, _P, _i64, _P]),
     "vv_ip_forward": (_i, [Operand, Operand, _P, _i, _i, _i, _i, C.POINTER(Act), _P, _P, _P]),
     "vv_ip_wgrad": (_i, [Operand, Operand, _i, _i, _i, _i, _f, _P, _i, _P, _sz, _P]),
     "vv_ip_wgrad_workspace_bytes": (_sz, [_i, _i, _i, _i]),

@@ -7,12 +7,13 @@ namespace caffe {
 
 #define CUDA_CHECK(call) do { cudaError_t _e = (call); CHECK_EQ(int(_e), 0) << cudaGetErrorString(_e); } while (0)
 
-Caffe::Caffe() : mode_(GPU), phase_(TRAIN), stream_(nullptr), seed_(1701), draws_(0), prec_(VV_PREC_TF32X3) {
+Caffe::Caffe() : mode_(GPU), phase_(TRAIN), stream_(nullptr), seed_(1701), draws_(0), prec_(VV_PREC_F16X3) {
   if (const char* e = getenv("VV_PRECISION")) {
     const string v(e);
     if (v == "fp32_simt") prec_ = VV_PREC_FP32_SIMT; else if (v == "tf32x3") prec_ = VV_PREC_TF32X3;
     else if (v == "tf32") prec_ = VV_PREC_TF32; else if (v == "bf16") prec_ = VV_PREC_BF16;
-    else LOG_FATAL << "VV_PRECISION must be fp32_simt|tf32x3|tf32|bf16, got " << v;
+    else if (v == "f16x3") prec_ = VV_PREC_F16X3;
+    else LOG_FATAL << "VV_PRECISION must be fp32_simt|tf32x3|f16x3|tf32|bf16, got " << v;
   }
 }
 Caffe& Caffe::Get() { static Caffe c; return c; }

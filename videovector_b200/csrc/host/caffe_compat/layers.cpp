@@ -75,6 +75,13 @@ vv_operand_t InnerProductLayer<Dtype>::Operand(const Dtype* src, int64_t count, 
     void* h = hi->get(count * 2);
     VV_CHECK(vv_prepare_operand(src, count, prec, h, nullptr, Caffe::stream()));
     o.hi = h;
+  } else if (prec == VV_PREC_F16X3) {
+    // one block: header + two fp16 planes; prepare_operand measures max|src| and sets the scale
+    size_t ho = 0, lo_off = 0;
+    const size_t bytes = vv_operand_bytes(count, prec, &ho, &lo_off);
+    char* base = static_cast<char*>(hi->get(bytes));
+    VV_CHECK(vv_prepare_operand(src, count, prec, base + ho, base + lo_off, Caffe::stream()));
+    o.hi = base + ho; o.lo = base + lo_off;
   }
   return o;
 }

@@ -49,16 +49,30 @@ constexpr int kNcclFloat = 7, kNcclSum = 0;
 
 struct DevBuf {
   void* p = nullptr; size_t bytes = 0;
+  void* base = nullptr;                // the allocation (p may point inside it); NULL = p is not owned
   int alloc(size_t n) {
     bytes = n;
     if (n == 0) return VV_OK;
-    VV_CUDA(cudaMalloc(&p, n));
-    VV_CUDA(cudaMemset(p, 0, n));      // zero-fill on first touch like SyncedMemory (syncedmem.cpp:24-25)
+    VV_CUDA(cudaMalloc(&base, n));
+    VV_CUDA(cudaMemset(base, 0, n));   // zero-fill on first touch like SyncedMemory (syncedmem.cpp:24-25)
+    p = base;
     return VV_OK;
   }
-  void release() { if (p) cudaFree(p); p = nullptr; }
+  void release() { if (base) cudaFree(base); base = nullptr; p = nullptr; }
   template <class T> T* as() const { return static_cast<T*>(p); }
 };
+// operand copies of `count` elements in the layout of `prec` (vv_operand_bytes): hi owns the block, lo points into it
+int alloc_operand(DevBuf& hi, DevBuf& lo, size_t count, int prec) {
+  size_t ho = 0, lo_off = 0;
+  const size_t bytes = vv_operand_bytes(int64_t(count), prec, &ho, &lo_off);
+  if (bytes == 0) return VV_OK;
+  hi.release(); lo.release();
+  int rc = hi.alloc(bytes);
+  if (rc) return rc;
+  hi.p = static_cast<char*>(hi.base) + ho;
+  if (lo_off) { lo.p = static_cast<char*>(hi.base) + lo_off; lo.base = nullptr; }
+  return VV_OK;
+}
 
 }  // namespace
 
@@ -76,6 +90,8 @@ struct vv_trainer {
   // gather-fused path: operand copies of the registered bank, per-step gather plan, quirk corrections
   DevBuf bank_hi, bank_lo, rowmap, delta, wlast, dq;
   const float* bank_reg = nullptr; int64_t bank_reg_rows = 0;
+  // F16X3: the X scale is fixed from max|bank| (gathered rows are a subset), the dZ scale trails the previous step
+  const float* scaled_bank = nullptr; int64_t scaled_bank_rows = 0; bool dz_scale_ready = false;
   bool x_allocated = false;
   ncclComm_t comm = nullptr;
   int last_launches = 0;
@@ -96,7 +112,7 @@ struct vv_trainer {
   vv_operand_t opdZ() const { return op(dZf, dZ_hi, dZ_lo); }
   vv_operand_t op(const DevBuf& f, const DevBuf& hi, const DevBuf& lo) const {
     vv_operand_t o;
-    if (cfg.prec == VV_PREC_TF32X3) { o.hi = hi.p; o.lo = lo.p; }
+    if (cfg.prec == VV_PREC_TF32X3 || cfg.prec == VV_PREC_F16X3) { o.hi = hi.p; o.lo = lo.p; }
     else if (cfg.prec == VV_PREC_BF16) { o.hi = hi.p; o.lo = nullptr; }
     else { o.hi = f.p; o.lo = nullptr; }
     return o;
@@ -111,8 +127,8 @@ struct vv_trainer {
 #define A(buf, n) if ((rc = buf.alloc(n))) return rc
     A(W, NK * 4); A(b, size_t(cfg.N) * 4); A(Wh, NK * 4); A(bh, size_t(cfg.N) * 4);
     // the materialised X operand (1-2 GB at B=4096) is allocated on first use: the gather-fused path never needs it
-    if (cfg.prec == VV_PREC_TF32X3) { A(W_hi, NK * 4); A(W_lo, NK * 4); A(dZ_hi, MN * 4); A(dZ_lo, MN * 4); }
-    if (cfg.prec == VV_PREC_BF16) { A(W_hi, NK * 2); A(dZ_hi, MN * 2); }
+    if ((rc = alloc_operand(W_hi, W_lo, NK, cfg.prec))) return rc;
+    if ((rc = alloc_operand(dZ_hi, dZ_lo, MN, cfg.prec))) return rc;
     if (f32op || cfg.keep_blobs) { A(dZf, MN * 4); }
     A(wlast, size_t(cfg.N) * 4); A(dq, size_t(cfg.N) * 4);
     A(rowmap, size_t((M + 127) / 128 * 128) * 4); A(delta, size_t((M + 127) / 128 * 128) * 4);
@@ -143,8 +159,7 @@ struct vv_trainer {
     if (x_allocated) return VV_OK;
     const size_t MK = size_t(M) * cfg.K;
     int rc;
-    if (cfg.prec == VV_PREC_TF32X3) { if ((rc = X_hi.alloc(MK * 4))) return rc; if ((rc = X_lo.alloc(MK * 4))) return rc; }
-    if (cfg.prec == VV_PREC_BF16) { if ((rc = X_hi.alloc(MK * 2))) return rc; }
+    if ((rc = alloc_operand(X_hi, X_lo, MK, cfg.prec))) return rc;
     if (needs_f32_operand() || cfg.keep_blobs) { if ((rc = Xf.alloc(MK * 4))) return rc; }
     x_allocated = true;
     return VV_OK;
@@ -175,7 +190,7 @@ extern "C" vv_trainer_t* vv_trainer_create(const vv_trainer_cfg_t* cfg, vv_strea
   if (cfg->B < 1 || cfg->C < 3 || (cfg->C % 2) != 1 || cfg->Nn < 1 || cfg->K < 4 || cfg->N < 4 || (cfg->K % 4) || (cfg->N % 4)) {
     set_error("bad trainer cfg: B=%d C=%d Nn=%d K=%d N=%d", cfg->B, cfg->C, cfg->Nn, cfg->K, cfg->N); return nullptr;
   }
-  if (cfg->prec < VV_PREC_FP32_SIMT || cfg->prec > VV_PREC_BF16) { set_error("bad precision %d", cfg->prec); return nullptr; }
+  if (cfg->prec < VV_PREC_FP32_SIMT || cfg->prec > VV_PREC_F16X3) { set_error("bad precision %d", cfg->prec); return nullptr; }
   if (cfg->world_size < 1 || cfg->rank < 0 || cfg->rank >= cfg->world_size) { set_error("bad rank/world_size"); return nullptr; }
   if (vv_device_check() != VV_OK) return nullptr;
   vv_trainer* t = new vv_trainer();
@@ -221,7 +236,7 @@ extern "C" int vv_trainer_set_bank(vv_trainer_t* t, const float* bank, int64_t b
   const vv_trainer_cfg_t& c = t->cfg;
   // materialised path: exact-fp32 mode, blob inspection, and tf32x3 (its gather variants are not built: gather4
   // measured slower than the K0 kernel)
-  if (c.prec == VV_PREC_FP32_SIMT || c.prec == VV_PREC_TF32X3 || c.keep_blobs) { t->bank_reg = nullptr; return VV_OK; }
+  if (c.prec == VV_PREC_FP32_SIMT || c.prec == VV_PREC_TF32X3 || c.prec == VV_PREC_F16X3 || c.keep_blobs) { t->bank_reg = nullptr; return VV_OK; }
   vv_stream_t s = reinterpret_cast<vv_stream_t>(t->stream);
   const int64_t n = bank_rows * c.K;
   int rc;
@@ -248,6 +263,13 @@ extern "C" int vv_trainer_step(vv_trainer_t* t, const float* bank, int64_t bank_
     if ((rc = vv_gather_plan(bank, K, idx, quirk, c.B, t->R, t->rowmap.as<int32_t>(), t->delta.as<float>(), s))) return rc;
   } else {
     if ((rc = t->alloc_x())) return rc;
+    if (c.prec == VV_PREC_F16X3 && (bank != t->scaled_bank || bank_rows != t->scaled_bank_rows)) {
+      // one pass over a newly seen bank fixes the scale of X for good (not counted in the per-step timing)
+      if ((rc = vv_operand_set_scale(t->X_hi.p, c.prec, 0, s))) return rc;
+      if ((rc = vv_operand_measure(t->X_hi.p, c.prec, bank, bank_rows * int64_t(K), s))) return rc;
+      if ((rc = vv_operand_rescale(t->X_hi.p, c.prec, 12, s))) return rc;
+      t->scaled_bank = bank; t->scaled_bank_rows = bank_rows;
+    }
     if ((rc = vv_gather_rows(bank, bank_rows, K, idx, quirk, c.B, t->R, t->Xf.as<float>(), t->X_hi.p, t->X_lo.p, c.prec,
                              nullptr, s))) return rc;
   }
@@ -271,31 +293,42 @@ extern "C" int vv_trainer_step(vv_trainer_t* t, const float* bank, int64_t bank_
   }
   t->toc(1);
   const float dscale = has_dropout ? dropout_scale(c.dropout_ratio) : 1.f;
-  if (vv_rank_loss_fused_supported(&t->rank) && !c.split_rank_loss) {
-    // K2 + K3 in one pass over H (+ bias gradient); timed as phase 3, phase 2 stays 0
-    t->tic(3);
-    VV_CUDA(cudaMemsetAsync(t->dbx.p, 0, size_t(N) * 4, t->stream));
-    if (fused_gather) VV_CUDA(cudaMemsetAsync(t->dq.p, 0, size_t(N) * 4, t->stream));
-    count_launch();
-    if ((rc = vv_rank_loss_fused(t->H.as<float>(), &t->rank, c.loss_weight, 1, dscale, t->stats.as<float>(), nullptr, nullptr,
-                                 t->item_loss.as<float>(), t->item_viol.as<float>(), t->loss_ptr(), t->viol_ptr(),
-                                 t->dZf.as<float>(), t->dZ_hi.p, t->dZ_lo.p, c.prec, t->dbx.as<float>(),
-                                 fused_gather ? t->delta.as<float>() : nullptr, fused_gather ? t->dq.as<float>() : nullptr, s))) return rc;
-  } else {
-    // K2
-    t->tic(2);
-    if ((rc = vv_rank_loss_forward(t->H.as<float>(), &t->rank, t->stats.as<float>(), nullptr, nullptr,
-                                   t->item_loss.as<float>(), t->item_viol.as<float>(), t->loss_ptr(), t->viol_ptr(), s))) return rc;
-    t->toc(2);
-    // K3 (+ bias gradient)
-    t->tic(3);
-    VV_CUDA(cudaMemsetAsync(t->dbx.p, 0, size_t(N) * 4, t->stream));
-    if (fused_gather) VV_CUDA(cudaMemsetAsync(t->dq.p, 0, size_t(N) * 4, t->stream));
-    count_launch();
-    if ((rc = vv_rank_loss_backward_ex(t->H.as<float>(), &t->rank, t->stats.as<float>(), c.loss_weight, 1, dscale,
-                                       t->dZf.as<float>(), t->dZ_hi.p, t->dZ_lo.p, c.prec, t->dbx.as<float>(),
-                                       fused_gather ? t->delta.as<float>() : nullptr, fused_gather ? t->dq.as<float>() : nullptr, s))) return rc;
+  auto run_rank = [&]() -> int {
+    int rc;
+    if (vv_rank_loss_fused_supported(&t->rank) && !c.split_rank_loss) {
+      // K2 + K3 in one pass over H (+ bias gradient); timed as phase 3, phase 2 stays 0
+      t->tic(3);
+      VV_CUDA(cudaMemsetAsync(t->dbx.p, 0, size_t(N) * 4, t->stream));
+      if (fused_gather) VV_CUDA(cudaMemsetAsync(t->dq.p, 0, size_t(N) * 4, t->stream));
+      count_launch();
+      if ((rc = vv_rank_loss_fused(t->H.as<float>(), &t->rank, c.loss_weight, 1, dscale, t->stats.as<float>(), nullptr, nullptr,
+                                   t->item_loss.as<float>(), t->item_viol.as<float>(), t->loss_ptr(), t->viol_ptr(),
+                                   t->dZf.as<float>(), t->dZ_hi.p, t->dZ_lo.p, c.prec, t->dbx.as<float>(),
+                                   fused_gather ? t->delta.as<float>() : nullptr, fused_gather ? t->dq.as<float>() : nullptr, s))) return rc;
+    } else {
+      // K2
+      t->tic(2);
+      if ((rc = vv_rank_loss_forward(t->H.as<float>(), &t->rank, t->stats.as<float>(), nullptr, nullptr,
+                                     t->item_loss.as<float>(), t->item_viol.as<float>(), t->loss_ptr(), t->viol_ptr(), s))) return rc;
+      t->toc(2);
+      // K3 (+ bias gradient)
+      t->tic(3);
+      VV_CUDA(cudaMemsetAsync(t->dbx.p, 0, size_t(N) * 4, t->stream));
+      if (fused_gather) VV_CUDA(cudaMemsetAsync(t->dq.p, 0, size_t(N) * 4, t->stream));
+      count_launch();
+      if ((rc = vv_rank_loss_backward_ex(t->H.as<float>(), &t->rank, t->stats.as<float>(), c.loss_weight, 1, dscale,
+                                         t->dZf.as<float>(), t->dZ_hi.p, t->dZ_lo.p, c.prec, t->dbx.as<float>(),
+                                         fused_gather ? t->delta.as<float>() : nullptr, fused_gather ? t->dq.as<float>() : nullptr, s))) return rc;
+    }
+    return VV_OK;
+  };
+  if (c.prec == VV_PREC_F16X3) {
+    // the dZ operand's scale trails the previous step's max|dZ| (x64 headroom, saturating conversion); the very
+    // first step runs the kernel once more up front just to measure
+    if (!t->dz_scale_ready) { if ((rc = run_rank())) return rc; t->dz_scale_ready = true; }
+    if ((rc = vv_operand_rescale(t->dZ_hi.p, c.prec, 10, s))) return rc;
   }
+  if ((rc = run_rank())) return rc;
   t->toc(3);
   // K1 wgrad into split-K slabs
   t->tic(4);
@@ -341,6 +374,8 @@ extern "C" int vv_trainer_step(vv_trainer_t* t, const float* bank, int64_t bank_
     // ref: solver.cpp:486-576 + net.cpp:804-839; weight then bias (net.params() order)
     const float rate = vv_learning_rate(c.lr_policy, c.base_lr, c.gamma, c.power, c.stepsize, iter);
     if (rate < 0.f) return VV_ERR_INVALID;
+    // F16X3: the new W operand copy is scaled from max|W| as the previous update (or the initial copy) recorded it
+    if ((rc = vv_operand_rescale(t->W_hi.p, c.prec, 10, s))) return rc;
     if ((rc = vv_sgd_update(t->W.as<float>(), t->dW_parts.as<float>(), nparts, NK, t->Wh.as<float>(),
                             t->dW_parts.as<float>(), NK, rate * c.lr_mult[0], c.momentum, c.weight_decay * c.decay_mult[0],
                             c.reg_type, gscale, t->W_hi.p, t->W_lo.p, c.prec, s))) return rc;
@@ -393,6 +428,7 @@ extern "C" int vv_trainer_extract(vv_trainer_t* t, const float* F, int64_t rows,
   act.relu = 1; act.dropout_mode = VV_DROPOUT_NONE;      // TEST phase: dropout is a copy (dropout_layer.cpp:46-48)
   int rc;
   if ((rc = t->alloc_x())) return rc;
+  t->scaled_bank = nullptr;             // F16X3: prepare_operand below rescales the X operand to this input
   launches_reset();
   for (int64_t r0 = 0; r0 < rows; r0 += t->M) {
     const int m = int(rows - r0 < t->M ? rows - r0 : t->M);

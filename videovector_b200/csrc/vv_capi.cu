@@ -88,7 +88,7 @@ extern "C" int vv_ip_wgrad_auto_nsplit(int M, int N, int K, int prec) {
   // tiles of 128 x 256 over the [N, K] output; split the M reduction so that the
   // persistent grid of num_sms CTAs is filled in (almost) whole waves.
   const int tiles = ((N + 127) / 128) * ((K + 255) / 256);
-  const int bk = (prec == VV_PREC_BF16) ? 64 : 32;
+  const int bk = (prec == VV_PREC_BF16 || prec == VV_PREC_F16X3) ? 64 : 32;
   const int num_kb = (M + bk - 1) / bk;
   const int sms = num_sms();
   int best = 1; double best_cost = 1e30;

@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include "vv_b200.h"
 
@@ -75,6 +76,38 @@ __device__ __forceinline__ void store_x3(float* hi, void* lo, size_t count, size
   *reinterpret_cast<uint2*>(planes + off) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
   *reinterpret_cast<uint2*>(planes + count + off) =
       make_uint2(pack_bf16x2(v.x - h.x, v.y - h.y), pack_bf16x2(v.z - h.z, v.w - h.w));
+}
+
+// The F16X3 operand: two fp16 planes h0 = fp16(s*x), h1 = fp16(s*x - h0) of a per-tensor power-of-two scale s.
+// A 128-byte header sits immediately before plane 0 (so every entry point keeps its (hi, lo) pointer pair):
+// the scale the producer uses, its inverse for the GEMM epilogue, and the largest |x| the last producer saw,
+// from which vv_operand_rescale picks the next scale.
+struct F16Hdr { float scale; float inv_scale; uint32_t absmax_bits; uint32_t reserved; };
+__host__ __device__ __forceinline__ F16Hdr* f16_hdr(const void* hi) {
+  return reinterpret_cast<F16Hdr*>(const_cast<char*>(static_cast<const char*>(hi)) - VV_F16X3_HEADER_BYTES);
+}
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));   // low half <- a
+  return r;
+}
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t u) {
+  return __half22float2(*reinterpret_cast<const __half2*>(&u));
+}
+__device__ __forceinline__ void store_f16x3(void* h0, void* h1, size_t off, const float4& v, float scale, float& amax) {
+  amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+  const float x0 = v.x * scale, x1 = v.y * scale, x2 = v.z * scale, x3 = v.w * scale;
+  const uint32_t p01 = pack_f16x2_sat(x0, x1), p23 = pack_f16x2_sat(x2, x3);
+  const float2 f01 = unpack_f16x2(p01), f23 = unpack_f16x2(p23);
+  *reinterpret_cast<uint2*>(static_cast<uint16_t*>(h0) + off) = make_uint2(p01, p23);
+  *reinterpret_cast<uint2*>(static_cast<uint16_t*>(h1) + off) =
+      make_uint2(pack_f16x2_sat(x0 - f01.x, x1 - f01.y), pack_f16x2_sat(x2 - f23.x, x3 - f23.y));
+}
+// one atomicMax per warp of the largest |x| a producer wrote (positive floats order like their bit patterns)
+__device__ __forceinline__ void f16_publish_absmax(const void* hi, float amax) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  if ((threadIdx.x & 31) == 0 && amax > 0.f) atomicMax(&f16_hdr(hi)->absmax_bits, __float_as_uint(amax));
 }
 
 // ----------------------------------------------------------------------------
@@ -321,6 +354,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 // Instruction descriptor (kind::f16 / kind::tf32), fp32 accumulate.
 //  c_format [4,6)=1 (F32) | a_format [7,10) | b_format [10,13) | a_major 15 | b_major 16 |
 //  N>>3 [17,23) | M>>4 [24,29).   format: 1 = BF16, 2 = TF32.  major: 0 = K, 1 = MN.
+// fmt: 0 = F16, 1 = BF16 (kind::f16); 2 = TF32 (kind::tf32)
 __host__ __device__ constexpr uint32_t make_idesc(int fmt, int a_mn_major, int b_mn_major, int M, int N) {
   return (1u << 4) | (uint32_t(fmt) << 7) | (uint32_t(fmt) << 10) | (uint32_t(a_mn_major) << 15) |
          (uint32_t(b_mn_major) << 16) | (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);

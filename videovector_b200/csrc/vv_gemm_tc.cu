@@ -15,7 +15,9 @@
 //   DGRAD D[M,K] = dZ W       A = dZ [M,N] K-major      B = W [N,K] MN-major   (reduce N)
 // Precisions: bf16 (kind::f16), tf32 (kind::tf32), and tf32x3 = split operands x = hi + lo with three products
 // per element pair: hi*hi on the tf32 pipe and the two cross terms bf16(x)*bf16(lo) on the (2x faster) bf16
-// pipe, all accumulated in the same fp32 TMEM tile -> fp32-level accuracy at 4 instead of 6 MMA units.
+// pipe, all accumulated in the same fp32 TMEM tile -> fp32-level accuracy at 4 instead of 6 MMA units;
+// and f16x3 = scaled operands s*x = h0 + h1 in fp16 with the three products h1*h0' + h0*h1' + h0*h0' on the f16
+// pipe (3 MMA units, 4 bytes per element), unscaled by 1/(s s') in the epilogue.
 #include <cuda.h>
 #include "vv_gemm.cuh"
 
@@ -35,11 +37,15 @@ struct TcParams {
   float* D; long long slab_stride;
   int act_N;                    // row pitch of mask/Z (= N of the layer) for the FWD epilogue
   const int* rowmap;            // gather variants: bank row of every X row (padded to a multiple of 128)
+  const float* inv_sa; const float* inv_sb;   // f16x3: 1/scale of the two operands (device, from their headers)
   GemmEpilogue epi;
 };
 
-template <bool kTF32, bool kAMN, bool kBMN, int kNProd, int kBlockN, int kStages, bool kFwdEpi, bool kGather = false>
+template <bool kTF32, bool kAMN, bool kBMN, int kNProd, int kBlockN, int kStages, bool kFwdEpi, bool kGather = false,
+          bool kF16 = false>
 struct Cfg {
+  static constexpr bool f16 = kF16;                    // fp16 elements (kind::f16 with F16 formats) instead of bf16
+  static_assert(!(kF16 && kTF32), "f16 and tf32 exclude each other");
   // kGather: the X operand (A when K-major = FWD, B when MN-major = WGRAD) is gathered row-wise from the bank
   static constexpr bool gather = kGather;
   static constexpr bool gather_a = kGather && !kAMN;   // FWD : A rows = X rows
@@ -50,7 +56,8 @@ struct Cfg {
   static constexpr bool tf32 = kTF32;
   static constexpr bool a_mn = kAMN, b_mn = kBMN;
   static constexpr int nprod = kNProd;                 // 1 or 3
-  static constexpr bool mixed = (kNProd == 3);          // tf32 hi*hi + bf16 cross terms
+  static constexpr bool mixed = (kNProd == 3) && !kF16; // tf32 hi*hi + bf16 cross terms
+  static constexpr bool split16 = (kNProd == 3) && kF16; // fp16 h0*h0' + the two fp16 cross terms
   static constexpr bool promote = (kNProd == 3);        // chunked TMEM accumulation + fp32 register sums
   static constexpr int block_n = kBlockN;
   static constexpr int stages = kStages;
@@ -65,7 +72,8 @@ struct Cfg {
   // mixed mode: two extra bf16 tiles per operand (bf16(x) and bf16(lo)) covering the same bk = 32 reduction
   // elements: K-major = rows of 64 B (SWIZZLE_64B); MN-major = 64-element chunks of [32 k-rows x 128 B] (SWIZZLE_128B)
   static constexpr int a_half = a_bytes / 2, b_half = b_bytes / 2;
-  static constexpr int stage_bytes = mixed ? 2 * (a_bytes + b_bytes) : (a_bytes + b_bytes);
+  // split16: a second full-size tile per operand (the h1 plane), stage = [A_h0][A_h1][B_h0][B_h1]
+  static constexpr int stage_bytes = (mixed || split16) ? 2 * (a_bytes + b_bytes) : (a_bytes + b_bytes);
   static constexpr int tmem_cols = 2 * kBlockN;
   static constexpr int smem_bytes = stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
   static_assert(tmem_cols == 256 || tmem_cols == 512, "TMEM allocation must be a power of two");
@@ -93,6 +101,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmB_hi);
     if (C::mixed) { tma_prefetch_desc(&tmA_hb); tma_prefetch_desc(&tmA_lb); tma_prefetch_desc(&tmB_hb); tma_prefetch_desc(&tmB_lb); }
+    if (C::split16) { tma_prefetch_desc(&tmA_hb); tma_prefetch_desc(&tmB_hb); }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], C::cluster); }
@@ -136,7 +145,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           if (C::gather) __syncwarp();
           // stage layout: [A_hi][A_hb][A_lb][B_hi][B_hb][B_lb]  (the bf16 tiles only in mixed mode)
           uint8_t* sa = smem + stage * C::stage_bytes;
-          uint8_t* sb = sa + (C::mixed ? 2 * C::a_bytes : C::a_bytes);
+          uint8_t* sb = sa + ((C::mixed || C::split16) ? 2 * C::a_bytes : C::a_bytes);
           const int k0 = kb * C::bk;
           if (C::gather_a) {
             // A tile [128 rows x 128 B]: lane l fills rows 4l..4l+3 (512 B, inside one swizzle atom)
@@ -180,6 +189,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 tma_load_2d(sb + c * (C::bk * kRowBytes), &tmB_hi, &full_bar[stage], n0 + c * C::chunk, k0);
             }
           }
+          if (C::split16 && lane == 0) {
+            // the h1 planes: same boxes as the h0 tiles, through the second pair of tensor maps
+            uint8_t* da = sa + C::a_bytes;
+            uint8_t* db = sb + C::b_bytes;
+            if (!C::a_mn) {
+              tma_load_2d(da, &tmA_hb, &full_bar[stage], k0, m0);
+            } else {
+#pragma unroll
+              for (int c = 0; c < kBlockM / C::chunk; ++c)
+                tma_load_2d(da + c * (C::bk * kRowBytes), &tmA_hb, &full_bar[stage], m0 + c * C::chunk, k0);
+            }
+            if (C::cluster > 1) {
+              if (!C::b_mn) {
+                tma_load_2d_mc(db + cta_rank * (C::b_bytes / 2), &tmB_hb, &full_bar[stage], k0, n0 + cta_rank * (C::block_n / 2), 0x3);
+              } else {
+                constexpr int kHalf = C::block_n / C::chunk / 2;
+#pragma unroll
+                for (int c = 0; c < kHalf; ++c)
+                  tma_load_2d_mc(db + (cta_rank * kHalf + c) * (C::bk * kRowBytes), &tmB_hb, &full_bar[stage],
+                                 n0 + (cta_rank * kHalf + c) * C::chunk, k0, 0x3);
+              }
+            } else if (!C::b_mn) {
+              tma_load_2d(db, &tmB_hb, &full_bar[stage], k0, n0);
+            } else {
+#pragma unroll
+              for (int c = 0; c < C::block_n / C::chunk; ++c)
+                tma_load_2d(db + c * (C::bk * kRowBytes), &tmB_hb, &full_bar[stage], n0 + c * C::chunk, k0);
+            }
+          }
           if (C::mixed && lane == 0) {
             // the two bf16 tiles of each operand for the cross terms
 #pragma unroll
@@ -221,7 +259,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(C::tf32 ? 2 : 1, C::a_mn ? 1 : 0, C::b_mn ? 1 : 0, kBlockM, C::block_n);
+      constexpr uint32_t idesc = make_idesc(C::tf32 ? 2 : (C::f16 ? 0 : 1), C::a_mn ? 1 : 0, C::b_mn ? 1 : 0, kBlockM, C::block_n);
       // K-major : rows of 128 B, 8-row atoms 1024 B apart (SBO); LBO unused (1)
       // MN-major: 128 B of MN contiguous, k-rows 128 B apart, 8-row atoms 1024 B apart (SBO),
       //           next MN chunk bk*128 B away (LBO)
@@ -253,7 +291,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
             const uint32_t sa = smem_u32(smem + stage * C::stage_bytes);
-            const uint32_t sb = sa + (C::mixed ? 2 * C::a_bytes : C::a_bytes);
+            const uint32_t sb = sa + ((C::mixed || C::split16) ? 2 * C::a_bytes : C::a_bytes);
             if (C::mixed) {
               // cross terms first (small magnitude), on the bf16 pipe: bf16(a)*bf16(b_lo) + bf16(a_lo)*bf16(b)
               constexpr uint32_t idesc16 = make_idesc(1, C::a_mn ? 1 : 0, C::b_mn ? 1 : 0, kBlockM, C::block_n);
@@ -277,6 +315,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             for (int k = 0; k < C::ksteps; ++k) {
               const uint64_t a_hi = make_smem_desc(sa + k * kadv_a, lbo_a, sbo_a, lay_a);
               const uint64_t b_hi = make_smem_desc(sb + k * kadv_b, lbo_b, sbo_b, lay_b);
+              if (C::split16) {
+                // cross terms first (small magnitude): h1*h0' + h0*h1', then h0*h0'
+                const uint64_t a_h1 = make_smem_desc(sa + C::a_bytes + k * kadv_a, lbo_a, sbo_a, lay_a);
+                const uint64_t b_h1 = make_smem_desc(sb + C::b_bytes + k * kadv_b, lbo_b, sbo_b, lay_b);
+                umma_ss<false>(d_tmem, a_h1, b_hi, idesc, accumulate);
+                umma_ss<false>(d_tmem, a_hi, b_h1, idesc, 1u);
+                accumulate = 1u;
+              }
               umma_ss<C::tf32>(d_tmem, a_hi, b_hi, idesc, accumulate);
               accumulate = 1u;
             }
@@ -329,12 +375,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           if (lane == 0) mbar_arrive(&tmem_empty[acc]);
           acc ^= 1; if (acc == 0) acc_phase ^= 1u;
         }
+        // f16x3: undo the operands' power-of-two scales (exact)
+        const float unscale = C::split16 ? __ldg(p.inv_sa) * __ldg(p.inv_sb) : 1.f;
         if (row_ok) {
 #pragma unroll
           for (int j = 0; j < kColsPerWarp / 4; ++j) {
             const int col = n0 + j * 4;
             if (col < p.d_cols) {
               float4 v = make_float4(accr[4 * j], accr[4 * j + 1], accr[4 * j + 2], accr[4 * j + 3]);
+              if (C::split16) { v.x *= unscale; v.y *= unscale; v.z *= unscale; v.w *= unscale; }
               if (C::fwd_epi) {
                 float4 z;
                 epilogue_act4(p.epi, p.act_N, row, col, v, z);
@@ -442,7 +491,7 @@ int launch_cfg(const GemmProblem& g, cudaStream_t stream) {
     default:         d_rows = g.M; d_cols = g.K; red = g.N; a_inner = g.N; a_outer = g.M; b_inner = g.K; b_outer = g.N; break;
   }
   const CUtensorMapDataType dt = C::tf32 ? (C::nprod == 3 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32)
-                                         : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+                                         : (C::f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
   CUtensorMap tA_hi, tA_hb, tA_lb, tB_hi, tB_hb, tB_lb;
   // gathered operands: the tensor is the whole bank and the box is one row (gather4 fetches 4 of them)
   if (C::gather) {
@@ -472,6 +521,11 @@ int launch_cfg(const GemmProblem& g, cudaStream_t stream) {
     if ((rc = make_tmap(&tA_lb, a_planes + a_count, bf, 2, a_inner, a_outer, a_box, s16a, bba))) return rc;
     if ((rc = make_tmap(&tB_hb, b_planes, bf, 2, b_inner, b_outer, b_box, s16b, bbb))) return rc;
     if ((rc = make_tmap(&tB_lb, b_planes + b_count, bf, 2, b_inner, b_outer, b_box, s16b, bbb))) return rc;
+  } else if (C::split16) {
+    if (!g.A.lo || !g.B.lo) { set_error("F16X3 needs the h0 and h1 planes of every operand"); return VV_ERR_INVALID; }
+    if ((rc = make_tmap(&tA_hb, g.A.lo, dt, C::elem_bytes, a_inner, a_outer, a_box, sw_a))) return rc;
+    if ((rc = make_tmap(&tB_hb, g.B.lo, dt, C::elem_bytes, b_inner, b_outer, b_box, sw_b))) return rc;
+    tA_lb = tA_hi; tB_lb = tB_hi;
   } else {
     tA_hb = tA_hi; tA_lb = tA_hi; tB_hb = tB_hi; tB_lb = tB_hi;
   }
@@ -488,8 +542,10 @@ int launch_cfg(const GemmProblem& g, cudaStream_t stream) {
     return VV_ERR_INVALID;
   }
   p.nsplit = nsplit;
-  // tf32x3: promote every 512 reduction elements (16 k-blocks of 32) -> truncation bias < 4e-6 relative
-  p.chunk_kb = C::promote ? 16 : p.kb_per_split;
+  // tf32x3 / f16x3: promote every 512 reduction elements (16 k-blocks of 32 / 8 of 64) -> truncation bias < 4e-6 relative
+  p.chunk_kb = C::promote ? 512 / C::bk : p.kb_per_split;
+  p.inv_sa = C::split16 ? &f16_hdr(g.A.hi)->inv_scale : nullptr;
+  p.inv_sb = C::split16 ? &f16_hdr(g.B.hi)->inv_scale : nullptr;
   p.D = g.D; p.slab_stride = g.slab_stride;
   p.act_N = g.N;
   p.epi = g.epi;
@@ -520,7 +576,7 @@ int launch_cfg(const GemmProblem& g, cudaStream_t stream) {
 bool gemm_tc_supported(const GemmProblem& g, const char** why) {
   static const char* w_prec = "precision is not a tensor-core mode";
   static const char* w_align = "tensor-core path needs N % 8 == 0 and K % 8 == 0";
-  if (g.prec != VV_PREC_TF32X3 && g.prec != VV_PREC_TF32 && g.prec != VV_PREC_BF16) { if (why) *why = w_prec; return false; }
+  if (g.prec != VV_PREC_TF32X3 && g.prec != VV_PREC_TF32 && g.prec != VV_PREC_BF16 && g.prec != VV_PREC_F16X3) { if (why) *why = w_prec; return false; }
   if ((g.N % 8) != 0 || (g.K % 8) != 0) { if (why) *why = w_align; return false; }
   return true;
 }
@@ -546,6 +602,13 @@ int gemm_tc_launch(const GemmProblem& g, cudaStream_t stream) {
       case GEMM_WGRAD: return gat ? launch_cfg<Cfg<true, true,  true,  1, 256, 4, false, true>>(g, stream)
                                   : launch_cfg<Cfg<true, true,  true,  1, 256, 4, false>>(g, stream);
       default:         return launch_cfg<Cfg<true, false, true,  1, 256, 4, false>>(g, stream);
+    }
+  } else if (g.prec == VV_PREC_F16X3) {
+    if (gat) { set_error("the gather-fused variants are built for bf16 / tf32 only"); return VV_ERR_UNSUPPORTED; }
+    switch (g.kind) {
+      case GEMM_FWD:   return launch_cfg<Cfg<false, false, false, 3, 256, 2, true,  false, true>>(g, stream);
+      case GEMM_WGRAD: return launch_cfg<Cfg<false, true,  true,  3, 256, 2, false, false, true>>(g, stream);
+      default:         return launch_cfg<Cfg<false, false, true,  3, 256, 2, false, false, true>>(g, stream);
     }
   } else {
     switch (g.kind) {

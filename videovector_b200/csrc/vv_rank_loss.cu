@@ -165,22 +165,25 @@ struct BwdOut {
   float* dZ; float* hi; float* lo; uint16_t* bf; int prec; size_t count;
 };
 
-__device__ __forceinline__ void store_row4(const BwdOut& o, size_t off, const float4& v) {
+__device__ __forceinline__ void store_row4(const BwdOut& o, size_t off, const float4& v, float scale, float& amax) {
   if (o.dZ) stg_stream(reinterpret_cast<float4*>(o.dZ + off), v);
   if (o.prec == VV_PREC_TF32X3) {
     store_x3(o.hi, o.lo, o.count, off, v);
+  } else if (o.prec == VV_PREC_F16X3) {
+    store_f16x3(o.hi, o.lo, off, v, scale, amax);
   } else if (o.prec == VV_PREC_BF16) {
     uint2 pk = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
     *reinterpret_cast<uint2*>(o.bf + off) = pk;
   }
 }
 
-// OUT bit 0: fp32 dZ, bits 1..: 0 none, 2 = TF32X3 operand copy, 4 = BF16 operand copy; OUT < 0: decide at run time
+// OUT bit 0: fp32 dZ; 2 = TF32X3 operand copy, 4 = BF16 operand copy, 8 = F16X3 operand copy; OUT < 0: decide at run time
 template <int OUT>
-__device__ __forceinline__ void store_row4_t(const BwdOut& o, size_t off, const float4& v) {
-  if (OUT < 0) { store_row4(o, off, v); return; }
+__device__ __forceinline__ void store_row4_t(const BwdOut& o, size_t off, const float4& v, float scale, float& amax) {
+  if (OUT < 0) { store_row4(o, off, v, scale, amax); return; }
   if (OUT & 1) stg_stream(reinterpret_cast<float4*>(o.dZ + off), v);
   if (OUT & 2) store_x3(o.hi, o.lo, o.count, off, v);
+  if (OUT & 8) store_f16x3(o.hi, o.lo, off, v, scale, amax);
   if (OUT & 4) {
     uint2 pk = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
     *reinterpret_cast<uint2*>(o.bf + off) = pk;
@@ -208,6 +211,8 @@ rank_bwd_kernel(const float* __restrict__ H, const RankDev p, const float* __res
   float4 dbacc[NVEC], dqacc[NVEC];
 #pragma unroll
   for (int v = 0; v < NVEC; ++v) { dbacc[v] = make_float4(0.f, 0.f, 0.f, 0.f); dqacc[v] = make_float4(0.f, 0.f, 0.f, 0.f); }
+  const float oscale = (out.prec == VV_PREC_F16X3) ? f16_hdr(out.hi)->scale : 1.f;
+  float amax = 0.f;
 
   for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
     const float* st = stats + size_t(b) * p.stride;
@@ -290,7 +295,7 @@ rank_bwd_kernel(const float* __restrict__ H, const RankDev p, const float* __res
               dbacc[v].x += o.x; dbacc[v].y += o.y; dbacc[v].z += o.z; dbacc[v].w += o.w;
               dqacc[v].x = fmaf(dl, o.x, dqacc[v].x); dqacc[v].y = fmaf(dl, o.y, dqacc[v].y);
               dqacc[v].z = fmaf(dl, o.z, dqacc[v].z); dqacc[v].w = fmaf(dl, o.w, dqacc[v].w);
-              store_row4(out, (size_t(row) * p.B + b) * p.N + c4 * 4, o);
+              store_row4(out, (size_t(row) * p.B + b) * p.N + c4 * 4, o, oscale, amax);
             }
           }
         }
@@ -319,12 +324,13 @@ rank_bwd_kernel(const float* __restrict__ H, const RankDev p, const float* __res
             o.z = xv.z > 0.f ? o.z * dscale : 0.f; o.w = xv.w > 0.f ? o.w * dscale : 0.f;
           }
           dbacc[v].x += o.x; dbacc[v].y += o.y; dbacc[v].z += o.z; dbacc[v].w += o.w;
-          store_row4(out, off, o);
+          store_row4(out, off, o, oscale, amax);
         }
       }
     }
     __syncthreads();   // smem coefficients are rewritten by the next item
   }
+  if (out.prec == VV_PREC_F16X3) f16_publish_absmax(out.hi, amax);
   if (db_accum) {
 #pragma unroll
     for (int v = 0; v < NVEC; ++v) {
@@ -396,6 +402,8 @@ rank_fused_kernel(const float* __restrict__ H, const RankDev p, const float gsca
   const int per = (2 * J + 1) * nw + 3 * J + 2;        // floats per smem buffer (double buffered by item parity)
   const bool col_ok = tid < p.N4;
   float4 dbacc = make_float4(0.f, 0.f, 0.f, 0.f), dqacc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float oscale = (out.prec == VV_PREC_F16X3) ? f16_hdr(out.hi)->scale : 1.f;
+  float amax = 0.f;
   int parity = 0;
   for (int b = blockIdx.x; b < p.B; b += gridDim.x, parity ^= 1) {
     float* part = sm + parity * per;                   // [2J+1][nw]: (s_x, p_x) per branch, then s_c
@@ -517,7 +525,7 @@ rank_fused_kernel(const float* __restrict__ H, const RankDev p, const float gsca
             dqacc.x = fmaf(dl, o.x, dqacc.x); dqacc.y = fmaf(dl, o.y, dqacc.y);
             dqacc.z = fmaf(dl, o.z, dqacc.z); dqacc.w = fmaf(dl, o.w, dqacc.w);
           }
-          store_row4_t<OUT>(out, (size_t(r) * p.B + b) * p.N + tid * 4, o);
+          store_row4_t<OUT>(out, (size_t(r) * p.B + b) * p.N + tid * 4, o, oscale, amax);
         }
       }
     }
@@ -537,12 +545,13 @@ rank_fused_kernel(const float* __restrict__ H, const RankDev p, const float gsca
           o.z = xv.z > 0.f ? o.z * dscale : 0.f; o.w = xv.w > 0.f ? o.w * dscale : 0.f;
         }
         dbacc.x += o.x; dbacc.y += o.y; dbacc.z += o.z; dbacc.w += o.w;
-        store_row4_t<OUT>(out, (size_t(r) * p.B + b) * p.N + tid * 4, o);
+        store_row4_t<OUT>(out, (size_t(r) * p.B + b) * p.N + tid * 4, o, oscale, amax);
       }
     }
     // no trailing barrier: the next item uses the other smem buffer, and the barrier after its reductions
     // orders this item's coefficient reads before the buffer is written again two items later
   }
+  if (out.prec == VV_PREC_F16X3) f16_publish_absmax(out.hi, amax);
   if (col_ok) {
     if (db_accum) {
       atomicAdd(db_accum + tid * 4 + 0, dbacc.x); atomicAdd(db_accum + tid * 4 + 1, dbacc.y);
@@ -623,8 +632,8 @@ extern "C" int vv_rank_loss_backward_ex(const float* H, const vv_rank_cfg_t* cfg
   VV_REQUIRE(H && stats, "H and stats must be non-NULL");
   BwdOut o; o.dZ = dZ; o.hi = nullptr; o.lo = nullptr; o.bf = nullptr; o.prec = VV_PREC_FP32_SIMT;
   o.count = size_t(d.B) * (d.C + d.Nn) * d.N;
-  if (prec == VV_PREC_TF32X3 && dZop_hi) {
-    VV_REQUIRE(dZop_lo, "TF32X3 operand copy needs hi and lo");
+  if ((prec == VV_PREC_TF32X3 || prec == VV_PREC_F16X3) && dZop_hi) {
+    VV_REQUIRE(dZop_lo, "split operand copy needs hi and lo");
     o.hi = static_cast<float*>(dZop_hi); o.lo = static_cast<float*>(dZop_lo); o.prec = prec;
   } else if (prec == VV_PREC_BF16 && dZop_hi) {
     o.bf = static_cast<uint16_t*>(dZop_hi); o.prec = prec;
@@ -663,8 +672,8 @@ extern "C" int vv_rank_loss_fused(const float* H, const vv_rank_cfg_t* cfg, floa
   VV_REQUIRE(!(loss || violations) || (item_loss && item_viol), "loss/violations need item_loss and item_viol scratch [B]");
   BwdOut o; o.dZ = dZ; o.hi = nullptr; o.lo = nullptr; o.bf = nullptr; o.prec = VV_PREC_FP32_SIMT;
   o.count = size_t(d.B) * (d.C + d.Nn) * d.N;
-  if (prec == VV_PREC_TF32X3 && dZop_hi) {
-    VV_REQUIRE(dZop_lo, "TF32X3 operand copy needs hi and lo");
+  if ((prec == VV_PREC_TF32X3 || prec == VV_PREC_F16X3) && dZop_hi) {
+    VV_REQUIRE(dZop_lo, "split operand copy needs hi and lo");
     o.hi = static_cast<float*>(dZop_hi); o.lo = static_cast<float*>(dZop_lo); o.prec = prec;
   } else if (prec == VV_PREC_BF16 && dZop_hi) {
     o.bf = static_cast<uint16_t*>(dZop_hi); o.prec = prec;
@@ -677,12 +686,14 @@ extern "C" int vv_rank_loss_fused(const float* H, const vv_rank_cfg_t* cfg, floa
   const size_t smem = sizeof(float) * 2 * ((2 * J + 1) * nw + 3 * J + 2);
   const int per_sm = (R <= 16) ? 4 : 2;         // resident CTAs per SM at the kernels' register counts x T threads
   const int grid = d.B < num_sms() * per_sm ? d.B : num_sms() * per_sm;
-  const int mode = (o.dZ ? 1 : 0) | (o.prec == VV_PREC_TF32X3 ? 2 : 0) | (o.prec == VV_PREC_BF16 ? 4 : 0);
+  const int mode = (o.dZ ? 1 : 0) | (o.prec == VV_PREC_TF32X3 ? 2 : 0) | (o.prec == VV_PREC_BF16 ? 4 : 0) |
+                   (o.prec == VV_PREC_F16X3 ? 8 : 0);
 #define VV_RANK_FUSED(RM, CT, NNT, OUT)                                                                              \
   rank_fused_kernel<RM, CT, NNT, OUT><<<grid, T, smem, stream>>>(H, d, gscale, act_fused, dropout_scale, o, db_accum, \
       delta, dq_accum, stats, target_score, neg_score, item_loss, item_viol)
   if (d.C == 5 && d.Nn == 10 && mode == 2) VV_RANK_FUSED(16, 5, 10, 2);        // the shipped net (C=5, Nn=10), training modes
   else if (d.C == 5 && d.Nn == 10 && mode == 4) VV_RANK_FUSED(16, 5, 10, 4);
+  else if (d.C == 5 && d.Nn == 10 && mode == 8) VV_RANK_FUSED(16, 5, 10, 8);
   else if (d.C == 5 && d.Nn == 10 && mode == 1) VV_RANK_FUSED(16, 5, 10, 1);
   else if (R <= 16) VV_RANK_FUSED(16, 0, 0, -1);
   else VV_RANK_FUSED(32, 0, 0, -1);

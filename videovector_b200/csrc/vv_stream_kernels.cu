@@ -26,11 +26,14 @@ struct GatherOut { float* X; float* hi; float* lo; uint16_t* bf; float* blob; in
 
 constexpr int kGatherUnroll = 4;   // 128-bit loads in flight per thread before the first store
 
-__device__ __forceinline__ void gather_store(const GatherOut& o, size_t total, size_t off, size_t blob_off, const float4& v) {
+__device__ __forceinline__ void gather_store(const GatherOut& o, size_t total, size_t off, size_t blob_off, const float4& v,
+                                             float scale, float& amax) {
   if (o.X) stg_stream(reinterpret_cast<float4*>(o.X + off), v);
   if (o.blob) stg_stream(reinterpret_cast<float4*>(o.blob + blob_off), v);
   if (o.prec == VV_PREC_TF32X3) {
     store_x3(o.hi, o.lo, total, off, v);
+  } else if (o.prec == VV_PREC_F16X3) {
+    store_f16x3(o.hi, o.lo, off, v, scale, amax);
   } else if (o.prec == VV_PREC_BF16) {
     *reinterpret_cast<uint2*>(o.bf + off) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
   }
@@ -42,6 +45,8 @@ gather_rows_kernel(const float* __restrict__ bank, const int* __restrict__ idx, 
   const int K4 = K >> 2;
   const long long M = (long long)B * R;
   const int T = blockDim.x;
+  const float scale = (o.prec == VV_PREC_F16X3) ? f16_hdr(o.hi)->scale : 1.f;
+  float amax = 0.f;
   // the row index of the NEXT row is fetched while this row streams (it heads a dependent chain of two DRAM trips)
   long long orow = blockIdx.x;
   int slot = 0; long long src = 0; int qk = -2;
@@ -72,11 +77,13 @@ gather_rows_kernel(const float* __restrict__ bank, const int* __restrict__ idx, 
         const int c = c0 + u * T + threadIdx.x;
         if (c < K4) {
           if (c == K4 - 1 && cur_qk != -2) v[u].w = last;
-          gather_store(o, size_t(M) * K, size_t(orow) * K + size_t(c) * 4, size_t(cur_slot) * K + size_t(c) * 4, v[u]);
+          gather_store(o, size_t(M) * K, size_t(orow) * K + size_t(c) * 4, size_t(cur_slot) * K + size_t(c) * 4, v[u],
+                       scale, amax);
         }
       }
     }
   }
+  if (o.prec == VV_PREC_F16X3) f16_publish_absmax(o.hi, amax);
 }
 
 // Gather plan for the gather-fused GEMMs: rowmap[m] = bank row of X row m = j*B+b (0 in the padding), and
@@ -106,14 +113,50 @@ __global__ void add_column_kernel(float* A, long long ld, int col, const float* 
 // fp32 -> operand copies
 __global__ void __launch_bounds__(256)
 prepare_operand_kernel(const float* __restrict__ src, long long n4, int prec, float* hi, float* lo, uint16_t* bf) {
+  const float scale = (prec == VV_PREC_F16X3) ? f16_hdr(hi)->scale : 1.f;
+  float amax = 0.f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const float4 v = ldg_stream(reinterpret_cast<const float4*>(src) + i);
     if (prec == VV_PREC_TF32X3) {
       store_x3(hi, lo, size_t(n4) * 4, size_t(i) * 4, v);
+    } else if (prec == VV_PREC_F16X3) {
+      store_f16x3(hi, lo, size_t(i) * 4, v, scale, amax);
     } else {
       reinterpret_cast<uint2*>(bf)[i] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
     }
   }
+  if (prec == VV_PREC_F16X3) f16_publish_absmax(hi, amax);
+}
+// F16X3 header maintenance
+__global__ void __launch_bounds__(256)
+absmax_kernel(const float* __restrict__ src, long long n, void* hi) {
+  float amax = 0.f;
+  const long long n4 = n >> 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = ldg_stream(reinterpret_cast<const float4*>(src) + i);
+    amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) amax = fmaxf(amax, fabsf(src[n4 * 4 + threadIdx.x]));
+  f16_publish_absmax(hi, amax);
+}
+__global__ void operand_rescale_kernel(void* hi, int target_log2, int set_log2, int do_set) {
+  F16Hdr* h = f16_hdr(hi);
+  int e;
+  if (do_set) {
+    e = set_log2;
+  } else {
+    const float amax = __uint_as_float(h->absmax_bits);
+    if (!(amax > 0.f) || !isfinite(amax)) {                 // nothing recorded: keep the scale (1 if never set)
+      if (!(h->scale > 0.f)) { h->scale = 1.f; h->inv_scale = 1.f; }
+      h->absmax_bits = 0u;
+      return;
+    }
+    int ex; frexpf(amax, &ex);                              // amax = m * 2^ex, m in [0.5, 1)
+    e = target_log2 - ex;
+  }
+  e = e < -60 ? -60 : (e > 60 ? 60 : e);
+  h->scale = ldexpf(1.f, e); h->inv_scale = ldexpf(1.f, -e);
+  h->absmax_bits = 0u;
 }
 
 // ----------------------------------------------------------------------------
@@ -125,6 +168,8 @@ __global__ void __launch_bounds__(256)
 sgd_update_kernel(float* W, const float* parts, int nparts, long long stride,
                   float* hist, float* diff_out, long long n4, float rate, float momentum,
                   float decay, int reg_type, float gscale, int prec, float* hi, float* lo, uint16_t* bf) {
+  const float scale = (prec == VV_PREC_F16X3 && hi) ? f16_hdr(hi)->scale : 1.f;
+  float amax = 0.f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     float4 g = reinterpret_cast<const float4*>(parts)[i];
     for (int s = 1; s < nparts; ++s) {
@@ -150,10 +195,13 @@ sgd_update_kernel(float* W, const float* parts, int nparts, long long stride,
     if (diff_out) reinterpret_cast<float4*>(diff_out)[i] = h;
     if (prec == VV_PREC_TF32X3 && hi) {
       store_x3(hi, lo, size_t(n4) * 4, size_t(i) * 4, w);
+    } else if (prec == VV_PREC_F16X3 && hi) {
+      store_f16x3(hi, lo, size_t(i) * 4, w, scale, amax);
     } else if (prec == VV_PREC_BF16 && bf) {
       reinterpret_cast<uint2*>(bf)[i] = make_uint2(pack_bf16x2(w.x, w.y), pack_bf16x2(w.z, w.w));
     }
   }
+  if (prec == VV_PREC_F16X3 && hi) f16_publish_absmax(hi, amax);
 }
 // scalar tail / unaligned version (bias blobs whose count is not a multiple of 4)
 __global__ void sgd_update_scalar_kernel(float* W, const float* parts, int nparts, long long stride, float* hist,
@@ -340,8 +388,8 @@ extern "C" int vv_gather_rows(const float* bank, int64_t bank_rows, int K, const
   VV_REQUIRE(VV_ALIGNED16(bank) && VV_ALIGNED16(X) && VV_ALIGNED16(Xop_hi) && VV_ALIGNED16(Xop_lo) && VV_ALIGNED16(Xblob),
              "gather buffers must be 16-byte aligned");
   GatherOut o; o.X = X; o.blob = Xblob; o.hi = nullptr; o.lo = nullptr; o.bf = nullptr; o.prec = VV_PREC_FP32_SIMT;
-  if (prec == VV_PREC_TF32X3 && Xop_hi) {
-    VV_REQUIRE(Xop_lo, "TF32X3 operand copy needs hi and lo");
+  if ((prec == VV_PREC_TF32X3 || prec == VV_PREC_F16X3) && Xop_hi) {
+    VV_REQUIRE(Xop_lo, "split operand copy needs hi and lo");
     o.hi = static_cast<float*>(Xop_hi); o.lo = static_cast<float*>(Xop_lo); o.prec = prec;
   } else if (prec == VV_PREC_BF16 && Xop_hi) {
     o.bf = static_cast<uint16_t*>(Xop_hi); o.prec = prec;
@@ -375,11 +423,57 @@ extern "C" int vv_add_column(float* A, int64_t ld, int col, const float* v, int 
 extern "C" int vv_prepare_operand(const float* src, int64_t count, int prec, void* hi, void* lo, vv_stream_t stream) {
   if (prec == VV_PREC_FP32_SIMT || prec == VV_PREC_TF32) return VV_OK;
   VV_REQUIRE(src && hi && count > 0 && count % 4 == 0, "prepare_operand: bad arguments (count must be a multiple of 4)");
-  VV_REQUIRE(prec != VV_PREC_TF32X3 || lo, "TF32X3 needs a lo array");
+  VV_REQUIRE((prec != VV_PREC_TF32X3 && prec != VV_PREC_F16X3) || lo, "split operand formats need a lo array");
   VV_REQUIRE(VV_ALIGNED16(src) && VV_ALIGNED16(hi) && VV_ALIGNED16(lo), "operand buffers must be 16-byte aligned");
   const long long n4 = count / 4;
+  if (prec == VV_PREC_F16X3) {
+    int rc;
+    if ((rc = vv_operand_set_scale(hi, prec, 0, stream))) return rc;
+    if ((rc = vv_operand_measure(hi, prec, src, count, stream))) return rc;
+    if ((rc = vv_operand_rescale(hi, prec, 10, stream))) return rc;
+  }
   prepare_operand_kernel<<<stream_grid(n4, 256), 256, 0, stream>>>(src, n4, prec, static_cast<float*>(hi),
                                                                   static_cast<float*>(lo), static_cast<uint16_t*>(hi));
+  VV_LAUNCH_CHECK();
+  count_launch();
+  return VV_OK;
+}
+
+extern "C" size_t vv_operand_bytes(int64_t count, int prec, size_t* hi_offset, size_t* lo_offset) {
+  size_t hi_off = 0, lo_off = 0, bytes = 0;
+  const size_t n = count > 0 ? size_t(count) : 0;
+  switch (prec) {
+    case VV_PREC_TF32X3: bytes = 8 * n; lo_off = 4 * n; break;
+    case VV_PREC_BF16:   bytes = 2 * n; break;
+    case VV_PREC_F16X3:  hi_off = VV_F16X3_HEADER_BYTES; lo_off = hi_off + ((2 * n + 127) & ~size_t(127));
+                         bytes = lo_off + 2 * n; break;
+    default: break;
+  }
+  if (hi_offset) *hi_offset = hi_off;
+  if (lo_offset) *lo_offset = lo_off;
+  return bytes;
+}
+extern "C" int vv_operand_set_scale(void* hi, int prec, int log2_scale, vv_stream_t stream) {
+  if (prec != VV_PREC_F16X3) return VV_OK;
+  VV_REQUIRE(hi, "operand_set_scale: NULL operand");
+  operand_rescale_kernel<<<1, 1, 0, stream>>>(hi, 0, log2_scale, 1);
+  VV_LAUNCH_CHECK();
+  count_launch();
+  return VV_OK;
+}
+extern "C" int vv_operand_rescale(void* hi, int prec, int target_log2, vv_stream_t stream) {
+  if (prec != VV_PREC_F16X3) return VV_OK;
+  VV_REQUIRE(hi, "operand_rescale: NULL operand");
+  VV_REQUIRE(target_log2 >= -14 && target_log2 <= 15, "operand_rescale: target_log2 must lie in the fp16 exponent range");
+  operand_rescale_kernel<<<1, 1, 0, stream>>>(hi, target_log2, 0, 0);
+  VV_LAUNCH_CHECK();
+  count_launch();
+  return VV_OK;
+}
+extern "C" int vv_operand_measure(void* hi, int prec, const float* src, int64_t count, vv_stream_t stream) {
+  if (prec != VV_PREC_F16X3) return VV_OK;
+  VV_REQUIRE(hi && src && count > 0 && VV_ALIGNED16(src), "operand_measure: bad arguments");
+  absmax_kernel<<<stream_grid(count / 4 + 1, 256), 256, 0, stream>>>(src, count, hi);
   VV_LAUNCH_CHECK();
   count_launch();
   return VV_OK;

@@ -28,8 +28,21 @@ def _prec(p):
 class OperandT:
     """GEMM operand copies of an fp32 tensor for a precision (see vv_operand_t)."""
 
-    def __init__(self, hi, lo=None):
-        self.hi, self.lo = hi, lo
+    def __init__(self, hi, lo=None, block=None):
+        self.hi, self.lo, self.block = hi, lo, block       # block: the f16x3 allocation (header + planes)
+
+    @property
+    def scale(self):
+        """f16x3: the power-of-two scale in the operand's header (device -> host read)."""
+        return float(self.block[:8].view(torch.float32)[0].item())
+
+    @property
+    def absmax(self):
+        return float(self.block[8:12].view(torch.float32)[0].item())
+
+    def dequant(self):
+        """f16x3: (h0 + h1) / scale as fp32 -- what the GEMM effectively multiplies."""
+        return (self.hi.float() + self.lo.float()) / self.scale
 
     def c(self):
         return Operand(_ptr(self.hi), _ptr(self.lo))
@@ -42,7 +55,25 @@ def alloc_operand(shape, prec, device="cuda"):
                         torch.empty(shape, dtype=torch.float32, device=device))
     if p == PREC["bf16"]:
         return OperandT(torch.empty(shape, dtype=torch.bfloat16, device=device))
+    if p == PREC["f16x3"]:
+        n = 1
+        for d in shape:
+            n *= int(d)
+        ho, lo_ = C.c_size_t(0), C.c_size_t(0)
+        nbytes = _lib.load().vv_operand_bytes(n, p, C.byref(ho), C.byref(lo_))
+        block = torch.zeros(nbytes, dtype=torch.uint8, device=device)            # zero header = "scale not set"
+        hi = block[ho.value:ho.value + 2 * n].view(torch.float16).view(shape)
+        lo = block[lo_.value:lo_.value + 2 * n].view(torch.float16).view(shape)
+        return OperandT(hi, lo, block)
     return None
+
+
+def operand_rescale(op, prec, target_log2=10):
+    check(_lib.load().vv_operand_rescale(_ptr(op.hi), _prec(prec), target_log2, _stream()))
+
+
+def operand_measure(op, prec, src):
+    check(_lib.load().vv_operand_measure(_ptr(op.hi), _prec(prec), _ptr(src), src.numel(), _stream()))
 
 
 def prepare_operand(x, prec):
@@ -64,6 +95,8 @@ def gather_rows(bank, idx, quirk, prec="fp32_simt", want_x=True, want_blob=False
     X = torch.empty((R * B, K), dtype=torch.float32, device=bank.device) if want_x else None
     op = alloc_operand((R * B, K), p, bank.device)
     blob = torch.empty((B, R, K), dtype=torch.float32, device=bank.device) if want_blob else None
+    if p == PREC["f16x3"]:                       # the X scale comes from max|bank|
+        operand_measure(op, p, bank); operand_rescale(op, p, 12)
     check(lib.vv_gather_rows(_ptr(bank), bank.shape[0], K, _ptr(idx), _ptr(quirk), B, R, _ptr(X),
                              _ptr(op.hi) if op else None, _ptr(op.lo) if op else None, p, _ptr(blob), _stream()))
     if op is None and X is not None:
@@ -157,9 +190,14 @@ def rank_loss_backward(H, cfg, stats, loss_weight=1.0, act_fused=True, dropout_s
     dZ = torch.empty_like(H)
     op = alloc_operand(H.shape, p, dev)
     db = torch.zeros((cfg.N,), dtype=torch.float32, device=dev) if want_db else None
-    check(_lib.load().vv_rank_loss_backward(_ptr(H), C.byref(cfg), _ptr(stats), loss_weight, int(act_fused),
-                                            dropout_scale, _ptr(dZ), _ptr(op.hi) if op else None,
-                                            _ptr(op.lo) if op else None, p, _ptr(db), _stream()))
+    for _pass in range(2 if p == PREC["f16x3"] else 1):     # f16x3: a first pass measures max|dZ| for the scale
+        if db is not None:
+            db.zero_()
+        if _pass == 1:
+            operand_rescale(op, p)
+        check(_lib.load().vv_rank_loss_backward(_ptr(H), C.byref(cfg), _ptr(stats), loss_weight, int(act_fused),
+                                                dropout_scale, _ptr(dZ), _ptr(op.hi) if op else None,
+                                                _ptr(op.lo) if op else None, p, _ptr(db), _stream()))
     return dZ, (op if op is not None else OperandT(dZ)), db
 
 
@@ -182,11 +220,16 @@ def rank_loss_fused(H, cfg, loss_weight=1.0, act_fused=True, dropout_scale=1.0, 
     dZ = torch.empty_like(H)
     op = alloc_operand(H.shape, p, dev)
     db = torch.zeros((cfg.N,), dtype=torch.float32, device=dev) if want_db else None
-    check(_lib.load().vv_rank_loss_fused(_ptr(H), C.byref(cfg), loss_weight, int(act_fused), dropout_scale,
-                                         _ptr(out["stats"]), _ptr(out["target_score"]), _ptr(out["neg_score"]),
-                                         _ptr(out["item_loss"]), _ptr(out["item_viol"]), _ptr(out["loss"]),
-                                         _ptr(out["violations"]), _ptr(dZ), _ptr(op.hi) if op else None,
-                                         _ptr(op.lo) if op else None, p, _ptr(db), None, None, _stream()))
+    for _pass in range(2 if p == PREC["f16x3"] else 1):     # f16x3: a first pass measures max|dZ| for the scale
+        if db is not None:
+            db.zero_()
+        if _pass == 1:
+            operand_rescale(op, p)
+        check(_lib.load().vv_rank_loss_fused(_ptr(H), C.byref(cfg), loss_weight, int(act_fused), dropout_scale,
+                                             _ptr(out["stats"]), _ptr(out["target_score"]), _ptr(out["neg_score"]),
+                                             _ptr(out["item_loss"]), _ptr(out["item_viol"]), _ptr(out["loss"]),
+                                             _ptr(out["violations"]), _ptr(dZ), _ptr(op.hi) if op else None,
+                                             _ptr(op.lo) if op else None, p, _ptr(db), None, None, _stream()))
     return out, dZ, (op if op is not None else OperandT(dZ)), db
 
 
@@ -195,6 +238,8 @@ def sgd_update(W, grad_parts, hist, local_rate, momentum, local_decay, reg_type=
     """K4 (in place on W, hist).  grad_parts [S, ...] or [...]."""
     count = W.numel()
     nparts = grad_parts.numel() // count
+    if Wop is not None and _prec(prec) == PREC["f16x3"]:
+        operand_rescale(Wop, prec)
     check(_lib.load().vv_sgd_update(_ptr(W), _ptr(grad_parts), nparts, count, _ptr(hist), _ptr(diff_out), count,
                                     local_rate, momentum, local_decay, reg_type, grad_scale,
                                     _ptr(Wop.hi) if Wop is not None else None,
@@ -295,7 +340,7 @@ SOLVER_DEFAULTS = dict(lr_policy="inv", base_lr=1e-3, gamma=1e-3, power=0.75, st
 
 
 def trainer_cfg(B, C_=5, Nn=10, K=4096, N=512, margin=2.0, norm=2, dropout_ratio=0.9, dropout_mode=DROPOUT_PHILOX,
-                dropout_seed=7, loss_weight=1.0, regularization=0.0, prec="tf32x3", world_size=1, rank=0,
+                dropout_seed=7, loss_weight=1.0, regularization=0.0, prec="f16x3", world_size=1, rank=0,
                 compute_dgrad=False, keep_blobs=False, coeff=None, split_rank_loss=False, **solver):
     s = dict(SOLVER_DEFAULTS); s.update(solver)
     c = TrainerCfg()
