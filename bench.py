@@ -183,6 +183,11 @@ DTYPE = {"tf32x3": "f32 (tf32 + bf16 split operands, 3 tensor-core products, fp3
          "bf16": "bf16", "tf32": "tf32", "fp32_simt": "f32"}
 
 
+def fused_gather_on(args):
+    """K0 folded into the GEMM producers: the default for the 2-byte operand formats; --materialised-gather turns it off."""
+    return getattr(args, "precision", "f16x3") in ("f16x3", "bf16") and not getattr(args, "materialised_gather", False)
+
+
 def workload_config(args, world):
     c = CFG
     return {"workload": "videovec_embedding context-ranking training step (BASELINE configs[1] per GPU): "
@@ -191,8 +196,9 @@ def workload_config(args, world):
             "global_batch": c["B"] * world, "K": c["K"], "N": c["N"], "C": c["C"], "Nn": c["Nn"],
             "parallelism": "dp%d" % world, "precision": getattr(args, "precision", "f16x3"),
             "dgrad": False, "bank_rows": c["V"] * c["S"],
-            "gather": "fused into the GEMM TMA producer (gather4)" if getattr(args, "fused_gather", False) else "materialised X (K0 kernel)",
-            "l2": "inputs larger than L2: each step streams a %.2f GB gathered operand (> 126 MB L2)" % (
+            "gather": "fused into the GEMMs (cp.async row gather of the bank's operand copy by two producer warps)"
+                      if fused_gather_on(args) else "materialised X (K0 kernel)",
+            "l2": "inputs larger than L2: every GEMM streams %.2f GB of gathered operand rows (> 126 MB L2)" % (
                 (c["C"] + c["Nn"]) * c["B"] * c["K"] * OPERAND_BYTES[getattr(args, "precision", "f16x3")] / 1e9)}
 
 
@@ -231,8 +237,8 @@ def run_gpu(args):
         g = torch.Generator(device="cuda").manual_seed(1701)
         W0 = torch.randn(N, K, device="cuda", generator=g) * 0.001          # gaussian filler std 0.001, bias 0
         tr.set_weights(W0, torch.zeros(N, device="cuda"))
-        if args.fused_gather:
-            tr.set_bank(bank)          # gather-fused GEMMs (TMA gather4): correct but measured 2-4x slower, see DESIGN.md
+        if fused_gather_on(args):
+            tr.set_bank(bank)          # one-time operand copy of the resident bank; the GEMMs then gather its rows themselves
         if world > 1:
             idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
             if rank == 0:
@@ -346,7 +352,7 @@ def run_gpu(args):
             kern[name] = {"ms": ms, "bound": "tensor", "achieved_tflops": tf, "frac": tf / tensor_peak if tf else None,
                           "tensor_pipe_frac": tf * units / tensor_peak if tf else None}
         fused_rank = phase["rank_loss_forward"] == 0
-        bytes_alg = {"gather": (M * K * (4 + (opb if prec not in ("tf32", "fp32_simt") else 4))) if not args.fused_gather
+        bytes_alg = {"gather": (M * K * (4 + (opb if prec not in ("tf32", "fp32_simt") else 4))) if not fused_gather_on(args)
                      else ((M + 127) // 128 * 128) * 8 + M * 8,
                      "rank_loss_forward": M * N * 4,
                      # fused K2+K3 reads H once; the two-kernel K3 reads it again
@@ -399,12 +405,12 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="f16x3", choices=["tf32x3", "f16x3", "tf32", "bf16", "fp32_simt"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--fused-gather", action="store_true", help="fold K0 into the GEMM TMA producer (gather4) instead of materialising X")
+    ap.add_argument("--materialised-gather", action="store_true", help="run K0 as its own kernel (materialised X operand) instead of gathering inside the GEMMs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

@@ -108,11 +108,12 @@ def test_solver_trajectory_matches_oracle(oracle, prec):
     tr.close(); smp.close()
 
 
-@pytest.mark.parametrize("prec,tol", [("tf32", 2e-2), ("bf16", 5e-2)])
-@pytest.mark.parametrize("B,C,Nn,K,N", [(128, 5, 10, 4096, 512), (24, 17, 50, 512, 1024), (8, 3, 4, 64, 32)])
+@pytest.mark.parametrize("prec,tol", [("f16x3", 1e-5), ("bf16", 5e-2)])
+@pytest.mark.parametrize("B,C,Nn,K,N", [(128, 5, 10, 4096, 512), (24, 17, 50, 512, 1024), (8, 3, 4, 64, 32), (40, 5, 10, 200, 72)])
 def test_gather_fused_step_matches_oracle(oracle, prec, tol, B, C, Nn, K, N):
-    """K0 folded into the GEMMs' TMA producer (gather4 from the registered bank): same results as the oracle,
-    including rows hit by the K-1 copy quirk (handled as a rank-1 correction in the fc7 epilogue / dW[:,K-1])."""
+    """K0 folded into the GEMMs (cp.async row gather from the registered bank's operand copy): same results as the
+    oracle, including rows hit by the K-1 copy quirk (a rank-1 correction in the fc7 epilogue / dW[:,K-1]) and
+    ragged K / N tails."""
     bank, smp, W0, b0 = setup_problem(B, C, Nn, K, N)
     bank_np = bank.cpu().numpy()
     ratio = 0.9 if N >= 512 else 0.5
@@ -152,7 +153,7 @@ def test_gather_fused_training_equals_materialised_path():
     res = []
     for fused in (False, True):
         bank, smp, W0, b0 = setup_problem(B, C, Nn, K, N, V=128, S=16, P=500)
-        tr = ops.Trainer(ops.trainer_cfg(B, C, Nn, K, N, dropout_ratio=0.9, dropout_mode=DROPOUT_PHILOX, prec="tf32", base_lr=0.01))
+        tr = ops.Trainer(ops.trainer_cfg(B, C, Nn, K, N, dropout_ratio=0.9, dropout_mode=DROPOUT_PHILOX, prec="f16x3", base_lr=0.01))
         tr.set_weights(torch.as_tensor(W0).cuda(), torch.as_tensor(b0).cuda())
         if fused:
             tr.set_bank(bank)
@@ -161,8 +162,9 @@ def test_gather_fused_training_equals_materialised_path():
             tr.step(bank, torch.as_tensor(idx).cuda(), torch.as_tensor(quirk).cuda(), None, it=it)
         res.append((tr.tensor("W").clone(), tr.tensor("b").clone(), tr.tensor("loss").item()))
         tr.close(); smp.close()
-    # tf32: both paths round the same operands the same way (TMA TFLOAT32), the quirk column differs by rounding only
-    assert rel(res[1][0], res[0][0]) < 1e-3 and rel(res[1][1], res[0][1]) < 1e-3 and abs(res[1][2] - res[0][2]) < 1e-3
+    # both paths multiply the same fp16 planes (the bank copy is scaled from max|bank| like the gathered X); the
+    # quirk column and the summation order differ by rounding only
+    assert rel(res[1][0], res[0][0]) < 1e-4 and rel(res[1][1], res[0][1]) < 1e-4 and abs(res[1][2] - res[0][2]) < 1e-4
 
 
 def test_dgrad_in_trainer_matches_oracle(oracle):

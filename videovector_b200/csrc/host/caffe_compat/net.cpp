@@ -1,6 +1,7 @@
 // Net<Dtype> (see caffe/net.hpp for the reference lines mirrored here).
 #include <cuda_runtime_api.h>
 #include <cstring>
+#include <cstdlib>
 #include "caffe/net.hpp"
 
 namespace caffe {
@@ -329,6 +330,10 @@ Dtype Net<Dtype>::FusedStep(int iter, bool do_update, const vv_trainer_cfg_t* so
     VV_CHECK(vv_trainer_sync_weights(trainer_));
     W->set_gpu_data(vv_trainer_weight(trainer_)); W->set_gpu_diff(vv_trainer_weight_diff(trainer_));
     b->set_gpu_data(vv_trainer_bias(trainer_)); b->set_gpu_diff(vv_trainer_bias_diff(trainer_));
+    // the data layer's resident feature bank: registered once so the GEMMs gather its rows themselves
+    // (a no-op for the precisions without gather producers); VV_MATERIALISE=1 keeps the K0 kernel
+    const char* mat = getenv("VV_MATERIALISE");
+    if (!(mat && mat[0] == '1')) VV_CHECK(vv_trainer_set_bank(trainer_, fused_data_->bank(), fused_data_->bank_rows()));
   }
   const int32_t* dq = nullptr;
   const int32_t* di = fused_data_->NextIndices(&dq);

@@ -166,9 +166,8 @@ struct vv_trainer {
   }
   vv_operand_t opBank() const {
     vv_operand_t o;
-    if (cfg.prec == VV_PREC_TF32X3) { o.hi = bank_hi.p; o.lo = bank_lo.p; }
-    else if (cfg.prec == VV_PREC_BF16) { o.hi = bank_hi.p; o.lo = nullptr; }
-    else { o.hi = bank_reg; o.lo = nullptr; }      // TF32: TMA reads the fp32 bank itself
+    if (cfg.prec == VV_PREC_F16X3) { o.hi = bank_hi.p; o.lo = bank_lo.p; }
+    else { o.hi = bank_hi.p; o.lo = nullptr; }     // BF16
     return o;
   }
   ~vv_trainer() {
@@ -234,14 +233,14 @@ extern "C" int vv_trainer_sync_weights(vv_trainer_t* t) {
 extern "C" int vv_trainer_set_bank(vv_trainer_t* t, const float* bank, int64_t bank_rows) {
   if (!t || !bank || bank_rows <= 0) { set_error("set_bank: bad arguments"); return VV_ERR_INVALID; }
   const vv_trainer_cfg_t& c = t->cfg;
-  // materialised path: exact-fp32 mode, blob inspection, and tf32x3 (its gather variants are not built: gather4
-  // measured slower than the K0 kernel)
-  if (c.prec == VV_PREC_FP32_SIMT || c.prec == VV_PREC_TF32X3 || c.prec == VV_PREC_F16X3 || c.keep_blobs) { t->bank_reg = nullptr; return VV_OK; }
+  // materialised path: exact-fp32 mode, blob inspection, and the 4-byte operand formats (the gather producers copy
+  // 16-byte chunks of 2-byte elements)
+  if (c.prec != VV_PREC_F16X3 && c.prec != VV_PREC_BF16) { t->bank_reg = nullptr; return VV_OK; }
+  if (c.keep_blobs) { t->bank_reg = nullptr; return VV_OK; }
   vv_stream_t s = reinterpret_cast<vv_stream_t>(t->stream);
   const int64_t n = bank_rows * c.K;
   int rc;
-  t->bank_hi.release(); t->bank_lo.release();
-  if (c.prec == VV_PREC_BF16) { if ((rc = t->bank_hi.alloc(size_t(n) * 2))) return rc; }
+  if ((rc = alloc_operand(t->bank_hi, t->bank_lo, size_t(n), c.prec))) return rc;
   if ((rc = vv_prepare_operand(bank, n, c.prec, t->bank_hi.p, t->bank_lo.p, s))) return rc;
   t->bank_reg = bank; t->bank_reg_rows = bank_rows;
   return VV_OK;

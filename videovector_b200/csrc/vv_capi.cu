@@ -167,7 +167,8 @@ extern "C" int vv_ip_wgrad_gathered(vv_operand_t dZ, vv_operand_t bank, int64_t 
              "ip_wgrad_gathered: bad arguments");
   VV_REQUIRE(prec != VV_PREC_FP32_SIMT, "ip_wgrad_gathered needs a tensor-core precision");
   GemmProblem g;
-  g.kind = GEMM_WGRAD; g.prec = prec; g.A = dZ; g.B = bank; g.M = M; g.N = N; g.K = K;
+  // computed as (X^T dZ)^T so that the gathered operand is A (see GEMM_WGRAD_T)
+  g.kind = GEMM_WGRAD_T; g.prec = prec; g.A = bank; g.B = dZ; g.M = M; g.N = N; g.K = K;
   g.rowmap = rowmap; g.bank_rows = bank_rows;
   int rc = fill_epilogue(nullptr, nullptr, nullptr, &g.epi);
   if (rc) return rc;

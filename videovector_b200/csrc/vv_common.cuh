@@ -213,6 +213,14 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, ui
       : "memory");
 }
 // 4 rows (any order, by index) x one box width of columns; the tensor map's box is {cols, 1}
+// 16-byte asynchronous global->shared copy (LDGSTS); src_bytes = 0 zero-fills the destination
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(smem_dst), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+// the mbarrier receives one (pre-counted) arrival from this thread once all its earlier cp.async have landed
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void tma_gather4(void* smem_dst, const void* tmap, uint64_t* bar, int col,
                                             int r0, int r1, int r2, int r3) {
   asm volatile(

@@ -8,7 +8,9 @@ namespace vv {
 enum GemmKind {
   GEMM_FWD = 0,    // D[M,N]  = X[M,K]  . W[N,K]^T     A K-major,  B K-major,  reduce K
   GEMM_WGRAD = 1,  // D[N,K]  = dZ[M,N]^T . X[M,K]     A MN-major, B MN-major, reduce M
-  GEMM_DGRAD = 2   // D[M,K]  = dZ[M,N] . W[N,K]       A K-major,  B MN-major, reduce N
+  GEMM_DGRAD = 2,  // D[M,K]  = dZ[M,N] . W[N,K]       A K-major,  B MN-major, reduce N
+  // gathered wgrad: the same dW computed as (X^T dZ)^T so that the gathered operand is A:
+  GEMM_WGRAD_T = 3 // D[N,K]^T = X[M,K]^T . dZ[M,N]    A = X MN-major (gathered), B = dZ MN-major, reduce M, D stored transposed
 };
 
 // Epilogue description (device side copy of vv_act_t plus bias / scaling)
@@ -35,8 +37,8 @@ struct GemmProblem {
   int M, N, K;            // the fc7 dims (rows, outputs, inputs) -- NOT the tile dims
   float* D; int64_t slab_stride; int nsplit;
   GemmEpilogue epi;
-  // gather-fused variants: the X operand (A of FWD, B of WGRAD) is the resident bank's operand copy and its
-  // rows are fetched by index with TMA gather4; rowmap[m] = bank row of X row m (padded to a multiple of 128)
+  // gather-fused variants (FWD, WGRAD_T): the X operand (= A) is the resident bank's operand copy and its rows
+  // are fetched by index with cp.async by two producer warps; rowmap[m] = bank row of X row m (padded to a multiple of 128)
   const int32_t* rowmap;  // NULL = X is materialised
   int64_t bank_rows;
 };

@@ -3,7 +3,7 @@
 // One persistent, warp-specialised kernel template for sm_100a:
 //   warp 0   : TMA producer  (cp.async.bulk.tensor 2D tiles, SWIZZLE_128B, mbarrier tx)
 //   warp 1   : MMA issuer    (tcgen05.mma cta_group::1, 128 x BLOCK_N x (32 B of K), fp32 accum in TMEM)
-//   warp 2   : TMEM allocator
+//   warp 2   : TMEM allocator; warps 2-3: cp.async row-gather producers of operand A in the gather-fused variants
 //   warps 4-11: epilogue     (tcgen05.ld 32x32b -> bias / ReLU / dropout / scale -> global)
 // Two TMEM accumulator buffers (2 x BLOCK_N columns) let the epilogue of tile i
 // overlap the main loop of tile i+1.
@@ -37,22 +37,25 @@ struct TcParams {
   float* D; long long slab_stride;
   int act_N;                    // row pitch of mask/Z (= N of the layer) for the FWD epilogue
   const int* rowmap;            // gather variants: bank row of every X row (padded to a multiple of 128)
+  const uint16_t* ga0; const uint16_t* ga1;   // gather variants: the bank's operand plane(s), row pitch ga_pitch elements
+  long long ga_pitch; int ga_cols; int rowmap_len;
   const float* inv_sa; const float* inv_sb;   // f16x3: 1/scale of the two operands (device, from their headers)
   GemmEpilogue epi;
 };
 
 template <bool kTF32, bool kAMN, bool kBMN, int kNProd, int kBlockN, int kStages, bool kFwdEpi, bool kGather = false,
-          bool kF16 = false>
+          bool kF16 = false, bool kTransOut = false>
 struct Cfg {
   static constexpr bool f16 = kF16;                    // fp16 elements (kind::f16 with F16 formats) instead of bf16
   static_assert(!(kF16 && kTF32), "f16 and tf32 exclude each other");
-  // kGather: the X operand (A when K-major = FWD, B when MN-major = WGRAD) is gathered row-wise from the bank
+  // kGather: operand A (X: the rows of FWD, the k-rows of WGRAD_T) is gathered row-wise from the bank's operand copy by
+  // warps 2-3 with 16-byte cp.async straight into the swizzled tile (2-byte element types only); B still arrives by TMA
   static constexpr bool gather = kGather;
-  static constexpr bool gather_a = kGather && !kAMN;   // FWD : A rows = X rows
-  static constexpr bool gather_b = kGather && kAMN;    // WGRAD: B k-rows = X rows
+  static_assert(!(kGather && kTF32), "the gather producers are written for 2-byte elements");
+  static constexpr bool trans_out = kTransOut;         // store D transposed (WGRAD_T)
   // 2-CTA clusters share the B tile: each CTA loads half of it with TMA multicast, which cuts the L2->smem
-  // fill per CTA from A+B to A+B/2 (the kernels are L2-bandwidth bound at ~12 TB/s, not MMA bound)
-  static constexpr int cluster = kGather ? 1 : 2;
+  // fill per CTA from A+B to A+B/2
+  static constexpr int cluster = 2;
   static constexpr bool tf32 = kTF32;
   static constexpr bool a_mn = kAMN, b_mn = kBMN;
   static constexpr int nprod = kNProd;                 // 1 or 3
@@ -104,7 +107,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     if (C::split16) { tma_prefetch_desc(&tmA_hb); tma_prefetch_desc(&tmB_hb); }
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < C::stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], C::cluster); }
+    // full: the TMA lane's arrive.expect_tx (+ one cp.async-completion arrival per gather lane, 2 warps)
+    for (int s = 0; s < C::stages; ++s) { mbar_init(&full_bar[s], C::gather ? 1 + 64 : 1); mbar_init(&empty_bar[s], C::cluster); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 8); }
     fence_barrier_init();
   }
@@ -124,9 +128,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    // Lane 0 issues the tiled loads; in the gather variants all 32 lanes issue gather4 loads (4 rows each)
-    // of the bank rows named by rowmap, so the gathered operand never exists in HBM.
-    if (lane == 0 || C::gather) {
+    if (lane == 0) {
+      constexpr int kTmaBytes = C::stage_bytes - (C::gather ? ((C::mixed || C::split16) ? 2 * C::a_bytes : C::a_bytes) : 0);
       int stage = 0; uint32_t phase = 0;
       for (int u = unit0; u < total_units; u += unit_stride) {
         const int split = u / tiles_mn;
@@ -135,22 +138,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const int n0 = (t % p.tiles_n) * C::block_n;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
-        int4 arow = make_int4(0, 0, 0, 0);
-        if (C::gather_a) arow = *reinterpret_cast<const int4*>(p.rowmap + m0 + 4 * lane);   // this lane's 4 A rows
         for (int kb = kb0; kb < kb1; ++kb) {
-          if (lane == 0) {
-            mbar_wait(&empty_bar[stage], phase ^ 1u);
-            mbar_arrive_expect_tx(&full_bar[stage], C::stage_bytes);
-          }
-          if (C::gather) __syncwarp();
-          // stage layout: [A_hi][A_hb][A_lb][B_hi][B_hb][B_lb]  (the bf16 tiles only in mixed mode)
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          mbar_arrive_expect_tx(&full_bar[stage], kTmaBytes);
+          // stage layout: [A_hi][A_hb][A_lb][B_hi][B_hb][B_lb]  (the extra tiles only in the split modes)
           uint8_t* sa = smem + stage * C::stage_bytes;
           uint8_t* sb = sa + ((C::mixed || C::split16) ? 2 * C::a_bytes : C::a_bytes);
           const int k0 = kb * C::bk;
-          if (C::gather_a) {
-            // A tile [128 rows x 128 B]: lane l fills rows 4l..4l+3 (512 B, inside one swizzle atom)
-            tma_gather4(sa + lane * 512, &tmA_hi, &full_bar[stage], k0, arow.x, arow.y, arow.z, arow.w);
-          } else if (lane == 0) {
+          if (!C::gather) {
             if (!C::a_mn) {
               tma_load_2d(sa, &tmA_hi, &full_bar[stage], k0, m0);
             } else {
@@ -159,41 +154,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 tma_load_2d(sa + c * (C::bk * kRowBytes), &tmA_hi, &full_bar[stage], m0 + c * C::chunk, k0);
             }
           }
-          if (C::gather_b) {
-            // B tile = chunks of [bk k-rows x 128 B]; a gather4 fills 4 k-rows of one chunk.
-            constexpr int kGroups = C::bk / 4;                 // row groups per chunk (16 bf16 / 8 tf32)
-            constexpr int kChunks = C::block_n / C::chunk;     // 4 bf16 / 8 tf32
-            const int grp = lane % kGroups;
-            const int4 r = *reinterpret_cast<const int4*>(p.rowmap + k0 + 4 * grp);
-#pragma unroll
-            for (int c = lane / kGroups; c < kChunks; c += 32 / kGroups)
-              tma_gather4(sb + c * (C::bk * kRowBytes) + grp * 512, &tmB_hi, &full_bar[stage],
-                          n0 + c * C::chunk, r.x, r.y, r.z, r.w);
-          } else if (lane == 0) {
-            if (C::cluster > 1) {
-              // this CTA fetches half of the shared B tile and multicasts it to both CTAs of the cluster
-              if (!C::b_mn) {
-                tma_load_2d_mc(sb + cta_rank * (C::b_bytes / 2), &tmB_hi, &full_bar[stage], k0, n0 + cta_rank * (C::block_n / 2), 0x3);
-              } else {
-                constexpr int kHalf = C::block_n / C::chunk / 2;
-#pragma unroll
-                for (int c = 0; c < kHalf; ++c)
-                  tma_load_2d_mc(sb + (cta_rank * kHalf + c) * (C::bk * kRowBytes), &tmB_hi, &full_bar[stage],
-                                 n0 + (cta_rank * kHalf + c) * C::chunk, k0, 0x3);
-              }
-            } else if (!C::b_mn) {
-              tma_load_2d(sb, &tmB_hi, &full_bar[stage], k0, n0);
+          {
+            // this CTA fetches half of the shared B tile and multicasts it to both CTAs of the cluster
+            if (!C::b_mn) {
+              tma_load_2d_mc(sb + cta_rank * (C::b_bytes / 2), &tmB_hi, &full_bar[stage], k0, n0 + cta_rank * (C::block_n / 2), 0x3);
             } else {
+              constexpr int kHalf = C::block_n / C::chunk / 2;
 #pragma unroll
-              for (int c = 0; c < C::block_n / C::chunk; ++c)
-                tma_load_2d(sb + c * (C::bk * kRowBytes), &tmB_hi, &full_bar[stage], n0 + c * C::chunk, k0);
+              for (int c = 0; c < kHalf; ++c)
+                tma_load_2d_mc(sb + (cta_rank * kHalf + c) * (C::bk * kRowBytes), &tmB_hi, &full_bar[stage],
+                               n0 + (cta_rank * kHalf + c) * C::chunk, k0, 0x3);
             }
           }
           if (C::split16 && lane == 0) {
             // the h1 planes: same boxes as the h0 tiles, through the second pair of tensor maps
             uint8_t* da = sa + C::a_bytes;
             uint8_t* db = sb + C::b_bytes;
-            if (!C::a_mn) {
+            if (C::gather) {
+              // the h1 plane of A is gathered together with h0 by warps 2-3
+            } else if (!C::a_mn) {
               tma_load_2d(da, &tmA_hb, &full_bar[stage], k0, m0);
             } else {
 #pragma unroll
@@ -290,6 +269,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           for (int kb = c0; kb < c1; ++kb) {
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
+            if (C::gather) fence_proxy_async();     // A was written by cp.async (generic proxy); the MMA reads through the async proxy
             const uint32_t sa = smem_u32(smem + stage * C::stage_bytes);
             const uint32_t sb = sa + ((C::mixed || C::split16) ? 2 * C::a_bytes : C::a_bytes);
             if (C::mixed) {
@@ -332,6 +312,79 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             if (++stage == C::stages) { stage = 0; phase ^= 1u; }
           }
           acc ^= 1; if (acc == 0) acc_phase ^= 1u;
+        }
+      }
+    }
+  } else if (C::gather && (warp == 2 || warp == 3)) {
+    // ===================== cp.async gather producers of operand A (2 warps) =====================
+    // 64 lanes x 16-byte chunks: lane t copies chunk column c = t % 8 of the tile rows r0 + 8i (r0 = t / 8), so 8
+    // consecutive lanes fetch one contiguous 128-byte piece of a bank row and the swizzle term (row % 8 = r0) is a
+    // per-lane constant.  Completion is signalled to full_bar by cp.async.mbarrier.arrive.noinc (no waiting here:
+    // as many stages in flight as the ring has); the MMA thread crosses to the async proxy with fence.proxy.async.
+    const int t64 = (warp - 2) * 32 + lane;
+    const int c = t64 & 7, r0 = t64 >> 3;
+    const uint32_t swz = uint32_t((c ^ r0) << 4);
+    constexpr int kPlanes = C::split16 ? 2 : 1;
+    int stage = 0; uint32_t phase = 0;
+    for (int u = unit0; u < total_units; u += unit_stride) {
+      const int split = u / tiles_mn;
+      const int t = u - split * tiles_mn;
+      const int m0 = ((t / p.tiles_n) * C::cluster + cta_rank) * kBlockM;
+      const int kb0 = split * p.kb_per_split;
+      const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
+      if (!C::a_mn) {
+        // FWD: A tile = [128 X rows x 128 B of K]; this lane's 16 rows are fixed for the whole unit
+        long long rowoff[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {     // an m-tile past the end (odd tile count in a cluster pair) reads row 0, stores nothing
+          const int rr = m0 + r0 + 8 * i;
+          rowoff[i] = (rr < p.rowmap_len) ? (long long)p.rowmap[rr] * p.ga_pitch : 0;
+        }
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          const uint32_t sa = smem_u32(smem + stage * C::stage_bytes);
+          int kcol = kb * C::bk + c * 8;
+          const int nb = kcol < p.ga_cols ? 16 : 0;                 // K tail: zero fill like TMA
+          if (!nb) kcol = 0;                                        // keep the (unread) source address inside the bank
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const uint32_t dst = sa + uint32_t((r0 + 8 * i) * kRowBytes) + swz;
+            cp_async16(dst, p.ga0 + rowoff[i] + kcol, nb);
+            if (kPlanes == 2) cp_async16(dst + C::a_bytes, p.ga1 + rowoff[i] + kcol, nb);
+          }
+          cp_async_mbar_arrive_noinc(&full_bar[stage]);
+          if (++stage == C::stages) { stage = 0; phase ^= 1u; }
+        }
+      } else {
+        // WGRAD_T: A tile = 2 chunks of [bk X rows (the reduction) x 128 B of features]; rows change every k-block
+        static_assert(!C::gather || C::bk == 64, "gather producers assume 64 reduction rows per k-block");
+        int rws[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) rws[j] = p.rowmap[kb0 * C::bk + r0 + 8 * j];
+        for (int kb = kb0; kb < kb1; ++kb) {
+          long long rowoff[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) rowoff[j] = (long long)rws[j] * p.ga_pitch;
+          if (kb + 1 < kb1) {                                       // next k-block's row indices, ahead of the wait
+#pragma unroll
+            for (int j = 0; j < 8; ++j) rws[j] = p.rowmap[(kb + 1) * C::bk + r0 + 8 * j];
+          }
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          const uint32_t sa = smem_u32(smem + stage * C::stage_bytes);
+#pragma unroll
+          for (int cf = 0; cf < kBlockM / C::chunk; ++cf) {
+            int f = m0 + cf * C::chunk + c * 8;
+            const int nb = f < p.ga_cols ? 16 : 0;                  // feature tail: zero fill
+            if (!nb) f = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint32_t dst = sa + uint32_t(cf * (C::bk * kRowBytes) + (r0 + 8 * j) * kRowBytes) + swz;
+              cp_async16(dst, p.ga0 + rowoff[j] + f, nb);
+              if (kPlanes == 2) cp_async16(dst + C::a_bytes, p.ga1 + rowoff[j] + f, nb);
+            }
+          }
+          cp_async_mbar_arrive_noinc(&full_bar[stage]);
+          if (++stage == C::stages) { stage = 0; phase ^= 1u; }
         }
       }
     }
@@ -392,7 +445,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 const float s = p.epi.out_scale;
                 v.x *= s; v.y *= s; v.z *= s; v.w *= s;
               }
-              *reinterpret_cast<float4*>(drow + col) = v;
+              if (C::trans_out) {
+                // D^T: element (row, col) lives at D[col * ldd + row]; a warp's 32 rows are 128 contiguous bytes
+                float* dt = p.D + (long long)split * p.slab_stride + row;
+                dt[(long long)col * p.ldd] = v.x;
+                if (col + 1 < p.d_cols) dt[(long long)(col + 1) * p.ldd] = v.y;
+                if (col + 2 < p.d_cols) dt[(long long)(col + 2) * p.ldd] = v.z;
+                if (col + 3 < p.d_cols) dt[(long long)(col + 3) * p.ldd] = v.w;
+              } else {
+                *reinterpret_cast<float4*>(drow + col) = v;
+              }
             }
           }
         }
@@ -421,6 +483,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                   const float s = p.epi.out_scale;
                   v.x *= s; v.y *= s; v.z *= s; v.w *= s;
                 }
+                if (C::trans_out) {
+                  float* dt = p.D + (long long)split * p.slab_stride + row;
+                  dt[(long long)col * p.ldd] = v.x;
+                  if (col + 1 < p.d_cols) dt[(long long)(col + 1) * p.ldd] = v.y;
+                  if (col + 2 < p.d_cols) dt[(long long)(col + 2) * p.ldd] = v.z;
+                  if (col + 3 < p.d_cols) dt[(long long)(col + 3) * p.ldd] = v.w;
+                } else
                 *reinterpret_cast<float4*>(drow + col) = v;
               }
             }
@@ -486,26 +555,29 @@ int launch_cfg(const GemmProblem& g, cudaStream_t stream) {
   int d_rows, d_cols, red;
   uint64_t a_inner, a_outer, b_inner, b_outer;
   switch (g.kind) {
-    case GEMM_FWD:   d_rows = g.M; d_cols = g.N; red = g.K; a_inner = g.K; a_outer = g.M; b_inner = g.K; b_outer = g.N; break;
-    case GEMM_WGRAD: d_rows = g.N; d_cols = g.K; red = g.M; a_inner = g.N; a_outer = g.M; b_inner = g.K; b_outer = g.M; break;
-    default:         d_rows = g.M; d_cols = g.K; red = g.N; a_inner = g.N; a_outer = g.M; b_inner = g.K; b_outer = g.N; break;
+    case GEMM_FWD:     d_rows = g.M; d_cols = g.N; red = g.K; a_inner = g.K; a_outer = g.M; b_inner = g.K; b_outer = g.N; break;
+    case GEMM_WGRAD:   d_rows = g.N; d_cols = g.K; red = g.M; a_inner = g.N; a_outer = g.M; b_inner = g.K; b_outer = g.M; break;
+    case GEMM_WGRAD_T: d_rows = g.K; d_cols = g.N; red = g.M; a_inner = g.K; a_outer = g.M; b_inner = g.N; b_outer = g.M; break;
+    default:           d_rows = g.M; d_cols = g.K; red = g.N; a_inner = g.N; a_outer = g.M; b_inner = g.K; b_outer = g.N; break;
   }
+  if (C::trans_out != (g.kind == GEMM_WGRAD_T)) { set_error("internal: transposed-output configuration mismatch"); return VV_ERR_INVALID; }
   const CUtensorMapDataType dt = C::tf32 ? (C::nprod == 3 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32)
                                          : (C::f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
   CUtensorMap tA_hi, tA_hb, tA_lb, tB_hi, tB_hb, tB_lb;
-  // gathered operands: the tensor is the whole bank and the box is one row (gather4 fetches 4 of them)
+  // gathered operand A: no tensor map, the producer warps read the bank's operand planes through rowmap
   if (C::gather) {
     if (!g.rowmap || g.bank_rows <= 0) { set_error("gather variant without a rowmap"); return VV_ERR_INVALID; }
-    if (C::gather_a) a_outer = uint64_t(g.bank_rows); else b_outer = uint64_t(g.bank_rows);
+    if ((reinterpret_cast<uintptr_t>(g.A.hi) & 15) != 0 || (g.K % 8) != 0) { set_error("gathered operand must be 16-byte aligned with K % 8 == 0"); return VV_ERR_INVALID; }
   }
-  const uint32_t a_box = C::gather_a ? 1 : (C::a_mn ? C::bk : kBlockM);
+  const uint32_t a_box = C::a_mn ? C::bk : kBlockM;
   // K-major B: with 2-CTA clusters each CTA fetches (and multicasts) half of the tile's rows
-  const uint32_t b_box = C::gather_b ? 1 : (C::b_mn ? C::bk : C::block_n / C::cluster);
+  const uint32_t b_box = C::b_mn ? C::bk : C::block_n / C::cluster;
   const CUtensorMapSwizzle sw_a = (C::tf32 && C::a_mn) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
   const CUtensorMapSwizzle sw_b = (C::tf32 && C::b_mn) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
   int rc;
-  if ((rc = make_tmap(&tA_hi, g.A.hi, dt, C::elem_bytes, a_inner, a_outer, a_box, sw_a))) return rc;
   if ((rc = make_tmap(&tB_hi, g.B.hi, dt, C::elem_bytes, b_inner, b_outer, b_box, sw_b))) return rc;
+  if (C::gather) tA_hi = tB_hi;
+  else if ((rc = make_tmap(&tA_hi, g.A.hi, dt, C::elem_bytes, a_inner, a_outer, a_box, sw_a))) return rc;
   if (C::mixed) {
     // lo = two bf16 planes [bf16(x) | bf16(x - hi)], each the shape of the operand
     if (!g.A.lo || !g.B.lo) { set_error("TF32X3 needs the hi array and the two-plane bf16 lo array of every operand"); return VV_ERR_INVALID; }
@@ -523,14 +595,15 @@ int launch_cfg(const GemmProblem& g, cudaStream_t stream) {
     if ((rc = make_tmap(&tB_lb, b_planes + b_count, bf, 2, b_inner, b_outer, b_box, s16b, bbb))) return rc;
   } else if (C::split16) {
     if (!g.A.lo || !g.B.lo) { set_error("F16X3 needs the h0 and h1 planes of every operand"); return VV_ERR_INVALID; }
-    if ((rc = make_tmap(&tA_hb, g.A.lo, dt, C::elem_bytes, a_inner, a_outer, a_box, sw_a))) return rc;
     if ((rc = make_tmap(&tB_hb, g.B.lo, dt, C::elem_bytes, b_inner, b_outer, b_box, sw_b))) return rc;
+    if (C::gather) tA_hb = tB_hb;
+    else if ((rc = make_tmap(&tA_hb, g.A.lo, dt, C::elem_bytes, a_inner, a_outer, a_box, sw_a))) return rc;
     tA_lb = tA_hi; tB_lb = tB_hi;
   } else {
     tA_hb = tA_hi; tA_lb = tA_hi; tB_hb = tB_hi; tB_lb = tB_hi;
   }
   TcParams p;
-  p.d_rows = d_rows; p.d_cols = d_cols; p.ldd = d_cols;
+  p.d_rows = d_rows; p.d_cols = d_cols; p.ldd = C::trans_out ? g.K : d_cols;
   p.tiles_m = (d_rows + kBlockM - 1) / kBlockM;
   p.tiles_n = (d_cols + C::block_n - 1) / C::block_n;
   p.num_kb = (red + C::bk - 1) / C::bk;
@@ -550,6 +623,8 @@ int launch_cfg(const GemmProblem& g, cudaStream_t stream) {
   p.act_N = g.N;
   p.epi = g.epi;
   p.rowmap = g.rowmap;
+  p.ga0 = static_cast<const uint16_t*>(g.A.hi); p.ga1 = static_cast<const uint16_t*>(g.A.lo);
+  p.ga_pitch = g.K; p.ga_cols = g.K; p.rowmap_len = ((g.M + 127) / 128) * 128;
   static bool attr_set = false;
   if (!attr_set) {
     VV_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::smem_bytes));
@@ -584,38 +659,38 @@ bool gemm_tc_supported(const GemmProblem& g, const char** why) {
 int gemm_tc_launch(const GemmProblem& g, cudaStream_t stream) {
   const char* why = nullptr;
   if (!gemm_tc_supported(g, &why)) { set_error("%s (M=%d N=%d K=%d)", why, g.M, g.N, g.K); return VV_ERR_UNSUPPORTED; }
-  //                 tf32   A-MN   B-MN  nprod  BN  stages fwd-epilogue gather
+  //                 tf32   A-MN   B-MN  nprod  BN  stages fwd-epi gather f16  transposed-out
   const bool gat = g.rowmap != nullptr;
-  if (gat && g.kind == GEMM_DGRAD) { set_error("dgrad has no gathered operand"); return VV_ERR_INVALID; }
+  if (gat != (g.kind == GEMM_WGRAD_T) && g.kind != GEMM_FWD) { set_error("only FWD and WGRAD_T take a gathered operand"); return VV_ERR_INVALID; }
+  if (gat && g.prec != VV_PREC_BF16 && g.prec != VV_PREC_F16X3) {
+    set_error("the gather-fused variants are built for the 2-byte operand formats (bf16, f16x3)"); return VV_ERR_UNSUPPORTED;
+  }
   if (g.prec == VV_PREC_BF16) {
     switch (g.kind) {
-      case GEMM_FWD:   return gat ? launch_cfg<Cfg<false, false, false, 1, 256, 4, true,  true>>(g, stream)
-                                  : launch_cfg<Cfg<false, false, false, 1, 256, 4, true >>(g, stream);
-      case GEMM_WGRAD: return gat ? launch_cfg<Cfg<false, true,  true,  1, 256, 4, false, true>>(g, stream)
-                                  : launch_cfg<Cfg<false, true,  true,  1, 256, 4, false>>(g, stream);
-      default:         return launch_cfg<Cfg<false, false, true,  1, 256, 4, false>>(g, stream);
+      case GEMM_FWD:     return gat ? launch_cfg<Cfg<false, false, false, 1, 256, 4, true,  true>>(g, stream)
+                                    : launch_cfg<Cfg<false, false, false, 1, 256, 4, true >>(g, stream);
+      case GEMM_WGRAD:   return launch_cfg<Cfg<false, true,  true,  1, 256, 4, false>>(g, stream);
+      case GEMM_WGRAD_T: return launch_cfg<Cfg<false, true,  true,  1, 256, 4, false, true, false, true>>(g, stream);
+      default:           return launch_cfg<Cfg<false, false, true,  1, 256, 4, false>>(g, stream);
     }
   } else if (g.prec == VV_PREC_TF32) {
     switch (g.kind) {
-      case GEMM_FWD:   return gat ? launch_cfg<Cfg<true, false, false, 1, 256, 4, true,  true>>(g, stream)
-                                  : launch_cfg<Cfg<true, false, false, 1, 256, 4, true >>(g, stream);
-      case GEMM_WGRAD: return gat ? launch_cfg<Cfg<true, true,  true,  1, 256, 4, false, true>>(g, stream)
-                                  : launch_cfg<Cfg<true, true,  true,  1, 256, 4, false>>(g, stream);
+      case GEMM_FWD:   return launch_cfg<Cfg<true, false, false, 1, 256, 4, true >>(g, stream);
+      case GEMM_WGRAD: return launch_cfg<Cfg<true, true,  true,  1, 256, 4, false>>(g, stream);
       default:         return launch_cfg<Cfg<true, false, true,  1, 256, 4, false>>(g, stream);
     }
   } else if (g.prec == VV_PREC_F16X3) {
-    if (gat) { set_error("the gather-fused variants are built for bf16 / tf32 only"); return VV_ERR_UNSUPPORTED; }
     switch (g.kind) {
-      case GEMM_FWD:   return launch_cfg<Cfg<false, false, false, 3, 256, 2, true,  false, true>>(g, stream);
-      case GEMM_WGRAD: return launch_cfg<Cfg<false, true,  true,  3, 256, 2, false, false, true>>(g, stream);
-      default:         return launch_cfg<Cfg<false, false, true,  3, 256, 2, false, false, true>>(g, stream);
+      case GEMM_FWD:     return gat ? launch_cfg<Cfg<false, false, false, 3, 256, 2, true,  true,  true>>(g, stream)
+                                    : launch_cfg<Cfg<false, false, false, 3, 256, 2, true,  false, true>>(g, stream);
+      case GEMM_WGRAD:   return launch_cfg<Cfg<false, true,  true,  3, 256, 2, false, false, true>>(g, stream);
+      case GEMM_WGRAD_T: return launch_cfg<Cfg<false, true,  true,  3, 256, 2, false, true,  true, true>>(g, stream);
+      default:           return launch_cfg<Cfg<false, false, true,  3, 256, 2, false, false, true>>(g, stream);
     }
   } else {
     switch (g.kind) {
-      case GEMM_FWD:   if (gat) { set_error("the gather-fused variants are built for bf16 / tf32 only"); return VV_ERR_UNSUPPORTED; }
-                       return launch_cfg<Cfg<true, false, false, 3, 256, 2, true >>(g, stream);
-      case GEMM_WGRAD: if (gat) { set_error("the gather-fused variants are built for bf16 / tf32 only"); return VV_ERR_UNSUPPORTED; }
-                       return launch_cfg<Cfg<true, true,  true,  3, 256, 2, false>>(g, stream);
+      case GEMM_FWD:   return launch_cfg<Cfg<true, false, false, 3, 256, 2, true >>(g, stream);
+      case GEMM_WGRAD: return launch_cfg<Cfg<true, true,  true,  3, 256, 2, false>>(g, stream);
       default:         return launch_cfg<Cfg<true, false, true,  3, 256, 2, false>>(g, stream);
     }
   }
