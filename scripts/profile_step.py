@@ -6,7 +6,8 @@ from videovector_b200 import ops
 from videovector_b200._lib import DROPOUT_PHILOX
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--precision", default="tf32x3")
+ap.add_argument("--precision", default="f16x3")
+ap.add_argument("--materialised", action="store_true")
 ap.add_argument("--steps", type=int, default=4)
 ap.add_argument("--B", type=int, default=4096)
 ap.add_argument("--C", type=int, default=5)
@@ -21,6 +22,8 @@ vid, off, sid = ops.synthetic_videos(V, S)
 smp = ops.Sampler(vid, off, sid, B, C, Nn, 5000, 50, 6, 100, rand_seed=1)
 tr = ops.Trainer(ops.trainer_cfg(B, C, Nn, K, N, prec=a.precision, dropout_mode=DROPOUT_PHILOX))
 tr.set_weights(torch.randn(N, K, device="cuda") * 0.001, torch.zeros(N, device="cuda"))
+if a.precision in ("f16x3", "bf16") and not a.materialised:
+    tr.set_bank(bank)
 for it in range(a.steps):
     idx, quirk = smp.next()
     tr.step(bank, torch.as_tensor(idx).cuda(), torch.as_tensor(quirk).cuda(), None, it=it)

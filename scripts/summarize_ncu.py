@@ -47,11 +47,14 @@ if __name__ == "__main__":
     rnd = sys.argv[1] if len(sys.argv) > 1 else "r01"
     go = os.path.join(ROOT, "gpurun_out")
     pr = os.path.join(ROOT, "profiles")
-    for p in ("tf32x3", "bf16"):
+    for p in ("f16x3", "tf32x3", "bf16"):
         if os.path.exists(os.path.join(go, "launches_%s.csv" % p)):
             launches(os.path.join(go, "launches_%s.csv" % p), os.path.join(pr, "%s_launches_%s.txt" % (rnd, p)),
                      "launch list, `python scripts/profile_step.py --precision %s --steps 4` (B=4096, K=4096, N=512, C=5, Nn=10)" % p)
-    for rep, tag in (("prof_gemm_tf32x3", "fc7 forward + wgrad GEMMs, tf32x3"), ("prof_gemm_bf16", "fc7 forward + wgrad GEMMs, bf16"),
+    for rep, tag in (("prof_gemm_f16x3", "fc7 forward + transposed wgrad GEMMs, f16x3, gather fused (default path)"),
+                     ("prof_gemm_tf32x3", "fc7 forward + wgrad GEMMs, tf32x3"), ("prof_gemm_bf16", "fc7 forward + wgrad GEMMs, bf16, gather fused"),
+                     ("prof_stream_f16x3", "streaming kernels (gather plan, fused rank loss, update), f16x3 step"),
+                     ("prof_gather_f16x3", "K0 gather kernel (materialised path, --materialised), f16x3"),
                      ("prof_stream_tf32x3", "streaming kernels (gather, rank loss, update), tf32x3 step")):
         p = os.path.join(go, rep + ".ncu-rep")
         if os.path.exists(p):
