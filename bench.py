@@ -269,7 +269,6 @@ def run_gpu(args):
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        clk = clocks.stop()
         ms_total = e0.elapsed_time(e1)
         launches = tr.last_launches * args.steps
         loss_final = float(tr.tensor("loss").item())
@@ -328,6 +327,10 @@ def run_gpu(args):
         t1 = time.perf_counter()
         th.join(timeout=10)
         e2e_ms = 1e3 * (t1 - t0)
+        # one sampler over the timed `value` region, the per-kernel timing steps and the timed e2e region (all the same
+        # workload): a 100 ms poll would see nothing of a short --steps run otherwise; idle samples are filtered by power
+        clk = clocks.stop()
+        clk["window"] = "value + per-kernel + e2e legs"
 
     # max over ranks
     if world > 1:
@@ -368,11 +371,19 @@ def run_gpu(args):
                          "frac": by / (ms * 1e-3) / 1e9 / pk["hbm"] if ms > 0 else None}
         dom = "wgrad" if phase["wgrad"] >= phase["fc7_forward"] else "fc7_forward"
         ach = kern[dom]["achieved_tflops"]
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
+            key = prec + ("_gathered" if fused_gather_on(args) else "")
+            traffic = json.load(open(tpath)).get(key, {}).get(dom)
         roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": tensor_peak, "unit": "TFLOP/s",
-                    "frac": ach / tensor_peak if ach else None, "traffic": None,
+                    "frac": ach / tensor_peak if ach else None, "traffic": traffic,
                     "peak_source": pk["src"] + " (cuBLAS bf16, sustained)",
                     "mma_units_per_product": units,
                     "tensor_pipe_frac": ach * units / tensor_peak if ach else None,
+                    "peak_burst": pk.get("bf16"),
+                    "tensor_pipe_frac_of_burst": (ach * units / pk["bf16"]) if (ach and pk.get("bf16")) else None,
                     "note": "achieved = algorithmic 2*M*N*K per launch / mean launch duration (CUDA events around the kernel "
                             "inside the step), against the measured full-rate 16-bit tensor peak.  The fp32-parity modes "
                             "spend several tensor-core products per algorithmic product (mma_units_per_product, in units "

@@ -24,6 +24,27 @@ def summarize(rep, out, tag):
                     f.write("  %-72s %s %s\n" % (w, r[i], units[i]))
 
 
+def traffic(rep):
+    """{fc7_forward|wgrad: dram bytes read+write per launch} from a GEMM capture (forward = the fwd-epilogue template flag)."""
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rows[0], rows[1]
+    out = {}
+    mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for r in rows[2:]:
+        name = r[hdr.index("Kernel Name")]
+        if "gemm_tc_kernel" not in name:
+            continue
+        args = name[name.index("Cfg<") + 4:].split(">")[0].replace("(bool)", "").replace("(int)", "").split(",")
+        key = "fc7_forward" if args[6].strip() == "1" else "wgrad"
+        tot = 0.0
+        for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = hdr.index(m)
+            tot += float(r[i].replace(",", "")) * mult.get(units[i], 1.0)
+        out[key] = tot
+    return out
+
+
 def launches(src, out, tag):
     rows = [r for r in csv.reader(open(src)) if len(r) > 10]
     hdr = rows[0]
@@ -51,6 +72,14 @@ if __name__ == "__main__":
         if os.path.exists(os.path.join(go, "launches_%s.csv" % p)):
             launches(os.path.join(go, "launches_%s.csv" % p), os.path.join(pr, "%s_launches_%s.txt" % (rnd, p)),
                      "launch list, `python scripts/profile_step.py --precision %s --steps 4` (B=4096, K=4096, N=512, C=5, Nn=10)" % p)
+    tr = {}
+    for key, rep in (("f16x3_gathered", "prof_gemm_f16x3"), ("bf16_gathered", "prof_gemm_bf16")):
+        p = os.path.join(go, rep + ".ncu-rep")
+        if os.path.exists(p):
+            tr[key] = traffic(p)
+    if tr:
+        import json
+        json.dump(tr, open(os.path.join(pr, "traffic.json"), "w"), indent=1)
     for rep, tag in (("prof_gemm_f16x3", "fc7 forward + transposed wgrad GEMMs, f16x3, gather fused (default path)"),
                      ("prof_gemm_tf32x3", "fc7 forward + wgrad GEMMs, tf32x3"), ("prof_gemm_bf16", "fc7 forward + wgrad GEMMs, bf16, gather fused"),
                      ("prof_stream_f16x3", "streaming kernels (gather plan, fused rank loss, update), f16x3 step"),
