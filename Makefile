@@ -13,7 +13,7 @@ CU_SRCS   := $(wildcard videovector_b200/csrc/*.cu) $(wildcard videovector_b200/
 CPP_SRCS  := $(wildcard videovector_b200/csrc/host/*.cpp) $(wildcard videovector_b200/csrc/host/caffe_compat/*.cpp)
 CU_OBJS   := $(patsubst %.cu,$(OBJDIR)/%.o,$(CU_SRCS))
 CPP_OBJS  := $(patsubst %.cpp,$(OBJDIR)/%.o,$(CPP_SRCS))
-HDRS      := include/vv_b200.h $(wildcard videovector_b200/csrc/host/caffe_compat/caffe/*.hpp) $(wildcard videovector_b200/csrc/host/caffe_compat/caffe/proto/*.hpp) $(wildcard videovector_b200/csrc/*.cuh) $(wildcard videovector_b200/csrc/host/*.h) $(wildcard videovector_b200/csrc/host/*.hpp)
+HDRS      := include/vv_b200.h $(wildcard videovector_b200/csrc/host/caffe_compat/caffe/proto/*.inc) $(wildcard videovector_b200/csrc/host/caffe_compat/caffe/*.hpp) $(wildcard videovector_b200/csrc/host/caffe_compat/caffe/proto/*.hpp) $(wildcard videovector_b200/csrc/*.cuh) $(wildcard videovector_b200/csrc/host/*.h) $(wildcard videovector_b200/csrc/host/*.hpp)
 
 all: $(LIBDIR)/libvv_b200.so build/vv_caffe
 

@@ -11,7 +11,7 @@ from videovector_b200._lib import DROPOUT_MASK01
 rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-prec = sys.argv[1] if len(sys.argv) > 1 else "tf32x3"
+prec = sys.argv[1] if len(sys.argv) > 1 else "f16x3"
 B, C, Nn, K, N = 64, 5, 10, 1024, 256          # per rank
 R = C + Nn
 V, S = 128, 24

@@ -151,3 +151,112 @@ def test_cli_train_log_format(tmp_path):
     solp.write_text(prototxt.solver(str(netp), display=1, max_iter=1).replace("solver_mode: GPU", "solver_mode: CPU"))
     r = subprocess.run([exe, "train", "--solver=%s" % solp], capture_output=True, text=True, timeout=120)
     assert r.returncode != 0 and "no CPU fallback" in r.stderr
+
+
+# ---- .caffemodel / .solverstate ---------------------------------------------------------------
+@pytest.mark.parametrize("fuse", [False, True])
+def test_snapshot_restore_roundtrip(tmp_path, monkeypatch, fuse):
+    """Solver::Snapshot writes <prefix>_iter_N.caffemodel/.solverstate that (a) the real protobuf runtime parses as the
+    reference's NetParameter / SolverState, (b) a fresh solver restores: weights, momentum history and iter continue
+    (ref: solver.cpp:320-341, 418-429; net.cpp:692-727)."""
+    from test_caffemodel_io import _classes
+    monkeypatch.setenv("VV_FUSE", "1" if fuse else "0")
+    W0, b0, mask, mask_dev = problem()
+    N, K = CFG["N"], CFG["K"]
+    caffe_host.set_device(0); caffe_host.set_precision("f16x3")
+    prefix = str(tmp_path / "snap" / "videovec")
+    os.makedirs(os.path.dirname(prefix))
+    sol = caffe_host.Solver(prototxt.solver(base_lr=0.05, display=0, snapshot=0, snapshot_prefix=prefix), prototxt.train_net(**CFG))
+    sol.net.set_param(0, W0); sol.net.set_param(1, b0); sol.net.set_dropout_mask(mask_dev)
+    for _ in range(3):
+        sol.step()
+    model = sol.snapshot()
+    assert model == prefix + "_iter_3.caffemodel" and os.path.exists(model) and os.path.exists(prefix + "_iter_3.solverstate")
+    W3, b3, hW3, hb3 = sol.net.param(0), sol.net.param(1), sol.history(0), sol.history(1)
+    assert np.abs(hW3).max() > 0
+    # (a) the reference's own schema, real protobuf runtime
+    get = _classes()
+    net = get("NetParameter")(); net.ParseFromString(open(model, "rb").read())
+    fc7 = [l for l in net.layers if l.name == "fc7"][0]
+    assert fc7.type == 14 and len(fc7.blobs) == 2 and fc7.inner_product_param.num_output == N
+    assert (fc7.blobs[0].num, fc7.blobs[0].channels, fc7.blobs[0].height, fc7.blobs[0].width) == (1, 1, N, K)
+    assert (fc7.blobs[1].num, fc7.blobs[1].channels, fc7.blobs[1].height, fc7.blobs[1].width) == (1, 1, 1, N)
+    assert np.array_equal(np.array(fc7.blobs[0].data, np.float32), W3) and np.array_equal(np.array(fc7.blobs[1].data, np.float32), b3)
+    assert len(fc7.blobs[0].diff) == 0                                      # snapshot_diff defaults to false
+    assert [l.name for l in net.layers] == sol.net.layer_names              # every layer is listed, split layers included
+    st = get("SolverState")(); st.ParseFromString(open(prefix + "_iter_3.solverstate", "rb").read())
+    assert st.iter == 3 and st.learned_net == model and len(st.history) == 2
+    assert np.array_equal(np.array(st.history[0].data, np.float32), hW3) and np.array_equal(np.array(st.history[1].data, np.float32), hb3)
+    # (b) a fresh solver picks everything up
+    sol2 = caffe_host.Solver(prototxt.solver(base_lr=0.05, display=0, snapshot=0), prototxt.train_net(**CFG))
+    sol2.net.set_dropout_mask(mask_dev)
+    sol2.restore(prefix + "_iter_3.solverstate")
+    assert sol2.iter == 3 and abs(sol2.learning_rate() - sol.learning_rate()) < 1e-12
+    assert np.array_equal(sol2.net.param(0), W3) and np.array_equal(sol2.net.param(1), b3)
+    l2 = sol2.step()
+    assert np.isfinite(l2) and sol2.iter == 4
+    # the restored momentum took part in the first step after the restore: W4 - W3 = -(momentum * h3 + rate * grad)
+    step = sol2.net.param(0) - W3
+    assert rel(sol2.history(0), -step) < 1e-6
+    assert np.abs(sol2.history(0) - 0.9 * hW3).max() < np.abs(sol2.history(0)).max()      # history carried, not restarted from 0
+    # restoring into a net whose fused trainer already exists also lands in the trainer's buffers
+    sol2.restore(prefix + "_iter_3.solverstate")
+    assert sol2.iter == 3 and np.array_equal(sol2.net.param(0), W3) and np.array_equal(sol2.history(0), hW3)
+    sol2.step()
+    sol.close(); sol2.close()
+
+
+def test_copy_trained_layers_semantics(tmp_path):
+    """Net::CopyTrainedLayersFrom: layers matched by name, unknown source layers ignored, shape mismatch fatal
+    (ref: net.cpp:692-722)."""
+    caffe_host.set_device(0); caffe_host.set_precision("f16x3")
+    N, K = CFG["N"], CFG["K"]
+    rng = np.random.RandomState(5)
+    W = rng.normal(0, 0.02, (N, K)).astype(np.float32); b = rng.normal(0, 0.01, N).astype(np.float32)
+    good = tmp_path / "good.caffemodel"
+    caffe_host.write_binary_proto(good, "NetParameter",
+        'name: "x"\nlayers { name: "somebody_elses_conv" type: CONVOLUTION blobs { num: 1 channels: 1 height: 1 width: 2 } }\n'
+        'layers { name: "fc7" type: INNER_PRODUCT blobs { num: 1 channels: 1 height: %d width: %d } blobs { num: 1 channels: 1 height: 1 width: %d } }\n' % (N, K, N),
+        {"layers[0].blobs[0].data": np.zeros(2, np.float32), "layers[1].blobs[0].data": W, "layers[1].blobs[1].data": b})
+    net = caffe_host.Net(prototxt.train_net(**CFG))
+    net.copy_trained_from(good)
+    assert np.array_equal(net.param(0), W.reshape(-1)) and np.array_equal(net.param(1), b)
+    out = tmp_path / "resaved.caffemodel"
+    net.save(out, write_diff=True)
+    _, arrays = caffe_host.read_binary_proto(out, "NetParameter")
+    keys = sorted(arrays)
+    assert len(keys) == 4 and all(".blobs[" in k for k in keys) and sum(k.endswith(".diff") for k in keys) == 2
+    bad = tmp_path / "bad.caffemodel"
+    caffe_host.write_binary_proto(bad, "NetParameter",
+        'layers { name: "fc7" type: INNER_PRODUCT blobs { num: 1 channels: 1 height: %d width: %d } blobs { num: 1 channels: 1 height: 1 width: %d } }\n' % (N + 1, K, N),
+        {"layers[0].blobs[0].data": np.zeros((N + 1) * K, np.float32), "layers[0].blobs[1].data": b})
+    with pytest.raises(Exception):
+        net.copy_trained_from(bad)
+    net.close()
+
+
+def test_cli_snapshot_and_resume(tmp_path):
+    """`vv_caffe train` honours snapshot / snapshot_prefix / snapshot_after_train and --snapshot / --weights
+    (ref: solver.cpp:180-184, 225-227; tools/caffe.cpp:106-118)."""
+    exe = os.path.join(ROOT, "build", "vv_caffe")
+    netp = tmp_path / "net.prototxt"; solp = tmp_path / "solver.prototxt"
+    prefix = str(tmp_path / "vv")
+    netp.write_text(prototxt.train_net(**CFG))
+    solp.write_text(prototxt.solver(str(netp), display=1, max_iter=4, snapshot=2, snapshot_prefix=prefix))
+    r = subprocess.run([exe, "train", "--solver=%s" % solp], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    for it in (2, 4):                                  # periodic at iter 2, final after training at iter 4
+        assert os.path.exists("%s_iter_%d.caffemodel" % (prefix, it)) and os.path.exists("%s_iter_%d.solverstate" % (prefix, it))
+    assert not os.path.exists(prefix + "_iter_0.caffemodel")
+    text, arrays = caffe_host.read_binary_proto(prefix + "_iter_4.solverstate", "SolverState")
+    assert "iter: 4" in text and len(arrays) == 2
+    solp.write_text(prototxt.solver(str(netp), display=1, max_iter=6, snapshot=0, snapshot_prefix=prefix))
+    r = subprocess.run([exe, "train", "--solver=%s" % solp, "--snapshot=%s_iter_4.solverstate" % prefix], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert "Resuming from" in r.stderr and "Iteration 4, loss = " in r.stderr and "Iteration 5, lr = " in r.stderr
+    assert "Iteration 0, loss" not in r.stderr and os.path.exists(prefix + "_iter_6.caffemodel")
+    r = subprocess.run([exe, "train", "--solver=%s" % solp, "--weights=%s_iter_4.caffemodel" % prefix, "--iterations=1"],
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "Finetuning from" in r.stderr and "Iteration 0, loss" in r.stderr
+    r = subprocess.run([exe, "train", "--solver=%s" % solp, "--weights=a", "--snapshot=b"], capture_output=True, text=True, timeout=120)
+    assert r.returncode != 0 and "not both" in r.stderr

@@ -1,6 +1,6 @@
 // vv_caffe -- the `caffe train` / `caffe time` entry points for this path (ref: tools/caffe.cpp:80-122 train,
 // :194-266 time) on the caffe_compat host.  Usage:
-//   vv_caffe train --solver=solver.prototxt [--gpu=0] [--iterations=N]
+//   vv_caffe train --solver=solver.prototxt [--snapshot=x.solverstate | --weights=x.caffemodel] [--gpu=0] [--iterations=N]
 //   vv_caffe time  --model=net.prototxt [--iterations=50] [--gpu=0]
 // Environment: VV_PRECISION=tf32x3|f16x3|tf32|bf16|fp32_simt, VV_FUSE=0 to run layer by layer.
 #include <chrono>
@@ -25,9 +25,14 @@ static int train(int argc, char** argv) {
   Caffe::set_mode(Caffe::GPU);
   shared_ptr<Solver<float> > solver(GetSolver<float>(sp));
   const int iters = atoi(flag(argc, argv, "iterations", "-1").c_str());
+  // ref: tools/caffe.cpp:106-118 -- resume from a .solverstate, or finetune from a .caffemodel
+  const string snapshot = flag(argc, argv, "snapshot", ""), weights = flag(argc, argv, "weights", "");
+  CHECK(snapshot.empty() || weights.empty()) << "Give a snapshot to resume training or weights to finetune but not both.";
+  if (!weights.empty()) { fprintf(stderr, "Finetuning from %s\n", weights.c_str()); solver->net()->CopyTrainedLayersFrom(weights); }
+  if (!snapshot.empty()) fprintf(stderr, "Resuming from %s\n", snapshot.c_str());
   fprintf(stderr, "Starting Optimization (%s)\n", solver->net()->fused() ? "fused kernel sequence" : "layer by layer");
   const auto t0 = std::chrono::steady_clock::now();
-  solver->Solve(iters);
+  solver->Solve(iters, snapshot.empty() ? nullptr : snapshot.c_str());
   vvc_device_synchronize();
   const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   fprintf(stderr, "Optimization Done: %d iterations in %.3f s\n", solver->iter(), sec);

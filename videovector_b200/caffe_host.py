@@ -40,6 +40,18 @@ def _l():
     lib.vvc_solver_history_read.argtypes = [_P, C.c_int, _P]
     lib.vvc_transform_net.argtypes = [C.c_char_p, C.c_int, _P, C.c_int]
     lib.vvc_set_stream.argtypes = [_P]
+    lib.vvc_net_save.argtypes = [_P, C.c_char_p, C.c_int]
+    lib.vvc_net_copy_trained_from.argtypes = [_P, C.c_char_p]
+    lib.vvc_solver_snapshot.argtypes = [_P, _P, C.c_int]
+    lib.vvc_solver_restore.argtypes = [_P, C.c_char_p]
+    lib.vvc_solver_solve_resume.argtypes = [_P, C.c_int, C.c_char_p]
+    lib.vvc_pb_open.restype = _P; lib.vvc_pb_open.argtypes = [C.c_char_p, C.c_char_p]
+    lib.vvc_pb_close.argtypes = [_P]; lib.vvc_pb_close.restype = None
+    lib.vvc_pb_text.argtypes = [_P, _P, C.c_int]
+    lib.vvc_pb_num_arrays.argtypes = [_P]
+    lib.vvc_pb_array_info.argtypes = [_P, C.c_int, _P, C.c_int]
+    lib.vvc_pb_array_read.argtypes = [_P, C.c_int, _P]
+    lib.vvc_pb_write.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, _P, _P, _P]
     lib._vvc_ready = True
     return lib
 
@@ -138,6 +150,13 @@ class Net:
         _check(self._lib.vvc_net_forward(self._h, C.byref(loss)))
         return loss.value
 
+    def save(self, path, write_diff=False):
+        """Net::ToProto + WriteProtoToBinaryFile: a .caffemodel the reference's CopyTrainedLayersFrom loads."""
+        _check(self._lib.vvc_net_save(self._h, str(path).encode(), int(write_diff)))
+
+    def copy_trained_from(self, path):
+        _check(self._lib.vvc_net_copy_trained_from(self._h, str(path).encode()))
+
     def close(self):
         if self._h and self._own:
             self._lib.vvc_net_destroy(self._h)
@@ -163,8 +182,20 @@ class Solver:
         _check(self._lib.vvc_solver_step(self._h, C.byref(loss)))
         return loss.value
 
-    def solve(self, max_iter):
-        _check(self._lib.vvc_solver_solve(self._h, max_iter))
+    def solve(self, max_iter, resume=None):
+        if resume is None:
+            _check(self._lib.vvc_solver_solve(self._h, max_iter))
+        else:
+            _check(self._lib.vvc_solver_solve_resume(self._h, max_iter, str(resume).encode()))
+
+    def snapshot(self):
+        """Solver::Snapshot: writes <snapshot_prefix>_iter_N.caffemodel / .solverstate, returns the model path."""
+        buf = C.create_string_buffer(1024)
+        _check(self._lib.vvc_solver_snapshot(self._h, buf, 1024))
+        return buf.value.decode()
+
+    def restore(self, state_path):
+        _check(self._lib.vvc_solver_restore(self._h, str(state_path).encode()))
 
     @property
     def iter(self):
@@ -188,3 +219,37 @@ class Solver:
             self.close()
         except Exception:
             pass
+
+
+# ---- binary protobuf files (.caffemodel = NetParameter, .solverstate = SolverState), host only ----------------------
+def read_binary_proto(path, type_name):
+    """Returns (text-format string of the message without float arrays, {dotted path: float32 array})."""
+    lib = _l()
+    h = lib.vvc_pb_open(str(path).encode(), type_name.encode())
+    if not h:
+        raise VVError("caffe host: " + lib.vvc_last_error().decode())
+    try:
+        buf = C.create_string_buffer(1 << 22)
+        _check(lib.vvc_pb_text(h, buf, len(buf)))
+        arrays = {}
+        for i in range(lib.vvc_pb_num_arrays(h)):
+            name = C.create_string_buffer(512)
+            n = _check(lib.vvc_pb_array_info(h, i, name, 512))
+            a = np.empty(n, np.float32)
+            _check(lib.vvc_pb_array_read(h, i, a.ctypes.data))
+            arrays[name.value.decode()] = a
+        return buf.value.decode(), arrays
+    finally:
+        lib.vvc_pb_close(h)
+
+
+def write_binary_proto(path, type_name, text, arrays=None):
+    """Writes message `type_name` from text format plus float arrays keyed by dotted path ("layers[0].blobs[1].data")."""
+    lib = _l()
+    arrays = arrays or {}
+    keys = list(arrays.keys())
+    vals = [np.ascontiguousarray(arrays[k], np.float32).reshape(-1) for k in keys]
+    kp = (C.c_char_p * len(keys))(*[k.encode() for k in keys])
+    vp = (C.c_void_p * len(keys))(*[v.ctypes.data for v in vals])
+    cn = (C.c_int * len(keys))(*[v.size for v in vals])
+    _check(lib.vvc_pb_write(str(path).encode(), type_name.encode(), text.encode(), len(keys), kp, vp, cn))

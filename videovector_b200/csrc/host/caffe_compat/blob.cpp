@@ -16,6 +16,34 @@ Caffe::Caffe() : mode_(GPU), phase_(TRAIN), stream_(nullptr), seed_(1701), draws
     else LOG_FATAL << "VV_PRECISION must be fp32_simt|tf32x3|f16x3|tf32|bf16, got " << v;
   }
 }
+}  // namespace caffe
+#include "caffe/proto/caffe_params.hpp"
+namespace caffe {
+template <typename Dtype>
+void Blob<Dtype>::FromProto(const PbMsg& proto) {
+  Reshape(int(proto.num("num", 0)), int(proto.num("channels", 0)), int(proto.num("height", 0)), int(proto.num("width", 0)));
+  const PbField* d = proto.nth("data", 0);
+  CHECK(d && d->floats && int(d->floats->size()) == count_) << "BlobProto data has " << (d && d->floats ? d->floats->size() : 0) << " values, shape needs " << count_;
+  memcpy(mutable_cpu_data(), d->floats->data(), sizeof(Dtype) * count_);
+  const PbField* g = proto.nth("diff", 0);
+  if (g && g->floats && !g->floats->empty()) {
+    CHECK_EQ(int(g->floats->size()), count_);
+    memcpy(mutable_cpu_diff(), g->floats->data(), sizeof(Dtype) * count_);
+  }
+}
+template <typename Dtype>
+void Blob<Dtype>::ToProto(PbMsg* proto, bool write_diff) const {
+  proto->fields.clear();
+  proto->add_scalar("num", std::to_string(num_)); proto->add_scalar("channels", std::to_string(channels_));
+  proto->add_scalar("height", std::to_string(height_)); proto->add_scalar("width", std::to_string(width_));
+  auto data = std::make_shared<vector<float> >(cpu_data(), cpu_data() + count_);
+  proto->fields.push_back(PbField{"data", "", nullptr, data});
+  if (write_diff) {
+    auto diff = std::make_shared<vector<float> >(cpu_diff(), cpu_diff() + count_);
+    proto->fields.push_back(PbField{"diff", "", nullptr, diff});
+  }
+}
+
 Caffe& Caffe::Get() { static Caffe c; return c; }
 void Caffe::SetDevice(int device_id) { CUDA_CHECK(cudaSetDevice(device_id)); VV_CHECK(vv_device_check()); }
 

@@ -56,6 +56,9 @@ class Blob {
   void ShareData(const Blob& other) { CHECK_EQ(count_, other.count()); data_ = other.data_; }
   void ShareDiff(const Blob& other) { CHECK_EQ(count_, other.count()); diff_ = other.diff_; }
   void CopyFrom(const Blob<Dtype>& source, bool copy_diff = false, bool reshape = false);
+  // (de)serialisation as a BlobProto message tree (ref: blob.cpp:243-256, 305-322)
+  void FromProto(const class PbMsg& proto);
+  void ToProto(class PbMsg* proto, bool write_diff = false) const;
   Dtype asum_data() const;
   Dtype asum_diff() const;
   const shared_ptr<SyncedMemory>& data() const { return data_; }

@@ -51,6 +51,13 @@ class Net {
   bool has_layer(const string& layer_name) { return layer_names_index_.count(layer_name) > 0; }
   const shared_ptr<Layer<Dtype> > layer_by_name(const string& layer_name);
 
+  // ---- trained-parameter IO (ref: net.cpp:692-801) ----
+  // NetParameter message tree: name + every layer's parameter message + its blobs (data, optionally diff)
+  shared_ptr<PbMsg> ToProto(bool write_diff = false) const;
+  // copies blobs into layers of the same name; unknown source layers are ignored, shapes must match exactly
+  void CopyTrainedLayersFrom(const PbMsg& net_param);
+  void CopyTrainedLayersFrom(const string& trained_filename);
+
   // ---- fusion ----
   // Returns true if the graph matched and the fused path is active.  `why` receives the reason if not.
   bool EnableFusion(string* why = nullptr);
@@ -58,6 +65,8 @@ class Net {
   vv_trainer_t* trainer() { return trainer_; }
   // fused step used by the solver: forward, backward and (optionally) the SGD update in one kernel sequence
   Dtype FusedStep(int iter, bool do_update, const vv_trainer_cfg_t* solver_cfg);
+  // first use of the fused path: builds the trainer with the solver constants and hands the parameters over
+  void CreateTrainer(const vv_trainer_cfg_t* solver_cfg);
   void set_fixed_dropout_mask(const uint32_t* device_mask01) { fixed_mask_ = device_mask01; }
 
  protected:

@@ -10,7 +10,8 @@
 namespace caffe {
 
 class PbMsg;
-struct PbField { string key; string scalar; shared_ptr<PbMsg> msg; };
+// `floats`: a packed repeated float field (BlobProto.data / .diff) kept as one array instead of one scalar per element
+struct PbField { string key; string scalar; shared_ptr<PbMsg> msg; shared_ptr<vector<float> > floats; };
 class PbMsg {
  public:
   vector<PbField> fields;
@@ -28,6 +29,14 @@ class PbMsg {
 shared_ptr<PbMsg> ParseTextFormat(const string& text);
 string PrintTextFormat(const PbMsg& m);
 string ReadFileOrDie(const string& path);
+
+// protobuf *binary* wire format for the reference's message types (ref: util/io.cpp:49-67 Read/WriteProtoFrom/ToBinaryFile;
+// schema = caffe/proto/caffe_schema.inc).  `type` names the root message ("NetParameter", "SolverState", "BlobProto" ...).
+// Fields are written in field-number order (repeated ones in stored order), enums by number, unknown fields skipped on read.
+string SerializeBinary(const PbMsg& m, const string& type);
+shared_ptr<PbMsg> ParseBinary(const string& bytes, const string& type);
+void WriteProtoToBinaryFile(const PbMsg& m, const string& type, const string& path);
+shared_ptr<PbMsg> ReadProtoFromBinaryFile(const string& path, const string& type);
 
 enum LayerParameter_LayerType {   // values as in caffe.proto:236-302
   LayerParameter_LayerType_NONE = 0, LayerParameter_LayerType_CONCAT = 3, LayerParameter_LayerType_DROPOUT = 6,
@@ -160,6 +169,8 @@ struct SolverParameter : ParamBase {
   int display() const { return int(m->num("display", 0)); }
   int snapshot() const { return int(m->num("snapshot", 0)); }
   string snapshot_prefix() const { return m->str("snapshot_prefix", ""); }
+  bool snapshot_diff() const { return m->boolean("snapshot_diff", false); }
+  bool snapshot_after_train() const { return m->boolean("snapshot_after_train", true); }
   long random_seed() const { return long(m->num("random_seed", -1)); }
   int test_interval() const { return int(m->num("test_interval", 0)); }
   string solver_mode() const { return m->str("solver_mode", "GPU"); }

@@ -11,7 +11,11 @@ class Solver {
   explicit Solver(const SolverParameter& param) : param_(param), iter_(0) { Init(param); }
   virtual ~Solver() {}
   void Init(const SolverParameter& param);
-  virtual void Solve(int max_iter = -1);
+  // resume_file: a .solverstate to continue from (ref: solver.cpp:160-172)
+  virtual void Solve(int max_iter = -1, const char* resume_file = nullptr);
+  // <snapshot_prefix>_iter_N.caffemodel + .solverstate (ref: solver.cpp:320-341); returns the model file name
+  string Snapshot();
+  void Restore(const char* state_file);                       // ref: solver.cpp:418-429
   // one iteration: ForwardBackward + ComputeUpdateValue + Update (fused into one kernel sequence when the net is fused)
   Dtype Step();
   inline shared_ptr<Net<Dtype> > net() { return net_; }
@@ -21,6 +25,8 @@ class Solver {
   virtual void PreSolve() {}
   virtual void ComputeUpdateValue() = 0;
   virtual void FillFusedSolverCfg(vv_trainer_cfg_t* cfg) = 0;
+  virtual void SnapshotSolverState(PbMsg* state) = 0;
+  virtual void RestoreSolverState(const PbMsg& state) = 0;
   SolverParameter param_;
   int iter_;
   shared_ptr<Net<Dtype> > net_;
@@ -37,6 +43,9 @@ class SGDSolver : public Solver<Dtype> {
   virtual void PreSolve();
   virtual void ComputeUpdateValue();
   virtual void FillFusedSolverCfg(vv_trainer_cfg_t* cfg);
+  virtual void SnapshotSolverState(PbMsg* state);             // ref: solver.cpp:576-596
+  virtual void RestoreSolverState(const PbMsg& state);
+  bool history_aliased_ = false;
   vector<shared_ptr<Blob<Dtype> > > history_, update_, temp_;
 };
 

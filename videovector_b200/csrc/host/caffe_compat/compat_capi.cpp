@@ -2,6 +2,7 @@
 // run it layer by layer or fused, read blobs by name.  Errors (failed CHECKs) come back as -1 + message.
 #include <cuda_runtime_api.h>
 #include <cstring>
+#include <map>
 #include "caffe/solver.hpp"
 
 using namespace caffe;
@@ -97,12 +98,96 @@ void vvc_solver_destroy(void* s) { delete static_cast<Solver<float>*>(s); }
 void* vvc_solver_net(void* s) { return static_cast<Solver<float>*>(s)->net().get(); }
 int vvc_solver_step(void* s, float* loss) { GUARD(*loss = static_cast<Solver<float>*>(s)->Step(); cudaDeviceSynchronize(); return 0;) }
 int vvc_solver_solve(void* s, int max_iter) { GUARD(static_cast<Solver<float>*>(s)->Solve(max_iter); cudaDeviceSynchronize(); return 0;) }
+int vvc_solver_solve_resume(void* s, int max_iter, const char* state_path) {
+  GUARD(static_cast<Solver<float>*>(s)->Solve(max_iter, state_path); cudaDeviceSynchronize(); return 0;)
+}
 int vvc_solver_iter(void* s) { return static_cast<Solver<float>*>(s)->iter(); }
 int vvc_solver_history_read(void* s, int i, float* out) {
   GUARD(auto* sg = dynamic_cast<SGDSolver<float>*>(static_cast<Solver<float>*>(s)); CHECK(sg);
         CHECK_LT(i, int(sg->history().size())) << "history is allocated by the first step";
         memcpy(out, sg->history()[i]->cpu_data(), sizeof(float) * sg->history()[i]->count()); return 0;)
 }
+// ---- trained-parameter IO: .caffemodel / .solverstate (binary protobuf, caffe_compat/wire.cpp) ----------------------
+int vvc_net_save(void* n, const char* path, int write_diff) {
+  GUARD(WriteProtoToBinaryFile(*static_cast<Net<float>*>(n)->ToProto(write_diff != 0), "NetParameter", path); return 0;)
+}
+int vvc_net_copy_trained_from(void* n, const char* path) { GUARD(static_cast<Net<float>*>(n)->CopyTrainedLayersFrom(string(path)); return 0;) }
+int vvc_solver_snapshot(void* s, char* model_path_out, int cap) {
+  GUARD(const string m = static_cast<Solver<float>*>(s)->Snapshot();
+        if (model_path_out && cap > 0) { strncpy(model_path_out, m.c_str(), cap - 1); model_path_out[cap - 1] = 0; }
+        return 0;)
+}
+int vvc_solver_restore(void* s, const char* state_path) { GUARD(static_cast<Solver<float>*>(s)->Restore(state_path); cudaDeviceSynchronize(); return 0;) }
+
+// Generic access to a binary message file for tests and tools (no device needed):
+//   open -> handle; text = the message in text format without the float arrays; blobs = every packed float array in
+//   document order with the dotted path of its owner ("layers[3].blobs[0].data", "history[1].data").
+struct PbFile { shared_ptr<PbMsg> root; string type; vector<std::pair<string, shared_ptr<vector<float> > > > arrays; };
+static void collect_arrays(const PbMsg& m, const string& prefix, PbFile* f) {
+  std::map<string, int> seen;
+  for (const PbField& fld : m.fields) {
+    const int k = seen[fld.key]++;
+    const string here = prefix + (prefix.empty() ? "" : ".") + fld.key;
+    if (fld.floats) f->arrays.push_back(std::make_pair(here, fld.floats));
+    else if (fld.msg) collect_arrays(*fld.msg, here + "[" + std::to_string(k) + "]", f);
+  }
+}
+static shared_ptr<PbMsg> strip_arrays(const PbMsg& m) {
+  auto out = std::make_shared<PbMsg>();
+  for (const PbField& fld : m.fields) {
+    if (fld.floats) continue;
+    out->fields.push_back(PbField{fld.key, fld.scalar, fld.msg ? strip_arrays(*fld.msg) : nullptr, nullptr});
+  }
+  return out;
+}
+void* vvc_pb_open(const char* path, const char* type) {
+  GUARDP(PbFile* f = new PbFile; f->type = type; f->root = ReadProtoFromBinaryFile(path, type); collect_arrays(*f->root, "", f); return f;)
+}
+void vvc_pb_close(void* h) { delete static_cast<PbFile*>(h); }
+int vvc_pb_text(void* h, char* out, int cap) {
+  GUARD(const string s = PrintTextFormat(*strip_arrays(*static_cast<PbFile*>(h)->root));
+        CHECK_LT(int(s.size()), cap) << "output buffer too small"; memcpy(out, s.c_str(), s.size() + 1); return int(s.size());)
+}
+int vvc_pb_num_arrays(void* h) { return int(static_cast<PbFile*>(h)->arrays.size()); }
+int vvc_pb_array_info(void* h, int i, char* path_out, int cap) {
+  GUARD(PbFile* f = static_cast<PbFile*>(h); CHECK_LT(i, int(f->arrays.size()));
+        strncpy(path_out, f->arrays[i].first.c_str(), cap - 1); path_out[cap - 1] = 0; return int(f->arrays[i].second->size());)
+}
+int vvc_pb_array_read(void* h, int i, float* out) {
+  GUARD(PbFile* f = static_cast<PbFile*>(h); CHECK_LT(i, int(f->arrays.size()));
+        memcpy(out, f->arrays[i].second->data(), sizeof(float) * f->arrays[i].second->size()); return 0;)
+}
+// Writes message `type` from its text form plus float arrays attached by dotted path (the parent message must exist in the text).
+int vvc_pb_write(const char* path, const char* type, const char* text, int n_arrays, const char** array_paths,
+                 const float** arrays, const int* counts) {
+  GUARD(
+    shared_ptr<PbMsg> root = ParseTextFormat(text);
+    for (int a = 0; a < n_arrays; ++a) {
+      // walk "layers[3].blobs[0].data"
+      PbMsg* cur = root.get();
+      string p = array_paths[a];
+      size_t pos = 0;
+      for (;;) {
+        const size_t dot = p.find('.', pos);
+        const string part = p.substr(pos, dot == string::npos ? string::npos : dot - pos);
+        if (dot == string::npos) {
+          cur->fields.push_back(PbField{part, "", nullptr, std::make_shared<vector<float> >(arrays[a], arrays[a] + counts[a])});
+          break;
+        }
+        const size_t lb = part.find('[');
+        CHECK(lb != string::npos) << "bad array path " << p;
+        const string key = part.substr(0, lb);
+        const int idx = atoi(part.c_str() + lb + 1);
+        const PbField* f = cur->nth(key, idx);
+        CHECK(f && f->msg) << "array path " << p << ": no message " << part;
+        cur = f->msg.get();
+        pos = dot + 1;
+      }
+    }
+    WriteProtoToBinaryFile(*root, type, path);
+    return 0;)
+}
+
 float vvc_solver_learning_rate(void* s) {
   try { auto* sg = dynamic_cast<SGDSolver<float>*>(static_cast<Solver<float>*>(s)); return sg->GetLearningRate(); }
   catch (const std::exception& e) { g_err = e.what(); return -1.f; }

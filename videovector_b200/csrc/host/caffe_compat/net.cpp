@@ -1,5 +1,6 @@
 // Net<Dtype> (see caffe/net.hpp for the reference lines mirrored here).
 #include <cuda_runtime_api.h>
+#include <algorithm>
 #include <cstring>
 #include <cstdlib>
 #include "caffe/net.hpp"
@@ -306,8 +307,62 @@ bool Net<Dtype>::EnableFusion(string* why) {
   return true;
 }
 
+// ref: net.cpp:774-801 (Net::ToProto) + layer.hpp:462-469 (Layer::ToProto: the layer's own parameter message, then its blobs)
 template <typename Dtype>
-Dtype Net<Dtype>::FusedStep(int iter, bool do_update, const vv_trainer_cfg_t* solver_cfg) {
+shared_ptr<PbMsg> Net<Dtype>::ToProto(bool write_diff) const {
+  auto out = std::make_shared<PbMsg>();
+  out->add_scalar("name", name_);
+  for (size_t i = 0; i < layers_.size(); ++i) {
+    auto lp = std::make_shared<PbMsg>(*layers_[i]->layer_param().m);       // copy of the parameter message
+    lp->fields.erase(std::remove_if(lp->fields.begin(), lp->fields.end(), [](const PbField& f) { return f.key == "blobs"; }), lp->fields.end());
+    for (auto& b : layers_[i]->blobs()) {
+      auto bp = std::make_shared<PbMsg>();
+      b->ToProto(bp.get(), write_diff);
+      lp->fields.push_back(PbField{"blobs", "", bp, nullptr});
+    }
+    out->fields.push_back(PbField{"layers", "", lp, nullptr});
+  }
+  return out;
+}
+// ref: net.cpp:692-727
+template <typename Dtype>
+void Net<Dtype>::CopyTrainedLayersFrom(const PbMsg& param) {
+  const int num_source_layers = param.count("layers");
+  for (int i = 0; i < num_source_layers; ++i) {
+    const shared_ptr<PbMsg> src = param.sub("layers", i);
+    const string source_layer_name = src->str("name");
+    size_t target = 0;
+    while (target != layer_names_.size() && layer_names_[target] != source_layer_name) ++target;
+    if (target == layer_names_.size()) { LogInfo("Ignoring source layer " + source_layer_name); continue; }
+    LogInfo("Copying source layer " + source_layer_name);
+    vector<shared_ptr<Blob<Dtype> > >& target_blobs = layers_[target]->blobs();
+    CHECK_EQ(int(target_blobs.size()), src->count("blobs")) << "Incompatible number of blobs for layer " << source_layer_name;
+    for (size_t j = 0; j < target_blobs.size(); ++j) {
+      const shared_ptr<PbMsg> sb = src->sub("blobs", int(j));
+      CHECK_EQ(target_blobs[j]->num(), int(sb->num("num", 0)));
+      CHECK_EQ(target_blobs[j]->channels(), int(sb->num("channels", 0)));
+      CHECK_EQ(target_blobs[j]->height(), int(sb->num("height", 0)));
+      CHECK_EQ(target_blobs[j]->width(), int(sb->num("width", 0)));
+      const PbField* d = sb->nth("data", 0);
+      CHECK(d && d->floats && int(d->floats->size()) == target_blobs[j]->count()) << "blob data size mismatch in layer " << source_layer_name;
+      // written through the existing storage (not FromProto's Reshape) so that a parameter blob aliasing the fused
+      // trainer's buffer keeps aliasing it
+      memcpy(target_blobs[j]->mutable_cpu_data(), d->floats->data(), sizeof(Dtype) * target_blobs[j]->count());
+      const PbField* g = sb->nth("diff", 0);
+      if (g && g->floats && int(g->floats->size()) == target_blobs[j]->count())
+        memcpy(target_blobs[j]->mutable_cpu_diff(), g->floats->data(), sizeof(Dtype) * target_blobs[j]->count());
+      target_blobs[j]->gpu_data();                        // push to the device copy (the trainer's buffer when fused)
+    }
+  }
+  if (trainer_) VV_CHECK(vv_trainer_sync_weights(trainer_));   // refresh the GEMM operand copy of W
+}
+template <typename Dtype>
+void Net<Dtype>::CopyTrainedLayersFrom(const string& trained_filename) {
+  CopyTrainedLayersFrom(*ReadProtoFromBinaryFile(trained_filename, "NetParameter"));
+}
+
+template <typename Dtype>
+void Net<Dtype>::CreateTrainer(const vv_trainer_cfg_t* solver_cfg) {
   CHECK(fused_data_) << "EnableFusion() did not match";
   if (!trainer_) {
     // first use: create the trainer with the solver constants, hand the current parameters over and make the
@@ -335,6 +390,11 @@ Dtype Net<Dtype>::FusedStep(int iter, bool do_update, const vv_trainer_cfg_t* so
     const char* mat = getenv("VV_MATERIALISE");
     if (!(mat && mat[0] == '1')) VV_CHECK(vv_trainer_set_bank(trainer_, fused_data_->bank(), fused_data_->bank_rows()));
   }
+}
+
+template <typename Dtype>
+Dtype Net<Dtype>::FusedStep(int iter, bool do_update, const vv_trainer_cfg_t* solver_cfg) {
+  CreateTrainer(solver_cfg);
   const int32_t* dq = nullptr;
   const int32_t* di = fused_data_->NextIndices(&dq);
   VV_CHECK(vv_trainer_step(trainer_, fused_data_->bank(), fused_data_->bank_rows(), di, dq, fixed_mask_, iter, do_update ? 1 : 0));

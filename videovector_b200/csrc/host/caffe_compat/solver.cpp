@@ -1,4 +1,5 @@
 // Solver / SGDSolver (see caffe/solver.hpp for the reference lines mirrored here).
+#include <cuda_runtime_api.h>
 #include <cmath>
 #include <cstring>
 #include "caffe/solver.hpp"
@@ -32,8 +33,10 @@ Dtype Solver<Dtype>::Step() {
     if (param_.display() && iter_ % param_.display() == 0)        // same line ComputeUpdateValue prints (solver.cpp:492-494)
       fprintf(stderr, "Iteration %d, lr = %g\n", iter_,
               double(vv_learning_rate(sc.lr_policy, sc.base_lr, sc.gamma, sc.power, sc.stepsize, iter_)));
+    net_->CreateTrainer(&sc);                        // no-op after the first step
+    FillFusedSolverCfg(&sc);                         // the momentum history moves into / aliases the trainer's buffers
     loss = net_->FusedStep(iter_, true, &sc);        // forward + backward + ComputeUpdateValue + Update
-    FillFusedSolverCfg(&sc);                         // (re)alias the momentum history to the trainer's buffers
+    FillFusedSolverCfg(&sc);                         // re-alias: the trainer wrote the buffers behind the blobs' back
   } else {
     loss = net_->ForwardBackward();
     ComputeUpdateValue();
@@ -43,11 +46,41 @@ Dtype Solver<Dtype>::Step() {
   return loss;
 }
 
-// ref: solver.cpp:160-240 (test / snapshot hooks are outside the path)
+// ref: solver.cpp:320-341
 template <typename Dtype>
-void Solver<Dtype>::Solve(int max_iter) {
+string Solver<Dtype>::Snapshot() {
+  if (!presolved_) { PreSolve(); presolved_ = true; }
+  char iter_str[32]; snprintf(iter_str, sizeof(iter_str), "_iter_%d", iter_);
+  const string filename = param_.snapshot_prefix() + iter_str;
+  const string model_filename = filename + ".caffemodel", state_filename = filename + ".solverstate";
+  LogInfo("Snapshotting to " + model_filename);
+  WriteProtoToBinaryFile(*net_->ToProto(param_.snapshot_diff()), "NetParameter", model_filename);
+  PbMsg state;
+  state.add_scalar("iter", std::to_string(iter_));
+  state.add_scalar("learned_net", model_filename);
+  SnapshotSolverState(&state);
+  LogInfo("Snapshotting solver state to " + state_filename);
+  WriteProtoToBinaryFile(state, "SolverState", state_filename);
+  return model_filename;
+}
+// ref: solver.cpp:418-429
+template <typename Dtype>
+void Solver<Dtype>::Restore(const char* state_file) {
+  if (!presolved_) { PreSolve(); presolved_ = true; }
+  const shared_ptr<PbMsg> state = ReadProtoFromBinaryFile(state_file, "SolverState");
+  if (state->has("learned_net")) net_->CopyTrainedLayersFrom(state->str("learned_net"));
+  iter_ = int(state->num("iter", 0));
+  RestoreSolverState(*state);
+}
+
+// ref: solver.cpp:160-240 (the TEST-net hooks are outside the path)
+template <typename Dtype>
+void Solver<Dtype>::Solve(int max_iter, const char* resume_file) {
   const int stop = max_iter >= 0 ? max_iter : param_.max_iter();
+  if (resume_file) { LogInfo(string("Restoring previous solver status from ") + resume_file); Restore(resume_file); }
+  const int start_iter = iter_;
   for (; iter_ < stop;) {
+    if (param_.snapshot() && iter_ > start_iter && iter_ % param_.snapshot() == 0) Snapshot();
     const int it = iter_;
     const Dtype loss = Step();
     if (param_.display() && it % param_.display() == 0) {
@@ -63,6 +96,8 @@ void Solver<Dtype>::Solve(int max_iter) {
       }
     }
   }
+  // "Always save a snapshot after optimization, unless overridden" (solver.cpp:225-227); only when a prefix is configured
+  if (max_iter < 0 && param_.snapshot_after_train() && !param_.snapshot_prefix().empty()) Snapshot();
 }
 
 template <typename Dtype>
@@ -90,10 +125,36 @@ void SGDSolver<Dtype>::FillFusedSolverCfg(vv_trainer_cfg_t* c) {
   const string rt = this->param_.regularization_type();
   CHECK(rt == "L2" || rt == "L1") << "Unknown regularization type: " << rt;
   c->reg_type = rt == "L2" ? 2 : 1;
-  // after the trainer exists the momentum history lives in its buffers
+  // after the trainer exists the momentum history lives in its buffers; what the solver held until then (zeros, or a
+  // restored .solverstate) moves over once
   if (this->net_->trainer() && history_.size() == 2) {
-    history_[0]->set_gpu_data(vv_trainer_weight_hist(this->net_->trainer()));   // also moves the head to the device
-    history_[1]->set_gpu_data(vv_trainer_bias_hist(this->net_->trainer()));
+    float* hist[2] = {vv_trainer_weight_hist(this->net_->trainer()), vv_trainer_bias_hist(this->net_->trainer())};
+    for (int i = 0; i < 2; ++i) {
+      if (!history_aliased_)
+        CHECK_EQ(int(cudaMemcpy(hist[i], history_[i]->gpu_data(), sizeof(Dtype) * history_[i]->count(), cudaMemcpyDeviceToDevice)), 0);
+      history_[i]->set_gpu_data(hist[i]);                                         // also moves the head to the device
+    }
+    history_aliased_ = true;
+  }
+}
+template <typename Dtype>
+void SGDSolver<Dtype>::SnapshotSolverState(PbMsg* state) {
+  for (size_t i = 0; i < history_.size(); ++i) {
+    auto bp = std::make_shared<PbMsg>();
+    history_[i]->ToProto(bp.get());
+    state->fields.push_back(PbField{"history", "", bp, nullptr});
+  }
+}
+template <typename Dtype>
+void SGDSolver<Dtype>::RestoreSolverState(const PbMsg& state) {
+  CHECK_EQ(state.count("history"), int(history_.size())) << "Incorrect length of history blobs.";
+  LogInfo("SGDSolver: restoring history");
+  for (size_t i = 0; i < history_.size(); ++i) {
+    const shared_ptr<PbMsg> hb = state.sub("history", int(i));
+    const PbField* d = hb->nth("data", 0);
+    CHECK(d && d->floats && int(d->floats->size()) == history_[i]->count()) << "history blob " << i << " has the wrong size";
+    memcpy(history_[i]->mutable_cpu_data(), d->floats->data(), sizeof(Dtype) * history_[i]->count());
+    history_[i]->gpu_data();       // to the device copy (the trainer's buffer once aliased)
   }
 }
 // Layer-by-layer mode: the reference's own sequence on the device (ref: solver.cpp:534-568):

@@ -29,6 +29,8 @@ struct Nccl {
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
   bool load() {
     if (h) return true;
@@ -39,6 +41,8 @@ struct Nccl {
     CommInitRank = (decltype(CommInitRank))dlsym(h, "ncclCommInitRank");
     AllReduce = (decltype(AllReduce))dlsym(h, "ncclAllReduce");
     CommDestroy = (decltype(CommDestroy))dlsym(h, "ncclCommDestroy");
+    GroupStart = (decltype(GroupStart))dlsym(h, "ncclGroupStart");
+    GroupEnd = (decltype(GroupEnd))dlsym(h, "ncclGroupEnd");
     GetErrorString = (decltype(GetErrorString))dlsym(h, "ncclGetErrorString");
     if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy) { set_error("libnccl is missing symbols"); return false; }
     return true;
@@ -359,8 +363,12 @@ extern "C" int vv_trainer_step(vv_trainer_t* t, const float* bank, int64_t bank_
     }
     VV_CUDA(cudaEventRecord(t->ev_grad, t->stream));
     VV_CUDA(cudaStreamWaitEvent(t->comm_stream, t->ev_grad, 0));
+    // dW and (db, loss, violations) as one NCCL group: a single fused launch
+    const bool grp = g_nccl.GroupStart && g_nccl.GroupEnd;
+    if (grp) g_nccl.GroupStart();
     ncclResult_t r1 = g_nccl.AllReduce(t->dW_parts.p, t->dW_parts.p, size_t(NK), kNcclFloat, kNcclSum, t->comm, t->comm_stream);
     ncclResult_t r2 = g_nccl.AllReduce(t->dbx.p, t->dbx.p, size_t(N + 2), kNcclFloat, kNcclSum, t->comm, t->comm_stream);
+    if (grp) { const ncclResult_t r3 = g_nccl.GroupEnd(); if (r1 == 0 && r2 == 0) r1 = r3; }
     if (r1 != 0 || r2 != 0) { set_error("ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r1 ? r1 : r2) : "?"); return VV_ERR_NCCL; }
     VV_CUDA(cudaEventRecord(t->ev_comm, t->comm_stream));
     VV_CUDA(cudaStreamWaitEvent(t->stream, t->ev_comm, 0));

@@ -55,10 +55,12 @@ def train_net(B=128, C=5, Nn=10, K=4096, N=512, dropout=0.9, margin=2.0, norm="L
 
 
 def solver(net_path="", base_lr=0.001, momentum=0.9, weight_decay=0.0005, lr_policy="inv", gamma=0.001, power=0.75,
-           max_iter=200000, display=10, random_seed=None):
+           max_iter=200000, display=10, random_seed=None, snapshot=2000, snapshot_prefix=None):
     s = ('net: "%s"\n' % net_path if net_path else "") + (
         "base_lr: %g\nmomentum: %g\nweight_decay: %g\nlr_policy: \"%s\"\ngamma: %g\npower: %g\n"
-        "display: %d\nmax_iter: %d\nsnapshot: 2000\nsolver_mode: GPU\n" % (base_lr, momentum, weight_decay, lr_policy, gamma, power, display, max_iter))
+        "display: %d\nmax_iter: %d\nsnapshot: %d\nsolver_mode: GPU\n" % (base_lr, momentum, weight_decay, lr_policy, gamma, power, display, max_iter, snapshot))
+    if snapshot_prefix is not None:
+        s += 'snapshot_prefix: "%s"\n' % snapshot_prefix
     if random_seed is not None:
         s += "random_seed: %d\n" % random_seed
     return s
