@@ -181,6 +181,11 @@ int vv_ip_forward_gathered(vv_operand_t bank, int64_t bank_rows, const int32_t* 
 int vv_ip_wgrad_gathered(vv_operand_t dZ, vv_operand_t bank, int64_t bank_rows, const int32_t* rowmap,
                          int M, int N, int K, int prec, float regularization, float* dW_parts, int nsplit,
                          vv_stream_t stream);
+/* the rows [n0, n0 + ncols) of dW only (n0 % 8 == 0), written in place inside the [nsplit, N, K] slabs: lets a
+ * data-parallel caller all-reduce one slice while the next one is computed */
+int vv_ip_wgrad_gathered_part(vv_operand_t dZ, vv_operand_t bank, int64_t bank_rows, const int32_t* rowmap,
+                              int M, int N, int K, int prec, float regularization, float* dW_parts, int nsplit,
+                              int n0, int ncols, vv_stream_t stream);
 /* A[i*ld + col] += v[i], i < n */
 int vv_add_column(float* A, int64_t ld, int col, const float* v, int n, vv_stream_t stream);
 

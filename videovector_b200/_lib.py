@@ -72,6 +72,7 @@ SIGNATURES = {
     "vv_gather_plan": (_i, [_P, _i, _P, _P, _i, _i, _P, _P, _P]),
     "vv_ip_forward_gathered": (_i, [Operand, _i64, _P, _P, _P, Operand, _P, _i, _i, _i, _i, C.POINTER(Act), _P, _P, _P]),
     "vv_ip_wgrad_gathered": (_i, [Operand, Operand, _i64, _P, _i, _i, _i, _i, _f, _P, _i, _P]),
+    "vv_ip_wgrad_gathered_part": (_i, [Operand, Operand, _i64, _P, _i, _i, _i, _i, _f, _P, _i, _i, _i, _P]),
     "vv_add_column": (_i, [_P, _i64, _i, _P, _i, _P]),
     "vv_rank_loss_backward_ex": (_i, [_P, C.POINTER(RankCfg), _P, _f, _i, _f, _P, _P, _P, _i, _P, _P, _P, _P]),
     "vv_trainer_set_bank": (_i, [_P, _P, _i64]),

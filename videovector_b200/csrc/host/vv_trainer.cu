@@ -8,6 +8,7 @@
 // One process per GPU; NCCL is dlopen'ed (the copy already loaded by the host
 // process, e.g. torch's, is reused), so the library has no link-time dependency.
 #include <dlfcn.h>
+#include <stdlib.h>
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
@@ -84,7 +85,7 @@ struct vv_trainer {
   vv_trainer_cfg_t cfg;
   cudaStream_t stream = nullptr;
   cudaStream_t comm_stream = nullptr;
-  cudaEvent_t ev_grad = nullptr, ev_comm = nullptr;
+  cudaEvent_t ev_grad = nullptr, ev_comm = nullptr, ev_slice[4] = {nullptr, nullptr, nullptr, nullptr};
   int R = 0, M = 0, nsplit = 1;
   vv_rank_cfg_t rank;
   // parameters
@@ -156,6 +157,7 @@ struct vv_trainer {
       VV_CUDA(cudaStreamCreateWithFlags(&comm_stream, cudaStreamNonBlocking));
       VV_CUDA(cudaEventCreateWithFlags(&ev_grad, cudaEventDisableTiming));
       VV_CUDA(cudaEventCreateWithFlags(&ev_comm, cudaEventDisableTiming));
+      for (int i = 0; i < 4; ++i) VV_CUDA(cudaEventCreateWithFlags(&ev_slice[i], cudaEventDisableTiming));
     }
     return VV_OK;
   }
@@ -182,6 +184,7 @@ struct vv_trainer {
     for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
     if (ev_grad) cudaEventDestroy(ev_grad);
     if (ev_comm) cudaEventDestroy(ev_comm);
+    for (int i = 0; i < 4; ++i) if (ev_slice[i]) cudaEventDestroy(ev_slice[i]);
     if (comm_stream) cudaStreamDestroy(comm_stream);
   }
   float* loss_ptr() { return dbx.as<float>() + cfg.N; }
@@ -334,14 +337,43 @@ extern "C" int vv_trainer_step(vv_trainer_t* t, const float* bank, int64_t bank_
   if ((rc = run_rank())) return rc;
   t->toc(3);
   // K1 wgrad into split-K slabs
+  int nparts = t->nsplit;
+  float gscale = 1.f;
+  // Data parallel + gathered wgrad can produce the outputs in slices of whole 256-wide tiles, with the split-K
+  // reduction + NCCL all-reduce of slice i on the side stream under the GEMM of slice i+1.  Measured on 2xB200 this
+  // LOSES (1.50 -> 1.58 ms/step): the persistent GEMM owns every SM's register file, so the concurrent NCCL kernel and
+  // the GEMM's CTAs wait for each other, and two half-size launches quantise worse.  Kept behind VV_DP_SLICES (2 / 4).
+  static const int want_slices = [] { const char* e = getenv("VV_DP_SLICES"); return e ? atoi(e) : 1; }();
+  const int nslices = (want_slices > 1 && want_slices <= 4 && c.world_size > 1 && fused_gather && t->comm &&
+                       N % (256 * want_slices) == 0) ? want_slices : 1;
   t->tic(4);
   if (fused_gather) {
-    if ((rc = vv_ip_wgrad_gathered(t->opdZ(), t->opBank(), bank_rows, t->rowmap.as<int32_t>(), M, N, K, c.prec, c.regularization,
-                                   t->dW_parts.as<float>(), t->nsplit, s))) return rc;
-    // the K-1 copy quirk's share of dW[:, K-1] (scaled like the GEMM output)
     const double reg = double(c.regularization) / 2;
+    // the K-1 copy quirk's share of dW[:, K-1] (scaled like the GEMM output)
     if (reg > 0) { if ((rc = vv_axpby(N, float(1.0 + reg), t->dq.as<float>(), 0.f, t->dq.as<float>(), s))) return rc; }
-    if ((rc = vv_add_column(t->dW_parts.as<float>(), K, K - 1, t->dq.as<float>(), N, s))) return rc;
+    const int cols = N / nslices;
+    for (int sl = 0; sl < nslices; ++sl) {
+      const int n0 = sl * cols;
+      float* slice = t->dW_parts.as<float>() + size_t(n0) * K;
+      if ((rc = vv_ip_wgrad_gathered_part(t->opdZ(), t->opBank(), bank_rows, t->rowmap.as<int32_t>(), M, N, K, c.prec, c.regularization,
+                                          t->dW_parts.as<float>(), t->nsplit, n0, cols, s))) return rc;
+      if ((rc = vv_add_column(slice, K, K - 1, t->dq.as<float>() + n0, cols, s))) return rc;
+      if (nslices > 1) {
+        if (nparts > 1) { if ((rc = vv_reduce_parts(slice, nparts, NK, int64_t(cols) * K, slice, s))) return rc; }
+        VV_CUDA(cudaEventRecord(t->ev_slice[sl], t->stream));
+        VV_CUDA(cudaStreamWaitEvent(t->comm_stream, t->ev_slice[sl], 0));
+        const bool last = sl == nslices - 1;
+        const bool grp = last && g_nccl.GroupStart && g_nccl.GroupEnd;
+        if (grp) g_nccl.GroupStart();
+        ncclResult_t r1 = g_nccl.AllReduce(slice, slice, size_t(cols) * K, kNcclFloat, kNcclSum, t->comm, t->comm_stream);
+        ncclResult_t r2 = 0;
+        if (last) r2 = g_nccl.AllReduce(t->dbx.p, t->dbx.p, size_t(N + 2), kNcclFloat, kNcclSum, t->comm, t->comm_stream);
+        if (grp) { const ncclResult_t r3 = g_nccl.GroupEnd(); if (r1 == 0 && r2 == 0) r1 = r3; }
+        if (r1 != 0 || r2 != 0) { set_error("ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r1 ? r1 : r2) : "?"); return VV_ERR_NCCL; }
+        count_launch(last ? 2 : 1);
+      }
+    }
+    if (nslices > 1) nparts = 1;
   } else {
     if ((rc = vv_ip_wgrad(t->opdZ(), t->opX(), M, N, K, c.prec, c.regularization, t->dW_parts.as<float>(), t->nsplit,
                           nullptr, 0, s))) return rc;
@@ -352,27 +384,27 @@ extern "C" int vv_trainer_step(vv_trainer_t* t, const float* bank, int64_t bank_
     if ((rc = vv_ip_dgrad(t->opdZ(), t->opW(), M, N, K, c.prec, t->dX.as<float>(), s))) return rc;
     t->toc(5);
   }
-  int nparts = t->nsplit;
-  float gscale = 1.f;
   if (c.world_size > 1) {
     t->tic(6);
     if (!t->comm) { set_error("trainer: world_size > 1 but vv_dp_init was not called"); return VV_ERR_NCCL; }
-    if (nparts > 1) {
-      if ((rc = vv_reduce_parts(t->dW_parts.as<float>(), nparts, NK, NK, t->dW_parts.as<float>(), s))) return rc;
-      nparts = 1;
+    if (nslices == 1) {
+      if (nparts > 1) {
+        if ((rc = vv_reduce_parts(t->dW_parts.as<float>(), nparts, NK, NK, t->dW_parts.as<float>(), s))) return rc;
+        nparts = 1;
+      }
+      VV_CUDA(cudaEventRecord(t->ev_grad, t->stream));
+      VV_CUDA(cudaStreamWaitEvent(t->comm_stream, t->ev_grad, 0));
+      // dW and (db, loss, violations) as one NCCL group: a single fused launch
+      const bool grp = g_nccl.GroupStart && g_nccl.GroupEnd;
+      if (grp) g_nccl.GroupStart();
+      ncclResult_t r1 = g_nccl.AllReduce(t->dW_parts.p, t->dW_parts.p, size_t(NK), kNcclFloat, kNcclSum, t->comm, t->comm_stream);
+      ncclResult_t r2 = g_nccl.AllReduce(t->dbx.p, t->dbx.p, size_t(N + 2), kNcclFloat, kNcclSum, t->comm, t->comm_stream);
+      if (grp) { const ncclResult_t r3 = g_nccl.GroupEnd(); if (r1 == 0 && r2 == 0) r1 = r3; }
+      if (r1 != 0 || r2 != 0) { set_error("ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r1 ? r1 : r2) : "?"); return VV_ERR_NCCL; }
+      count_launch(2);
     }
-    VV_CUDA(cudaEventRecord(t->ev_grad, t->stream));
-    VV_CUDA(cudaStreamWaitEvent(t->comm_stream, t->ev_grad, 0));
-    // dW and (db, loss, violations) as one NCCL group: a single fused launch
-    const bool grp = g_nccl.GroupStart && g_nccl.GroupEnd;
-    if (grp) g_nccl.GroupStart();
-    ncclResult_t r1 = g_nccl.AllReduce(t->dW_parts.p, t->dW_parts.p, size_t(NK), kNcclFloat, kNcclSum, t->comm, t->comm_stream);
-    ncclResult_t r2 = g_nccl.AllReduce(t->dbx.p, t->dbx.p, size_t(N + 2), kNcclFloat, kNcclSum, t->comm, t->comm_stream);
-    if (grp) { const ncclResult_t r3 = g_nccl.GroupEnd(); if (r1 == 0 && r2 == 0) r1 = r3; }
-    if (r1 != 0 || r2 != 0) { set_error("ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r1 ? r1 : r2) : "?"); return VV_ERR_NCCL; }
     VV_CUDA(cudaEventRecord(t->ev_comm, t->comm_stream));
     VV_CUDA(cudaStreamWaitEvent(t->stream, t->ev_comm, 0));
-    count_launch(2);
     gscale = 1.f / float(c.world_size);
     t->toc(6);
   }

@@ -163,6 +163,11 @@ extern "C" int vv_ip_forward_gathered(vv_operand_t bank, int64_t bank_rows, cons
 
 extern "C" int vv_ip_wgrad_gathered(vv_operand_t dZ, vv_operand_t bank, int64_t bank_rows, const int32_t* rowmap, int M, int N,
                                     int K, int prec, float regularization, float* dW_parts, int nsplit, vv_stream_t stream) {
+  return vv_ip_wgrad_gathered_part(dZ, bank, bank_rows, rowmap, M, N, K, prec, regularization, dW_parts, nsplit, 0, N, stream);
+}
+extern "C" int vv_ip_wgrad_gathered_part(vv_operand_t dZ, vv_operand_t bank, int64_t bank_rows, const int32_t* rowmap, int M, int N,
+                                         int K, int prec, float regularization, float* dW_parts, int nsplit, int n0, int ncols,
+                                         vv_stream_t stream) {
   VV_REQUIRE(dZ.hi && bank.hi && rowmap && dW_parts && M > 0 && N > 0 && K > 0 && nsplit >= 1 && bank_rows > 0,
              "ip_wgrad_gathered: bad arguments");
   VV_REQUIRE(prec != VV_PREC_FP32_SIMT, "ip_wgrad_gathered needs a tensor-core precision");
@@ -175,5 +180,6 @@ extern "C" int vv_ip_wgrad_gathered(vv_operand_t dZ, vv_operand_t bank, int64_t 
   const double reg = double(regularization) / 2;
   g.epi.out_scale = reg > 0 ? float(1.0 + reg) : 1.f;
   g.slab_stride = (long long)N * K; g.D = dW_parts; g.nsplit = nsplit;
+  g.n0 = n0; g.ncols = ncols;
   return gemm_tc_launch(g, stream);
 }

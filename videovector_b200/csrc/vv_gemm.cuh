@@ -41,6 +41,7 @@ struct GemmProblem {
   // are fetched by index with cp.async by two producer warps; rowmap[m] = bank row of X row m (padded to a multiple of 128)
   const int32_t* rowmap;  // NULL = X is materialised
   int64_t bank_rows;
+  int n0 = 0, ncols = 0;  // WGRAD_T only: compute outputs [n0, n0 + ncols) (ncols = 0: all)
 };
 
 int gemm_tc_launch(const GemmProblem& p, cudaStream_t stream);     // tcgen05 path (TF32X3 / TF32 / BF16)

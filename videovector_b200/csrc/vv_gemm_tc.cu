@@ -532,15 +532,17 @@ EncodeTiledFn get_encode() {
 
 // 2D row-major tensor [outer rows, inner contiguous elems]; box = [box_outer rows, box_bytes of inner].
 int make_tmap(CUtensorMap* tm, const void* base, CUtensorMapDataType dt, int elem_bytes, uint64_t inner,
-              uint64_t outer, uint32_t box_outer, CUtensorMapSwizzle swizzle, int box_bytes = kRowBytes) {
+              uint64_t outer, uint32_t box_outer, CUtensorMapSwizzle swizzle, int box_bytes = kRowBytes,
+              uint64_t pitch_elems = 0 /* 0 = dense rows */) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return VV_ERR_CUDA;
-  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || ((inner * elem_bytes) & 15) != 0) {
+  const uint64_t pitch = pitch_elems ? pitch_elems : inner;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || ((pitch * elem_bytes) & 15) != 0) {
     set_error("GEMM operand must be 16-byte aligned with a row pitch that is a multiple of 16 bytes");
     return VV_ERR_INVALID;
   }
   cuuint64_t dims[2] = {inner, outer};
-  cuuint64_t strides[1] = {inner * elem_bytes};
+  cuuint64_t strides[1] = {pitch * elem_bytes};
   cuuint32_t box[2] = {uint32_t(box_bytes / elem_bytes), box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(tm, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -561,6 +563,19 @@ int launch_cfg(const GemmProblem& g, cudaStream_t stream) {
     default:           d_rows = g.M; d_cols = g.K; red = g.N; a_inner = g.N; a_outer = g.M; b_inner = g.K; b_outer = g.N; break;
   }
   if (C::trans_out != (g.kind == GEMM_WGRAD_T)) { set_error("internal: transposed-output configuration mismatch"); return VV_ERR_INVALID; }
+  // WGRAD_T may be asked for a slice [n0, n0 + ncols) of the outputs (the data-parallel trainer pipelines the
+  // all-reduce of one slice under the GEMM of the next): a column window of dZ and a row window of dW
+  const int n0 = (g.kind == GEMM_WGRAD_T) ? g.n0 : 0;
+  const int ncols = (g.kind == GEMM_WGRAD_T && g.ncols > 0) ? g.ncols : int(g.N - n0);
+  uint64_t b_pitch = 0;
+  const char* b_hi = static_cast<const char*>(g.B.hi);
+  const char* b_lo = static_cast<const char*>(g.B.lo);
+  if (g.kind == GEMM_WGRAD_T) {
+    if (n0 < 0 || ncols <= 0 || n0 + ncols > g.N || (n0 % 8) != 0) { set_error("wgrad slice [%d, +%d) of N=%d is invalid", n0, ncols, g.N); return VV_ERR_INVALID; }
+    b_pitch = uint64_t(g.N); b_inner = uint64_t(ncols); d_cols = ncols;
+    b_hi += size_t(n0) * C::elem_bytes;
+    if (b_lo) b_lo += size_t(n0) * C::elem_bytes;
+  }
   const CUtensorMapDataType dt = C::tf32 ? (C::nprod == 3 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32)
                                          : (C::f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
   CUtensorMap tA_hi, tA_hb, tA_lb, tB_hi, tB_hb, tB_lb;
@@ -575,7 +590,7 @@ int launch_cfg(const GemmProblem& g, cudaStream_t stream) {
   const CUtensorMapSwizzle sw_a = (C::tf32 && C::a_mn) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
   const CUtensorMapSwizzle sw_b = (C::tf32 && C::b_mn) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
   int rc;
-  if ((rc = make_tmap(&tB_hi, g.B.hi, dt, C::elem_bytes, b_inner, b_outer, b_box, sw_b))) return rc;
+  if ((rc = make_tmap(&tB_hi, b_hi, dt, C::elem_bytes, b_inner, b_outer, b_box, sw_b, kRowBytes, b_pitch))) return rc;
   if (C::gather) tA_hi = tB_hi;
   else if ((rc = make_tmap(&tA_hi, g.A.hi, dt, C::elem_bytes, a_inner, a_outer, a_box, sw_a))) return rc;
   if (C::mixed) {
@@ -595,7 +610,7 @@ int launch_cfg(const GemmProblem& g, cudaStream_t stream) {
     if ((rc = make_tmap(&tB_lb, b_planes + b_count, bf, 2, b_inner, b_outer, b_box, s16b, bbb))) return rc;
   } else if (C::split16) {
     if (!g.A.lo || !g.B.lo) { set_error("F16X3 needs the h0 and h1 planes of every operand"); return VV_ERR_INVALID; }
-    if ((rc = make_tmap(&tB_hb, g.B.lo, dt, C::elem_bytes, b_inner, b_outer, b_box, sw_b))) return rc;
+    if ((rc = make_tmap(&tB_hb, b_lo, dt, C::elem_bytes, b_inner, b_outer, b_box, sw_b, kRowBytes, b_pitch))) return rc;
     if (C::gather) tA_hb = tB_hb;
     else if ((rc = make_tmap(&tA_hb, g.A.lo, dt, C::elem_bytes, a_inner, a_outer, a_box, sw_a))) return rc;
     tA_lb = tA_hi; tB_lb = tB_hi;
@@ -619,7 +634,7 @@ int launch_cfg(const GemmProblem& g, cudaStream_t stream) {
   p.chunk_kb = C::promote ? 512 / C::bk : p.kb_per_split;
   p.inv_sa = C::split16 ? &f16_hdr(g.A.hi)->inv_scale : nullptr;
   p.inv_sb = C::split16 ? &f16_hdr(g.B.hi)->inv_scale : nullptr;
-  p.D = g.D; p.slab_stride = g.slab_stride;
+  p.D = g.D + (C::trans_out ? (long long)n0 * g.K : 0); p.slab_stride = g.slab_stride;
   p.act_N = g.N;
   p.epi = g.epi;
   p.rowmap = g.rowmap;
