@@ -298,7 +298,7 @@ int vv_fill_bank(float* bank, int64_t rows, int K, uint64_t seed, vv_stream_t st
 float vv_bank_value_host(uint64_t seed, int64_t row, int col, int K);
 
 /* ------------------------------------------------------------------------- */
-/* Host sampler: VideoSampledShotsDataLayer's WINDOW sampler as an index stream */
+/* Host sampler: VideoSampledShotsDataLayer's sampler as an index stream        */
 /* (ref: video_sampled_shots_data_layer.cpp:25-44,245-344,372-507,769-909;     */
 /* util/rng.hpp:43-54).  Self-contained glibc-compatible rand() (TYPE_3, the    */
 /* reference never seeds it -> seed 1), so it is reproducible per rank and does */
@@ -311,6 +311,20 @@ vv_sampler_t* vv_sampler_create(int num_videos, const int32_t* video_id,
                                 int max_buffer_size, int negative_swap_percentage,
                                 int max_same_video_negs, int max_tries_for_negs,
                                 unsigned int rand_seed);
+/* context_type = VideoSampledShotsDataParameter.CONTEXT (caffe.proto:598-604; vv_sampler_create = WINDOW):
+ *   PAIRWISE (context_size must be 2): two distinct shots of the video (:396-404)
+ *   WINDOW   : sorted random window, target = its median (:425-506)
+ *   PAST     : sorted random window, target = its last shot; same-video negatives from before the window (:509-583)
+ *   PAST_CONTINUOUS[_FIXED]: evenly spaced frames with a random (fixed) stride, target = the last; negatives = the
+ *              frames right before the window (:586-757) */
+enum { VV_CONTEXT_PAIRWISE = 0, VV_CONTEXT_WINDOW = 1, VV_CONTEXT_PAST = 2, VV_CONTEXT_PAST_CONTINUOUS = 3,
+       VV_CONTEXT_PAST_CONTINUOUS_FIXED = 4 };
+vv_sampler_t* vv_sampler_create_ex(int num_videos, const int32_t* video_id,
+                                   const int32_t* shot_off /*[V+1]*/, const int32_t* shot_ids,
+                                   int batch_size, int context_size, int num_negative_samples,
+                                   int max_buffer_size, int negative_swap_percentage,
+                                   int max_same_video_negs, int max_tries_for_negs,
+                                   unsigned int rand_seed, int context_type);
 void vv_sampler_destroy(vv_sampler_t* s);
 /* idx, quirk: host [B,R] int32 (see vv_gather_rows).  Returns 0 or <0. */
 int vv_sampler_next(vv_sampler_t* s, int32_t* idx, int32_t* quirk);

@@ -651,6 +651,7 @@ template <class It> static void orc_random_unique(It first, It last, int num_ran
 }
 
 struct OrcSampler {
+  int mode = 1;
   int V, K, B, C, Nn, P, swap_pct, max_same;
   const int* video_id; const int* shot_off; const int* shot_ids; const float* feat;
   int cursor;
@@ -670,13 +671,31 @@ static std::string orc_key(int vid, int shot_id) {
 
 extern "C" {
 
+void* orc_sampler_create_mode(int V, int K, const int* video_id, const int* shot_off,
+                              const int* shot_ids, const float* feat,
+                              int batch_size, int context_size, int num_negative_samples,
+                              int max_buffer_size, int negative_swap_percentage,
+                              int max_same_video_negs, int max_tries_for_negs, int context_type);
 void* orc_sampler_create(int V, int K, const int* video_id, const int* shot_off,
                          const int* shot_ids, const float* feat,
                          int batch_size, int context_size, int num_negative_samples,
                          int max_buffer_size, int negative_swap_percentage,
                          int max_same_video_negs, int max_tries_for_negs) {
+  return orc_sampler_create_mode(V, K, video_id, shot_off, shot_ids, feat, batch_size, context_size, num_negative_samples,
+                                 max_buffer_size, negative_swap_percentage, max_same_video_negs, max_tries_for_negs, 1);
+}
+// context_type: VideoSampledShotsDataParameter.CONTEXT (caffe.proto:598-604): 0 PAIRWISE, 1 WINDOW, 2 PAST,
+// 3 PAST_CONTINUOUS, 4 PAST_CONTINUOUS_FIXED
+void* orc_sampler_create_mode(int V, int K, const int* video_id, const int* shot_off,
+                              const int* shot_ids, const float* feat,
+                              int batch_size, int context_size, int num_negative_samples,
+                              int max_buffer_size, int negative_swap_percentage,
+                              int max_same_video_negs, int max_tries_for_negs, int context_type) {
   if (max_same_video_negs > num_negative_samples) return nullptr;   // undefined in the reference (slot overflow)
+  if (context_type < 0 || context_type > 4) return nullptr;
+  if (context_type == 0 && context_size != 2) return nullptr;       // PAIRWISE fills channels 0 and 1 only (:396-404)
   OrcSampler* s = new OrcSampler();
+  s->mode = context_type;
   s->V = V; s->K = K; s->B = batch_size; s->C = context_size; s->Nn = num_negative_samples;
   s->P = num_negative_samples > 0 ? max_buffer_size : 0;
   s->swap_pct = negative_swap_percentage; s->max_same = max_same_video_negs;
@@ -727,36 +746,66 @@ int orc_sampler_next(void* h, int* idx, int* quirk, float* data) {
     const int v = s->cursor;
     s->cursor = (s->cursor + 1) % s->V;            // advanced before knowing if used (:826-846)
     const int off = s->shot_off[v], n = s->shot_off[v + 1] - off;
-    // ---- AddSamplesToTop, WINDOW branch (:372-507)
+    // ---- AddSamplesToTop (:372-757)
     if (n < 2) continue;                           // :387-389
     std::vector<int> ids(n);
     std::iota(ids.begin(), ids.end(), 0);
-    if ((int)ids.size() < C) continue;             // :427-429
-    orc_random_unique(ids.begin(), ids.end(), C);  // :432
-    std::sort(ids.begin(), ids.begin() + C);       // :437
-    const int half = C / 2;
-    int context_id = 0;
-    for (int i = 0; i < C; ++i) {
-      const int slot = (i == half) ? 0 : (context_id++ + 1);
-      const int g = off + ids[i];
+    int added = 0;
+    auto put_full = [&](int slot, int shot) {      // a full K-float copy into a slot
+      const int g = off + shot;
       if (top) memcpy(top + ((size_t)item_id * R + slot) * K, s->feat + (size_t)g * K, K * sizeof(float));
       idx[item_id * R + slot] = g; quirk[item_id * R + slot] = -2;
       s->last_full[item_id * R + slot] = g;
-    }
-    int added = 0;
-    if (Nn > 0 && n > C) {                          // :479-503
-      std::random_shuffle(ids.begin() + C, ids.end());
-      for (int nid = C; nid < n && added < s->max_same; ++nid) {
-        if (ids[nid] < ids[half - 1] || ids[nid] > ids[half + 1]) {
-          const int slot = C + added;
-          const int g = off + ids[nid];
-          // copies datum_height_-1 floats only (:492)
-          if (top) memcpy(top + ((size_t)item_id * R + slot) * K, s->feat + (size_t)g * K, (K - 1) * sizeof(float));
-          idx[item_id * R + slot] = g;
-          quirk[item_id * R + slot] = s->last_full[item_id * R + slot];   // -1 or a shot
-          added++;
-        }
+    };
+    auto put_negative = [&](int shot) {            // same-video negative: datum_height_-1 floats only (:492, :567, :655, :742)
+      const int slot = C + added;
+      const int g = off + shot;
+      if (top) memcpy(top + ((size_t)item_id * R + slot) * K, s->feat + (size_t)g * K, (K - 1) * sizeof(float));
+      idx[item_id * R + slot] = g;
+      quirk[item_id * R + slot] = s->last_full[item_id * R + slot];   // -1 or a shot
+      added++;
+    };
+    if (s->mode == 0) {                            // PAIRWISE :396-422
+      orc_random_unique(ids.begin(), ids.end(), 2);
+      put_full(0, ids[0]); put_full(1, ids[1]);
+    } else if (s->mode == 1) {                     // WINDOW :425-506
+      if ((int)ids.size() < C) continue;           // :427-429
+      orc_random_unique(ids.begin(), ids.end(), C);  // :432
+      std::sort(ids.begin(), ids.begin() + C);       // :437
+      const int half = C / 2;
+      int context_id = 0;
+      for (int i = 0; i < C; ++i) put_full((i == half) ? 0 : (context_id++ + 1), ids[i]);
+      if (Nn > 0 && n > C) {                          // :479-503
+        std::random_shuffle(ids.begin() + C, ids.end());
+        for (int nid = C; nid < n && added < s->max_same; ++nid)
+          if (ids[nid] < ids[half - 1] || ids[nid] > ids[half + 1]) put_negative(ids[nid]);
       }
+    } else if (s->mode == 2) {                     // PAST :509-583: the target is the LAST of the sorted window
+      if ((int)ids.size() < C) continue;
+      orc_random_unique(ids.begin(), ids.end(), C);
+      std::sort(ids.begin(), ids.begin() + C);
+      int context_id = 0;
+      for (int i = 0; i < C; ++i) put_full((i == C - 1) ? 0 : (context_id++ + 1), ids[i]);
+      if (Nn > 0 && n > C) {
+        std::random_shuffle(ids.begin() + C, ids.end());
+        for (int nid = C; nid < n && added < s->max_same; ++nid)
+          if (ids[nid] < ids[1]) put_negative(ids[nid]);          // :562
+      }
+    } else {                                       // PAST_CONTINUOUS :586-671 / PAST_CONTINUOUS_FIXED :674-757
+      if ((int)ids.size() < C) continue;
+      const int max_sample_length = (n - C) / (C - 1);
+      int sample_length, begin_frame;
+      if (s->mode == 3) {
+        sample_length = rand() % (max_sample_length + 1);                                   // :596
+        begin_frame = rand() % (n - (C - 1) * sample_length - C + 1);                       // :598-599
+      } else {
+        sample_length = (max_sample_length >= 1) ? (max_sample_length - 1) : 0;             // :685
+        begin_frame = n - (C - 1) * sample_length - C;                                      // :687-688
+      }
+      int context_id = 0;
+      for (int i = 0; i < C; ++i) put_full((i == C - 1) ? 0 : (context_id++ + 1), begin_frame + i * (sample_length + 1));
+      if (Nn > 0 && begin_frame > 0)
+        for (int nid = begin_frame - 1; nid >= 0 && added < s->max_same; --nid) put_negative(nid);   // :645-660
     }
     // ---- remaining negatives from the buffer (:852-874)
     if (Nn > 0) {

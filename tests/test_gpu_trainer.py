@@ -272,3 +272,32 @@ def test_extract_matches_forward(oracle):
         assert rel(out, ref) < tol
         tr.close()
     smp.close()
+
+
+@pytest.mark.parametrize("mode,C", [("past", 4), ("past_continuous", 5), ("past_continuous_fixed", 3), ("pairwise", 2)])
+def test_other_context_types_train_step_matches_oracle(oracle, mode, C):
+    """The step is agnostic to how the data layer picked the rows: the other context types of the sampler (even
+    window sizes included) through the default gather-fused f16x3 path against the oracle net."""
+    B, Nn, K, N = 32, 6, 256, 64
+    video_id, shot_off, shot_ids = ops.synthetic_videos(64, 24)
+    bank = ops.fill_bank(64 * 24, K, 1234)
+    smp = ops.Sampler(video_id, shot_off, shot_ids, B, C, Nn, 200, 50, 0 if mode == "pairwise" else 4, 100, rand_seed=1, context_type=mode)
+    rng = np.random.RandomState(1701)
+    W0 = rng.normal(0, 0.02, (N, K)).astype(np.float32); b0 = rng.normal(0, 0.01, N).astype(np.float32)
+    tr = ops.Trainer(ops.trainer_cfg(B, C, Nn, K, N, dropout_ratio=0.5, dropout_mode=DROPOUT_MASK01, prec="f16x3"))
+    tr.set_weights(torch.as_tensor(W0).cuda(), torch.as_tensor(b0).cuda())
+    tr.set_bank(bank)
+    bank_np = bank.cpu().numpy()
+    oracle.use_openblas(0)
+    for it in range(2):
+        idx, quirk = smp.next()
+        mask = (rng.uniform(0, 1, ((C + Nn) * B, N)) > 0.5).astype(np.uint32)
+        tr.step(bank, torch.as_tensor(idx).cuda(), torch.as_tensor(quirk).cuda(), torch.as_tensor(mask.astype(np.int32)).cuda(),
+                it=it, do_update=False)
+        ref = oracle.net_forward_backward(oracle_data_blob(bank_np, idx, quirk), W0, b0, mask, B, C, Nn, margin=2.0, norm=2,
+                                          dropout_ratio=0.5, want=("loss", "violations", "dW", "db"))
+        assert abs(tr.tensor("loss").item() - ref["loss"][0]) < 1e-5 * max(1.0, ref["loss"][0])
+        assert tr.tensor("violations").item() == ref["violations"][0]
+        assert rel(tr.tensor("dW_raw"), ref["dW"]) < 2e-5 and rel(tr.tensor("db_raw"), ref["db"]) < 2e-5
+    oracle.use_builtin_blas()
+    tr.close(); smp.close()

@@ -97,3 +97,66 @@ def test_synthetic_bank_hash_host_matches_numpy(vvlib):
             assert b[r, c] == vvlib.vv_bank_value_host(1234, r, c, 16)
     big = ops.bank_host(64, 256, 1234)
     assert 0.3 < (big > 0).mean() < 0.7 and 0.4 < big.std() < 0.8
+
+
+# ---- the other context types of the data layer -----------------------------------------------
+MODE_CASES = [
+    # mode, V, smin, smax, B, C, Nn, P, swap, max_same
+    ("pairwise", 200, 1, 12, 16, 2, 10, 50, 50, 0),            # two shots per record, every negative from the buffer
+    ("pairwise", 100, 2, 5, 8, 2, 0, 0, 0, 0),                 # no negatives at all
+    ("past", 200, 3, 30, 16, 5, 10, 100, 50, 6),               # target = last frame of the sorted window
+    ("past", 150, 4, 9, 8, 4, 6, 40, 99, 6),                   # even context size, n == C records
+    ("past", 120, 18, 30, 8, 17, 50, 400, 50, 6),
+    ("past_continuous", 200, 3, 40, 16, 5, 10, 100, 50, 6),    # random stride, negatives = frames before the window
+    ("past_continuous", 150, 2, 8, 8, 2, 4, 30, 50, 2),
+    ("past_continuous_fixed", 200, 3, 40, 16, 5, 10, 100, 50, 6),
+    ("past_continuous_fixed", 64, 9, 9, 64, 3, 6, 60, 0, 6),
+]
+
+
+@pytest.mark.parametrize("mode,V,smin,smax,B,C,Nn,P,swap,max_same", MODE_CASES)
+def test_other_context_types_match_oracle(vvlib, oracle, mode, V, smin, smax, B, C, Nn, P, swap, max_same):
+    """PAIRWISE / PAST / PAST_CONTINUOUS / PAST_CONTINUOUS_FIXED (video_sampled_shots_data_layer.cpp:396-422, 509-757):
+    the same bit-exact index stream contract as WINDOW, against the oracle on the real libc rand()."""
+    from videovector_b200._lib import CONTEXT
+    rng = np.random.RandomState(V + B + C)
+    video_id, shot_off, shot_ids, feat = make_dataset(rng, V, smin, smax, K=6)
+    R = C + Nn
+    for seed in (1, 5):
+        osmp = oracle.Sampler(video_id, shot_off, shot_ids, feat, 6, B, C, Nn, P, swap, max_same, 100, seed=seed, context_type=CONTEXT[mode])
+        ostream = [osmp.next() for _ in range(10)]
+        ocur = osmp.cursor
+        osmp.close()
+        psmp = ops.Sampler(video_id, shot_off, shot_ids, B, C, Nn, P, swap, max_same, 100, rand_seed=seed, context_type=mode)
+        prev = np.zeros((B, R, 6), np.float32)                      # the prefetch buffer persists between batches
+        for it, (oi, oq, data) in enumerate(ostream):
+            pi, pq = psmp.next()
+            assert np.array_equal(pi, oi), "%s: idx differs at batch %d" % (mode, it)
+            assert np.array_equal(pq, oq), "%s: quirk differs at batch %d" % (mode, it)
+            # gathering bank rows with (idx, quirk) rebuilds the reference's data blob, K-1 copy quirk included
+            blob = feat[pi]
+            last = np.where(pq >= 0, feat[np.maximum(pq, 0), 5], np.where(pq == -1, 0.0, blob[..., 5]))
+            blob[..., 5] = last
+            assert np.array_equal(blob, data), "%s: data blob differs at batch %d" % (mode, it)
+            # structure: the target is the LAST frame of its window in the PAST modes, one video per item
+            vid_of = np.searchsorted(shot_off, pi[:, :C], side="right") - 1
+            assert (vid_of == vid_of[:, :1]).all()
+            if mode.startswith("past"):
+                assert (pi[:, 0:1] > pi[:, 1:C]).all() and (np.diff(pi[:, 1:C], axis=1) > 0).all()
+            if mode == "past_continuous_fixed" and C > 2:
+                d = np.diff(np.concatenate([pi[:, 1:C], pi[:, :1]], 1), axis=1)
+                assert (d == d[:, :1]).all()                             # evenly spaced
+        assert psmp.cursor == ocur
+        psmp.close()
+
+
+def test_context_type_argument_checks(vvlib):
+    rng = np.random.RandomState(0)
+    video_id, shot_off, shot_ids, _ = make_dataset(rng, 50, 6, 12)
+    with pytest.raises(Exception):
+        ops.Sampler(video_id, shot_off, shot_ids, 4, 3, 4, 20, 50, 2, 100, context_type="pairwise")    # PAIRWISE needs C == 2
+    with pytest.raises(Exception):
+        ops.Sampler(video_id, shot_off, shot_ids, 4, 4, 4, 20, 50, 2, 100, context_type="window")      # WINDOW needs an odd C
+    ops.Sampler(video_id, shot_off, shot_ids, 4, 4, 4, 20, 50, 2, 100, context_type="past").close()   # PAST does not
+    with pytest.raises(Exception):
+        ops.Sampler(video_id, shot_off, shot_ids, 4, 5, 4, 20, 50, 2, 100, context_type=7)

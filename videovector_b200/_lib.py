@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libvv_b200.so")
 VV_MAX_CONTEXT = 64
 PREC = {"fp32_simt": 0, "tf32x3": 1, "tf32": 2, "bf16": 3, "f16x3": 4}
 F16X3_HEADER_BYTES = 128
+CONTEXT = {"pairwise": 0, "window": 1, "past": 2, "past_continuous": 3, "past_continuous_fixed": 4}
 DROPOUT_NONE, DROPOUT_MASK01, DROPOUT_MASK_U32, DROPOUT_PHILOX = 0, 1, 2, 3
 
 
@@ -101,6 +102,7 @@ SIGNATURES = {
     "vv_fill_bank": (_i, [_P, _i64, _i, _u64, _P]),
     "vv_bank_value_host": (_f, [_u64, _i64, _i, _i]),
     "vv_sampler_create": (_P, [_i, _P, _P, _P, _i, _i, _i, _i, _i, _i, _i, C.c_uint]),
+    "vv_sampler_create_ex": (_P, [_i, _P, _P, _P, _i, _i, _i, _i, _i, _i, _i, C.c_uint, _i]),
     "vv_sampler_destroy": (None, [_P]),
     "vv_sampler_next": (_i, [_P, _P, _P]),
     "vv_sampler_cursor": (_i, [_P]),

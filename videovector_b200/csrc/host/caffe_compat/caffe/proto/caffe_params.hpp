@@ -50,9 +50,10 @@ const char* LayerTypeName(LayerParameter_LayerType t);
 
 enum EltwiseParameter_EltwiseOp { EltwiseParameter_EltwiseOp_PROD = 0, EltwiseParameter_EltwiseOp_SUM = 1, EltwiseParameter_EltwiseOp_MAX = 2 };
 enum MaxMarginLossParameter_Norm { MaxMarginLossParameter_Norm_L1 = 1, MaxMarginLossParameter_Norm_L2 = 2 };
-enum VideoSampledShotsDataParameter_ContextType {
-  VideoSampledShotsDataParameter_CONTEXT_WINDOW = 0, VideoSampledShotsDataParameter_CONTEXT_PAIRWISE = 1,
-  VideoSampledShotsDataParameter_CONTEXT_PAST = 2 };
+enum VideoSampledShotsDataParameter_ContextType {   // values as in caffe.proto:598-604 (= VV_CONTEXT_*)
+  VideoSampledShotsDataParameter_CONTEXT_PAIRWISE = 0, VideoSampledShotsDataParameter_CONTEXT_WINDOW = 1,
+  VideoSampledShotsDataParameter_CONTEXT_PAST = 2, VideoSampledShotsDataParameter_CONTEXT_PAST_CONTINUOUS = 3,
+  VideoSampledShotsDataParameter_CONTEXT_PAST_CONTINUOUS_FIXED = 4 };
 
 struct ParamBase { shared_ptr<PbMsg> m; explicit ParamBase(shared_ptr<PbMsg> p) : m(p ? p : std::make_shared<PbMsg>()) {} };
 

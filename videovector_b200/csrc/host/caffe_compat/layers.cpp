@@ -450,7 +450,6 @@ void VideoSampledShotsDataLayer<Dtype>::LayerSetUp(const vector<Blob<Dtype>*>& b
   const string src = p.source();
   CHECK(src.compare(0, 12, "synthetic://") == 0)
       << "only synthetic:// sources are built (LMDB/LevelDB readers are out of scope, SURVEY 8f); got '" << src << "'";
-  CHECK(p.context_type() == VideoSampledShotsDataParameter_CONTEXT_WINDOW) << "only context_type WINDOW is built";
   const int V = int(UrlParam(src, "videos", 2048)), S = int(UrlParam(src, "shots", 32));
   feature_size_ = int(UrlParam(src, "dim", 4096));
   const uint64_t seed = uint64_t(UrlParam(src, "seed", 1234));
@@ -462,9 +461,10 @@ void VideoSampledShotsDataLayer<Dtype>::LayerSetUp(const vector<Blob<Dtype>*>& b
   vector<int32_t> vid(V), off(V + 1), ids(size_t(V) * S);
   for (int v = 0; v < V; ++v) { vid[v] = v; off[v] = v * S; for (int s = 0; s < S; ++s) ids[size_t(v) * S + s] = s; }
   off[V] = V * S;
-  sampler_ = vv_sampler_create(V, vid.data(), off.data(), ids.data(), batch_size_, context_size_, num_negative_samples_,
-                               p.max_buffer_size(), p.negative_swap_percentage(), p.max_same_video_negs(), 100, 1 /* rand() is never seeded */);
-  CHECK(sampler_) << "Could not add requested number of negatives";
+  sampler_ = vv_sampler_create_ex(V, vid.data(), off.data(), ids.data(), batch_size_, context_size_, num_negative_samples_,
+                                  p.max_buffer_size(), p.negative_swap_percentage(), p.max_same_video_negs(), 100,
+                                  1 /* rand() is never seeded */, int(p.context_type()));
+  CHECK(sampler_) << "Could not add requested number of negatives (or an invalid context_size for this context_type)";
   const int R = context_size_ + num_negative_samples_;
   (*top)[0]->Reshape(batch_size_, R, feature_size_, 1);     // channels = slots, height = feature (ref: :215-220)
   if (top->size() > 1) (*top)[1]->Reshape(batch_size_, 1, 1, 1);

@@ -126,10 +126,14 @@ EltwiseParameter_EltwiseOp EltwiseParameter::operation() const {
   return EltwiseParameter_EltwiseOp_SUM;
 }
 VideoSampledShotsDataParameter_ContextType VideoSampledShotsDataParameter::context_type() const {
-  const string t = m->str("context_type", "WINDOW");
+  const string t = m->str("context_type", "PAIRWISE");            // [default = PAIRWISE], caffe.proto:606
   if (t == "PAIRWISE") return VideoSampledShotsDataParameter_CONTEXT_PAIRWISE;
   if (t == "WINDOW") return VideoSampledShotsDataParameter_CONTEXT_WINDOW;
-  return VideoSampledShotsDataParameter_CONTEXT_PAST;
+  if (t == "PAST") return VideoSampledShotsDataParameter_CONTEXT_PAST;
+  if (t == "PAST_CONTINUOUS") return VideoSampledShotsDataParameter_CONTEXT_PAST_CONTINUOUS;
+  if (t == "PAST_CONTINUOUS_FIXED") return VideoSampledShotsDataParameter_CONTEXT_PAST_CONTINUOUS_FIXED;
+  LOG_FATAL << "Unknown context type " << t;
+  return VideoSampledShotsDataParameter_CONTEXT_PAIRWISE;
 }
 
 }  // namespace caffe

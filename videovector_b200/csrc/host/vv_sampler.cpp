@@ -108,6 +108,7 @@ struct FastMod {
 
 struct vv_sampler {
   int V, B, C, Nn, P, swap_pct, max_same;
+  int mode = VV_CONTEXT_WINDOW;           // VideoSampledShotsDataParameter.CONTEXT
   std::vector<int32_t> video_id, shot_off, shot_ids;
   vv_glibc_rand rng;
   int cursor;
@@ -165,7 +166,8 @@ struct vv_sampler {
       const int v = cursor;
       cursor = (cursor + 1) % V;
       const int off = shot_off[v], n = shot_off[v + 1] - off;
-      if (n < 2 || n < C) continue;                       // :387-389, :427-429 (no rand consumed)
+      if (n < 2) continue;                                // :387-389 (no rand consumed)
+      if (mode != VV_CONTEXT_PAIRWISE && n < C) continue; // :427-429, :511-513, :588-590, :676-678
       if (int(ids.size()) < n) { ids.resize(n); js.resize(std::max(n, Nn) + 1); }
       // every draw this record can consume: C (window) + n-C-1 (shuffle) + Nn (buffer) + 2n (swap)
       rng.reserve(3 * n + Nn + 8);
@@ -173,35 +175,65 @@ struct vv_sampler {
       const uint8_t* __restrict tk = rng.take.data() + rng.pos;
       int used = 0;
       int* __restrict id = ids.data();
-      for (int i = 0; i < n; ++i) id[i] = i;
-      random_unique(id, n, C, d); used += C;              // :432
-      std::sort(id, id + C);                              // :437
-      const int half = C / 2;
       int32_t* I = idx + (size_t)item * R;
       int32_t* Q = quirk + (size_t)item * R;
       int32_t* L = last_full.data() + (size_t)item * R;
-      int ctx = 0;
-      for (int i = 0; i < C; ++i) {
-        const int slot = (i == half) ? 0 : ++ctx;         // target -> slot 0, others in temporal order
-        I[slot] = off + id[i]; Q[slot] = -2; L[slot] = off + id[i];
-      }
       int added = 0;
-      if (Nn > 0 && n > C) {                              // same-video negatives :479-503
-        // std::random_shuffle(ids+C, end): for i in C+1..n-1 swap(ids[i], ids[C + rand() % (i-C+1)])
-        int* __restrict J = js.data();
-        const int cnt = n - C - 1;
-        for (int k = 0; k < cnt; ++k) J[k] = C + fm.mod(int(d[used + k] >> 1), k + 2);
-        for (int k = 0; k < cnt; ++k) std::swap(id[C + 1 + k], id[J[k]]);
-        used += cnt > 0 ? cnt : 0;
-        const int lo = id[half - 1], hi = id[half + 1];
-        // branch-free filter: the candidate is written every time and kept by advancing `added`; a rejected
-        // candidate's slot is overwritten by the next one or by the buffer negatives below
-        for (int nid = C; nid < n && added < max_same; ++nid) {
-          const int slot = C + added;
-          I[slot] = off + id[nid];
-          Q[slot] = L[slot];                              // K-1 floats copied (:492): element K-1 keeps the old value
-          added += int(id[nid] < lo) | int(id[nid] > hi);
+      if (mode == VV_CONTEXT_WINDOW || mode == VV_CONTEXT_PAST) {
+        for (int i = 0; i < n; ++i) id[i] = i;
+        random_unique(id, n, C, d); used += C;            // :432 / :516
+        std::sort(id, id + C);                            // :437 / :521
+        // WINDOW: the target is the temporal median; PAST: the last frame of the window (:523-537)
+        const int tpos = (mode == VV_CONTEXT_WINDOW) ? C / 2 : C - 1;
+        int ctx = 0;
+        for (int i = 0; i < C; ++i) {
+          const int slot = (i == tpos) ? 0 : ++ctx;       // target -> slot 0, others in temporal order
+          I[slot] = off + id[i]; Q[slot] = -2; L[slot] = off + id[i];
         }
+        if (Nn > 0 && n > C) {                            // same-video negatives :479-503 / :556-575
+          // std::random_shuffle(ids+C, end): for i in C+1..n-1 swap(ids[i], ids[C + rand() % (i-C+1)])
+          int* __restrict J = js.data();
+          const int cnt = n - C - 1;
+          for (int k = 0; k < cnt; ++k) J[k] = C + fm.mod(int(d[used + k] >> 1), k + 2);
+          for (int k = 0; k < cnt; ++k) std::swap(id[C + 1 + k], id[J[k]]);
+          used += cnt > 0 ? cnt : 0;
+          // WINDOW keeps shots outside [ids[half-1], ids[half+1]]; PAST keeps shots before the second window frame (:562)
+          const int lo = (mode == VV_CONTEXT_WINDOW) ? id[C / 2 - 1] : id[1];
+          const int hi = (mode == VV_CONTEXT_WINDOW) ? id[C / 2 + 1] : 0x7fffffff;
+          // branch-free filter: the candidate is written every time and kept by advancing `added`; a rejected
+          // candidate's slot is overwritten by the next one or by the buffer negatives below
+          for (int nid = C; nid < n && added < max_same; ++nid) {
+            const int slot = C + added;
+            I[slot] = off + id[nid];
+            Q[slot] = L[slot];                            // K-1 floats copied (:492): element K-1 keeps the old value
+            added += int(id[nid] < lo) | int(id[nid] > hi);
+          }
+        }
+      } else if (mode == VV_CONTEXT_PAIRWISE) {           // :396-404: two distinct shots, no same-video negatives
+        for (int i = 0; i < n; ++i) id[i] = i;
+        random_unique(id, n, 2, d); used += 2;
+        for (int slot = 0; slot < 2; ++slot) { I[slot] = off + id[slot]; Q[slot] = -2; L[slot] = off + id[slot]; }
+      } else {                                            // PAST_CONTINUOUS :586-671 / _FIXED :674-757
+        const int max_len = (n - C) / (C - 1);
+        int len, begin;
+        if (mode == VV_CONTEXT_PAST_CONTINUOUS) {
+          len = fm.mod(int(d[used++] >> 1), max_len + 1);                               // :596
+          begin = fm.mod(int(d[used++] >> 1), n - (C - 1) * len - C + 1);               // :598-599
+        } else {
+          len = max_len >= 1 ? max_len - 1 : 0;                                         // :685
+          begin = n - (C - 1) * len - C;                                                // :687-688
+        }
+        for (int i = 0; i < C; ++i) {                     // evenly spaced frames, the last one is the target
+          const int slot = (i == C - 1) ? 0 : i + 1;
+          const int g = off + begin + i * (len + 1);
+          I[slot] = g; Q[slot] = -2; L[slot] = g;
+        }
+        if (Nn > 0)                                       // the frames right before the window, nearest first (:645-660)
+          for (int nid = begin - 1; nid >= 0 && added < max_same; --nid) {
+            const int slot = C + added;
+            I[slot] = off + nid; Q[slot] = L[slot];
+            ++added;
+          }
       }
       if (Nn > 0) {                                       // buffer negatives :852-874
         random_unique(buffer_ids.data(), P, Nn - added, d + used); used += Nn - added;
@@ -241,8 +273,21 @@ extern "C" vv_sampler_t* vv_sampler_create(int num_videos, const int32_t* video_
                                            int num_negative_samples, int max_buffer_size,
                                            int negative_swap_percentage, int max_same_video_negs,
                                            int max_tries_for_negs, unsigned int rand_seed) {
+  return vv_sampler_create_ex(num_videos, video_id, shot_off, shot_ids, batch_size, context_size, num_negative_samples,
+                              max_buffer_size, negative_swap_percentage, max_same_video_negs, max_tries_for_negs, rand_seed,
+                              VV_CONTEXT_WINDOW);
+}
+extern "C" vv_sampler_t* vv_sampler_create_ex(int num_videos, const int32_t* video_id, const int32_t* shot_off,
+                                              const int32_t* shot_ids, int batch_size, int context_size,
+                                              int num_negative_samples, int max_buffer_size,
+                                              int negative_swap_percentage, int max_same_video_negs,
+                                              int max_tries_for_negs, unsigned int rand_seed, int context_type) {
+  if (context_type < VV_CONTEXT_PAIRWISE || context_type > VV_CONTEXT_PAST_CONTINUOUS_FIXED) return nullptr;
+  // WINDOW takes the temporal median as target (odd window); PAIRWISE fills exactly two slots
+  if (context_type == VV_CONTEXT_WINDOW && (context_size % 2) != 1) return nullptr;
+  if (context_type == VV_CONTEXT_PAIRWISE && context_size != 2) return nullptr;
   if (num_videos <= 0 || !video_id || !shot_off || !shot_ids || batch_size < 1 || context_size < 2 ||
-      (context_size % 2) != 1 || num_negative_samples < 0 || negative_swap_percentage < 0 ||
+      num_negative_samples < 0 || negative_swap_percentage < 0 ||
       negative_swap_percentage > 99 || (num_negative_samples > 0 && max_buffer_size < num_negative_samples) ||
       // the reference writes max_same_video_negs slots unconditionally (:483-499) and then draws
       // Nn - added buffer negatives; more same-video negatives than slots is undefined there, an error here
@@ -255,6 +300,7 @@ extern "C" vv_sampler_t* vv_sampler_create(int num_videos, const int32_t* video_
   s->V = num_videos; s->B = batch_size; s->C = context_size; s->Nn = num_negative_samples;
   s->P = num_negative_samples > 0 ? max_buffer_size : 0;
   s->swap_pct = negative_swap_percentage; s->max_same = max_same_video_negs;
+  s->mode = context_type;
   s->video_id.assign(video_id, video_id + num_videos);
   s->shot_off.assign(shot_off, shot_off + num_videos + 1);
   s->shot_ids.assign(shot_ids, shot_ids + shot_off[num_videos]);

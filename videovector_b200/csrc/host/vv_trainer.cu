@@ -193,7 +193,7 @@ struct vv_trainer {
 
 extern "C" vv_trainer_t* vv_trainer_create(const vv_trainer_cfg_t* cfg, vv_stream_t stream) {
   if (!cfg) { set_error("trainer cfg is NULL"); return nullptr; }
-  if (cfg->B < 1 || cfg->C < 3 || (cfg->C % 2) != 1 || cfg->Nn < 1 || cfg->K < 4 || cfg->N < 4 || (cfg->K % 4) || (cfg->N % 4)) {
+  if (cfg->B < 1 || cfg->C < 2 || cfg->Nn < 1 || cfg->K < 4 || cfg->N < 4 || (cfg->K % 4) || (cfg->N % 4)) {
     set_error("bad trainer cfg: B=%d C=%d Nn=%d K=%d N=%d", cfg->B, cfg->C, cfg->Nn, cfg->K, cfg->N); return nullptr;
   }
   if (cfg->prec < VV_PREC_FP32_SIMT || cfg->prec > VV_PREC_F16X3) { set_error("bad precision %d", cfg->prec); return nullptr; }

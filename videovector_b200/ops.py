@@ -290,20 +290,21 @@ def synthetic_videos(V, S):
 
 
 class Sampler:
-    """VideoSampledShotsDataLayer's WINDOW sampler as an index stream (host, C++)."""
+    """VideoSampledShotsDataLayer's sampler (all five context types) as an index stream (host, C++)."""
 
     def __init__(self, video_id, shot_off, shot_ids, batch_size, context_size=5, num_negative_samples=10,
                  max_buffer_size=5000, negative_swap_percentage=50, max_same_video_negs=6,
-                 max_tries_for_negs=100, rand_seed=1):
+                 max_tries_for_negs=100, rand_seed=1, context_type="window"):
         self._lib = _lib.load()
         self.video_id = np.ascontiguousarray(video_id, dtype=np.int32)
         self.shot_off = np.ascontiguousarray(shot_off, dtype=np.int32)
         self.shot_ids = np.ascontiguousarray(shot_ids, dtype=np.int32)
         self.B, self.R = batch_size, context_size + num_negative_samples
-        self._h = self._lib.vv_sampler_create(len(self.video_id), self.video_id.ctypes.data, self.shot_off.ctypes.data,
-                                              self.shot_ids.ctypes.data, batch_size, context_size, num_negative_samples,
-                                              max_buffer_size, negative_swap_percentage, max_same_video_negs,
-                                              max_tries_for_negs, rand_seed)
+        ct = _lib.CONTEXT[context_type] if isinstance(context_type, str) else int(context_type)
+        self._h = self._lib.vv_sampler_create_ex(len(self.video_id), self.video_id.ctypes.data, self.shot_off.ctypes.data,
+                                                 self.shot_ids.ctypes.data, batch_size, context_size, num_negative_samples,
+                                                 max_buffer_size, negative_swap_percentage, max_same_video_negs,
+                                                 max_tries_for_negs, rand_seed, ct)
         if not self._h:
             raise VVError("vv_sampler_create failed (bad parameters, or could not fill the negative buffer)")
 
