@@ -336,6 +336,23 @@ int vv_glibc_rand_next(vv_glibc_rand_t* g);
 void vv_glibc_rand_destroy(vv_glibc_rand_t* g);
 
 /* ------------------------------------------------------------------------- */
+/* TEST-phase evaluation (ref: mednet_embedding_train.prototxt TEST graph;      */
+/* retrieval_stats_layer.cpp:98-140 ComputeStats, :143-359 Forward_cpu).        */
+/* ------------------------------------------------------------------------- */
+/* "average_for_test": Xbar[b,:] = sum_f coeff[f] * bank[idx[b,f],:] (coeff host array or NULL = 1/F), idx [B,F]. */
+int vv_gather_mean_rows(const float* bank, int64_t bank_rows, int K, const int32_t* idx, int B, int F,
+                        const float* coeff_host, float* Xbar, vv_stream_t stream);
+/* RetrievalStatsLayer, shot level: distances -2 E E^T over the B L2-normalised embeddings E [B,N], every query
+ * ranked against all others (the query itself excluded; with exclude_same_video_shots also its video's shots),
+ * relevance = same label; queries with labels[i] < 0 are not scored.
+ *   out3 (device) = {mean AP, hit@1, hit@5}; per_query (device, [B,3], optional) = per-query values (-1 if unscored).
+ *   gram_given: optional precomputed E E^T [B,B] (then E may be NULL); workspace: vv_retrieval_stats_workspace_bytes(B). */
+size_t vv_retrieval_stats_workspace_bytes(int B);
+int vv_retrieval_stats(const float* E, int B, int N, const int32_t* video_ids, const int32_t* labels,
+                       int exclude_same_video_shots, const float* gram_given, void* workspace, size_t workspace_bytes,
+                       double* out3, double* per_query, vv_stream_t stream);
+
+/* ------------------------------------------------------------------------- */
 /* Trainer: one data-parallel rank of the fused training step                   */
 /* (gather -> fc7 fwd(+relu+dropout) -> rank loss fwd/bwd -> wgrad -> [allreduce]*/
 /*  -> sgd update), i.e. Solver::Solve's loop body (ref: solver.cpp:177-220)    */

@@ -265,3 +265,23 @@ class Sampler:
     def close(self):
         if self._h:
             lib().orc_sampler_destroy(self._h); self._h = None
+
+
+def test_embed(frames, W, bias, coeff=None):
+    """TEST-phase embedding of frames [B, F, K]: mean of the F frames -> fc7 -> ReLU -> L2 normalisation.  Returns (xbar, E)."""
+    frames = f32(frames); W = f32(W); bias = f32(bias)
+    B, F, K = frames.shape; N = W.shape[0]
+    coeff = f32(coeff if coeff is not None else np.full(F, 1.0 / F))
+    xbar = np.empty((B, K), np.float32); E = np.empty((B, N), np.float32)
+    lib().orc_test_embed(B, F, K, N, _p(frames), _p(coeff), _p(W), _p(bias), _p(xbar), _p(E))
+    return xbar, E
+
+
+def retrieval_stats(E, video_ids, labels, exclude_same_video_shots=False, dist=None):
+    """RetrievalStatsLayer (shot level).  Returns dict(map, hit1, hit5, per_query [B,3], dist [B,B])."""
+    E = f32(E); B, N = E.shape
+    vid = np.ascontiguousarray(video_ids, np.int32); lab = np.ascontiguousarray(labels, np.int32)
+    D = f32(dist).copy() if dist is not None else np.empty((B, B), np.float32)
+    out = np.zeros(3, np.float64); pq = np.empty((B, 3), np.float64)
+    lib().orc_retrieval_stats(B, N, _p(E), _p(vid), _p(lab), int(exclude_same_video_shots), _p(D), int(dist is not None), _p(out), _p(pq))
+    return dict(map=out[0], hit1=out[1], hit5=out[2], per_query=pq, dist=D)

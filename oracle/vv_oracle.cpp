@@ -845,6 +845,70 @@ int orc_sampler_next(void* h, int* idx, int* quirk, float* data) {
   return 0;
 }
 
+// ----------------------------------------------------------------------------
+// TEST phase: mednet_embedding_train.prototxt TEST graph + RetrievalStatsLayer
+// ----------------------------------------------------------------------------
+// Embedding of a test batch: frames [B, F, K] (F = 4 sampled frames per shot window) ->
+//   slice dim 1 + concat dim 0 + flatten + slice dim 0 + ELTWISE SUM coeff 1/F ("average_for_test", :85-102 of the
+//   prototxt; eltwise_layer.cpp:67-73: top = 0, then axpy per bottom) -> fc7 -> ReLU -> Dropout(TEST = copy,
+//   dropout_layer.cpp:46-48) -> NORMALIZATION ("test_norm").
+void orc_test_embed(int B, int F, int K, int N, const float* frames, const float* coeff, const float* W,
+                    const float* bias, float* xbar_out, float* E) {
+  std::vector<float> xbar((size_t)B * K, 0.f), Z((size_t)B * N), H((size_t)B * N);
+  std::vector<float> plane((size_t)B * K);
+  for (int f = 0; f < F; ++f) {
+    for (int b = 0; b < B; ++b) memcpy(&plane[(size_t)b * K], frames + ((size_t)b * F + f) * K, K * sizeof(float));
+    cpu_axpy((size_t)B * K, coeff[f], plane.data(), xbar.data());
+  }
+  if (xbar_out) memcpy(xbar_out, xbar.data(), xbar.size() * sizeof(float));
+  orc_ip_forward(B, N, K, xbar.data(), W, bias, Z.data());
+  orc_relu_forward((size_t)B * N, Z.data(), 0.f, H.data());
+  orc_normalization_forward(B, N, H.data(), E);
+}
+
+// RetrievalStatsLayer::Forward_cpu, shot-level branch (retrieval_stats_layer.cpp:143-359) with ComputeStats (:98-140).
+// E [B, N] embeddings, video_ids [B], labels [B] = video_id_to_class_[video_id] (< 0: sample not scored, :256-258).
+// dist_io: if non-NULL and *use_dist != 0 the given [B,B] matrix is used instead of -2 E E^T (to compare rank
+// statistics on identical distances); it always receives the matrix used (diagonal set to -1e15, :240-241).
+// out = {mean AP, hit@1, hit@5}; per_query (optional) [B,3].
+void orc_retrieval_stats(int B, int N, const float* E, const int* video_ids, const int* labels,
+                         int exclude_same_video_shots, float* dist_io, int use_dist, double* out, double* per_query) {
+  std::vector<float> D((size_t)B * B);
+  if (dist_io && use_dist) memcpy(D.data(), dist_io, D.size() * sizeof(float));
+  else cpu_gemm(false, true, B, B, N, -2.f, E, E, 0.f, D.data());                       // :226-228
+  double mean_ap = 0, mean_acc_1 = 0, mean_acc_5 = 0, num_positives = 0;
+  std::vector<int> sort_ids(B);
+  for (int i = 0; i < B; ++i) {
+    std::iota(sort_ids.begin(), sort_ids.end(), 0);
+    D[(size_t)i * B + i] = -1e15f;                                                      // :240-241
+    const float* row = &D[(size_t)i * B];
+    // ties broken by index: the reference's std::sort leaves their order unspecified
+    std::sort(sort_ids.begin(), sort_ids.end(), [row](int a, int b) { return row[a] < row[b] || (row[a] == row[b] && a < b); });
+    if (per_query) per_query[3 * i] = per_query[3 * i + 1] = per_query[3 * i + 2] = -1;
+    if (labels[i] < 0) continue;                                                        // :256-258
+    // ComputeStats :98-140
+    double ap = 0, acc_1 = 0, acc_5 = 0, val = 0, ret = 0;
+    for (int k = 1; k < B; ++k) {                                                       // the first hit is the query itself
+      const int j = sort_ids[k];
+      if (video_ids[j] != video_ids[i] || !exclude_same_video_shots) {
+        val++;
+        if (labels[j] == labels[i]) {
+          if (val <= 1) acc_1++;
+          if (val <= 5) acc_5++;
+          ret++;
+          ap += ret / val;
+        }
+      }
+    }
+    if (ret > 0) ap /= ret;
+    acc_5 /= 5;
+    mean_ap += ap; mean_acc_1 += acc_1; mean_acc_5 += acc_5; num_positives++;
+    if (per_query) { per_query[3 * i] = ap; per_query[3 * i + 1] = acc_1; per_query[3 * i + 2] = acc_5; }
+  }
+  if (dist_io) memcpy(dist_io, D.data(), D.size() * sizeof(float));
+  out[0] = mean_ap / num_positives; out[1] = mean_acc_1 / num_positives; out[2] = mean_acc_5 / num_positives;   // :352-354
+}
+
 void orc_srand(unsigned seed) { srand(seed); }
 int orc_rand(void) { return rand(); }
 

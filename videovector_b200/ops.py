@@ -464,3 +464,43 @@ def _device_view(ptr, shape):
     """Zero-copy torch view of trainer-owned device memory."""
     t = torch.as_tensor(_CudaArrayHolder(ptr, shape), device="cuda")
     return t.view(*shape)
+
+
+# ---- TEST-phase evaluation ------------------------------------------------------------------------------------
+def gather_mean_rows(bank, idx, coeff=None):
+    """average_for_test: mean (or coeff-weighted sum) of the F bank rows of every item.  idx [B,F] int32 (device)."""
+    B, F = idx.shape
+    K = bank.shape[1]
+    out = torch.empty((B, K), dtype=torch.float32, device=bank.device)
+    c = np.ascontiguousarray(coeff, np.float32) if coeff is not None else None
+    check(_lib.load().vv_gather_mean_rows(_ptr(bank), bank.shape[0], K, _ptr(idx), B, F, c.ctypes.data if c is not None else None,
+                                          _ptr(out), _stream()))
+    return out
+
+
+def test_embed(bank, idx, W, bias, prec="f16x3", coeff=None):
+    """The TEST graph up to `ip2_norm`: frame mean -> fc7 + ReLU (dropout is a copy in TEST) -> L2 normalisation."""
+    xbar = gather_mean_rows(bank, idx, coeff)
+    M, K = xbar.shape
+    N = W.shape[0]
+    H, _ = ip_forward(prepare_operand(xbar, prec), prepare_operand(W, prec), bias, M, N, K, prec, act=make_act(True, 0.0, DROPOUT_NONE))
+    E = torch.empty_like(H)
+    check(_lib.load().vv_l2norm_forward(_ptr(H), M, N, _ptr(E), _stream()))
+    return xbar, E
+
+
+def retrieval_stats(E, video_ids, labels, exclude_same_video_shots=False, gram=None):
+    """RetrievalStatsLayer on the device.  Returns dict(map, hit1, hit5, per_query [B,3] float64 tensor)."""
+    lib = _lib.load()
+    B, N = (E.shape if E is not None else (gram.shape[0], 0))
+    dev = (E if E is not None else gram).device
+    ws_bytes = lib.vv_retrieval_stats_workspace_bytes(B)
+    ws = torch.empty((ws_bytes + 7) // 8, dtype=torch.float64, device=dev)
+    out = torch.zeros(3, dtype=torch.float64, device=dev)
+    pq = torch.empty((B, 3), dtype=torch.float64, device=dev)
+    vid = torch.as_tensor(np.ascontiguousarray(video_ids, np.int32)).to(dev)
+    lab = torch.as_tensor(np.ascontiguousarray(labels, np.int32)).to(dev)
+    check(lib.vv_retrieval_stats(_ptr(E), B, max(N, 1), _ptr(vid), _ptr(lab), int(exclude_same_video_shots), _ptr(gram), _ptr(ws),
+                                 ws_bytes, _ptr(out), _ptr(pq), _stream()))
+    o = out.cpu().numpy()
+    return dict(map=float(o[0]), hit1=float(o[1]), hit5=float(o[2]), per_query=pq)
