@@ -260,3 +260,61 @@ def test_cli_snapshot_and_resume(tmp_path):
     assert r.returncode == 0 and "Finetuning from" in r.stderr and "Iteration 0, loss" in r.stderr
     r = subprocess.run([exe, "train", "--solver=%s" % solp, "--weights=a", "--snapshot=b"], capture_output=True, text=True, timeout=120)
     assert r.returncode != 0 and "not both" in r.stderr
+
+
+# ---- TEST-phase net ---------------------------------------------------------------------------
+def test_test_phase_net_and_solver_test(tmp_path, oracle, monkeypatch):
+    """The shipped file's TEST graph through the reference interface: data -> average_for_test -> shared fc7 ->
+    test_norm -> retrieval_stats, run by Solver::Test with the TRAIN net's (fused) weights, against the oracle's
+    restatement of the TEST graph + RetrievalStatsLayer (ref: solver.cpp:243-317, retrieval_stats_layer.cpp)."""
+    monkeypatch.setenv("VV_FUSE", "1")
+    caffe_host.set_device(0); caffe_host.set_precision("f16x3")
+    tv, ts, F, TB = 24, 10, 4, 60
+    idfile = tmp_path / "id_to_class.txt"
+    classes = {v: (v * 7) % 5 for v in range(tv)}
+    idfile.write_text("".join("%d,%d\n" % (v, c) for v, c in classes.items() if v != 3))      # video 3 unlisted -> class 0 (map operator[])
+    classes[3] = 0
+    net_txt = prototxt.train_net(test=dict(batch=TB, frames=F, videos=tv, shots=ts, seed=99, id_to_class_file=str(idfile), exclude_same=True), **CFG)
+    sol = caffe_host.Solver(prototxt.solver(base_lr=0.05, display=0, snapshot=0, test_iter=2, test_interval=1000), net_txt)
+    W0, b0, mask, mask_dev = problem()
+    sol.net.set_param(0, W0); sol.net.set_param(1, b0); sol.net.set_dropout_mask(mask_dev)
+    tnet = sol.test_net(0)
+    assert tnet.layer_names == ["shot_windows", "slice_input_data", "batch_concat_input_test", "flatten_input", "slice_test",
+                                "average_for_test", "fc7", "fc7_relu", "test_norm", "retrieval_stats"]
+    for rounds in range(2):                     # before any training step, then after two fused steps (weights moved)
+        scores = sol.test(0)
+        assert scores.shape == (3,)
+        W, b = sol.net.param(0).reshape(CFG["N"], CFG["K"]), sol.net.param(1)
+        # the last of the two test iterations is still in the test net's blobs
+        data = tnet.blob("data").reshape(TB, F, CFG["K"])
+        vids = tnet.blob("video_ids").reshape(-1).astype(np.int32)
+        xbar_ref, E_ref = oracle.test_embed(data, W, b)
+        assert rel(tnet.blob("original_feature").reshape(TB, -1), xbar_ref) < 1e-6
+        assert rel(tnet.blob("ip2_norm").reshape(TB, -1), E_ref) < 1e-5
+        labels = np.array([classes[int(v)] for v in vids], np.int32)
+        ref = oracle.retrieval_stats(E_ref, vids, labels, True)
+        last = np.array([tnet.blob("test_map")[0, 0, 0, 0], tnet.blob("test_hit_at_1")[0, 0, 0, 0], tnet.blob("test_hit_at_5")[0, 0, 0, 0]])
+        assert np.abs(last - np.array([ref["map"], ref["hit1"], ref["hit5"]])).max() < 2e-3
+        assert (scores >= 0).all() and (scores <= 1).all()
+        assert tnet.blob_names[-3:] == ["test_map", "test_hit_at_1", "test_hit_at_5"]
+        # windows are served in order: consecutive batches differ, the pass after next repeats nothing yet
+        assert vids[0] == ((2 * (2 * rounds + 1) * TB) - TB) % tv
+        if rounds == 0:
+            sol.step(); sol.step()
+    sol.close()
+
+
+def test_cli_runs_test_phase(tmp_path):
+    """`vv_caffe train` with test_iter / test_interval prints the reference's test log lines (solver.cpp:252-253, 306-313)."""
+    exe = os.path.join(ROOT, "build", "vv_caffe")
+    idfile = tmp_path / "id.txt"; idfile.write_text("".join("%d,%d\n" % (v, v % 3) for v in range(16)))
+    netp = tmp_path / "net.prototxt"; solp = tmp_path / "solver.prototxt"
+    netp.write_text(prototxt.train_net(test=dict(batch=32, videos=16, shots=8, id_to_class_file=str(idfile)), **CFG))
+    solp.write_text(prototxt.solver(str(netp), display=1, max_iter=4, snapshot=0, test_iter=1, test_interval=2))
+    r = subprocess.run([exe, "train", "--solver=%s" % solp], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert r.stderr.count("Testing net (#0)") == 3                               # iterations 0 (test_initialization), 2 and 4
+    for it in (0, 2, 4):
+        assert "Iteration %d, Testing net (#0)" % it in r.stderr
+    # net outputs come out of a std::set of blob names (net.cpp:158-165), i.e. in lexicographic order
+    assert "    Test net output #0: test_hit_at_1 = " in r.stderr and "    Test net output #2: test_map = " in r.stderr

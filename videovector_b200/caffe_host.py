@@ -40,6 +40,9 @@ def _l():
     lib.vvc_solver_history_read.argtypes = [_P, C.c_int, _P]
     lib.vvc_transform_net.argtypes = [C.c_char_p, C.c_int, _P, C.c_int]
     lib.vvc_set_stream.argtypes = [_P]
+    lib.vvc_solver_test.argtypes = [_P, C.c_int, _P, C.c_int]
+    lib.vvc_solver_test_net.restype = _P; lib.vvc_solver_test_net.argtypes = [_P, C.c_int]
+    lib.vvc_net_share_trained_layers_with.argtypes = [_P, _P]
     lib.vvc_net_save.argtypes = [_P, C.c_char_p, C.c_int]
     lib.vvc_net_copy_trained_from.argtypes = [_P, C.c_char_p]
     lib.vvc_solver_snapshot.argtypes = [_P, _P, C.c_int]
@@ -64,6 +67,10 @@ def _check(rc):
 
 def set_device(dev=0):
     _check(_l().vvc_set_device(dev))
+
+
+def set_phase(phase):
+    _l().vvc_set_phase(1 if phase == "TEST" else 0)
 
 
 def set_seed(seed):
@@ -187,6 +194,16 @@ class Solver:
             _check(self._lib.vvc_solver_solve(self._h, max_iter))
         else:
             _check(self._lib.vvc_solver_solve_resume(self._h, max_iter, str(resume).encode()))
+
+    def test(self, test_net_id=0):
+        """Solver::Test: test_iter forward passes of the TEST net on the shared weights; mean of every output value."""
+        out = np.zeros(16, np.float32)
+        n = _check(self._lib.vvc_solver_test(self._h, test_net_id, out.ctypes.data, 16))
+        return out[:n].copy()
+
+    def test_net(self, i=0):
+        h = self._lib.vvc_solver_test_net(self._h, i)
+        return Net(handle=h, owner=self) if h else None
 
     def snapshot(self):
         """Solver::Snapshot: writes <snapshot_prefix>_iter_N.caffemodel / .solverstate, returns the model path."""

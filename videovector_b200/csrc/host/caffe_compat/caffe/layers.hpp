@@ -233,4 +233,46 @@ class VideoSampledShotsDataLayer : public Layer<Dtype> {
   DeviceBuffer idx_dev_, quirk_dev_;
 };
 
+// ref: data_layers.hpp (VideoShotWindowTestDataLayer), video_shot_window_test_data_layer.cpp: the TEST-phase data layer,
+// tops = data [B, F, K, 1] (the F context frames of a shot window) and video_ids [B].  As for the TRAIN layer the
+// DB reader is out of scope: `source` is "synthetic://videos=V&shots=S&dim=K&seed=s&frames=F"; windows of F
+// consecutive shots are served in order (video by video, wrapping), so every test pass sees the same data.
+template <typename Dtype>
+class VideoShotWindowTestDataLayer : public Layer<Dtype> {
+ public:
+  explicit VideoShotWindowTestDataLayer(const LayerParameter& param) : Layer<Dtype>(param) {}
+  virtual void LayerSetUp(const vector<Blob<Dtype>*>& bottom, vector<Blob<Dtype>*>* top);
+  virtual void Reshape(const vector<Blob<Dtype>*>& bottom, vector<Blob<Dtype>*>* top) {}
+  VV_LAYER_COMMON(VideoShotWindowTestData, VIDEO_SHOT_WINDOW_TEST_DATA)
+  virtual inline int ExactNumBottomBlobs() const { return 0; }
+  virtual inline int ExactNumTopBlobs() const { return 2; }
+ protected:
+  virtual void Forward_gpu(const vector<Blob<Dtype>*>& bottom, vector<Blob<Dtype>*>* top);
+  virtual void Backward_gpu(const vector<Blob<Dtype>*>& top, const vector<bool>& propagate_down, vector<Blob<Dtype>*>* bottom) {}
+  Blob<Dtype> bank_;
+  int64_t bank_rows_ = 0;
+  int videos_ = 0, shots_ = 0, frames_ = 4, batch_size_ = 0, feature_size_ = 0;
+  long cursor_ = 0;
+  vector<int32_t> idx_host_;
+  DeviceBuffer idx_dev_;
+};
+// ref: retrieval_stats_layer.cpp (CPU only in the reference; vv_retrieval_stats on the device here), shot level:
+// bottoms = L2-normalised embeddings [B, N] and video_ids [B]; tops = mean AP, hit@1, hit@5.
+template <typename Dtype>
+class RetrievalStatsLayer : public Layer<Dtype> {
+ public:
+  explicit RetrievalStatsLayer(const LayerParameter& param) : Layer<Dtype>(param) {}
+  virtual void LayerSetUp(const vector<Blob<Dtype>*>& bottom, vector<Blob<Dtype>*>* top);
+  virtual void Reshape(const vector<Blob<Dtype>*>& bottom, vector<Blob<Dtype>*>* top);
+  VV_LAYER_COMMON(RetrievalStats, RETRIEVAL_STATS)
+  virtual inline int ExactNumBottomBlobs() const { return 2; }
+  virtual inline int ExactNumTopBlobs() const { return 3; }
+ protected:
+  virtual void Forward_gpu(const vector<Blob<Dtype>*>& bottom, vector<Blob<Dtype>*>* top);
+  virtual void Backward_gpu(const vector<Blob<Dtype>*>& top, const vector<bool>& propagate_down, vector<Blob<Dtype>*>* bottom) {}
+  std::map<int, int> video_id_to_class_;
+  bool exclude_same_video_shots_ = true;
+  DeviceBuffer ids_dev_, labels_dev_, work_, out_dev_;
+};
+
 }  // namespace caffe

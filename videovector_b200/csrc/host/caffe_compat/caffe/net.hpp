@@ -57,6 +57,10 @@ class Net {
   // copies blobs into layers of the same name; unknown source layers are ignored, shapes must match exactly
   void CopyTrainedLayersFrom(const PbMsg& net_param);
   void CopyTrainedLayersFrom(const string& trained_filename);
+  // parameter blobs of same-named layers become views of `other`'s (ref: net.cpp:638-668): the TEST net reads the
+  // weights the TRAIN net (or its fused trainer) is updating
+  void ShareTrainedLayersWith(Net* other);
+  inline const vector<Dtype>& blob_loss_weights() const { return blob_loss_weights_; }
 
   // ---- fusion ----
   // Returns true if the graph matched and the fused path is active.  `why` receives the reason if not.

@@ -43,7 +43,8 @@ enum LayerParameter_LayerType {   // values as in caffe.proto:236-302
   LayerParameter_LayerType_FLATTEN = 8, LayerParameter_LayerType_INNER_PRODUCT = 14, LayerParameter_LayerType_RELU = 18,
   LayerParameter_LayerType_SPLIT = 22, LayerParameter_LayerType_ELTWISE = 25, LayerParameter_LayerType_SLICE = 33,
   LayerParameter_LayerType_NORMALIZATION = 41, LayerParameter_LayerType_MAX_MARGIN_LOSS = 43,
-  LayerParameter_LayerType_SUM = 44, LayerParameter_LayerType_VIDEO_SAMPLED_SHOTS_DATA = 49
+  LayerParameter_LayerType_SUM = 44, LayerParameter_LayerType_RETRIEVAL_STATS = 45,
+  LayerParameter_LayerType_VIDEO_SHOT_WINDOW_TEST_DATA = 48, LayerParameter_LayerType_VIDEO_SAMPLED_SHOTS_DATA = 49
 };
 LayerParameter_LayerType LayerTypeFromName(const string& name);
 const char* LayerTypeName(LayerParameter_LayerType t);
@@ -111,6 +112,19 @@ struct VideoSampledShotsDataParameter : ParamBase {
   int context_size() const { return int(m->num("context_size", 5)); }
   VideoSampledShotsDataParameter_ContextType context_type() const;
 };
+// ref: caffe.proto:538-559 (TEST-phase data layer) and :956-967
+struct VideoShotWindowTestDataParameter : ParamBase {
+  using ParamBase::ParamBase;
+  string source() const { return m->str("source", ""); }
+  int batch_size() const { return int(m->num("batch_size", 0)); }
+};
+struct RetrievalStatsParameter : ParamBase {
+  using ParamBase::ParamBase;
+  string id_to_class_file() const { return m->str("id_to_class_file", ""); }
+  string stats_output_file() const { return m->str("stats_output_file", ""); }
+  bool exclude_same_video_shots() const { return m->boolean("exclude_same_video_shots", true); }
+  bool video_level_retrieval() const { return m->boolean("video_level_retrieval", false); }
+};
 struct NetStateRule : ParamBase { using ParamBase::ParamBase; bool has_phase() const { return m->has("phase"); } Caffe::Phase phase() const { return m->str("phase") == "TEST" ? Caffe::TEST : Caffe::TRAIN; } };
 
 struct LayerParameter : ParamBase {
@@ -140,6 +154,8 @@ struct LayerParameter : ParamBase {
   SliceParameter slice_param() const { return SliceParameter(m->sub("slice_param")); }
   ConcatParameter concat_param() const { return ConcatParameter(m->sub("concat_param")); }
   VideoSampledShotsDataParameter video_sampled_shots_data_param() const { return VideoSampledShotsDataParameter(m->sub("video_sampled_shots_data_param")); }
+  VideoShotWindowTestDataParameter video_shot_window_test_data_param() const { return VideoShotWindowTestDataParameter(m->sub("video_shot_window_test_data_param")); }
+  RetrievalStatsParameter retrieval_stats_param() const { return RetrievalStatsParameter(m->sub("retrieval_stats_param")); }
   // builders used by InsertSplits and tests
   void set_name(const string& v) { m->set_scalar("name", v); }
   void set_type(LayerParameter_LayerType t) { m->set_scalar("type", LayerTypeName(t)); }
@@ -174,6 +190,12 @@ struct SolverParameter : ParamBase {
   bool snapshot_after_train() const { return m->boolean("snapshot_after_train", true); }
   long random_seed() const { return long(m->num("random_seed", -1)); }
   int test_interval() const { return int(m->num("test_interval", 0)); }
+  int test_iter_size() const { return m->count("test_iter"); }
+  int test_iter(int i) const { return int(m->num("test_iter", 0, i)); }
+  int test_net_size() const { return m->count("test_net"); }
+  string test_net(int i) const { return m->str("test_net", "", i); }
+  bool test_initialization() const { return m->boolean("test_initialization", true); }
+  bool test_compute_loss() const { return m->boolean("test_compute_loss", false); }
   string solver_mode() const { return m->str("solver_mode", "GPU"); }
   int device_id() const { return int(m->num("device_id", 0)); }
   bool debug_info() const { return m->boolean("debug_info", false); }

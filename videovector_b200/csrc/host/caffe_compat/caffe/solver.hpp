@@ -19,6 +19,11 @@ class Solver {
   // one iteration: ForwardBackward + ComputeUpdateValue + Update (fused into one kernel sequence when the net is fused)
   Dtype Step();
   inline shared_ptr<Net<Dtype> > net() { return net_; }
+  inline const vector<shared_ptr<Net<Dtype> > >& test_nets() { return test_nets_; }
+  // ref: solver.cpp:243-317: runs test_iter forward passes of a TEST-phase net sharing the trained layers, logs and
+  // returns the mean of every output value
+  void TestAll();
+  vector<Dtype> Test(const int test_net_id = 0);
   int iter() const { return iter_; }
   const SolverParameter& param() const { return param_; }
  protected:
@@ -30,6 +35,7 @@ class Solver {
   SolverParameter param_;
   int iter_;
   shared_ptr<Net<Dtype> > net_;
+  vector<shared_ptr<Net<Dtype> > > test_nets_;
   bool presolved_ = false;
 };
 

@@ -101,6 +101,22 @@ int vvc_solver_solve(void* s, int max_iter) { GUARD(static_cast<Solver<float>*>(
 int vvc_solver_solve_resume(void* s, int max_iter, const char* state_path) {
   GUARD(static_cast<Solver<float>*>(s)->Solve(max_iter, state_path); cudaDeviceSynchronize(); return 0;)
 }
+// runs Solver::Test(test_net_id): returns the number of output values, copies up to cap of their means to out
+int vvc_solver_test(void* s, int test_net_id, float* out, int cap) {
+  GUARD(Solver<float>* sol = static_cast<Solver<float>*>(s);
+        CHECK_LT(test_net_id, int(sol->test_nets().size())) << "no such test net";
+        const vector<float> r = sol->Test(test_net_id); cudaDeviceSynchronize();
+        for (int i = 0; i < int(r.size()) && i < cap; ++i) out[i] = r[i];
+        return int(r.size());)
+}
+void* vvc_solver_test_net(void* s, int i) {
+  Solver<float>* sol = static_cast<Solver<float>*>(s);
+  return i < int(sol->test_nets().size()) ? sol->test_nets()[i].get() : nullptr;
+}
+int vvc_net_share_trained_layers_with(void* n, void* other) {
+  GUARD(static_cast<Net<float>*>(n)->ShareTrainedLayersWith(static_cast<Net<float>*>(other)); return 0;)
+}
+int vvc_set_phase(int phase) { Caffe::set_phase(phase == 1 ? Caffe::TEST : Caffe::TRAIN); return 0; }
 int vvc_solver_iter(void* s) { return static_cast<Solver<float>*>(s)->iter(); }
 int vvc_solver_history_read(void* s, int i, float* out) {
   GUARD(auto* sg = dynamic_cast<SGDSolver<float>*>(static_cast<Solver<float>*>(s)); CHECK(sg);

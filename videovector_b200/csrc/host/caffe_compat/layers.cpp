@@ -4,6 +4,7 @@
 #include <cuda_runtime_api.h>
 #include <cmath>
 #include <random>
+#include <fstream>
 #include "caffe/layers.hpp"
 
 namespace caffe {
@@ -491,6 +492,94 @@ void VideoSampledShotsDataLayer<Dtype>::Forward_gpu(const vector<Blob<Dtype>*>& 
                           nullptr, nullptr, nullptr, VV_PREC_FP32_SIMT, (*top)[0]->mutable_gpu_data(), Caffe::stream()));
 }
 
+// =================================== TEST-phase data + retrieval stats ===================================
+template <typename Dtype>
+void VideoShotWindowTestDataLayer<Dtype>::LayerSetUp(const vector<Blob<Dtype>*>& bottom, vector<Blob<Dtype>*>* top) {
+  const VideoShotWindowTestDataParameter p = this->layer_param_.video_shot_window_test_data_param();
+  const string src = p.source();
+  CHECK(src.compare(0, 12, "synthetic://") == 0)
+      << "only synthetic:// sources are built (LMDB/LevelDB readers are out of scope, SURVEY 8f); got '" << src << "'";
+  videos_ = int(UrlParam(src, "videos", 256)); shots_ = int(UrlParam(src, "shots", 32));
+  feature_size_ = int(UrlParam(src, "dim", 4096)); frames_ = int(UrlParam(src, "frames", 4));
+  const uint64_t seed = uint64_t(UrlParam(src, "seed", 4321));
+  batch_size_ = p.batch_size();
+  CHECK_GE(batch_size_, 1); CHECK_GE(frames_, 1); CHECK_GE(shots_, frames_);
+  bank_rows_ = int64_t(videos_) * shots_;
+  bank_.Reshape(int(bank_rows_), 1, feature_size_, 1);
+  VV_CHECK(vv_fill_bank(bank_.mutable_gpu_data(), bank_rows_, feature_size_, seed, Caffe::stream()));
+  (*top)[0]->Reshape(batch_size_, frames_, feature_size_, 1);     // channels = frames, height = feature
+  (*top)[1]->Reshape(batch_size_, 1, 1, 1);
+  idx_host_.resize(size_t(batch_size_) * frames_);
+}
+template <typename Dtype>
+void VideoShotWindowTestDataLayer<Dtype>::Forward_gpu(const vector<Blob<Dtype>*>& bottom, vector<Blob<Dtype>*>* top) {
+  // record c = window number: video c % V, first shot ((c / V) * frames) % (S - frames + 1)
+  Dtype* ids = (*top)[1]->mutable_cpu_data();
+  for (int b = 0; b < batch_size_; ++b, ++cursor_) {
+    const int v = int(cursor_ % videos_);
+    const int start = int(((cursor_ / videos_) * frames_) % (shots_ - frames_ + 1));
+    for (int f = 0; f < frames_; ++f) idx_host_[size_t(b) * frames_ + f] = v * shots_ + start + f;
+    ids[b] = Dtype(v);
+  }
+  const size_t bytes = idx_host_.size() * sizeof(int32_t);
+  int32_t* di = static_cast<int32_t*>(idx_dev_.get(bytes));
+  CHECK_EQ(int(cudaMemcpyAsync(di, idx_host_.data(), bytes, cudaMemcpyHostToDevice, reinterpret_cast<cudaStream_t>(Caffe::stream()))), 0);
+  VV_CHECK(vv_gather_rows(bank_.gpu_data(), bank_rows_, feature_size_, di, nullptr, batch_size_, frames_, nullptr, nullptr, nullptr,
+                          VV_PREC_FP32_SIMT, (*top)[0]->mutable_gpu_data(), Caffe::stream()));
+  CHECK_EQ(int(cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(Caffe::stream()))), 0);   // idx_host_ is reused by the next call
+}
+
+// ref: retrieval_stats_layer.cpp:20-66 (id,class text file), :71-84 Reshape, :143-359 Forward_cpu
+template <typename Dtype>
+void RetrievalStatsLayer<Dtype>::LayerSetUp(const vector<Blob<Dtype>*>& bottom, vector<Blob<Dtype>*>* top) {
+  const RetrievalStatsParameter p = this->layer_param_.retrieval_stats_param();
+  CHECK(!p.video_level_retrieval()) << "video_level_retrieval is not built";
+  CHECK(p.stats_output_file().empty()) << "stats_output_file is not built";
+  exclude_same_video_shots_ = p.exclude_same_video_shots();
+  std::ifstream f(p.id_to_class_file().c_str());
+  CHECK(f.good()) << "cannot open id_to_class_file " << p.id_to_class_file();
+  string line;
+  while (std::getline(f, line)) {
+    if (line.empty()) continue;
+    const size_t comma = line.find(',');
+    CHECK(comma != string::npos && line.find(',', comma + 1) == string::npos) << "id_to_class_file: expected 'video_id,class_id', got '" << line << "'";
+    char* e1 = nullptr; char* e2 = nullptr;
+    const long vid = strtol(line.c_str(), &e1, 10), cls = strtol(line.c_str() + comma + 1, &e2, 10);
+    CHECK(e1 == line.c_str() + comma && *e2 == 0) << "id_to_class_file: bad line '" << line << "'";
+    video_id_to_class_.insert(std::make_pair(int(vid), int(cls)));
+  }
+  CHECK_GE(int(video_id_to_class_.size()), 1) << "need atleast one entry in id-to-class map!";
+}
+template <typename Dtype>
+void RetrievalStatsLayer<Dtype>::Reshape(const vector<Blob<Dtype>*>& bottom, vector<Blob<Dtype>*>* top) {
+  CHECK_EQ(bottom[0]->num(), bottom[1]->num()) << "The data and label should have the same number.";
+  CHECK_EQ(bottom[1]->channels(), 1); CHECK_EQ(bottom[1]->height(), 1); CHECK_EQ(bottom[1]->width(), 1);
+  for (int i = 0; i < 3; ++i) (*top)[i]->Reshape(1, 1, 1, 1);      // mean AP, hit@1, hit@5
+}
+template <typename Dtype>
+void RetrievalStatsLayer<Dtype>::Forward_gpu(const vector<Blob<Dtype>*>& bottom, vector<Blob<Dtype>*>* top) {
+  const int B = bottom[0]->num(), N = bottom[0]->count() / bottom[0]->num();
+  const Dtype* vids = bottom[1]->cpu_data();
+  vector<int32_t> ids(B), labels(B);
+  for (int b = 0; b < B; ++b) {
+    ids[b] = static_cast<int>(vids[b]);
+    labels[b] = video_id_to_class_[ids[b]];        // operator[]: an unlisted video gets class 0, as in the reference (:249-253)
+  }
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(Caffe::stream());
+  int32_t* d_ids = static_cast<int32_t*>(ids_dev_.get(sizeof(int32_t) * B));
+  int32_t* d_lab = static_cast<int32_t*>(labels_dev_.get(sizeof(int32_t) * B));
+  CHECK_EQ(int(cudaMemcpyAsync(d_ids, ids.data(), sizeof(int32_t) * B, cudaMemcpyHostToDevice, s)), 0);
+  CHECK_EQ(int(cudaMemcpyAsync(d_lab, labels.data(), sizeof(int32_t) * B, cudaMemcpyHostToDevice, s)), 0);
+  const size_t ws = vv_retrieval_stats_workspace_bytes(B);
+  double* out = static_cast<double*>(out_dev_.get(3 * sizeof(double)));
+  VV_CHECK(vv_retrieval_stats(bottom[0]->gpu_data(), B, N, d_ids, d_lab, exclude_same_video_shots_ ? 1 : 0, nullptr, work_.get(ws), ws,
+                              out, nullptr, Caffe::stream()));
+  double host[3];
+  CHECK_EQ(int(cudaMemcpyAsync(host, out, sizeof(host), cudaMemcpyDeviceToHost, s)), 0);
+  CHECK_EQ(int(cudaStreamSynchronize(s)), 0);
+  for (int i = 0; i < 3; ++i) (*top)[i]->mutable_cpu_data()[0] = Dtype(host[i]);
+}
+
 // =================================== factory ===================================
 template <typename Dtype>
 Layer<Dtype>* GetLayer(const LayerParameter& param) {
@@ -508,6 +597,8 @@ Layer<Dtype>* GetLayer(const LayerParameter& param) {
     case LayerParameter_LayerType_SPLIT: return new SplitLayer<Dtype>(param);
     case LayerParameter_LayerType_SUM: return new SumLayer<Dtype>(param);
     case LayerParameter_LayerType_VIDEO_SAMPLED_SHOTS_DATA: return new VideoSampledShotsDataLayer<Dtype>(param);
+    case LayerParameter_LayerType_VIDEO_SHOT_WINDOW_TEST_DATA: return new VideoShotWindowTestDataLayer<Dtype>(param);
+    case LayerParameter_LayerType_RETRIEVAL_STATS: return new RetrievalStatsLayer<Dtype>(param);
     case LayerParameter_LayerType_NONE: LOG_FATAL << "Layer " << name << " has unspecified or unsupported type '" << param.m->str("type") << "'.";
     default: LOG_FATAL << "Layer " << name << " has unknown type " << param.type();
   }
@@ -518,5 +609,6 @@ template class InnerProductLayer<float>; template class ReLULayer<float>; templa
 template class SliceLayer<float>; template class ConcatLayer<float>; template class FlattenLayer<float>;
 template class SplitLayer<float>; template class EltwiseLayer<float>; template class NormalizationLayer<float>;
 template class SumLayer<float>; template class MaxMarginLossLayer<float>; template class VideoSampledShotsDataLayer<float>;
+template class VideoShotWindowTestDataLayer<float>; template class RetrievalStatsLayer<float>;
 
 }  // namespace caffe

@@ -357,6 +357,24 @@ void Net<Dtype>::CopyTrainedLayersFrom(const PbMsg& param) {
   if (trainer_) VV_CHECK(vv_trainer_sync_weights(trainer_));   // refresh the GEMM operand copy of W
 }
 template <typename Dtype>
+void Net<Dtype>::ShareTrainedLayersWith(Net* other) {
+  for (size_t i = 0; i < other->layers().size(); ++i) {
+    Layer<Dtype>* source_layer = other->layers()[i].get();
+    const string& source_layer_name = other->layer_names()[i];
+    size_t target = 0;
+    while (target != layer_names_.size() && layer_names_[target] != source_layer_name) ++target;
+    if (target == layer_names_.size()) continue;
+    vector<shared_ptr<Blob<Dtype> > >& target_blobs = layers_[target]->blobs();
+    CHECK_EQ(target_blobs.size(), source_layer->blobs().size()) << "Incompatible number of blobs for layer " << source_layer_name;
+    for (size_t j = 0; j < target_blobs.size(); ++j) {
+      Blob<Dtype>* source_blob = source_layer->blobs()[j].get();
+      CHECK_EQ(target_blobs[j]->num(), source_blob->num()); CHECK_EQ(target_blobs[j]->channels(), source_blob->channels());
+      CHECK_EQ(target_blobs[j]->height(), source_blob->height()); CHECK_EQ(target_blobs[j]->width(), source_blob->width());
+      target_blobs[j]->ShareData(*source_blob);
+    }
+  }
+}
+template <typename Dtype>
 void Net<Dtype>::CopyTrainedLayersFrom(const string& trained_filename) {
   CopyTrainedLayersFrom(*ReadProtoFromBinaryFile(trained_filename, "NetParameter"));
 }

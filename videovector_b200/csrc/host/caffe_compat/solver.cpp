@@ -20,7 +20,61 @@ void Solver<Dtype>::Init(const SolverParameter& param) {
     string why;
     if (!net_->EnableFusion(&why)) LogInfo("net not fused (" + why + "): running layer by layer");
   }
+  // TEST nets (ref: solver.cpp:104-157 InitTestNets): one per `test_net` file, else the `net` file itself, each filtered
+  // to phase TEST; every test net needs its test_iter
+  if (param_.test_iter_size() > 0) {
+    vector<string> files;
+    for (int i = 0; i < param_.test_net_size(); ++i) files.push_back(param_.test_net(i));
+    if (files.empty()) files.push_back(net_file);
+    CHECK_EQ(int(files.size()), param_.test_iter_size()) << "test_iter must be specified for each test network.";
+    CHECK_GT(param_.test_interval(), 0) << "test_interval must be positive when test nets are given";
+    for (size_t i = 0; i < files.size(); ++i) {
+      LogInfo("Creating test net (#" + std::to_string(i) + ") specified by net file: " + files[i]);
+      test_nets_.push_back(shared_ptr<Net<Dtype> >(new Net<Dtype>(files[i], Caffe::TEST)));
+    }
+  }
   iter_ = 0;
+}
+
+template <typename Dtype>
+void Solver<Dtype>::TestAll() { for (size_t i = 0; i < test_nets_.size(); ++i) Test(int(i)); }
+
+template <typename Dtype>
+vector<Dtype> Solver<Dtype>::Test(const int test_net_id) {
+  fprintf(stderr, "Iteration %d, Testing net (#%d)\n", iter_, test_net_id);
+  Caffe::set_phase(Caffe::TEST);                       // dropout becomes a copy
+  CHECK(test_nets_[test_net_id]);
+  const shared_ptr<Net<Dtype> >& test_net = test_nets_[test_net_id];
+  test_net->ShareTrainedLayersWith(net_.get());
+  vector<Dtype> test_score;
+  vector<int> test_score_output_id;
+  Dtype loss = 0;
+  const int iters = param_.test_iter(test_net_id);
+  for (int i = 0; i < iters; ++i) {
+    Dtype iter_loss = 0;
+    const vector<Blob<Dtype>*>& result = test_net->ForwardPrefilled(&iter_loss);
+    if (param_.test_compute_loss()) loss += iter_loss;
+    int idx = 0;
+    for (size_t j = 0; j < result.size(); ++j) {
+      const Dtype* v = result[j]->cpu_data();
+      for (int k = 0; k < result[j]->count(); ++k) {
+        if (i == 0) { test_score.push_back(v[k]); test_score_output_id.push_back(int(j)); }
+        else test_score[idx++] += v[k];
+      }
+    }
+  }
+  if (param_.test_compute_loss()) fprintf(stderr, "Test loss: %g\n", double(loss / iters));
+  for (size_t i = 0; i < test_score.size(); ++i) {
+    const int output_blob_index = test_net->output_blob_indices()[test_score_output_id[i]];
+    const string& output_name = test_net->blob_names()[output_blob_index];
+    const Dtype loss_weight = test_net->blob_loss_weights()[output_blob_index];
+    test_score[i] /= iters;
+    if (loss_weight) fprintf(stderr, "    Test net output #%zu: %s = %g (* %g = %g loss)\n", i, output_name.c_str(), double(test_score[i]),
+                             double(loss_weight), double(loss_weight * test_score[i]));
+    else fprintf(stderr, "    Test net output #%zu: %s = %g\n", i, output_name.c_str(), double(test_score[i]));
+  }
+  Caffe::set_phase(Caffe::TRAIN);
+  return test_score;
 }
 
 template <typename Dtype>
@@ -81,6 +135,7 @@ void Solver<Dtype>::Solve(int max_iter, const char* resume_file) {
   const int start_iter = iter_;
   for (; iter_ < stop;) {
     if (param_.snapshot() && iter_ > start_iter && iter_ % param_.snapshot() == 0) Snapshot();
+    if (!test_nets_.empty() && iter_ % param_.test_interval() == 0 && (iter_ > 0 || param_.test_initialization())) TestAll();
     const int it = iter_;
     const Dtype loss = Step();
     if (param_.display() && it % param_.display() == 0) {
@@ -98,6 +153,7 @@ void Solver<Dtype>::Solve(int max_iter, const char* resume_file) {
   }
   // "Always save a snapshot after optimization, unless overridden" (solver.cpp:225-227); only when a prefix is configured
   if (max_iter < 0 && param_.snapshot_after_train() && !param_.snapshot_prefix().empty()) Snapshot();
+  if (!test_nets_.empty() && iter_ % param_.test_interval() == 0) TestAll();          // solver.cpp:237-239
 }
 
 template <typename Dtype>

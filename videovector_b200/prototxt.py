@@ -5,7 +5,9 @@ feature bank because the LMDB reader is out of scope."""
 
 
 def train_net(B=128, C=5, Nn=10, K=4096, N=512, dropout=0.9, margin=2.0, norm="L2", videos=2048, shots=32, seed=1234,
-              max_buffer_size=5000, swap=50, max_same=6, name="med_embedding"):
+              max_buffer_size=5000, swap=50, max_same=6, name="med_embedding", test=None):
+    """test = dict(batch=673, frames=4, videos=.., shots=.., seed=.., id_to_class_file=.., exclude_same=True) adds the shipped
+    file's TEST-phase graph (data -> frame average -> shared fc7 -> test_norm -> retrieval_stats)."""
     L = []
 
     def layer(s, both_phases=False):
@@ -49,16 +51,40 @@ def train_net(B=128, C=5, Nn=10, K=4096, N=512, dropout=0.9, margin=2.0, norm="L
           '  top: "negative_score"\n  concat_param {\n    concat_dim: 1\n  }\n')
     layer('  name: "max_margin_loss"\n  type: MAX_MARGIN_LOSS\n  bottom: "target_score"\n  bottom: "negative_score"\n  top: "loss_output"\n'
           '  top: "train_violations"\n  loss_weight: 1\n  loss_weight: 0\n  max_margin_loss_param {\n    norm: %s\n    margin: %g\n  }\n' % (norm, margin))
-    # one TEST-only layer like the shipped file, to exercise phase filtering
-    test = ('layers {\n  name: "test_norm"\n  type: NORMALIZATION\n  bottom: "ip2"\n  top: "ip2_norm"\n  include: { phase: TEST }\n}\n')
-    return 'name: "%s"\n' % name + "".join(L[:7]) + test + "".join(L[7:])
+    # the TEST-only layers of the shipped file (:29-45, 75-177, 345-352, 673-689); without `test` only test_norm, to
+    # exercise phase filtering
+    norm_l = 'layers {\n  name: "test_norm"\n  type: NORMALIZATION\n  bottom: "ip2"\n  top: "ip2_norm"\n  include: { phase: TEST }\n}\n'
+    head, tail = "", ""
+    if test:
+        F = test.get("frames", 4)
+        fr = ["context_datum_%d" % i for i in range(1, F + 1)]
+        sl = ["test_sample_frame_%d" % i for i in range(1, F + 1)]
+
+        def tl(s):
+            return "layers {\n" + s.rstrip() + "\n  include: { phase: TEST }\n}\n"
+        head = (tl('  name: "shot_windows"\n  type: VIDEO_SHOT_WINDOW_TEST_DATA\n  top: "data"\n  top: "video_ids"\n  video_shot_window_test_data_param {\n'
+                   '    source: "synthetic://videos=%d&shots=%d&dim=%d&seed=%d&frames=%d"\n    backend: LMDB\n    batch_size: %d\n  }\n'
+                   % (test.get("videos", 128), test.get("shots", 16), K, test.get("seed", 4321), F, test.get("batch", 673))) +
+                tl('  name: "slice_input_data"\n  type: SLICE\n  bottom: "data"\n' + tops(fr) + '  slice_param {\n    slice_dim: 1\n  }\n') +
+                tl('  name: "batch_concat_input_test"\n  type: CONCAT\n' + tops(fr, "bottom") + '  top: "concat_input_datums"\n  concat_param {\n    concat_dim: 0\n  }\n') +
+                tl('  name: "flatten_input"\n  type: FLATTEN\n  bottom: "concat_input_datums"\n  top: "concat_input_datums_flat"\n') +
+                tl('  name: "slice_test"\n  type: SLICE\n  bottom: "concat_input_datums_flat"\n' + tops(sl) + '  slice_param {\n    slice_dim: 0\n  }\n') +
+                tl('  name: "average_for_test"\n  type: ELTWISE\n' + tops(sl, "bottom") + '  top: "original_feature"\n  eltwise_param {\n    operation: SUM\n' +
+                   "".join("    coeff: %.10g\n" % (1.0 / F) for _ in sl) + '  }\n'))
+        tail = tl('  name: "retrieval_stats"\n  type: RETRIEVAL_STATS\n  bottom: "ip2_norm"\n  bottom: "video_ids"\n  top: "test_map"\n  top: "test_hit_at_1"\n'
+                  '  top: "test_hit_at_5"\n  retrieval_stats_param {\n    id_to_class_file: "%s"\n    exclude_same_video_shots: %s\n  }\n'
+                  % (test["id_to_class_file"], "true" if test.get("exclude_same", True) else "false"))
+    return 'name: "%s"\n' % name + "".join(L[:4]) + head + "".join(L[4:7]) + norm_l + "".join(L[7:]) + tail
 
 
 def solver(net_path="", base_lr=0.001, momentum=0.9, weight_decay=0.0005, lr_policy="inv", gamma=0.001, power=0.75,
-           max_iter=200000, display=10, random_seed=None, snapshot=2000, snapshot_prefix=None):
+           max_iter=200000, display=10, random_seed=None, snapshot=2000, snapshot_prefix=None, test_iter=None, test_interval=50,
+           test_initialization=True):
     s = ('net: "%s"\n' % net_path if net_path else "") + (
         "base_lr: %g\nmomentum: %g\nweight_decay: %g\nlr_policy: \"%s\"\ngamma: %g\npower: %g\n"
         "display: %d\nmax_iter: %d\nsnapshot: %d\nsolver_mode: GPU\n" % (base_lr, momentum, weight_decay, lr_policy, gamma, power, display, max_iter, snapshot))
+    if test_iter is not None:
+        s += "test_iter: %d\ntest_interval: %d\ntest_initialization: %s\n" % (test_iter, test_interval, "true" if test_initialization else "false")
     if snapshot_prefix is not None:
         s += 'snapshot_prefix: "%s"\n' % snapshot_prefix
     if random_seed is not None:
