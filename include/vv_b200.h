@@ -352,6 +352,12 @@ int vv_retrieval_stats(const float* E, int B, int N, const int32_t* video_ids, c
                        int exclude_same_video_shots, const float* gram_given, void* workspace, size_t workspace_bytes,
                        double* out3, double* per_query, vv_stream_t stream);
 
+/* IdToWeightMapping: a per-id embedding table (ref: id_to_weight_mapping_layer.cpp:61-148; CPU loops in the reference).
+ *  forward : top[i,:] = table[ids[i],:]        ids [M] floats holding integers (a Caffe blob), table [rows, N]
+ *  backward: table_diff = 0, then += top_diff[i,:] into row ids[i] in increasing i (deterministic, the reference's order) */
+int vv_id_lookup_forward(const float* table, int rows, int N, const float* ids, int M, float* top, vv_stream_t stream);
+int vv_id_lookup_backward(const float* top_diff, const float* ids, int M, int N, int rows, float* table_diff, vv_stream_t stream);
+
 /* ------------------------------------------------------------------------- */
 /* Trainer: one data-parallel rank of the fused training step                   */
 /* (gather -> fc7 fwd(+relu+dropout) -> rank loss fwd/bwd -> wgrad -> [allreduce]*/

@@ -285,3 +285,15 @@ def retrieval_stats(E, video_ids, labels, exclude_same_video_shots=False, dist=N
     out = np.zeros(3, np.float64); pq = np.empty((B, 3), np.float64)
     lib().orc_retrieval_stats(B, N, _p(E), _p(vid), _p(lab), int(exclude_same_video_shots), _p(D), int(dist is not None), _p(out), _p(pq))
     return dict(map=out[0], hit1=out[1], hit5=out[2], per_query=pq, dist=D)
+
+
+def id_lookup_forward(table, ids):
+    table = f32(table); ids = f32(ids); top = np.empty((ids.size, table.shape[1]), np.float32)
+    lib().orc_id_lookup_forward(ids.size, table.shape[1], _p(table), _p(ids), _p(top))
+    return top
+
+
+def id_lookup_backward(top_diff, ids, rows):
+    top_diff = f32(top_diff); ids = f32(ids); d = np.empty((rows, top_diff.shape[1]), np.float32)
+    lib().orc_id_lookup_backward(ids.size, top_diff.shape[1], rows, _p(top_diff), _p(ids), _p(d))
+    return d

@@ -909,6 +909,15 @@ void orc_retrieval_stats(int B, int N, const float* E, const int* video_ids, con
   out[0] = mean_ap / num_positives; out[1] = mean_acc_1 / num_positives; out[2] = mean_acc_5 / num_positives;   // :352-354
 }
 
+// IdToWeightMappingLayer (id_to_weight_mapping_layer.cpp:61-77 forward, :80-107 backward)
+void orc_id_lookup_forward(int M, int N, const float* table, const float* ids, float* top) {
+  for (int i = 0; i < M; ++i) memcpy(top + (size_t)i * N, table + (size_t)static_cast<int>(ids[i]) * N, N * sizeof(float));
+}
+void orc_id_lookup_backward(int M, int N, int rows, const float* top_diff, const float* ids, float* table_diff) {
+  memset(table_diff, 0, (size_t)rows * N * sizeof(float));                                   // caffe_set :98
+  for (int i = 0; i < M; ++i) cpu_axpy(N, 1.f, top_diff + (size_t)i * N, table_diff + (size_t)static_cast<int>(ids[i]) * N);   // :100-106
+}
+
 void orc_srand(unsigned seed) { srand(seed); }
 int orc_rand(void) { return rand(); }
 

@@ -87,3 +87,22 @@ def test_retrieval_stats_argument_checks():
         ops.retrieval_stats(torch.zeros(9000, 8, device="cuda"), np.zeros(9000), np.zeros(9000))      # > 8192 items
     out = ops.retrieval_stats(E, [1, 1, 2, 2], [-1, -1, -1, -1])
     assert np.isnan(out["map"])                                                                       # nothing scored: 0/0 as in the reference
+
+
+# ---- IdToWeightMapping ---------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,rows", [(4096, 512, 300), (64, 64, 1000), (7, 5, 3), (1, 33, 9)])
+def test_id_lookup_matches_oracle_bit_exact(oracle, M, N, rows):
+    """Forward = row gather; backward = scatter-add in increasing item order (id_to_weight_mapping_layer.cpp:61-106):
+    the device result is bit-identical to the reference's sequential axpy loop, duplicates included."""
+    rng = np.random.RandomState(M + N)
+    table = rng.normal(0, 1, (rows, N)).astype(np.float32)
+    ids = rng.randint(0, rows, M).astype(np.float32)                         # ids travel as floats in a Caffe blob
+    ids[: M // 3] = ids[0]                                                     # heavy duplication
+    dtop = rng.normal(0, 1, (M, N)).astype(np.float32)
+    top = ops.id_lookup_forward(torch.as_tensor(table).cuda(), torch.as_tensor(ids).cuda())
+    assert np.array_equal(top.cpu().numpy(), oracle.id_lookup_forward(table, ids))
+    d = ops.id_lookup_backward(torch.as_tensor(dtop).cuda(), torch.as_tensor(ids).cuda(), rows)
+    ref = oracle.id_lookup_backward(dtop, ids, rows)
+    assert np.array_equal(d.cpu().numpy(), ref)
+    untouched = np.setdiff1d(np.arange(rows), ids.astype(int))
+    assert (d.cpu().numpy()[untouched] == 0).all()

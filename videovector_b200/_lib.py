@@ -101,6 +101,8 @@ SIGNATURES = {
     "vv_max_margin_backward": (_i, [_P, _P, _i, _f, _i, _f, _P, _P, _P]),
     "vv_fill_bank": (_i, [_P, _i64, _i, _u64, _P]),
     "vv_bank_value_host": (_f, [_u64, _i64, _i, _i]),
+    "vv_id_lookup_forward": (_i, [_P, _i, _i, _P, _i, _P, _P]),
+    "vv_id_lookup_backward": (_i, [_P, _P, _i, _i, _i, _P, _P]),
     "vv_gather_mean_rows": (_i, [_P, _i64, _i, _P, _i, _i, _P, _P, _P]),
     "vv_retrieval_stats_workspace_bytes": (C.c_size_t, [_i]),
     "vv_retrieval_stats": (_i, [_P, _i, _i, _P, _P, _i, _P, _P, C.c_size_t, _P, _P, _P]),

@@ -233,6 +233,22 @@ class VideoSampledShotsDataLayer : public Layer<Dtype> {
   DeviceBuffer idx_dev_, quirk_dev_;
 };
 
+// ref: vision_layers.hpp (IdToWeightMappingLayer), id_to_weight_mapping_layer.cpp: a [max_ids, num_output] table indexed by
+// the bottom's ids (one per item); the gradient flows to the table only.  Host loops in the reference, kernels here.
+template <typename Dtype>
+class IdToWeightMappingLayer : public Layer<Dtype> {
+ public:
+  explicit IdToWeightMappingLayer(const LayerParameter& param) : Layer<Dtype>(param) {}
+  virtual void LayerSetUp(const vector<Blob<Dtype>*>& bottom, vector<Blob<Dtype>*>* top);
+  virtual void Reshape(const vector<Blob<Dtype>*>& bottom, vector<Blob<Dtype>*>* top);
+  VV_LAYER_COMMON(IdToWeightMapping, ID_TO_WEIGHT_MAPPING)
+  virtual inline int ExactNumBottomBlobs() const { return 1; }
+  virtual inline int ExactNumTopBlobs() const { return 1; }
+ protected:
+  virtual void Forward_gpu(const vector<Blob<Dtype>*>& bottom, vector<Blob<Dtype>*>* top);
+  virtual void Backward_gpu(const vector<Blob<Dtype>*>& top, const vector<bool>& propagate_down, vector<Blob<Dtype>*>* bottom);
+  int M_ = 0, K_ = 0, N_ = 0;
+};
 // ref: data_layers.hpp (VideoShotWindowTestDataLayer), video_shot_window_test_data_layer.cpp: the TEST-phase data layer,
 // tops = data [B, F, K, 1] (the F context frames of a shot window) and video_ids [B].  As for the TRAIN layer the
 // DB reader is out of scope: `source` is "synthetic://videos=V&shots=S&dim=K&seed=s&frames=F"; windows of F

@@ -42,7 +42,7 @@ enum LayerParameter_LayerType {   // values as in caffe.proto:236-302
   LayerParameter_LayerType_NONE = 0, LayerParameter_LayerType_CONCAT = 3, LayerParameter_LayerType_DROPOUT = 6,
   LayerParameter_LayerType_FLATTEN = 8, LayerParameter_LayerType_INNER_PRODUCT = 14, LayerParameter_LayerType_RELU = 18,
   LayerParameter_LayerType_SPLIT = 22, LayerParameter_LayerType_ELTWISE = 25, LayerParameter_LayerType_SLICE = 33,
-  LayerParameter_LayerType_NORMALIZATION = 41, LayerParameter_LayerType_MAX_MARGIN_LOSS = 43,
+  LayerParameter_LayerType_NORMALIZATION = 41, LayerParameter_LayerType_ID_TO_WEIGHT_MAPPING = 42, LayerParameter_LayerType_MAX_MARGIN_LOSS = 43,
   LayerParameter_LayerType_SUM = 44, LayerParameter_LayerType_RETRIEVAL_STATS = 45,
   LayerParameter_LayerType_VIDEO_SHOT_WINDOW_TEST_DATA = 48, LayerParameter_LayerType_VIDEO_SAMPLED_SHOTS_DATA = 49
 };
@@ -74,6 +74,12 @@ struct InnerProductParameter : ParamBase {
   FillerParameter weight_filler() const { return FillerParameter(m->sub("weight_filler")); }
   FillerParameter bias_filler() const { return FillerParameter(m->sub("bias_filler")); }
   float regularization() const { return float(m->num("regularization", 0)); }   // fork-added, proto:836
+};
+struct IdToWeightMappingParameter : ParamBase {     // caffe.proto:824-828
+  using ParamBase::ParamBase;
+  int num_output() const { return int(m->num("num_output", 0)); }
+  int max_ids() const { return int(m->num("max_ids", 0)); }
+  FillerParameter weight_filler() const { return FillerParameter(m->sub("weight_filler")); }
 };
 struct EltwiseParameter : ParamBase {
   using ParamBase::ParamBase;
@@ -147,6 +153,7 @@ struct LayerParameter : ParamBase {
   int blobs_size() const { return 0; }   // serialized blobs arrive through CopyTrainedLayersFrom, not text
   InnerProductParameter inner_product_param() const { return InnerProductParameter(m->sub("inner_product_param")); }
   EltwiseParameter eltwise_param() const { return EltwiseParameter(m->sub("eltwise_param")); }
+  IdToWeightMappingParameter id_to_weight_mapping_param() const { return IdToWeightMappingParameter(m->sub("id_to_weight_mapping_param")); }
   SumParameter sum_param() const { return SumParameter(m->sub("sum_param")); }
   MaxMarginLossParameter max_margin_loss_param() const { return MaxMarginLossParameter(m->sub("max_margin_loss_param")); }
   DropoutParameter dropout_param() const { return DropoutParameter(m->sub("dropout_param")); }

@@ -492,6 +492,42 @@ void VideoSampledShotsDataLayer<Dtype>::Forward_gpu(const vector<Blob<Dtype>*>& 
                           nullptr, nullptr, nullptr, VV_PREC_FP32_SIMT, (*top)[0]->mutable_gpu_data(), Caffe::stream()));
 }
 
+// =================================== IdToWeightMapping ===================================
+template <typename Dtype>
+void IdToWeightMappingLayer<Dtype>::LayerSetUp(const vector<Blob<Dtype>*>& bottom, vector<Blob<Dtype>*>* top) {
+  const IdToWeightMappingParameter p = this->layer_param_.id_to_weight_mapping_param();
+  K_ = p.max_ids(); N_ = p.num_output();
+  CHECK_GE(K_, 1); CHECK_GE(N_, 1);
+  CHECK_EQ(bottom[0]->count(), bottom[0]->num());
+  if (this->blobs_.size() > 0) {
+    LogInfo("Skipping parameter initialization");
+  } else {
+    this->blobs_.resize(1);
+    this->blobs_[0].reset(new Blob<Dtype>(K_, N_, 1, 1));
+    Fill(p.weight_filler(), this->blobs_[0].get(), 3);
+  }
+  this->param_propagate_down_.resize(this->blobs_.size(), true);
+}
+template <typename Dtype>
+void IdToWeightMappingLayer<Dtype>::Reshape(const vector<Blob<Dtype>*>& bottom, vector<Blob<Dtype>*>* top) {
+  M_ = bottom[0]->num();
+  CHECK_EQ(bottom[0]->count(), M_) << "Input size incompatible with inner product parameters.";
+  (*top)[0]->Reshape(M_, N_, 1, 1);
+}
+template <typename Dtype>
+void IdToWeightMappingLayer<Dtype>::Forward_gpu(const vector<Blob<Dtype>*>& bottom, vector<Blob<Dtype>*>* top) {
+  const Dtype* ids = bottom[0]->cpu_data();
+  for (int i = 0; i < M_; ++i) CHECK(int(ids[i]) >= 0 && int(ids[i]) < K_) << "id " << ids[i] << " outside [0, max_ids)";
+  VV_CHECK(vv_id_lookup_forward(this->blobs_[0]->gpu_data(), K_, N_, bottom[0]->gpu_data(), M_, (*top)[0]->mutable_gpu_data(), Caffe::stream()));
+}
+template <typename Dtype>
+void IdToWeightMappingLayer<Dtype>::Backward_gpu(const vector<Blob<Dtype>*>& top, const vector<bool>& propagate_down,
+                                                 vector<Blob<Dtype>*>* bottom) {
+  CHECK(!propagate_down[0]) << this->type_name() << "Layer cannot backpropogate to input ids.";
+  if (this->param_propagate_down_[0])
+    VV_CHECK(vv_id_lookup_backward(top[0]->gpu_diff(), (*bottom)[0]->gpu_data(), M_, N_, K_, this->blobs_[0]->mutable_gpu_diff(), Caffe::stream()));
+}
+
 // =================================== TEST-phase data + retrieval stats ===================================
 template <typename Dtype>
 void VideoShotWindowTestDataLayer<Dtype>::LayerSetUp(const vector<Blob<Dtype>*>& bottom, vector<Blob<Dtype>*>* top) {
@@ -599,6 +635,7 @@ Layer<Dtype>* GetLayer(const LayerParameter& param) {
     case LayerParameter_LayerType_VIDEO_SAMPLED_SHOTS_DATA: return new VideoSampledShotsDataLayer<Dtype>(param);
     case LayerParameter_LayerType_VIDEO_SHOT_WINDOW_TEST_DATA: return new VideoShotWindowTestDataLayer<Dtype>(param);
     case LayerParameter_LayerType_RETRIEVAL_STATS: return new RetrievalStatsLayer<Dtype>(param);
+    case LayerParameter_LayerType_ID_TO_WEIGHT_MAPPING: return new IdToWeightMappingLayer<Dtype>(param);
     case LayerParameter_LayerType_NONE: LOG_FATAL << "Layer " << name << " has unspecified or unsupported type '" << param.m->str("type") << "'.";
     default: LOG_FATAL << "Layer " << name << " has unknown type " << param.type();
   }
@@ -609,6 +646,6 @@ template class InnerProductLayer<float>; template class ReLULayer<float>; templa
 template class SliceLayer<float>; template class ConcatLayer<float>; template class FlattenLayer<float>;
 template class SplitLayer<float>; template class EltwiseLayer<float>; template class NormalizationLayer<float>;
 template class SumLayer<float>; template class MaxMarginLossLayer<float>; template class VideoSampledShotsDataLayer<float>;
-template class VideoShotWindowTestDataLayer<float>; template class RetrievalStatsLayer<float>;
+template class VideoShotWindowTestDataLayer<float>; template class RetrievalStatsLayer<float>; template class IdToWeightMappingLayer<float>;
 
 }  // namespace caffe

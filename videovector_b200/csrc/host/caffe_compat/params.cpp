@@ -111,7 +111,7 @@ static const struct { const char* name; LayerParameter_LayerType t; } kTypes[] =
   {"ELTWISE", LayerParameter_LayerType_ELTWISE}, {"SLICE", LayerParameter_LayerType_SLICE},
   {"NORMALIZATION", LayerParameter_LayerType_NORMALIZATION}, {"MAX_MARGIN_LOSS", LayerParameter_LayerType_MAX_MARGIN_LOSS},
   {"SUM", LayerParameter_LayerType_SUM}, {"VIDEO_SAMPLED_SHOTS_DATA", LayerParameter_LayerType_VIDEO_SAMPLED_SHOTS_DATA},
-  {"RETRIEVAL_STATS", LayerParameter_LayerType_RETRIEVAL_STATS}, {"VIDEO_SHOT_WINDOW_TEST_DATA", LayerParameter_LayerType_VIDEO_SHOT_WINDOW_TEST_DATA}};
+  {"RETRIEVAL_STATS", LayerParameter_LayerType_RETRIEVAL_STATS}, {"ID_TO_WEIGHT_MAPPING", LayerParameter_LayerType_ID_TO_WEIGHT_MAPPING}, {"VIDEO_SHOT_WINDOW_TEST_DATA", LayerParameter_LayerType_VIDEO_SHOT_WINDOW_TEST_DATA}};
 LayerParameter_LayerType LayerTypeFromName(const string& name) {
   for (auto& e : kTypes) if (name == e.name) return e.t;
   return LayerParameter_LayerType_NONE;

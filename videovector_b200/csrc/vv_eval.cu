@@ -121,6 +121,35 @@ __global__ void retrieval_mean_kernel(const double* __restrict__ per_query, cons
   out[0] = ap / n; out[1] = a1 / n; out[2] = a5 / n;
 }
 
+// ---- IdToWeightMapping (ref: id_to_weight_mapping_layer.cpp:61-148): a per-id embedding table -----------------------
+// forward: top[i,:] = table[ids[i],:]   (ids arrive as floats, like every Caffe blob)
+__global__ void __launch_bounds__(256)
+id_lookup_fwd_kernel(const float* __restrict__ table, const float* __restrict__ ids, int M, int N, float* __restrict__ top) {
+  for (int i = blockIdx.x; i < M; i += gridDim.x) {
+    const float* src = table + (size_t)static_cast<int>(ids[i]) * N;
+    for (int c = threadIdx.x; c < N; c += blockDim.x) top[(size_t)i * N + c] = src[c];
+  }
+}
+// backward: table_diff = 0; for i in order: table_diff[ids[i],:] += top_diff[i,:]  (:100-106).  Deterministic and in
+// the reference's order without atomics: the CTA of the FIRST occurrence of an id sums all rows carrying that id in
+// increasing i; later occurrences exit.  (table_diff must have been zeroed: rows no id names stay 0.)
+__global__ void __launch_bounds__(256)
+id_lookup_bwd_kernel(const float* __restrict__ top_diff, const float* __restrict__ ids, int M, int N, float* __restrict__ table_diff) {
+  extern __shared__ int s_ids[];
+  for (int j = threadIdx.x; j < M; j += blockDim.x) s_ids[j] = static_cast<int>(ids[j]);
+  __syncthreads();
+  const int i = blockIdx.x, id = s_ids[i];
+  int seen = 0;
+  for (int j = threadIdx.x; j < i; j += blockDim.x) seen |= (s_ids[j] == id);
+  if (__syncthreads_or(seen)) return;
+  for (int c = threadIdx.x; c < N; c += blockDim.x) {
+    float acc = 0.f;
+    for (int j = i; j < M; ++j)
+      if (s_ids[j] == id) acc += top_diff[(size_t)j * N + c];
+    table_diff[(size_t)id * N + c] = acc;
+  }
+}
+
 }  // namespace
 }  // namespace vv
 
@@ -172,6 +201,27 @@ extern "C" int vv_retrieval_stats(const float* E, int B, int N, const int32_t* v
   retrieval_stats_kernel<<<B, T, smem, stream>>>(Guse, B, n2, video_ids, labels, exclude_same_video_shots, pq);
   VV_LAUNCH_CHECK();
   retrieval_mean_kernel<<<1, 32, 0, stream>>>(pq, labels, B, out3);
+  VV_LAUNCH_CHECK();
+  count_launch(2);
+  return VV_OK;
+}
+
+extern "C" int vv_id_lookup_forward(const float* table, int rows, int N, const float* ids, int M, float* top, vv_stream_t stream) {
+  VV_REQUIRE(table && ids && top && rows > 0 && N > 0 && M > 0, "id_lookup_forward: bad arguments");
+  const int grid = M < num_sms() * 8 ? M : num_sms() * 8;
+  id_lookup_fwd_kernel<<<grid, 256, 0, stream>>>(table, ids, M, N, top);
+  VV_LAUNCH_CHECK();
+  count_launch();
+  return VV_OK;
+}
+extern "C" int vv_id_lookup_backward(const float* top_diff, const float* ids, int M, int N, int rows, float* table_diff,
+                                     vv_stream_t stream) {
+  VV_REQUIRE(top_diff && ids && table_diff && rows > 0 && N > 0 && M > 0, "id_lookup_backward: bad arguments");
+  VV_REQUIRE(size_t(M) * 4 <= 200 * 1024, "id_lookup_backward: at most 51200 ids per batch");
+  VV_CUDA(cudaMemsetAsync(table_diff, 0, size_t(rows) * N * sizeof(float), stream));       // caffe_set(K_*N_, 0, diff) :98
+  const size_t smem = size_t(M) * 4;
+  if (smem > 48 * 1024) VV_CUDA(cudaFuncSetAttribute(id_lookup_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  id_lookup_bwd_kernel<<<M, 256, smem, stream>>>(top_diff, ids, M, N, table_diff);
   VV_LAUNCH_CHECK();
   count_launch(2);
   return VV_OK;

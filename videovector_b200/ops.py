@@ -504,3 +504,18 @@ def retrieval_stats(E, video_ids, labels, exclude_same_video_shots=False, gram=N
                                  ws_bytes, _ptr(out), _ptr(pq), _stream()))
     o = out.cpu().numpy()
     return dict(map=float(o[0]), hit1=float(o[1]), hit5=float(o[2]), per_query=pq)
+
+
+def id_lookup_forward(table, ids):
+    """IdToWeightMapping forward: rows of `table` [rows, N] named by the float ids [M]."""
+    M = ids.numel(); rows, N = table.shape
+    top = torch.empty((M, N), dtype=torch.float32, device=table.device)
+    check(_lib.load().vv_id_lookup_forward(_ptr(table), rows, N, _ptr(ids), M, _ptr(top), _stream()))
+    return top
+
+
+def id_lookup_backward(top_diff, ids, rows):
+    M, N = top_diff.shape
+    d = torch.empty((rows, N), dtype=torch.float32, device=top_diff.device)
+    check(_lib.load().vv_id_lookup_backward(_ptr(top_diff), _ptr(ids), M, N, rows, _ptr(d), _stream()))
+    return d
