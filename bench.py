@@ -369,6 +369,10 @@ def run_gpu(args):
             key = "rank_loss_fused" if (name == "rank_loss_backward" and fused_rank) else name
             kern[key] = {"ms": ms, "bound": "hbm", "achieved_gbs": by / (ms * 1e-3) / 1e9 if ms > 0 else None,
                          "frac": by / (ms * 1e-3) / 1e9 / pk["hbm"] if ms > 0 else None}
+        if phase.get("allreduce", 0) > 0:
+            # exposed time of the gradient exchange on the main stream: split-K reduce + wait for the NCCL all-reduce of
+            # dW [N,K] and (db, loss, violations) -- includes waiting for the slowest rank
+            kern["allreduce"] = {"ms": phase["allreduce"], "bound": "nvlink", "bytes": N * K * 4 + (N + 2) * 4}
         dom = "wgrad" if phase["wgrad"] >= phase["fc7_forward"] else "fc7_forward"
         ach = kern[dom]["achieved_tflops"]
         traffic = None
