@@ -209,7 +209,7 @@ def run_gpu(args):
     import torch
     import torch.distributed as dist
     from videovector_b200 import ops
-    from videovector_b200._lib import DROPOUT_PHILOX
+    from videovector_b200._lib import DROPOUT_HASH
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -232,7 +232,7 @@ def run_gpu(args):
 
     stream = torch.cuda.Stream()
     with torch.cuda.stream(stream):
-        tr = ops.Trainer(ops.trainer_cfg(B, C, Nn, K, N, prec=prec, dropout_ratio=0.9, dropout_mode=DROPOUT_PHILOX,
+        tr = ops.Trainer(ops.trainer_cfg(B, C, Nn, K, N, prec=prec, dropout_ratio=0.9, dropout_mode=DROPOUT_HASH,
                                          dropout_seed=7, world_size=world, rank=rank), stream=stream)
         g = torch.Generator(device="cuda").manual_seed(1701)
         W0 = torch.randn(N, K, device="cuda", generator=g) * 0.001          # gaussian filler std 0.001, bias 0

@@ -86,7 +86,9 @@ typedef struct vv_operand {
 
 /* ReLU + Dropout spec for the fc7 epilogue.
  * ref: relu_layer.cu:9-33 (max(x,0)+slope*min(x,0)), dropout_layer.cu:14-41 */
-enum { VV_DROPOUT_NONE = 0, VV_DROPOUT_MASK01 = 1, VV_DROPOUT_MASK_U32 = 2, VV_DROPOUT_PHILOX = 3 };
+/* PHILOX: Philox4x32-10 keyed (seed, step, row, col/4); HASH: a 32-bit integer hash per element of the same counters,
+ * one third of the arithmetic (what the perf runs use; the reference's curand stream is unspecified either way) */
+enum { VV_DROPOUT_NONE = 0, VV_DROPOUT_MASK01 = 1, VV_DROPOUT_MASK_U32 = 2, VV_DROPOUT_PHILOX = 3, VV_DROPOUT_HASH = 4 };
 typedef struct vv_act {
   int relu;              /* 0/1 */
   float negative_slope;  /* relu_param.negative_slope */
@@ -94,9 +96,9 @@ typedef struct vv_act {
   float dropout_ratio;   /* dropout_param.dropout_ratio (threshold_) */
   const uint32_t* mask;  /* [M,N]: MASK01 -> 0/1 (CPU layer's rand_vec_, dropout_layer.cpp:41);
                             MASK_U32 -> raw u32, keep iff mask > uint_thres_ (dropout_layer.cu:19) */
-  uint32_t* mask_out;    /* optional [M,N] 0/1 mask written in PHILOX mode (else NULL) */
-  uint64_t seed;         /* PHILOX: key */
-  uint64_t step;         /* PHILOX: iteration, mixed into the counter */
+  uint32_t* mask_out;    /* optional [M,N] 0/1 mask written in PHILOX / HASH mode (else NULL) */
+  uint64_t seed;         /* PHILOX / HASH: key */
+  uint64_t step;         /* PHILOX / HASH: iteration, mixed into the counter */
 } vv_act_t;
 
 const char* vv_last_error(void);
@@ -275,6 +277,8 @@ int vv_dropout_forward(const float* x, const uint32_t* mask, int mask_mode, int6
 int vv_dropout_backward(const float* dy, const uint32_t* mask, int mask_mode, int64_t n, float ratio, float* dx, vv_stream_t s); /* :44-70 */
 /* 0/1 mask [rows, cols] drawn from the same Philox stream the fused fc7 epilogue uses (VV_DROPOUT_PHILOX) */
 int vv_dropout_make_mask(uint32_t* mask01, int rows, int cols, float ratio, uint64_t seed, uint64_t step, vv_stream_t s);
+/* same for either generated stream (mode = VV_DROPOUT_PHILOX | VV_DROPOUT_HASH) */
+int vv_dropout_make_mask_mode(uint32_t* mask01, int rows, int cols, float ratio, uint64_t seed, uint64_t step, int mode, vv_stream_t s);
 int vv_eltwise_sum_forward(const float* const* bottoms, const float* coeffs, int nb, int64_t n, float* top, vv_stream_t s); /* eltwise_layer.cu:48-54; host arrays of device ptrs */
 int vv_eltwise_prod_forward(const float* a, const float* b, int64_t n, float* top, vv_stream_t s);  /* eltwise_layer.cu:41-47 */
 int vv_axpby(int64_t n, float alpha, const float* x, float beta, float* y, vv_stream_t s);         /* y = alpha*x + beta*y */
@@ -371,7 +375,7 @@ typedef struct vv_trainer_cfg {
   float coeff[VV_MAX_CONTEXT]; /* zeros -> 1/(C-1) */
   float margin; int norm;
   float dropout_ratio;   /* 0 -> no dropout layer */
-  int dropout_mode;      /* VV_DROPOUT_PHILOX for perf runs, MASK01 for parity */
+  int dropout_mode;      /* VV_DROPOUT_HASH (or PHILOX) for perf runs, MASK01 for parity */
   uint64_t dropout_seed;
   float loss_weight;
   float regularization;  /* inner_product_param.regularization */

@@ -4,7 +4,7 @@ import argparse, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from videovector_b200 import ops
-from videovector_b200._lib import DROPOUT_PHILOX
+from videovector_b200._lib import DROPOUT_HASH
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--precision", default="f16x3")
@@ -23,7 +23,7 @@ V, S = 8192, 32
 bank = ops.fill_bank(V * S, K, 1234)
 vid, off, sid = ops.synthetic_videos(V, S)
 smp = ops.Sampler(vid, off, sid, B, C, Nn, 5000, 50, 6, 100, rand_seed=1)
-tr = ops.Trainer(ops.trainer_cfg(B, C, Nn, K, N, prec=a.precision, dropout_mode=DROPOUT_PHILOX, split_rank_loss=a.split_rank))
+tr = ops.Trainer(ops.trainer_cfg(B, C, Nn, K, N, prec=a.precision, dropout_mode=DROPOUT_HASH, split_rank_loss=a.split_rank))
 tr.set_weights(torch.randn(N, K, device="cuda") * 0.001, torch.zeros(N, device="cuda"))
 if a.precision in ("f16x3", "bf16") and not a.materialised:
     tr.set_bank(bank)

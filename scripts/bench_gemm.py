@@ -4,7 +4,7 @@ import sys, os, ctypes as C
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from videovector_b200 import ops, _lib
-from videovector_b200._lib import DROPOUT_PHILOX, DROPOUT_NONE
+from videovector_b200._lib import DROPOUT_PHILOX, DROPOUT_HASH, DROPOUT_NONE
 
 torch.cuda.set_device(0)
 prec = sys.argv[1] if len(sys.argv) > 1 else "f16x3"
@@ -42,6 +42,7 @@ def fwd(act):
 timeit("fwd  plain (no activation)", lambda: fwd(None))
 timeit("fwd  relu", lambda: fwd(ops.make_act(True, 0.0, DROPOUT_NONE)))
 timeit("fwd  relu + philox dropout", lambda: fwd(ops.make_act(True, 0.0, DROPOUT_PHILOX, 0.9, seed=7, step=1)))
+timeit("fwd  relu + hash dropout", lambda: fwd(ops.make_act(True, 0.0, DROPOUT_HASH, 0.9, seed=7, step=1)))
 nsplit = lib.vv_ip_wgrad_auto_nsplit(M, N, K, ops.PREC[prec])
 parts = torch.empty(nsplit, N, K, device="cuda")
 timeit("wgrad (nsplit %d)" % nsplit, lambda: ops.check(lib.vv_ip_wgrad(dZo.c(), Xo.c(), M, N, K, ops.PREC[prec], 0.0, ops._ptr(parts), nsplit, None, 0, ops._stream())))
@@ -51,8 +52,8 @@ if prec in ("f16x3", "bf16"):
     bank = torch.relu(torch.randn(rows, K, device="cuda", generator=g))
     Bo = ops.prepare_operand(bank, prec)
     rowmap = torch.randint(0, rows, (M,), device="cuda", dtype=torch.int32)
-    act = ops.make_act(True, 0.0, DROPOUT_PHILOX, 0.9, seed=7, step=1)
-    timeit("fwd  gathered, relu + philox dropout", lambda: ops.check(lib.vv_ip_forward_gathered(
+    act = ops.make_act(True, 0.0, DROPOUT_HASH, 0.9, seed=7, step=1)
+    timeit("fwd  gathered, relu + hash dropout", lambda: ops.check(lib.vv_ip_forward_gathered(
         Bo.c(), rows, ops._ptr(rowmap), None, None, Wo.c(), ops._ptr(b), M, N, K, ops.PREC[prec], C.byref(act), None, ops._ptr(H), ops._stream())))
     timeit("fwd  gathered, plain", lambda: ops.check(lib.vv_ip_forward_gathered(
         Bo.c(), rows, ops._ptr(rowmap), None, None, Wo.c(), ops._ptr(b), M, N, K, ops.PREC[prec], None, None, ops._ptr(H), ops._stream())))

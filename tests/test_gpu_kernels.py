@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from videovector_b200 import ops
-from videovector_b200._lib import DROPOUT_MASK01, DROPOUT_MASK_U32, DROPOUT_NONE, DROPOUT_PHILOX
+from videovector_b200._lib import DROPOUT_HASH, DROPOUT_MASK01, DROPOUT_MASK_U32, DROPOUT_NONE, DROPOUT_PHILOX
 
 pytestmark = pytest.mark.gpu
 
@@ -150,7 +150,7 @@ def test_ip_forward_matches_oracle_cfg1(oracle, prec):
 
 
 @pytest.mark.parametrize("prec", ALL)
-@pytest.mark.parametrize("mode", [DROPOUT_NONE, DROPOUT_MASK01, DROPOUT_MASK_U32, DROPOUT_PHILOX])
+@pytest.mark.parametrize("mode", [DROPOUT_NONE, DROPOUT_MASK01, DROPOUT_MASK_U32, DROPOUT_PHILOX, DROPOUT_HASH])
 def test_ip_forward_fused_relu_dropout(oracle, prec, mode):
     M, N, K = 256, 264, 96
     ratio = 0.9
@@ -164,9 +164,9 @@ def test_ip_forward_fused_relu_dropout(oracle, prec, mode):
         mask = keep
     elif mode == DROPOUT_MASK_U32:
         mask = torch.where(raw >= 2 ** 31, raw - 2 ** 32, raw).to(torch.int32).contiguous()   # raw u32 bit patterns
-    elif mode == DROPOUT_PHILOX:
+    elif mode in (DROPOUT_PHILOX, DROPOUT_HASH):
         mask_out = torch.zeros((M, N), dtype=torch.int32, device="cuda")
-        keep = ops.dropout_make_mask(M, N, ratio, 7, 5)
+        keep = ops.dropout_make_mask(M, N, ratio, 7, 5, mode=mode)
     act = ops.make_act(relu=True, dropout_mode=mode, ratio=ratio, mask=mask, mask_out=mask_out, seed=7, step=5)
     H, Z = ops.ip_forward(ops.prepare_operand(X, prec), ops.prepare_operand(W, prec), b, M, N, K, prec, act=act, want_z=True)
     Zref = oracle.ip_forward(X.cpu().numpy(), W.cpu().numpy(), b.cpu().numpy())
@@ -175,11 +175,30 @@ def test_ip_forward_fused_relu_dropout(oracle, prec, mode):
     Href = oracle.relu_forward(Z.cpu().numpy())
     if mode != DROPOUT_NONE:
         Href = oracle.dropout_forward(Href, keep.cpu().numpy().astype(np.uint32), ratio)
-        if mode == DROPOUT_PHILOX:
+        if mode in (DROPOUT_PHILOX, DROPOUT_HASH):
             assert torch.equal(mask_out, keep)
             frac = keep.float().mean().item()
             assert abs(frac - (1 - ratio)) < 0.01
     assert np.array_equal(H.cpu().numpy(), Href)
+
+
+@pytest.mark.parametrize("mode", [DROPOUT_PHILOX, DROPOUT_HASH])
+def test_generated_dropout_streams_are_sound(mode):
+    """Both generated streams: keep rate = 1 - ratio to 3 sigma, rows / columns / steps / seeds decorrelated, and
+    reproducible (same key -> same mask)."""
+    rows, cols, ratio = 2048, 512, 0.9
+    m = ops.dropout_make_mask(rows, cols, ratio, 7, 5, mode=mode).float()
+    n = rows * cols
+    assert abs(m.mean().item() - 0.1) < 3 * (0.09 / n) ** 0.5
+    assert torch.equal(m, ops.dropout_make_mask(rows, cols, ratio, 7, 5, mode=mode).float())
+    for other in (ops.dropout_make_mask(rows, cols, ratio, 7, 6, mode=mode), ops.dropout_make_mask(rows, cols, ratio, 8, 5, mode=mode)):
+        o = other.float()
+        both = (m * o).mean().item()                         # independent masks overlap on ~1 % of the entries
+        assert abs(both - 0.01) < 5 * (0.01 / n) ** 0.5
+    # neighbouring rows and columns are uncorrelated; per-row and per-column keep counts spread like a binomial
+    assert abs(((m[1:] * m[:-1]).mean() - 0.01).item()) < 5 * (0.01 / n) ** 0.5
+    assert abs(((m[:, 1:] * m[:, :-1]).mean() - 0.01).item()) < 5 * (0.01 / n) ** 0.5
+    assert abs(m.sum(1).var().item() / (cols * 0.09) - 1) < 0.15 and abs(m.sum(0).var().item() / (rows * 0.09) - 1) < 0.25
 
 
 @pytest.mark.parametrize("prec", ALL)

@@ -13,7 +13,7 @@ VV_MAX_CONTEXT = 64
 PREC = {"fp32_simt": 0, "tf32x3": 1, "tf32": 2, "bf16": 3, "f16x3": 4}
 F16X3_HEADER_BYTES = 128
 CONTEXT = {"pairwise": 0, "window": 1, "past": 2, "past_continuous": 3, "past_continuous_fixed": 4}
-DROPOUT_NONE, DROPOUT_MASK01, DROPOUT_MASK_U32, DROPOUT_PHILOX = 0, 1, 2, 3
+DROPOUT_NONE, DROPOUT_MASK01, DROPOUT_MASK_U32, DROPOUT_PHILOX, DROPOUT_HASH = 0, 1, 2, 3, 4
 
 
 class VVError(RuntimeError):
@@ -88,6 +88,7 @@ SIGNATURES = {
     "vv_dropout_forward": (_i, [_P, _P, _i, _i64, _f, _P, _P]),
     "vv_dropout_backward": (_i, [_P, _P, _i, _i64, _f, _P, _P]),
     "vv_dropout_make_mask": (_i, [_P, _i, _i, _f, _u64, _u64, _P]),
+    "vv_dropout_make_mask_mode": (_i, [_P, _i, _i, _f, _u64, _u64, _i, _P]),
     "vv_eltwise_sum_forward": (_i, [C.POINTER(_P), C.POINTER(_f), _i, _i64, _P, _P]),
     "vv_eltwise_prod_forward": (_i, [_P, _P, _i64, _P, _P]),
     "vv_axpby": (_i, [_i64, _f, _P, _f, _P, _P]),

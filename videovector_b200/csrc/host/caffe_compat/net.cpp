@@ -294,7 +294,7 @@ bool Net<Dtype>::EnableFusion(string* why) {
   fused_cfg_.B = B; fused_cfg_.C = C; fused_cfg_.Nn = Nn; fused_cfg_.K = K; fused_cfg_.N = N;
   fused_cfg_.margin = lossp.max_margin_loss_param().margin();
   fused_cfg_.norm = lossp.max_margin_loss_param().norm() == MaxMarginLossParameter_Norm_L2 ? 2 : 1;
-  fused_cfg_.dropout_ratio = ratio; fused_cfg_.dropout_mode = VV_DROPOUT_PHILOX; fused_cfg_.dropout_seed = Caffe::rng_seed();
+  fused_cfg_.dropout_ratio = ratio; fused_cfg_.dropout_mode = VV_DROPOUT_HASH; fused_cfg_.dropout_seed = Caffe::rng_seed();
   fused_cfg_.loss_weight = layers_[li]->loss(0);
   fused_cfg_.regularization = ipp.inner_product_param().regularization();
   strncpy(fused_cfg_.lr_policy, "fixed", sizeof(fused_cfg_.lr_policy));

@@ -34,7 +34,7 @@ int launches_reset() { const int n = g_launches; g_launches = 0; return n; }
 static int fill_epilogue(const vv_act_t* act, const float* bias, float* Z, GemmEpilogue* e) {
   e->bias = bias; e->Z = Z; e->has_act = act ? 1 : 0; e->out_scale = 1.f;
   e->relu = 0; e->negative_slope = 0.f; e->dropout_mode = VV_DROPOUT_NONE; e->dropout_scale = 1.f;
-  e->dropout_thres = 0; e->mask = nullptr; e->mask_out = nullptr; e->seed = 0; e->step = 0;
+  e->dropout_thres = 0; e->mask = nullptr; e->mask_out = nullptr; e->seed = 0; e->step = 0; e->hash_base = 0;
   e->delta = nullptr; e->wlast = nullptr;
   if (!act) return VV_OK;
   e->relu = act->relu; e->negative_slope = act->negative_slope;
@@ -46,6 +46,7 @@ static int fill_epilogue(const vv_act_t* act, const float* bias, float* Z, GemmE
     if (act->dropout_mode == VV_DROPOUT_MASK01 || act->dropout_mode == VV_DROPOUT_MASK_U32)
       VV_REQUIRE(act->mask, "dropout mask mode needs a mask pointer");
     e->mask = act->mask; e->mask_out = act->mask_out; e->seed = act->seed; e->step = act->step;
+    e->hash_base = dropout_hash_base(act->seed, act->step);
   }
   return VV_OK;
 }

@@ -154,6 +154,23 @@ __host__ __device__ __forceinline__ void dropout_words(uint64_t seed, uint64_t s
                                                        uint32_t col4, uint32_t out[4]) {
   philox4x32(col4, row, uint32_t(step), uint32_t(step >> 32), uint32_t(seed), uint32_t(seed >> 32), out);
 }
+// The cheap alternative stream (VV_DROPOUT_HASH): one 32-bit integer hash per element instead of a Philox block per
+// four.  h(x) = lowbias32 (two multiplies, three xor-shifts; avalanche bias < 0.2 %): word(row, col) =
+// h(h(h(seed_lo ^ h(seed_hi ^ step_lo) ^ step_hi) ^ row) + col * golden), ~8 integer ops per element against ~25 --
+// inside the fc7 epilogue the RNG arithmetic costs tensor-pipe clocks through the power cap.
+__host__ __device__ __forceinline__ uint32_t hash32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
+__host__ __device__ __forceinline__ uint32_t dropout_hash_base(uint64_t seed, uint64_t step) {
+  return hash32(uint32_t(seed) ^ hash32(uint32_t(seed >> 32) ^ uint32_t(step)) ^ uint32_t(step >> 32));
+}
+__host__ __device__ __forceinline__ void dropout_words_hash(uint32_t base, uint32_t row, uint32_t col4, uint32_t out[4]) {
+  const uint32_t rb = hash32(base ^ row);
+  const uint32_t c = col4 * 4u;
+  out[0] = hash32(rb + (c + 0u) * 0x9E3779B9u); out[1] = hash32(rb + (c + 1u) * 0x9E3779B9u);
+  out[2] = hash32(rb + (c + 2u) * 0x9E3779B9u); out[3] = hash32(rb + (c + 3u) * 0x9E3779B9u);
+}
 __host__ __device__ __forceinline__ uint32_t dropout_uint_thres(float ratio) {
   return static_cast<unsigned int>(4294967295u * ratio);   // UINT_MAX * threshold_ in float (dropout_layer.cpp:21)
 }

@@ -22,6 +22,7 @@ struct GemmEpilogue {
   int dropout_mode; float dropout_scale; uint32_t dropout_thres;
   const uint32_t* mask; uint32_t* mask_out;
   uint64_t seed, step;
+  uint32_t hash_base;     // VV_DROPOUT_HASH: dropout_hash_base(seed, step)
   float out_scale;        // multiplies the accumulator (wgrad regularization), 1 otherwise
   // gather-fused forward: Z[m,:] += delta[m] * wlast[:]  (the K-1 copy quirk as a rank-1 correction)
   const float* delta;     // [M] or NULL
@@ -49,9 +50,38 @@ int gemm_simt_launch(const GemmProblem& p, cudaStream_t stream);   // exact fp32
 bool gemm_tc_supported(const GemmProblem& p, const char** why);
 
 // ---- shared epilogue element math (used by both paths) ----------------------
-// Applies bias/ReLU/dropout to 4 consecutive columns [col, col+4) of row `row`.
+// Keep bits (bit k = keep column col + k) of 4 consecutive columns of row `row`, for every dropout mode; writes the
+// 0/1 mask to mask_out in the generated modes.  Kept apart from the activation so that callers with a long unrolled
+// epilogue can run it in a ROLLED loop first (32 inlined Philox blocks put the promoting forward kernels past the
+// instruction cache and cost 30 % of their speed).
+__device__ __forceinline__ uint32_t dropout_keep_bits(const GemmEpilogue& e, int N, int row, int col) {
+  uint32_t keep[4];
+  if (e.dropout_mode == VV_DROPOUT_PHILOX || e.dropout_mode == VV_DROPOUT_HASH) {
+    uint32_t w[4];
+    if (e.dropout_mode == VV_DROPOUT_PHILOX) dropout_words(e.seed, e.step, uint32_t(row), uint32_t(col >> 2), w);
+    else dropout_words_hash(e.hash_base, uint32_t(row), uint32_t(col >> 2), w);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) keep[j] = (w[j] > e.dropout_thres) ? 1u : 0u;
+    if (e.mask_out) {
+      *reinterpret_cast<uint4*>(e.mask_out + size_t(row) * N + col) = make_uint4(keep[0], keep[1], keep[2], keep[3]);
+    }
+  } else {
+    const uint4 m = *reinterpret_cast<const uint4*>(e.mask + size_t(row) * N + col);
+    if (e.dropout_mode == VV_DROPOUT_MASK_U32) {
+      keep[0] = m.x > e.dropout_thres; keep[1] = m.y > e.dropout_thres;
+      keep[2] = m.z > e.dropout_thres; keep[3] = m.w > e.dropout_thres;
+    } else {
+      keep[0] = m.x; keep[1] = m.y; keep[2] = m.z; keep[3] = m.w;
+    }
+  }
+  return (keep[0] & 1u) | ((keep[1] & 1u) << 1) | ((keep[2] & 1u) << 2) | ((keep[3] & 1u) << 3);
+}
+__device__ __forceinline__ bool epilogue_has_dropout(const GemmEpilogue& e) { return e.has_act && e.dropout_mode != VV_DROPOUT_NONE; }
+
+// Applies the quirk correction, bias, ReLU and dropout (keep bits from dropout_keep_bits) to 4 consecutive columns
+// [col, col+4) of row `row`.
 __device__ __forceinline__ void epilogue_act4(const GemmEpilogue& e, int N, int row, int col,
-                                              float4& v, float4& z_out) {
+                                              float4& v, float4& z_out, uint32_t keep_bits) {
   if (e.delta) {
     const float d = e.delta[row];
     if (d != 0.f) {
@@ -73,29 +103,11 @@ __device__ __forceinline__ void epilogue_act4(const GemmEpilogue& e, int N, int 
     v.w = fmaxf(v.w, 0.f) + s * fminf(v.w, 0.f);
   }
   if (e.dropout_mode == VV_DROPOUT_NONE) return;
-  uint32_t keep[4];
-  if (e.dropout_mode == VV_DROPOUT_PHILOX) {
-    uint32_t w[4];
-    dropout_words(e.seed, e.step, uint32_t(row), uint32_t(col >> 2), w);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) keep[j] = (w[j] > e.dropout_thres) ? 1u : 0u;
-    if (e.mask_out) {
-      *reinterpret_cast<uint4*>(e.mask_out + size_t(row) * N + col) = make_uint4(keep[0], keep[1], keep[2], keep[3]);
-    }
-  } else {
-    const uint4 m = *reinterpret_cast<const uint4*>(e.mask + size_t(row) * N + col);
-    if (e.dropout_mode == VV_DROPOUT_MASK_U32) {
-      keep[0] = m.x > e.dropout_thres; keep[1] = m.y > e.dropout_thres;
-      keep[2] = m.z > e.dropout_thres; keep[3] = m.w > e.dropout_thres;
-    } else {
-      keep[0] = m.x; keep[1] = m.y; keep[2] = m.z; keep[3] = m.w;
-    }
-  }
   // reference order: x * mask * scale (dropout_layer.cpp:44)
-  v.x = v.x * float(keep[0]) * e.dropout_scale;
-  v.y = v.y * float(keep[1]) * e.dropout_scale;
-  v.z = v.z * float(keep[2]) * e.dropout_scale;
-  v.w = v.w * float(keep[3]) * e.dropout_scale;
+  v.x = v.x * float(keep_bits & 1u) * e.dropout_scale;
+  v.y = v.y * float((keep_bits >> 1) & 1u) * e.dropout_scale;
+  v.z = v.z * float((keep_bits >> 2) & 1u) * e.dropout_scale;
+  v.w = v.w * float((keep_bits >> 3) & 1u) * e.dropout_scale;
 }
 
 }  // namespace vv

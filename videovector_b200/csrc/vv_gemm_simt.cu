@@ -26,9 +26,10 @@ __device__ __forceinline__ float epilogue_act1(const GemmEpilogue& e, int N, int
   if (e.relu) v = fmaxf(v, 0.f) + e.negative_slope * fminf(v, 0.f);
   if (e.dropout_mode == VV_DROPOUT_NONE) return v;
   uint32_t keep;
-  if (e.dropout_mode == VV_DROPOUT_PHILOX) {
+  if (e.dropout_mode == VV_DROPOUT_PHILOX || e.dropout_mode == VV_DROPOUT_HASH) {
     uint32_t w[4];
-    dropout_words(e.seed, e.step, uint32_t(row), uint32_t(col >> 2), w);
+    if (e.dropout_mode == VV_DROPOUT_PHILOX) dropout_words(e.seed, e.step, uint32_t(row), uint32_t(col >> 2), w);
+    else dropout_words_hash(e.hash_base, uint32_t(row), uint32_t(col >> 2), w);
     keep = (w[col & 3] > e.dropout_thres) ? 1u : 0u;
     if (e.mask_out) e.mask_out[size_t(row) * N + col] = keep;
   } else {

@@ -430,6 +430,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         }
         // f16x3: undo the operands' power-of-two scales (exact)
         const float unscale = C::split16 ? __ldg(p.inv_sa) * __ldg(p.inv_sb) : 1.f;
+        // dropout keep bits of this thread's 128 columns, 4 bits per column group, produced by ROLLED loops (the
+        // generator must not be unrolled 32 times into the epilogue below: instruction cache)
+        uint32_t kbits[kColsPerWarp / 32];
+#pragma unroll
+        for (int q = 0; q < kColsPerWarp / 32; ++q) kbits[q] = 0u;
+        if (C::fwd_epi && row_ok && epilogue_has_dropout(p.epi)) {
+#pragma unroll
+          for (int q = 0; q < kColsPerWarp / 32; ++q) {
+            uint32_t bits = 0u;
+#pragma unroll 1
+            for (int jj = 0; jj < 8; ++jj) {
+              const int col = n0 + (q * 8 + jj) * 4;
+              if (col < p.d_cols) bits |= dropout_keep_bits(p.epi, p.act_N, row, col) << (4 * jj);
+            }
+            kbits[q] = bits;
+          }
+        }
         if (row_ok) {
 #pragma unroll
           for (int j = 0; j < kColsPerWarp / 4; ++j) {
@@ -439,7 +456,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
               if (C::split16) { v.x *= unscale; v.y *= unscale; v.z *= unscale; v.w *= unscale; }
               if (C::fwd_epi) {
                 float4 z;
-                epilogue_act4(p.epi, p.act_N, row, col, v, z);
+                epilogue_act4(p.epi, p.act_N, row, col, v, z, (kbits[j >> 3] >> (4 * (j & 7))) & 15u);
                 if (p.epi.Z) *reinterpret_cast<float4*>(p.epi.Z + (long long)row * p.act_N + col) = z;
               } else {
                 const float s = p.epi.out_scale;
@@ -477,7 +494,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                                        __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
                 if (C::fwd_epi) {
                   float4 z;
-                  epilogue_act4(p.epi, p.act_N, row, col, v, z);
+                  const uint32_t kb = epilogue_has_dropout(p.epi) ? dropout_keep_bits(p.epi, p.act_N, row, col) : 0u;
+                  epilogue_act4(p.epi, p.act_N, row, col, v, z, kb);
                   if (p.epi.Z) *reinterpret_cast<float4*>(p.epi.Z + (long long)row * p.act_N + col) = z;
                 } else {
                   const float s = p.epi.out_scale;

@@ -276,11 +276,13 @@ __global__ void dropout_kernel(const float* x, const unsigned* mask, int mode, u
   }
 }
 // same stream as the fused fc7 epilogue: element (row, 4*col4 + j) = word j of dropout_words(seed, step, row, col4)
-__global__ void dropout_make_mask_kernel(unsigned* mask, int rows, int cols4, unsigned thres, unsigned long long seed, unsigned long long step) {
+__global__ void dropout_make_mask_kernel(unsigned* mask, int rows, int cols4, unsigned thres, unsigned long long seed, unsigned long long step,
+                                         int mode) {
+  const unsigned base = dropout_hash_base(seed, step);
   GS_LOOP(i, (long long)rows * cols4) {
     const unsigned row = unsigned(i / cols4), c4 = unsigned(i - (long long)row * cols4);
     unsigned w[4];
-    dropout_words(seed, step, row, c4, w);
+    if (mode == VV_DROPOUT_HASH) dropout_words_hash(base, row, c4, w); else dropout_words(seed, step, row, c4, w);
     reinterpret_cast<uint4*>(mask)[i] = make_uint4(w[0] > thres, w[1] > thres, w[2] > thres, w[3] > thres);
   }
 }
@@ -568,8 +570,13 @@ extern "C" int vv_dropout_backward(const float* dy, const uint32_t* mask, int mo
   VV_SIMPLE_LAUNCH(dropout_kernel, n, dy, mask, mode, dropout_uint_thres(ratio), n, dropout_scale(ratio), dx);
 }
 extern "C" int vv_dropout_make_mask(uint32_t* mask01, int rows, int cols, float ratio, uint64_t seed, uint64_t step, vv_stream_t s) {
+  return vv_dropout_make_mask_mode(mask01, rows, cols, ratio, seed, step, VV_DROPOUT_PHILOX, s);
+}
+extern "C" int vv_dropout_make_mask_mode(uint32_t* mask01, int rows, int cols, float ratio, uint64_t seed, uint64_t step, int mode,
+                                         vv_stream_t s) {
   VV_REQUIRE(mask01 && rows > 0 && cols > 0 && cols % 4 == 0 && VV_ALIGNED16(mask01), "dropout_make_mask: cols must be a multiple of 4, mask 16-byte aligned");
-  VV_SIMPLE_LAUNCH(dropout_make_mask_kernel, (long long)rows * (cols / 4), mask01, rows, cols / 4, dropout_uint_thres(ratio), seed, step);
+  VV_REQUIRE(mode == VV_DROPOUT_PHILOX || mode == VV_DROPOUT_HASH, "dropout_make_mask: mode must be a generated stream (PHILOX or HASH)");
+  VV_SIMPLE_LAUNCH(dropout_make_mask_kernel, (long long)rows * (cols / 4), mask01, rows, cols / 4, dropout_uint_thres(ratio), seed, step, mode);
 }
 extern "C" int vv_eltwise_sum_forward(const float* const* bottoms, const float* coeffs, int nb, int64_t n, float* top, vv_stream_t s) {
   VV_REQUIRE(bottoms && coeffs && top && nb >= 1 && nb <= VV_MAX_CONTEXT && n > 0, "eltwise_sum: bad arguments");

@@ -7,7 +7,7 @@ import torch
 
 from . import _lib
 from ._lib import (Act, Operand, RankCfg, TrainerCfg, PREC, DROPOUT_NONE, DROPOUT_MASK01,
-                   DROPOUT_MASK_U32, DROPOUT_PHILOX, VVError, check)
+                   DROPOUT_MASK_U32, DROPOUT_PHILOX, DROPOUT_HASH, VVError, check)
 
 
 def _ptr(t):
@@ -251,9 +251,9 @@ def learning_rate(policy, base_lr, gamma, power, stepsize, it):
     return float(_lib.load().vv_learning_rate(policy.encode(), base_lr, gamma, power, stepsize, it))
 
 
-def dropout_make_mask(rows, cols, ratio, seed, step, device="cuda"):
+def dropout_make_mask(rows, cols, ratio, seed, step, device="cuda", mode=DROPOUT_PHILOX):
     m = torch.empty((rows, cols), dtype=torch.int32, device=device)
-    check(_lib.load().vv_dropout_make_mask(_ptr(m), rows, cols, ratio, seed, step, _stream()))
+    check(_lib.load().vv_dropout_make_mask_mode(_ptr(m), rows, cols, ratio, seed, step, mode, _stream()))
     return m
 
 
