@@ -73,7 +73,7 @@ enum vv_precision {
  *   BF16             : hi = bf16 array (uint16 storage), lo = NULL
  *   F16X3            : hi = fp16 plane h0, lo = fp16 plane h1 (`count` elements each), and the
  *                      VV_F16X3_HEADER_BYTES bytes immediately BEFORE hi are the operand's header
- *                      {float scale, float 1/scale, uint32 bits of max|x| seen by the last producer, pad}:
+ *                      {float scale, float 1/scale, uint32 bits of max|x| seen by the last producer, uint32 layout}:
  *                      allocate header + planes as one block (vv_operand_bytes), zero the header or call
  *                      vv_operand_set_scale once, and call vv_operand_rescale before each re-production.
  * vv_prepare_operand() produces these from an fp32 array; the producer kernels
@@ -126,6 +126,11 @@ int vv_gather_rows(const float* bank, int64_t bank_rows, int K,
  * sets the header's scale from it. */
 int vv_prepare_operand(const float* src, int64_t count, int prec,
                        void* hi, void* lo, vv_stream_t stream);
+/* Operand copy of a resident feature bank [rows, K] for the gather-fused GEMMs (vv_ip_forward_gathered /
+ * vv_ip_wgrad_gathered ONLY).  Same allocation as vv_prepare_operand; for F16X3 with K % 64 == 0 the two fp16 planes
+ * are interleaved per row in blocks of 64 elements ([64 x h0 | 64 x h1] = 256 contiguous bytes, flagged in the
+ * operand header), so that a gathered k-block of a row is one DRAM access instead of two. */
+int vv_prepare_bank_operand(const float* bank, int64_t rows, int K, int prec, void* hi, void* lo, vv_stream_t stream);
 /* Bytes of one operand allocation for `count` elements and the offsets of hi / lo inside it (lo_offset = 0
  * when the format has no lo array; FP32_SIMT / TF32 read the fp32 array itself: returns 0). */
 size_t vv_operand_bytes(int64_t count, int prec, size_t* hi_offset, size_t* lo_offset);

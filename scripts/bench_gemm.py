@@ -50,7 +50,8 @@ dX = torch.empty(8192, K, device="cuda")
 if prec in ("f16x3", "bf16"):
     rows = 65536
     bank = torch.relu(torch.randn(rows, K, device="cuda", generator=g))
-    Bo = ops.prepare_operand(bank, prec)
+    Bo = ops.alloc_operand(bank.shape, prec)        # the bank's operand copy in the gather producers' preferred layout
+    ops.check(lib.vv_prepare_bank_operand(ops._ptr(bank), rows, K, ops.PREC[prec], ops._ptr(Bo.hi), ops._ptr(Bo.lo), ops._stream()))
     rowmap = torch.randint(0, rows, (M,), device="cuda", dtype=torch.int32)
     act = ops.make_act(True, 0.0, DROPOUT_HASH, 0.9, seed=7, step=1)
     timeit("fwd  gathered, relu + hash dropout", lambda: ops.check(lib.vv_ip_forward_gathered(

@@ -455,3 +455,26 @@ def test_errors_are_loud(vvlib):
     assert "K" in vvlib.vv_last_error().decode() or "tensor-core" in vvlib.vv_last_error().decode()
     with pytest.raises(Exception):
         ops.rank_loss_forward(torch.zeros((15, 6), device="cuda"), ops.rank_cfg(1, 5, 10, 6))   # N % 4 != 0
+
+
+def test_bank_operand_row_interleaved_layout(vvlib):
+    """vv_prepare_bank_operand (F16X3, K % 64 == 0): the same fp16 pairs as the two-plane form, stored per row as blocks
+    [64 x h0 | 64 x h1]; header layout flag 1; other K / precisions fall back to the plain operand."""
+    from videovector_b200.ops import _ptr, _stream
+    rows, K = 37, 256
+    bank = torch.relu(torch.randn(rows, K, device="cuda")) * 3
+    planar = ops.prepare_operand(bank, "f16x3")
+    il = ops.alloc_operand((rows, K), "f16x3")
+    ops.check(vvlib.vv_prepare_bank_operand(_ptr(bank), rows, K, ops.PREC["f16x3"], _ptr(il.hi), _ptr(il.lo), _stream()))
+    hdr = il.block[:16].view(torch.int32)
+    assert int(hdr[3]) == 1 and int(planar.block[:16].view(torch.int32)[3]) == 0
+    raw = il.block[128:128 + rows * K * 4].view(torch.float16).view(rows, K // 64, 2, 64)
+    s_il, s_pl = il.scale, planar.scale                              # bank copy: max -> 2^12, plain operand: 2^10
+    assert s_il == 4 * s_pl
+    assert torch.equal(raw[:, :, 0, :].reshape(rows, K), (bank * s_il).to(torch.float16))
+    assert torch.equal(raw[:, :, 1, :].reshape(rows, K), (bank * s_il - (bank * s_il).to(torch.float16).float()).to(torch.float16))
+    # K not a multiple of 64 -> two planes
+    bank2 = torch.relu(torch.randn(5, 72, device="cuda"))
+    op2 = ops.alloc_operand((5, 72), "f16x3")
+    ops.check(vvlib.vv_prepare_bank_operand(_ptr(bank2), 5, 72, ops.PREC["f16x3"], _ptr(op2.hi), _ptr(op2.lo), _stream()))
+    assert int(op2.block[:16].view(torch.int32)[3]) == 0 and torch.equal(op2.hi, (bank2 * op2.scale).to(torch.float16))

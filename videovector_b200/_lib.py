@@ -59,6 +59,7 @@ SIGNATURES = {
     "vv_device_check": (_i, []),
     "vv_gather_rows": (_i, [_P, _i64, _i, _P, _P, _i, _i, _P, _P, _P, _i, _P, _P]),
     "vv_prepare_operand": (_i, [_P, _i64, _i, _P, _P, _P]),
+    "vv_prepare_bank_operand": (_i, [_P, _i64, _i, _i, _P, _P, _P]),
     "vv_operand_bytes": (C.c_size_t, [_i64, _i, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "vv_operand_set_scale": (_i, [_P, _i, _i, _P]),
     "vv_operand_rescale": (_i, [_P, _i, _i, _P]),

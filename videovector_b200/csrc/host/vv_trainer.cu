@@ -248,7 +248,7 @@ extern "C" int vv_trainer_set_bank(vv_trainer_t* t, const float* bank, int64_t b
   const int64_t n = bank_rows * c.K;
   int rc;
   if ((rc = alloc_operand(t->bank_hi, t->bank_lo, size_t(n), c.prec))) return rc;
-  if ((rc = vv_prepare_operand(bank, n, c.prec, t->bank_hi.p, t->bank_lo.p, s))) return rc;
+  if ((rc = vv_prepare_bank_operand(bank, bank_rows, c.K, c.prec, t->bank_hi.p, t->bank_lo.p, s))) return rc;
   t->bank_reg = bank; t->bank_reg_rows = bank_rows;
   return VV_OK;
 }

@@ -82,7 +82,9 @@ __device__ __forceinline__ void store_x3(float* hi, void* lo, size_t count, size
 // A 128-byte header sits immediately before plane 0 (so every entry point keeps its (hi, lo) pointer pair):
 // the scale the producer uses, its inverse for the GEMM epilogue, and the largest |x| the last producer saw,
 // from which vv_operand_rescale picks the next scale.
-struct F16Hdr { float scale; float inv_scale; uint32_t absmax_bits; uint32_t reserved; };
+// layout: 0 = two planes (hi = h0, lo = h1); 1 = row-interleaved in blocks of 64 elements: a row of K elements is
+// K/64 blocks [64 x h0 | 64 x h1] (256 contiguous bytes), the form the gather producers prefer for the resident bank
+struct F16Hdr { float scale; float inv_scale; uint32_t absmax_bits; uint32_t layout; };
 __host__ __device__ __forceinline__ F16Hdr* f16_hdr(const void* hi) {
   return reinterpret_cast<F16Hdr*>(const_cast<char*>(static_cast<const char*>(hi)) - VV_F16X3_HEADER_BYTES);
 }
@@ -233,6 +235,11 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, ui
 // 16-byte asynchronous global->shared copy (LDGSTS); src_bytes = 0 zero-fills the destination
 __device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc, int src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(smem_dst), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+// same, asking L2 to fetch the whole 256-byte block around the source: a K-major row gather walks along the row, so
+// the neighbouring 128 bytes are the next k-block's piece -- one DRAM access per row and two k-blocks instead of two
+__device__ __forceinline__ void cp_async16_l2_256(uint32_t smem_dst, const void* gsrc, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global.L2::256B [%0], [%1], 16, %2;" :: "r"(smem_dst), "l"(gsrc), "r"(src_bytes) : "memory");
 }
 // the mbarrier receives one (pre-counted) arrival from this thread once all its earlier cp.async have landed
 __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {

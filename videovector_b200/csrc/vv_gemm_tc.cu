@@ -325,6 +325,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     const int c = t64 & 7, r0 = t64 >> 3;
     const uint32_t swz = uint32_t((c ^ r0) << 4);
     constexpr int kPlanes = C::split16 ? 2 : 1;
+    // operand addressing: element k of bank row r lives at r*pitch + (k/64)*blk + k%64 (+ h1d for the h1 plane);
+    // two planes: pitch K, blk 64, h1d = plane distance; row-interleaved F16X3 bank: pitch 2K, blk 128, h1d 64
+    const bool il = C::split16 && f16_hdr(p.ga0)->layout == 1u;
+    const long long pitch = il ? 2 * p.ga_pitch : p.ga_pitch;
+    const int blk = il ? 128 : 64;
+    const long long h1d = il ? 64 : (kPlanes == 2 ? (long long)(p.ga1 - p.ga0) : 0);
     int stage = 0; uint32_t phase = 0;
     for (int u = unit0; u < total_units; u += unit_stride) {
       const int split = u / tiles_mn;
@@ -338,7 +344,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 #pragma unroll
         for (int i = 0; i < 16; ++i) {     // an m-tile past the end (odd tile count in a cluster pair) reads row 0, stores nothing
           const int rr = m0 + r0 + 8 * i;
-          rowoff[i] = (rr < p.rowmap_len) ? (long long)p.rowmap[rr] * p.ga_pitch : 0;
+          rowoff[i] = (rr < p.rowmap_len) ? (long long)p.rowmap[rr] * pitch : 0;
         }
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
@@ -346,11 +352,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           int kcol = kb * C::bk + c * 8;
           const int nb = kcol < p.ga_cols ? 16 : 0;                 // K tail: zero fill like TMA
           if (!nb) kcol = 0;                                        // keep the (unread) source address inside the bank
+          const long long koff = (long long)(kcol >> 6) * blk + (kcol & 63);
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const uint32_t dst = sa + uint32_t((r0 + 8 * i) * kRowBytes) + swz;
-            cp_async16(dst, p.ga0 + rowoff[i] + kcol, nb);
-            if (kPlanes == 2) cp_async16(dst + C::a_bytes, p.ga1 + rowoff[i] + kcol, nb);
+            const uint16_t* src = p.ga0 + rowoff[i] + koff;
+            cp_async16_l2_256(dst, src, nb);
+            if (kPlanes == 2) cp_async16_l2_256(dst + C::a_bytes, src + h1d, nb);
           }
           cp_async_mbar_arrive_noinc(&full_bar[stage]);
           if (++stage == C::stages) { stage = 0; phase ^= 1u; }
@@ -364,7 +372,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         for (int kb = kb0; kb < kb1; ++kb) {
           long long rowoff[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) rowoff[j] = (long long)rws[j] * p.ga_pitch;
+          for (int j = 0; j < 8; ++j) rowoff[j] = (long long)rws[j] * pitch;
           if (kb + 1 < kb1) {                                       // next k-block's row indices, ahead of the wait
 #pragma unroll
             for (int j = 0; j < 8; ++j) rws[j] = p.rowmap[(kb + 1) * C::bk + r0 + 8 * j];
@@ -376,11 +384,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             int f = m0 + cf * C::chunk + c * 8;
             const int nb = f < p.ga_cols ? 16 : 0;                  // feature tail: zero fill
             if (!nb) f = 0;
+            const long long foff = (long long)(f >> 6) * blk + (f & 63);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const uint32_t dst = sa + uint32_t(cf * (C::bk * kRowBytes) + (r0 + 8 * j) * kRowBytes) + swz;
-              cp_async16(dst, p.ga0 + rowoff[j] + f, nb);
-              if (kPlanes == 2) cp_async16(dst + C::a_bytes, p.ga1 + rowoff[j] + f, nb);
+              const uint16_t* src = p.ga0 + rowoff[j] + foff;
+              cp_async16_l2_256(dst, src, nb);
+              if (kPlanes == 2) cp_async16_l2_256(dst + C::a_bytes, src + h1d, nb);
             }
           }
           cp_async_mbar_arrive_noinc(&full_bar[stage]);

@@ -127,6 +127,23 @@ prepare_operand_kernel(const float* __restrict__ src, long long n4, int prec, fl
   }
   if (prec == VV_PREC_F16X3) f16_publish_absmax(hi, amax);
 }
+// fp32 [rows, K] -> the row-interleaved F16X3 form (K % 64 == 0): element (r, k) -> h0 at r*2K + (k/64)*128 + k%64, h1 64 further
+__global__ void __launch_bounds__(256)
+prepare_interleaved_kernel(const float* __restrict__ src, long long rows, int K, void* hi) {
+  const float scale = f16_hdr(hi)->scale;
+  float amax = 0.f;
+  const long long n4 = rows * (K >> 2);
+  uint16_t* base = static_cast<uint16_t*>(hi);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = ldg_stream(reinterpret_cast<const float4*>(src) + i);
+    const long long r = i / (K >> 2);
+    const int k = int(i - r * (K >> 2)) * 4;
+    const size_t off = size_t(r) * 2 * K + size_t(k >> 6) * 128 + (k & 63);
+    store_f16x3(base, base + 64, off, v, scale, amax);
+  }
+  f16_publish_absmax(hi, amax);
+}
+__global__ void set_layout_kernel(void* hi, unsigned layout) { f16_hdr(hi)->layout = layout; }
 // F16X3 header maintenance
 __global__ void __launch_bounds__(256)
 absmax_kernel(const float* __restrict__ src, long long n, void* hi) {
@@ -433,11 +450,30 @@ extern "C" int vv_prepare_operand(const float* src, int64_t count, int prec, voi
     if ((rc = vv_operand_set_scale(hi, prec, 0, stream))) return rc;
     if ((rc = vv_operand_measure(hi, prec, src, count, stream))) return rc;
     if ((rc = vv_operand_rescale(hi, prec, 10, stream))) return rc;
+    set_layout_kernel<<<1, 1, 0, stream>>>(hi, 0u);          // two planes
+    VV_LAUNCH_CHECK();
+    count_launch();
   }
   prepare_operand_kernel<<<stream_grid(n4, 256), 256, 0, stream>>>(src, n4, prec, static_cast<float*>(hi),
                                                                   static_cast<float*>(lo), static_cast<uint16_t*>(hi));
   VV_LAUNCH_CHECK();
   count_launch();
+  return VV_OK;
+}
+
+extern "C" int vv_prepare_bank_operand(const float* bank, int64_t rows, int K, int prec, void* hi, void* lo, vv_stream_t stream) {
+  VV_REQUIRE(bank && hi && rows > 0 && K > 0, "prepare_bank_operand: bad arguments");
+  if (prec != VV_PREC_F16X3 || (K % 64) != 0) return vv_prepare_operand(bank, rows * int64_t(K), prec, hi, lo, stream);
+  VV_REQUIRE(VV_ALIGNED16(bank) && VV_ALIGNED16(hi), "operand buffers must be 16-byte aligned");
+  int rc;
+  if ((rc = vv_operand_set_scale(hi, prec, 0, stream))) return rc;
+  if ((rc = vv_operand_measure(hi, prec, bank, rows * int64_t(K), stream))) return rc;
+  if ((rc = vv_operand_rescale(hi, prec, 12, stream))) return rc;
+  set_layout_kernel<<<1, 1, 0, stream>>>(hi, 1u);
+  VV_LAUNCH_CHECK();
+  prepare_interleaved_kernel<<<stream_grid(rows * (K / 4), 256), 256, 0, stream>>>(bank, rows, K, hi);
+  VV_LAUNCH_CHECK();
+  count_launch(2);
   return VV_OK;
 }
 
