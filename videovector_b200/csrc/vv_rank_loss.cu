@@ -399,7 +399,7 @@ rank_fused_kernel(const float* __restrict__ H, const RankDev p, const float gsca
   const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = T >> 5;
   const int Cc = CT > 0 ? CT : p.C, Nn = NNT > 0 ? NNT : p.Nn;
   const int J = 1 + Nn, R = Cc + Nn;
-  const int per = (2 * J + 1) * nw + 3 * J + 2;        // floats per smem buffer (double buffered by item parity)
+  const int per = (2 * J + 1) * nw + 4 * J + 2;        // floats per smem buffer (double buffered by item parity)
   const bool col_ok = tid < p.N4;
   float4 dbacc = make_float4(0.f, 0.f, 0.f, 0.f), dqacc = make_float4(0.f, 0.f, 0.f, 0.f);
   const float oscale = (out.prec == VV_PREC_F16X3) ? f16_hdr(out.hi)->scale : 1.f;
@@ -410,7 +410,8 @@ rank_fused_kernel(const float* __restrict__ H, const RankDev p, const float gsca
     float* cA = part + (2 * J + 1) * nw;               // [J] coefficient on cbar
     float* cB = cA + J;                                // [J] coefficient on x
     float* cE = cB + J;                                // [J] w_j / n_j
-    float* sc = cE + J;                                // Fs, Fc
+    float* cD = cE + J;                                // [J] K-1 quirk correction of the branch's row (0 without a plan)
+    float* sc = cD + J;                                // Fs, Fc
     // ---- one load phase: R independent 128-bit loads per thread
     float4 x[RMAX];
 #pragma unroll
@@ -480,13 +481,11 @@ rank_fused_kernel(const float* __restrict__ H, const RankDev p, const float gsca
       // max_margin_loss_layer.cpp:149-192: L2 g = h * (lw*2/count); L1 g = [h>0] * lw/count
       float w = neg ? ((p.norm == 2) ? h * gscale : (h > 0.f ? gscale : 0.f)) : 0.f;
       const float vterm = (neg && dlt < 0.f) ? 1.f : 0.f;
-      float loss = 0.f, viol = 0.f, g = 0.f;
-      for (int k = 1; k < J; ++k) {                                       // serial order of the reference loops
-        const float hk = __shfl_sync(0xffffffffu, h, k);
-        loss += (p.norm == 2) ? hk * hk : fabsf(hk);
-        viol += __shfl_sync(0xffffffffu, vterm, k);
-        g += __shfl_sync(0xffffffffu, w, k);
-      }
+      // sums over the negatives as xor-butterfly reductions (the reference sums serially; the order differs, the
+      // three independent butterflies overlap instead of ~30 dependent shuffles on the item's critical path)
+      const float loss = warp_sum(neg ? ((p.norm == 2) ? h * h : fabsf(h)) : 0.f);
+      const float viol = warp_sum(vterm);
+      const float g = warp_sum(w);
       if (lane == 0) w = -g;                                              // d s+ = -1 * d s- (axpby, :210-212)
       if (neg) {
         if (tscore) tscore[size_t(b) * Nn + lane - 1] = score_t;        // sum_true replicates to Nn columns
@@ -496,9 +495,11 @@ rank_fused_kernel(const float* __restrict__ H, const RankDev p, const float gsca
       const float q = powf(sj, 1.5f) + p.eps;                             // normalization_layer.cpp:101-107
       const float aj = w * pj / nc;
       const float e = w / nj;
-      if (lane < J) { cA[lane] = sj * w / (nc * q); cB[lane] = -aj / q; cE[lane] = e; }
-      float ac = 0.f;                                                     // a_c = <cbar, d c^>, split order
-      for (int j = 0; j < J; ++j) ac += __shfl_sync(0xffffffffu, e, j) * __shfl_sync(0xffffffffu, pj, j);
+      if (lane < J) {
+        cA[lane] = sj * w / (nc * q); cB[lane] = -aj / q; cE[lane] = e;
+        cD[lane] = delta ? delta[size_t(lane == 0 ? 0 : Cc + lane - 1) * p.B + b] : 0.f;
+      }
+      const float ac = warp_sum(lane < J ? e * pj : 0.f);                 // a_c = <cbar, d c^>
       if (lane == 0) { const float qc = powf(s_c, 1.5f) + p.eps; sc[0] = s_c / qc; sc[1] = -ac / qc; }
     }
     __syncthreads();
@@ -520,8 +521,8 @@ rank_fused_kernel(const float* __restrict__ H, const RankDev p, const float gsca
             o.z = xv.z > 0.f ? o.z * dscale : 0.f; o.w = xv.w > 0.f ? o.w * dscale : 0.f;
           }
           dbacc.x += o.x; dbacc.y += o.y; dbacc.z += o.z; dbacc.w += o.w;
-          if (delta) {                                                    // uniform
-            const float dl = delta[size_t(r) * p.B + b];
+          const float dl = cD[j];
+          if (dl != 0.f) {                                                // uniform; only rows hit by the K-1 copy quirk
             dqacc.x = fmaf(dl, o.x, dqacc.x); dqacc.y = fmaf(dl, o.y, dqacc.y);
             dqacc.z = fmaf(dl, o.z, dqacc.z); dqacc.w = fmaf(dl, o.w, dqacc.w);
           }
@@ -683,7 +684,7 @@ extern "C" int vv_rank_loss_fused(const float* H, const vv_rank_cfg_t* cfg, floa
   const int count = d.B * d.Nn;
   const float gscale = (d.norm == 2) ? loss_weight * 2 / count : loss_weight / count;
   const int J = 1 + d.Nn, nw = T / 32, R = d.C + d.Nn;
-  const size_t smem = sizeof(float) * 2 * ((2 * J + 1) * nw + 3 * J + 2);
+  const size_t smem = sizeof(float) * 2 * ((2 * J + 1) * nw + 4 * J + 2);
   const int per_sm = (R <= 16) ? 4 : 2;         // resident CTAs per SM at the kernels' register counts x T threads
   const int grid = d.B < num_sms() * per_sm ? d.B : num_sms() * per_sm;
   const int mode = (o.dZ ? 1 : 0) | (o.prec == VV_PREC_TF32X3 ? 2 : 0) | (o.prec == VV_PREC_BF16 ? 4 : 0) |
