@@ -283,7 +283,7 @@ def run_gpu(args):
 
         # ---- leg 3: `e2e` -- the public API with HOST buffers: sampler (prefetch thread, as the reference's
         # prefetching data layer) -> pinned host indices -> H2D -> step -> D2H loss, all inside the timed region
-        nbuf = 3
+        nbuf = 8                  # batches the sampler thread may run ahead (absorbs host jitter; the average rates decide)
         hi = [torch.empty((B, R), dtype=torch.int32).pin_memory() for _ in range(nbuf)]
         hq = [torch.empty((B, R), dtype=torch.int32).pin_memory() for _ in range(nbuf)]
         di = [torch.empty((B, R), dtype=torch.int32, device="cuda") for _ in range(nbuf)]
