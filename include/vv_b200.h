@@ -172,14 +172,15 @@ int vv_ip_bias_grad(const float* dZ, int M, int N, float* db, vv_stream_t stream
 int vv_ip_dgrad(vv_operand_t dZ, vv_operand_t W, int M, int N, int K, int prec,
                 float* dX, vv_stream_t stream);
 
-/* ---- gather-fused variants: K0 folded into K1's TMA producer (cp.async.bulk.tensor tile::gather4). ----
+/* ---- gather-fused variants: K0 folded into K1 (two producer warps fetch the rows with 16-byte cp.async). ----
  * The X operand is never materialised: `bank` is the operand copy of the whole resident feature bank
- * (vv_prepare_operand of the bank, made once) and rowmap/delta come from vv_gather_plan:
+ * (vv_prepare_bank_operand, made once; BF16 or F16X3) and rowmap/delta come from vv_gather_plan:
  *   rowmap [round_up(R*B,128)] int32 : bank row of X row j*B+b
  *   delta  [round_up(R*B,128)] fp32  : correction of feature K-1 for rows hit by the K-1 copy quirk
  * forward : Z = bank[rowmap] W^T + delta (x) W[:,K-1] + bias      (wlast [N] = W[:,K-1], fp32)
  * wgrad   : dW = dZ^T bank[rowmap]; the quirk's contribution to dW[:,K-1] is sum_m delta[m] dZ[m,:], which
- *           vv_rank_loss_backward_ex accumulates (dq_accum) and vv_add_column adds.  Tensor-core precisions only. */
+ *           vv_rank_loss_backward_ex / vv_rank_loss_fused accumulate (dq_accum) and vv_add_column adds; computed as
+ *           (X^T dZ)^T so that the gathered operand is again operand A.  2-byte operand formats only (BF16, F16X3). */
 int vv_gather_plan(const float* bank, int K, const int32_t* idx, const int32_t* quirk, int B, int R,
                    int32_t* rowmap, float* delta, vv_stream_t stream);
 int vv_ip_forward_gathered(vv_operand_t bank, int64_t bank_rows, const int32_t* rowmap, const float* delta,

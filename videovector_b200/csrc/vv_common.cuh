@@ -245,15 +245,6 @@ __device__ __forceinline__ void cp_async16_l2_256(uint32_t smem_dst, const void*
 __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tma_gather4(void* smem_dst, const void* tmap, uint64_t* bar, int col,
-                                            int r0, int r1, int r2, int r3) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      :: "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)),
-         "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
-      : "memory");
-}
 __device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const void* tmap, uint64_t* bar,
                                                  int c0, int c1, uint64_t policy) {
   asm volatile(
