@@ -110,6 +110,8 @@ def cpu_reference_run(steps, warmup, threads=0):
     c = CFG
     B = CPU_SAMPLE_B
     V, S = 512, 16                                       # 8192 shots >= the 5000-entry negative buffer
+    if threads <= 0:                                     # every host core this process may use, whatever OMP_NUM_THREADS says
+        threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     cores = orc.use_openblas(threads)                    # same OpenBLAS instance the reference library links
     use_ref = pyref.available()
     feat = ops.bank_host(V * S, c["K"], 1234)
