@@ -14,6 +14,11 @@ from videovector_b200 import caffe_host as ch
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
+@pytest.fixture(scope="module", autouse=True)
+def _built(vvlib):            # builds libvv_b200.so on first use if the tree is fresh
+    return vvlib
+
+
 def _classes():
     from google.protobuf import descriptor_pb2, descriptor_pool, message_factory
     fds = descriptor_pb2.FileDescriptorSet()
