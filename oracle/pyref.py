@@ -68,3 +68,24 @@ def inner_product(X, W, b, dZ, regularization=0.0):
     Z = np.empty((M, N), np.float32); dW = np.empty((N, K), np.float32); db = np.empty(N, np.float32); dX = np.empty((M, K), np.float32)
     assert lib().ref_inner_product(M, N, K, _p(X), _p(W), _p(b), _p(dZ), C.c_float(regularization), _p(Z), _p(dW), _p(db), _p(dX)) == 0
     return Z, dW, db, dX
+
+
+def retrieval_stats(E, video_ids, id_to_class_file, exclude_same_video_shots=True):
+    """The reference's RetrievalStatsLayer (shot level).  Returns (mAP, hit@1, hit@5)."""
+    E = f32(E); ids = f32(video_ids)
+    out = np.zeros(3, np.float32)
+    rc = lib().ref_retrieval_stats(E.shape[0], E.shape[1], _p(E), _p(ids), str(id_to_class_file).encode(), int(exclude_same_video_shots), _p(out))
+    assert rc == 0
+    return out
+
+
+def id_to_weight(table, ids, top_diff=None):
+    """The reference's IdToWeightMappingLayer: (top, table_diff or None)."""
+    table = f32(table); ids = f32(ids)
+    M = ids.size; rows, N = table.shape
+    top = np.empty((M, N), np.float32)
+    d = np.empty((rows, N), np.float32) if top_diff is not None else None
+    td = f32(top_diff) if top_diff is not None else None
+    rc = lib().ref_id_to_weight(M, N, rows, _p(table), _p(ids), _p(td), _p(top), _p(d))
+    assert rc == 0
+    return top, d

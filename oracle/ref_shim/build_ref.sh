@@ -20,10 +20,10 @@ PY
 [ -n "$BLAS" ] || { echo "no OpenBLAS found"; exit 1; }
 # hidden visibility: the reference's caffe:: symbols must not interpose with (or be interposed by) the product's
 # caffe_compat classes of the same names when both libraries are loaded into one process (bench.py)
-CXXFLAGS="-std=c++14 -O2 -fPIC -fvisibility=hidden -fvisibility-inlines-hidden -DCPU_ONLY -w -include cstring -include climits -include unistd.h -include cstdlib -I$HERE/include -I$OUT/gen -I$REF/include"
+CXXFLAGS="-std=c++14 -O2 -fPIC -fvisibility=hidden -fvisibility-inlines-hidden -DCPU_ONLY -w -include cstring -include climits -include unistd.h -include cstdlib -include numeric -I$HERE/include -I$OUT/gen -I$REF/include"
 SRCS="blob syncedmem common util/math_functions layers/inner_product_layer layers/relu_layer layers/dropout_layer layers/eltwise_layer
       layers/normalization_layer layers/sum_layer layers/split_layer layers/slice_layer layers/concat_layer layers/flatten_layer
-      layers/max_margin_loss_layer layers/loss_layer layers/neuron_layer"
+      layers/max_margin_loss_layer layers/loss_layer layers/neuron_layer layers/retrieval_stats_layer layers/id_to_weight_mapping_layer"
 OBJS=""
 for s in $SRCS; do
   o="$OUT/obj/$(basename $s).o"

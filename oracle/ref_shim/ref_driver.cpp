@@ -203,4 +203,48 @@ REF_API int ref_inner_product(int M, int N, int K, const float* X, const float* 
   } catch (const std::exception& e) { fprintf(stderr, "ref_driver: %s\n", e.what()); return -1; }
 }
 
+// RetrievalStatsLayer (retrieval_stats_layer.cpp), shot level: E [B,N], video ids and an id->class text file; out = {mAP, hit@1, hit@5}
+REF_API int ref_retrieval_stats(int B, int N, const float* E, const float* video_ids, const char* id_to_class_file,
+                                int exclude_same_video_shots, float* out3) {
+  try {
+    Caffe::set_mode(Caffe::CPU);
+    Blob<float> e(B, N, 1, 1), ids(B, 1, 1, 1), t0, t1, t2;
+    memcpy(e.mutable_cpu_data(), E, sizeof(float) * size_t(B) * N);
+    memcpy(ids.mutable_cpu_data(), video_ids, sizeof(float) * B);
+    LayerParameter p;
+    p.mutable_retrieval_stats_param()->set_id_to_class_file(id_to_class_file);
+    p.mutable_retrieval_stats_param()->set_exclude_same_video_shots(exclude_same_video_shots != 0);
+    RetrievalStatsLayer<float> l(p);
+    BV bv{&e, &ids}, tv{&t0, &t1, &t2};
+    l.SetUp(bv, &tv); l.Forward(bv, &tv);
+    out3[0] = t0.cpu_data()[0]; out3[1] = t1.cpu_data()[0]; out3[2] = t2.cpu_data()[0];
+    return 0;
+  } catch (const std::exception& e) { fprintf(stderr, "ref_driver: %s\n", e.what()); return -1; }
+}
+// IdToWeightMappingLayer (id_to_weight_mapping_layer.cpp): table [rows,N], ids [M]; top [M,N] and the table gradient for top_diff
+REF_API int ref_id_to_weight(int M, int N, int rows, const float* table, const float* ids, const float* top_diff,
+                             float* top, float* table_diff) {
+  try {
+    Caffe::set_mode(Caffe::CPU);
+    Blob<float> b(M, 1, 1, 1), t;
+    memcpy(b.mutable_cpu_data(), ids, sizeof(float) * M);
+    LayerParameter p;
+    p.mutable_id_to_weight_mapping_param()->set_num_output(N);
+    p.mutable_id_to_weight_mapping_param()->set_max_ids(rows);
+    p.mutable_id_to_weight_mapping_param()->mutable_weight_filler()->set_type("constant");
+    IdToWeightMappingLayer<float> l(p);
+    BV bv{&b}, tv{&t};
+    l.SetUp(bv, &tv);
+    memcpy(l.blobs()[0]->mutable_cpu_data(), table, sizeof(float) * size_t(rows) * N);
+    l.Forward(bv, &tv);
+    memcpy(top, t.cpu_data(), sizeof(float) * size_t(M) * N);
+    if (top_diff && table_diff) {
+      memcpy(t.mutable_cpu_diff(), top_diff, sizeof(float) * size_t(M) * N);
+      l.Backward(tv, {false}, &bv);
+      memcpy(table_diff, l.blobs()[0]->cpu_diff(), sizeof(float) * size_t(rows) * N);
+    }
+    return 0;
+  } catch (const std::exception& e) { fprintf(stderr, "ref_driver: %s\n", e.what()); return -1; }
+}
+
 }  // extern "C"

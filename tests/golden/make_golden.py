@@ -48,3 +48,29 @@ Z, dW, db, dX = pyref.inner_product(X, W, bb, dZ, regularization=0.5)
 np.savez_compressed(os.path.join(OUT, "layers.npz"), norm_x=x, norm_dy=dy, norm_y=y, norm_dx=dx, mm_t=t, mm_s=s,
                     ip_X=X, ip_W=W, ip_b=bb, ip_dZ=dZ, ip_Z=Z, ip_dW=dW, ip_db=db, ip_dX=dX, **mm)
 print("layers.npz written")
+
+# TEST-phase + embedding-table layers: RetrievalStatsLayer and IdToWeightMappingLayer of the reference
+import tempfile
+rng = np.random.RandomState(2015)
+Bq, Nq, ncls = 97, 24, 4
+cls_of_video = rng.randint(0, ncls, 40)
+vids = rng.randint(0, 40, Bq).astype(np.float32)
+centers = rng.normal(0, 1, (ncls, Nq)).astype(np.float32)
+E = centers[cls_of_video[vids.astype(int)]] * 0.8 + rng.normal(0, 1, (Bq, Nq)).astype(np.float32)
+E = (E / np.sqrt((E ** 2).sum(1, keepdims=True))).astype(np.float32)
+idmap = {v: int(cls_of_video[v]) for v in range(40)}
+idmap[7] = -1                                                   # an unscored video (label < 0)
+with tempfile.NamedTemporaryFile("w", suffix=".txt", delete=False) as f:
+    f.write("".join("%d,%d\n" % kv for kv in idmap.items()))
+rs = {}
+for excl in (0, 1):
+    rs["rs_out_%d" % excl] = pyref.retrieval_stats(E, vids, f.name, bool(excl))
+os.unlink(f.name)
+table = rng.normal(0, 1, (11, 9)).astype(np.float32)
+ids = rng.randint(0, 11, 30).astype(np.float32); ids[:8] = 3
+tdiff = rng.normal(0, 1, (30, 9)).astype(np.float32)
+top, tgrad = pyref.id_to_weight(table, ids, tdiff)
+np.savez_compressed(os.path.join(OUT, "eval_layers.npz"), rs_E=E, rs_vids=vids, rs_map_keys=np.array(list(idmap.keys()), np.int32),
+                    rs_map_vals=np.array(list(idmap.values()), np.int32), id_table=table, id_ids=ids, id_tdiff=tdiff, id_top=top,
+                    id_tgrad=tgrad, **rs)
+print("eval_layers.npz written", rs)

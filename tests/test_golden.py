@@ -72,3 +72,18 @@ def test_live_reference_agrees_with_fixtures_and_oracle(oracle):
         oracle.use_builtin_blas()
         assert abs(o["loss"][0] - r["loss"][0]) < 2e-6 * max(1, r["loss"][0]) and o["violations"][0] == r["violations"][0]
         assert rel(o["dW"], r["dW"]) < 5e-6 and rel(o["db"], r["db"]) < 5e-6 and rel(o["dZ"], r["dZ"]) < 5e-6
+
+
+def test_oracle_reproduces_reference_eval_layers(oracle):
+    """RetrievalStatsLayer / IdToWeightMappingLayer outputs of the compiled reference (tests/golden/eval_layers.npz)."""
+    g = np.load(os.path.join(GOLD, "eval_layers.npz"))
+    idmap = dict(zip(g["rs_map_keys"].tolist(), g["rs_map_vals"].tolist()))
+    vids = g["rs_vids"].astype(np.int32)
+    labels = np.array([idmap[int(v)] for v in vids], np.int32)
+    assert (labels < 0).any()
+    for excl in (0, 1):
+        o = oracle.retrieval_stats(g["rs_E"], vids, labels, bool(excl))
+        ref = g["rs_out_%d" % excl]
+        assert abs(o["map"] - ref[0]) < 1e-6 and abs(o["hit1"] - ref[1]) < 1e-6 and abs(o["hit5"] - ref[2]) < 1e-6, (excl, o, ref)
+    assert np.array_equal(oracle.id_lookup_forward(g["id_table"], g["id_ids"]), g["id_top"])
+    assert np.array_equal(oracle.id_lookup_backward(g["id_tdiff"], g["id_ids"], g["id_table"].shape[0]), g["id_tgrad"])

@@ -59,3 +59,21 @@ def test_layer_kernels_reproduce_reference(vvlib):
         b = torch.as_tensor(np.pad(g["ip_b"], (0, 6))).cuda()
         H, _ = ops.ip_forward(ops.prepare_operand(X, prec), ops.prepare_operand(W, prec), b, 7, 16, 64, prec)
         assert rel(H[:, :10], g["ip_Z"]) < tol
+
+
+def test_device_eval_kernels_reproduce_reference_fixtures():
+    """vv_retrieval_stats / vv_id_lookup_* against the compiled reference's outputs (tests/golden/eval_layers.npz)."""
+    import torch
+    from videovector_b200 import ops
+    g = np.load(os.path.join(GOLD, "eval_layers.npz"))
+    idmap = dict(zip(g["rs_map_keys"].tolist(), g["rs_map_vals"].tolist()))
+    vids = g["rs_vids"].astype(np.int32)
+    labels = np.array([idmap[int(v)] for v in vids], np.int32)
+    for excl in (0, 1):
+        o = ops.retrieval_stats(torch.as_tensor(g["rs_E"]).cuda(), vids, labels, bool(excl))
+        ref = g["rs_out_%d" % excl]
+        assert abs(o["map"] - ref[0]) < 1e-5 and abs(o["hit1"] - ref[1]) < 1e-6 and abs(o["hit5"] - ref[2]) < 1e-6, (excl, o, ref)
+    top = ops.id_lookup_forward(torch.as_tensor(g["id_table"]).cuda(), torch.as_tensor(g["id_ids"]).cuda())
+    assert np.array_equal(top.cpu().numpy(), g["id_top"])
+    d = ops.id_lookup_backward(torch.as_tensor(g["id_tdiff"]).cuda(), torch.as_tensor(g["id_ids"]).cuda(), g["id_table"].shape[0])
+    assert np.array_equal(d.cpu().numpy(), g["id_tgrad"])
