@@ -89,3 +89,34 @@ def id_to_weight(table, ids, top_diff=None):
     rc = lib().ref_id_to_weight(M, N, rows, _p(table), _p(ids), _p(td), _p(top), _p(d))
     assert rc == 0
     return top, d
+
+
+class Sampler:
+    """The REFERENCE's VideoSampledShotsDataLayer itself (compiled unmodified) over an in-memory fake LMDB.  Draws from the
+    process-global libc rand() like the oracle's sampler does: run one of them to completion before the other."""
+
+    def __init__(self, video_id, shot_off, shot_ids, feat, K, batch_size, context_size=5, num_negative_samples=10,
+                 max_buffer_size=5000, negative_swap_percentage=50, max_same_video_negs=6, seed=1, context_type=1):
+        L = lib()
+        L.ref_sampler_create.restype = C.c_void_p
+        L.ref_sampler_next.argtypes = [C.c_void_p, C.c_void_p]
+        L.ref_sampler_rows.argtypes = [C.c_void_p]
+        L.ref_sampler_destroy.argtypes = [C.c_void_p]
+        self.vid = np.ascontiguousarray(video_id, np.int32); self.off = np.ascontiguousarray(shot_off, np.int32)
+        self.sid = np.ascontiguousarray(shot_ids, np.int32); self.feat = f32(feat)
+        L.ref_srand(C.c_uint(seed))
+        self._h = L.ref_sampler_create(len(self.vid), K, _p(self.vid), _p(self.off), _p(self.sid), _p(self.feat), batch_size,
+                                       context_size, num_negative_samples, max_buffer_size, negative_swap_percentage,
+                                       max_same_video_negs, context_type)
+        if not self._h:
+            raise RuntimeError("reference data layer failed to set up")
+        self.B, self.R, self.K = batch_size, L.ref_sampler_rows(self._h), K
+
+    def next(self):
+        data = np.empty((self.B, self.R, self.K), np.float32)
+        assert lib().ref_sampler_next(self._h, _p(data)) == 0
+        return data
+
+    def close(self):
+        if self._h:
+            lib().ref_sampler_destroy(self._h); self._h = None

@@ -155,9 +155,12 @@ def gen(proto_text, package):
                    "\n  void Clear() {\n" + "\n".join(clear) + "\n  }\n"
                    "  void CopyFrom(const %s& o) { *this = o; }\n  void MergeFrom(const %s& o) { *this = o; }\n"
                    "  std::string DebugString() const { return \"<%s>\"; }\n"
-                   "  bool ParseFromString(const std::string&) { return false; }\n  bool ParseFromArray(const void*, int) { return false; }\n"
+                   "  bool ParseFromString(const std::string&) { return false; }\n"
+                   "  // no wire format in the shim: the in-memory fake LMDB of ref_driver.cpp hands out a pointer to a live message\n"
+                   "  // (size = VV_SHIM_LIVE_OBJECT) and parsing is a copy\n"
+                   "  bool ParseFromArray(const void* p, int n) { if (n != -0x5EED) return false; *this = *static_cast<const %s*>(p); return true; }\n"
                    "  bool SerializeToString(std::string*) const { return false; }\n"
-                   "  static const %s& default_instance() { static %s d; return d; }\n private:\n" % (name, name, name, name, name) +
+                   "  static const %s& default_instance() { static %s d; return d; }\n private:\n" % (name, name, name, name, name, name) +
                    "\n".join(priv) + "\n};")
     # out-of-line bodies that need complete types
     for name, fields in messages.items():

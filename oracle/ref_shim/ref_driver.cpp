@@ -11,6 +11,8 @@
 #include "caffe/blob.hpp"
 #include "caffe/common.hpp"
 #include "caffe/vision_layers.hpp"
+#include "caffe/data_layers.hpp"
+#include "caffe/util/io.hpp"
 
 using namespace caffe;  // NOLINT
 typedef std::vector<Blob<float>*> BV;
@@ -246,5 +248,105 @@ REF_API int ref_id_to_weight(int M, int N, int rows, const float* table, const f
     return 0;
   } catch (const std::exception& e) { fprintf(stderr, "ref_driver: %s\n", e.what()); return -1; }
 }
+
+}  // extern "C"
+
+// ---- the reference's own data layer over an in-memory fake LMDB --------------------------------------------------
+// VideoSampledShotsDataLayer (video_sampled_shots_data_layer.cpp) is compiled unmodified; the LMDB C functions it calls
+// are implemented here over a vector of live VideoShots messages (the shim's ParseFromArray copies the object a value
+// points to).  This runs the reference's DataLayerSetUp (negative-buffer initialisation) and InternalThreadEntry
+// (AddSamplesToTop, RandomShuffleTopids, AddToBuffer) -- i.e. the whole sampler state machine on the real libc rand().
+leveldb::Options caffe::GetLevelDBOptions() { return leveldb::Options(); }
+// data_transformer.cpp reads a mean file through this when transform_param.mean_file is set (never here)
+bool caffe::ReadProtoFromBinaryFile(const char*, google::protobuf::Message*) { return false; }
+
+namespace {
+typedef video_shot_sentences::VideoShots VideoShots;
+struct FakeDb { std::vector<std::shared_ptr<VideoShots> > records; };
+FakeDb* g_fake_db = nullptr;          // the dataset the next mdb_env_open serves
+}  // namespace
+struct MDB_env { FakeDb* db; };
+struct MDB_txn { MDB_env* env; };
+struct MDB_cursor { FakeDb* db; size_t pos; };
+extern "C" {
+int mdb_env_create(MDB_env** env) { *env = new MDB_env{nullptr}; return MDB_SUCCESS; }
+int mdb_env_set_mapsize(MDB_env*, size_t) { return MDB_SUCCESS; }
+int mdb_env_open(MDB_env* env, const char*, unsigned int, mdb_mode_t) { env->db = g_fake_db; return env->db ? MDB_SUCCESS : -1; }
+int mdb_txn_begin(MDB_env* env, MDB_txn*, unsigned int, MDB_txn** txn) { *txn = new MDB_txn{env}; return MDB_SUCCESS; }
+int mdb_open(MDB_txn*, const char*, unsigned int, MDB_dbi* dbi) { *dbi = 1; return MDB_SUCCESS; }
+int mdb_cursor_open(MDB_txn* txn, MDB_dbi, MDB_cursor** cursor) { *cursor = new MDB_cursor{txn->env->db, 0}; return MDB_SUCCESS; }
+int mdb_cursor_get(MDB_cursor* c, MDB_val* key, MDB_val* data, MDB_cursor_op op) {
+  if (op == MDB_FIRST) c->pos = 0;
+  else if (op == MDB_NEXT) { if (c->pos + 1 >= c->db->records.size()) return MDB_NOTFOUND; ++c->pos; }
+  if (c->db->records.empty()) return MDB_NOTFOUND;
+  if (key) { key->mv_size = 0; key->mv_data = nullptr; }
+  data->mv_data = c->db->records[c->pos].get();
+  data->mv_size = size_t(VV_SHIM_LIVE_OBJECT);          // ParseFromArray(void*, int) sees -0x5EED
+  return MDB_SUCCESS;
+}
+void mdb_cursor_close(MDB_cursor* c) { delete c; }
+void mdb_close(MDB_env*, MDB_dbi) {}
+void mdb_txn_abort(MDB_txn* t) { delete t; }
+void mdb_env_close(MDB_env* e) { delete e; }
+}  // extern "C"
+
+namespace {
+struct RefSampler {
+  FakeDb db;
+  std::unique_ptr<VideoSampledShotsDataLayer<float> > layer;
+  Blob<float> top;
+  int B, R, K;
+};
+}  // namespace
+
+extern "C" {
+// Dataset as in the oracle's sampler: videos [V] with shots [shot_off[v], shot_off[v+1]) of `feat` [total, K].
+// context_type: 0 PAIRWISE, 1 WINDOW, 2 PAST, 3 PAST_CONTINUOUS, 4 PAST_CONTINUOUS_FIXED.  Call srand(seed) first: the
+// layer draws from the process-global rand() (from its prefetch thread; one batch is always prefetched ahead).
+REF_API void* ref_sampler_create(int V, int K, const int* video_id, const int* shot_off, const int* shot_ids, const float* feat,
+                                 int batch_size, int context_size, int num_negative_samples, int max_buffer_size,
+                                 int negative_swap_percentage, int max_same_video_negs, int context_type) {
+  try {
+    Caffe::set_mode(Caffe::CPU);
+    RefSampler* s = new RefSampler();
+    for (int v = 0; v < V; ++v) {
+      std::shared_ptr<VideoShots> rec(new VideoShots());
+      rec->set_video_id(video_id[v]);
+      for (int g = shot_off[v]; g < shot_off[v + 1]; ++g) {
+        rec->add_shot_ids(shot_ids[g]);
+        Datum* d = rec->add_shot_words();
+        for (int k = 0; k < K; ++k) d->add_float_data(feat[size_t(g) * K + k]);
+      }
+      s->db.records.push_back(rec);
+    }
+    LayerParameter p;
+    VideoSampledShotsDataParameter* vp = p.mutable_video_sampled_shots_data_param();
+    vp->set_source("mem://fake-lmdb"); vp->set_backend(VideoSampledShotsDataParameter_DB_LMDB);
+    vp->set_batch_size(batch_size); vp->set_context_size(context_size); vp->set_num_negative_samples(num_negative_samples);
+    vp->set_max_buffer_size(max_buffer_size); vp->set_negative_swap_percentage(negative_swap_percentage);
+    vp->set_max_same_video_negs(max_same_video_negs);
+    vp->set_context_type(VideoSampledShotsDataParameter_CONTEXT(context_type));
+    g_fake_db = &s->db;
+    s->layer.reset(new VideoSampledShotsDataLayer<float>(p));
+    BV bottom, tv{&s->top};
+    s->layer->SetUp(bottom, &tv);            // DataLayerSetUp (negative buffer init) + first prefetch
+    g_fake_db = nullptr;
+    s->B = batch_size; s->R = s->top.channels(); s->K = K;
+    return s;
+  } catch (const std::exception& e) { fprintf(stderr, "ref_driver: %s\n", e.what()); return nullptr; }
+}
+// next batch: data [B, R, K] as the reference's Forward_cpu hands it to the net
+REF_API int ref_sampler_next(void* h, float* data) {
+  try {
+    RefSampler* s = static_cast<RefSampler*>(h);
+    BV bottom, tv{&s->top};
+    s->layer->Forward(bottom, &tv);
+    memcpy(data, s->top.cpu_data(), sizeof(float) * size_t(s->B) * s->R * s->K);
+    return 0;
+  } catch (const std::exception& e) { fprintf(stderr, "ref_driver: %s\n", e.what()); return -1; }
+}
+REF_API int ref_sampler_rows(void* h) { return static_cast<RefSampler*>(h)->R; }
+REF_API void ref_sampler_destroy(void* h) { delete static_cast<RefSampler*>(h); }
+REF_API void ref_srand(unsigned seed) { srand(seed); }
 
 }  // extern "C"

@@ -74,3 +74,22 @@ np.savez_compressed(os.path.join(OUT, "eval_layers.npz"), rs_E=E, rs_vids=vids, 
                     rs_map_vals=np.array(list(idmap.values()), np.int32), id_table=table, id_ids=ids, id_tdiff=tdiff, id_top=top,
                     id_tgrad=tgrad, **rs)
 print("eval_layers.npz written", rs)
+
+# The data layer itself: the reference's VideoSampledShotsDataLayer (compiled unmodified, fake in-memory LMDB, real libc
+# rand()) for every context type -> data blobs of the first batches.  Pins row S (the sampler).
+rng = np.random.RandomState(77)
+counts = rng.randint(2, 19, size=90)
+s_vid = (rng.permutation(90) + 500).astype(np.int32)
+s_off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+s_sid = np.concatenate([np.sort(rng.choice(400, c, replace=False)) for c in counts]).astype(np.int32)
+s_feat = rng.normal(0, 1, (s_off[-1], 5)).astype(np.float32)
+samp = dict(vid=s_vid, off=s_off, sid=s_sid, feat=s_feat)
+CASES = [("window", 1, 5, 10, 6), ("window_c3", 1, 3, 4, 2), ("past", 2, 4, 6, 4), ("past_continuous", 3, 5, 8, 6),
+         ("past_continuous_fixed", 4, 3, 6, 6), ("pairwise", 0, 2, 6, 0)]
+for name, mode, C, Nn, max_same in CASES:
+    r = pyref.Sampler(s_vid, s_off, s_sid, s_feat, 5, 12, C, Nn, 70, 50, max_same, seed=1, context_type=mode)
+    samp["blobs_" + name] = np.stack([r.next() for _ in range(8)])
+    samp["cfg_" + name] = np.array([mode, 12, C, Nn, 70, 50, max_same], np.int32)
+    r.close()
+np.savez_compressed(os.path.join(OUT, "sampler_ref.npz"), **samp)
+print("sampler_ref.npz written:", [k for k in samp if k.startswith("blobs_")])

@@ -160,3 +160,53 @@ def test_context_type_argument_checks(vvlib):
     ops.Sampler(video_id, shot_off, shot_ids, 4, 4, 4, 20, 50, 2, 100, context_type="past").close()   # PAST does not
     with pytest.raises(Exception):
         ops.Sampler(video_id, shot_off, shot_ids, 4, 5, 4, 20, 50, 2, 100, context_type=7)
+
+
+# ---- pinned to the REFERENCE's own data layer ----------------------------------------------------------------------
+GOLD_SAMPLER = __import__("os").path.join(__import__("os").path.dirname(__import__("os").path.abspath(__file__)), "golden", "sampler_ref.npz")
+FIXTURE_CASES = ["window", "window_c3", "past", "past_continuous", "past_continuous_fixed", "pairwise"]
+
+
+def _blob_from_indices(feat, idx, quirk):
+    blob = feat[idx]
+    K = feat.shape[1]
+    blob[..., K - 1] = np.where(quirk >= 0, feat[np.maximum(quirk, 0), K - 1], np.where(quirk == -1, 0.0, blob[..., K - 1]))
+    return blob
+
+
+@pytest.mark.parametrize("name", FIXTURE_CASES)
+def test_sampler_reproduces_reference_data_layer_fixtures(vvlib, oracle, name):
+    """tests/golden/sampler_ref.npz holds the data blobs the reference's VideoSampledShotsDataLayer ITSELF produced
+    (video_sampled_shots_data_layer.cpp compiled unmodified, fake in-memory LMDB, real libc rand(), seed 1; see
+    make_golden.py).  The oracle's sampler and the product's index stream (+ gather) must rebuild them bit for bit."""
+    g = np.load(GOLD_SAMPLER)
+    mode, B, C, Nn, P, swap, max_same = [int(x) for x in g["cfg_" + name]]
+    ref = g["blobs_" + name]
+    osmp = oracle.Sampler(g["vid"], g["off"], g["sid"], g["feat"], 5, B, C, Nn, P, swap, max_same, 100, seed=1, context_type=mode)
+    for i in range(ref.shape[0]):
+        assert np.array_equal(osmp.next()[2], ref[i]), "oracle differs from the reference data layer at batch %d" % i
+    osmp.close()
+    psmp = ops.Sampler(g["vid"], g["off"], g["sid"], B, C, Nn, P, swap, max_same, 100, rand_seed=1, context_type=mode)
+    for i in range(ref.shape[0]):
+        idx, quirk = psmp.next()
+        assert np.array_equal(_blob_from_indices(g["feat"], idx, quirk), ref[i]), "product differs at batch %d" % i
+    psmp.close()
+
+
+@pytest.mark.parametrize("mode,C", [(1, 5), (2, 6), (3, 4), (4, 5), (0, 2)])
+def test_live_reference_data_layer(vvlib, oracle, mode, C):
+    """Where oracle/_ref was built: the reference's data layer run live on a fresh dataset against the product sampler."""
+    from oracle import pyref
+    if not pyref.available():
+        pytest.skip("oracle/_ref not built on this machine")
+    rng = np.random.RandomState(100 + mode)
+    video_id, shot_off, shot_ids, feat = make_dataset(rng, 150, 2, 25, K=4)
+    B, Nn, P, max_same = 24, 10, 90, (0 if mode == 0 else 6)
+    r = pyref.Sampler(video_id, shot_off, shot_ids, feat, 4, B, C, Nn, P, 50, max_same, seed=3, context_type=mode)
+    ref = [r.next() for _ in range(10)]
+    r.close()
+    psmp = ops.Sampler(video_id, shot_off, shot_ids, B, C, Nn, P, 50, max_same, 100, rand_seed=3, context_type=mode)
+    for i, blob in enumerate(ref):
+        idx, quirk = psmp.next()
+        assert np.array_equal(_blob_from_indices(feat, idx, quirk), blob), "batch %d" % i
+    psmp.close()

@@ -319,6 +319,9 @@ extern "C" vv_sampler_t* vv_sampler_create_ex(int num_videos, const int32_t* vid
         s->key_of[g] = it.first->second;
       }
     s->in_set.assign(ids.size() + 1, 0);     // + one dummy key for the branch-free swap loop
+    // the dummy slot P must hold the dummy key from the start: the swap loop clears in_set[slot_key[pos]] before it
+    // stores, and a zero-initialised dummy slot would name key 0 -- a real shot (found by the reference-pinned fixtures)
+    s->slot_key[s->P] = int32_t(ids.size());
   }
   s->last_full.assign((size_t)batch_size * (context_size + num_negative_samples), -1);
   if (s->P > 0 && !s->init(max_tries_for_negs)) { delete s; return nullptr; }
