@@ -308,6 +308,44 @@ int vv_fill_bank(float* bank, int64_t rows, int K, uint64_t seed, vv_stream_t st
 float vv_bank_value_host(uint64_t seed, int64_t row, int col, int K);
 
 /* ------------------------------------------------------------------------- */
+/* Record reader: the DB values the reference's data layers  */
+/* parse -> a dense host feature bank [rows,K] + the tables the sampler takes.  */
+/*   VV_RECORD_VIDEO_SHOTS : video_shot_sentences.VideoShots                    */
+/*     (video_shot_sentences.proto:15-20), as VideoSampledShotsDataLayer reads  */
+/*     it (video_sampled_shots_data_layer.cpp:184-199,301-314,789-846): one     */
+/*     record per video, one bank row per shot_words datum (float_data only,    */
+/*     feature_size = float_data_size of the first datum), shot_ids alongside.  */
+/*   VV_RECORD_TEST_WINDOWS: video_shot_sentences.TestVideoShotWindows          */
+/*     (:22-30) as VideoShotWindowTestDataLayer reads it                        */
+/*     (video_shot_window_test_data_layer.cpp:95-114,186-239): per record the   */
+/*     context, then (include_positives) positive, then (include_negatives)     */
+/*     negative datums as consecutive rows = one item of the data blob; the     */
+/*     label is video_id.  Sizes are fixed by the first record, later records   */
+/*     must agree (the reference's CHECK_EQs).                                  */
+/* Records are added in DB key order, i.e. the order of the reference's         */
+/* mdb_cursor_get(MDB_FIRST/MDB_NEXT) / leveldb iterator loop: either by the    */
+/* caller from its own cursor (vv_record_set_add; the binding in INTEGRATION.md)*/
+/* or from a file: a "VVRS0001" stream (per record: u32 key_len, key, u64       */
+/* value_len, value; little endian) or the text `mdb_dump [-p]` prints.         */
+/* Protobuf wire format decoded directly: packed and unpacked repeated scalars, */
+/* unknown fields skipped, malformed input -> VV_ERR_INVALID + vv_last_error(). */
+/* ------------------------------------------------------------------------- */
+enum { VV_RECORD_VIDEO_SHOTS = 0, VV_RECORD_TEST_WINDOWS = 1 };
+typedef struct vv_record_set vv_record_set_t;
+vv_record_set_t* vv_record_set_create(int kind, int include_positives, int include_negatives);
+void vv_record_set_destroy(vv_record_set_t* s);
+int vv_record_set_add(vv_record_set_t* s, const void* value, size_t size);
+int vv_record_set_load_file(vv_record_set_t* s, const char* path);
+/* rows_per_record: rows of one TEST item (0 for VIDEO_SHOTS, where it varies: see row_off) */
+int vv_record_set_info(const vv_record_set_t* s, int64_t* records, int64_t* rows, int32_t* feature_size,
+                       int32_t* rows_per_record);
+/* video_id [records], row_off [records+1] (= the sampler's shot_off), shot_ids [rows] (TEST: the positive /
+ * negative shot ids, -1 for context rows); any may be NULL */
+int vv_record_set_tables(const vv_record_set_t* s, int32_t* video_id, int32_t* row_off, int32_t* shot_ids);
+const float* vv_record_set_bank(const vv_record_set_t* s);          /* host [rows, feature_size], owned by the set */
+int vv_record_set_upload(const vv_record_set_t* s, float* bank_dev, vv_stream_t stream);   /* -> device bank */
+
+/* ------------------------------------------------------------------------- */
 /* Host sampler: VideoSampledShotsDataLayer's sampler as an index stream        */
 /* (ref: video_sampled_shots_data_layer.cpp:25-44,245-344,372-507,769-909;     */
 /* util/rng.hpp:43-54).  Self-contained glibc-compatible rand() (TYPE_3, the    */

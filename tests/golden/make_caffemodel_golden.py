@@ -16,9 +16,11 @@ SCALAR = {"double": T.TYPE_DOUBLE, "float": T.TYPE_FLOAT, "int32": T.TYPE_INT32,
           "uint64": T.TYPE_UINT64, "bool": T.TYPE_BOOL, "string": T.TYPE_STRING, "bytes": T.TYPE_BYTES}
 
 
-def build_descriptor(proto_text, package="caffe"):
+def build_descriptor(proto_text, package="caffe", name="caffe.proto", deps=(), external=()):
+    """external: fully qualified message types of imported files (e.g. "caffe.Datum")."""
     text = re.sub(r"//[^\n]*", "", proto_text)
-    fdp = descriptor_pb2.FileDescriptorProto(name="caffe.proto", package=package, syntax="proto2")
+    fdp = descriptor_pb2.FileDescriptorProto(name=name, package=package, syntax="proto2")
+    fdp.dependency.extend(deps)
     names = {}        # fully scoped name -> "message" / "enum"
 
     def scan(body, scope):
@@ -72,6 +74,9 @@ def build_descriptor(proto_text, package="caffe"):
                 f.label = {"optional": T.LABEL_OPTIONAL, "repeated": T.LABEL_REPEATED, "required": T.LABEL_REQUIRED}[label]
                 if typ in SCALAR:
                     f.type = SCALAR[typ]
+                elif typ in external:
+                    f.type = T.TYPE_MESSAGE
+                    f.type_name = "." + typ
                 else:
                     full = resolve(typ, scope)
                     f.type = T.TYPE_ENUM if names[full] == "enum" else T.TYPE_MESSAGE

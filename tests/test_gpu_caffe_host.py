@@ -318,3 +318,74 @@ def test_cli_runs_test_phase(tmp_path):
         assert "Iteration %d, Testing net (#0)" % it in r.stderr
     # net outputs come out of a std::set of blob names (net.cpp:158-165), i.e. in lexicographic order
     assert "    Test net output #0: test_hit_at_1 = " in r.stderr and "    Test net output #2: test_map = " in r.stderr
+
+
+def _record_dataset(rng, V=70, K=256):
+    counts = rng.randint(2, 21, size=V)
+    vid = (rng.permutation(V) + 100).astype(np.int32)
+    off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    sid = np.concatenate([np.sort(rng.choice(300, c, replace=False)) for c in counts]).astype(np.int32)
+    feat = np.maximum(rng.normal(0, 1, (off[-1], K)), 0).astype(np.float32)
+    return vid, off, sid, feat
+
+
+@pytest.mark.parametrize("container", ["vvrs", "lmdb"])
+def test_net_trains_from_video_shots_records(tmp_path, oracle, container):
+    """`source:` naming real VideoShots records: the data layer decodes them into the resident bank,
+    its data blob must equal records -> oracle sampler -> copy, and the fused step on that bank must match the oracle."""
+    import records_util
+    from videovector_b200 import ops
+    rng = np.random.RandomState(11)
+    vid, off, sid, feat = _record_dataset(rng, K=CFG["K"])
+    recs = records_util.video_shots_records(vid, off, sid, feat)
+    if container == "vvrs":
+        src = records_util.write_vvrs(tmp_path / "train.vvrs", recs)
+    else:
+        from lmdb_writer import write_lmdb
+        src = str(tmp_path / "train_lmdb"); write_lmdb(src, recs)
+    cfg = dict(CFG, max_buffer_size=60); cfg.pop("videos"); cfg.pop("shots")
+    W0, b0, mask, mask_dev = problem()
+    caffe_host.set_device(0); caffe_host.set_precision("f16x3")
+    B, C, Nn, K, N = cfg["B"], cfg["C"], cfg["Nn"], cfg["K"], cfg["N"]
+    osmp = oracle.Sampler(vid, off, sid, feat, K, B, C, Nn, 60, 50, 6, 100, seed=1)
+    blobs = [osmp.next()[2] for _ in range(3)]
+    osmp.close()
+    net = caffe_host.Net(prototxt.train_net(source=src, **cfg))
+    net.set_param(0, W0); net.set_param(1, b0); net.set_dropout_mask(mask_dev)
+    for it in range(2):                               # layer by layer: the data blob itself is materialised
+        loss = net.forward_backward()
+        assert np.array_equal(net.blob("data").reshape(B, C + Nn, K), blobs[it])
+        ref = oracle.net_forward_backward(blobs[it], W0, b0, mask, B, C, Nn, margin=2.0, norm=2, dropout_ratio=0.5, want=("loss", "dW"))
+        assert abs(loss - ref["loss"]) < 1e-5 * max(1, abs(ref["loss"]))
+        assert rel(net.param(0, diff=True).reshape(N, K), ref["dW"]) < 1e-5
+    net2 = caffe_host.Net(prototxt.train_net(source=src, **cfg))
+    net2.set_param(0, W0); net2.set_param(1, b0); net2.set_dropout_mask(mask_dev)
+    ok, why = net2.enable_fusion()
+    assert ok, why
+    loss = net2.forward_backward()                    # fused: gather folded into the GEMMs, same first batch
+    ref = oracle.net_forward_backward(blobs[0], W0, b0, mask, B, C, Nn, margin=2.0, norm=2, dropout_ratio=0.5, want=("loss", "dW"))
+    assert abs(loss - ref["loss"]) < 1e-5 * max(1, abs(ref["loss"]))
+    assert rel(net2.param(0, diff=True).reshape(N, K), ref["dW"]) < 1e-5
+
+
+def test_test_net_reads_test_window_records(tmp_path):
+    """TEST-phase data layer on TestVideoShotWindows records: items in DB order, label = video_id, wrap at the end
+    (video_shot_window_test_data_layer.cpp:160-262)."""
+    import records_util
+    rng = np.random.RandomState(12)
+    n, F, K, TB = 37, 4, CFG["K"], 16
+    data = rng.normal(0, 1, (n, F, K)).astype(np.float32); vids = rng.randint(0, 12, n).astype(np.int32)
+    src = records_util.write_vvrs(tmp_path / "test.vvrs", records_util.test_window_records(data, vids))
+    idfile = tmp_path / "id_to_class.txt"; idfile.write_text("".join("%d,%d\n" % (v, v % 3) for v in range(12)))
+    caffe_host.set_device(0); caffe_host.set_precision("f16x3")
+    caffe_host.set_phase("TEST")
+    try:
+        tnet = caffe_host.Net(prototxt.train_net(test=dict(batch=TB, frames=F, source=src, id_to_class_file=str(idfile)), **CFG))
+        for it in range(4):                            # 64 items over 37 records: wraps once
+            tnet.forward()
+            want = (np.arange(TB) + it * TB) % n
+            assert np.array_equal(tnet.blob("data").reshape(TB, F, K), data[want])
+            assert np.array_equal(tnet.blob("video_ids").reshape(-1).astype(np.int32), vids[want])
+            assert 0 <= tnet.blob("test_map").reshape(-1)[0] <= 1
+    finally:
+        caffe_host.set_phase("TRAIN")

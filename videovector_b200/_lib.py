@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libvv_b200.so")
 VV_MAX_CONTEXT = 64
 PREC = {"fp32_simt": 0, "tf32x3": 1, "tf32": 2, "bf16": 3, "f16x3": 4}
 F16X3_HEADER_BYTES = 128
+RECORD_VIDEO_SHOTS, RECORD_TEST_WINDOWS = 0, 1
 CONTEXT = {"pairwise": 0, "window": 1, "past": 2, "past_continuous": 3, "past_continuous_fixed": 4}
 DROPOUT_NONE, DROPOUT_MASK01, DROPOUT_MASK_U32, DROPOUT_PHILOX, DROPOUT_HASH = 0, 1, 2, 3, 4
 
@@ -108,6 +109,14 @@ SIGNATURES = {
     "vv_gather_mean_rows": (_i, [_P, _i64, _i, _P, _i, _i, _P, _P, _P]),
     "vv_retrieval_stats_workspace_bytes": (C.c_size_t, [_i]),
     "vv_retrieval_stats": (_i, [_P, _i, _i, _P, _P, _i, _P, _P, C.c_size_t, _P, _P, _P]),
+    "vv_record_set_create": (_P, [_i, _i, _i]),
+    "vv_record_set_destroy": (None, [_P]),
+    "vv_record_set_add": (_i, [_P, C.c_char_p, C.c_size_t]),
+    "vv_record_set_load_file": (_i, [_P, C.c_char_p]),
+    "vv_record_set_info": (_i, [_P, _P, _P, _P, _P]),
+    "vv_record_set_tables": (_i, [_P, _P, _P, _P]),
+    "vv_record_set_bank": (_P, [_P]),
+    "vv_record_set_upload": (_i, [_P, _P, _P]),
     "vv_sampler_create": (_P, [_i, _P, _P, _P, _i, _i, _i, _i, _i, _i, _i, C.c_uint]),
     "vv_sampler_create_ex": (_P, [_i, _P, _P, _P, _i, _i, _i, _i, _i, _i, _i, C.c_uint, _i]),
     "vv_sampler_destroy": (None, [_P]),

@@ -215,7 +215,7 @@ class VideoSampledShotsDataLayer : public Layer<Dtype> {
   virtual inline int MinTopBlobs() const { return 1; }
   virtual inline int MaxTopBlobs() const { return 2; }
   // access for the net-level fusion pass
-  const float* bank() const { return (const float*)bank_.gpu_data(); }
+  const float* bank() const { return bank_ptr_; }
   int64_t bank_rows() const { return bank_rows_; }
   const int32_t* NextIndices(const int32_t** quirk);   // draws a batch, returns device idx [B,R]
   int batch_size() const { return batch_size_; }
@@ -226,7 +226,8 @@ class VideoSampledShotsDataLayer : public Layer<Dtype> {
   virtual void Forward_gpu(const vector<Blob<Dtype>*>& bottom, vector<Blob<Dtype>*>* top);
   virtual void Backward_gpu(const vector<Blob<Dtype>*>& top, const vector<bool>& propagate_down, vector<Blob<Dtype>*>* bottom) {}
   vv_sampler_t* sampler_;
-  Blob<Dtype> bank_;
+  DeviceBuffer bank_;            // [bank_rows_, feature_size_] fp32 (size_t bytes: real banks exceed a Blob's int count)
+  float* bank_ptr_ = nullptr;
   int64_t bank_rows_;
   int batch_size_, context_size_, num_negative_samples_, feature_size_;
   vector<int32_t> idx_host_, quirk_host_;
@@ -265,10 +266,13 @@ class VideoShotWindowTestDataLayer : public Layer<Dtype> {
  protected:
   virtual void Forward_gpu(const vector<Blob<Dtype>*>& bottom, vector<Blob<Dtype>*>* top);
   virtual void Backward_gpu(const vector<Blob<Dtype>*>& top, const vector<bool>& propagate_down, vector<Blob<Dtype>*>* bottom) {}
-  Blob<Dtype> bank_;
+  DeviceBuffer bank_;
+  float* bank_ptr_ = nullptr;
   int64_t bank_rows_ = 0;
   int videos_ = 0, shots_ = 0, frames_ = 4, batch_size_ = 0, feature_size_ = 0;
   long cursor_ = 0;
+  bool from_records_ = false;    // records: item c = rows [c*frames_, (c+1)*frames_) of the bank, label record_video_id_[c]
+  vector<int32_t> record_video_id_;
   vector<int32_t> idx_host_;
   DeviceBuffer idx_dev_;
 };

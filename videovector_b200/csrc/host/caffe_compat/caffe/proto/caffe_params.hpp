@@ -123,6 +123,8 @@ struct VideoShotWindowTestDataParameter : ParamBase {
   using ParamBase::ParamBase;
   string source() const { return m->str("source", ""); }
   int batch_size() const { return int(m->num("batch_size", 0)); }
+  bool include_positives() const { return m->boolean("include_positives", true); }
+  bool include_negatives() const { return m->boolean("include_negatives", true); }
 };
 struct RetrievalStatsParameter : ParamBase {
   using ParamBase::ParamBase;

@@ -449,19 +449,43 @@ template <typename Dtype>
 void VideoSampledShotsDataLayer<Dtype>::LayerSetUp(const vector<Blob<Dtype>*>& bottom, vector<Blob<Dtype>*>* top) {
   const VideoSampledShotsDataParameter p = this->layer_param_.video_sampled_shots_data_param();
   const string src = p.source();
-  CHECK(src.compare(0, 12, "synthetic://") == 0)
-      << "only synthetic:// sources are built (LMDB/LevelDB readers are out of scope, SURVEY 8f); got '" << src << "'";
-  const int V = int(UrlParam(src, "videos", 2048)), S = int(UrlParam(src, "shots", 32));
-  feature_size_ = int(UrlParam(src, "dim", 4096));
-  const uint64_t seed = uint64_t(UrlParam(src, "seed", 1234));
   batch_size_ = p.batch_size(); context_size_ = p.context_size(); num_negative_samples_ = p.num_negative_samples();
+  CHECK(p.negative_dataset().empty()) << "negative_dataset is not built";
+  CHECK_EQ(p.rand_skip(), 0) << "rand_skip is not built";
+  int V = 0;
+  vector<int32_t> vid, off, ids;
+  if (src.compare(0, 12, "synthetic://") == 0) {
+    V = int(UrlParam(src, "videos", 2048));
+    const int S = int(UrlParam(src, "shots", 32));
+    feature_size_ = int(UrlParam(src, "dim", 4096));
+    const uint64_t seed = uint64_t(UrlParam(src, "seed", 1234));
+    CHECK_GE(feature_size_, 1);
+    bank_rows_ = int64_t(V) * S;
+    bank_ptr_ = static_cast<float*>(bank_.get(size_t(bank_rows_) * feature_size_ * sizeof(float)));
+    VV_CHECK(vv_fill_bank(bank_ptr_, bank_rows_, feature_size_, seed, Caffe::stream()));
+    vid.resize(V); off.resize(V + 1); ids.resize(size_t(V) * S);
+    for (int v = 0; v < V; ++v) { vid[v] = v; off[v] = v * S; for (int s = 0; s < S; ++s) ids[size_t(v) * S + s] = s; }
+    off[V] = V * S;
+  } else {
+    // the reference's `source`: an LMDB environment of VideoShots records (:121-135), or a VVRS / mdb_dump file of them;
+    // every record is decoded once into the resident device bank, the cursor loop becomes the sampler's index stream
+    vv_record_set_t* rs = vv_record_set_create(VV_RECORD_VIDEO_SHOTS, 1, 1);
+    CHECK(rs) << vv_last_error();
+    const int rc = vv_record_set_load_file(rs, src.c_str());
+    if (rc != 0) { const string e = vv_last_error(); vv_record_set_destroy(rs); LOG_FATAL << "cannot read VideoShots records from '" << src << "': " << e; }
+    int64_t records = 0, rows = 0; int32_t K = 0;
+    VV_CHECK(vv_record_set_info(rs, &records, &rows, &K, nullptr));
+    if (records < 1 || rows < 1) { vv_record_set_destroy(rs); LOG_FATAL << "no VideoShots records in '" << src << "'"; }
+    V = int(records); feature_size_ = K; bank_rows_ = rows;
+    vid.resize(V); off.resize(V + 1); ids.resize(size_t(rows));
+    VV_CHECK(vv_record_set_tables(rs, vid.data(), off.data(), ids.data()));
+    bank_ptr_ = static_cast<float*>(bank_.get(size_t(rows) * K * sizeof(float)));
+    const int urc = vv_record_set_upload(rs, bank_ptr_, Caffe::stream());
+    vv_record_set_destroy(rs);
+    VV_CHECK(urc);
+    LogInfo("VideoShots records: " + std::to_string(records) + " videos, " + std::to_string(rows) + " shots, feature size " + std::to_string(K));
+  }
   CHECK_GE(feature_size_, 1); CHECK_GE(context_size_, 2); CHECK_GE(batch_size_, 1);
-  bank_rows_ = int64_t(V) * S;
-  bank_.Reshape(int(bank_rows_), 1, feature_size_, 1);
-  VV_CHECK(vv_fill_bank(bank_.mutable_gpu_data(), bank_rows_, feature_size_, seed, Caffe::stream()));
-  vector<int32_t> vid(V), off(V + 1), ids(size_t(V) * S);
-  for (int v = 0; v < V; ++v) { vid[v] = v; off[v] = v * S; for (int s = 0; s < S; ++s) ids[size_t(v) * S + s] = s; }
-  off[V] = V * S;
   sampler_ = vv_sampler_create_ex(V, vid.data(), off.data(), ids.data(), batch_size_, context_size_, num_negative_samples_,
                                   p.max_buffer_size(), p.negative_swap_percentage(), p.max_same_video_negs(), 100,
                                   1 /* rand() is never seeded */, int(p.context_type()));
@@ -533,16 +557,34 @@ template <typename Dtype>
 void VideoShotWindowTestDataLayer<Dtype>::LayerSetUp(const vector<Blob<Dtype>*>& bottom, vector<Blob<Dtype>*>* top) {
   const VideoShotWindowTestDataParameter p = this->layer_param_.video_shot_window_test_data_param();
   const string src = p.source();
-  CHECK(src.compare(0, 12, "synthetic://") == 0)
-      << "only synthetic:// sources are built (LMDB/LevelDB readers are out of scope, SURVEY 8f); got '" << src << "'";
-  videos_ = int(UrlParam(src, "videos", 256)); shots_ = int(UrlParam(src, "shots", 32));
-  feature_size_ = int(UrlParam(src, "dim", 4096)); frames_ = int(UrlParam(src, "frames", 4));
-  const uint64_t seed = uint64_t(UrlParam(src, "seed", 4321));
   batch_size_ = p.batch_size();
-  CHECK_GE(batch_size_, 1); CHECK_GE(frames_, 1); CHECK_GE(shots_, frames_);
-  bank_rows_ = int64_t(videos_) * shots_;
-  bank_.Reshape(int(bank_rows_), 1, feature_size_, 1);
-  VV_CHECK(vv_fill_bank(bank_.mutable_gpu_data(), bank_rows_, feature_size_, seed, Caffe::stream()));
+  CHECK_GE(batch_size_, 1);
+  if (src.compare(0, 12, "synthetic://") == 0) {
+    videos_ = int(UrlParam(src, "videos", 256)); shots_ = int(UrlParam(src, "shots", 32));
+    feature_size_ = int(UrlParam(src, "dim", 4096)); frames_ = int(UrlParam(src, "frames", 4));
+    const uint64_t seed = uint64_t(UrlParam(src, "seed", 4321));
+    CHECK_GE(frames_, 1); CHECK_GE(shots_, frames_);
+    bank_rows_ = int64_t(videos_) * shots_;
+    bank_ptr_ = static_cast<float*>(bank_.get(size_t(bank_rows_) * feature_size_ * sizeof(float)));
+    VV_CHECK(vv_fill_bank(bank_ptr_, bank_rows_, feature_size_, seed, Caffe::stream()));
+  } else {
+    // TestVideoShotWindows records (video_shot_window_test_data_layer.cpp:76-135): channels = context (+ positive
+    // + negative) datums of one record, label = its video_id, the cursor wraps at the end (:241-262)
+    vv_record_set_t* rs = vv_record_set_create(VV_RECORD_TEST_WINDOWS, p.include_positives(), p.include_negatives());
+    CHECK(rs) << vv_last_error();
+    const int rc = vv_record_set_load_file(rs, src.c_str());
+    if (rc != 0) { const string e = vv_last_error(); vv_record_set_destroy(rs); LOG_FATAL << "cannot read TestVideoShotWindows records from '" << src << "': " << e; }
+    int64_t records = 0, rows = 0; int32_t K = 0, per = 0;
+    VV_CHECK(vv_record_set_info(rs, &records, &rows, &K, &per));
+    if (records < 1) { vv_record_set_destroy(rs); LOG_FATAL << "no TestVideoShotWindows records in '" << src << "'"; }
+    from_records_ = true; videos_ = int(records); frames_ = per; feature_size_ = K; bank_rows_ = rows;
+    record_video_id_.resize(size_t(records));
+    VV_CHECK(vv_record_set_tables(rs, record_video_id_.data(), nullptr, nullptr));
+    bank_ptr_ = static_cast<float*>(bank_.get(size_t(rows) * K * sizeof(float)));
+    const int urc = vv_record_set_upload(rs, bank_ptr_, Caffe::stream());
+    vv_record_set_destroy(rs);
+    VV_CHECK(urc);
+  }
   (*top)[0]->Reshape(batch_size_, frames_, feature_size_, 1);     // channels = frames, height = feature
   (*top)[1]->Reshape(batch_size_, 1, 1, 1);
   idx_host_.resize(size_t(batch_size_) * frames_);
@@ -551,7 +593,12 @@ template <typename Dtype>
 void VideoShotWindowTestDataLayer<Dtype>::Forward_gpu(const vector<Blob<Dtype>*>& bottom, vector<Blob<Dtype>*>* top) {
   // record c = window number: video c % V, first shot ((c / V) * frames) % (S - frames + 1)
   Dtype* ids = (*top)[1]->mutable_cpu_data();
-  for (int b = 0; b < batch_size_; ++b, ++cursor_) {
+  for (int b = 0; b < batch_size_ && from_records_; ++b, ++cursor_) {
+    const long c = cursor_ % videos_;
+    for (int f = 0; f < frames_; ++f) idx_host_[size_t(b) * frames_ + f] = int32_t(c * frames_ + f);
+    ids[b] = Dtype(record_video_id_[size_t(c)]);
+  }
+  for (int b = 0; b < batch_size_ && !from_records_; ++b, ++cursor_) {
     const int v = int(cursor_ % videos_);
     const int start = int(((cursor_ / videos_) * frames_) % (shots_ - frames_ + 1));
     for (int f = 0; f < frames_; ++f) idx_host_[size_t(b) * frames_ + f] = v * shots_ + start + f;
@@ -560,7 +607,7 @@ void VideoShotWindowTestDataLayer<Dtype>::Forward_gpu(const vector<Blob<Dtype>*>
   const size_t bytes = idx_host_.size() * sizeof(int32_t);
   int32_t* di = static_cast<int32_t*>(idx_dev_.get(bytes));
   CHECK_EQ(int(cudaMemcpyAsync(di, idx_host_.data(), bytes, cudaMemcpyHostToDevice, reinterpret_cast<cudaStream_t>(Caffe::stream()))), 0);
-  VV_CHECK(vv_gather_rows(bank_.gpu_data(), bank_rows_, feature_size_, di, nullptr, batch_size_, frames_, nullptr, nullptr, nullptr,
+  VV_CHECK(vv_gather_rows(bank_ptr_, bank_rows_, feature_size_, di, nullptr, batch_size_, frames_, nullptr, nullptr, nullptr,
                           VV_PREC_FP32_SIMT, (*top)[0]->mutable_gpu_data(), Caffe::stream()));
   CHECK_EQ(int(cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(Caffe::stream()))), 0);   // idx_host_ is reused by the next call
 }

@@ -289,6 +289,63 @@ def synthetic_videos(V, S):
     return video_id, shot_off, shot_ids
 
 
+class RecordSet:
+    """The DB values the reference's data layers parse (VideoShots / TestVideoShotWindows protobuf records, in DB key
+    order) -> host feature bank [rows, K] + the sampler's tables (vv_record_set_*, include/vv_b200.h)."""
+
+    def __init__(self, kind="video_shots", include_positives=True, include_negatives=True):
+        self._lib = _lib.load()
+        k = {"video_shots": _lib.RECORD_VIDEO_SHOTS, "test_windows": _lib.RECORD_TEST_WINDOWS}[kind]
+        self._h = self._lib.vv_record_set_create(k, int(include_positives), int(include_negatives))
+        if not self._h:
+            raise VVError(_lib.last_error())
+
+    def add(self, value):
+        check(self._lib.vv_record_set_add(self._h, bytes(value), len(value)))
+
+    def load_file(self, path):
+        check(self._lib.vv_record_set_load_file(self._h, str(path).encode()))
+        return self
+
+    def info(self):
+        import ctypes as C
+        rec, rows, K, rpr = C.c_int64(), C.c_int64(), C.c_int32(), C.c_int32()
+        check(self._lib.vv_record_set_info(self._h, C.addressof(rec), C.addressof(rows), C.addressof(K), C.addressof(rpr)))
+        return dict(records=rec.value, rows=rows.value, feature_size=K.value, rows_per_record=rpr.value)
+
+    def tables(self):
+        i = self.info()
+        vid = np.empty(i["records"], np.int32); off = np.empty(i["records"] + 1, np.int32); ids = np.empty(i["rows"], np.int32)
+        check(self._lib.vv_record_set_tables(self._h, vid.ctypes.data, off.ctypes.data, ids.ctypes.data))
+        return vid, off, ids
+
+    def bank_host(self):
+        import ctypes as C
+        i = self.info()
+        p = self._lib.vv_record_set_bank(self._h)
+        if not p:
+            return np.empty((0, i["feature_size"]), np.float32)
+        a = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(i["rows"], i["feature_size"]))
+        return a.copy()
+
+    def bank_device(self, device="cuda"):
+        i = self.info()
+        bank = torch.empty((i["rows"], i["feature_size"]), dtype=torch.float32, device=device)
+        check(self._lib.vv_record_set_upload(self._h, bank.data_ptr(), _stream()))
+        return bank
+
+    def close(self):
+        if self._h:
+            self._lib.vv_record_set_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Sampler:
     """VideoSampledShotsDataLayer's sampler (all five context types) as an index stream (host, C++)."""
 

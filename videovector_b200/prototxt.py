@@ -5,9 +5,12 @@ feature bank because the LMDB reader is out of scope."""
 
 
 def train_net(B=128, C=5, Nn=10, K=4096, N=512, dropout=0.9, margin=2.0, norm="L2", videos=2048, shots=32, seed=1234,
-              max_buffer_size=5000, swap=50, max_same=6, name="med_embedding", test=None):
+              max_buffer_size=5000, swap=50, max_same=6, name="med_embedding", test=None, source=None,
+              context_type="WINDOW"):
     """test = dict(batch=673, frames=4, videos=.., shots=.., seed=.., id_to_class_file=.., exclude_same=True) adds the shipped
-    file's TEST-phase graph (data -> frame average -> shared fc7 -> test_norm -> retrieval_stats)."""
+    file's TEST-phase graph (data -> frame average -> shared fc7 -> test_norm -> retrieval_stats).  `source` (and
+    test["source"]): a record source in place of the synthetic bank -- an LMDB directory, a VVRS stream or an mdb_dump text
+    file of VideoShots (TEST: TestVideoShotWindows) records."""
     L = []
 
     def layer(s, both_phases=False):
@@ -20,9 +23,10 @@ def train_net(B=128, C=5, Nn=10, K=4096, N=512, dropout=0.9, margin=2.0, norm="L
     def tops(names, key="top"):
         return "".join('  %s: "%s"\n' % (key, n) for n in names)
     layer('  name: "shot_windows"\n  type: VIDEO_SAMPLED_SHOTS_DATA\n  top: "data"\n  video_sampled_shots_data_param {\n'
-          '    source: "synthetic://videos=%d&shots=%d&dim=%d&seed=%d"\n    backend: LMDB\n    batch_size: %d\n'
+          '    source: "%s"\n    backend: LMDB\n    batch_size: %d\n'
           '    num_negative_samples: %d\n    max_buffer_size: %d\n    negative_swap_percentage: %d\n    max_same_video_negs: %d\n'
-          '    context_type: WINDOW\n    context_size: %d\n  }\n' % (videos, shots, K, seed, B, Nn, max_buffer_size, swap, max_same, C))
+          '    context_type: %s\n    context_size: %d\n  }\n' % (source or "synthetic://videos=%d&shots=%d&dim=%d&seed=%d" % (videos, shots, K, seed),
+                                                                B, Nn, max_buffer_size, swap, max_same, context_type, C))
     layer('  name: "slice_input_data"\n  type: SLICE\n  bottom: "data"\n' + tops(raw) + '  slice_param {\n    slice_dim: 1\n  }\n')
     layer('  name: "batch_concat_input"\n  type: CONCAT\n  top: "batch_concat"\n' + tops(raw, "bottom") + '  concat_param {\n    concat_dim: 0\n  }\n')
     layer('  name: "flatten_input"\n  type: FLATTEN\n  bottom: "batch_concat"\n  top: "original_feature"\n')
@@ -63,8 +67,9 @@ def train_net(B=128, C=5, Nn=10, K=4096, N=512, dropout=0.9, margin=2.0, norm="L
         def tl(s):
             return "layers {\n" + s.rstrip() + "\n  include: { phase: TEST }\n}\n"
         head = (tl('  name: "shot_windows"\n  type: VIDEO_SHOT_WINDOW_TEST_DATA\n  top: "data"\n  top: "video_ids"\n  video_shot_window_test_data_param {\n'
-                   '    source: "synthetic://videos=%d&shots=%d&dim=%d&seed=%d&frames=%d"\n    backend: LMDB\n    batch_size: %d\n  }\n'
-                   % (test.get("videos", 128), test.get("shots", 16), K, test.get("seed", 4321), F, test.get("batch", 673))) +
+                   '    source: "%s"\n    backend: LMDB\n    batch_size: %d\n  }\n'
+                   % (test.get("source") or "synthetic://videos=%d&shots=%d&dim=%d&seed=%d&frames=%d" % (
+                       test.get("videos", 128), test.get("shots", 16), K, test.get("seed", 4321), F), test.get("batch", 673))) +
                 tl('  name: "slice_input_data"\n  type: SLICE\n  bottom: "data"\n' + tops(fr) + '  slice_param {\n    slice_dim: 1\n  }\n') +
                 tl('  name: "batch_concat_input_test"\n  type: CONCAT\n' + tops(fr, "bottom") + '  top: "concat_input_datums"\n  concat_param {\n    concat_dim: 0\n  }\n') +
                 tl('  name: "flatten_input"\n  type: FLATTEN\n  bottom: "concat_input_datums"\n  top: "concat_input_datums_flat"\n') +
