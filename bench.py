@@ -291,32 +291,19 @@ def run_gpu(args):
         di = [torch.empty((B, R), dtype=torch.int32, device="cuda") for _ in range(nbuf)]
         dq = [torch.empty((B, R), dtype=torch.int32, device="cuda") for _ in range(nbuf)]
         loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
-        ready = [threading.Semaphore(0) for _ in range(nbuf)]
-        free = [threading.Semaphore(1) for _ in range(nbuf)]
         e2e_steps = args.steps
-
-        def producer():
-            for i in range(args.warmup + e2e_steps):
-                k = i % nbuf
-                free[k].acquire()
-                smp.next_into(hi[k].numpy(), hq[k].numpy())
-                ready[k].release()
-        th = threading.Thread(target=producer, daemon=True); th.start()
+        smp.prefetch(nbuf)        # native prefetch thread (vv_sampler_prefetch), the reference's InternalThread
         evs = [torch.cuda.Event() for _ in range(nbuf)]
 
         def e2e_step(i):
             k = i % nbuf
-            ready[k].acquire()
+            if i >= nbuf:
+                evs[k].synchronize()          # the H2D copy that last read this pinned buffer (nbuf steps ago) is done
+            smp.next_into(hi[k].numpy(), hq[k].numpy())
             di[k].copy_(hi[k], non_blocking=True); dq[k].copy_(hq[k], non_blocking=True)
             evs[k].record(stream)
             tr.step(bank, di[k], dq[k], None, it=2 * total + i)
             loss_host.copy_(tr.tensor("db_raw_ext")[N:N + 2], non_blocking=True)      # loss + violations, 8 bytes D2H
-            # a pinned index buffer may be refilled once its H2D copy has completed: release the previous
-            # step's buffer (its copy is long done) so the host never stalls on the step it just launched
-            if i > 0:
-                kp = (i - 1) % nbuf
-                evs[kp].synchronize()
-                free[kp].release()
         for i in range(args.warmup):
             e2e_step(i)
         stream.synchronize()
@@ -327,7 +314,7 @@ def run_gpu(args):
             e2e_step(i)
         stream.synchronize()
         t1 = time.perf_counter()
-        th.join(timeout=10)
+        smp.prefetch(0)
         e2e_ms = 1e3 * (t1 - t0)
         # one sampler over the timed `value` region, the per-kernel timing steps and the timed e2e region (all the same
         # workload): a 100 ms poll would see nothing of a short --steps run otherwise; idle samples are filtered by power

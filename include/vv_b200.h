@@ -377,6 +377,10 @@ void vv_sampler_destroy(vv_sampler_t* s);
 /* idx, quirk: host [B,R] int32 (see vv_gather_rows).  Returns 0 or <0. */
 int vv_sampler_next(vv_sampler_t* s, int32_t* idx, int32_t* quirk);
 int vv_sampler_cursor(const vv_sampler_t* s);
+/* Prefetch thread, the reference's BasePrefetchingDataLayer/InternalThread (base_data_layer.cpp:53-95): a producer
+ * thread draws up to `depth` batches ahead, vv_sampler_next hands them out in order (same stream as without it).
+ * depth <= 0 stops the thread; batches already drawn are still served first. */
+int vv_sampler_prefetch(vv_sampler_t* s, int depth);
 /* the generator alone, for tests against libc rand() */
 typedef struct vv_glibc_rand vv_glibc_rand_t;
 vv_glibc_rand_t* vv_glibc_rand_create(unsigned int seed);

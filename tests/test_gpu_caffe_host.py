@@ -378,9 +378,8 @@ def test_test_net_reads_test_window_records(tmp_path):
     src = records_util.write_vvrs(tmp_path / "test.vvrs", records_util.test_window_records(data, vids))
     idfile = tmp_path / "id_to_class.txt"; idfile.write_text("".join("%d,%d\n" % (v, v % 3) for v in range(12)))
     caffe_host.set_device(0); caffe_host.set_precision("f16x3")
-    caffe_host.set_phase("TEST")
     try:
-        tnet = caffe_host.Net(prototxt.train_net(test=dict(batch=TB, frames=F, source=src, id_to_class_file=str(idfile)), **CFG))
+        tnet = caffe_host.Net(prototxt.train_net(test=dict(batch=TB, frames=F, source=src, id_to_class_file=str(idfile)), **CFG), phase="TEST")
         for it in range(4):                            # 64 items over 37 records: wraps once
             tnet.forward()
             want = (np.arange(TB) + it * TB) % n

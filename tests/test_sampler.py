@@ -210,3 +210,29 @@ def test_live_reference_data_layer(vvlib, oracle, mode, C):
         idx, quirk = psmp.next()
         assert np.array_equal(_blob_from_indices(feat, idx, quirk), blob), "batch %d" % i
     psmp.close()
+
+
+def test_prefetch_thread_serves_the_same_stream(vvlib):
+    """vv_sampler_prefetch (the reference's prefetch thread, base_data_layer.cpp:53-95): same index stream, same cursor per
+    batch, stop/restart in the middle loses nothing, destroy with a full ring does not hang."""
+    rng = np.random.RandomState(21)
+    video_id, shot_off, shot_ids, _ = make_dataset(rng, 120, 2, 30, K=2)
+    args = (video_id, shot_off, shot_ids, 32, 5, 10, 80, 50, 6, 100)
+    plain = ops.Sampler(*args, rand_seed=1)
+    want = []
+    for _ in range(40):
+        i, q = plain.next(); want.append((i, q, plain.cursor))
+    plain.close()
+    pf = ops.Sampler(*args, rand_seed=1)
+    pf.prefetch(4)
+    for k in range(40):
+        if k == 13:
+            pf.prefetch(0)          # stop: the batches drawn ahead are served first, then inline generation continues
+        if k == 22:
+            pf.prefetch(3)
+        i, q = pf.next()
+        assert np.array_equal(i, want[k][0]) and np.array_equal(q, want[k][1]), k
+        assert pf.cursor == want[k][2], k
+    pf.close()                      # ring full, producer blocked
+    with pytest.raises(Exception):
+        ops.Sampler(*args, rand_seed=1).prefetch(5000)

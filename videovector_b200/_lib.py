@@ -122,6 +122,7 @@ SIGNATURES = {
     "vv_sampler_destroy": (None, [_P]),
     "vv_sampler_next": (_i, [_P, _P, _P]),
     "vv_sampler_cursor": (_i, [_P]),
+    "vv_sampler_prefetch": (_i, [_P, _i]),
     "vv_glibc_rand_create": (_P, [C.c_uint]),
     "vv_glibc_rand_next": (_i, [_P]),
     "vv_glibc_rand_destroy": (None, [_P]),

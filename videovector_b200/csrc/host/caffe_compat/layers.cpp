@@ -490,6 +490,7 @@ void VideoSampledShotsDataLayer<Dtype>::LayerSetUp(const vector<Blob<Dtype>*>& b
                                   p.max_buffer_size(), p.negative_swap_percentage(), p.max_same_video_negs(), 100,
                                   1 /* rand() is never seeded */, int(p.context_type()));
   CHECK(sampler_) << "Could not add requested number of negatives (or an invalid context_size for this context_type)";
+  VV_CHECK(vv_sampler_prefetch(sampler_, 3));      // BasePrefetchingDataLayer: the next batches are drawn on a thread
   const int R = context_size_ + num_negative_samples_;
   (*top)[0]->Reshape(batch_size_, R, feature_size_, 1);     // channels = slots, height = feature (ref: :215-220)
   if (top->size() > 1) (*top)[1]->Reshape(batch_size_, 1, 1, 1);

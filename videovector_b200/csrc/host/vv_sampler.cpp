@@ -16,9 +16,12 @@
 // seed (tests/test_sampler.py compares it against libc), so ranks and threads are
 // independent of global state.
 #include <algorithm>
+#include <condition_variable>
 #include <cstdint>
 #include <cstring>
+#include <mutex>
 #include <numeric>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 #include "vv_b200.h"
@@ -123,6 +126,78 @@ struct vv_sampler {
   FastMod fm;
   std::vector<int> ids, js;
   vv_sampler(unsigned seed, int max_d, int pct) : rng(seed, pct), cursor(0), fm(max_d) {}
+  ~vv_sampler() { stop_prefetch(); }
+
+  // Prefetch thread (the reference's BasePrefetchingDataLayer / InternalThread, base_data_layer.cpp:53-95): one producer
+  // draws batches in stream order into a ring of `depth` slots, vv_sampler_next pops them.  The index stream is the
+  // same with or without it (a single thread owns the sampler state either way).
+  struct Ring {
+    std::thread th;
+    std::mutex m;
+    std::condition_variable cv;
+    std::vector<std::vector<int32_t>> idx, quirk;
+    std::vector<int> cur;
+    int depth = 0, head = 0, count = 0, status = 0;
+    bool stop = false, running = false;
+  };
+  Ring* ring = nullptr;
+  int served_cursor = -1;
+  void stop_prefetch() {
+    if (!ring) return;
+    if (ring->running) {
+      { std::lock_guard<std::mutex> l(ring->m); ring->stop = true; }
+      ring->cv.notify_all();
+      ring->th.join();
+      ring->running = false;
+    }
+  }
+  int start_prefetch(int depth) {
+    if (depth <= 0) { stop_prefetch(); return 0; }          // batches already drawn stay queued and are served first
+    if (ring && ring->running) return 0;
+    if (ring && ring->count > 0) return VV_ERR_INVALID;      // restart only once the old queue has been drained
+    delete ring;
+    ring = new Ring;
+    const size_t n = size_t(B) * (C + Nn);
+    ring->depth = depth; ring->idx.assign(depth, std::vector<int32_t>(n)); ring->quirk.assign(depth, std::vector<int32_t>(n));
+    ring->cur.assign(depth, 0);
+    ring->running = true;
+    ring->th = std::thread([this] {
+      Ring* r = ring;
+      for (;;) {
+        int slot;
+        {
+          std::unique_lock<std::mutex> l(r->m);
+          r->cv.wait(l, [r] { return r->stop || r->count < r->depth; });
+          if (r->stop) return;
+          slot = (r->head + r->count) % r->depth;
+        }
+        const int rc = next(r->idx[slot].data(), r->quirk[slot].data());
+        {
+          std::lock_guard<std::mutex> l(r->m);
+          r->cur[slot] = cursor;
+          if (rc != 0) { r->status = rc; r->stop = true; } else ++r->count;
+        }
+        r->cv.notify_all();
+        if (rc != 0) return;
+      }
+    });
+    return 0;
+  }
+  int pop(int32_t* idx, int32_t* quirk) {
+    Ring* r = ring;
+    {
+      std::unique_lock<std::mutex> l(r->m);
+      r->cv.wait(l, [r] { return r->count > 0 || r->stop || !r->running; });
+      if (r->count == 0) return r->status ? r->status : VV_ERR_INVALID;
+    }
+    const size_t bytes = r->idx[r->head].size() * sizeof(int32_t);   // slot `head` belongs to the consumer until count drops
+    std::memcpy(idx, r->idx[r->head].data(), bytes);
+    std::memcpy(quirk, r->quirk[r->head].data(), bytes);
+    served_cursor = r->cur[r->head];
+    { std::lock_guard<std::mutex> l(r->m); r->head = (r->head + 1) % r->depth; --r->count; }
+    r->cv.notify_all();
+    return 0;
+  }
 
   // random_unique over a range (rng.hpp:43-54) from `count` reserved draws d[0..count):
   // for k < count: swap(a[k], a[k + draw_k % (n - k)]).  The targets are computed first and the swaps done in a
@@ -327,12 +402,21 @@ extern "C" vv_sampler_t* vv_sampler_create_ex(int num_videos, const int32_t* vid
   if (s->P > 0 && !s->init(max_tries_for_negs)) { delete s; return nullptr; }
   return s;
 }
-extern "C" void vv_sampler_destroy(vv_sampler_t* s) { delete s; }
+extern "C" void vv_sampler_destroy(vv_sampler_t* s) { if (s) { s->stop_prefetch(); delete s->ring; s->ring = nullptr; } delete s; }
 extern "C" int vv_sampler_next(vv_sampler_t* s, int32_t* idx, int32_t* quirk) {
   if (!s || !idx || !quirk) return VV_ERR_INVALID;
+  if (s->ring && (s->ring->running || s->ring->count > 0)) return s->pop(idx, quirk);
+  s->served_cursor = -1;
   return s->next(idx, quirk);
 }
-extern "C" int vv_sampler_cursor(const vv_sampler_t* s) { return s ? s->cursor : -1; }
+extern "C" int vv_sampler_prefetch(vv_sampler_t* s, int depth) {
+  if (!s || depth > 1024) return VV_ERR_INVALID;
+  return s->start_prefetch(depth);
+}
+extern "C" int vv_sampler_cursor(const vv_sampler_t* s) {
+  if (!s) return -1;
+  return s->ring && s->served_cursor >= 0 ? s->served_cursor : s->cursor;     // the cursor as of the last batch handed out
+}
 
 extern "C" vv_glibc_rand_t* vv_glibc_rand_create(unsigned int seed) { return new vv_glibc_rand(seed); }
 extern "C" int vv_glibc_rand_next(vv_glibc_rand_t* g) { return g->next(); }

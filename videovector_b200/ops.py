@@ -374,6 +374,10 @@ class Sampler:
     def next_into(self, idx, quirk):
         check(self._lib.vv_sampler_next(self._h, idx.ctypes.data, quirk.ctypes.data))
 
+    def prefetch(self, depth):
+        """Start (depth > 0) / stop the native prefetch thread; next() then pops batches drawn ahead, same stream."""
+        check(self._lib.vv_sampler_prefetch(self._h, int(depth)))
+
     @property
     def cursor(self):
         return self._lib.vv_sampler_cursor(self._h)
