@@ -293,16 +293,22 @@ def run_gpu(args):
         loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
         e2e_steps = args.steps
         smp.prefetch(nbuf)        # native prefetch thread (vv_sampler_prefetch), the reference's InternalThread
-        evs = [torch.cuda.Event() for _ in range(nbuf)]
+        evs = [torch.cuda.Event() for _ in range(nbuf)]         # H2D of buffer k complete
+        used = [torch.cuda.Event() for _ in range(nbuf)]        # the step that read device buffer k complete
+        cstream = torch.cuda.Stream()                           # copy stream: step i+1's indices arrive under step i
 
         def e2e_step(i):
             k = i % nbuf
             if i >= nbuf:
                 evs[k].synchronize()          # the H2D copy that last read this pinned buffer (nbuf steps ago) is done
+                cstream.wait_event(used[k])   # ... and the step that consumed device buffer k has finished with it
             smp.next_into(hi[k].numpy(), hq[k].numpy())
-            di[k].copy_(hi[k], non_blocking=True); dq[k].copy_(hq[k], non_blocking=True)
-            evs[k].record(stream)
+            with torch.cuda.stream(cstream):
+                di[k].copy_(hi[k], non_blocking=True); dq[k].copy_(hq[k], non_blocking=True)
+                evs[k].record(cstream)
+            stream.wait_event(evs[k])
             tr.step(bank, di[k], dq[k], None, it=2 * total + i)
+            used[k].record(stream)
             loss_host.copy_(tr.tensor("db_raw_ext")[N:N + 2], non_blocking=True)      # loss + violations, 8 bytes D2H
         for i in range(args.warmup):
             e2e_step(i)
