@@ -565,6 +565,224 @@ rank_fused_kernel(const float* __restrict__ H, const RankDev p, const float gsca
   }
 }
 
+// ---- K2+K3 with the rows staged in shared memory by bulk async copies -----------------------------------------
+// Same math, reduction trees and outputs as rank_fused_kernel (bit-identical results), different data movement: a
+// producer warp streams whole items (R rows x N floats, one cp.async.bulk per row, mbarrier complete_tx) into a ring
+// of `stages` shared-memory slots while the consumer warps work on earlier items, so row loads stay in flight through
+// the reductions / scalar chain / stores of the current item (the register-resident kernel has no loads in flight
+// during those phases and runs latency-bound at ~45 % of HBM peak).  Rows are read from shared memory twice (scores,
+// then gradients) instead of living in 60+ registers.  blockDim = T consumer threads + one producer warp.
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ void bulk_load_row(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void consumer_sync(int nthreads) { asm volatile("bar.sync 1, %0;" :: "r"(nthreads) : "memory"); }
+#endif
+
+template <int RMAX, int CT, int NNT, int OUT>
+__global__ void __launch_bounds__(288)
+rank_ring_kernel(const float* __restrict__ H, const RankDev p, const float gscale, const int act_fused,
+                 const float dscale, const BwdOut out, float* __restrict__ db_accum,
+                 const float* __restrict__ delta, float* __restrict__ dq_accum,
+                 float* __restrict__ stats, float* __restrict__ tscore, float* __restrict__ nscore,
+                 float* __restrict__ item_loss, float* __restrict__ item_viol, const int stages) {
+#if defined(__CUDA_ARCH__)      // the mbarrier / bulk-copy helpers exist in the device pass only
+  extern __shared__ __align__(128) float sm[];
+  const int T = blockDim.x - 32, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = T >> 5;
+  const int Cc = CT > 0 ? CT : p.C, Nn = NNT > 0 ? NNT : p.Nn;
+  const int J = 1 + Nn, R = Cc + Nn;
+  const int per = (2 * J + 1) * nw + 4 * J + 2;        // floats per scalar buffer (double buffered by item parity)
+  const size_t slot = size_t(R) * p.N;                  // floats per ring slot
+  float* rows = sm;
+  float* scal = rows + size_t(stages) * slot;
+  uint64_t* full = reinterpret_cast<uint64_t*>(scal + 2 * per + ((2 * per) & 1));
+  uint64_t* empty = full + stages;
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], nw); }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (warp == nw) {                                     // ---- producer warp
+    if (lane == 0) {
+      const uint32_t row_bytes = uint32_t(p.N) * 4u;
+      int k = 0;
+      for (int b = blockIdx.x; b < p.B; b += gridDim.x, ++k) {
+        const int s = k % stages;
+        if (k >= stages) mbar_wait(&empty[s], uint32_t((k / stages - 1) & 1));
+        mbar_arrive_expect_tx(&full[s], row_bytes * uint32_t(R));
+        float* dst = rows + size_t(s) * slot;
+        for (int r = 0; r < R; ++r) bulk_load_row(dst + size_t(r) * p.N, H + (size_t(r) * p.B + b) * p.N, row_bytes, &full[s]);
+      }
+    }
+    return;
+  }
+  const bool col_ok = tid < p.N4;
+  float4 dbacc = make_float4(0.f, 0.f, 0.f, 0.f), dqacc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float oscale = (out.prec == VV_PREC_F16X3) ? f16_hdr(out.hi)->scale : 1.f;
+  float amax = 0.f;
+  int parity = 0, k = 0;
+  for (int b = blockIdx.x; b < p.B; b += gridDim.x, parity ^= 1, ++k) {
+    float* part = scal + parity * per;                 // [2J+1][nw]: (s_x, p_x) per branch, then s_c
+    float* cA = part + (2 * J + 1) * nw;
+    float* cB = cA + J;
+    float* cE = cB + J;
+    float* cD = cE + J;
+    float* sc = cD + J;
+    const int s = k % stages;
+    const float4* xs = reinterpret_cast<const float4*>(rows + size_t(s) * slot) + tid;     // row r: xs[r * N4]
+    mbar_wait(&full[s], uint32_t((k / stages) & 1));
+#define VV_X(r) (col_ok ? xs[size_t(r) * p.N4] : make_float4(0.f, 0.f, 0.f, 0.f))
+    // ---- context mean, bottom order (eltwise_layer.cpp:67-73)
+    float4 cbar = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int r = 1; r < RMAX; ++r) {
+      if (r < Cc) {
+        const float a = p.coeff[r - 1];
+        const float4 xv = VV_X(r);
+        cbar.x = fmaf(a, xv.x, cbar.x); cbar.y = fmaf(a, xv.y, cbar.y);
+        cbar.z = fmaf(a, xv.z, cbar.z); cbar.w = fmaf(a, xv.w, cbar.w);
+      }
+    }
+    if (NNT > 0) {
+      constexpr int NV = 2 * (NNT > 0 ? 1 + NNT : 1) + 1;
+      float v[NV];
+#pragma unroll
+      for (int r = 0; r < RMAX; ++r) {
+        if (r < R && (r == 0 || r >= Cc)) {
+          const int j = (r == 0) ? 0 : r - Cc + 1;
+          const float4 xv = VV_X(r);
+          v[2 * j] = dot4(xv, xv); v[2 * j + 1] = dot4(cbar, xv);
+        }
+      }
+      v[NV - 1] = dot4(cbar, cbar);
+      int e; bool ok;
+      warp_multi_sum<NV>(v, lane, e, ok);
+      if (ok) part[e * nw + warp] = v[0];
+    } else {
+      {
+        float ssum = warp_sum(dot4(cbar, cbar));
+        if (lane == 0) part[2 * J * nw + warp] = ssum;
+      }
+#pragma unroll
+      for (int r = 0; r < RMAX; ++r) {
+        if (r < R && (r == 0 || r >= Cc)) {             // uniform branch
+          const int j = (r == 0) ? 0 : r - Cc + 1;
+          const float4 xv = VV_X(r);
+          float sx = warp_sum(dot4(xv, xv)), px = warp_sum(dot4(cbar, xv));
+          if (lane == 0) { part[(j * 2 + 0) * nw + warp] = sx; part[(j * 2 + 1) * nw + warp] = px; }
+        }
+      }
+    }
+    consumer_sync(T);
+    // ---- per-item scalars on warp 0, lane j = branch j (identical to rank_fused_kernel)
+    if (warp == 0) {
+      float s_c = 0.f;
+      for (int w = 0; w < nw; ++w) s_c += part[2 * J * nw + w];
+      float sj = 0.f, pj = 0.f;
+      if (lane < J) {
+        for (int w = 0; w < nw; ++w) sj += part[(lane * 2 + 0) * nw + w];
+        for (int w = 0; w < nw; ++w) pj += part[(lane * 2 + 1) * nw + w];
+      }
+      if (stats) {
+        float* st = stats + size_t(b) * p.stride;
+        if (lane == 0) st[0] = s_c;
+        if (lane < J) { st[1 + 2 * lane] = sj; st[2 + 2 * lane] = pj; }
+      }
+      const float nc = sqrtf(s_c) + p.eps;
+      const float nj = sqrtf(sj) + p.eps;
+      const float score = pj / (nc * nj);
+      const float score_t = __shfl_sync(0xffffffffu, score, 0);
+      const float dlt = score_t - score;
+      const float h = fmaxf(0.f, p.margin - dlt);
+      const bool neg = lane >= 1 && lane < J;
+      float w = neg ? ((p.norm == 2) ? h * gscale : (h > 0.f ? gscale : 0.f)) : 0.f;
+      const float vterm = (neg && dlt < 0.f) ? 1.f : 0.f;
+      const float loss = warp_sum(neg ? ((p.norm == 2) ? h * h : fabsf(h)) : 0.f);
+      const float viol = warp_sum(vterm);
+      const float g = warp_sum(w);
+      if (lane == 0) w = -g;
+      if (neg) {
+        if (tscore) tscore[size_t(b) * Nn + lane - 1] = score_t;
+        if (nscore) nscore[size_t(b) * Nn + lane - 1] = score;
+      }
+      if (lane == 0) { if (item_loss) item_loss[b] = loss; if (item_viol) item_viol[b] = viol; }
+      const float q = powf(sj, 1.5f) + p.eps;
+      const float aj = w * pj / nc;
+      const float e = w / nj;
+      if (lane < J) {
+        cA[lane] = sj * w / (nc * q); cB[lane] = -aj / q; cE[lane] = e;
+        cD[lane] = delta ? delta[size_t(lane == 0 ? 0 : Cc + lane - 1) * p.B + b] : 0.f;
+      }
+      const float ac = warp_sum(lane < J ? e * pj : 0.f);
+      if (lane == 0) { const float qc = powf(s_c, 1.5f) + p.eps; sc[0] = s_c / qc; sc[1] = -ac / qc; }
+    }
+    consumer_sync(T);
+    // ---- target + negative rows: dx = cA*cbar + cB*x ; D += cE*x
+    float4 D = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < RMAX; ++r) {
+      if (r < R && (r == 0 || r >= Cc)) {
+        const int j = (r == 0) ? 0 : r - Cc + 1;
+        const float a = cA[j], bb = cB[j], e = cE[j];
+        if (col_ok) {
+          const float4 xv = xs[size_t(r) * p.N4];
+          float4 o;
+          o.x = fmaf(a, cbar.x, bb * xv.x); o.y = fmaf(a, cbar.y, bb * xv.y);
+          o.z = fmaf(a, cbar.z, bb * xv.z); o.w = fmaf(a, cbar.w, bb * xv.w);
+          D.x = fmaf(e, xv.x, D.x); D.y = fmaf(e, xv.y, D.y); D.z = fmaf(e, xv.z, D.z); D.w = fmaf(e, xv.w, D.w);
+          if (act_fused) {
+            o.x = xv.x > 0.f ? o.x * dscale : 0.f; o.y = xv.y > 0.f ? o.y * dscale : 0.f;
+            o.z = xv.z > 0.f ? o.z * dscale : 0.f; o.w = xv.w > 0.f ? o.w * dscale : 0.f;
+          }
+          dbacc.x += o.x; dbacc.y += o.y; dbacc.z += o.z; dbacc.w += o.w;
+          const float dl = cD[j];
+          if (dl != 0.f) {
+            dqacc.x = fmaf(dl, o.x, dqacc.x); dqacc.y = fmaf(dl, o.y, dqacc.y);
+            dqacc.z = fmaf(dl, o.z, dqacc.z); dqacc.w = fmaf(dl, o.w, dqacc.w);
+          }
+          store_row4_t<OUT>(out, (size_t(r) * p.B + b) * p.N + tid * 4, o, oscale, amax);
+        }
+      }
+    }
+    // ---- context rows: d cbar = (s_c * d c^ - cbar * a_c) / q_c ; d c_i = coeff_i * d cbar
+    const float Fs = sc[0], Fc = sc[1];
+    float4 dcb;
+    dcb.x = fmaf(Fs, D.x, Fc * cbar.x); dcb.y = fmaf(Fs, D.y, Fc * cbar.y);
+    dcb.z = fmaf(Fs, D.z, Fc * cbar.z); dcb.w = fmaf(Fs, D.w, Fc * cbar.w);
+#pragma unroll
+    for (int r = 1; r < RMAX; ++r) {
+      if (r < Cc && col_ok) {
+        const float a = p.coeff[r - 1];
+        float4 o = make_float4(a * dcb.x, a * dcb.y, a * dcb.z, a * dcb.w);
+        if (act_fused) {
+          const float4 xv = xs[size_t(r) * p.N4];
+          o.x = xv.x > 0.f ? o.x * dscale : 0.f; o.y = xv.y > 0.f ? o.y * dscale : 0.f;
+          o.z = xv.z > 0.f ? o.z * dscale : 0.f; o.w = xv.w > 0.f ? o.w * dscale : 0.f;
+        }
+        dbacc.x += o.x; dbacc.y += o.y; dbacc.z += o.z; dbacc.w += o.w;
+        store_row4_t<OUT>(out, (size_t(r) * p.B + b) * p.N + tid * 4, o, oscale, amax);
+      }
+    }
+#undef VV_X
+    // this warp is done with the slot: hand it back to the producer
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+  }
+  if (out.prec == VV_PREC_F16X3) f16_publish_absmax(out.hi, amax);
+  if (col_ok) {
+    if (db_accum) {
+      atomicAdd(db_accum + tid * 4 + 0, dbacc.x); atomicAdd(db_accum + tid * 4 + 1, dbacc.y);
+      atomicAdd(db_accum + tid * 4 + 2, dbacc.z); atomicAdd(db_accum + tid * 4 + 3, dbacc.w);
+    }
+    if (dq_accum) {
+      atomicAdd(dq_accum + tid * 4 + 0, dqacc.x); atomicAdd(dq_accum + tid * 4 + 1, dqacc.y);
+      atomicAdd(dq_accum + tid * 4 + 2, dqacc.z); atomicAdd(dq_accum + tid * 4 + 3, dqacc.w);
+    }
+  }
+#endif
+}
+
 int make_dev(const vv_rank_cfg_t* cfg, RankDev* d, int* threads) {
   VV_REQUIRE(cfg, "rank cfg is NULL");
   VV_REQUIRE(cfg->B > 0 && cfg->C >= 2 && cfg->Nn >= 1 && cfg->N > 0, "bad rank cfg B=%d C=%d Nn=%d N=%d", cfg->B, cfg->C, cfg->Nn, cfg->N);
@@ -689,16 +907,50 @@ extern "C" int vv_rank_loss_fused(const float* H, const vv_rank_cfg_t* cfg, floa
   const int grid = d.B < num_sms() * per_sm ? d.B : num_sms() * per_sm;
   const int mode = (o.dZ ? 1 : 0) | (o.prec == VV_PREC_TF32X3 ? 2 : 0) | (o.prec == VV_PREC_BF16 ? 4 : 0) |
                    (o.prec == VV_PREC_F16X3 ? 8 : 0);
+  // ring variant (rows staged in shared memory by a producer warp): whenever two slots of R rows fit
+  const char* ring_e = getenv("VV_RANK_RING");                      // 0 = register-resident kernel, n >= 2 = ring stages
+  const int ring_env = ring_e ? atoi(ring_e) : -1;
+  const size_t slot_bytes = size_t(R) * d.N * sizeof(float);
+  const size_t scal_bytes = sizeof(float) * (2 * ((2 * J + 1) * nw + 4 * J + 2) + 1);
+  int stages = ring_env >= 0 ? ring_env : 0;     // experimental: off unless VV_RANK_RING names the stage count
+  while (stages >= 2 && stages * slot_bytes + scal_bytes + 16 * stages > 200 * 1024) --stages;
+  const bool ring = stages >= 2 && d.N % 4 == 0 && (d.N * 4) % 16 == 0 && T == d.N4 && R <= 32;
+  if (ring) {
+    const size_t rsmem = stages * slot_bytes + scal_bytes + 16 * stages;
+    int rper_sm = int((224 * 1024) / (rsmem + 1024));
+    if (rper_sm > 2048 / (T + 32)) rper_sm = 2048 / (T + 32);
+    if (const char* e = getenv("VV_RANK_RING_PER_SM")) rper_sm = atoi(e) < rper_sm ? atoi(e) : rper_sm;
+    if (rper_sm < 1) rper_sm = 1;
+    const int rgrid = d.B < num_sms() * rper_sm ? d.B : num_sms() * rper_sm;
+#define VV_RANK_RING(RM, CT, NNT, OUT)                                                                                 \
+  do {                                                                                                                 \
+    static bool attr_set = false;                                                                                      \
+    if (!attr_set) {                                                                                                   \
+      VV_CUDA(cudaFuncSetAttribute(rank_ring_kernel<RM, CT, NNT, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024)); \
+      attr_set = true;                                                                                                 \
+    }                                                                                                                  \
+    rank_ring_kernel<RM, CT, NNT, OUT><<<rgrid, T + 32, rsmem, stream>>>(H, d, gscale, act_fused, dropout_scale, o, db_accum, \
+        delta, dq_accum, stats, target_score, neg_score, item_loss, item_viol, stages);                                \
+  } while (0)
+    if (d.C == 5 && d.Nn == 10 && mode == 2) VV_RANK_RING(16, 5, 10, 2);
+    else if (d.C == 5 && d.Nn == 10 && mode == 4) VV_RANK_RING(16, 5, 10, 4);
+    else if (d.C == 5 && d.Nn == 10 && mode == 8) VV_RANK_RING(16, 5, 10, 8);
+    else if (d.C == 5 && d.Nn == 10 && mode == 1) VV_RANK_RING(16, 5, 10, 1);
+    else if (R <= 16) VV_RANK_RING(16, 0, 0, -1);
+    else VV_RANK_RING(32, 0, 0, -1);
+#undef VV_RANK_RING
+  } else {
 #define VV_RANK_FUSED(RM, CT, NNT, OUT)                                                                              \
-  rank_fused_kernel<RM, CT, NNT, OUT><<<grid, T, smem, stream>>>(H, d, gscale, act_fused, dropout_scale, o, db_accum, \
-      delta, dq_accum, stats, target_score, neg_score, item_loss, item_viol)
-  if (d.C == 5 && d.Nn == 10 && mode == 2) VV_RANK_FUSED(16, 5, 10, 2);        // the shipped net (C=5, Nn=10), training modes
-  else if (d.C == 5 && d.Nn == 10 && mode == 4) VV_RANK_FUSED(16, 5, 10, 4);
-  else if (d.C == 5 && d.Nn == 10 && mode == 8) VV_RANK_FUSED(16, 5, 10, 8);
-  else if (d.C == 5 && d.Nn == 10 && mode == 1) VV_RANK_FUSED(16, 5, 10, 1);
-  else if (R <= 16) VV_RANK_FUSED(16, 0, 0, -1);
-  else VV_RANK_FUSED(32, 0, 0, -1);
-#undef VV_RANK_FUSED
+    rank_fused_kernel<RM, CT, NNT, OUT><<<grid, T, smem, stream>>>(H, d, gscale, act_fused, dropout_scale, o, db_accum, \
+        delta, dq_accum, stats, target_score, neg_score, item_loss, item_viol)
+    if (d.C == 5 && d.Nn == 10 && mode == 2) VV_RANK_FUSED(16, 5, 10, 2);        // the shipped net (C=5, Nn=10), training modes
+    else if (d.C == 5 && d.Nn == 10 && mode == 4) VV_RANK_FUSED(16, 5, 10, 4);
+    else if (d.C == 5 && d.Nn == 10 && mode == 8) VV_RANK_FUSED(16, 5, 10, 8);
+    else if (d.C == 5 && d.Nn == 10 && mode == 1) VV_RANK_FUSED(16, 5, 10, 1);
+    else if (R <= 16) VV_RANK_FUSED(16, 0, 0, -1);
+    else VV_RANK_FUSED(32, 0, 0, -1);
+  #undef VV_RANK_FUSED
+  }
   VV_LAUNCH_CHECK();
   count_launch();
   if (loss || violations) {
