@@ -45,6 +45,9 @@ def run(tag, env):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 2:                       # one variant only (for ncu): bench_rank.py <stages> <per_sm>
+        ms, bw, _ = run("ring", {"VV_RANK_RING": sys.argv[1], "VV_RANK_RING_PER_SM": sys.argv[2]})
+        print("stages=%s per_sm=%s %.4f ms %.0f GB/s" % (sys.argv[1], sys.argv[2], ms, bw)); sys.exit(0)
     ms, bw, ref = run("reg", {"VV_RANK_RING": "0"})
     print("%-28s %.4f ms  %.0f GB/s" % ("register-resident", ms, bw), flush=True)
     for st in (2, 3, 4, 5, 6):
