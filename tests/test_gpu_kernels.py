@@ -299,9 +299,12 @@ def test_rank_loss_forward_backward(B, C, Nn, N, norm):
 @pytest.mark.parametrize("B,C,Nn,N,norm", [(64, 5, 10, 512, 2), (33, 3, 4, 64, 1), (7, 5, 10, 1000, 2), (300, 7, 20, 256, 2),
                                             (1, 5, 10, 512, 2)])
 @pytest.mark.parametrize("prec", ["fp32_simt", "tf32x3", "f16x3", "bf16"])
-def test_rank_loss_fused_equals_two_kernel_path(B, C, Nn, N, norm, prec):
-    """K2+K3 fused (rows in registers) against the forward + backward kernels: same formulas, reductions equal up to
-    FMA contraction / summation order (1e-6)."""
+@pytest.mark.parametrize("ring", ["0", "2", "3"])
+def test_rank_loss_fused_equals_two_kernel_path(B, C, Nn, N, norm, prec, ring, monkeypatch):
+    """K2+K3 fused (rows in registers; ring != 0: the variant that stages items in shared memory with bulk async copies,
+    VV_RANK_RING) against the forward + backward kernels: same formulas, reductions equal up to FMA contraction /
+    summation order (1e-6)."""
+    monkeypatch.setenv("VV_RANK_RING", ring)
     R = C + Nn
     g = torch.Generator(device="cuda").manual_seed(B + N)
     H = torch.relu(torch.randn(R * B, N, device="cuda", generator=g))

@@ -624,11 +624,6 @@ rank_ring_kernel(const float* __restrict__ H, const RankDev p, const float gscal
   int parity = 0, k = 0;
   for (int b = blockIdx.x; b < p.B; b += gridDim.x, parity ^= 1, ++k) {
     float* part = scal + parity * per;                 // [2J+1][nw]: (s_x, p_x) per branch, then s_c
-    float* cA = part + (2 * J + 1) * nw;
-    float* cB = cA + J;
-    float* cE = cB + J;
-    float* cD = cE + J;
-    float* sc = cD + J;
     const int s = k % stages;
     const float4* xs = reinterpret_cast<const float4*>(rows + size_t(s) * slot) + tid;     // row r: xs[r * N4]
     mbar_wait(&full[s], uint32_t((k / stages) & 1));
@@ -675,8 +670,11 @@ rank_ring_kernel(const float* __restrict__ H, const RankDev p, const float gscal
       }
     }
     consumer_sync(T);
-    // ---- per-item scalars on warp 0, lane j = branch j (identical to rank_fused_kernel)
-    if (warp == 0) {
+    // ---- per-item scalars, lane j = branch j (formulas of rank_fused_kernel).  Every warp evaluates the chain
+    // redundantly from the shared partial sums and keeps the coefficients in registers (broadcast by shuffle below):
+    // no second barrier, and no warp idles while one of them works through the sqrt / pow / divide chain.
+    float rA = 0.f, rB = 0.f, rE = 0.f, rD = 0.f, Fs, Fc;
+    {
       float s_c = 0.f;
       for (int w = 0; w < nw; ++w) s_c += part[2 * J * nw + w];
       float sj = 0.f, pj = 0.f;
@@ -684,7 +682,7 @@ rank_ring_kernel(const float* __restrict__ H, const RankDev p, const float gscal
         for (int w = 0; w < nw; ++w) sj += part[(lane * 2 + 0) * nw + w];
         for (int w = 0; w < nw; ++w) pj += part[(lane * 2 + 1) * nw + w];
       }
-      if (stats) {
+      if (stats && warp == 0) {
         float* st = stats + size_t(b) * p.stride;
         if (lane == 0) st[0] = s_c;
         if (lane < J) { st[1 + 2 * lane] = sj; st[2 + 2 * lane] = pj; }
@@ -702,29 +700,30 @@ rank_ring_kernel(const float* __restrict__ H, const RankDev p, const float gscal
       const float viol = warp_sum(vterm);
       const float g = warp_sum(w);
       if (lane == 0) w = -g;
-      if (neg) {
+      if (neg && warp == 0) {
         if (tscore) tscore[size_t(b) * Nn + lane - 1] = score_t;
         if (nscore) nscore[size_t(b) * Nn + lane - 1] = score;
       }
-      if (lane == 0) { if (item_loss) item_loss[b] = loss; if (item_viol) item_viol[b] = viol; }
+      if (lane == 0 && warp == 0) { if (item_loss) item_loss[b] = loss; if (item_viol) item_viol[b] = viol; }
       const float q = powf(sj, 1.5f) + p.eps;
       const float aj = w * pj / nc;
       const float e = w / nj;
       if (lane < J) {
-        cA[lane] = sj * w / (nc * q); cB[lane] = -aj / q; cE[lane] = e;
-        cD[lane] = delta ? delta[size_t(lane == 0 ? 0 : Cc + lane - 1) * p.B + b] : 0.f;
+        rA = sj * w / (nc * q); rB = -aj / q; rE = e;
+        rD = delta ? delta[size_t(lane == 0 ? 0 : Cc + lane - 1) * p.B + b] : 0.f;
       }
       const float ac = warp_sum(lane < J ? e * pj : 0.f);
-      if (lane == 0) { const float qc = powf(s_c, 1.5f) + p.eps; sc[0] = s_c / qc; sc[1] = -ac / qc; }
+      const float qc = powf(s_c, 1.5f) + p.eps;
+      Fs = s_c / qc; Fc = -ac / qc;
     }
-    consumer_sync(T);
     // ---- target + negative rows: dx = cA*cbar + cB*x ; D += cE*x
     float4 D = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int r = 0; r < RMAX; ++r) {
       if (r < R && (r == 0 || r >= Cc)) {
         const int j = (r == 0) ? 0 : r - Cc + 1;
-        const float a = cA[j], bb = cB[j], e = cE[j];
+        const float a = __shfl_sync(0xffffffffu, rA, j), bb = __shfl_sync(0xffffffffu, rB, j), e = __shfl_sync(0xffffffffu, rE, j);
+        const float dl = __shfl_sync(0xffffffffu, rD, j);
         if (col_ok) {
           const float4 xv = xs[size_t(r) * p.N4];
           float4 o;
@@ -736,7 +735,6 @@ rank_ring_kernel(const float* __restrict__ H, const RankDev p, const float gscal
             o.z = xv.z > 0.f ? o.z * dscale : 0.f; o.w = xv.w > 0.f ? o.w * dscale : 0.f;
           }
           dbacc.x += o.x; dbacc.y += o.y; dbacc.z += o.z; dbacc.w += o.w;
-          const float dl = cD[j];
           if (dl != 0.f) {
             dqacc.x = fmaf(dl, o.x, dqacc.x); dqacc.y = fmaf(dl, o.y, dqacc.y);
             dqacc.z = fmaf(dl, o.z, dqacc.z); dqacc.w = fmaf(dl, o.w, dqacc.w);
@@ -746,7 +744,6 @@ rank_ring_kernel(const float* __restrict__ H, const RankDev p, const float gscal
       }
     }
     // ---- context rows: d cbar = (s_c * d c^ - cbar * a_c) / q_c ; d c_i = coeff_i * d cbar
-    const float Fs = sc[0], Fc = sc[1];
     float4 dcb;
     dcb.x = fmaf(Fs, D.x, Fc * cbar.x); dcb.y = fmaf(Fs, D.y, Fc * cbar.y);
     dcb.z = fmaf(Fs, D.z, Fc * cbar.z); dcb.w = fmaf(Fs, D.w, Fc * cbar.w);
@@ -913,8 +910,8 @@ extern "C" int vv_rank_loss_fused(const float* H, const vv_rank_cfg_t* cfg, floa
   const size_t slot_bytes = size_t(R) * d.N * sizeof(float);
   const size_t scal_bytes = sizeof(float) * (2 * ((2 * J + 1) * nw + 4 * J + 2) + 1);
   int stages = ring_env >= 0 ? ring_env : 0;     // experimental: off unless VV_RANK_RING names the stage count
-  while (stages >= 2 && stages * slot_bytes + scal_bytes + 16 * stages > 200 * 1024) --stages;
-  const bool ring = stages >= 2 && d.N % 4 == 0 && (d.N * 4) % 16 == 0 && T == d.N4 && R <= 32;
+  while (stages >= 1 && stages * slot_bytes + scal_bytes + 16 * stages > 200 * 1024) --stages;
+  const bool ring = stages >= 1 && d.N % 4 == 0 && (d.N * 4) % 16 == 0 && T == d.N4 && R <= 32;
   if (ring) {
     const size_t rsmem = stages * slot_bytes + scal_bytes + 16 * stages;
     int rper_sm = int((224 * 1024) / (rsmem + 1024));
