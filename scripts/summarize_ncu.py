@@ -58,7 +58,7 @@ def launches(src, out, tag):
             name = r[ki].split("(")[0].replace("void ", "").replace("vv::<unnamed>::", "")[:90]
             f.write("%4d, %10.2f, %s\n" % (int(r[ii]), us, name))
             tot[name] = tot.get(name, 0) + us
-        f.write("\n# share of all captured launches (4 steps + setup)\n")
+        f.write("\n# share of all captured launches (steps + setup)\n")
         s = sum(tot.values())
         for k, v in sorted(tot.items(), key=lambda kv: -kv[1]):
             f.write("# %6.2f %%  %10.1f us  %s\n" % (100 * v / s, v, k))
@@ -72,6 +72,9 @@ if __name__ == "__main__":
         if os.path.exists(os.path.join(go, "launches_%s.csv" % p)):
             launches(os.path.join(go, "launches_%s.csv" % p), os.path.join(pr, "%s_launches_%s.txt" % (rnd, p)),
                      "launch list, `python scripts/profile_step.py --precision %s --steps 4` (B=4096, K=4096, N=512, C=5, Nn=10)" % p)
+    if os.path.exists(os.path.join(go, "launches_bench.csv")):
+        launches(os.path.join(go, "launches_bench.csv"), os.path.join(pr, "%s_launches_bench.txt" % rnd),
+                 "launch list of the bench command itself: `python bench.py --steps 2 --warmup 1 --no-cpu-baseline` (value leg, per-kernel leg, e2e leg)")
     tr = {}
     for key, rep in (("f16x3_gathered", "prof_gemm_f16x3"), ("bf16_gathered", "prof_gemm_bf16")):
         p = os.path.join(go, rep + ".ncu-rep")
@@ -84,6 +87,7 @@ if __name__ == "__main__":
                      ("prof_gemm_tf32x3", "fc7 forward + wgrad GEMMs, tf32x3"), ("prof_gemm_bf16", "fc7 forward + wgrad GEMMs, bf16, gather fused"),
                      ("prof_stream_f16x3", "streaming kernels (gather plan, fused rank loss, update), f16x3 step"),
                      ("prof_gather_f16x3", "K0 gather kernel (materialised path, --materialised), f16x3"),
+                     ("prof_rank_ring", "rank_ring_kernel (VV_RANK_RING=2, 3 CTAs/SM), timed alone on cold data: scripts/bench_rank.py 2 3"),
                      ("prof_stream_tf32x3", "streaming kernels (gather, rank loss, update), tf32x3 step")):
         p = os.path.join(go, rep + ".ncu-rep")
         if os.path.exists(p):
