@@ -135,7 +135,7 @@ struct vv_trainer {
     if ((rc = alloc_operand(W_hi, W_lo, NK, cfg.prec))) return rc;
     if ((rc = alloc_operand(dZ_hi, dZ_lo, MN, cfg.prec))) return rc;
     if (f32op || cfg.keep_blobs) { A(dZf, MN * 4); }
-    A(wlast, size_t(cfg.N) * 4); A(dq, size_t(cfg.N) * 4);
+    A(wlast, size_t(cfg.N) * 4);
     A(rowmap, size_t((M + 127) / 128 * 128) * 4); A(delta, size_t((M + 127) / 128 * 128) * 4);
     if (cfg.keep_blobs) { A(Zf, MN * 4); }
     A(H, MN * 4);
@@ -143,7 +143,10 @@ struct vv_trainer {
     A(item_loss, size_t(cfg.B) * 4); A(item_viol, size_t(cfg.B) * 4);
     nsplit = vv_ip_wgrad_auto_nsplit(M, cfg.N, cfg.K, cfg.prec);
     A(dW_parts, size_t(nsplit) * NK * 4);
-    A(dbx, size_t(cfg.N + 4) * 4);            // db [N] + loss + violations (+pad): one allreduce payload
+    // db [N] + loss + violations (one all-reduce payload) + the fused loss kernel's ticket counter + pad, then dq [N]
+    // (the K-1 quirk's column sums): one memset zeroes all accumulators of a step
+    A(dbx, size_t(2 * cfg.N + 4) * 4);
+    dq.p = dbx.as<float>() + cfg.N + 4; dq.bytes = size_t(cfg.N) * 4; dq.base = nullptr;
     if (cfg.compute_dgrad) { A(dX, MK * 4); }
 #undef A
     memset(&rank, 0, sizeof(rank));
@@ -304,13 +307,13 @@ extern "C" int vv_trainer_step(vv_trainer_t* t, const float* bank, int64_t bank_
     if (vv_rank_loss_fused_supported(&t->rank) && !c.split_rank_loss) {
       // K2 + K3 in one pass over H (+ bias gradient); timed as phase 3, phase 2 stays 0
       t->tic(3);
-      VV_CUDA(cudaMemsetAsync(t->dbx.p, 0, size_t(N) * 4, t->stream));
-      if (fused_gather) VV_CUDA(cudaMemsetAsync(t->dq.p, 0, size_t(N) * 4, t->stream));
+      VV_CUDA(cudaMemsetAsync(t->dbx.p, 0, size_t(2 * N + 4) * 4, t->stream));      // db, loss, viol, ticket, dq
       count_launch();
-      if ((rc = vv_rank_loss_fused(t->H.as<float>(), &t->rank, c.loss_weight, 1, dscale, t->stats.as<float>(), nullptr, nullptr,
-                                   t->item_loss.as<float>(), t->item_viol.as<float>(), t->loss_ptr(), t->viol_ptr(),
-                                   t->dZf.as<float>(), t->dZ_hi.p, t->dZ_lo.p, c.prec, t->dbx.as<float>(),
-                                   fused_gather ? t->delta.as<float>() : nullptr, fused_gather ? t->dq.as<float>() : nullptr, s))) return rc;
+      if ((rc = rank_loss_fused_counted(t->H.as<float>(), &t->rank, c.loss_weight, 1, dscale, t->stats.as<float>(), nullptr, nullptr,
+                                        t->item_loss.as<float>(), t->item_viol.as<float>(), t->loss_ptr(), t->viol_ptr(),
+                                        t->dZf.as<float>(), t->dZ_hi.p, t->dZ_lo.p, c.prec, t->dbx.as<float>(),
+                                        fused_gather ? t->delta.as<float>() : nullptr, fused_gather ? t->dq.as<float>() : nullptr,
+                                        reinterpret_cast<unsigned int*>(t->dbx.as<float>() + N + 2), s))) return rc;
     } else {
       // K2
       t->tic(2);
@@ -319,7 +322,7 @@ extern "C" int vv_trainer_step(vv_trainer_t* t, const float* bank, int64_t bank_
       t->toc(2);
       // K3 (+ bias gradient)
       t->tic(3);
-      VV_CUDA(cudaMemsetAsync(t->dbx.p, 0, size_t(N) * 4, t->stream));
+      VV_CUDA(cudaMemsetAsync(t->dbx.p, 0, size_t(N) * 4, t->stream));          // the forward kernel above wrote loss / viol
       if (fused_gather) VV_CUDA(cudaMemsetAsync(t->dq.p, 0, size_t(N) * 4, t->stream));
       count_launch();
       if ((rc = vv_rank_loss_backward_ex(t->H.as<float>(), &t->rank, t->stats.as<float>(), c.loss_weight, 1, dscale,
@@ -346,6 +349,7 @@ extern "C" int vv_trainer_step(vv_trainer_t* t, const float* bank, int64_t bank_
   static const int want_slices = [] { const char* e = getenv("VV_DP_SLICES"); return e ? atoi(e) : 1; }();
   const int nslices = (want_slices > 1 && want_slices <= 4 && c.world_size > 1 && fused_gather && t->comm &&
                        N % (256 * want_slices) == 0) ? want_slices : 1;
+  const bool fold_col = fused_gather && c.world_size == 1 && do_update;
   t->tic(4);
   if (fused_gather) {
     const double reg = double(c.regularization) / 2;
@@ -357,7 +361,9 @@ extern "C" int vv_trainer_step(vv_trainer_t* t, const float* bank, int64_t bank_
       float* slice = t->dW_parts.as<float>() + size_t(n0) * K;
       if ((rc = vv_ip_wgrad_gathered_part(t->opdZ(), t->opBank(), bank_rows, t->rowmap.as<int32_t>(), M, N, K, c.prec, c.regularization,
                                           t->dW_parts.as<float>(), t->nsplit, n0, cols, s))) return rc;
-      if ((rc = vv_add_column(slice, K, K - 1, t->dq.as<float>() + n0, cols, s))) return rc;
+      // the quirk's share of dW[:, K-1]: folded into the update kernel on a single GPU; a data-parallel rank (dq is
+      // rank-local and must be in before the all-reduce) and a no-update step add it here
+      if (!fold_col) { if ((rc = vv_add_column(slice, K, K - 1, t->dq.as<float>() + n0, cols, s))) return rc; }
       if (nslices > 1) {
         if (nparts > 1) { if ((rc = vv_reduce_parts(slice, nparts, NK, int64_t(cols) * K, slice, s))) return rc; }
         VV_CUDA(cudaEventRecord(t->ev_slice[sl], t->stream));
@@ -415,13 +421,17 @@ extern "C" int vv_trainer_step(vv_trainer_t* t, const float* bank, int64_t bank_
     if (rate < 0.f) return VV_ERR_INVALID;
     // F16X3: the new W operand copy is scaled from max|W| as the previous update (or the initial copy) recorded it
     if ((rc = vv_operand_rescale(t->W_hi.p, c.prec, 10, s))) return rc;
-    if ((rc = vv_sgd_update(t->W.as<float>(), t->dW_parts.as<float>(), nparts, NK, t->Wh.as<float>(),
-                            t->dW_parts.as<float>(), NK, rate * c.lr_mult[0], c.momentum, c.weight_decay * c.decay_mult[0],
-                            c.reg_type, gscale, t->W_hi.p, t->W_lo.p, c.prec, s))) return rc;
-    if ((rc = vv_copy_strided(t->W.as<float>() + (K - 1), K, t->wlast.as<float>(), 1, N, 1, s))) return rc;
-    if ((rc = vv_sgd_update(t->b.as<float>(), t->dbx.as<float>(), 1, 0, t->bh.as<float>(), t->dbx.as<float>(), N,
-                            rate * c.lr_mult[1], c.momentum, c.weight_decay * c.decay_mult[1], c.reg_type, gscale,
-                            nullptr, nullptr, VV_PREC_FP32_SIMT, s))) return rc;
+    // weight then bias (net.params() order), one launch: + the quirk column, + wlast = W[:, K-1] for the next plan
+    UpdateTail u;
+    u.W = t->W.as<float>(); u.parts = t->dW_parts.as<float>(); u.nparts = nparts; u.stride = NK; u.hist = t->Wh.as<float>();
+    u.diff_out = t->dW_parts.as<float>(); u.count = NK; u.K = K;
+    u.rate_w = rate * c.lr_mult[0]; u.decay_w = c.weight_decay * c.decay_mult[0];
+    u.col_add = fold_col ? t->dq.as<float>() : nullptr; u.col_out = t->wlast.as<float>();
+    u.Wop_hi = t->W_hi.p; u.Wop_lo = t->W_lo.p; u.prec = c.prec;
+    u.b = t->b.as<float>(); u.db = t->dbx.as<float>(); u.bh = t->bh.as<float>(); u.b_diff = t->dbx.as<float>(); u.nb = N;
+    u.rate_b = rate * c.lr_mult[1]; u.decay_b = c.weight_decay * c.decay_mult[1];
+    u.momentum = c.momentum; u.reg_type = c.reg_type; u.gscale = gscale;
+    if ((rc = sgd_update_tail(u, s))) return rc;
     if (c.world_size > 1) {
       // loss/violations were summed over ranks: loss -> mean over ranks (global-batch mean)
       if ((rc = vv_axpby(1, gscale, t->loss_ptr(), 0.f, t->loss_ptr(), s))) return rc;

@@ -29,6 +29,27 @@ int num_sms();
 void count_launch(int n = 1);   // per-thread launch counter (vv_trainer_last_launches)
 int launches_reset();           // returns the count and zeroes it
 
+// K4 for the trainer's two parameter blobs in ONE launch (vv_stream_kernels.cu): the weight update of vv_sgd_update
+// with (a) col_add[n] added to slab 0's gradient of column K-1 first (the K-1 copy quirk's share; what vv_add_column
+// did in its own launch), (b) the updated column K-1 saved to col_out (was vv_copy_strided), and (c) the bias blob
+// updated by extra CTAs of the same grid (was a second vv_sgd_update).  Element-wise arithmetic identical to the
+// separate launches.
+struct UpdateTail {
+  float* W; const float* parts; int nparts; long long stride; float* hist; float* diff_out; long long count; int K;
+  float rate_w, decay_w;
+  const float* col_add; float* col_out;
+  void* Wop_hi; void* Wop_lo; int prec;
+  float* b; const float* db; float* bh; float* b_diff; int nb; float rate_b, decay_b;
+  float momentum; int reg_type; float gscale;
+};
+int sgd_update_tail(const UpdateTail& u, vv_stream_t stream);
+// vv_rank_loss_fused with the batch loss / violation reduction folded into the kernel (vv_rank_loss.cu)
+int rank_loss_fused_counted(const float* H, const vv_rank_cfg_t* cfg, float loss_weight, int act_fused,
+                            float dropout_scale, float* stats, float* target_score, float* neg_score,
+                            float* item_loss, float* item_viol, float* loss, float* violations,
+                            float* dZ, void* dZop_hi, void* dZop_lo, int prec, float* db_accum,
+                            const float* delta, float* dq_accum, unsigned int* done_counter, vv_stream_t stream);
+
 constexpr int kNumSMsB200 = 148;
 
 // ----------------------------------------------------------------------------

@@ -380,6 +380,31 @@ __device__ __forceinline__ void warp_multi_sum(float (&v)[NV], int lane, int& in
   index = base; valid = nvalid >= 1;
 }
 
+// Folded rank_loss_reduce_kernel: the CTA that takes the last ticket sums item_loss / item_viol over the batch in a
+// fixed order (thread-strided partials, xor-butterfly per warp, warps in index order) -> deterministic like the
+// separate launch, without it.  `counter` must be zero at launch.  Called by the T compute threads of every CTA.
+template <bool NAMED_BARRIER>
+__device__ __forceinline__ void last_cta_loss_reduce(unsigned int* counter, const float* item_loss, const float* item_viol,
+                                                     int B, float inv_count, float* loss, float* viol, float* red /*[66]*/,
+                                                     int tid, int T) {
+  __threadfence();                                   // this CTA's item_loss / item_viol stores (thread 0) are visible
+  if (tid == 0) red[64] = __uint_as_float(atomicAdd(counter, 1u));
+  if (NAMED_BARRIER) asm volatile("bar.sync 1, %0;" :: "r"(T) : "memory"); else __syncthreads();
+  if (__float_as_uint(red[64]) != gridDim.x - 1) return;
+  __threadfence();
+  float a = 0.f, c = 0.f;
+  for (int i = tid; i < B; i += T) { a += __ldcg(item_loss + i); c += __ldcg(item_viol + i); }
+  a = warp_sum(a); c = warp_sum(c);
+  if ((tid & 31) == 0) { red[tid >> 5] = a; red[32 + (tid >> 5)] = c; }
+  if (NAMED_BARRIER) asm volatile("bar.sync 1, %0;" :: "r"(T) : "memory"); else __syncthreads();
+  if (tid == 0) {
+    a = 0.f; c = 0.f;
+    for (int w = 0; w < (T >> 5); ++w) { a += red[w]; c += red[32 + w]; }
+    if (loss) *loss = a * inv_count;
+    if (viol) *viol = c;
+  }
+}
+
 // ---- K2+K3 in one pass -------------------------------------------------------------------------------------
 // All R rows of an item live in registers (R*N*4 bytes are read from HBM exactly once), the 2J+1 dot products
 // are reduced through shared memory, warp 0 evaluates the per-item scalar chain (scores, hinge, every backward
@@ -394,7 +419,9 @@ rank_fused_kernel(const float* __restrict__ H, const RankDev p, const float gsca
                   const float dscale, const BwdOut out, float* __restrict__ db_accum,
                   const float* __restrict__ delta, float* __restrict__ dq_accum,
                   float* __restrict__ stats, float* __restrict__ tscore, float* __restrict__ nscore,
-                  float* __restrict__ item_loss, float* __restrict__ item_viol) {
+                  float* __restrict__ item_loss, float* __restrict__ item_viol,
+                  unsigned int* __restrict__ done_counter, const float inv_count, float* __restrict__ loss_out,
+                  float* __restrict__ viol_out) {
   extern __shared__ float sm[];
   const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = T >> 5;
   const int Cc = CT > 0 ? CT : p.C, Nn = NNT > 0 ? NNT : p.Nn;
@@ -563,6 +590,11 @@ rank_fused_kernel(const float* __restrict__ H, const RankDev p, const float gsca
       atomicAdd(dq_accum + tid * 4 + 2, dqacc.z); atomicAdd(dq_accum + tid * 4 + 3, dqacc.w);
     }
   }
+  if (done_counter) {
+    __shared__ float red[66];
+    __syncthreads();                                 // every item of this CTA has been written
+    last_cta_loss_reduce<false>(done_counter, item_loss, item_viol, p.B, inv_count, loss_out, viol_out, red, tid, T);
+  }
 }
 
 // ---- K2+K3 with the rows staged in shared memory by bulk async copies -----------------------------------------
@@ -586,7 +618,9 @@ rank_ring_kernel(const float* __restrict__ H, const RankDev p, const float gscal
                  const float dscale, const BwdOut out, float* __restrict__ db_accum,
                  const float* __restrict__ delta, float* __restrict__ dq_accum,
                  float* __restrict__ stats, float* __restrict__ tscore, float* __restrict__ nscore,
-                 float* __restrict__ item_loss, float* __restrict__ item_viol, const int stages) {
+                 float* __restrict__ item_loss, float* __restrict__ item_viol, const int stages,
+                 unsigned int* __restrict__ done_counter, const float inv_count, float* __restrict__ loss_out,
+                 float* __restrict__ viol_out) {
 #if defined(__CUDA_ARCH__)      // the mbarrier / bulk-copy helpers exist in the device pass only
   extern __shared__ __align__(128) float sm[];
   const int T = blockDim.x - 32, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = T >> 5;
@@ -777,6 +811,11 @@ rank_ring_kernel(const float* __restrict__ H, const RankDev p, const float gscal
       atomicAdd(dq_accum + tid * 4 + 2, dqacc.z); atomicAdd(dq_accum + tid * 4 + 3, dqacc.w);
     }
   }
+  if (done_counter) {
+    __shared__ float red[66];
+    consumer_sync(T);                                // every item of this CTA has been written (by warp 0)
+    last_cta_loss_reduce<true>(done_counter, item_loss, item_viol, p.B, inv_count, loss_out, viol_out, red, tid, T);
+  }
 #endif
 }
 
@@ -880,6 +919,18 @@ extern "C" int vv_rank_loss_fused(const float* H, const vv_rank_cfg_t* cfg, floa
                                   float* item_loss, float* item_viol, float* loss, float* violations,
                                   float* dZ, void* dZop_hi, void* dZop_lo, int prec, float* db_accum,
                                   const float* delta, float* dq_accum, vv_stream_t stream) {
+  return vv::rank_loss_fused_counted(H, cfg, loss_weight, act_fused, dropout_scale, stats, target_score, neg_score, item_loss,
+                                     item_viol, loss, violations, dZ, dZop_hi, dZop_lo, prec, db_accum, delta, dq_accum,
+                                     nullptr, stream);
+}
+
+// done_counter != NULL (a zeroed device word): the batch loss / violation sums are produced by the last CTA of the
+// fused kernel instead of a separate rank_loss_reduce_kernel launch (the trainer's path).
+int vv::rank_loss_fused_counted(const float* H, const vv_rank_cfg_t* cfg, float loss_weight, int act_fused,
+                                float dropout_scale, float* stats, float* target_score, float* neg_score,
+                                float* item_loss, float* item_viol, float* loss, float* violations,
+                                float* dZ, void* dZop_hi, void* dZop_lo, int prec, float* db_accum,
+                                const float* delta, float* dq_accum, unsigned int* done_counter, vv_stream_t stream) {
   RankDev d; int T;
   int rc = make_dev(cfg, &d, &T);
   if (rc) return rc;
@@ -904,6 +955,8 @@ extern "C" int vv_rank_loss_fused(const float* H, const vv_rank_cfg_t* cfg, floa
   const int grid = d.B < num_sms() * per_sm ? d.B : num_sms() * per_sm;
   const int mode = (o.dZ ? 1 : 0) | (o.prec == VV_PREC_TF32X3 ? 2 : 0) | (o.prec == VV_PREC_BF16 ? 4 : 0) |
                    (o.prec == VV_PREC_F16X3 ? 8 : 0);
+  unsigned int* cnt = (loss || violations) ? done_counter : nullptr;       // fold the batch reduction into the kernel
+  const float inv_count = 1.f / float(d.B * d.Nn);
   // ring variant (rows staged in shared memory by a producer warp): whenever two slots of R rows fit
   const char* ring_e = getenv("VV_RANK_RING");                      // 0 = register-resident kernel, n >= 2 = ring stages
   const int ring_env = ring_e ? atoi(ring_e) : -1;
@@ -927,7 +980,7 @@ extern "C" int vv_rank_loss_fused(const float* H, const vv_rank_cfg_t* cfg, floa
       attr_set = true;                                                                                                 \
     }                                                                                                                  \
     rank_ring_kernel<RM, CT, NNT, OUT><<<rgrid, T + 32, rsmem, stream>>>(H, d, gscale, act_fused, dropout_scale, o, db_accum, \
-        delta, dq_accum, stats, target_score, neg_score, item_loss, item_viol, stages);                                \
+        delta, dq_accum, stats, target_score, neg_score, item_loss, item_viol, stages, cnt, inv_count, loss, violations); \
   } while (0)
     if (d.C == 5 && d.Nn == 10 && mode == 2) VV_RANK_RING(16, 5, 10, 2);
     else if (d.C == 5 && d.Nn == 10 && mode == 4) VV_RANK_RING(16, 5, 10, 4);
@@ -939,7 +992,7 @@ extern "C" int vv_rank_loss_fused(const float* H, const vv_rank_cfg_t* cfg, floa
   } else {
 #define VV_RANK_FUSED(RM, CT, NNT, OUT)                                                                              \
     rank_fused_kernel<RM, CT, NNT, OUT><<<grid, T, smem, stream>>>(H, d, gscale, act_fused, dropout_scale, o, db_accum, \
-        delta, dq_accum, stats, target_score, neg_score, item_loss, item_viol)
+        delta, dq_accum, stats, target_score, neg_score, item_loss, item_viol, cnt, inv_count, loss, violations)
     if (d.C == 5 && d.Nn == 10 && mode == 2) VV_RANK_FUSED(16, 5, 10, 2);        // the shipped net (C=5, Nn=10), training modes
     else if (d.C == 5 && d.Nn == 10 && mode == 4) VV_RANK_FUSED(16, 5, 10, 4);
     else if (d.C == 5 && d.Nn == 10 && mode == 8) VV_RANK_FUSED(16, 5, 10, 8);
@@ -950,8 +1003,8 @@ extern "C" int vv_rank_loss_fused(const float* H, const vv_rank_cfg_t* cfg, floa
   }
   VV_LAUNCH_CHECK();
   count_launch();
-  if (loss || violations) {
-    rank_loss_reduce_kernel<<<1, 1024, 0, stream>>>(item_loss, item_viol, d.B, 1.f / float(d.B * d.Nn), loss, violations);
+  if ((loss || violations) && !cnt) {
+    rank_loss_reduce_kernel<<<1, 1024, 0, stream>>>(item_loss, item_viol, d.B, inv_count, loss, violations);
     VV_LAUNCH_CHECK();
     count_launch();
   }

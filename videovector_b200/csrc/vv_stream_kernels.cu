@@ -236,6 +236,63 @@ __global__ void sgd_update_scalar_kernel(float* W, const float* parts, int npart
   }
 }
 
+// weights + bias in one launch (see UpdateTail in vv_common.cuh); same per-element arithmetic as sgd_update_kernel
+__global__ void __launch_bounds__(256)
+sgd_update_tail_kernel(const UpdateTail u, const int main_blocks) {
+  if (int(blockIdx.x) >= main_blocks) {            // ---- bias blob (scalar, nb elements)
+    for (int i = (blockIdx.x - main_blocks) * blockDim.x + threadIdx.x; i < u.nb; i += (gridDim.x - main_blocks) * blockDim.x) {
+      float g = u.db[i];
+      if (u.gscale != 1.f) g *= u.gscale;
+      const float w = u.b[i];
+      if (u.decay_b != 0.f) g = (u.reg_type == 2) ? fmaf(u.decay_b, w, g) : g + u.decay_b * float((0.f < w) - (w < 0.f));
+      const float h = fmaf(u.rate_b, g, u.momentum * u.bh[i]);
+      u.bh[i] = h; u.b[i] = w - h;
+      if (u.b_diff) u.b_diff[i] = h;
+    }
+    return;
+  }
+  float* hi = static_cast<float*>(u.Wop_hi); float* lo = static_cast<float*>(u.Wop_lo);
+  const float scale = (u.prec == VV_PREC_F16X3 && hi) ? f16_hdr(hi)->scale : 1.f;
+  const long long n4 = u.count / 4, k4 = u.K / 4;
+  const float rate = u.rate_w, momentum = u.momentum, decay = u.decay_w, gscale = u.gscale;
+  float amax = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)main_blocks * blockDim.x) {
+    float4 g = reinterpret_cast<const float4*>(u.parts)[i];
+    const bool last_col = (i % k4) == k4 - 1;                    // .w is column K-1 of row i / k4
+    if (last_col && u.col_add) g.w += u.col_add[i / k4];
+    for (int s = 1; s < u.nparts; ++s) {
+      const float4 t = reinterpret_cast<const float4*>(u.parts + s * u.stride)[i];
+      g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+    }
+    if (gscale != 1.f) { g.x *= gscale; g.y *= gscale; g.z *= gscale; g.w *= gscale; }
+    float4 w = reinterpret_cast<float4*>(u.W)[i];
+    if (decay != 0.f) {
+      if (u.reg_type == 2) {
+        g.x = fmaf(decay, w.x, g.x); g.y = fmaf(decay, w.y, g.y); g.z = fmaf(decay, w.z, g.z); g.w = fmaf(decay, w.w, g.w);
+      } else {
+        g.x += decay * float((0.f < w.x) - (w.x < 0.f)); g.y += decay * float((0.f < w.y) - (w.y < 0.f));
+        g.z += decay * float((0.f < w.z) - (w.z < 0.f)); g.w += decay * float((0.f < w.w) - (w.w < 0.f));
+      }
+    }
+    float4 h = reinterpret_cast<float4*>(u.hist)[i];
+    h.x = fmaf(rate, g.x, momentum * h.x); h.y = fmaf(rate, g.y, momentum * h.y);
+    h.z = fmaf(rate, g.z, momentum * h.z); h.w = fmaf(rate, g.w, momentum * h.w);
+    w.x -= h.x; w.y -= h.y; w.z -= h.z; w.w -= h.w;
+    reinterpret_cast<float4*>(u.hist)[i] = h;
+    reinterpret_cast<float4*>(u.W)[i] = w;
+    if (u.diff_out) reinterpret_cast<float4*>(u.diff_out)[i] = h;
+    if (last_col && u.col_out) u.col_out[i / k4] = w.w;
+    if (u.prec == VV_PREC_TF32X3 && hi) {
+      store_x3(hi, lo, size_t(n4) * 4, size_t(i) * 4, w);
+    } else if (u.prec == VV_PREC_F16X3 && hi) {
+      store_f16x3(hi, lo, size_t(i) * 4, w, scale, amax);
+    } else if (u.prec == VV_PREC_BF16 && hi) {
+      reinterpret_cast<uint2*>(hi)[i] = make_uint2(pack_bf16x2(w.x, w.y), pack_bf16x2(w.z, w.w));
+    }
+  }
+  if (u.prec == VV_PREC_F16X3 && hi) f16_publish_absmax(hi, amax);
+}
+
 __global__ void __launch_bounds__(256)
 reduce_parts_kernel(const float* parts, int nparts, long long stride, long long n, float* out) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -534,6 +591,19 @@ extern "C" int vv_sgd_update(float* W, const float* grad_parts, int nparts, int6
     sgd_update_scalar_kernel<<<stream_grid(count, 256), 256, 0, stream>>>(
         W, grad_parts, nparts, part_stride, hist, diff_out, count, local_rate, momentum, local_decay, reg_type, grad_scale);
   }
+  VV_LAUNCH_CHECK();
+  count_launch();
+  return VV_OK;
+}
+
+int vv::sgd_update_tail(const UpdateTail& u, vv_stream_t stream) {
+  VV_REQUIRE(u.W && u.parts && u.hist && u.b && u.db && u.bh && u.count > 0 && u.nparts >= 1 && u.nb > 0, "sgd_update_tail: bad arguments");
+  VV_REQUIRE(u.reg_type == 1 || u.reg_type == 2, "regularization type must be 1 (L1) or 2 (L2)");
+  VV_REQUIRE(u.K > 0 && u.K % 4 == 0 && u.count % u.K == 0 && u.stride % 4 == 0 && VV_ALIGNED16(u.W) && VV_ALIGNED16(u.parts) &&
+             VV_ALIGNED16(u.hist) && VV_ALIGNED16(u.diff_out) && VV_ALIGNED16(u.Wop_hi) && VV_ALIGNED16(u.Wop_lo),
+             "sgd_update_tail: needs 16-byte aligned blobs and K a multiple of 4");
+  const int main_blocks = stream_grid(u.count / 4, 256), bias_blocks = (u.nb + 255) / 256;
+  sgd_update_tail_kernel<<<main_blocks + bias_blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(u, main_blocks);
   VV_LAUNCH_CHECK();
   count_launch();
   return VV_OK;
