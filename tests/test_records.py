@@ -128,6 +128,17 @@ def test_malformed_records_fail_loudly():
     t.context_shot_words.add().float_data.extend([1.0])
     with pytest.raises(VVError, match="2 context words, expected 1"):
         ts.add(t.SerializeToString())
+    # sizes come from the first ACCEPTED record: a rejected first record leaves nothing behind
+    ts2 = ops.RecordSet("test_windows")
+    bad = Test(); bad.video_id = 1
+    bad.context_shot_words.add().float_data.extend([1.0, 2.0]); bad.context_shot_words.add().float_data.extend([1.0])
+    with pytest.raises(VVError, match="feature_size is 2"):
+        ts2.add(bad.SerializeToString())
+    good3 = Test(); good3.video_id = 2
+    for _ in range(3):
+        good3.context_shot_words.add().float_data.extend([4.0, 5.0, 6.0])
+    ts2.add(good3.SerializeToString())
+    assert ts2.info() == dict(records=1, rows=3, feature_size=3, rows_per_record=3)
 
 
 def test_load_file_errors(tmp_path):

@@ -12,6 +12,7 @@
 // length-prefixed record stream ("VVRS") and for the text dump `mdb_dump` prints.
 #include <cuda_runtime.h>
 
+#include <sys/mman.h>
 #include <sys/stat.h>
 
 #include <cstdio>
@@ -188,11 +189,14 @@ static int add_test_windows(vv_record_set* s, Rd r) {
     s->neg = s->with_neg ? int(neg.size()) : 0;
     if (s->ctx < 1) { s->ctx = -1; return vv_set_error("TestVideoShotWindows: context_size must be >= 1"); }
   }
-  if (int(ctx.size()) != s->ctx) return vv_set_error("TestVideoShotWindows: %zu context words, expected %d", ctx.size(), s->ctx);
-  if (s->with_pos && (int(pos.size()) != s->pos || int(s->ids_tmp.size()) != s->pos))          // :190-197
-    return vv_set_error("TestVideoShotWindows: %zu positive words / %zu ids, expected %d", pos.size(), s->ids_tmp.size(), s->pos);
-  if (s->with_neg && int(neg.size()) != s->neg)                                                 // :199-201
-    return vv_set_error("TestVideoShotWindows: %zu negative words, expected %d", neg.size(), s->neg);
+  const bool first = s->video_id.empty();
+  int bad = 0;
+  if (int(ctx.size()) != s->ctx) bad = vv_set_error("TestVideoShotWindows: %zu context words, expected %d", ctx.size(), s->ctx);
+  else if (s->with_pos && (int(pos.size()) != s->pos || int(s->ids_tmp.size()) != s->pos))     // :190-197
+    bad = vv_set_error("TestVideoShotWindows: %zu positive words / %zu ids, expected %d", pos.size(), s->ids_tmp.size(), s->pos);
+  else if (s->with_neg && int(neg.size()) != s->neg)                                            // :199-201
+    bad = vv_set_error("TestVideoShotWindows: %zu negative words, expected %d", neg.size(), s->neg);
+  if (bad) { if (first) s->ctx = s->pos = s->neg = -1; return bad; }
   const size_t rows0 = s->bank.size(), ids0 = s->shot_ids.size(), K0 = size_t(s->K);
   int rc = 0;
   for (int i = 0; i < s->ctx && !rc; ++i) { rc = add_rows(s, ctx[i], "context_shot_words"); s->shot_ids.push_back(-1); }
@@ -201,7 +205,12 @@ static int add_test_windows(vv_record_set* s, Rd r) {
     rc = add_rows(s, neg[i], "negative_shot_words");
     s->shot_ids.push_back(i < int(s->neg_ids_tmp.size()) ? s->neg_ids_tmp[i] : -1);
   }
-  if (rc) { s->bank.resize(rows0); s->shot_ids.resize(ids0); if (!K0) s->K = 0; return rc; }
+  if (rc) {
+    s->bank.resize(rows0); s->shot_ids.resize(ids0);
+    if (!K0) s->K = 0;
+    if (s->video_id.empty()) s->ctx = s->pos = s->neg = -1;      // sizes come from the first ACCEPTED record
+    return rc;
+  }
   s->video_id.push_back(vid);
   s->row_off.push_back(s->row_off.back() + s->ctx + s->pos + s->neg);
   return 0;
@@ -218,9 +227,10 @@ static int add_test_windows(vv_record_set* s, Rd r) {
 namespace {
 enum { P_BRANCH = 0x01, P_LEAF = 0x02, P_OVERFLOW = 0x04, P_META = 0x08, P_LEAF2 = 0x20, F_BIGDATA = 0x01, F_SUBDATA = 0x02, F_DUPDATA = 0x04 };
 struct LmdbFile {
-  std::vector<uint8_t> buf;         // the pages up to last_pg (the file is read once; the bank is the only long-lived copy)
-  size_t psize = 0, npages = 0;
-  const uint8_t* page(uint64_t pgno) const { return pgno < npages ? buf.data() + pgno * psize : nullptr; }
+  const uint8_t* map = nullptr;     // read-only mapping of data.mdb: pages are touched once, in key order, no copy
+  size_t map_bytes = 0, psize = 0, npages = 0;
+  const uint8_t* page(uint64_t pgno) const { return pgno < npages ? map + pgno * psize : nullptr; }
+  ~LmdbFile() { if (map) munmap(const_cast<uint8_t*>(map), map_bytes); }
 };
 template <typename T> T rd(const uint8_t* p) { T v; memcpy(&v, p, sizeof(T)); return v; }
 
@@ -248,7 +258,7 @@ int lmdb_walk(vv_record_set* s, const LmdbFile& f, uint64_t pgno, int depth, con
       if (size_t(off) + 8 + ksize + 8 > f.psize) return vv_set_error("%s: truncated overflow reference", path);
       const uint64_t opg = rd<uint64_t>(data);
       const uint8_t* ov = f.page(opg);
-      if (!ov || !(rd<uint16_t>(ov + 10) & P_OVERFLOW) || (opg * f.psize + 16 + dsize) > f.buf.size())
+      if (!ov || !(rd<uint16_t>(ov + 10) & P_OVERFLOW) || (opg * f.psize + 16 + dsize) > f.npages * f.psize)
         return vv_set_error("%s: bad overflow page %llu", path, (unsigned long long)opg);
       data = ov + 16;
     } else if (size_t(off) + 8 + ksize + dsize > f.psize) {
@@ -283,9 +293,15 @@ int load_lmdb(vv_record_set* s, FILE* fp, const char* path) {
   const uint64_t root = rd<uint64_t>(maindb + 40), last_pg = rd<uint64_t>(meta + 24 + 96);
   if (root == ~uint64_t(0)) return 0;                       // empty database
   f.psize = psize; f.npages = size_t(last_pg) + 1;
-  if (f.npages > (uint64_t(1) << 40) / psize) return vv_set_error("%s: implausible page count", path);
-  f.buf.resize(f.npages * psize);
-  if (fseek(fp, 0, SEEK_SET) != 0 || fread(f.buf.data(), 1, f.buf.size(), fp) != f.buf.size()) return vv_set_error("%s: file shorter than its last page %llu", path, (unsigned long long)last_pg);
+  if (f.npages > (uint64_t(1) << 44) / psize) return vv_set_error("%s: implausible page count", path);
+  struct stat st;
+  if (fstat(fileno(fp), &st) != 0 || uint64_t(st.st_size) < uint64_t(f.npages) * psize)
+    return vv_set_error("%s: file shorter than its last page %llu", path, (unsigned long long)last_pg);
+  f.map_bytes = f.npages * psize;
+  void* m = mmap(nullptr, f.map_bytes, PROT_READ, MAP_PRIVATE, fileno(fp), 0);
+  if (m == MAP_FAILED) return vv_set_error("%s: mmap failed", path);
+  f.map = static_cast<const uint8_t*>(m);
+  madvise(m, f.map_bytes, MADV_SEQUENTIAL);
   return lmdb_walk(s, f, root, 0, path);
 }
 }  // namespace
