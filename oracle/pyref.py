@@ -120,3 +120,33 @@ class Sampler:
     def close(self):
         if self._h:
             lib().ref_sampler_destroy(self._h); self._h = None
+
+
+class TestLayer:
+    """The REFERENCE's VideoShotWindowTestDataLayer (compiled unmodified) over the fake LMDB: records of
+    TestVideoShotWindows built from data [n, ctx+pos+neg, K]; next() -> (data blob [B, rows, K], labels [B])."""
+
+    def __init__(self, data, video_id, pos_id, neg_id, ctx, pos, neg, batch_size, include_positives=True, include_negatives=True):
+        L = lib()
+        L.ref_testlayer_create.restype = C.c_void_p
+        L.ref_testlayer_next.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_testlayer_rows.argtypes = [C.c_void_p]
+        L.ref_testlayer_destroy.argtypes = [C.c_void_p]
+        self.data = f32(data); n, rows, K = self.data.shape
+        assert rows == ctx + pos + neg
+        self.vid = np.ascontiguousarray(video_id, np.int32)
+        self.pid = np.ascontiguousarray(pos_id, np.int32); self.nid = np.ascontiguousarray(neg_id, np.int32)
+        self._h = L.ref_testlayer_create(n, ctx, pos, neg, K, _p(self.data), _p(self.vid), _p(self.pid), _p(self.nid), batch_size,
+                                         int(include_positives), int(include_negatives))
+        if not self._h:
+            raise RuntimeError("reference test data layer failed to set up")
+        self.B, self.R, self.K = batch_size, L.ref_testlayer_rows(self._h), K
+
+    def next(self):
+        data = np.empty((self.B, self.R, self.K), np.float32); lab = np.empty(self.B, np.float32)
+        assert lib().ref_testlayer_next(self._h, _p(data), _p(lab)) == 0
+        return data, lab
+
+    def close(self):
+        if self._h:
+            lib().ref_testlayer_destroy(self._h); self._h = None

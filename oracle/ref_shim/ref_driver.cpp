@@ -262,7 +262,8 @@ bool caffe::ReadProtoFromBinaryFile(const char*, google::protobuf::Message*) { r
 
 namespace {
 typedef video_shot_sentences::VideoShots VideoShots;
-struct FakeDb { std::vector<std::shared_ptr<VideoShots> > records; };
+typedef video_shot_sentences::TestVideoShotWindows TestVideoShotWindows;
+struct FakeDb { std::vector<std::shared_ptr<void> > records; };      // live VideoShots / TestVideoShotWindows messages
 FakeDb* g_fake_db = nullptr;          // the dataset the next mdb_env_open serves
 }  // namespace
 struct MDB_env { FakeDb* db; };
@@ -346,6 +347,57 @@ REF_API int ref_sampler_next(void* h, float* data) {
   } catch (const std::exception& e) { fprintf(stderr, "ref_driver: %s\n", e.what()); return -1; }
 }
 REF_API int ref_sampler_rows(void* h) { return static_cast<RefSampler*>(h)->R; }
+
+// The reference's TEST-phase data layer (video_shot_window_test_data_layer.cpp, compiled unmodified) over the same fake
+// LMDB: n records of TestVideoShotWindows with ctx context / pos positive / neg negative datums each (data [n, ctx+pos+neg, K]).
+struct RefTestLayer {
+  FakeDb db;
+  std::unique_ptr<VideoShotWindowTestDataLayer<float> > layer;
+  Blob<float> top, label;
+  int B, R, K;
+};
+REF_API void* ref_testlayer_create(int n, int ctx, int pos, int neg, int K, const float* data, const int* video_id,
+                                   const int* pos_id, const int* neg_id, int batch_size, int include_pos, int include_neg) {
+  try {
+    Caffe::set_mode(Caffe::CPU);
+    RefTestLayer* s = new RefTestLayer();
+    const int rows = ctx + pos + neg;
+    for (int i = 0; i < n; ++i) {
+      std::shared_ptr<TestVideoShotWindows> rec(new TestVideoShotWindows());
+      rec->set_video_id(video_id[i]);
+      for (int r = 0; r < rows; ++r) {
+        Datum* d = r < ctx ? rec->add_context_shot_words() : r < ctx + pos ? rec->add_positive_shot_words() : rec->add_negative_shot_words();
+        for (int k = 0; k < K; ++k) d->add_float_data(data[(size_t(i) * rows + r) * K + k]);
+        if (r >= ctx && r < ctx + pos) rec->add_positive_shot_id(pos_id[i * pos + (r - ctx)]);
+        if (r >= ctx + pos) rec->add_negative_shot_id(neg_id[i * neg + (r - ctx - pos)]);
+      }
+      s->db.records.push_back(rec);
+    }
+    LayerParameter p;
+    VideoShotWindowTestDataParameter* vp = p.mutable_video_shot_window_test_data_param();
+    vp->set_source("mem://fake-lmdb"); vp->set_backend(VideoShotWindowTestDataParameter_DB_LMDB);
+    vp->set_batch_size(batch_size); vp->set_include_positives(include_pos != 0); vp->set_include_negatives(include_neg != 0);
+    g_fake_db = &s->db;
+    s->layer.reset(new VideoShotWindowTestDataLayer<float>(p));
+    BV bottom, tv{&s->top, &s->label};
+    s->layer->SetUp(bottom, &tv);
+    g_fake_db = nullptr;
+    s->B = batch_size; s->R = s->top.channels(); s->K = K;
+    return s;
+  } catch (const std::exception& e) { fprintf(stderr, "ref_driver: %s\n", e.what()); return nullptr; }
+}
+REF_API int ref_testlayer_rows(void* h) { return static_cast<RefTestLayer*>(h)->R; }
+REF_API int ref_testlayer_next(void* h, float* data, float* labels) {
+  try {
+    RefTestLayer* s = static_cast<RefTestLayer*>(h);
+    BV bottom, tv{&s->top, &s->label};
+    s->layer->Forward(bottom, &tv);
+    memcpy(data, s->top.cpu_data(), sizeof(float) * size_t(s->B) * s->R * s->K);
+    memcpy(labels, s->label.cpu_data(), sizeof(float) * size_t(s->B));
+    return 0;
+  } catch (const std::exception& e) { fprintf(stderr, "ref_driver: %s\n", e.what()); return -1; }
+}
+REF_API void ref_testlayer_destroy(void* h) { delete static_cast<RefTestLayer*>(h); }
 REF_API void ref_sampler_destroy(void* h) { delete static_cast<RefSampler*>(h); }
 REF_API void ref_srand(unsigned seed) { srand(seed); }
 

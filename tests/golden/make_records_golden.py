@@ -99,7 +99,17 @@ def main():
             m.negative_shot_id.append(int(neg_id[i, j])); m.negative_shot_words.add().float_data.extend(data[i, F + P + j].tolist())
         recs.append((b"%08d" % i, m.SerializeToString()))
     write_vvrs(os.path.join(HERE, "test_windows.vvrs"), recs)
-    np.savez_compressed(os.path.join(HERE, "test_windows.npz"), data=data, vids=vids, pos_id=pos_id, neg_id=neg_id)
+    # what the reference's own VideoShotWindowTestDataLayer (oracle/_ref, compiled unmodified, fake LMDB) serves from these
+    # records: 4 batches of 10 (wraps after 23 records) for the three include_positives / include_negatives settings
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from oracle import pyref
+    ref = {}
+    for tag, ip, ineg in (("pn", True, True), ("p", True, False), ("ctx", False, False)):
+        lay = pyref.TestLayer(data, vids, pos_id, neg_id, F, P, Ng, 10, ip, ineg)
+        out = [lay.next() for _ in range(4)]
+        ref["blob_" + tag] = np.stack([o[0] for o in out]); ref["label_" + tag] = np.stack([o[1] for o in out])
+        lay.close()
+    np.savez_compressed(os.path.join(HERE, "test_windows.npz"), data=data, vids=vids, pos_id=pos_id, neg_id=neg_id, **ref)
     print("wrote", [f for f in sorted(os.listdir(HERE)) if "video_shots" in f or "test_windows" in f or f == "records_schema.desc"])
 
 

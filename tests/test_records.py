@@ -196,3 +196,28 @@ def test_lmdb_environment_directory(tmp_path):
     (tmp_path / "cut_lmdb").mkdir(); open(tmp_path / "cut_lmdb" / "data.mdb", "wb").write(raw[:len(raw) // 2])
     with pytest.raises(VVError, match="shorter than its last page"):
         ops.RecordSet().load_file(tmp_path / "cut_lmdb")
+
+
+@pytest.mark.parametrize("tag,pos,neg", [("pn", True, True), ("p", True, False), ("ctx", False, False)])
+def test_test_windows_match_reference_test_data_layer(tag, pos, neg):
+    """tests/golden/test_windows.npz also holds what the reference's VideoShotWindowTestDataLayer ITSELF (compiled
+    unmodified into oracle/_ref, fake LMDB) served from these records: item c of the stream = record c mod n, channels =
+    its rows, label = its video_id.  The product's decoded record set must reproduce blobs and labels bit for bit; where
+    oracle/_ref exists the layer is also run live."""
+    t = np.load(os.path.join(GOLD, "test_windows.npz"))
+    rs = ops.RecordSet("test_windows", include_positives=pos, include_negatives=neg).load_file(os.path.join(GOLD, "test_windows.vvrs"))
+    info = rs.info(); n, rows = info["records"], info["rows_per_record"]
+    bank = rs.bank_host().reshape(n, rows, -1); vid = rs.tables()[0]
+    blobs, labels = t["blob_" + tag], t["label_" + tag]
+    B = blobs.shape[1]
+    assert blobs.shape[2] == rows
+    for it in range(blobs.shape[0]):
+        item = (np.arange(B) + it * B) % n
+        assert np.array_equal(bank[item], blobs[it]) and np.array_equal(vid[item].astype(np.float32), labels[it])
+    from oracle import pyref
+    if pyref.available():
+        lay = pyref.TestLayer(t["data"], t["vids"], t["pos_id"], t["neg_id"], 4, 1, 2, B, pos, neg)
+        for it in range(3):
+            d, l = lay.next()
+            assert np.array_equal(d, blobs[it]) and np.array_equal(l, labels[it])
+        lay.close()
