@@ -150,3 +150,55 @@ class TestLayer:
     def close(self):
         if self._h:
             lib().ref_testlayer_destroy(self._h); self._h = None
+
+
+class Solver:
+    """The REFERENCE's whole training pipeline: its VideoSampledShotsDataLayer (fake LMDB, libc rand()), Net (net.cpp,
+    insert_splits.cpp) and SGDSolver (solver.cpp: learning-rate policy, weight decay, momentum, Net::Update), compiled
+    unmodified, on the shipped TRAIN graph without the dropout layer.  step() = one iteration of Solver::Solve's loop."""
+    POLICY = {"fixed": 0, "inv": 1, "step": 2}
+
+    def __init__(self, video_id, shot_off, shot_ids, feat, W0, b0, batch_size, context_size=5, num_negative_samples=10,
+                 max_buffer_size=5000, negative_swap_percentage=50, max_same_video_negs=6, context_type=1, margin=2.0,
+                 norm=2, base_lr=0.001, momentum=0.9, weight_decay=0.0005, lr_policy="inv", gamma=0.001, power=0.75,
+                 stepsize=1, seed=1, dropout_ratio=0.0):
+        L = lib()
+        L.ref_solver_create.restype = C.c_void_p
+        L.ref_solver_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_solver_get.argtypes = [C.c_void_p] + [C.c_void_p] * 5
+        L.ref_solver_num_layers.argtypes = [C.c_void_p]
+        L.ref_solver_layer_name.argtypes = [C.c_void_p, C.c_int]; L.ref_solver_layer_name.restype = C.c_char_p
+        L.ref_solver_destroy.argtypes = [C.c_void_p]
+        self.vid = np.ascontiguousarray(video_id, np.int32); self.off = np.ascontiguousarray(shot_off, np.int32)
+        self.sid = np.ascontiguousarray(shot_ids, np.int32); self.feat = f32(feat)
+        W0, b0 = f32(W0), f32(b0)
+        self.N, self.K = W0.shape
+        self.B, self.R = batch_size, context_size + num_negative_samples
+        L.ref_srand(C.c_uint(seed))
+        fl = C.c_float
+        self._h = L.ref_solver_create(len(self.vid), self.K, _p(self.vid), _p(self.off), _p(self.sid), _p(self.feat), batch_size,
+                                      context_size, num_negative_samples, self.N, max_buffer_size, negative_swap_percentage,
+                                      max_same_video_negs, context_type, fl(margin), norm, fl(base_lr), fl(momentum),
+                                      fl(weight_decay), self.POLICY[lr_policy], fl(gamma), fl(power), stepsize, _p(W0), _p(b0),
+                                      fl(dropout_ratio))
+        if not self._h:
+            raise RuntimeError("reference solver failed to set up")
+
+    def step(self):
+        loss, viol = C.c_float(0), C.c_float(0)
+        assert lib().ref_solver_step(self._h, C.addressof(loss), C.addressof(viol)) == 0
+        return loss.value, viol.value
+
+    def state(self, want_data=False):
+        W = np.empty((self.N, self.K), np.float32); b = np.empty(self.N, np.float32)
+        hW = np.empty_like(W); hb = np.empty_like(b)
+        data = np.empty((self.B, self.R, self.K), np.float32) if want_data else None
+        assert lib().ref_solver_get(self._h, _p(W), _p(b), _p(hW), _p(hb), _p(data)) == 0
+        return dict(W=W, b=b, hW=hW, hb=hb, data=data)
+
+    def layer_names(self):
+        return [lib().ref_solver_layer_name(self._h, i).decode() for i in range(lib().ref_solver_num_layers(self._h))]
+
+    def close(self):
+        if self._h:
+            lib().ref_solver_destroy(self._h); self._h = None

@@ -24,7 +24,8 @@ CXXFLAGS="-std=c++14 -O2 -fPIC -fvisibility=hidden -fvisibility-inlines-hidden -
 SRCS="blob syncedmem common util/math_functions layers/inner_product_layer layers/relu_layer layers/dropout_layer layers/eltwise_layer
       layers/normalization_layer layers/sum_layer layers/split_layer layers/slice_layer layers/concat_layer layers/flatten_layer
       layers/max_margin_loss_layer layers/loss_layer layers/neuron_layer layers/retrieval_stats_layer layers/id_to_weight_mapping_layer
-      layers/video_sampled_shots_data_layer layers/video_shot_window_test_data_layer layers/base_data_layer internal_thread data_transformer"
+      layers/video_sampled_shots_data_layer layers/video_shot_window_test_data_layer layers/base_data_layer internal_thread data_transformer
+      net solver util/insert_splits"
 OBJS=""
 for s in $SRCS; do
   o="$OUT/obj/$(basename $s).o"

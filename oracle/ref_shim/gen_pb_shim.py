@@ -75,7 +75,8 @@ def gen(proto_text, package):
     out = []
     # enums first
     for name, vals in enums.items():
-        out.append("enum %s { %s };" % (name, ", ".join("%s_%s = %s" % (name, v, n) for v, n in vals)))
+        plain = ["%s = %s" % (v, n) for v, n in vals] if "_" not in name else []     # protoc: top-level enum values are plain names
+        out.append("enum %s { %s };" % (name, ", ".join(["%s_%s = %s" % (name, v, n) for v, n in vals] + plain)))
         out.append("inline const std::string& %s_Name(%s v) { static std::map<int, std::string> m = {%s}; static std::string e; auto it = m.find(int(v)); return it == m.end() ? e : it->second; }" %
                    (name, name, ", ".join('{%s, "%s"}' % (n, v) for v, n in vals)))
         out.append("inline bool %s_IsValid(int v) { return %s; }" % (name, " || ".join("v == %s" % n for _, n in vals) or "false"))

@@ -13,6 +13,10 @@
 #include "caffe/vision_layers.hpp"
 #include "caffe/data_layers.hpp"
 #include "caffe/util/io.hpp"
+#include "caffe/net.hpp"
+#include "caffe/solver.hpp"
+#include "caffe/util/upgrade_proto.hpp"
+#include "caffe/util/pb2json.h"
 
 using namespace caffe;  // NOLINT
 typedef std::vector<Blob<float>*> BV;
@@ -401,4 +405,188 @@ REF_API void ref_testlayer_destroy(void* h) { delete static_cast<RefTestLayer*>(
 REF_API void ref_sampler_destroy(void* h) { delete static_cast<RefSampler*>(h); }
 REF_API void ref_srand(unsigned seed) { srand(seed); }
 
+}  // extern "C"
+
+
+// ---- the reference's own Net + SGDSolver (net.cpp, solver.cpp, util/insert_splits.cpp compiled unmodified) ------------
+// The whole training pipeline of the reference -- VideoSampledShotsDataLayer (fake LMDB, libc rand()), Net::Init with
+// split insertion and loss weights, Net::ForwardBackward, SGDSolver::ComputeUpdateValue (learning-rate policy, weight
+// decay, momentum history), Net::Update -- on a NetParameter built here with the structure of
+// projects/videovec_embedding/mednet_embedding_train.prototxt (no text parser in the shim).  Not compiled from the
+// reference and replaced by the few stand-ins below: layer_factory.cpp (it names every layer type of the fork),
+// util/io.cpp / upgrade_proto.cpp (protobuf text + binary IO), pb2json.
+namespace caffe {
+template <typename Dtype>
+Layer<Dtype>* GetLayer(const LayerParameter& param) {
+  switch (param.type()) {
+    case LayerParameter_LayerType_VIDEO_SAMPLED_SHOTS_DATA: return new VideoSampledShotsDataLayer<Dtype>(param);
+    case LayerParameter_LayerType_SLICE: return new SliceLayer<Dtype>(param);
+    case LayerParameter_LayerType_CONCAT: return new ConcatLayer<Dtype>(param);
+    case LayerParameter_LayerType_FLATTEN: return new FlattenLayer<Dtype>(param);
+    case LayerParameter_LayerType_INNER_PRODUCT: return new InnerProductLayer<Dtype>(param);
+    case LayerParameter_LayerType_RELU: return new ReLULayer<Dtype>(param);
+    case LayerParameter_LayerType_DROPOUT: return new DropoutLayer<Dtype>(param);
+    case LayerParameter_LayerType_ELTWISE: return new EltwiseLayer<Dtype>(param);
+    case LayerParameter_LayerType_NORMALIZATION: return new NormalizationLayer<Dtype>(param);
+    case LayerParameter_LayerType_SUM: return new SumLayer<Dtype>(param);
+    case LayerParameter_LayerType_SPLIT: return new SplitLayer<Dtype>(param);
+    case LayerParameter_LayerType_MAX_MARGIN_LOSS: return new MaxMarginLossLayer<Dtype>(param);
+    default: LOG(FATAL) << "layer type " << param.type() << " is not part of the shim factory"; return NULL;
+  }
+}
+template Layer<float>* GetLayer(const LayerParameter& param);
+template Layer<double>* GetLayer(const LayerParameter& param);
+bool NetNeedsUpgrade(const NetParameter&) { return false; }
+bool UpgradeV0Net(const NetParameter&, NetParameter*) { return false; }
+bool NetNeedsDataUpgrade(const NetParameter&) { return false; }
+void UpgradeNetDataTransformation(NetParameter*) {}
+void ReadNetParamsFromTextFileOrDie(const string&, NetParameter*) { LOG(FATAL) << "no text parser in the shim"; }
+void ReadNetParamsFromBinaryFileOrDie(const string&, NetParameter*) { LOG(FATAL) << "no binary parser in the shim"; }
+bool ReadProtoFromTextFile(const char*, google::protobuf::Message*) { return false; }
+void WriteProtoToTextFile(const google::protobuf::Message&, const char*) {}
+void WriteProtoToBinaryFile(const google::protobuf::Message&, const char*) {}
+}  // namespace caffe
+char* pb2json(const google::protobuf::Message&) { return strdup("{}"); }
+
+namespace {
+struct StepSolver : public SGDSolver<float> {
+  explicit StepSolver(const SolverParameter& p) : SGDSolver<float>(p) {}
+  void pre() { Caffe::set_phase(Caffe::TRAIN); PreSolve(); iter_ = 0; }
+  // the body of Solver::Solve's loop (solver.cpp:195-220) without display / snapshot / test
+  float step() {
+    vector<Blob<float>*> bottom_vec;
+    const float loss = net_->ForwardBackward(bottom_vec);
+    ComputeUpdateValue();
+    net_->Update();
+    ++iter_;
+    return loss;
+  }
+  vector<shared_ptr<Blob<float> > >& hist() { return history_; }
+};
+struct RefSolver { FakeDb db; std::unique_ptr<StepSolver> solver; };
+LayerParameter* add_layer(NetParameter* np, const char* name, LayerParameter_LayerType type,
+                          const std::vector<std::string>& bottoms, const std::vector<std::string>& tops) {
+  LayerParameter* l = np->add_layers();
+  l->set_name(name); l->set_type(type);
+  for (const auto& b : bottoms) l->add_bottom(b);
+  for (const auto& t : tops) l->add_top(t);
+  return l;
+}
+std::string nm(const char* fmt, int i) { char buf[96]; snprintf(buf, sizeof(buf), fmt, i); return buf; }
+}  // namespace
+
+extern "C" {
+// lr_policy: 0 fixed, 1 inv, 2 step.  Parity runs pass dropout_ratio = 0 (no dropout layer: its mask comes from boost's
+// generator in the reference; DropoutLayer itself is pinned at the layer level).  Call ref_srand(seed) first (the data layer's rand()).
+REF_API void* ref_solver_create(int V, int K, const int* video_id, const int* shot_off, const int* shot_ids, const float* feat,
+                                int B, int C, int Nn, int N, int max_buffer_size, int negative_swap_percentage,
+                                int max_same_video_negs, int context_type, float margin, int norm,
+                                float base_lr, float momentum, float weight_decay, int lr_policy, float gamma, float power,
+                                int stepsize, const float* W0, const float* b0, float dropout_ratio) {
+  try {
+    Caffe::set_mode(Caffe::CPU);
+    Caffe::set_phase(Caffe::TRAIN);
+    RefSolver* s = new RefSolver();
+    for (int v = 0; v < V; ++v) {
+      std::shared_ptr<VideoShots> rec(new VideoShots());
+      rec->set_video_id(video_id[v]);
+      for (int g = shot_off[v]; g < shot_off[v + 1]; ++g) {
+        rec->add_shot_ids(shot_ids[g]);
+        Datum* d = rec->add_shot_words();
+        for (int k = 0; k < K; ++k) d->add_float_data(feat[size_t(g) * K + k]);
+      }
+      s->db.records.push_back(rec);
+    }
+    SolverParameter sp;
+    sp.set_base_lr(base_lr); sp.set_momentum(momentum); sp.set_weight_decay(weight_decay);
+    sp.set_lr_policy(lr_policy == 1 ? "inv" : lr_policy == 2 ? "step" : "fixed");
+    sp.set_gamma(gamma); sp.set_power(power); sp.set_stepsize(stepsize);
+    sp.set_max_iter(1 << 30); sp.set_display(0); sp.set_snapshot(0); sp.set_snapshot_after_train(false);
+    sp.set_solver_mode(SolverParameter_SolverMode_CPU);
+    NetParameter* np = sp.mutable_net_param();
+    np->set_name("med_embedding");
+    typedef std::vector<std::string> SV;
+    LayerParameter* l = add_layer(np, "shot_windows", LayerParameter_LayerType_VIDEO_SAMPLED_SHOTS_DATA, {}, {"data"});
+    VideoSampledShotsDataParameter* vp = l->mutable_video_sampled_shots_data_param();
+    vp->set_source("mem://fake-lmdb"); vp->set_backend(VideoSampledShotsDataParameter_DB_LMDB);
+    vp->set_batch_size(B); vp->set_context_size(C); vp->set_num_negative_samples(Nn);
+    vp->set_max_buffer_size(max_buffer_size); vp->set_negative_swap_percentage(negative_swap_percentage);
+    vp->set_max_same_video_negs(max_same_video_negs);
+    vp->set_context_type(VideoSampledShotsDataParameter_CONTEXT(context_type));
+    SV raw{"target"}, ctx_e, neg_e, neg_n;
+    for (int i = 1; i < C; ++i) { raw.push_back(nm("context_window_%d", i)); ctx_e.push_back(nm("context_window_emb_%d_nonorm", i)); }
+    for (int k = 1; k <= Nn; ++k) { raw.push_back(nm("negative_%d", k)); neg_e.push_back(nm("negative_emb_%d", k)); neg_n.push_back(nm("negative_emb_%d_nonorm", k)); }
+    add_layer(np, "slice_input_data", LayerParameter_LayerType_SLICE, {"data"}, raw)->mutable_slice_param()->set_slice_dim(1);
+    add_layer(np, "batch_concat_input", LayerParameter_LayerType_CONCAT, raw, {"batch_concat"})->mutable_concat_param()->set_concat_dim(0);
+    add_layer(np, "flatten_input", LayerParameter_LayerType_FLATTEN, {"batch_concat"}, {"original_feature"});
+    l = add_layer(np, "fc7", LayerParameter_LayerType_INNER_PRODUCT, {"original_feature"}, {"ip1_nonorm"});
+    l->add_blobs_lr(1); l->add_blobs_lr(2); l->add_weight_decay(1); l->add_weight_decay(0);
+    l->mutable_inner_product_param()->set_num_output(N);
+    l->mutable_inner_product_param()->mutable_weight_filler()->set_type("constant");
+    l->mutable_inner_product_param()->mutable_bias_filler()->set_type("constant");
+    add_layer(np, "fc7_relu", LayerParameter_LayerType_RELU, {"ip1_nonorm"}, {"ip2"});
+    if (dropout_ratio > 0.f)      // timing runs only: the mask comes from the shim's stand-in for boost's generator
+      add_layer(np, "drop2", LayerParameter_LayerType_DROPOUT, {"ip2"}, {"ip2"})->mutable_dropout_param()->set_dropout_ratio(dropout_ratio);
+    SV emb{"target_emb_nonorm"}; emb.insert(emb.end(), ctx_e.begin(), ctx_e.end()); emb.insert(emb.end(), neg_n.begin(), neg_n.end());
+    add_layer(np, "slice_emb", LayerParameter_LayerType_SLICE, {"ip2"}, emb)->mutable_slice_param()->set_slice_dim(0);
+    l = add_layer(np, "context_average", LayerParameter_LayerType_ELTWISE, ctx_e, {"context_feature_nonorm"});
+    l->mutable_eltwise_param()->set_operation(EltwiseParameter_EltwiseOp_SUM);
+    for (int i = 1; i < C; ++i) l->mutable_eltwise_param()->add_coeff(1.0f / float(C - 1));
+    add_layer(np, "word_embedding_norm", LayerParameter_LayerType_NORMALIZATION, {"context_feature_nonorm"}, {"context_feature"});
+    SV pn{"target_emb_nonorm"}; pn.insert(pn.end(), neg_n.begin(), neg_n.end());
+    add_layer(np, "concat_pos_neg_nonorm", LayerParameter_LayerType_CONCAT, pn, {"pos_neg_nonorm"})->mutable_concat_param()->set_concat_dim(0);
+    add_layer(np, "pos_neg_normalize", LayerParameter_LayerType_NORMALIZATION, {"pos_neg_nonorm"}, {"pos_neg_norm"});
+    SV pe{"target_emb"}; pe.insert(pe.end(), neg_e.begin(), neg_e.end());
+    add_layer(np, "slice_pos_neg_norm", LayerParameter_LayerType_SLICE, {"pos_neg_norm"}, pe)->mutable_slice_param()->set_slice_dim(0);
+    add_layer(np, "prod_true", LayerParameter_LayerType_ELTWISE, {"context_feature", "target_emb"}, {"target_prod"})
+        ->mutable_eltwise_param()->set_operation(EltwiseParameter_EltwiseOp_PROD);
+    add_layer(np, "sum_true", LayerParameter_LayerType_SUM, {"target_prod"}, {"target_score"})->mutable_sum_param()->set_num_output(Nn);
+    SV nsc;
+    for (int k = 1; k <= Nn; ++k) {
+      add_layer(np, nm("prod_neg_%d", k).c_str(), LayerParameter_LayerType_ELTWISE, {"context_feature", nm("negative_emb_%d", k)},
+                {nm("negative_emb_%d_prod", k)})->mutable_eltwise_param()->set_operation(EltwiseParameter_EltwiseOp_PROD);
+      add_layer(np, nm("sum_neg_%d", k).c_str(), LayerParameter_LayerType_SUM, {nm("negative_emb_%d_prod", k)}, {nm("neg_score_%d", k)});
+      nsc.push_back(nm("neg_score_%d", k));
+    }
+    add_layer(np, "concat_negative_scores", LayerParameter_LayerType_CONCAT, nsc, {"negative_score"})->mutable_concat_param()->set_concat_dim(1);
+    l = add_layer(np, "max_margin_loss", LayerParameter_LayerType_MAX_MARGIN_LOSS, {"target_score", "negative_score"},
+                  {"loss_output", "train_violations"});
+    l->add_loss_weight(1); l->add_loss_weight(0);
+    l->mutable_max_margin_loss_param()->set_margin(margin);
+    l->mutable_max_margin_loss_param()->set_norm(norm == 2 ? MaxMarginLossParameter_Norm_L2 : MaxMarginLossParameter_Norm_L1);
+    g_fake_db = &s->db;
+    s->solver.reset(new StepSolver(sp));           // Solver::Init -> Net::Init -> every layer's SetUp (data layer: buffer init)
+    g_fake_db = nullptr;
+    s->solver->pre();
+    const vector<shared_ptr<Blob<float> > >& params = s->solver->net()->params();
+    if (params.size() != 2) { fprintf(stderr, "ref_driver: expected 2 parameter blobs, got %d\n", int(params.size())); delete s; return nullptr; }
+    memcpy(params[0]->mutable_cpu_data(), W0, sizeof(float) * size_t(N) * K);
+    memcpy(params[1]->mutable_cpu_data(), b0, sizeof(float) * N);
+    return s;
+  } catch (const std::exception& e) { fprintf(stderr, "ref_driver: %s\n", e.what()); return nullptr; }
+}
+REF_API int ref_solver_step(void* h, float* loss, float* violations) {
+  try {
+    RefSolver* s = static_cast<RefSolver*>(h);
+    *loss = s->solver->step();
+    if (violations) *violations = s->solver->net()->blob_by_name("train_violations")->cpu_data()[0];
+    return 0;
+  } catch (const std::exception& e) { fprintf(stderr, "ref_driver: %s\n", e.what()); return -1; }
+}
+// W [N,K], b [N], their momentum histories, and the data blob [B,R,K] of the last step (any may be NULL)
+REF_API int ref_solver_get(void* h, float* W, float* b, float* hW, float* hb, float* data) {
+  try {
+    RefSolver* s = static_cast<RefSolver*>(h);
+    const vector<shared_ptr<Blob<float> > >& params = s->solver->net()->params();
+    if (W) memcpy(W, params[0]->cpu_data(), sizeof(float) * params[0]->count());
+    if (b) memcpy(b, params[1]->cpu_data(), sizeof(float) * params[1]->count());
+    if (hW) memcpy(hW, s->solver->hist()[0]->cpu_data(), sizeof(float) * params[0]->count());
+    if (hb) memcpy(hb, s->solver->hist()[1]->cpu_data(), sizeof(float) * params[1]->count());
+    if (data) { const shared_ptr<Blob<float> > d = s->solver->net()->blob_by_name("data"); memcpy(data, d->cpu_data(), sizeof(float) * d->count()); }
+    return 0;
+  } catch (const std::exception& e) { fprintf(stderr, "ref_driver: %s\n", e.what()); return -1; }
+}
+REF_API int ref_solver_num_layers(void* h) { return int(static_cast<RefSolver*>(h)->solver->net()->layers().size()); }
+REF_API const char* ref_solver_layer_name(void* h, int i) { return static_cast<RefSolver*>(h)->solver->net()->layer_names()[i].c_str(); }
+REF_API void ref_solver_destroy(void* h) { delete static_cast<RefSolver*>(h); }
 }  // extern "C"

@@ -93,3 +93,25 @@ for name, mode, C, Nn, max_same in CASES:
     r.close()
 np.savez_compressed(os.path.join(OUT, "sampler_ref.npz"), **samp)
 print("sampler_ref.npz written:", [k for k in samp if k.startswith("blobs_")])
+
+
+# The whole reference training pipeline: VideoSampledShotsDataLayer + Net (net.cpp, insert_splits.cpp) + SGDSolver
+# (solver.cpp), compiled unmodified, 8 iterations of Solver::Solve's loop body on the shipped TRAIN graph (no dropout).
+# Pins the trajectory: per-iteration loss / violations, final weights, bias and momentum histories.
+rng = np.random.RandomState(91)
+V = 64; counts = rng.randint(8, 22, V)
+t_vid = (rng.permutation(V) + 40).astype(np.int32); t_off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+t_sid = np.concatenate([np.sort(rng.choice(100, c, replace=False)) for c in counts]).astype(np.int32)
+TK, TN, TB = 128, 64, 16
+t_feat = np.maximum(rng.normal(0, 1, (t_off[-1], TK)), 0).astype(np.float32)
+t_W0 = rng.normal(0, 0.03, (TN, TK)).astype(np.float32); t_b0 = rng.normal(0, 0.01, TN).astype(np.float32)
+hyper = dict(base_lr=0.05, momentum=0.9, weight_decay=5e-4, lr_policy="inv", gamma=1e-3, power=0.75)
+sol = pyref.Solver(t_vid, t_off, t_sid, t_feat, t_W0, t_b0, TB, 5, 10, 60, 50, 6, **hyper)
+layer_names = sol.layer_names()
+traj = [sol.step() for _ in range(8)]
+st = sol.state(); sol.close()
+np.savez_compressed(os.path.join(OUT, "solver_ref.npz"), vid=t_vid, off=t_off, sid=t_sid, feat=t_feat, W0=t_W0, b0=t_b0,
+                    cfg=np.array([TB, 5, 10, 60, 50, 6], np.int32), hyper=np.array([0.05, 0.9, 5e-4, 1e-3, 0.75], np.float64),
+                    loss=np.array([t[0] for t in traj], np.float32), violations=np.array([t[1] for t in traj], np.float32),
+                    W=st["W"], b=st["b"], hW=st["hW"], hb=st["hb"], layer_names=np.array(layer_names))
+print("solver_ref.npz written: losses", [round(t[0], 5) for t in traj])

@@ -87,3 +87,46 @@ def test_oracle_reproduces_reference_eval_layers(oracle):
         assert abs(o["map"] - ref[0]) < 1e-6 and abs(o["hit1"] - ref[1]) < 1e-6 and abs(o["hit5"] - ref[2]) < 1e-6, (excl, o, ref)
     assert np.array_equal(oracle.id_lookup_forward(g["id_table"], g["id_ids"]), g["id_top"])
     assert np.array_equal(oracle.id_lookup_backward(g["id_tdiff"], g["id_ids"], g["id_table"].shape[0]), g["id_tgrad"])
+
+
+def test_oracle_reproduces_reference_solver_trajectory(oracle):
+    """tests/golden/solver_ref.npz: 8 iterations of the REFERENCE's whole pipeline -- its data layer, Net (net.cpp,
+    insert_splits.cpp) and SGDSolver (solver.cpp), compiled unmodified in oracle/_ref (make_golden.py).  The oracle's
+    sampler + net + solver-update restatements must follow the same trajectory; where oracle/_ref exists the reference is
+    also run live with another policy / norm."""
+    g = np.load(os.path.join(GOLD, "solver_ref.npz"))
+    B, C, Nn, P, swap, max_same = [int(x) for x in g["cfg"]]
+    base_lr, mom, wd, gamma, power = [float(x) for x in g["hyper"]]
+    K = g["feat"].shape[1]
+
+    def run(vid, off, sid, feat, W0, b0, steps, policy, norm, stepsize=1):
+        smp = oracle.Sampler(vid, off, sid, feat, K, B, C, Nn, P, swap, max_same, 100, seed=1)
+        W, b = W0.copy(), b0.copy(); hW = np.zeros_like(W); hb = np.zeros_like(b)
+        out = []
+        for it in range(steps):
+            data = smp.next()[2]
+            r = oracle.net_forward_backward(data, W, b, None, B, C, Nn, margin=2.0, norm=norm, dropout_ratio=0.0)
+            rate = oracle.learning_rate(policy, base_lr, gamma, power, stepsize, it)
+            W, _, hW = oracle.sgd_update(W, r["dW"], hW, rate * 1.0, mom, wd * 1.0)      # blobs_lr 1 / 2, weight_decay 1 / 0
+            b, _, hb = oracle.sgd_update(b, r["db"], hb, rate * 2.0, mom, 0.0)
+            out.append((float(r["loss"][0]), float(r["violations"][0])))
+        smp.close()
+        return out, dict(W=W, b=b, hW=hW, hb=hb)
+
+    traj, st = run(g["vid"], g["off"], g["sid"], g["feat"], g["W0"], g["b0"], len(g["loss"]), "inv", 2)
+    for it, (loss, viol) in enumerate(traj):
+        assert abs(loss - g["loss"][it]) < 1e-5 * max(1, abs(g["loss"][it])) and viol == g["violations"][it], it
+    for k in ("W", "b", "hW", "hb"):
+        assert rel(st[k], g[k]) < 1e-5, k
+    from oracle import pyref
+    if pyref.available():
+        gamma, power = 0.5, 0.0          # "step": rate = base_lr * gamma^(iter / stepsize)
+        ref = pyref.Solver(g["vid"], g["off"], g["sid"], g["feat"], g["W0"], g["b0"], B, C, Nn, P, swap, max_same, norm=1,
+                           base_lr=base_lr, momentum=mom, weight_decay=wd, lr_policy="step", gamma=gamma, power=power, stepsize=2)
+        rt = [ref.step() for _ in range(5)]
+        rs = ref.state(); ref.close()
+        traj, st = run(g["vid"], g["off"], g["sid"], g["feat"], g["W0"], g["b0"], 5, "step", 1, stepsize=2)
+        for it in range(5):
+            assert abs(traj[it][0] - rt[it][0]) < 1e-5 * max(1, abs(rt[it][0])) and traj[it][1] == rt[it][1], it
+        for k in ("W", "b", "hW", "hb"):
+            assert rel(st[k], rs[k]) < 1e-5, k

@@ -77,3 +77,58 @@ def test_device_eval_kernels_reproduce_reference_fixtures():
     assert np.array_equal(top.cpu().numpy(), g["id_top"])
     d = ops.id_lookup_backward(torch.as_tensor(g["id_tdiff"]).cuda(), torch.as_tensor(g["id_ids"]).cuda(), g["id_table"].shape[0])
     assert np.array_equal(d.cpu().numpy(), g["id_tgrad"])
+
+
+def _solver_fixture():
+    g = np.load(os.path.join(GOLD, "solver_ref.npz"))
+    B, C, Nn, P, swap, max_same = [int(x) for x in g["cfg"]]
+    base_lr, mom, wd, gamma, power = [float(x) for x in g["hyper"]]
+    return g, (B, C, Nn, P, swap, max_same), dict(base_lr=base_lr, momentum=mom, weight_decay=wd, gamma=gamma, power=power, lr_policy="inv")
+
+
+@pytest.mark.parametrize("prec,fused_gather", [("fp32_simt", False), ("tf32x3", False), ("f16x3", False), ("f16x3", True)])
+def test_trainer_follows_reference_solver_trajectory(prec, fused_gather):
+    """tests/golden/solver_ref.npz = the REFERENCE's whole pipeline (its data layer + Net + SGDSolver, compiled unmodified)
+    over 8 iterations.  The product -- host sampler + fused trainer step on the device -- must follow it: loss (1e-5) and
+    violation count (exact) every iteration, weights, bias and both momentum histories at the end (1e-5)."""
+    g, (B, C, Nn, P, swap, max_same), hyper = _solver_fixture()
+    N, K = g["W0"].shape
+    bank = torch.as_tensor(g["feat"]).cuda()
+    smp = ops.Sampler(g["vid"], g["off"], g["sid"], B, C, Nn, P, swap, max_same, 100, rand_seed=1)
+    tr = ops.Trainer(ops.trainer_cfg(B, C, Nn, K, N, dropout_ratio=0.0, prec=prec, **hyper))
+    tr.set_weights(torch.as_tensor(g["W0"]).cuda(), torch.as_tensor(g["b0"]).cuda())
+    if fused_gather:
+        tr.set_bank(bank)
+    for it in range(len(g["loss"])):
+        idx, quirk = smp.next()
+        tr.step(bank, torch.as_tensor(idx).cuda(), torch.as_tensor(quirk).cuda(), None, it=it)
+        assert abs(tr.tensor("loss").item() - g["loss"][it]) < 1e-5 * max(1, abs(g["loss"][it])), it
+        assert tr.tensor("violations").item() == g["violations"][it], it
+    for name, key in (("W", "W"), ("b", "b"), ("W_hist", "hW"), ("b_hist", "hb")):
+        assert rel(tr.tensor(name), g[key]) < 1e-5, name
+    tr.close(); smp.close()
+
+
+@pytest.mark.parametrize("fuse", [False, True])
+def test_caffe_host_solver_follows_reference_solver_trajectory(tmp_path, monkeypatch, fuse):
+    """The same fixture through the drop-in boundary end to end: VideoShots records (protobuf wire bytes) -> the compat
+    data layer -> Net built from the prototxt -> SGDSolver, layer by layer and fused.  The net must also contain the
+    layers (names, order, the inserted split) the reference's Net::Init produced."""
+    import records_util
+    from videovector_b200 import caffe_host, prototxt
+    g, (B, C, Nn, P, swap, max_same), hyper = _solver_fixture()
+    N, K = g["W0"].shape
+    src = records_util.write_vvrs(tmp_path / "train.vvrs", records_util.video_shots_records(g["vid"], g["off"], g["sid"], g["feat"]))
+    monkeypatch.setenv("VV_FUSE", "1" if fuse else "0")
+    caffe_host.set_device(0); caffe_host.set_precision("f16x3")
+    net_txt = prototxt.train_net(B=B, C=C, Nn=Nn, K=K, N=N, dropout=0, max_buffer_size=P, swap=swap, max_same=max_same, source=src)
+    sol = caffe_host.Solver(prototxt.solver(base_lr=hyper["base_lr"], momentum=hyper["momentum"], weight_decay=hyper["weight_decay"],
+                                            gamma=hyper["gamma"], power=hyper["power"], display=0, snapshot=0), net_txt)
+    assert sol.net.layer_names == [str(x) for x in g["layer_names"]]
+    sol.net.set_param(0, g["W0"]); sol.net.set_param(1, g["b0"])
+    for it in range(len(g["loss"])):
+        loss = sol.step()
+        assert abs(loss - g["loss"][it]) < 1e-5 * max(1, abs(g["loss"][it])), it
+    assert rel(sol.net.param(0), g["W"].reshape(-1)) < 1e-5 and rel(sol.net.param(1), g["b"]) < 1e-5
+    assert rel(sol.history(0), g["hW"].reshape(-1)) < 1e-5 and rel(sol.history(1), g["hb"]) < 1e-5
+    sol.close()
