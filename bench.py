@@ -28,8 +28,9 @@ CFG = dict(C=5, Nn=10, K=4096, N=512, B=4096, V=8192, S=32, P=5000, swap=50, max
 CPU_SAMPLE_B = 256          # bounded CPU sample: items per oracle step (same K, N, C, Nn)
 METRIC = "training triplets/sec"
 CPU_NOTE = {
-    "reference": "layers = the reference's own src/caffe/layers/*.cpp compiled unmodified against shim headers (oracle/_ref, "
-                 "Caffe CPU mode, OpenBLAS from the SciPy wheel); sampler and solver update = oracle restatements",
+    "reference": "the reference's own sources compiled unmodified against shim headers (oracle/_ref): its "
+                 "VideoSampledShotsDataLayer (prefetch thread, in-memory fake LMDB), Net (net.cpp) and SGDSolver (solver.cpp) "
+                 "in Caffe CPU mode, OpenBLAS from the SciPy wheel; one step = one iteration of Solver::Solve's loop",
     "port": "oracle/vv_oracle.cpp = restated reference CPU layers + solver + sampler, OpenBLAS from the SciPy wheel "
             "(oracle/_ref was not built on this machine)"}
 
@@ -99,11 +100,10 @@ class ClockSampler:
 # CPU baseline / reference arm: the oracle (port of the reference's CPU layers) on the host cores
 # ---------------------------------------------------------------------------------------------------
 def cpu_reference_run(steps, warmup, threads=0):
-    """One 'step' = sampler (materialising the data blob) + whole-net forward/backward + SGD update on a bounded
-    sample of CPU_SAMPLE_B items of the workload, on the host cores.  The layers run through oracle/_ref (the
-    reference's own layer sources, shim-compiled) when that library exists -- kind "reference" -- else through the
-    oracle port; the sampler and the solver update are the oracle's restatements in both cases (the reference's
-    data layer and solver.cpp need LMDB / protobuf).  Returns (triplets/s, ms/step, cores, phase dict, kind)."""
+    """One 'step' = one training iteration on a bounded sample of CPU_SAMPLE_B items of the workload, on the host cores.
+    With oracle/_ref (the reference's own data layer, Net and SGDSolver sources, shim-compiled) it is one iteration of the
+    reference's Solver::Solve loop -- kind "reference"; without it the oracle port runs sampler + net + update.
+    Returns (triplets/s, ms/step, cores, phase dict, kind)."""
     from oracle import pyoracle as orc
     from oracle import pyref
     from videovector_b200 import ops
@@ -113,10 +113,27 @@ def cpu_reference_run(steps, warmup, threads=0):
     if threads <= 0:                                     # every host core this process may use, whatever OMP_NUM_THREADS says
         threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     cores = orc.use_openblas(threads)                    # same OpenBLAS instance the reference library links
-    use_ref = pyref.available()
+    use_ref = pyref.available() and hasattr(pyref.lib(), "ref_solver_create")
     feat = ops.bank_host(V * S, c["K"], 1234)
     vid, off, sid = ops.synthetic_videos(V, S)
-    smp = orc.Sampler(vid, off, sid, feat, c["K"], B, c["C"], c["Nn"], c["P"], c["swap"], c["max_same"], 100, seed=1)
+    if use_ref:
+        # the reference's whole pipeline: data layer (its own prefetch thread) + Net + SGDSolver, shipped hyper-parameters
+        rng = np.random.RandomState(1701)
+        W = rng.normal(0, 0.001, (c["N"], c["K"])).astype(np.float32)
+        sol = pyref.Solver(vid, off, sid, feat, W, np.zeros(c["N"], np.float32), B, c["C"], c["Nn"], c["P"], c["swap"],
+                           c["max_same"], margin=2.0, norm=2, base_lr=1e-3, momentum=0.9, weight_decay=5e-4, lr_policy="inv",
+                           gamma=1e-3, power=0.75, dropout_ratio=0.9)
+        times = []
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            loss, _ = sol.step()
+            if it >= warmup:
+                times.append(time.perf_counter() - t0)
+        sol.close()
+        orc.use_builtin_blas()
+        ms = 1e3 * float(np.mean(times))
+        return B / (ms * 1e-3), ms, cores, {"solver_step": ms, "last_loss": loss}, "reference"
+    smp = orc.Sampler(vid, off, sid, feat, c["K"], B, c["C"], c["Nn"], c["P"], c["swap"], c["max_same"], 100, seed=1)   # port
     rng = np.random.RandomState(1701)
     W = rng.normal(0, 0.001, (c["N"], c["K"])).astype(np.float32)
     b = np.zeros(c["N"], np.float32)
@@ -125,36 +142,27 @@ def cpu_reference_run(steps, warmup, threads=0):
     mrng = np.random.RandomState(7)
     times, phases = [], np.zeros(8)
     for it in range(warmup + steps):
-        mask = None if use_ref else (mrng.uniform(0, 1, (R * B, c["N"])) > 0.9).astype(np.uint32)   # mask generation not timed
+        mask = (mrng.uniform(0, 1, (R * B, c["N"])) > 0.9).astype(np.uint32)   # mask generation not timed
         t0 = time.perf_counter()
         idx, quirk, data = smp.next()
         t1 = time.perf_counter()
-        if use_ref:
-            out = pyref.net_forward_backward(data, W, b, B, c["C"], c["Nn"], margin=2.0, norm=2, dropout_ratio=0.9, seed=it)
-            net_s = float(out["seconds"][1] + out["seconds"][2])      # Forward + Backward of the built net (setup excluded)
-        else:
-            out = orc.net_forward_backward(data, W, b, mask, B, c["C"], c["Nn"], margin=2.0, norm=2, dropout_ratio=0.9,
-                                           want=("loss", "violations", "dW", "db"))
-            net_s = None
+        out = orc.net_forward_backward(data, W, b, mask, B, c["C"], c["Nn"], margin=2.0, norm=2, dropout_ratio=0.9,
+                                       want=("loss", "violations", "dW", "db"))
         t2 = time.perf_counter()
         rate = orc.learning_rate("inv", 1e-3, 1e-3, 0.75, 1, it)
         W, _, hW = orc.sgd_update(W, out["dW"], hW, rate, 0.9, 5e-4)
         b, _, hb = orc.sgd_update(b, out["db"], hb, rate * 2, 0.9, 0.0)
         t3 = time.perf_counter()
         if it >= warmup:
-            step_s = (t1 - t0) + (net_s if net_s is not None else (t2 - t1)) + (t3 - t2)
-            times.append(step_s)
-            if use_ref:
-                phases[1] += out["seconds"][1]; phases[3] += out["seconds"][2]
-            else:
-                phases[:5] += out["phase_seconds"][:5]
+            times.append(t3 - t0)
+            phases[:5] += out["phase_seconds"][:5]
             phases[5] += t1 - t0; phases[6] += t3 - t2
     smp.close()
     orc.use_builtin_blas()
     ms = 1e3 * float(np.mean(times))
     names = ["slice_concat", "forward", "loss_forward", "backward", "fc7_backward", "sampler", "sgd_update"]
     ph = {k: 1e3 * phases[i] / len(times) for i, k in enumerate(names) if phases[i] > 0}
-    return B / (ms * 1e-3), ms, cores, ph, ("reference" if use_ref else "port")
+    return B / (ms * 1e-3), ms, cores, ph, "port"
 
 
 def run_reference(args):
