@@ -161,7 +161,9 @@ class Solver:
     def __init__(self, video_id, shot_off, shot_ids, feat, W0, b0, batch_size, context_size=5, num_negative_samples=10,
                  max_buffer_size=5000, negative_swap_percentage=50, max_same_video_negs=6, context_type=1, margin=2.0,
                  norm=2, base_lr=0.001, momentum=0.9, weight_decay=0.0005, lr_policy="inv", gamma=0.001, power=0.75,
-                 stepsize=1, seed=1, dropout_ratio=0.0):
+                 stepsize=1, seed=1, dropout_ratio=0.0, test=None):
+        """test = dict(data=[n, frames, K], video_id=[n], batch=.., id_to_class_file=path, exclude_same=True): adds the shipped
+        file's TEST-phase graph (TestVideoShotWindows records on a second fake LMDB); see test()."""
         L = lib()
         L.ref_solver_create.restype = C.c_void_p
         L.ref_solver_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -176,11 +178,23 @@ class Solver:
         self.B, self.R = batch_size, context_size + num_negative_samples
         L.ref_srand(C.c_uint(seed))
         fl = C.c_float
+        if test:
+            self.tdata = f32(test["data"]); self.tvid = np.ascontiguousarray(test["video_id"], np.int32)
+            n, frames, tk = self.tdata.shape
+            assert tk == self.K
+            targs = (n, frames, _p(self.tdata), _p(self.tvid), int(test["batch"]), str(test["id_to_class_file"]).encode(),
+                     int(test.get("exclude_same", True)))
+        else:
+            targs = (0, 0, None, None, 0, None, 0)
+        L.ref_solver_test.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.ref_solver_test_num_layers.argtypes = [C.c_void_p]
+        L.ref_solver_test_layer_name.argtypes = [C.c_void_p, C.c_int]; L.ref_solver_test_layer_name.restype = C.c_char_p
+        L.ref_solver_test_output_name.argtypes = [C.c_void_p, C.c_int]; L.ref_solver_test_output_name.restype = C.c_char_p
         self._h = L.ref_solver_create(len(self.vid), self.K, _p(self.vid), _p(self.off), _p(self.sid), _p(self.feat), batch_size,
                                       context_size, num_negative_samples, self.N, max_buffer_size, negative_swap_percentage,
                                       max_same_video_negs, context_type, fl(margin), norm, fl(base_lr), fl(momentum),
                                       fl(weight_decay), self.POLICY[lr_policy], fl(gamma), fl(power), stepsize, _p(W0), _p(b0),
-                                      fl(dropout_ratio))
+                                      fl(dropout_ratio), *targs)
         if not self._h:
             raise RuntimeError("reference solver failed to set up")
 
@@ -198,6 +212,19 @@ class Solver:
 
     def layer_names(self):
         return [lib().ref_solver_layer_name(self._h, i).decode() for i in range(lib().ref_solver_num_layers(self._h))]
+
+    def test(self, iters):
+        """Solver::Test's loop on the TEST net (weights shared with the TRAIN net): mean (mAP, hit@1, hit@5) over iters."""
+        out = np.zeros(3, np.float32)
+        assert lib().ref_solver_test(self._h, iters, _p(out)) == 0
+        return out
+
+    def test_output_names(self):
+        """in the order the reference's Net reports its outputs (Net::Init's std::set of blob names: lexicographic)"""
+        return [lib().ref_solver_test_output_name(self._h, j).decode() for j in range(3)]
+
+    def test_layer_names(self):
+        return [lib().ref_solver_test_layer_name(self._h, i).decode() for i in range(lib().ref_solver_test_num_layers(self._h))]
 
     def close(self):
         if self._h:

@@ -83,8 +83,10 @@ def gen(proto_text, package):
     for name in messages:
         out.append("class %s;" % name)
     # messages in dependency-safe form: message fields are held through std::shared_ptr, so order is free
+    merges = {}
     for name, fields in messages.items():
-        pub, priv, clear, copy = [], [], [], []
+        pub, priv, clear, copy, merge = [], [], [], [], []
+        merges[name] = merge
         for f in fields:
             if f[0] == "__enum__":
                 _, short, full, vals = f
@@ -106,6 +108,7 @@ def gen(proto_text, package):
                             "  %s* add_%s();" % (ctype, fname),
                             "  void clear_%s() { %s_.clear(); }" % (fname, fname)]
                     priv.append("  std::vector<std::shared_ptr<%s> > %s_;" % (ctype, fname))
+                    merge.append("  for (const auto& p : o.%s_) add_%s()->MergeFrom(*p);" % (fname, fname))
                 else:
                     arg = "const std::string&" if ctype == "std::string" else ctype
                     ret = "const std::string&" if ctype == "std::string" else ctype
@@ -117,6 +120,7 @@ def gen(proto_text, package):
                             "  const ::google::protobuf::RepeatedField<%s>& %s() const { return %s_; }" % (ctype, fname, fname),
                             "  ::google::protobuf::RepeatedField<%s>* mutable_%s() { return &%s_; }" % (ctype, fname, fname)]
                     priv.append("  ::google::protobuf::RepeatedField<%s> %s_;" % (ctype, fname))
+                    merge.append("  %s_.insert(%s_.end(), o.%s_.begin(), o.%s_.end());" % (fname, fname, fname, fname))
                 clear.append("    %s_.clear();" % fname)
                 continue
             if is_msg:
@@ -126,6 +130,7 @@ def gen(proto_text, package):
                         "  void clear_%s() { %s_.reset(); }" % (fname, fname)]
                 priv.append("  std::shared_ptr<%s> %s_;" % (ctype, fname))
                 clear.append("    %s_.reset();" % fname)
+                merge.append("  if (o.%s_) mutable_%s()->MergeFrom(*o.%s_);" % (fname, fname, fname))
                 continue
             if dflt is None:
                 d = '""' if ctype == "std::string" else ("%s(0)" % ctype)
@@ -152,9 +157,12 @@ def gen(proto_text, package):
                     "  void clear_%s() { %s_ = %s; has_%s_ = false; }" % (fname, fname, d, fname)]
             priv += ["  %s %s_ = %s;" % (ctype, fname, d), "  bool has_%s_ = false;" % fname]
             clear.append("    clear_%s();" % fname)
+            merge.append("  if (o.has_%s_) { %s_ = o.%s_; has_%s_ = true; }" % (fname, fname, fname, fname))
         out.append("class %s : public ::google::protobuf::Message {\n public:\n  %s() {}\n" % (name, name) + "\n".join(pub) +
                    "\n  void Clear() {\n" + "\n".join(clear) + "\n  }\n"
-                   "  void CopyFrom(const %s& o) { *this = o; }\n  void MergeFrom(const %s& o) { *this = o; }\n"
+                   "  // protobuf semantics: MergeFrom takes the fields that are set in o (repeated fields append, sub-messages merge\n"
+                   "  // recursively); CopyFrom is a deep copy.  operator= stays the shallow member-wise copy (sub-messages shared)\n"
+                   "  void MergeFrom(const %s& o);\n  void CopyFrom(const %s& o) { if (&o == this) return; Clear(); MergeFrom(o); }\n"
                    "  std::string DebugString() const { return \"<%s>\"; }\n"
                    "  bool ParseFromString(const std::string&) { return false; }\n"
                    "  // no wire format in the shim: the in-memory fake LMDB of ref_driver.cpp hands out a pointer to a live message\n"
@@ -164,6 +172,8 @@ def gen(proto_text, package):
                    "  static const %s& default_instance() { static %s d; return d; }\n private:\n" % (name, name, name, name, name, name) +
                    "\n".join(priv) + "\n};")
     # out-of-line bodies that need complete types
+    for name in messages:
+        out.append("inline void %s::MergeFrom(const %s& o) {\n%s\n}" % (name, name, "\n".join(merges[name])))
     for name, fields in messages.items():
         for f in fields:
             if f[0] == "__enum__":

@@ -268,7 +268,8 @@ namespace {
 typedef video_shot_sentences::VideoShots VideoShots;
 typedef video_shot_sentences::TestVideoShotWindows TestVideoShotWindows;
 struct FakeDb { std::vector<std::shared_ptr<void> > records; };      // live VideoShots / TestVideoShotWindows messages
-FakeDb* g_fake_db = nullptr;          // the dataset the next mdb_env_open serves
+FakeDb* g_fake_db = nullptr;          // the dataset the next mdb_env_open serves ...
+FakeDb* g_fake_db_test = nullptr;     // ... unless the source names the TEST database
 }  // namespace
 struct MDB_env { FakeDb* db; };
 struct MDB_txn { MDB_env* env; };
@@ -276,7 +277,10 @@ struct MDB_cursor { FakeDb* db; size_t pos; };
 extern "C" {
 int mdb_env_create(MDB_env** env) { *env = new MDB_env{nullptr}; return MDB_SUCCESS; }
 int mdb_env_set_mapsize(MDB_env*, size_t) { return MDB_SUCCESS; }
-int mdb_env_open(MDB_env* env, const char*, unsigned int, mdb_mode_t) { env->db = g_fake_db; return env->db ? MDB_SUCCESS : -1; }
+int mdb_env_open(MDB_env* env, const char* path, unsigned int, mdb_mode_t) {
+  env->db = (path && strstr(path, "fake-lmdb-test")) ? g_fake_db_test : g_fake_db;
+  return env->db ? MDB_SUCCESS : -1;
+}
 int mdb_txn_begin(MDB_env* env, MDB_txn*, unsigned int, MDB_txn** txn) { *txn = new MDB_txn{env}; return MDB_SUCCESS; }
 int mdb_open(MDB_txn*, const char*, unsigned int, MDB_dbi* dbi) { *dbi = 1; return MDB_SUCCESS; }
 int mdb_cursor_open(MDB_txn* txn, MDB_dbi, MDB_cursor** cursor) { *cursor = new MDB_cursor{txn->env->db, 0}; return MDB_SUCCESS; }
@@ -431,6 +435,8 @@ Layer<Dtype>* GetLayer(const LayerParameter& param) {
     case LayerParameter_LayerType_SUM: return new SumLayer<Dtype>(param);
     case LayerParameter_LayerType_SPLIT: return new SplitLayer<Dtype>(param);
     case LayerParameter_LayerType_MAX_MARGIN_LOSS: return new MaxMarginLossLayer<Dtype>(param);
+    case LayerParameter_LayerType_VIDEO_SHOT_WINDOW_TEST_DATA: return new VideoShotWindowTestDataLayer<Dtype>(param);
+    case LayerParameter_LayerType_RETRIEVAL_STATS: return new RetrievalStatsLayer<Dtype>(param);
     default: LOG(FATAL) << "layer type " << param.type() << " is not part of the shim factory"; return NULL;
   }
 }
@@ -463,7 +469,8 @@ struct StepSolver : public SGDSolver<float> {
   }
   vector<shared_ptr<Blob<float> > >& hist() { return history_; }
 };
-struct RefSolver { FakeDb db; std::unique_ptr<StepSolver> solver; };
+struct RefSolver { FakeDb db, test_db; std::unique_ptr<StepSolver> solver; };
+void phase_rule(LayerParameter* l, Phase p) { l->add_include()->set_phase(p); }
 LayerParameter* add_layer(NetParameter* np, const char* name, LayerParameter_LayerType type,
                           const std::vector<std::string>& bottoms, const std::vector<std::string>& tops) {
   LayerParameter* l = np->add_layers();
@@ -482,7 +489,9 @@ REF_API void* ref_solver_create(int V, int K, const int* video_id, const int* sh
                                 int B, int C, int Nn, int N, int max_buffer_size, int negative_swap_percentage,
                                 int max_same_video_negs, int context_type, float margin, int norm,
                                 float base_lr, float momentum, float weight_decay, int lr_policy, float gamma, float power,
-                                int stepsize, const float* W0, const float* b0, float dropout_ratio) {
+                                int stepsize, const float* W0, const float* b0, float dropout_ratio,
+                                int n_test, int frames, const float* test_data /*[n_test, frames, K]*/, const int* test_video_id,
+                                int test_batch, const char* id_to_class_file, int exclude_same_video_shots) {
   try {
     Caffe::set_mode(Caffe::CPU);
     Caffe::set_phase(Caffe::TRAIN);
@@ -497,7 +506,18 @@ REF_API void* ref_solver_create(int V, int K, const int* video_id, const int* sh
       }
       s->db.records.push_back(rec);
     }
+    const bool with_test = n_test > 0 && test_data && id_to_class_file;
+    for (int i = 0; with_test && i < n_test; ++i) {
+      std::shared_ptr<TestVideoShotWindows> rec(new TestVideoShotWindows());
+      rec->set_video_id(test_video_id[i]);
+      for (int f = 0; f < frames; ++f) {
+        Datum* d = rec->add_context_shot_words();
+        for (int k = 0; k < K; ++k) d->add_float_data(test_data[(size_t(i) * frames + f) * K + k]);
+      }
+      s->test_db.records.push_back(rec);
+    }
     SolverParameter sp;
+    if (with_test) { sp.add_test_iter(1); sp.set_test_interval(1 << 30); sp.set_test_initialization(false); }
     sp.set_base_lr(base_lr); sp.set_momentum(momentum); sp.set_weight_decay(weight_decay);
     sp.set_lr_policy(lr_policy == 1 ? "inv" : lr_policy == 2 ? "step" : "fixed");
     sp.set_gamma(gamma); sp.set_power(power); sp.set_stepsize(stepsize);
@@ -506,6 +526,7 @@ REF_API void* ref_solver_create(int V, int K, const int* video_id, const int* sh
     NetParameter* np = sp.mutable_net_param();
     np->set_name("med_embedding");
     typedef std::vector<std::string> SV;
+    const size_t first_layer = 0;
     LayerParameter* l = add_layer(np, "shot_windows", LayerParameter_LayerType_VIDEO_SAMPLED_SHOTS_DATA, {}, {"data"});
     VideoSampledShotsDataParameter* vp = l->mutable_video_sampled_shots_data_param();
     vp->set_source("mem://fake-lmdb"); vp->set_backend(VideoSampledShotsDataParameter_DB_LMDB);
@@ -554,9 +575,52 @@ REF_API void* ref_solver_create(int V, int K, const int* video_id, const int* sh
     l->add_loss_weight(1); l->add_loss_weight(0);
     l->mutable_max_margin_loss_param()->set_margin(margin);
     l->mutable_max_margin_loss_param()->set_norm(norm == 2 ? MaxMarginLossParameter_Norm_L2 : MaxMarginLossParameter_Norm_L1);
-    g_fake_db = &s->db;
+    if (with_test) {
+      // every layer so far is TRAIN-only except fc7 / fc7_relu (no include rule in the shipped file), then the TEST graph
+      for (int i = int(first_layer); i < np->layers_size(); ++i) {
+        const std::string& n = np->layers(i).name();
+        if (n != "fc7" && n != "fc7_relu") phase_rule(np->mutable_layers(i), TRAIN);
+      }
+      SV fr, sl;
+      for (int f = 1; f <= frames; ++f) { fr.push_back(nm("context_datum_%d", f)); sl.push_back(nm("test_sample_frame_%d", f)); }
+      LayerParameter* t = add_layer(np, "shot_windows", LayerParameter_LayerType_VIDEO_SHOT_WINDOW_TEST_DATA, {}, {"data", "video_ids"});
+      t->mutable_video_shot_window_test_data_param()->set_source("mem://fake-lmdb-test");
+      t->mutable_video_shot_window_test_data_param()->set_backend(VideoShotWindowTestDataParameter_DB_LMDB);
+      t->mutable_video_shot_window_test_data_param()->set_batch_size(test_batch);
+      phase_rule(t, TEST);
+      t = add_layer(np, "slice_input_data", LayerParameter_LayerType_SLICE, {"data"}, fr); t->mutable_slice_param()->set_slice_dim(1); phase_rule(t, TEST);
+      t = add_layer(np, "batch_concat_input_test", LayerParameter_LayerType_CONCAT, fr, {"concat_input_datums"}); t->mutable_concat_param()->set_concat_dim(0); phase_rule(t, TEST);
+      t = add_layer(np, "flatten_input", LayerParameter_LayerType_FLATTEN, {"concat_input_datums"}, {"concat_input_datums_flat"}); phase_rule(t, TEST);
+      t = add_layer(np, "slice_test", LayerParameter_LayerType_SLICE, {"concat_input_datums_flat"}, sl); t->mutable_slice_param()->set_slice_dim(0); phase_rule(t, TEST);
+      t = add_layer(np, "average_for_test", LayerParameter_LayerType_ELTWISE, sl, {"original_feature"});
+      t->mutable_eltwise_param()->set_operation(EltwiseParameter_EltwiseOp_SUM);
+      for (int f = 0; f < frames; ++f) t->mutable_eltwise_param()->add_coeff(1.0f / float(frames));
+      phase_rule(t, TEST);
+      t = add_layer(np, "test_norm", LayerParameter_LayerType_NORMALIZATION, {"ip2"}, {"ip2_norm"}); phase_rule(t, TEST);
+      t = add_layer(np, "retrieval_stats", LayerParameter_LayerType_RETRIEVAL_STATS, {"ip2_norm", "video_ids"},
+                    {"test_map", "test_hit_at_1", "test_hit_at_5"});
+      t->mutable_retrieval_stats_param()->set_id_to_class_file(id_to_class_file);
+      t->mutable_retrieval_stats_param()->set_exclude_same_video_shots(exclude_same_video_shots != 0);
+      phase_rule(t, TEST);
+      // Net::Init appends layers in file order and a blob must be produced before it is consumed: the TEST data path has to
+      // precede fc7, as in the shipped file (its TEST layers sit between the TRAIN input layers and fc7)
+      NetParameter ordered; ordered.set_name(np->name());
+      auto is_test_input = [&](const std::string& n, const LayerParameter& lp) {
+        return lp.include_size() == 1 && lp.include(0).phase() == TEST && n != "test_norm" && n != "retrieval_stats";
+      };
+      for (int i = 0; i < np->layers_size(); ++i) { const LayerParameter& lp = np->layers(i); if (lp.name() == "fc7") break; ordered.add_layers()->CopyFrom(lp); }
+      for (int i = 0; i < np->layers_size(); ++i) { const LayerParameter& lp = np->layers(i); if (is_test_input(lp.name(), lp)) ordered.add_layers()->CopyFrom(lp); }
+      bool after = false;
+      for (int i = 0; i < np->layers_size(); ++i) {
+        const LayerParameter& lp = np->layers(i);
+        if (lp.name() == "fc7") after = true;
+        if (after && !is_test_input(lp.name(), lp)) ordered.add_layers()->CopyFrom(lp);
+      }
+      np->CopyFrom(ordered);
+    }
+    g_fake_db = &s->db; g_fake_db_test = with_test ? &s->test_db : nullptr;
     s->solver.reset(new StepSolver(sp));           // Solver::Init -> Net::Init -> every layer's SetUp (data layer: buffer init)
-    g_fake_db = nullptr;
+    g_fake_db = nullptr; g_fake_db_test = nullptr;
     s->solver->pre();
     const vector<shared_ptr<Blob<float> > >& params = s->solver->net()->params();
     if (params.size() != 2) { fprintf(stderr, "ref_driver: expected 2 parameter blobs, got %d\n", int(params.size())); delete s; return nullptr; }
@@ -585,6 +649,40 @@ REF_API int ref_solver_get(void* h, float* W, float* b, float* hW, float* hb, fl
     if (data) { const shared_ptr<Blob<float> > d = s->solver->net()->blob_by_name("data"); memcpy(data, d->cpu_data(), sizeof(float) * d->count()); }
     return 0;
   } catch (const std::exception& e) { fprintf(stderr, "ref_driver: %s\n", e.what()); return -1; }
+}
+// Solver::Test's loop (solver.cpp:252-317) on test net 0: weights shared with the train net, `iters` forward passes,
+// mean of the three outputs (test_map, test_hit_at_1, test_hit_at_5)
+REF_API int ref_solver_test(void* h, int iters, float* out3) {
+  try {
+    RefSolver* s = static_cast<RefSolver*>(h);
+    if (s->solver->test_nets().empty()) return -2;
+    Net<float>* tn = s->solver->test_nets()[0].get();
+    Caffe::set_phase(Caffe::TEST);
+    tn->ShareTrainedLayersWith(s->solver->net().get());
+    double acc[3] = {0, 0, 0};
+    vector<Blob<float>*> bottom_vec;
+    for (int i = 0; i < iters; ++i) {
+      float loss = 0;
+      const vector<Blob<float>*>& res = tn->Forward(bottom_vec, &loss);
+      if (res.size() != 3) { Caffe::set_phase(Caffe::TRAIN); return -3; }
+      // output blobs come in the order of Net::Init's std::set of blob names (lexicographic): place them by name
+      for (int j = 0; j < 3; ++j) {
+        const std::string& nme = tn->blob_names()[tn->output_blob_indices()[j]];
+        const int slot = nme == "test_map" ? 0 : nme == "test_hit_at_1" ? 1 : nme == "test_hit_at_5" ? 2 : -1;
+        if (slot < 0) { Caffe::set_phase(Caffe::TRAIN); return -4; }
+        acc[slot] += res[j]->cpu_data()[0];
+      }
+    }
+    Caffe::set_phase(Caffe::TRAIN);
+    for (int j = 0; j < 3; ++j) out3[j] = float(acc[j] / iters);
+    return 0;
+  } catch (const std::exception& e) { fprintf(stderr, "ref_driver: %s\n", e.what()); Caffe::set_phase(Caffe::TRAIN); return -1; }
+}
+REF_API int ref_solver_test_num_layers(void* h) { RefSolver* s = static_cast<RefSolver*>(h); return s->solver->test_nets().empty() ? 0 : int(s->solver->test_nets()[0]->layers().size()); }
+REF_API const char* ref_solver_test_layer_name(void* h, int i) { return static_cast<RefSolver*>(h)->solver->test_nets()[0]->layer_names()[i].c_str(); }
+REF_API const char* ref_solver_test_output_name(void* h, int j) {
+  Net<float>* tn = static_cast<RefSolver*>(h)->solver->test_nets()[0].get();
+  return tn->blob_names()[tn->output_blob_indices()[j]].c_str();
 }
 REF_API int ref_solver_num_layers(void* h) { return int(static_cast<RefSolver*>(h)->solver->net()->layers().size()); }
 REF_API const char* ref_solver_layer_name(void* h, int i) { return static_cast<RefSolver*>(h)->solver->net()->layer_names()[i].c_str(); }

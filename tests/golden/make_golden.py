@@ -110,8 +110,25 @@ sol = pyref.Solver(t_vid, t_off, t_sid, t_feat, t_W0, t_b0, TB, 5, 10, 60, 50, 6
 layer_names = sol.layer_names()
 traj = [sol.step() for _ in range(8)]
 st = sol.state(); sol.close()
+# the same run with the shipped file's TEST-phase graph in the NetParameter: the TRAIN trajectory must not move, and
+# Solver::Test's loop (2 iterations of the TEST net on shared weights) is recorded before and after the 8 steps
+tn, tF, tTB = 50, 4, 20
+t_tdata = np.maximum(rng.normal(0, 1, (tn, tF, TK)), 0).astype(np.float32); t_tvid = rng.randint(0, 9, tn).astype(np.int32)
+idmap = {v: v % 3 for v in range(9) if v != 4}                  # video 4 unlisted -> class 0 (std::map operator[])
+idf = os.path.join(OUT, "_id2class.tmp"); open(idf, "w").write("".join("%d,%d\n" % kv for kv in idmap.items()))
+sol = pyref.Solver(t_vid, t_off, t_sid, t_feat, t_W0, t_b0, TB, 5, 10, 60, 50, 6,
+                   test=dict(data=t_tdata, video_id=t_tvid, batch=tTB, id_to_class_file=idf, exclude_same=True), **hyper)
+test_before = sol.test(2)
+traj2 = [sol.step() for _ in range(8)]
+test_after = sol.test(2)
+assert traj2 == traj and sol.layer_names() == layer_names
+test_layer_names, test_output_names = sol.test_layer_names(), sol.test_output_names()
+sol.close(); os.remove(idf)
 np.savez_compressed(os.path.join(OUT, "solver_ref.npz"), vid=t_vid, off=t_off, sid=t_sid, feat=t_feat, W0=t_W0, b0=t_b0,
                     cfg=np.array([TB, 5, 10, 60, 50, 6], np.int32), hyper=np.array([0.05, 0.9, 5e-4, 1e-3, 0.75], np.float64),
                     loss=np.array([t[0] for t in traj], np.float32), violations=np.array([t[1] for t in traj], np.float32),
-                    W=st["W"], b=st["b"], hW=st["hW"], hb=st["hb"], layer_names=np.array(layer_names))
-print("solver_ref.npz written: losses", [round(t[0], 5) for t in traj])
+                    W=st["W"], b=st["b"], hW=st["hW"], hb=st["hb"], layer_names=np.array(layer_names),
+                    test_data=t_tdata, test_vid=t_tvid, test_batch=np.int32(tTB), id_keys=np.array(list(idmap.keys()), np.int32),
+                    id_vals=np.array(list(idmap.values()), np.int32), test_before=test_before, test_after=test_after,
+                    test_layer_names=np.array(test_layer_names), test_output_names=np.array(test_output_names))
+print("solver_ref.npz written: losses", [round(t[0], 5) for t in traj], "test", test_before, test_after)

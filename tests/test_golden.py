@@ -118,6 +118,21 @@ def test_oracle_reproduces_reference_solver_trajectory(oracle):
         assert abs(loss - g["loss"][it]) < 1e-5 * max(1, abs(g["loss"][it])) and viol == g["violations"][it], it
     for k in ("W", "b", "hW", "hb"):
         assert rel(st[k], g[k]) < 1e-5, k
+    # Solver::Test's loop on the reference's TEST net (shared weights), 2 iterations before and after the 8 steps
+    tdata, tvid, TB = g["test_data"], g["test_vid"], int(g["test_batch"])
+    cls = dict(zip(g["id_keys"].tolist(), g["id_vals"].tolist()))
+
+    def test_scores(W, b, start):
+        acc = np.zeros(3)
+        for i in range(2):
+            item = (np.arange(TB) + (start + i) * TB) % len(tdata)
+            E = oracle.test_embed(tdata[item], W, b)[1]
+            labels = np.array([cls.get(int(v), 0) for v in tvid[item]], np.int32)
+            r = oracle.retrieval_stats(E, tvid[item], labels, True)
+            acc += [r["map"], r["hit1"], r["hit5"]]
+        return acc / 2
+    assert np.abs(test_scores(g["W0"], g["b0"], 0) - g["test_before"]).max() < 1e-6
+    assert np.abs(test_scores(st["W"], st["b"], 2) - g["test_after"]).max() < 1e-5
     from oracle import pyref
     if pyref.available():
         gamma, power = 0.5, 0.0          # "step": rate = base_lr * gamma^(iter / stepsize)

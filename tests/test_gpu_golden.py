@@ -121,14 +121,31 @@ def test_caffe_host_solver_follows_reference_solver_trajectory(tmp_path, monkeyp
     src = records_util.write_vvrs(tmp_path / "train.vvrs", records_util.video_shots_records(g["vid"], g["off"], g["sid"], g["feat"]))
     monkeypatch.setenv("VV_FUSE", "1" if fuse else "0")
     caffe_host.set_device(0); caffe_host.set_precision("f16x3")
-    net_txt = prototxt.train_net(B=B, C=C, Nn=Nn, K=K, N=N, dropout=0, max_buffer_size=P, swap=swap, max_same=max_same, source=src)
+    tsrc = records_util.write_vvrs(tmp_path / "test.vvrs", records_util.test_window_records(g["test_data"], g["test_vid"]))
+    idfile = tmp_path / "id_to_class.txt"
+    idfile.write_text("".join("%d,%d\n" % (k, v) for k, v in zip(g["id_keys"].tolist(), g["id_vals"].tolist())))
+    net_txt = prototxt.train_net(B=B, C=C, Nn=Nn, K=K, N=N, dropout=0, max_buffer_size=P, swap=swap, max_same=max_same, source=src,
+                                 test=dict(batch=int(g["test_batch"]), frames=g["test_data"].shape[1], source=tsrc,
+                                           id_to_class_file=str(idfile), exclude_same=True))
     sol = caffe_host.Solver(prototxt.solver(base_lr=hyper["base_lr"], momentum=hyper["momentum"], weight_decay=hyper["weight_decay"],
-                                            gamma=hyper["gamma"], power=hyper["power"], display=0, snapshot=0), net_txt)
+                                            gamma=hyper["gamma"], power=hyper["power"], display=0, snapshot=0, test_iter=2,
+                                            test_interval=1000000), net_txt)
     assert sol.net.layer_names == [str(x) for x in g["layer_names"]]
+    assert sol.test_net(0).layer_names == [str(x) for x in g["test_layer_names"]]
     sol.net.set_param(0, g["W0"]); sol.net.set_param(1, g["b0"])
+    # Solver::Test (2 iterations of the TEST net on the shared weights) against the reference's TEST net; the reference
+    # reports its outputs in Net::Init's lexicographic order, the scores are matched by name
+    order = [str(x) for x in g["test_output_names"]]
+    assert sol.test_net(0).blob_names[-3:] == ["test_map", "test_hit_at_1", "test_hit_at_5"]
+    before = dict(zip(order, sol.test(0)))
+    assert abs(before["test_map"] - g["test_before"][0]) < 2e-3 and abs(before["test_hit_at_1"] - g["test_before"][1]) < 1e-6 \
+        and abs(before["test_hit_at_5"] - g["test_before"][2]) < 1e-6, before
     for it in range(len(g["loss"])):
         loss = sol.step()
         assert abs(loss - g["loss"][it]) < 1e-5 * max(1, abs(g["loss"][it])), it
+    after = dict(zip(order, sol.test(0)))
+    assert abs(after["test_map"] - g["test_after"][0]) < 2e-3 and abs(after["test_hit_at_1"] - g["test_after"][1]) < 1e-6 \
+        and abs(after["test_hit_at_5"] - g["test_after"][2]) < 1e-6, after
     assert rel(sol.net.param(0), g["W"].reshape(-1)) < 1e-5 and rel(sol.net.param(1), g["b"]) < 1e-5
     assert rel(sol.history(0), g["hW"].reshape(-1)) < 1e-5 and rel(sol.history(1), g["hb"]) < 1e-5
     sol.close()
