@@ -124,12 +124,7 @@ test_after = sol.test(2)
 assert traj2 == traj and sol.layer_names() == layer_names
 test_layer_names, test_output_names = sol.test_layer_names(), sol.test_output_names()
 sol.close(); os.remove(idf)
-# 1000 iterations of the reference pipeline on the same problem: the loss curve the tensor-core modes must stay within
-# 1e-2 of (north_star)
-sol = pyref.Solver(t_vid, t_off, t_sid, t_feat, t_W0, t_b0, TB, 5, 10, 60, 50, 6, **hyper)
-loss_1k = np.array([sol.step()[0] for _ in range(1000)], np.float32)
-sol.close()
-np.savez_compressed(os.path.join(OUT, "solver_ref.npz"), loss_1k=loss_1k, vid=t_vid, off=t_off, sid=t_sid, feat=t_feat, W0=t_W0, b0=t_b0,
+np.savez_compressed(os.path.join(OUT, "solver_ref.npz"), vid=t_vid, off=t_off, sid=t_sid, feat=t_feat, W0=t_W0, b0=t_b0,
                     cfg=np.array([TB, 5, 10, 60, 50, 6], np.int32), hyper=np.array([0.05, 0.9, 5e-4, 1e-3, 0.75], np.float64),
                     loss=np.array([t[0] for t in traj], np.float32), violations=np.array([t[1] for t in traj], np.float32),
                     W=st["W"], b=st["b"], hW=st["hW"], hb=st["hb"], layer_names=np.array(layer_names),
