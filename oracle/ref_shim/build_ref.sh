@@ -10,7 +10,14 @@ REF="${VV_REFERENCE:-/root/reference}"
 OUT="$ROOT/oracle/_ref"
 [ -d "$REF/src/caffe" ] || { echo "no reference tree at $REF: keeping any prebuilt oracle/_ref"; exit 0; }
 mkdir -p "$OUT/obj"
-python "$HERE/gen_pb_shim.py" "$REF" "$OUT/gen" > /dev/null
+# generated accessor headers: replaced only when their content changes, so that object files can depend on them by mtime
+rm -rf "$OUT/gen.new"; python "$HERE/gen_pb_shim.py" "$REF" "$OUT/gen.new" > /dev/null
+mkdir -p "$OUT/gen/caffe/proto"
+for f in "$OUT"/gen.new/caffe/proto/*.h; do
+  cmp -s "$f" "$OUT/gen/caffe/proto/$(basename "$f")" || cp "$f" "$OUT/gen/caffe/proto/$(basename "$f")"
+done
+rm -rf "$OUT/gen.new"
+NEWEST_HDR="$(ls -t "$OUT"/gen/caffe/proto/*.h $(find "$HERE/include" -type f) | head -1)"
 BLAS="$(python - <<'PY'
 import glob, os, scipy
 c = glob.glob(os.path.join(os.path.dirname(os.path.dirname(scipy.__file__)), "scipy.libs", "libscipy_openblas*.so"))
@@ -27,11 +34,18 @@ SRCS="blob syncedmem common util/math_functions layers/inner_product_layer layer
       layers/video_sampled_shots_data_layer layers/video_shot_window_test_data_layer layers/base_data_layer internal_thread data_transformer
       net solver util/insert_splits"
 OBJS=""
+JOBS="$(nproc 2>/dev/null || echo 4)"
+pids=""
 for s in $SRCS; do
   o="$OUT/obj/$(basename $s).o"
-  if [ ! -f "$o" ] || [ "$REF/src/caffe/$s.cpp" -nt "$o" ]; then g++ $CXXFLAGS -c "$REF/src/caffe/$s.cpp" -o "$o"; fi
+  if [ ! -f "$o" ] || [ "$REF/src/caffe/$s.cpp" -nt "$o" ] || [ "$NEWEST_HDR" -nt "$o" ]; then
+    g++ $CXXFLAGS -c "$REF/src/caffe/$s.cpp" -o "$o" &
+    pids="$pids $!"
+    while [ "$(jobs -rp | wc -l)" -ge "$JOBS" ]; do sleep 0.2; done
+  fi
   OBJS="$OBJS $o"
 done
+for p in $pids; do wait "$p"; done
 g++ $CXXFLAGS -c "$HERE/ref_driver.cpp" -o "$OUT/obj/ref_driver.o"
 # link the SciPy wheel's OpenBLAS in place (same image, hence same path, on the GPU box)
 g++ -shared -o "$OUT/libvv_ref.so" $OBJS "$OUT/obj/ref_driver.o" "$BLAS" -Wl,-Bsymbolic -Wl,-rpath,"$(dirname "$BLAS")" -lpthread
