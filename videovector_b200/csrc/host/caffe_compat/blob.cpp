@@ -109,12 +109,14 @@ template <> void Blob<float>::Update() {
   // data -= diff on the device wherever the head is (no CPU arithmetic in this build)
   VV_CHECK(vv_axpby(count_, -1.f, (const float*)diff_->gpu_data(), 1.f, (float*)data_->mutable_gpu_data(), Caffe::stream()));
 }
-template <> float Blob<float>::asum_data() const {
-  if (!data_) return 0; const float* p = cpu_data(); double s = 0; for (int i = 0; i < count_; ++i) s += p[i] < 0 ? -p[i] : p[i]; return float(s);
+// debug_info sums (net.cpp's ForwardDebugInfo): read back and summed on the host, not part of any step
+static float abs_sum(const float* p, int n) {
+  double s = 0;
+  for (int i = 0; i < n; ++i) s += p[i] < 0 ? -p[i] : p[i];
+  return float(s);
 }
-template <> float Blob<float>::asum_diff() const {
-  if (!diff_) return 0; const float* p = cpu_diff(); double s = 0; for (int i = 0; i < count_; ++i) s += p[i] < 0 ? -p[i] : p[i]; return float(s);
-}
+template <> float Blob<float>::asum_data() const { return data_ ? abs_sum(cpu_data(), count_) : 0.f; }
+template <> float Blob<float>::asum_diff() const { return diff_ ? abs_sum(cpu_diff(), count_) : 0.f; }
 template <typename Dtype>
 void Blob<Dtype>::CopyFrom(const Blob<Dtype>& source, bool copy_diff, bool reshape) {
   if (num_ != source.num() || channels_ != source.channels() || height_ != source.height() || width_ != source.width()) {
