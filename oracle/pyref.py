@@ -161,7 +161,7 @@ class Solver:
     def __init__(self, video_id, shot_off, shot_ids, feat, W0, b0, batch_size, context_size=5, num_negative_samples=10,
                  max_buffer_size=5000, negative_swap_percentage=50, max_same_video_negs=6, context_type=1, margin=2.0,
                  norm=2, base_lr=0.001, momentum=0.9, weight_decay=0.0005, lr_policy="inv", gamma=0.001, power=0.75,
-                 stepsize=1, seed=1, dropout_ratio=0.0, test=None):
+                 stepsize=1, seed=1, dropout_ratio=0.0, test=None, reg_type=2):
         """test = dict(data=[n, frames, K], video_id=[n], batch=.., id_to_class_file=path, exclude_same=True): adds the shipped
         file's TEST-phase graph (TestVideoShotWindows records on a second fake LMDB); see test()."""
         L = lib()
@@ -194,7 +194,7 @@ class Solver:
                                       context_size, num_negative_samples, self.N, max_buffer_size, negative_swap_percentage,
                                       max_same_video_negs, context_type, fl(margin), norm, fl(base_lr), fl(momentum),
                                       fl(weight_decay), self.POLICY[lr_policy], fl(gamma), fl(power), stepsize, _p(W0), _p(b0),
-                                      fl(dropout_ratio), *targs)
+                                      fl(dropout_ratio), *targs, int(reg_type))
         if not self._h:
             raise RuntimeError("reference solver failed to set up")
 

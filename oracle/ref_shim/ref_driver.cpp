@@ -491,7 +491,7 @@ REF_API void* ref_solver_create(int V, int K, const int* video_id, const int* sh
                                 float base_lr, float momentum, float weight_decay, int lr_policy, float gamma, float power,
                                 int stepsize, const float* W0, const float* b0, float dropout_ratio,
                                 int n_test, int frames, const float* test_data /*[n_test, frames, K]*/, const int* test_video_id,
-                                int test_batch, const char* id_to_class_file, int exclude_same_video_shots) {
+                                int test_batch, const char* id_to_class_file, int exclude_same_video_shots, int reg_type) {
   try {
     Caffe::set_mode(Caffe::CPU);
     Caffe::set_phase(Caffe::TRAIN);
@@ -519,6 +519,7 @@ REF_API void* ref_solver_create(int V, int K, const int* video_id, const int* sh
     SolverParameter sp;
     if (with_test) { sp.add_test_iter(1); sp.set_test_interval(1 << 30); sp.set_test_initialization(false); }
     sp.set_base_lr(base_lr); sp.set_momentum(momentum); sp.set_weight_decay(weight_decay);
+    if (reg_type == 1) sp.set_regularization_type("L1");
     sp.set_lr_policy(lr_policy == 1 ? "inv" : lr_policy == 2 ? "step" : "fixed");
     sp.set_gamma(gamma); sp.set_power(power); sp.set_stepsize(stepsize);
     sp.set_max_iter(1 << 30); sp.set_display(0); sp.set_snapshot(0); sp.set_snapshot_after_train(false);

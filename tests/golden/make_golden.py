@@ -124,7 +124,16 @@ test_after = sol.test(2)
 assert traj2 == traj and sol.layer_names() == layer_names
 test_layer_names, test_output_names = sol.test_layer_names(), sol.test_output_names()
 sol.close(); os.remove(idf)
-np.savez_compressed(os.path.join(OUT, "solver_ref.npz"), vid=t_vid, off=t_off, sid=t_sid, feat=t_feat, W0=t_W0, b0=t_b0,
+# a second trajectory with the other branches of the path: L1 hinge (max_margin_loss norm: L1), "step" learning-rate
+# policy, L1 weight regularisation
+alt_hyper = dict(base_lr=0.02, momentum=0.8, weight_decay=1e-3, lr_policy="step", gamma=0.5, power=0.0, stepsize=2)
+sol = pyref.Solver(t_vid, t_off, t_sid, t_feat, t_W0, t_b0, TB, 5, 10, 60, 50, 6, norm=1, reg_type=1, **alt_hyper)
+alt_traj = [sol.step() for _ in range(6)]
+alt_st = sol.state(); sol.close()
+alt = dict(alt_loss=np.array([t[0] for t in alt_traj], np.float32), alt_violations=np.array([t[1] for t in alt_traj], np.float32),
+           alt_W=alt_st["W"], alt_b=alt_st["b"], alt_hW=alt_st["hW"], alt_hb=alt_st["hb"],
+           alt_hyper=np.array([0.02, 0.8, 1e-3, 0.5, 2], np.float64))
+np.savez_compressed(os.path.join(OUT, "solver_ref.npz"), **alt, vid=t_vid, off=t_off, sid=t_sid, feat=t_feat, W0=t_W0, b0=t_b0,
                     cfg=np.array([TB, 5, 10, 60, 50, 6], np.int32), hyper=np.array([0.05, 0.9, 5e-4, 1e-3, 0.75], np.float64),
                     loss=np.array([t[0] for t in traj], np.float32), violations=np.array([t[1] for t in traj], np.float32),
                     W=st["W"], b=st["b"], hW=st["hW"], hb=st["hb"], layer_names=np.array(layer_names),

@@ -99,16 +99,17 @@ def test_oracle_reproduces_reference_solver_trajectory(oracle):
     base_lr, mom, wd, gamma, power = [float(x) for x in g["hyper"]]
     K = g["feat"].shape[1]
 
-    def run(vid, off, sid, feat, W0, b0, steps, policy, norm, stepsize=1):
+    def run(vid, off, sid, feat, W0, b0, steps, policy, norm, stepsize=1, reg_type=2, hyper=None):
+        lr0, mo, dec, gam, pw = hyper if hyper is not None else (base_lr, mom, wd, gamma, power)
         smp = oracle.Sampler(vid, off, sid, feat, K, B, C, Nn, P, swap, max_same, 100, seed=1)
         W, b = W0.copy(), b0.copy(); hW = np.zeros_like(W); hb = np.zeros_like(b)
         out = []
         for it in range(steps):
             data = smp.next()[2]
             r = oracle.net_forward_backward(data, W, b, None, B, C, Nn, margin=2.0, norm=norm, dropout_ratio=0.0)
-            rate = oracle.learning_rate(policy, base_lr, gamma, power, stepsize, it)
-            W, _, hW = oracle.sgd_update(W, r["dW"], hW, rate * 1.0, mom, wd * 1.0)      # blobs_lr 1 / 2, weight_decay 1 / 0
-            b, _, hb = oracle.sgd_update(b, r["db"], hb, rate * 2.0, mom, 0.0)
+            rate = oracle.learning_rate(policy, lr0, gam, pw, stepsize, it)
+            W, _, hW = oracle.sgd_update(W, r["dW"], hW, rate * 1.0, mo, dec * 1.0, reg_type)      # blobs_lr 1 / 2, weight_decay 1 / 0
+            b, _, hb = oracle.sgd_update(b, r["db"], hb, rate * 2.0, mo, 0.0, reg_type)
             out.append((float(r["loss"][0]), float(r["violations"][0])))
         smp.close()
         return out, dict(W=W, b=b, hW=hW, hb=hb)
@@ -118,6 +119,14 @@ def test_oracle_reproduces_reference_solver_trajectory(oracle):
         assert abs(loss - g["loss"][it]) < 1e-5 * max(1, abs(g["loss"][it])) and viol == g["violations"][it], it
     for k in ("W", "b", "hW", "hb"):
         assert rel(st[k], g[k]) < 1e-5, k
+    # the second fixture trajectory: L1 hinge, "step" policy, L1 weight regularisation
+    a_lr, a_mom, a_wd, a_gamma, a_step = [float(x) for x in g["alt_hyper"]]
+    traj, sa = run(g["vid"], g["off"], g["sid"], g["feat"], g["W0"], g["b0"], len(g["alt_loss"]), "step", 1, stepsize=int(a_step),
+                   reg_type=1, hyper=(a_lr, a_mom, a_wd, a_gamma, 0.0))
+    for it, (loss, viol) in enumerate(traj):
+        assert abs(loss - g["alt_loss"][it]) < 1e-5 * max(1, abs(g["alt_loss"][it])) and viol == g["alt_violations"][it], it
+    for k in ("W", "b", "hW", "hb"):
+        assert rel(sa[k], g["alt_" + k]) < 1e-5, k
     # Solver::Test's loop on the reference's TEST net (shared weights), 2 iterations before and after the 8 steps
     tdata, tvid, TB = g["test_data"], g["test_vid"], int(g["test_batch"])
     cls = dict(zip(g["id_keys"].tolist(), g["id_vals"].tolist()))

@@ -150,3 +150,27 @@ def test_caffe_host_solver_follows_reference_solver_trajectory(tmp_path, monkeyp
     assert rel(sol.history(0), g["hW"].reshape(-1)) < 1e-5 and rel(sol.history(1), g["hb"]) < 1e-5
     sol.close()
 
+
+
+@pytest.mark.parametrize("prec,fused_gather", [("fp32_simt", False), ("f16x3", True)])
+def test_trainer_follows_reference_trajectory_l1_step_policy(prec, fused_gather):
+    """The fixture's second reference trajectory: L1 hinge (max_margin_loss norm: L1), "step" learning-rate policy and L1
+    weight regularisation -- the other branches of the loss gradient and of SGDSolver::ComputeUpdateValue."""
+    g, (B, C, Nn, P, swap, max_same), _ = _solver_fixture()
+    lr, mom, wd, gamma, stepsize = [float(x) for x in g["alt_hyper"]]
+    N, K = g["W0"].shape
+    bank = torch.as_tensor(g["feat"]).cuda()
+    smp = ops.Sampler(g["vid"], g["off"], g["sid"], B, C, Nn, P, swap, max_same, 100, rand_seed=1)
+    tr = ops.Trainer(ops.trainer_cfg(B, C, Nn, K, N, norm=1, dropout_ratio=0.0, prec=prec, base_lr=lr, momentum=mom, weight_decay=wd,
+                                     lr_policy="step", gamma=gamma, power=0.0, stepsize=int(stepsize), reg_type=1))
+    tr.set_weights(torch.as_tensor(g["W0"]).cuda(), torch.as_tensor(g["b0"]).cuda())
+    if fused_gather:
+        tr.set_bank(bank)
+    for it in range(len(g["alt_loss"])):
+        idx, quirk = smp.next()
+        tr.step(bank, torch.as_tensor(idx).cuda(), torch.as_tensor(quirk).cuda(), None, it=it)
+        assert abs(tr.tensor("loss").item() - g["alt_loss"][it]) < 1e-5 * max(1, abs(g["alt_loss"][it])), it
+        assert tr.tensor("violations").item() == g["alt_violations"][it], it
+    for name, key in (("W", "alt_W"), ("b", "alt_b"), ("W_hist", "alt_hW"), ("b_hist", "alt_hb")):
+        assert rel(tr.tensor(name), g[key]) < 1e-5, name
+    tr.close(); smp.close()
