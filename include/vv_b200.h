@@ -464,7 +464,7 @@ int vv_trainer_step(vv_trainer_t* t, const float* bank, int64_t bank_rows,
 int vv_trainer_last_launches(const vv_trainer_t* t);
 /* Per-phase device timing with CUDA events on the trainer's stream (off by default).
  * Phases: 0 gather, 1 fc7 forward, 2 rank-loss forward, 3 rank-loss backward, 4 wgrad,
- * 5 dgrad, 6 allreduce (+slab reduce), 7 sgd update.  vv_trainer_phase_ms synchronises the
+ * 5 dgrad, 6 allreduce (+slab reduce; NCCL mode only), 7 sgd update (peer-memory mode: the whole exchange + update kernel).  vv_trainer_phase_ms synchronises the
  * stream, writes the summed milliseconds per phase and the number of timed steps, and resets. */
 #define VV_NUM_PHASES 8
 int vv_trainer_set_timing(vv_trainer_t* t, int enable);
@@ -473,9 +473,23 @@ int vv_trainer_phase_ms(vv_trainer_t* t, float* ms_out /*[VV_NUM_PHASES]*/, int*
  * reading blob ip2 of videovec_extraction.prototxt:179-205). rows_op = operand copies of F rows. */
 int vv_trainer_extract(vv_trainer_t* t, const float* F, int64_t rows, float* out);
 
-/* Data-parallel plumbing (NCCL over NVLink; ref has none). */
+/* Data-parallel plumbing (ref has none).  vv_dp_init creates the NCCL communicator and then maps every
+ * rank's exchange buffers into every other rank (CUDA IPC over NVLink).  With the mapping in place (vv_dp_mode == 2)
+ * a training step exchanges its gradients INSIDE the update kernel: split-K sum -> rows pushed to their owner rank ->
+ * the owner adds the G contributions in rank order, updates its N/G rows of W and of the history, and pushes the new
+ * rows (fp32 master optional, GEMM operand copy, W[:,K-1]) to every rank; the next forward GEMM waits for them in its
+ * TMA producer.  Replicas are bit-identical by construction.  The optimiser state is then SHARDED: rank r holds the
+ * current history (and, unless VV_DP_REPLICATE_MASTER=1 or the precision uses fp32 operands, the current fp32 master
+ * weights) only for rows [r*N/G, (r+1)*N/G); vv_dp_gather_state (collective: every rank calls it) all-gathers them so
+ * that vv_trainer_weight / _weight_hist / _weight_diff hold the whole blobs, e.g. before a snapshot.
+ * vv_dp_mode == 1: NCCL all-reduce between wgrad and the update (VV_DP_MODE=nccl, no peer access, more than 8
+ * ranks, or N not divisible by the world size; vv_dp_mode_reason says which).  In either mode the loss blob holds the
+ * mean over ranks (the global-batch mean) and violations the global count, with or without an update. */
 int vv_dp_unique_id(void* id128 /*128 bytes out*/);
 int vv_dp_init(vv_trainer_t* t, const void* id128);
+int vv_dp_mode(const vv_trainer_t* t);                 /* 0 = single rank, 1 = NCCL all-reduce, 2 = peer-memory exchange */
+const char* vv_dp_mode_reason(const vv_trainer_t* t);  /* why mode 1 was chosen ("" otherwise) */
+int vv_dp_gather_state(vv_trainer_t* t);
 int vv_dp_allreduce_inplace(vv_trainer_t* t, float* buf, int64_t count, vv_stream_t stream);
 
 #ifdef __cplusplus

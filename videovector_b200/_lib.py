@@ -144,6 +144,9 @@ SIGNATURES = {
     "vv_dp_unique_id": (_i, [_P]),
     "vv_dp_init": (_i, [_P, _P]),
     "vv_dp_allreduce_inplace": (_i, [_P, _P, _i64, _P]),
+    "vv_dp_mode": (_i, [_P]),
+    "vv_dp_mode_reason": (C.c_char_p, [_P]),
+    "vv_dp_gather_state": (_i, [_P]),
 }
 
 _lib = None

@@ -4,9 +4,12 @@
 // ForwardBackward, ComputeUpdateValue, Net::Update) as a fixed kernel sequence:
 //   K0 gather -> K1 fc7 fwd (+ReLU+dropout epilogue) -> K2 rank-loss fwd ->
 //   K3 rank-loss bwd (+ReLU'/dropout', db) -> K1 wgrad (split-K slabs) ->
-//   [K1 dgrad] -> [NCCL allreduce of dW, db, loss] -> K4 fused SGD update
-// One process per GPU; NCCL is dlopen'ed (the copy already loaded by the host
-// process, e.g. torch's, is reused), so the library has no link-time dependency.
+//   [K1 dgrad] -> K4 fused SGD update
+// Data parallel (one process per GPU): the gradient exchange is part of K4 -- reduce-scatter by push, owner update,
+// all-gather by push over CUDA-IPC-mapped peer memory (vv_dp_exchange.cuh), consumed by the next forward GEMM's
+// producer.  NCCL (dlopen'ed: the copy already loaded by the host process, e.g. torch's, is reused, so the library
+// has no link-time dependency) bootstraps the IPC handles, serves forward/backward-only steps and vv_dp_gather_state,
+// and remains the whole exchange when peer mapping is unavailable or VV_DP_MODE=nccl.
 #include <dlfcn.h>
 #include <stdlib.h>
 #include <math.h>
@@ -14,7 +17,7 @@
 #include <string.h>
 #include <string>
 #include <vector>
-#include "../vv_common.cuh"
+#include "../vv_gemm.cuh"
 
 using namespace vv;
 
@@ -29,6 +32,7 @@ struct Nccl {
   ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
@@ -41,16 +45,33 @@ struct Nccl {
     GetUniqueId = (decltype(GetUniqueId))dlsym(h, "ncclGetUniqueId");
     CommInitRank = (decltype(CommInitRank))dlsym(h, "ncclCommInitRank");
     AllReduce = (decltype(AllReduce))dlsym(h, "ncclAllReduce");
+    AllGather = (decltype(AllGather))dlsym(h, "ncclAllGather");
     CommDestroy = (decltype(CommDestroy))dlsym(h, "ncclCommDestroy");
     GroupStart = (decltype(GroupStart))dlsym(h, "ncclGroupStart");
     GroupEnd = (decltype(GroupEnd))dlsym(h, "ncclGroupEnd");
     GetErrorString = (decltype(GetErrorString))dlsym(h, "ncclGetErrorString");
-    if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy) { set_error("libnccl is missing symbols"); return false; }
+    if (!GetUniqueId || !CommInitRank || !AllReduce || !AllGather || !CommDestroy) { set_error("libnccl is missing symbols"); return false; }
     return true;
   }
 };
 Nccl g_nccl;
-constexpr int kNcclFloat = 7, kNcclSum = 0;
+constexpr int kNcclFloat = 7, kNcclSum = 0, kNcclInt8 = 0;
+
+// ---- peer-memory exchange state (vv_dp_exchange.cuh) ------------------------
+struct DpP2P {
+  bool on = false;
+  void* region = nullptr; size_t region_bytes = 0;       // recv_dw | recv_small | flags | wlast (this rank's)
+  size_t off_small = 0, off_flags = 0, off_wlast = 0;
+  int small_stride = 0, rows_per = 0;
+  void* opened[3 * kDpMaxRanks] = {};                      // mappings to close (region, W operand block, W master per peer)
+  int n_opened = 0;
+  DpPeers peers;
+  unsigned int seq = 0, waited = 0;                        // exchanged steps; the last one some consumer already waited for
+  unsigned int* err_host = nullptr; unsigned int* err_dev = nullptr;   // host-mapped time-out word
+  int replicate_master = 0;
+  bool in_kernel_wait = true;
+  std::string why_off;
+};
 
 struct DevBuf {
   void* p = nullptr; size_t bytes = 0;
@@ -99,6 +120,7 @@ struct vv_trainer {
   const float* scaled_bank = nullptr; int64_t scaled_bank_rows = 0; bool dz_scale_ready = false;
   bool x_allocated = false;
   ncclComm_t comm = nullptr;
+  DpP2P p2p;
   int last_launches = 0;
   // optional per-phase timing
   bool timing = false;
@@ -179,7 +201,26 @@ struct vv_trainer {
     else { o.hi = bank_hi.p; o.lo = nullptr; }     // BF16
     return o;
   }
+  // peers write into this rank's memory until THEIR last update kernel has finished: wait for their flags, then for
+  // every rank to get here, before anything is unmapped or freed
+  void p2p_quiesce() {
+    if (!p2p.on) return;
+    const bool healthy = !(p2p.err_host && *p2p.err_host);
+    if (healthy && p2p.waited < p2p.seq) {
+      dp_wait_w_ready(p2p.peers.flags[cfg.rank], cfg.world_size, p2p.seq, p2p.err_dev, reinterpret_cast<vv_stream_t>(stream));
+      p2p.waited = p2p.seq;
+    }
+    cudaStreamSynchronize(stream);
+    if (healthy && comm && !(p2p.err_host && *p2p.err_host)) {
+      g_nccl.AllReduce(p2p.peers.flags[cfg.rank] + kDpFlagCtr + 3, p2p.peers.flags[cfg.rank] + kDpFlagCtr + 3, 1, kNcclFloat, kNcclSum, comm, stream);
+      cudaStreamSynchronize(stream);
+    }
+  }
   ~vv_trainer() {
+    p2p_quiesce();
+    for (int i = 0; i < p2p.n_opened; ++i) cudaIpcCloseMemHandle(p2p.opened[i]);
+    if (p2p.region) { if (wlast.p && !wlast.base) wlast.p = nullptr; cudaFree(p2p.region); }
+    if (p2p.err_host) cudaFreeHost(p2p.err_host);
     if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
     DevBuf* all[] = {&W, &b, &Wh, &bh, &W_hi, &W_lo, &Xf, &X_hi, &X_lo, &Zf, &H, &stats, &item_loss, &item_viol,
                      &dZf, &dZ_hi, &dZ_lo, &dW_parts, &dbx, &dX, &bank_hi, &bank_lo, &rowmap, &delta, &wlast, &dq};
@@ -190,9 +231,117 @@ struct vv_trainer {
     for (int i = 0; i < 4; ++i) if (ev_slice[i]) cudaEventDestroy(ev_slice[i]);
     if (comm_stream) cudaStreamDestroy(comm_stream);
   }
+  int dp_check_error() {
+    if (p2p.err_host && *p2p.err_host) {
+      set_error("data-parallel exchange timed out waiting for a peer (code %u: 1 = gradient contributions, 2 = updated weights); "
+                "a rank died or fell more than VV_DP_TIMEOUT_MS behind", *p2p.err_host);
+      return VV_ERR_NCCL;
+    }
+    return VV_OK;
+  }
+  int p2p_setup();
   float* loss_ptr() { return dbx.as<float>() + cfg.N; }
   float* viol_ptr() { return dbx.as<float>() + cfg.N + 1; }
 };
+
+
+// Map every rank's exchange region, W operand block and W master into this process (CUDA IPC; the handles travel
+// through one ncclAllGather).  Any failure leaves the NCCL all-reduce path in place and records why.
+int vv_trainer::p2p_setup() {
+  const vv_trainer_cfg_t& c = cfg;
+  const int G = c.world_size;
+  const char* mode = getenv("VV_DP_MODE");
+  if (mode && !strcmp(mode, "nccl")) { p2p.why_off = "VV_DP_MODE=nccl"; return VV_OK; }
+  if (G > kDpMaxRanks) { p2p.why_off = "more than 8 ranks"; return VV_OK; }
+  if (c.N % G != 0) { p2p.why_off = "N does not divide evenly over the ranks"; return VV_OK; }
+  const size_t NK = size_t(c.N) * c.K;
+  p2p.rows_per = c.N / G;
+  p2p.small_stride = ((c.N + 2 + 31) / 32) * 32;
+  size_t off = NK * 4;                                   // recv_dw: G sources x (N/G x K)
+  p2p.off_small = off; off += size_t(G) * p2p.small_stride * 4;
+  p2p.off_flags = (off + 255) & ~size_t(255); off = p2p.off_flags + kDpFlagWords * 4;
+  p2p.off_wlast = (off + 255) & ~size_t(255); off = p2p.off_wlast + size_t(c.N) * 4;
+  p2p.region_bytes = off;
+  VV_CUDA(cudaMalloc(&p2p.region, p2p.region_bytes));
+  VV_CUDA(cudaMemset(p2p.region, 0, p2p.region_bytes));
+  VV_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&p2p.err_host), sizeof(unsigned int), cudaHostAllocMapped));
+  *p2p.err_host = 0u;
+  VV_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&p2p.err_dev), p2p.err_host, 0));
+  // wlast moves into the region (the owners write it remotely); keep what sync_weights put there
+  char* reg = static_cast<char*>(p2p.region);
+  VV_CUDA(cudaMemcpy(reg + p2p.off_wlast, wlast.p, size_t(c.N) * 4, cudaMemcpyDeviceToDevice));
+  // handles: region, W operand block (absent for the fp32-operand precisions), W master
+  const bool has_op = W_hi.base != nullptr;
+  struct Pack { cudaIpcMemHandle_t region, wblk, wm; int has_op; int pad[15]; };
+  static_assert(sizeof(Pack) == 3 * 64 + 64, "handle pack layout");
+  Pack mine; memset(&mine, 0, sizeof(mine));
+  cudaError_t e = cudaIpcGetMemHandle(&mine.region, p2p.region);
+  if (e == cudaSuccess && has_op) e = cudaIpcGetMemHandle(&mine.wblk, W_hi.base);
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&mine.wm, W.base);
+  mine.has_op = has_op ? 1 : 0;
+  int ok = (e == cudaSuccess) ? 1 : 0;
+  if (!ok) { p2p.why_off = std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e); cudaGetLastError(); }
+  // all-gather the packs (a failed rank still takes part so that nobody hangs)
+  Pack* dsend = nullptr; Pack* drecv = nullptr;
+  VV_CUDA(cudaMalloc(&dsend, sizeof(Pack))); VV_CUDA(cudaMalloc(&drecv, sizeof(Pack) * G));
+  if (!ok) mine.has_op = -1;
+  VV_CUDA(cudaMemcpy(dsend, &mine, sizeof(Pack), cudaMemcpyHostToDevice));
+  ncclResult_t r = g_nccl.AllGather(dsend, drecv, sizeof(Pack), kNcclInt8, comm, stream);
+  if (r != 0) { set_error("ncclAllGather of the IPC handles failed (%d)", r); return VV_ERR_NCCL; }
+  VV_CUDA(cudaStreamSynchronize(stream));
+  std::vector<Pack> all(G);
+  VV_CUDA(cudaMemcpy(all.data(), drecv, sizeof(Pack) * G, cudaMemcpyDeviceToHost));
+  cudaFree(dsend); cudaFree(drecv);
+  for (int g = 0; g < G; ++g) if (all[g].has_op < 0) { ok = 0; if (p2p.why_off.empty()) p2p.why_off = "a peer could not export its memory"; }
+  const size_t ho = has_op ? size_t(static_cast<char*>(W_hi.p) - static_cast<char*>(W_hi.base)) : 0;
+  const size_t lo_off = (has_op && W_lo.p) ? size_t(static_cast<char*>(W_lo.p) - static_cast<char*>(W_hi.base)) : 0;
+  int dev = 0; VV_CUDA(cudaGetDevice(&dev));
+  memset(&p2p.peers, 0, sizeof(p2p.peers));
+  for (int g = 0; g < G && ok; ++g) {
+    char* preg; char* pblk = nullptr; char* pwm;
+    if (g == c.rank) {
+      preg = reg; pblk = static_cast<char*>(W_hi.base); pwm = static_cast<char*>(W.base);
+    } else {
+      void* m = nullptr;
+      e = cudaIpcOpenMemHandle(&m, all[g].region, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) { ok = 0; p2p.why_off = std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e); cudaGetLastError(); break; }
+      p2p.opened[p2p.n_opened++] = m; preg = static_cast<char*>(m);
+      if (has_op) {
+        e = cudaIpcOpenMemHandle(&m, all[g].wblk, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) { ok = 0; p2p.why_off = std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e); cudaGetLastError(); break; }
+        p2p.opened[p2p.n_opened++] = m; pblk = static_cast<char*>(m);
+      }
+      e = cudaIpcOpenMemHandle(&m, all[g].wm, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) { ok = 0; p2p.why_off = std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e); cudaGetLastError(); break; }
+      p2p.opened[p2p.n_opened++] = m; pwm = static_cast<char*>(m);
+    }
+    p2p.peers.recv_dw[g] = reinterpret_cast<float*>(preg);
+    p2p.peers.recv_small[g] = reinterpret_cast<float*>(preg + p2p.off_small);
+    p2p.peers.flags[g] = reinterpret_cast<unsigned int*>(preg + p2p.off_flags);
+    p2p.peers.wlast[g] = reinterpret_cast<float*>(preg + p2p.off_wlast);
+    p2p.peers.Wm[g] = reinterpret_cast<float*>(pwm);
+    p2p.peers.wop_hi[g] = has_op ? pblk + ho : nullptr;
+    p2p.peers.wop_lo[g] = (has_op && lo_off) ? pblk + lo_off : nullptr;
+  }
+  // every rank must agree (one that could not map its peers would otherwise wait for pushes that go elsewhere)
+  float* agree = reinterpret_cast<float*>(reg + p2p.off_flags) + kDpFlagCtr + 3;
+  const float mine_ok = ok ? 0.f : 1.f;
+  VV_CUDA(cudaMemcpy(agree, &mine_ok, 4, cudaMemcpyHostToDevice));
+  r = g_nccl.AllReduce(agree, agree, 1, kNcclFloat, kNcclSum, comm, stream);
+  if (r != 0) { set_error("ncclAllReduce failed (%d)", r); return VV_ERR_NCCL; }
+  VV_CUDA(cudaStreamSynchronize(stream));
+  float bad = 0.f; VV_CUDA(cudaMemcpy(&bad, agree, 4, cudaMemcpyDeviceToHost));
+  VV_CUDA(cudaMemset(agree, 0, 4));
+  if (bad != 0.f) { if (p2p.why_off.empty()) p2p.why_off = "a peer could not map this rank's memory"; return VV_OK; }
+  if (wlast.base) { cudaFree(wlast.base); wlast.base = nullptr; }
+  wlast.p = reg + p2p.off_wlast;
+  const char* rep = getenv("VV_DP_REPLICATE_MASTER");
+  p2p.replicate_master = (rep && atoi(rep) != 0) ? 1 : 0;
+  const char* wk = getenv("VV_DP_WAIT_KERNEL");
+  p2p.in_kernel_wait = !(wk && atoi(wk) != 0);
+  p2p.on = true;
+  return VV_OK;
+}
 
 extern "C" vv_trainer_t* vv_trainer_create(const vv_trainer_cfg_t* cfg, vv_stream_t stream) {
   if (!cfg) { set_error("trainer cfg is NULL"); return nullptr; }
@@ -227,6 +376,9 @@ extern "C" float* vv_trainer_blob(vv_trainer_t* t, const char* name) {
   if (n == "dW_raw") return t->dW_parts.as<float>();
   if (n == "db_raw") return t->dbx.as<float>();
   if (n == "dX") return t->dX.as<float>();
+  if (n == "wlast") return t->wlast.as<float>();
+  if (n == "Wop_hi") return t->W_hi.as<float>();     // raw operand planes of W (layout per precision, vv_operand_bytes)
+  if (n == "Wop_lo") return t->W_lo.as<float>();
   set_error("unknown trainer blob '%s'", n.c_str());
   return nullptr;
 }
@@ -288,17 +440,35 @@ extern "C" int vv_trainer_step(vv_trainer_t* t, const float* bank, int64_t bank_
   act.relu = 1; act.negative_slope = 0.f;
   const bool has_dropout = c.dropout_ratio > 0.f;
   act.dropout_mode = has_dropout ? c.dropout_mode : VV_DROPOUT_NONE;
-  act.dropout_ratio = c.dropout_ratio; act.mask = mask; act.seed = c.dropout_seed; act.step = uint64_t(iter);
+  // data parallel: every rank draws its own stream (rank 0 keeps the single-GPU one); without the fold all ranks would
+  // apply the same mask to their local row m, unlike the global-batch run the ranks stand for
+  act.dropout_ratio = c.dropout_ratio; act.mask = mask; act.step = uint64_t(iter);
+  act.seed = c.rank > 0 ? (c.dropout_seed ^ splitmix64(uint64_t(c.rank))) : c.dropout_seed;
   if (has_dropout && (act.dropout_mode == VV_DROPOUT_MASK01 || act.dropout_mode == VV_DROPOUT_MASK_U32) && !mask) {
     set_error("trainer: dropout mask mode needs a mask"); return VV_ERR_INVALID;
   }
   t->tic(1);
+  // data parallel: the rows of W written by the other ranks' last update kernels are awaited by the forward GEMM's TMA
+  // producer lane (tensor-core precisions) or by a one-warp kernel in front of it
+  DpWait dpw = {nullptr, 0, 0u, nullptr, 0ull};
+  const DpWait* wait = nullptr;
+  if ((rc = t->dp_check_error())) return rc;
+  if (t->p2p.on && t->p2p.waited < t->p2p.seq) {
+    if (t->p2p.in_kernel_wait && c.prec != VV_PREC_FP32_SIMT) {
+      dpw.flags = t->p2p.peers.flags[c.rank]; dpw.G = c.world_size; dpw.seq = t->p2p.seq; dpw.err = t->p2p.err_dev;
+      dpw.timeout_ns = dp_wait_timeout_ns();
+      wait = &dpw;
+    } else {
+      if ((rc = dp_wait_w_ready(t->p2p.peers.flags[c.rank], c.world_size, t->p2p.seq, t->p2p.err_dev, s))) return rc;
+    }
+    t->p2p.waited = t->p2p.seq;
+  }
   if (fused_gather) {
-    if ((rc = vv_ip_forward_gathered(t->opBank(), bank_rows, t->rowmap.as<int32_t>(), t->delta.as<float>(), t->wlast.as<float>(),
-                                     t->opW(), t->b.as<float>(), M, N, K, c.prec, &act, nullptr, t->H.as<float>(), s))) return rc;
+    if ((rc = ip_forward_gathered_ex(t->opBank(), bank_rows, t->rowmap.as<int32_t>(), t->delta.as<float>(), t->wlast.as<float>(),
+                                     t->opW(), t->b.as<float>(), M, N, K, c.prec, &act, nullptr, t->H.as<float>(), wait, s))) return rc;
   } else {
-    if ((rc = vv_ip_forward(t->opX(), t->opW(), t->b.as<float>(), M, N, K, c.prec, &act, t->Zf.as<float>(),
-                            t->H.as<float>(), s))) return rc;
+    if ((rc = ip_forward_ex(t->opX(), t->opW(), t->b.as<float>(), M, N, K, c.prec, &act, t->Zf.as<float>(),
+                            t->H.as<float>(), wait, s))) return rc;
   }
   t->toc(1);
   const float dscale = has_dropout ? dropout_scale(c.dropout_ratio) : 1.f;
@@ -347,9 +517,10 @@ extern "C" int vv_trainer_step(vv_trainer_t* t, const float* bank, int64_t bank_
   // LOSES (1.50 -> 1.58 ms/step): the persistent GEMM owns every SM's register file, so the concurrent NCCL kernel and
   // the GEMM's CTAs wait for each other, and two half-size launches quantise worse.  Kept behind VV_DP_SLICES (2 / 4).
   static const int want_slices = [] { const char* e = getenv("VV_DP_SLICES"); return e ? atoi(e) : 1; }();
-  const int nslices = (want_slices > 1 && want_slices <= 4 && c.world_size > 1 && fused_gather && t->comm &&
+  const int nslices = (want_slices > 1 && want_slices <= 4 && c.world_size > 1 && fused_gather && t->comm && !t->p2p.on &&
                        N % (256 * want_slices) == 0) ? want_slices : 1;
-  const bool fold_col = fused_gather && c.world_size == 1 && do_update;
+  const bool use_p2p = t->p2p.on && do_update;           // the exchange runs inside the update kernel
+  const bool fold_col = fused_gather && (c.world_size == 1 || use_p2p) && do_update;
   t->tic(4);
   if (fused_gather) {
     const double reg = double(c.regularization) / 2;
@@ -390,9 +561,10 @@ extern "C" int vv_trainer_step(vv_trainer_t* t, const float* bank, int64_t bank_
     if ((rc = vv_ip_dgrad(t->opdZ(), t->opW(), M, N, K, c.prec, t->dX.as<float>(), s))) return rc;
     t->toc(5);
   }
-  if (c.world_size > 1) {
+  if (c.world_size > 1 && !use_p2p) {
     t->tic(6);
     if (!t->comm) { set_error("trainer: world_size > 1 but vv_dp_init was not called"); return VV_ERR_NCCL; }
+
     if (nslices == 1) {
       if (nparts > 1) {
         if ((rc = vv_reduce_parts(t->dW_parts.as<float>(), nparts, NK, NK, t->dW_parts.as<float>(), s))) return rc;
@@ -412,9 +584,33 @@ extern "C" int vv_trainer_step(vv_trainer_t* t, const float* bank, int64_t bank_
     VV_CUDA(cudaEventRecord(t->ev_comm, t->comm_stream));
     VV_CUDA(cudaStreamWaitEvent(t->stream, t->ev_comm, 0));
     gscale = 1.f / float(c.world_size);
+    // loss was summed over ranks -> mean over ranks (global-batch mean), whether or not an update follows;
+    // violations stay the global count
+    if ((rc = vv_axpby(1, gscale, t->loss_ptr(), 0.f, t->loss_ptr(), s))) return rc;
     t->toc(6);
   }
-  if (do_update) {
+  if (use_p2p) {
+    t->tic(7);
+    const float rate = vv_learning_rate(c.lr_policy, c.base_lr, c.gamma, c.power, c.stepsize, iter);
+    if (rate < 0.f) return VV_ERR_INVALID;
+    // F16X3: every rank derives the same new scale of W from max|W| over all owners' rows of the previous update
+    if ((rc = operand_rescale_ex(t->W_hi.p, c.prec, 10, t->p2p.peers.flags[c.rank] + kDpFlagAmax, c.world_size, s))) return rc;
+    DpExchange x;
+    x.G = c.world_size; x.rank = c.rank; x.seq = t->p2p.seq + 1;
+    x.parts = t->dW_parts.as<float>(); x.nparts = nparts; x.stride = NK;
+    x.col_add = fold_col ? t->dq.as<float>() : nullptr;
+    x.small_src = t->dbx.as<float>(); x.nsmall = N + 2; x.small_stride = t->p2p.small_stride;
+    x.hist = t->Wh.as<float>(); x.diff_out = t->dW_parts.as<float>(); x.count = NK; x.K = K; x.rows_per = t->p2p.rows_per;
+    x.rate_w = rate * c.lr_mult[0]; x.decay_w = c.weight_decay * c.decay_mult[0]; x.momentum = c.momentum;
+    x.reg_type = c.reg_type; x.gscale = 1.f / float(c.world_size); x.prec = c.prec;
+    x.b = t->b.as<float>(); x.bh = t->bh.as<float>(); x.b_diff = t->dbx.as<float>(); x.nb = N;
+    x.rate_b = rate * c.lr_mult[1]; x.decay_b = c.weight_decay * c.decay_mult[1];
+    x.loss_out = t->loss_ptr(); x.viol_out = t->viol_ptr();
+    x.peers = t->p2p.peers;
+    if ((rc = dp_exchange_update(x, t->p2p.err_dev, t->p2p.replicate_master, s))) return rc;
+    t->p2p.seq += 1;
+    t->toc(7);
+  } else if (do_update) {
     t->tic(7);
     // ref: solver.cpp:486-576 + net.cpp:804-839; weight then bias (net.params() order)
     const float rate = vv_learning_rate(c.lr_policy, c.base_lr, c.gamma, c.power, c.stepsize, iter);
@@ -432,10 +628,6 @@ extern "C" int vv_trainer_step(vv_trainer_t* t, const float* bank, int64_t bank_
     u.rate_b = rate * c.lr_mult[1]; u.decay_b = c.weight_decay * c.decay_mult[1];
     u.momentum = c.momentum; u.reg_type = c.reg_type; u.gscale = gscale;
     if ((rc = sgd_update_tail(u, s))) return rc;
-    if (c.world_size > 1) {
-      // loss/violations were summed over ranks: loss -> mean over ranks (global-batch mean)
-      if ((rc = vv_axpby(1, gscale, t->loss_ptr(), 0.f, t->loss_ptr(), s))) return rc;
-    }
     t->toc(7);
   } else if (nparts > 1) {
     if ((rc = vv_reduce_parts(t->dW_parts.as<float>(), nparts, NK, NK, t->dW_parts.as<float>(), s))) return rc;
@@ -510,7 +702,29 @@ extern "C" int vv_dp_init(vv_trainer_t* t, const void* id128) {
   ncclUniqueId id; memcpy(&id, id128, 128);
   ncclResult_t r = g_nccl.CommInitRank(&t->comm, t->cfg.world_size, id, t->cfg.rank);
   if (r != 0) { set_error("ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"); return VV_ERR_NCCL; }
-  return VV_OK;
+  return t->p2p_setup();
+}
+extern "C" int vv_dp_mode(const vv_trainer_t* t) { return !t || t->cfg.world_size == 1 ? 0 : (t->p2p.on ? 2 : 1); }
+extern "C" const char* vv_dp_mode_reason(const vv_trainer_t* t) { return t ? t->p2p.why_off.c_str() : ""; }
+extern "C" int vv_dp_gather_state(vv_trainer_t* t) {
+  if (!t) return VV_ERR_INVALID;
+  if (!t->p2p.on) return VV_OK;                       // NCCL mode: every rank already holds the whole state
+  int rc;
+  if ((rc = t->dp_check_error())) return rc;
+  vv_stream_t s = reinterpret_cast<vv_stream_t>(t->stream);
+  if (t->p2p.waited < t->p2p.seq) {
+    if ((rc = dp_wait_w_ready(t->p2p.peers.flags[t->cfg.rank], t->cfg.world_size, t->p2p.seq, t->p2p.err_dev, s))) return rc;
+    t->p2p.waited = t->p2p.seq;
+  }
+  const size_t own = size_t(t->p2p.rows_per) * t->cfg.K;
+  float* bufs[3] = {t->W.as<float>(), t->Wh.as<float>(), t->dW_parts.as<float>()};
+  for (int i = 0; i < 3; ++i) {
+    if (i == 0 && (t->p2p.replicate_master || !t->W_hi.base)) continue;      // the master rows are already everywhere
+    ncclResult_t r = g_nccl.AllGather(bufs[i] + own * t->cfg.rank, bufs[i], own, kNcclFloat, t->comm, t->stream);
+    if (r != 0) { set_error("ncclAllGather failed (%d)", r); return VV_ERR_NCCL; }
+  }
+  VV_CUDA(cudaStreamSynchronize(t->stream));
+  return t->dp_check_error();
 }
 extern "C" int vv_dp_allreduce_inplace(vv_trainer_t* t, float* buf, int64_t count, vv_stream_t stream) {
   if (!t || !buf || count <= 0) return VV_ERR_INVALID;

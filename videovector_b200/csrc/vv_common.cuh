@@ -43,6 +43,8 @@ struct UpdateTail {
   float momentum; int reg_type; float gscale;
 };
 int sgd_update_tail(const UpdateTail& u, vv_stream_t stream);
+// vv_operand_rescale that also folds in n_extra recorded maxima (bit patterns) kept outside the operand's header
+int operand_rescale_ex(void* hi, int prec, int target_log2, const unsigned int* extra_bits, int n_extra, vv_stream_t stream);
 // vv_rank_loss_fused with the batch loss / violation reduction folded into the kernel (vv_rank_loss.cu)
 int rank_loss_fused_counted(const float* H, const vv_rank_cfg_t* cfg, float loss_weight, int act_fused,
                             float dropout_scale, float* stats, float* target_score, float* neg_score,

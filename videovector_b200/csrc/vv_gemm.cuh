@@ -1,6 +1,7 @@
 // vv_gemm.cuh -- internal interface of the projection GEMMs (K1).
 #pragma once
 #include "vv_common.cuh"
+#include "vv_dp_exchange.cuh"
 
 namespace vv {
 
@@ -43,8 +44,17 @@ struct GemmProblem {
   const int32_t* rowmap;  // NULL = X is materialised
   int64_t bank_rows;
   int n0 = 0, ncols = 0;  // WGRAD_T only: compute outputs [n0, n0 + ncols) (ncols = 0: all)
+  // data parallel: W (operand B of FWD / DGRAD) is being written by the owner ranks' update kernels; the TMA producer
+  // lane waits for their w_ready flags right before its first W tile (flags == NULL: nothing to wait for)
+  DpWait wait = {nullptr, 0, 0u, nullptr, 0ull};
 };
 
+// vv_ip_forward / vv_ip_forward_gathered with the data-parallel wait (wait == NULL: the C-ABI entry points)
+int ip_forward_ex(vv_operand_t X, vv_operand_t W, const float* bias, int M, int N, int K, int prec,
+                  const vv_act_t* act, float* Z, float* H, const DpWait* wait, vv_stream_t stream);
+int ip_forward_gathered_ex(vv_operand_t bank, int64_t bank_rows, const int32_t* rowmap, const float* delta,
+                           const float* wlast, vv_operand_t W, const float* bias, int M, int N, int K, int prec,
+                           const vv_act_t* act, float* Z, float* H, const DpWait* wait, vv_stream_t stream);
 int gemm_tc_launch(const GemmProblem& p, cudaStream_t stream);     // tcgen05 path (TF32X3 / TF32 / BF16)
 int gemm_simt_launch(const GemmProblem& p, cudaStream_t stream);   // exact fp32 path
 bool gemm_tc_supported(const GemmProblem& p, const char** why);

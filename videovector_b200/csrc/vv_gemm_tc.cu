@@ -40,6 +40,7 @@ struct TcParams {
   const uint16_t* ga0; const uint16_t* ga1;   // gather variants: the bank's operand plane(s), row pitch ga_pitch elements
   long long ga_pitch; int ga_cols; int rowmap_len;
   const float* inv_sa; const float* inv_sb;   // f16x3: 1/scale of the two operands (device, from their headers)
+  DpWait wait;                  // data parallel: owner ranks' w_ready flags to wait for before the first B (= W) tile
   GemmEpilogue epi;
 };
 
@@ -131,6 +132,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     if (lane == 0) {
       constexpr int kTmaBytes = C::stage_bytes - (C::gather ? ((C::mixed || C::split16) ? 2 * C::a_bytes : C::a_bytes) : 0);
       int stage = 0; uint32_t phase = 0;
+      if (p.wait.flags) {
+        // the weights arrive from their owner ranks (vv_dp_exchange.cuh): everything up to here -- and the row-gather
+        // producers of operand A, which do not depend on W -- has run under the tail of the exchange
+        for (int r = 0; r < p.wait.G; ++r)
+          dp_spin_wait_flag(&p.wait.flags[kDpFlagWReady + r], p.wait.seq, p.wait.timeout_ns, p.wait.err, 2u);
+        asm volatile("fence.proxy.async;" ::: "memory");   // peer stores (generic proxy) -> TMA reads (async proxy)
+      }
       for (int u = unit0; u < total_units; u += unit_stride) {
         const int split = u / tiles_mn;
         const int t = u - split * tiles_mn;
@@ -664,6 +672,7 @@ int launch_cfg(const GemmProblem& g, cudaStream_t stream) {
   p.inv_sb = C::split16 ? &f16_hdr(g.B.hi)->inv_scale : nullptr;
   p.D = g.D + (C::trans_out ? (long long)n0 * g.K : 0); p.slab_stride = g.slab_stride;
   p.act_N = g.N;
+  p.wait = g.wait;
   p.epi = g.epi;
   p.rowmap = g.rowmap;
   p.ga0 = static_cast<const uint16_t*>(g.A.hi); p.ga1 = static_cast<const uint16_t*>(g.A.lo);

@@ -156,13 +156,17 @@ absmax_kernel(const float* __restrict__ src, long long n, void* hi) {
   if (blockIdx.x == 0 && threadIdx.x < (n & 3)) amax = fmaxf(amax, fabsf(src[n4 * 4 + threadIdx.x]));
   f16_publish_absmax(hi, amax);
 }
-__global__ void operand_rescale_kernel(void* hi, int target_log2, int set_log2, int do_set) {
+// extra[0..n_extra): more recorded maxima (bit patterns of non-negative floats) to fold in -- the data-parallel update
+// leaves one per owner rank there (vv_dp_exchange.cuh), so that every rank derives the same scale for W
+__global__ void operand_rescale_kernel(void* hi, int target_log2, int set_log2, int do_set, const unsigned int* extra, int n_extra) {
   F16Hdr* h = f16_hdr(hi);
   int e;
   if (do_set) {
     e = set_log2;
   } else {
-    const float amax = __uint_as_float(h->absmax_bits);
+    unsigned int bits = h->absmax_bits;
+    for (int i = 0; i < n_extra; ++i) { const unsigned int b = extra[i]; bits = b > bits ? b : bits; }
+    const float amax = __uint_as_float(bits);
     if (!(amax > 0.f) || !isfinite(amax)) {                 // nothing recorded: keep the scale (1 if never set)
       if (!(h->scale > 0.f)) { h->scale = 1.f; h->inv_scale = 1.f; }
       h->absmax_bits = 0u;
@@ -551,16 +555,19 @@ extern "C" size_t vv_operand_bytes(int64_t count, int prec, size_t* hi_offset, s
 extern "C" int vv_operand_set_scale(void* hi, int prec, int log2_scale, vv_stream_t stream) {
   if (prec != VV_PREC_F16X3) return VV_OK;
   VV_REQUIRE(hi, "operand_set_scale: NULL operand");
-  operand_rescale_kernel<<<1, 1, 0, stream>>>(hi, 0, log2_scale, 1);
+  operand_rescale_kernel<<<1, 1, 0, stream>>>(hi, 0, log2_scale, 1, nullptr, 0);
   VV_LAUNCH_CHECK();
   count_launch();
   return VV_OK;
 }
 extern "C" int vv_operand_rescale(void* hi, int prec, int target_log2, vv_stream_t stream) {
+  return vv::operand_rescale_ex(hi, prec, target_log2, nullptr, 0, stream);
+}
+int vv::operand_rescale_ex(void* hi, int prec, int target_log2, const unsigned int* extra_bits, int n_extra, vv_stream_t stream) {
   if (prec != VV_PREC_F16X3) return VV_OK;
   VV_REQUIRE(hi, "operand_rescale: NULL operand");
   VV_REQUIRE(target_log2 >= -14 && target_log2 <= 15, "operand_rescale: target_log2 must lie in the fp16 exponent range");
-  operand_rescale_kernel<<<1, 1, 0, stream>>>(hi, target_log2, 0, 0);
+  operand_rescale_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(hi, target_log2, 0, 0, extra_bits, n_extra);
   VV_LAUNCH_CHECK();
   count_launch();
   return VV_OK;

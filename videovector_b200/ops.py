@@ -450,7 +450,10 @@ class Trainer:
             return _device_view(fn(self._h), shape)
         shapes = {"X": (self.M, K), "Z": (self.M, N), "H": (self.M, N), "dZ": (self.M, N),
                   "stats": (B, 1 + 2 * (1 + self.cfg.Nn)), "loss": (1,), "violations": (1,),
-                  "dW_raw": (N, K), "db_raw": (N,), "dX": (self.M, K), "db_raw_ext": (N + 2,)}
+                  "dW_raw": (N, K), "db_raw": (N,), "dX": (self.M, K), "db_raw_ext": (N + 2,), "wlast": (N,)}
+        # raw operand planes of W as float32 words (f16x3 / bf16: 2-byte elements; tf32x3: hi fp32, lo two bf16 planes)
+        pw = {PREC["f16x3"]: (N * K // 2, N * K // 2), PREC["bf16"]: (N * K // 2, 0), PREC["tf32x3"]: (N * K, N * K)}.get(self.cfg.prec, (0, 0))
+        shapes["Wop_hi"], shapes["Wop_lo"] = (pw[0],), (pw[1],)
         ptr = L.vv_trainer_blob(self._h, (b"db_raw" if which == "db_raw_ext" else which.encode()))
         if not ptr:
             raise VVError("trainer blob %s is not allocated in this configuration" % which)
@@ -496,6 +499,19 @@ class Trainer:
     def dp_init(self, id_bytes):
         buf = (C.c_char * 128).from_buffer_copy(id_bytes)
         check(self._lib.vv_dp_init(self._h, C.addressof(buf)))
+
+    @property
+    def dp_mode(self):
+        """'single', 'nccl' (all-reduce between wgrad and update) or 'p2p' (exchange inside the update kernel over peer memory)."""
+        return ("single", "nccl", "p2p")[self._lib.vv_dp_mode(self._h)]
+
+    @property
+    def dp_mode_reason(self):
+        return self._lib.vv_dp_mode_reason(self._h).decode()
+
+    def dp_gather_state(self):
+        """Collective (every rank): all-gather the owner-sharded master weights / history of the p2p mode."""
+        check(self._lib.vv_dp_gather_state(self._h))
 
     def close(self):
         if self._h:
