@@ -4,7 +4,9 @@
   python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun, one rank per GPU)
   python bench.py --impl reference --gpus N --steps K --warmup W    (the reference's CPU path, rank 0 only)
 
-Prints ONE JSON line (rank 0).  Workload (BASELINE.json configs[1] per GPU, weak scaling):
+Prints ONE JSON line (rank 0); its "configs" object carries the other BASELINE configurations measured in the same run
+(bf16_dp = configs[2], large_window = configs[3], inference = configs[4]; --no-extra-configs skips them).
+Headline workload (BASELINE.json configs[1] per GPU, weak scaling):
 synthetic post-ReLU 4096-d features resident in HBM, 512-d embedding, window +-2 (C=5),
 10 negatives, B = 4096 triplets per GPU per step, dropout 0.9 (Philox), squared hinge margin 2,
 SGD momentum 0.9 / decay 5e-4 / inv LR policy.  Default precision: f16x3 (scaled fp16 split operands, three
@@ -172,11 +174,17 @@ def run_reference(args):
     val, ms, cores, ph, kind = cpu_reference_run(args.steps, max(args.warmup, 1))
     sample = "B=%d items per step (1/%d of the %d-item GPU step), same K/N/C/Nn; %d timed steps" % (
         CPU_SAMPLE_B, CFG["B"] // CPU_SAMPLE_B, CFG["B"], args.steps)
+    c = CFG
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "triplets/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, 1),
+        # what THIS arm steps: the same net on the host cores, on a bounded sample of the GPU arm's batch
+        "config": {"workload": "videovec_embedding context-ranking training step in Caffe CPU mode (BASELINE configs[0]/[1] net): "
+                               "4096-d features -> %d-d embedding, window +-%d, %d negatives, dropout 0.9, squared hinge margin 2, "
+                               "SGD momentum; bounded sample of the GPU arm's B=%d step" % (c["N"], c["C"] // 2, c["Nn"], c["B"]),
+                   "global_batch": CPU_SAMPLE_B, "K": c["K"], "N": c["N"], "C": c["C"], "Nn": c["Nn"],
+                   "parallelism": "cpu (%d host threads)" % cores, "gpu_arm_global_batch": c["B"] * max(args.gpus, 1)},
         "cpu_baseline": {"value": val, "unit": "triplets/s", "cores": cores, "kind": kind, "sample": sample,
                          "phase_ms": ph, "note": CPU_NOTE[kind]},
         "e2e": {"value": val, "unit": "triplets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -193,23 +201,316 @@ DTYPE = {"tf32x3": "f32 (tf32 + bf16 split operands, 3 tensor-core products, fp3
          "bf16": "bf16", "tf32": "tf32", "fp32_simt": "f32"}
 
 
-def fused_gather_on(args):
+def fused_gather_for(prec, args):
     """K0 folded into the GEMM producers: the default for the 2-byte operand formats; --materialised-gather turns it off."""
-    return getattr(args, "precision", "f16x3") in ("f16x3", "bf16") and not getattr(args, "materialised_gather", False)
+    return prec in ("f16x3", "bf16") and not getattr(args, "materialised_gather", False)
 
 
-def workload_config(args, world):
-    c = CFG
-    return {"workload": "videovec_embedding context-ranking training step (BASELINE configs[1] per GPU): "
+def host_cores():
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
+def sampler_streams(args, world):
+    """Reference-exact sampler streams per rank (each on its own sub-shard of the rank's videos, each with a native prefetch
+    thread).  One stream draws ~3.3 M items/s on one host core; default = what the rank's share of the host cores allows."""
+    if args.sampler_streams > 0:
+        return args.sampler_streams
+    per_rank = max(1, host_cores() // max(world, 1))
+    return max(1, min(4, per_rank // 2))
+
+
+def workload_config(args, world, c=None, prec=None, name="BASELINE configs[1] per GPU", streams=None):
+    c = c or CFG
+    prec = prec or getattr(args, "precision", "f16x3")
+    smode = getattr(args, "sampler", "sharded")
+    return {"workload": "videovec_embedding context-ranking training step (%s): "
                         "4096-d features -> %d-d embedding, window +-%d, %d negatives, B=%d triplets/GPU/step, "
-                        "dropout 0.9, squared hinge margin 2, SGD momentum" % (c["N"], c["C"] // 2, c["Nn"], c["B"]),
+                        "dropout 0.9, squared hinge margin 2, SGD momentum" % (name, c["N"], c["C"] // 2, c["Nn"], c["B"]),
             "global_batch": c["B"] * world, "K": c["K"], "N": c["N"], "C": c["C"], "Nn": c["Nn"],
-            "parallelism": "dp%d" % world, "precision": getattr(args, "precision", "f16x3"),
+            "parallelism": "dp%d" % world, "precision": prec,
             "dgrad": False, "bank_rows": c["V"] * c["S"],
+            "sampler": smode,
+            "sampler_note": ("sharded: every rank owns a shard of the videos (its own resident bank) and draws its own reference-exact "
+                             "stream(s) over it -- the G-GPU index stream is NOT the 1-GPU stream; "
+                             if smode == "sharded" else
+                             "global: ONE reference-exact stream of G*B items per step, drawn identically on every rank, rank r takes items "
+                             "[r*B, (r+1)*B) -- the G-GPU index stream is the 1-GPU stream of the global batch (SURVEY 8e); ") +
+                            "%s stream(s) per rank, batches round-robin" % (streams if streams is not None else "?"),
             "gather": "fused into the GEMMs (cp.async row gather of the bank's operand copy by two producer warps)"
-                      if fused_gather_on(args) else "materialised X (K0 kernel)",
+                      if fused_gather_for(prec, args) else "materialised X (K0 kernel)",
             "l2": "inputs larger than L2: every GEMM streams %.2f GB of gathered operand rows (> 126 MB L2)" % (
-                (c["C"] + c["Nn"]) * c["B"] * c["K"] * OPERAND_BYTES[getattr(args, "precision", "f16x3")] / 1e9)}
+                (c["C"] + c["Nn"]) * c["B"] * c["K"] * OPERAND_BYTES[prec] / 1e9)}
+
+
+class GlobalSliceSampler:
+    """SURVEY 8e's partition: one sampler stream of world*B items per step, identical on every rank; this rank's slice."""
+
+    def __init__(self, smp, rank, world, B):
+        self.smp, self.rank, self.world, self.B = smp, rank, world, B
+        R = smp.R
+        self._i = np.empty((world * B, R), np.int32); self._q = np.empty((world * B, R), np.int32)
+
+    def next_into(self, idx, quirk):
+        self.smp.next_into(self._i, self._q)
+        idx[...] = self._i[self.rank * self.B:(self.rank + 1) * self.B]
+        quirk[...] = self._q[self.rank * self.B:(self.rank + 1) * self.B]
+
+    def prefetch(self, depth):
+        self.smp.prefetch(depth)
+
+    @property
+    def ready(self):
+        return self.smp.ready
+
+    def close(self):
+        self.smp.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# one training configuration on this rank: `value` leg, per-kernel leg, `e2e` leg
+# ---------------------------------------------------------------------------------------------------
+def run_training(c, prec, args, steps, warmup, world, rank, stream, pk, want_e2e=True):
+    import torch
+    import torch.distributed as dist
+    from videovector_b200 import ops
+    from videovector_b200._lib import DROPOUT_HASH
+    B, C, Nn, K, N = c["B"], c["C"], c["Nn"], c["K"], c["N"]
+    R = C + Nn
+    fg = fused_gather_for(prec, args)
+    nstreams = sampler_streams(args, world)
+    # synthetic feature bank (resident in HBM) and the host sampler
+    vid, off, sid = ops.synthetic_videos(c["V"], c["S"])
+    if args.sampler == "global":
+        bank = ops.fill_bank(c["V"] * c["S"], K, 1234)
+        smp = GlobalSliceSampler(ops.Sampler(vid, off, sid, B * world, C, Nn, c["P"], c["swap"], c["max_same"], 100, rand_seed=1),
+                                 rank, world, B)
+        nstreams = 1
+    else:
+        bank = ops.fill_bank(c["V"] * c["S"], K, 1234 + rank)
+        smp = ops.MultiSampler(vid + rank * c["V"], off, sid, B, C, Nn, c["P"], c["swap"], c["max_same"], 100,
+                               rand_seed=1 + 16 * rank, streams=nstreams)
+    out = {"streams": nstreams}
+    with torch.cuda.stream(stream):
+        tr = ops.Trainer(ops.trainer_cfg(B, C, Nn, K, N, prec=prec, dropout_ratio=0.9, dropout_mode=DROPOUT_HASH,
+                                         dropout_seed=7, world_size=world, rank=rank), stream=stream)
+        g = torch.Generator(device="cuda").manual_seed(1701)
+        W0 = torch.randn(N, K, device="cuda", generator=g) * 0.001          # gaussian filler std 0.001, bias 0
+        tr.set_weights(W0, torch.zeros(N, device="cuda"))
+        if fg:
+            tr.set_bank(bank)          # one-time operand copy of the resident bank; the GEMMs then gather its rows themselves
+        if world > 1:
+            idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                idt.copy_(torch.frombuffer(bytearray(ops.dp_unique_id()), dtype=torch.uint8))
+            dist.broadcast(idt, 0)
+            tr.dp_init(bytes(idt.cpu().numpy().tobytes()))
+        out["dp_mode"] = tr.dp_mode + ((" (" + tr.dp_mode_reason + ")") if tr.dp_mode_reason else "")
+        total = warmup + steps
+        # ---- leg 1: `value` -- inputs already resident in HBM when the timed region starts
+        idx_host = torch.empty((total, B, R), dtype=torch.int32).pin_memory()
+        qk_host = torch.empty((total, B, R), dtype=torch.int32).pin_memory()
+        for i in range(total):
+            smp.next_into(idx_host[i].numpy(), qk_host[i].numpy())
+        idx_dev = idx_host.cuda(non_blocking=True); qk_dev = qk_host.cuda(non_blocking=True)
+        for i in range(warmup):
+            tr.step(bank, idx_dev[i], qk_dev[i], None, it=i)
+        stream.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(warmup, total):
+            tr.step(bank, idx_dev[i], qk_dev[i], None, it=i)
+        e1.record(stream)
+        stream.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        out["ms_total"] = e0.elapsed_time(e1)
+        out["launches"] = tr.last_launches * steps
+        out["loss"] = float(tr.tensor("loss").item())
+
+        # ---- leg 2: per-kernel timing inside the step (CUDA events on the launching stream)
+        tr.set_timing(True)
+        nt = min(steps, 20)
+        for i in range(nt):
+            tr.step(bank, idx_dev[warmup + i % steps], qk_dev[warmup + i % steps], None, it=total + i)
+        out["phase"], _ = tr.phase_ms()
+        tr.set_timing(False)
+        out["nsplit"] = tr._lib.vv_ip_wgrad_auto_nsplit(R * B, N, K, ops.PREC[prec])
+
+        # ---- leg 3: `e2e` -- the public API with HOST buffers: sampler (prefetch threads, as the reference's
+        # prefetching data layer) -> pinned host indices -> H2D -> step -> D2H loss, all inside the timed region
+        if want_e2e:
+            nbuf = 8                  # batches the sampler threads may run ahead (absorbs host jitter; the average rates decide)
+            hi = [torch.empty((B, R), dtype=torch.int32).pin_memory() for _ in range(nbuf)]
+            hq = [torch.empty((B, R), dtype=torch.int32).pin_memory() for _ in range(nbuf)]
+            di = [torch.empty((B, R), dtype=torch.int32, device="cuda") for _ in range(nbuf)]
+            dq = [torch.empty((B, R), dtype=torch.int32, device="cuda") for _ in range(nbuf)]
+            loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+            smp.prefetch(nbuf)        # native prefetch thread(s) (vv_sampler_prefetch), the reference's InternalThread
+            evs = [torch.cuda.Event() for _ in range(nbuf)]         # H2D of buffer k complete
+            used = [torch.cuda.Event() for _ in range(nbuf)]        # the step that read device buffer k complete
+            cstream = torch.cuda.Stream()                           # copy stream: step i+1's indices arrive under step i
+
+            def e2e_step(i):
+                k = i % nbuf
+                if i >= nbuf:
+                    evs[k].synchronize()          # the H2D copy that last read this pinned buffer (nbuf steps ago) is done
+                    cstream.wait_event(used[k])   # ... and the step that consumed device buffer k has finished with it
+                smp.next_into(hi[k].numpy(), hq[k].numpy())
+                with torch.cuda.stream(cstream):
+                    di[k].copy_(hi[k], non_blocking=True); dq[k].copy_(hq[k], non_blocking=True)
+                    evs[k].record(cstream)
+                stream.wait_event(evs[k])
+                tr.step(bank, di[k], dq[k], None, it=2 * total + i)
+                used[k].record(stream)
+                loss_host.copy_(tr.tensor("db_raw_ext")[N:N + 2], non_blocking=True)      # loss + violations, 8 bytes D2H
+            for i in range(warmup):
+                e2e_step(i)
+            stream.synchronize()
+            if world > 1:
+                dist.barrier()
+            ready0 = smp.ready        # batches drawn ahead when the clock starts ...
+            t0 = time.perf_counter()
+            for i in range(warmup, warmup + steps):
+                e2e_step(i)
+            stream.synchronize()
+            # ... must be drawn ahead again when it stops: the sampler work of exactly `steps` batches lies inside the region
+            # (a sampler-bound run would otherwise borrow up to nbuf batches drawn before t0)
+            while smp.ready < ready0 and time.perf_counter() - t0 < 120.0:
+                time.sleep(20e-6)
+            t1 = time.perf_counter()
+            smp.prefetch(0)
+            out["e2e_ms"] = 1e3 * (t1 - t0)
+            out["e2e_ring"] = {"ahead_at_t0": ready0, "ahead_at_t1": smp.ready, "depth": nbuf}
+        tr.close()
+    smp.close()
+    del bank
+    torch.cuda.empty_cache()
+    return out
+
+
+def training_kernels(c, prec, out, args, pk):
+    """Per-kernel roofline table of one training configuration from the in-step CUDA-event timings."""
+    B, C, Nn, K, N = c["B"], c["C"], c["Nn"], c["K"], c["N"]
+    R = C + Nn; M = R * B
+    phase = out["phase"]
+    flops = 2.0 * M * N * K
+    units, opb = MMA_UNITS[prec], OPERAND_BYTES[prec]
+    opw = opb if prec not in ("tf32", "fp32_simt") else 0          # bytes of a separate operand copy per element
+    tensor_peak = pk["bf16_sus"]       # the kernels are timed inside a long step: sustained peak
+    kern = {}
+    for name in ("fc7_forward", "wgrad"):
+        ms = phase[name]
+        tf = flops / (ms * 1e-3) / 1e12 if ms > 0 else None
+        kern[name] = {"ms": ms, "bound": "tensor", "achieved_tflops": tf, "frac": tf / tensor_peak if tf else None,
+                      "tensor_pipe_frac": tf * units / tensor_peak if tf else None}
+    fused_rank = phase["rank_loss_forward"] == 0
+    p2p = str(out.get("dp_mode", "")).startswith("p2p")
+    fg = fused_gather_for(prec, args)
+    bytes_alg = {"rank_loss_forward": M * N * 4,
+                 # fused K2+K3 reads H once; the two-kernel K3 reads it again
+                 "rank_loss_backward": M * N * (4 + (opw if opw else 4)),
+                 # SURVEY 8(d): read W, dW, hist + write W, hist = 5*N*K*4, + the refreshed operand copy of W
+                 "sgd_update": N * K * (5 * 4 + opw)}
+    if not fg:
+        bytes_alg["gather"] = M * K * (4 + (opw if opw else 4))
+    for name, by in bytes_alg.items():
+        ms = phase[name]
+        if (name == "rank_loss_forward" and fused_rank) or ms <= 0:
+            continue
+        key = "rank_loss_fused" if (name == "rank_loss_backward" and fused_rank) else name
+        kern[key] = {"ms": ms, "bound": "hbm", "achieved_gbs": by / (ms * 1e-3) / 1e9, "frac": by / (ms * 1e-3) / 1e9 / pk["hbm"]}
+    if "sgd_update" in kern:
+        kern["sgd_update"]["note"] = ("algorithmic bytes = 5*N*K*4 + operand refresh; the kernel also reads the %d split-K slabs the wgrad "
+                                      "wrote (not counted as algorithmic)" % out["nsplit"])
+        if p2p:
+            kern["dp_exchange_update"] = kern.pop("sgd_update")
+            kern["dp_exchange_update"].update({
+                "bound": "nvlink + hbm (not graded)", "frac": None,
+                "note": "ONE kernel: split-K sum -> rows pushed to their owner rank over NVLink -> owner adds the G contributions, "
+                        "updates its N/G rows -> pushes the new operand rows to every rank; includes waiting for the slowest rank",
+                "nvlink_bytes_out": (out["world"] - 1) * (N * K // out["world"]) * (4 + opw)})
+    if fg and phase["gather"] > 0:
+        kern["gather_plan"] = {"ms": phase["gather"], "bound": "latency (index traffic only; not graded)", "frac": None}
+    if phase.get("allreduce", 0) > 0:
+        # exposed time of the gradient exchange on the main stream: split-K reduce + wait for the NCCL all-reduce of
+        # dW [N,K] and (db, loss, violations) -- includes waiting for the slowest rank
+        kern["allreduce"] = {"ms": phase["allreduce"], "bound": "nvlink", "bytes": N * K * 4 + (N + 2) * 4}
+    return kern
+
+
+def run_inference(args, world, rank, stream, pk, prec):
+    """BASELINE configs[4]: relu(F W^T + b) over this rank's shard of the 10 M-row sweep (rows sharded 8 ways, no collective)."""
+    import torch
+    import torch.distributed as dist
+    from videovector_b200 import ops
+    K, N = CFG["K"], CFG["N"]
+    total_rows, shards = 10_000_000, 8
+    rows = total_rows // shards
+    with torch.cuda.stream(stream):
+        F = ops.fill_bank(rows, K, 4242 + rank)
+        tr = ops.Trainer(ops.trainer_cfg(4096, 5, 10, K, N, prec=prec), stream=stream)
+        g = torch.Generator(device="cuda").manual_seed(1701)
+        tr.set_weights(torch.randn(N, K, device="cuda", generator=g) * 0.01, torch.zeros(N, device="cuda"))
+        out = torch.empty((rows, N), dtype=torch.float32, device="cuda")
+        tr.extract_into(F, out)                      # warm-up (also allocates the operand staging buffer)
+        stream.synchronize()
+        if world > 1:
+            dist.barrier()
+        reps = 3
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            tr.extract_into(F, out)
+        e1.record(stream)
+        stream.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        launches = tr.last_launches
+        # e2e: HOST rows -> H2D -> extract -> D2H embeddings, on a bounded chunk of the shard (PCIe-bound by construction)
+        chunk = 65536
+        Fh = torch.empty((chunk, K), dtype=torch.float32).pin_memory()
+        Fh.copy_(F[:chunk])
+        Oh = torch.empty((chunk, N), dtype=torch.float32).pin_memory()
+        Fd = torch.empty((chunk, K), dtype=torch.float32, device="cuda"); Od = torch.empty((chunk, N), dtype=torch.float32, device="cuda")
+        def e2e_once():
+            Fd.copy_(Fh, non_blocking=True)
+            tr.extract_into(Fd, Od)
+            Oh.copy_(Od, non_blocking=True)
+        e2e_once(); stream.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            e2e_once()
+        stream.synchronize()
+        e2e_ms = 1e3 * (time.perf_counter() - t0) / 3
+        tr.close()
+    del F, out
+    torch.cuda.empty_cache()
+    t = torch.tensor([ms, e2e_ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = float(t[0]), float(t[1])
+    by = rows * (K + N) * 4
+    fl = 2.0 * rows * K * N
+    units = MMA_UNITS[prec]
+    return {
+        "metric": "embedding inference rows/sec", "unit": "rows/s", "value": world * rows / (ms * 1e-3), "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "dtype": DTYPE[prec], "gpu_launches": launches,
+        "config": {"workload": "embedding inference sweep (BASELINE configs[4]): relu(F W^T + b), 10 M synthetic 4096-d rows -> %d-d, "
+                               "rows sharded 8 ways, this run holds %d of the 8 shards (one per GPU, %d rows each), no collective; "
+                               "one step = one pass over the shard" % (N, world, rows),
+                   "rows_per_gpu": rows, "K": K, "N": N, "precision": prec, "parallelism": "row-sharded x%d" % world},
+        "roofline": {"bound": "hbm", "achieved": by / (ms * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                     "frac": by / (ms * 1e-3) / 1e9 / pk["hbm"], "traffic": None,
+                     "algorithmic_bytes_per_row": (K + N) * 4,
+                     "tensor_pipe_frac": fl / (ms * 1e-3) / 1e12 * units / pk["bf16_sus"],
+                     "note": "SURVEY 8(d): at N=512 with fp32 input this sits at the ridge (AI 227 flop/B); both fractions reported"},
+        "e2e": {"value": world * chunk / (e2e_ms * 1e-3), "unit": "rows/s", "h2d_bytes_per_step": chunk * K * 4,
+                "d2h_bytes_per_step": chunk * N * 4, "ms_per_step": e2e_ms,
+                "note": "pinned host rows -> H2D -> vv_trainer_extract -> D2H embeddings on a %d-row chunk: PCIe-bound" % chunk},
+    }
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -218,8 +519,6 @@ def workload_config(args, world):
 def run_gpu(args):
     import torch
     import torch.distributed as dist
-    from videovector_b200 import ops
-    from videovector_b200._lib import DROPOUT_HASH
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -233,156 +532,42 @@ def run_gpu(args):
     R = C + Nn
     prec = args.precision
     pk = peaks()
-
-    # synthetic feature bank (resident in HBM) and the host sampler.  Data parallel: every rank owns a
-    # shard of the videos and runs its own reference-exact sampler stream over it (no data-path collective).
-    bank = ops.fill_bank(c["V"] * c["S"], K, 1234 + rank)
-    vid, off, sid = ops.synthetic_videos(c["V"], c["S"])
-    smp = ops.Sampler(vid + rank * c["V"], off, sid, B, C, Nn, c["P"], c["swap"], c["max_same"], 100, rand_seed=1 + rank)
-
     stream = torch.cuda.Stream()
-    with torch.cuda.stream(stream):
-        tr = ops.Trainer(ops.trainer_cfg(B, C, Nn, K, N, prec=prec, dropout_ratio=0.9, dropout_mode=DROPOUT_HASH,
-                                         dropout_seed=7, world_size=world, rank=rank), stream=stream)
-        g = torch.Generator(device="cuda").manual_seed(1701)
-        W0 = torch.randn(N, K, device="cuda", generator=g) * 0.001          # gaussian filler std 0.001, bias 0
-        tr.set_weights(W0, torch.zeros(N, device="cuda"))
-        if fused_gather_on(args):
-            tr.set_bank(bank)          # one-time operand copy of the resident bank; the GEMMs then gather its rows themselves
-        if world > 1:
-            idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
-            if rank == 0:
-                idt.copy_(torch.frombuffer(bytearray(ops.dp_unique_id()), dtype=torch.uint8))
-            dist.broadcast(idt, 0)
-            tr.dp_init(bytes(idt.cpu().numpy().tobytes()))
 
-        total = args.warmup + args.steps
-        # ---- leg 1: `value` -- inputs already resident in HBM when the timed region starts
-        idx_host = torch.empty((total, B, R), dtype=torch.int32).pin_memory()
-        qk_host = torch.empty((total, B, R), dtype=torch.int32).pin_memory()
-        for i in range(total):
-            smp.next_into(idx_host[i].numpy(), qk_host[i].numpy())
-        idx_dev = idx_host.cuda(non_blocking=True); qk_dev = qk_host.cuda(non_blocking=True)
-        for i in range(args.warmup):
-            tr.step(bank, idx_dev[i], qk_dev[i], None, it=i)
-        stream.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        clocks = ClockSampler(local); clocks.start()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for i in range(args.warmup, total):
-            tr.step(bank, idx_dev[i], qk_dev[i], None, it=i)
-        e1.record(stream)
-        stream.synchronize()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        ms_total = e0.elapsed_time(e1)
-        launches = tr.last_launches * args.steps
-        loss_final = float(tr.tensor("loss").item())
-
-        # ---- leg 2: per-kernel timing inside the step (CUDA events on the launching stream)
-        tr.set_timing(True)
-        nt = min(args.steps, 20)
-        for i in range(nt):
-            tr.step(bank, idx_dev[args.warmup + i % args.steps], qk_dev[args.warmup + i % args.steps], None, it=total + i)
-        phase, _ = tr.phase_ms()
-        tr.set_timing(False)
-
-        # ---- leg 3: `e2e` -- the public API with HOST buffers: sampler (prefetch thread, as the reference's
-        # prefetching data layer) -> pinned host indices -> H2D -> step -> D2H loss, all inside the timed region
-        nbuf = 8                  # batches the sampler thread may run ahead (absorbs host jitter; the average rates decide)
-        hi = [torch.empty((B, R), dtype=torch.int32).pin_memory() for _ in range(nbuf)]
-        hq = [torch.empty((B, R), dtype=torch.int32).pin_memory() for _ in range(nbuf)]
-        di = [torch.empty((B, R), dtype=torch.int32, device="cuda") for _ in range(nbuf)]
-        dq = [torch.empty((B, R), dtype=torch.int32, device="cuda") for _ in range(nbuf)]
-        loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
-        e2e_steps = args.steps
-        smp.prefetch(nbuf)        # native prefetch thread (vv_sampler_prefetch), the reference's InternalThread
-        evs = [torch.cuda.Event() for _ in range(nbuf)]         # H2D of buffer k complete
-        used = [torch.cuda.Event() for _ in range(nbuf)]        # the step that read device buffer k complete
-        cstream = torch.cuda.Stream()                           # copy stream: step i+1's indices arrive under step i
-
-        def e2e_step(i):
-            k = i % nbuf
-            if i >= nbuf:
-                evs[k].synchronize()          # the H2D copy that last read this pinned buffer (nbuf steps ago) is done
-                cstream.wait_event(used[k])   # ... and the step that consumed device buffer k has finished with it
-            smp.next_into(hi[k].numpy(), hq[k].numpy())
-            with torch.cuda.stream(cstream):
-                di[k].copy_(hi[k], non_blocking=True); dq[k].copy_(hq[k], non_blocking=True)
-                evs[k].record(cstream)
-            stream.wait_event(evs[k])
-            tr.step(bank, di[k], dq[k], None, it=2 * total + i)
-            used[k].record(stream)
-            loss_host.copy_(tr.tensor("db_raw_ext")[N:N + 2], non_blocking=True)      # loss + violations, 8 bytes D2H
-        for i in range(args.warmup):
-            e2e_step(i)
-        stream.synchronize()
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        for i in range(args.warmup, args.warmup + e2e_steps):
-            e2e_step(i)
-        stream.synchronize()
-        t1 = time.perf_counter()
-        smp.prefetch(0)
-        e2e_ms = 1e3 * (t1 - t0)
-        # one sampler over the timed `value` region, the per-kernel timing steps and the timed e2e region (all the same
-        # workload): a 100 ms poll would see nothing of a short --steps run otherwise; idle samples are filtered by power
-        clk = clocks.stop()
-        clk["window"] = "value + per-kernel + e2e legs"
-
-    # max over ranks
-    if world > 1:
-        t = torch.tensor([ms_total, e2e_ms], device="cuda", dtype=torch.float64)
+    def reduce_max(vals):
+        if world == 1:
+            return [float(v) for v in vals]
+        t = torch.tensor(vals, device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, e2e_ms = float(t[0]), float(t[1])
+        return [float(v) for v in t]
+
+    # ---- the headline: BASELINE configs[1] per GPU
+    clocks = ClockSampler(local); clocks.start()
+    out = run_training(c, prec, args, args.steps, args.warmup, world, rank, stream, pk)
+    out["world"] = world
+    # one sampler over the timed `value` region, the per-kernel timing steps and the timed e2e region (all the same
+    # workload): a 100 ms poll would see nothing of a short --steps run otherwise; idle samples are filtered by power
+    clk = clocks.stop()
+    clk["window"] = "value + per-kernel + e2e legs of the headline configuration"
+    ms_total, e2e_ms = reduce_max([out["ms_total"], out["e2e_ms"]])
     ms_step = ms_total / args.steps
     value = world * B / (ms_step * 1e-3)
-    e2e_val = world * B * e2e_steps / (e2e_ms * 1e-3)
+    e2e_val = world * B * args.steps / (e2e_ms * 1e-3)
 
+    line = None
     if rank == 0:
         M = R * B
-        flops = 2.0 * M * N * K
         units = MMA_UNITS[prec]
-        opb = OPERAND_BYTES[prec]
-        # peak of the full-rate 16-bit tensor pipe, measured (sustained: the kernel is timed inside a long step)
         tensor_peak = pk["bf16_sus"]
-        kern = {}
-        for name, f in (("fc7_forward", flops), ("wgrad", flops)):
-            ms = phase[name]
-            tf = flops / (ms * 1e-3) / 1e12 if ms > 0 else None
-            kern[name] = {"ms": ms, "bound": "tensor", "achieved_tflops": tf, "frac": tf / tensor_peak if tf else None,
-                          "tensor_pipe_frac": tf * units / tensor_peak if tf else None}
-        fused_rank = phase["rank_loss_forward"] == 0
-        bytes_alg = {"gather": (M * K * (4 + (opb if prec not in ("tf32", "fp32_simt") else 4))) if not fused_gather_on(args)
-                     else ((M + 127) // 128 * 128) * 8 + M * 8,
-                     "rank_loss_forward": M * N * 4,
-                     # fused K2+K3 reads H once; the two-kernel K3 reads it again
-                     "rank_loss_backward": M * N * (4 + (opb if prec not in ("tf32", "fp32_simt") else 4)),
-                     "sgd_update": N * K * (4 * (5 + tr._lib.vv_ip_wgrad_auto_nsplit(M, N, K, ops.PREC[prec]))
-                                            + (opb if prec not in ("tf32", "fp32_simt") else 0))}
-        for name, by in bytes_alg.items():
-            ms = phase[name]
-            if name == "rank_loss_forward" and fused_rank:
-                continue
-            key = "rank_loss_fused" if (name == "rank_loss_backward" and fused_rank) else name
-            kern[key] = {"ms": ms, "bound": "hbm", "achieved_gbs": by / (ms * 1e-3) / 1e9 if ms > 0 else None,
-                         "frac": by / (ms * 1e-3) / 1e9 / pk["hbm"] if ms > 0 else None}
-        if phase.get("allreduce", 0) > 0:
-            # exposed time of the gradient exchange on the main stream: split-K reduce + wait for the NCCL all-reduce of
-            # dW [N,K] and (db, loss, violations) -- includes waiting for the slowest rank
-            kern["allreduce"] = {"ms": phase["allreduce"], "bound": "nvlink", "bytes": N * K * 4 + (N + 2) * 4}
+        kern = training_kernels(c, prec, out, args, pk)
+        phase = out["phase"]
         dom = "wgrad" if phase["wgrad"] >= phase["fc7_forward"] else "fc7_forward"
         ach = kern[dom]["achieved_tflops"]
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
-            key = prec + ("_gathered" if fused_gather_on(args) else "")
+            key = prec + ("_gathered" if fused_gather_for(prec, args) else "")
             traffic = json.load(open(tpath)).get(key, {}).get(dom)
         roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": tensor_peak, "unit": "TFLOP/s",
                     "frac": ach / tensor_peak if ach else None, "traffic": traffic,
@@ -395,26 +580,63 @@ def run_gpu(args):
                             "inside the step), against the measured full-rate 16-bit tensor peak.  The fp32-parity modes "
                             "spend several tensor-core products per algorithmic product (mma_units_per_product, in units "
                             "of one full-rate 16-bit MMA); tensor_pipe_frac = frac x units is the pipe's utilisation"}
+        cfgd = workload_config(args, world, streams=out["streams"])
+        cfgd["dp_mode"] = out["dp_mode"]
         line = {
             "metric": METRIC, "value": value, "unit": "triplets/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": DTYPE[prec],
-            "data": "synthetic", "config": workload_config(args, world),
-            "clocks": clk, "gpu_launches": launches,
+            "data": "synthetic", "config": cfgd,
+            "clocks": clk, "gpu_launches": out["launches"],
             "e2e": {"value": e2e_val, "unit": "triplets/s", "h2d_bytes_per_step": 2 * B * R * 4, "d2h_bytes_per_step": 8,
-                    "ms_per_step": e2e_ms / e2e_steps,
-                    "note": "host sampler on a prefetch thread -> pinned int32 [B,R] indices -> H2D -> vv_trainer_step -> "
-                            "D2H loss; the feature bank is resident in HBM (uploaded once, like opening the LMDB)"},
-            "roofline": roofline, "kernels": kern, "loss": loss_final,
+                    "ms_per_step": e2e_ms / args.steps, "ring": out["e2e_ring"],
+                    "note": "host sampler on prefetch thread(s) -> pinned int32 [B,R] indices -> H2D -> vv_trainer_step -> "
+                            "D2H loss; the feature bank is resident in HBM (uploaded once, like opening the LMDB); the clock stops "
+                            "only when the sampler is as far ahead as it was when the clock started"},
+            "roofline": roofline, "kernels": kern, "loss": out["loss"],
             "hinge_terms_per_s": value * Nn,
         }
+
+    # ---- the other BASELINE configurations, same run (each with value, ms_per_step, roofline.frac, e2e)
+    extra = {}
+    if not args.no_extra_configs:
+        xs = max(10, min(args.steps, 60))
+        # configs[2]: bf16 tensor-core mode, 4096 triplets per GPU (32 k per step on 8 GPUs)
+        o2 = run_training(c, "bf16", args, xs, args.warmup, world, rank, stream, pk); o2["world"] = world
+        # configs[3]: large window, N=1024, C=17 (+-8), 50 negatives: the HBM-bound loss kernels matter here
+        c4 = dict(c, C=17, Nn=50, N=1024)
+        o4 = run_training(c4, prec, args, max(5, xs // 4), args.warmup, world, rank, stream, pk); o4["world"] = world
+        for name, cc, pp, oo, st, label in (("bf16_dp", c, "bf16", o2, xs, "BASELINE configs[2] per GPU"),
+                                            ("large_window", c4, prec, o4, max(5, xs // 4), "BASELINE configs[3] per GPU")):
+            mt, em = reduce_max([oo["ms_total"], oo["e2e_ms"]])
+            if rank == 0:
+                ms1 = mt / st
+                kk = training_kernels(cc, pp, oo, args, pk)
+                dom = "wgrad" if oo["phase"]["wgrad"] >= oo["phase"]["fc7_forward"] else "fc7_forward"
+                Bc = cc["B"]
+                cf = workload_config(args, world, cc, pp, label, streams=oo["streams"]); cf["dp_mode"] = oo["dp_mode"]
+                extra[name] = {
+                    "metric": METRIC, "unit": "triplets/s", "value": world * Bc / (ms1 * 1e-3), "ms_per_step": ms1, "steps": st,
+                    "higher_is_better": True, "scaling": "weak", "dtype": DTYPE[pp], "gpu_launches": oo["launches"], "config": cf,
+                    "roofline": {"kernel": dom, "bound": "tensor", "achieved": kk[dom]["achieved_tflops"], "peak": pk["bf16_sus"],
+                                 "unit": "TFLOP/s", "frac": kk[dom]["frac"], "tensor_pipe_frac": kk[dom]["tensor_pipe_frac"],
+                                 "mma_units_per_product": MMA_UNITS[pp], "traffic": None},
+                    "kernels": kk, "loss": oo["loss"],
+                    "e2e": {"value": world * Bc * st / (em * 1e-3), "unit": "triplets/s", "ms_per_step": em / st,
+                            "h2d_bytes_per_step": 2 * Bc * (cc["C"] + cc["Nn"]) * 4, "d2h_bytes_per_step": 8, "ring": oo["e2e_ring"]}}
+        # configs[4]: inference sweep, rows sharded
+        inf = run_inference(args, world, rank, stream, pk, "bf16")
+        if rank == 0:
+            extra["inference"] = inf
+    if rank == 0:
+        if extra:
+            line["configs"] = extra
         if world == 1 and not args.no_cpu_baseline:
             val, ms, cores, ph, kind = cpu_reference_run(5, 2)
             line["cpu_baseline"] = {"value": val, "unit": "triplets/s", "cores": cores, "kind": kind, "note": CPU_NOTE[kind],
                                     "sample": "B=%d items per step (1/%d of the GPU step), same K/N/C/Nn, 5 timed steps after 2 warm-up"
                                               % (CPU_SAMPLE_B, B // CPU_SAMPLE_B), "ms_per_step": ms, "phase_ms": ph}
         print(json.dumps(line))
-    tr.close(); smp.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -429,6 +651,11 @@ def main():
     ap.add_argument("--precision", default="f16x3", choices=["tf32x3", "f16x3", "tf32", "bf16", "fp32_simt"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--materialised-gather", action="store_true", help="run K0 as its own kernel (materialised X operand) instead of gathering inside the GEMMs")
+    ap.add_argument("--sampler", default="sharded", choices=["sharded", "global"],
+                    help="sharded: every rank draws its own reference-exact stream(s) over its shard of the videos; "
+                         "global: one stream of G*B items per step (SURVEY 8e), every rank takes its slice")
+    ap.add_argument("--sampler-streams", type=int, default=0, help="reference-exact sampler streams per rank (0 = from the host core count)")
+    ap.add_argument("--no-extra-configs", action="store_true", help="only the headline configuration (skip configs[2], [3], [4])")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

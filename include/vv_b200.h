@@ -381,6 +381,11 @@ int vv_sampler_cursor(const vv_sampler_t* s);
  * thread draws up to `depth` batches ahead, vv_sampler_next hands them out in order (same stream as without it).
  * depth <= 0 stops the thread; batches already drawn are still served first. */
 int vv_sampler_prefetch(vv_sampler_t* s, int depth);
+int vv_sampler_prefetch_ready(vv_sampler_t* s);   /* batches drawn ahead and not yet handed out */
+/* A sampler built over a SUB-SHARD of the videos (its shot tables start at 0) whose rows live at [row_base, ...) of a
+ * larger resident bank: every emitted index (idx, and quirk where >= 0) is offset by row_base.  Lets k samplers over k
+ * disjoint sub-shards -- each reference-exact on its own videos, each with its own prefetch thread -- feed one GPU. */
+int vv_sampler_set_row_base(vv_sampler_t* s, int32_t row_base);
 /* the generator alone, for tests against libc rand() */
 typedef struct vv_glibc_rand vv_glibc_rand_t;
 vv_glibc_rand_t* vv_glibc_rand_create(unsigned int seed);

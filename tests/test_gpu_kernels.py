@@ -117,7 +117,11 @@ SHAPES = [(1920, 512, 4096),   # cfg-1: B=128, R=15
           (128, 256, 64),      # exactly one tile, two k-blocks (bf16) / two (tf32)
           (130, 264, 72),      # ragged M, N, K tails (TMA zero fill + predicated stores)
           (200, 24, 40),       # smaller than one tile in every dimension
-          (1005, 1024, 512)]   # cfg-4 embedding width
+          (1005, 1024, 512),   # cfg-4 embedding width
+          # > 4 work units per CTA of the persistent kernels (157 m-tile pairs x 2 n-tiles on 74 clusters) with an ODD number
+          # of 512-element promotion chunks per unit (K = 1280 = 2.5 chunks): the unit-to-unit hand-off -- the epilogue of tile
+          # i under the main loop of tile i+1, the stage ring and both TMEM buffers carried across units -- against fp64
+          (40000, 512, 1280)]
 
 
 def _inputs(M, N, K, seed=0):

@@ -123,6 +123,8 @@ SIGNATURES = {
     "vv_sampler_next": (_i, [_P, _P, _P]),
     "vv_sampler_cursor": (_i, [_P]),
     "vv_sampler_prefetch": (_i, [_P, _i]),
+    "vv_sampler_prefetch_ready": (_i, [_P]),
+    "vv_sampler_set_row_base": (_i, [_P, C.c_int32]),
     "vv_glibc_rand_create": (_P, [C.c_uint]),
     "vv_glibc_rand_next": (_i, [_P]),
     "vv_glibc_rand_destroy": (None, [_P]),

@@ -143,6 +143,7 @@ struct vv_sampler {
   };
   Ring* ring = nullptr;
   int served_cursor = -1;
+  int32_t row_base = 0;                   // added to every emitted bank row (sub-shard samplers over one bank)
   void stop_prefetch() {
     if (!ring) return;
     if (ring->running) {
@@ -406,13 +407,31 @@ extern "C" vv_sampler_t* vv_sampler_create_ex(int num_videos, const int32_t* vid
 extern "C" void vv_sampler_destroy(vv_sampler_t* s) { if (s) { s->stop_prefetch(); delete s->ring; s->ring = nullptr; } delete s; }
 extern "C" int vv_sampler_next(vv_sampler_t* s, int32_t* idx, int32_t* quirk) {
   if (!s || !idx || !quirk) return VV_ERR_INVALID;
-  if (s->ring && (s->ring->running || s->ring->count > 0)) return s->pop(idx, quirk);
-  s->served_cursor = -1;
-  return s->next(idx, quirk);
+  int rc;
+  if (s->ring && (s->ring->running || s->ring->count > 0)) rc = s->pop(idx, quirk);
+  else { s->served_cursor = -1; rc = s->next(idx, quirk); }
+  if (rc == 0 && s->row_base != 0) {
+    // this sampler's videos are a sub-shard of a larger bank: its rows start at row_base there
+    const size_t n = size_t(s->B) * (s->C + s->Nn);
+    const int32_t base = s->row_base;
+    for (size_t i = 0; i < n; ++i) { idx[i] += base; quirk[i] += quirk[i] >= 0 ? base : 0; }
+  }
+  return rc;
+}
+extern "C" int vv_sampler_set_row_base(vv_sampler_t* s, int32_t row_base) {
+  if (!s || row_base < 0) return VV_ERR_INVALID;
+  s->row_base = row_base;
+  return 0;
 }
 extern "C" int vv_sampler_prefetch(vv_sampler_t* s, int depth) {
   if (!s || depth > 1024) return VV_ERR_INVALID;
   return s->start_prefetch(depth);
+}
+extern "C" int vv_sampler_prefetch_ready(vv_sampler_t* s) {
+  if (!s) return VV_ERR_INVALID;
+  if (!s->ring) return 0;
+  std::lock_guard<std::mutex> l(s->ring->m);
+  return s->ring->count;
 }
 extern "C" int vv_sampler_cursor(const vv_sampler_t* s) {
   if (!s) return -1;

@@ -377,6 +377,8 @@ extern "C" float* vv_trainer_blob(vv_trainer_t* t, const char* name) {
   if (n == "db_raw") return t->dbx.as<float>();
   if (n == "dX") return t->dX.as<float>();
   if (n == "wlast") return t->wlast.as<float>();
+  if (n == "dZop_hi") return t->dZ_hi.as<float>();   // raw operand planes of dZ (F16X3: the 128-byte header precedes hi)
+  if (n == "dZop_lo") return t->dZ_lo.as<float>();
   if (n == "Wop_hi") return t->W_hi.as<float>();     // raw operand planes of W (layout per precision, vv_operand_bytes)
   if (n == "Wop_lo") return t->W_lo.as<float>();
   set_error("unknown trainer blob '%s'", n.c_str());

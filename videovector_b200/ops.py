@@ -379,6 +379,11 @@ class Sampler:
         check(self._lib.vv_sampler_prefetch(self._h, int(depth)))
 
     @property
+    def ready(self):
+        """Batches the prefetch thread has drawn ahead and not yet handed out."""
+        return self._lib.vv_sampler_prefetch_ready(self._h)
+
+    @property
     def cursor(self):
         return self._lib.vv_sampler_cursor(self._h)
 
@@ -392,6 +397,55 @@ class Sampler:
             self.close()
         except Exception:
             pass
+
+
+class MultiSampler:
+    """k reference-exact sampler streams over k disjoint sub-shards of the videos, one native prefetch thread each;
+    batch i comes from stream i % k.  Each stream is the reference's sampler on its own videos (own rand() stream seeded
+    rand_seed + s, own negative buffer); a single sequential stream tops out near 3.3 M items/s per host core, k streams
+    feed a GPU k times faster.  streams=1 is exactly Sampler."""
+
+    def __init__(self, video_id, shot_off, shot_ids, batch_size, context_size=5, num_negative_samples=10,
+                 max_buffer_size=5000, negative_swap_percentage=50, max_same_video_negs=6,
+                 max_tries_for_negs=100, rand_seed=1, context_type="window", streams=2, row_base=0):
+        video_id = np.ascontiguousarray(video_id, dtype=np.int32)
+        shot_off = np.ascontiguousarray(shot_off, dtype=np.int32)
+        shot_ids = np.ascontiguousarray(shot_ids, dtype=np.int32)
+        V = len(video_id)
+        assert 1 <= streams <= V
+        self.B, self.R = batch_size, context_size + num_negative_samples
+        self.parts = []
+        for s in range(streams):
+            v0, v1 = s * V // streams, (s + 1) * V // streams
+            sm = Sampler(video_id[v0:v1], shot_off[v0:v1 + 1] - shot_off[v0], shot_ids[shot_off[v0]:shot_off[v1]], batch_size,
+                         context_size, num_negative_samples, max_buffer_size, negative_swap_percentage, max_same_video_negs,
+                         max_tries_for_negs, rand_seed + s, context_type)
+            check(sm._lib.vv_sampler_set_row_base(sm._h, int(row_base + shot_off[v0])))
+            self.parts.append(sm)
+        self._i = 0
+
+    def next_into(self, idx, quirk):
+        self.parts[self._i % len(self.parts)].next_into(idx, quirk)
+        self._i += 1
+
+    def next(self):
+        idx = np.empty((self.B, self.R), dtype=np.int32); quirk = np.empty((self.B, self.R), dtype=np.int32)
+        self.next_into(idx, quirk)
+        return idx, quirk
+
+    def prefetch(self, depth):
+        """depth = batches drawn ahead over ALL streams (rounded up to a multiple of the stream count); 0 stops."""
+        k = len(self.parts)
+        for sm in self.parts:
+            sm.prefetch((depth + k - 1) // k if depth > 0 else 0)
+
+    @property
+    def ready(self):
+        return sum(sm.ready for sm in self.parts)
+
+    def close(self):
+        for sm in self.parts:
+            sm.close()
 
 
 # ---------------------------------------------------------------------------------
@@ -454,10 +508,27 @@ class Trainer:
         # raw operand planes of W as float32 words (f16x3 / bf16: 2-byte elements; tf32x3: hi fp32, lo two bf16 planes)
         pw = {PREC["f16x3"]: (N * K // 2, N * K // 2), PREC["bf16"]: (N * K // 2, 0), PREC["tf32x3"]: (N * K, N * K)}.get(self.cfg.prec, (0, 0))
         shapes["Wop_hi"], shapes["Wop_lo"] = (pw[0],), (pw[1],)
+        MN = self.M * N
+        pz = {PREC["f16x3"]: (MN // 2, MN // 2), PREC["bf16"]: (MN // 2, 0), PREC["tf32x3"]: (MN, MN)}.get(self.cfg.prec, (0, 0))
+        shapes["dZop_hi"], shapes["dZop_lo"] = (pz[0],), (pz[1],)
         ptr = L.vv_trainer_blob(self._h, (b"db_raw" if which == "db_raw_ext" else which.encode()))
         if not ptr:
             raise VVError("trainer blob %s is not allocated in this configuration" % which)
         return _device_view(ptr, shapes[which])
+
+    def dZ_from_operand(self):
+        """fp32 dZ [M,N] reconstructed from the operand copy the wgrad multiplies (f16x3: (h0 + h1) / scale; bf16: the
+        bf16 values) -- the gather-fused path keeps no fp32 dZ."""
+        N = self.cfg.N
+        hi = self.tensor("dZop_hi")
+        if self.cfg.prec == PREC["f16x3"]:
+            ptr = self._lib.vv_trainer_blob(self._h, b"dZop_hi")
+            scale = _device_view(ptr - _lib.F16X3_HEADER_BYTES, (4,))[0]
+            h0 = hi.view(torch.float16).float(); h1 = self.tensor("dZop_lo").view(torch.float16).float()
+            return ((h0 + h1) / scale).view(self.M, N)
+        if self.cfg.prec == PREC["bf16"]:
+            return hi.view(torch.bfloat16).float().view(self.M, N)
+        raise VVError("dZ_from_operand: f16x3 / bf16 only")
 
     def set_weights(self, W, b):
         self.tensor("W").copy_(W)
@@ -477,6 +548,9 @@ class Trainer:
         out = torch.empty((F.shape[0], self.cfg.N), dtype=torch.float32, device=F.device)
         check(self._lib.vv_trainer_extract(self._h, _ptr(F), F.shape[0], _ptr(out)))
         return out
+
+    def extract_into(self, F, out):
+        check(self._lib.vv_trainer_extract(self._h, _ptr(F), F.shape[0], _ptr(out)))
 
     @property
     def last_launches(self):
