@@ -288,6 +288,7 @@ int vv_dropout_make_mask_mode(uint32_t* mask01, int rows, int cols, float ratio,
 int vv_eltwise_sum_forward(const float* const* bottoms, const float* coeffs, int nb, int64_t n, float* top, vv_stream_t s); /* eltwise_layer.cu:48-54; host arrays of device ptrs */
 int vv_eltwise_prod_forward(const float* a, const float* b, int64_t n, float* top, vv_stream_t s);  /* eltwise_layer.cu:41-47 */
 int vv_axpby(int64_t n, float alpha, const float* x, float beta, float* y, vv_stream_t s);         /* y = alpha*x + beta*y */
+int vv_sign_axpy(int64_t n, float alpha, const float* x, float* y, vv_stream_t s);   /* y += alpha*sign(x): L1 decay, solver.cpp:547-554 */
 int vv_mul(int64_t n, const float* a, const float* b, float* y, vv_stream_t s);
 int vv_l2norm_forward(const float* x, int num, int dim, float* y, vv_stream_t s);                   /* normalization_layer.cu:10-45 */
 int vv_l2norm_backward(const float* x, const float* dy, int num, int dim, float* dx, vv_stream_t s);/* normalization_layer.cu:47-97 */

@@ -51,6 +51,23 @@ def _worker(rank, world, port, q):
         q.put(dict(dW=float(np.abs(t[0].numpy() - glob["dW"]).max() / np.abs(glob["dW"]).max()),
                    db=float(np.abs(t[1].numpy() - glob["db"]).max() / np.abs(glob["db"]).max()),
                    loss=float(abs(t[2].item() - glob["loss"][0])), viol=float(viol.item() - glob["violations"][0])))
+    # ---- the peer-memory exchange's protocol on the host (reduce-scatter by push, owner update, all-gather by push):
+    # owner-sharded updates reproduce the replicated all-reduce + full update, and every rank ends with the same W
+    r0, r1 = dp.owner_rows(N, rank, world)
+    mine = torch.from_numpy(loc["dW"].copy())
+    everyone = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(everyone, mine)                                    # "push": every rank's contribution, by source rank
+    hist = np.zeros_like(W)
+    Wr, hr = dp.owner_update([e.numpy()[r0:r1] for e in everyone], W[r0:r1], hist[r0:r1], 0.05, 0.9, 5e-4, world)
+    rows = [torch.empty((N // world, K), dtype=torch.float32) for _ in range(world)]
+    dist.all_gather(rows, torch.from_numpy(np.ascontiguousarray(Wr)))  # "push" of the updated rows to every rank
+    W_sharded = torch.cat(rows).numpy()
+    W_repl, _, _ = orc.sgd_update(W, t[0].numpy(), hist, 0.05, 0.9, 5e-4)    # all-reduce mean + full update on one rank
+    chk = torch.from_numpy(W_sharded.copy()); lo = chk.clone()
+    dist.all_reduce(chk, op=dist.ReduceOp.MAX); dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        q.put(dict(sharded_vs_replicated=float(np.abs(W_sharded - W_repl).max() / np.abs(W_repl).max()),
+                   replicas_identical=bool(torch.equal(chk, lo))))
     # ---- sharded streams: each rank samples only from its own videos
     v0, v1 = dp.shard_videos(V, rank, world)
     s2 = ops.Sampler(vid[v0:v1], off[v0:v1 + 1] - off[v0], sid[off[v0]:off[v1]], B, C, Nn, 60, 50, 6, 100, rand_seed=1 + rank)
@@ -72,12 +89,13 @@ def test_dp_two_ranks_gloo(vvlib, oracle):
     for p in procs:
         p.start()
     res = {}
-    for _ in range(2):
+    for _ in range(3):
         res.update(q.get(timeout=180))
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
     assert res["dW"] < 2e-6 and res["db"] < 2e-6 and res["loss"] < 1e-6 and res["viol"] == 0.0, res
+    assert res["sharded_vs_replicated"] < 1e-6 and res["replicas_identical"], res
     assert res["shard_ok"] == 1
 
 

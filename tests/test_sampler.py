@@ -236,3 +236,29 @@ def test_prefetch_thread_serves_the_same_stream(vvlib):
     pf.close()                      # ring full, producer blocked
     with pytest.raises(Exception):
         ops.Sampler(*args, rand_seed=1).prefetch(5000)
+
+
+def test_multi_stream_sampler_is_k_reference_exact_streams(vvlib):
+    """ops.MultiSampler: k sub-shard samplers (each the reference's sampler on its own videos, own rand() stream and
+    negative buffer, own prefetch thread), batches round-robin; indices are offset into the common bank."""
+    V, S, B, C, Nn = 96, 20, 24, 5, 10
+    vid, off, sid = ops.synthetic_videos(V, S)
+    for k in (1, 2, 3):
+        ms = ops.MultiSampler(vid, off, sid, B, C, Nn, 300, 50, 6, 100, rand_seed=5, streams=k, row_base=1000)
+        ms.prefetch(4)
+        parts = []
+        for s in range(k):
+            v0, v1 = s * V // k, (s + 1) * V // k
+            parts.append((ops.Sampler(vid[v0:v1], off[v0:v1 + 1] - off[v0], sid[off[v0]:off[v1]], B, C, Nn, 300, 50, 6, 100,
+                                      rand_seed=5 + s), 1000 + int(off[v0]), int(off[v0]), int(off[v1])))
+        for it in range(3 * k + 1):
+            idx, quirk = ms.next()
+            smp, base, lo, hi = parts[it % k]
+            ri, rq = smp.next()
+            assert np.array_equal(idx, ri + base) and np.array_equal(quirk, np.where(rq >= 0, rq + base, rq))
+            assert idx.min() >= 1000 + lo and idx.max() < 1000 + hi          # stays inside its sub-shard of the bank
+        ms.prefetch(0)
+        assert ms.ready >= 0
+        ms.close()
+        for p in parts:
+            p[0].close()

@@ -95,6 +95,7 @@ SIGNATURES = {
     "vv_eltwise_prod_forward": (_i, [_P, _P, _i64, _P, _P]),
     "vv_axpby": (_i, [_i64, _f, _P, _f, _P, _P]),
     "vv_mul": (_i, [_i64, _P, _P, _P, _P]),
+    "vv_sign_axpy": (_i, [_i64, _f, _P, _P, _P]),
     "vv_l2norm_forward": (_i, [_P, _i, _i, _P, _P]),
     "vv_l2norm_backward": (_i, [_P, _P, _i, _i, _P, _P]),
     "vv_rowsum_forward": (_i, [_P, _i, _i, _i, _P, _P]),

@@ -267,6 +267,10 @@ bool Net<Dtype>::EnableFusion(string* why) {
   FUSE_REQUIRE(ipp.inner_product_param().bias_term(), "fc7 without bias is not fused");
   const int N = ipp.inner_product_param().num_output();
   FUSE_REQUIRE(N % 4 == 0 && K % 4 == 0 && N <= 4096, "embedding / feature dims must be multiples of 4 (N <= 4096)");
+  // the tensor-core GEMMs (and the row gather) need N % 8 == 0 and K % 8 == 0 (gemm_tc_supported); other shapes stay on
+  // the layer-by-layer path, whose InnerProductLayer falls back to the exact fp32 kernel
+  FUSE_REQUIRE(Caffe::precision() == VV_PREC_FP32_SIMT || (N % 8 == 0 && K % 8 == 0),
+               "the tensor-core precisions need embedding / feature dims that are multiples of 8");
   FUSE_REQUIRE(!bottom_need_backward_[li][0], "fc7 bottom needs a gradient (dgrad) -- not the shipped net");
   ++li; FUSE_REQUIRE(layers_[li]->layer_param().relu_param().negative_slope() == 0.f, "leaky ReLU is not fused");
   float ratio = 0.f;

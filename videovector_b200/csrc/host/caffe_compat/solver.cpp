@@ -131,6 +131,9 @@ void Solver<Dtype>::Restore(const char* state_file) {
 template <typename Dtype>
 void Solver<Dtype>::Solve(int max_iter, const char* resume_file) {
   const int stop = max_iter >= 0 ? max_iter : param_.max_iter();
+  // the reference's Solve(resume_file) starts from iteration 0 unless a state is restored (solver.cpp:165-169); the
+  // explicit-max_iter form continues from wherever earlier Step()/Solve(n) calls left the solver
+  if (max_iter < 0) iter_ = 0;
   if (resume_file) { LogInfo(string("Restoring previous solver status from ") + resume_file); Restore(resume_file); }
   const int start_iter = iter_;
   for (; iter_ < stop;) {
@@ -151,8 +154,17 @@ void Solver<Dtype>::Solve(int max_iter, const char* resume_file) {
       }
     }
   }
-  // "Always save a snapshot after optimization, unless overridden" (solver.cpp:225-227); only when a prefix is configured
-  if (max_iter < 0 && param_.snapshot_after_train() && !param_.snapshot_prefix().empty()) Snapshot();
+  // "Always save a snapshot after optimization, unless overridden by setting snapshot_after_train := false"
+  // (solver.cpp:225-227) -- <snapshot_prefix>_iter_N.caffemodel / .solverstate, with an empty prefix too, as there.
+  // The explicit-max_iter form (an interactive "run n more iterations") leaves snapshots to the caller.
+  if (max_iter < 0 && param_.snapshot_after_train()) Snapshot();
+  // the final display-only pass: forward only, the parameters were already updated max_iter times (solver.cpp:228-236)
+  if (max_iter < 0 && param_.display() && iter_ % param_.display() == 0) {
+    Dtype loss = 0;
+    if (net_->fused()) loss = net_->FusedStep(iter_, false, nullptr);      // the fused sequence has no forward-only form; no update
+    else net_->ForwardPrefilled(&loss);
+    fprintf(stderr, "Iteration %d, loss = %g\n", iter_, double(loss));
+  }
   if (!test_nets_.empty() && iter_ % param_.test_interval() == 0) TestAll();          // solver.cpp:237-239
 }
 
@@ -230,8 +242,13 @@ void SGDSolver<Dtype>::ComputeUpdateValue() {
     Blob<Dtype>* p = net_params[i].get();
     const Dtype local_rate = rate * lr[i], local_decay = weight_decay * wd[i];
     if (local_decay) {
-      CHECK(rt == "L2") << "regularization_type " << rt << " is only built in the fused update kernel";
-      VV_CHECK(vv_axpby(p->count(), local_decay, p->gpu_data(), 1.f, p->mutable_gpu_diff(), Caffe::stream()));
+      if (rt == "L2") {
+        VV_CHECK(vv_axpby(p->count(), local_decay, p->gpu_data(), 1.f, p->mutable_gpu_diff(), Caffe::stream()));
+      } else if (rt == "L1") {       // diff += decay * sign(data)  (caffe_gpu_sign + axpy, solver.cpp:547-554)
+        VV_CHECK(vv_sign_axpy(p->count(), local_decay, p->gpu_data(), p->mutable_gpu_diff(), Caffe::stream()));
+      } else {
+        CHECK(false) << "Unknown regularization type: " << rt;
+      }
     }
     VV_CHECK(vv_axpby(p->count(), local_rate, p->gpu_diff(), momentum, history_[i]->mutable_gpu_data(), Caffe::stream()));
     VV_CHECK(vv_axpby(p->count(), 1.f, history_[i]->gpu_data(), 0.f, p->mutable_gpu_diff(), Caffe::stream()));

@@ -349,6 +349,10 @@ extern "C" vv_trainer_t* vv_trainer_create(const vv_trainer_cfg_t* cfg, vv_strea
     set_error("bad trainer cfg: B=%d C=%d Nn=%d K=%d N=%d", cfg->B, cfg->C, cfg->Nn, cfg->K, cfg->N); return nullptr;
   }
   if (cfg->prec < VV_PREC_FP32_SIMT || cfg->prec > VV_PREC_F16X3) { set_error("bad precision %d", cfg->prec); return nullptr; }
+  if (cfg->prec != VV_PREC_FP32_SIMT && ((cfg->K % 8) || (cfg->N % 8))) {
+    set_error("trainer: the tensor-core precisions need K %% 8 == 0 and N %% 8 == 0 (K=%d N=%d); use VV_PREC_FP32_SIMT", cfg->K, cfg->N);
+    return nullptr;
+  }
   if (cfg->world_size < 1 || cfg->rank < 0 || cfg->rank >= cfg->world_size) { set_error("bad rank/world_size"); return nullptr; }
   if (vv_device_check() != VV_OK) return nullptr;
   vv_trainer* t = new vv_trainer();

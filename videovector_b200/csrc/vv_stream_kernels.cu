@@ -367,6 +367,9 @@ __global__ void dropout_make_mask_kernel(unsigned* mask, int rows, int cols4, un
 __global__ void axpby_kernel(long long n, float a, const float* x, float b, float* y) {
   GS_LOOP(i, n) { y[i] = (b == 0.f) ? a * x[i] : fmaf(a, x[i], b * y[i]); }
 }
+__global__ void sign_axpy_kernel(long long n, float a, const float* x, float* y) {
+  GS_LOOP(i, n) { const float v = x[i]; y[i] += a * float((0.f < v) - (v < 0.f)); }
+}
 __global__ void mul_kernel(long long n, const float* a, const float* b, float* y) { GS_LOOP(i, n) { y[i] = a[i] * b[i]; } }
 struct PtrPack { const float* p[VV_MAX_CONTEXT]; float c[VV_MAX_CONTEXT]; int nb; };
 __global__ void eltwise_sum_kernel(const PtrPack pk, long long n, float* top) {
@@ -704,6 +707,10 @@ extern "C" int vv_eltwise_prod_forward(const float* a, const float* b, int64_t n
 extern "C" int vv_axpby(int64_t n, float alpha, const float* x, float beta, float* y, vv_stream_t s) {
   VV_REQUIRE(x && y && n > 0, "axpby: bad arguments");
   VV_SIMPLE_LAUNCH(axpby_kernel, n, n, alpha, x, beta, y);
+}
+extern "C" int vv_sign_axpy(int64_t n, float alpha, const float* x, float* y, vv_stream_t s) {
+  VV_REQUIRE(x && y && n > 0, "sign_axpy: bad arguments");
+  VV_SIMPLE_LAUNCH(sign_axpy_kernel, n, n, alpha, x, y);
 }
 extern "C" int vv_mul(int64_t n, const float* a, const float* b, float* y, vv_stream_t s) {
   VV_REQUIRE(a && b && y && n > 0, "mul: bad arguments");

@@ -1,5 +1,6 @@
 """Host-side data-parallel logic (pure numpy / torch.distributed, no CUDA): how a global batch is split over
-ranks and how per-rank results combine.  The device side is vv_trainer_step's NCCL all-reduce.
+ranks, which rows of W a rank owns in the peer-memory exchange, and how per-rank results combine.  The device side is
+the exchange inside the update kernel (csrc/vv_dp_exchange.cu) or, in NCCL mode, vv_trainer_step's all-reduce.
 
 Two ways to feed G ranks:
   * sharded streams (bench default): rank r owns videos [r*V/G, (r+1)*V/G) and runs its own reference-exact
@@ -23,6 +24,26 @@ def shard_batch(idx, quirk, rank, world):
     assert gb % world == 0, "global batch must divide evenly over ranks"
     b = gb // world
     return idx[rank * b:(rank + 1) * b], quirk[rank * b:(rank + 1) * b]
+
+
+def owner_rows(N, rank, world):
+    """[begin, end) of the rows of W [N,K] (and of the momentum history) rank `rank` owns and updates in the peer-memory
+    exchange (vv_dp_exchange.cuh): contiguous blocks of N/world rows; N must divide evenly."""
+    assert N % world == 0, "N must divide evenly over the ranks"
+    per = N // world
+    return rank * per, (rank + 1) * per
+
+
+def owner_update(contribs, W_rows, hist_rows, rate, momentum, decay, world):
+    """What the owner does with the G contributions to its rows (phase B of the exchange): sum in rank order, scale by
+    1/G, L2 decay, momentum, update.  numpy float32, same operation order as the kernel.  Returns (W_rows, hist_rows)."""
+    g = contribs[0].astype(np.float32).copy()
+    for c in contribs[1:]:
+        g += c
+    g *= np.float32(1.0 / world)
+    g += np.float32(decay) * W_rows
+    h = np.float32(rate) * g + np.float32(momentum) * hist_rows
+    return W_rows - h, h
 
 
 def combine_gradients(local_grads, world):
