@@ -4,13 +4,20 @@ Prints 'DP_CHECK OK ...' on rank 0 (used by tests/test_gpu_dp.py and the multi-G
 Checks: (1) W, history, bias, loss, violations of the G-rank run against one rank on the global batch (1e-5 for the
 fp32-parity modes; the summation order differs), every step; (2) replicas bit-identical: the operand copy of W, W[:,K-1]
 and the bias every rank ends up with; (3) HASH-mode dropout draws a different mask on every rank."""
-import os, sys
+import os, sys, threading, traceback
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 import torch.distributed as dist
 from videovector_b200 import ops, dp
 from videovector_b200._lib import DROPOUT_MASK01, DROPOUT_HASH
+
+# a rank that fails must not leave the others waiting in a collective: any uncaught exception ends the process at once
+# (torchrun then stops the other ranks), and a watchdog ends a run that outlives its budget
+def _die(exc_type, exc, tb):
+    traceback.print_exception(exc_type, exc, tb); sys.stdout.flush(); sys.stderr.flush(); os._exit(1)
+sys.excepthook = _die
+threading.Timer(float(os.environ.get("DP_CHECK_BUDGET_S", "120")), lambda: (print("DP_CHECK FAIL watchdog: run exceeded its budget", flush=True), os._exit(2))).start()
 
 rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
@@ -68,7 +75,7 @@ for it in range(steps):
     if rank == 0:
         ref.step(bank, torch.as_tensor(gidx).cuda(), torch.as_tensor(gq).cuda(), torch.as_tensor(gmask.reshape(R * B * world, N)).cuda(), it=it)
         torch.cuda.synchronize()
-        rel = lambda a, b: float((tr.tensor(a) - ref.tensor(a)).abs().max() / ref.tensor(a).abs().max())
+        rel = lambda a: float((tr.tensor(a) - ref.tensor(a)).abs().max() / ref.tensor(a).abs().max())
         eW, eH, eb = rel("W"), rel("W_hist"), rel("b")
         eL = abs(tr.tensor("loss").item() - ref.tensor("loss").item())
         eV = abs(tr.tensor("violations").item() - ref.tensor("violations").item())
@@ -112,3 +119,4 @@ th.close(); tr.close()
 if ref is not None:
     ref.close()
 dist.destroy_process_group()
+os._exit(0)

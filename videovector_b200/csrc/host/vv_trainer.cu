@@ -201,8 +201,10 @@ struct vv_trainer {
     else { o.hi = bank_hi.p; o.lo = nullptr; }     // BF16
     return o;
   }
-  // peers write into this rank's memory until THEIR last update kernel has finished: wait for their flags, then for
-  // every rank to get here, before anything is unmapped or freed
+  // Peers write into this rank's memory only during a step's update kernel, and raise w_ready[peer] = seq here after
+  // their last write: once those flags are in (and this rank's own kernels have drained, its stores acknowledged by the
+  // fences in front of its flags) nothing is in flight in either direction and the mappings can go -- no collective
+  // needed, so a rank that dies cannot hang the others' teardown (the wait kernel gives up after VV_DP_TIMEOUT_MS).
   void p2p_quiesce() {
     if (!p2p.on) return;
     const bool healthy = !(p2p.err_host && *p2p.err_host);
@@ -211,10 +213,6 @@ struct vv_trainer {
       p2p.waited = p2p.seq;
     }
     cudaStreamSynchronize(stream);
-    if (healthy && comm && !(p2p.err_host && *p2p.err_host)) {
-      g_nccl.AllReduce(p2p.peers.flags[cfg.rank] + kDpFlagCtr + 3, p2p.peers.flags[cfg.rank] + kDpFlagCtr + 3, 1, kNcclFloat, kNcclSum, comm, stream);
-      cudaStreamSynchronize(stream);
-    }
   }
   ~vv_trainer() {
     p2p_quiesce();
