@@ -12,7 +12,7 @@ from oracle import pyoracle as orc, pyref
 from videovector_b200 import ops
 
 CURVE = dict(B=128, C=5, Nn=10, K=1024, N=256, V=256, S=16, P=1000, swap=50, max_same=6, steps=1000,
-             base_lr=0.01, gamma=1e-3, power=0.75, momentum=0.9, weight_decay=5e-4, bank_seed=1234, w_seed=1701, w_std=0.02, b_std=0.01)
+             base_lr=0.01, gamma=1e-3, power=0.75, momentum=0.9, weight_decay=5e-4, bank_seed=1234, w_seed=1701, w_std=0.1, b_std=0.01)
 
 
 def problem(c=CURVE):

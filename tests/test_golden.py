@@ -154,3 +154,30 @@ def test_oracle_reproduces_reference_solver_trajectory(oracle):
             assert abs(traj[it][0] - rt[it][0]) < 1e-5 * max(1, abs(rt[it][0])) and traj[it][1] == rt[it][1], it
         for k in ("W", "b", "hW", "hb"):
             assert rel(st[k], rs[k]) < 1e-5, k
+
+
+def test_oracle_follows_reference_loss_curve(oracle):
+    """tests/golden/curve_ref.npz = 1 000 iterations of the compiled reference pipeline (make_curve_golden.py) at a
+    well-conditioned shape (no dropout layer: the curve is a function of the bit-exact sampler stream alone).  The oracle's
+    sampler + net + update restatements follow it step by step (first 150 iterations here; the generator checks all 1 000)."""
+    import sys
+    sys.path.insert(0, GOLD)
+    from make_curve_golden import CURVE as c, problem
+    g = np.load(os.path.join(GOLD, "curve_ref.npz"))
+    assert len(g["loss"]) == c["steps"] == 1000
+    vid, off, sid, feat, W0, b0 = problem()
+    smp = oracle.Sampler(vid, off, sid, feat, c["K"], c["B"], c["C"], c["Nn"], c["P"], c["swap"], c["max_same"], 100, seed=1)
+    W, b = W0.copy(), b0.copy(); hW = np.zeros_like(W); hb = np.zeros_like(b)
+    oracle.use_openblas(0)
+    n = 150
+    for it in range(n):
+        idx, quirk, data = smp.next()
+        out = oracle.net_forward_backward(data, W, b, None, c["B"], c["C"], c["Nn"], margin=2.0, norm=2, dropout_ratio=0.0,
+                                          want=("loss", "violations", "dW", "db"))
+        assert abs(out["loss"][0] - g["loss"][it]) <= 1e-5 * g["loss"][it], it
+        assert out["violations"][0] == g["viol"][it], it
+        rate = oracle.learning_rate("inv", c["base_lr"], c["gamma"], c["power"], 1, it)
+        W, _, hW = oracle.sgd_update(W, out["dW"], hW, rate, c["momentum"], c["weight_decay"])
+        b, _, hb = oracle.sgd_update(b, out["db"], hb, rate * 2, c["momentum"], 0.0)
+    oracle.use_builtin_blas()
+    smp.close()
