@@ -114,7 +114,7 @@ struct vv_trainer {
   // activations / gradients
   DevBuf Xf, X_hi, X_lo, Zf, H, stats, item_loss, item_viol, dZf, dZ_hi, dZ_lo, dW_parts, dbx, dX;
   // gather-fused path: operand copies of the registered bank, per-step gather plan, quirk corrections
-  DevBuf bank_hi, bank_lo, rowmap, delta, wlast, dq;
+  DevBuf bank_hi, bank_lo, rowmap, delta, wlast, dq, tickets, rank_ws;
   const float* bank_reg = nullptr; int64_t bank_reg_rows = 0;
   // F16X3: the X scale is fixed from max|bank| (gathered rows are a subset), the dZ scale trails the previous step
   const float* scaled_bank = nullptr; int64_t scaled_bank_rows = 0; bool dz_scale_ready = false;
@@ -158,6 +158,9 @@ struct vv_trainer {
     if ((rc = alloc_operand(dZ_hi, dZ_lo, MN, cfg.prec))) return rc;
     if (f32op || cfg.keep_blobs) { A(dZf, MN * 4); }
     A(wlast, size_t(cfg.N) * 4);
+    A(rank_ws, rank_loss_workspace_bytes(cfg.N));       // deterministic db / dq / loss sums of the fused rank-loss kernel
+    // split-K finish: one ticket counter per wgrad output tile (+ one for the tiles finished), zeroed here, self-resetting
+    A(tickets, (size_t((cfg.K + 127) / 128 + 1) * size_t((cfg.N + 127) / 128 + 1) + 1) * 4);
     A(rowmap, size_t((M + 127) / 128 * 128) * 4); A(delta, size_t((M + 127) / 128 * 128) * 4);
     if (cfg.keep_blobs) { A(Zf, MN * 4); }
     A(H, MN * 4);
@@ -221,7 +224,7 @@ struct vv_trainer {
     if (p2p.err_host) cudaFreeHost(p2p.err_host);
     if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
     DevBuf* all[] = {&W, &b, &Wh, &bh, &W_hi, &W_lo, &Xf, &X_hi, &X_lo, &Zf, &H, &stats, &item_loss, &item_viol,
-                     &dZf, &dZ_hi, &dZ_lo, &dW_parts, &dbx, &dX, &bank_hi, &bank_lo, &rowmap, &delta, &wlast, &dq};
+                     &dZf, &dZ_hi, &dZ_lo, &dW_parts, &dbx, &dX, &bank_hi, &bank_lo, &rowmap, &delta, &wlast, &dq, &tickets, &rank_ws};
     for (DevBuf* d : all) d->release();
     for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
     if (ev_grad) cudaEventDestroy(ev_grad);
@@ -487,7 +490,7 @@ extern "C" int vv_trainer_step(vv_trainer_t* t, const float* bank, int64_t bank_
                                         t->item_loss.as<float>(), t->item_viol.as<float>(), t->loss_ptr(), t->viol_ptr(),
                                         t->dZf.as<float>(), t->dZ_hi.p, t->dZ_lo.p, c.prec, t->dbx.as<float>(),
                                         fused_gather ? t->delta.as<float>() : nullptr, fused_gather ? t->dq.as<float>() : nullptr,
-                                        reinterpret_cast<unsigned int*>(t->dbx.as<float>() + N + 2), s))) return rc;
+                                        reinterpret_cast<unsigned int*>(t->dbx.as<float>() + N + 2), s, t->rank_ws.p, t->rank_ws.bytes))) return rc;
     } else {
       // K2
       t->tic(2);
@@ -525,6 +528,74 @@ extern "C" int vv_trainer_step(vv_trainer_t* t, const float* bank, int64_t bank_
                        N % (256 * want_slices) == 0) ? want_slices : 1;
   const bool use_p2p = t->p2p.on && do_update;           // the exchange runs inside the update kernel
   const bool fold_col = fused_gather && (c.world_size == 1 || use_p2p) && do_update;
+  // The update (one GPU) / the push to the owner ranks (data parallel) as the split-K finish INSIDE the wgrad kernel
+  // (WgradFinish, vv_gemm.cuh): no update launch, no second pass over the slabs.  VV_FUSED_UPDATE=0 keeps the separate
+  // K4 launch (A/B timing).
+  static const bool want_finish = [] { const char* e = getenv("VV_FUSED_UPDATE"); return !(e && atoi(e) == 0); }();
+  const bool fuse_finish = want_finish && do_update && (c.world_size == 1 || use_p2p) && c.prec != VV_PREC_FP32_SIMT && nslices == 1;
+  if (fuse_finish) {
+    const float rate = vv_learning_rate(c.lr_policy, c.base_lr, c.gamma, c.power, c.stepsize, iter);
+    if (rate < 0.f) return VV_ERR_INVALID;
+    if (c.compute_dgrad) {             // reads W: before the wgrad kernel rewrites it
+      t->tic(5);
+      if ((rc = vv_ip_dgrad(t->opdZ(), t->opW(), M, N, K, c.prec, t->dX.as<float>(), s))) return rc;
+      t->toc(5);
+    }
+    // F16X3: the scale of the new W operand copy, from max|W| as the previous update (or the initial copy) recorded it
+    // (data parallel: over all owners' rows, so every rank derives the same scale)
+    if (use_p2p) { if ((rc = operand_rescale_ex(t->W_hi.p, c.prec, 10, t->p2p.peers.flags[c.rank] + kDpFlagAmax, c.world_size, s))) return rc; }
+    else { if ((rc = vv_operand_rescale(t->W_hi.p, c.prec, 10, s))) return rc; }
+    WgradFinish f;
+    f.tickets = t->tickets.as<unsigned int>();
+    UpdateTail& u = f.u;
+    u.W = t->W.as<float>(); u.parts = t->dW_parts.as<float>(); u.nparts = t->nsplit; u.stride = NK; u.hist = t->Wh.as<float>();
+    u.diff_out = t->dW_parts.as<float>(); u.count = NK; u.K = K;
+    u.rate_w = rate * c.lr_mult[0]; u.decay_w = c.weight_decay * c.decay_mult[0];
+    u.col_add = fold_col ? t->dq.as<float>() : nullptr; u.col_out = t->wlast.as<float>();
+    u.Wop_hi = t->W_hi.p; u.Wop_lo = t->W_lo.p; u.prec = c.prec;
+    u.b = t->b.as<float>(); u.db = t->dbx.as<float>(); u.bh = t->bh.as<float>(); u.b_diff = t->dbx.as<float>(); u.nb = N;
+    u.rate_b = rate * c.lr_mult[1]; u.decay_b = c.weight_decay * c.decay_mult[1];
+    u.momentum = c.momentum; u.reg_type = c.reg_type; u.gscale = 1.f;
+    if (use_p2p) {
+      f.mode = 2; f.G = c.world_size; f.rank = c.rank; f.rows_per = t->p2p.rows_per; f.seq = t->p2p.seq + 1;
+      f.col_add = fold_col ? t->dq.as<float>() : nullptr;
+      f.small_src = t->dbx.as<float>(); f.nsmall = N + 2; f.small_stride = t->p2p.small_stride;
+      f.peers = t->p2p.peers;
+    } else {
+      f.mode = 1;
+    }
+    t->tic(4);
+    if (fused_gather) {
+      const double reg = double(c.regularization) / 2;
+      if (reg > 0) { if ((rc = vv_axpby(N, float(1.0 + reg), t->dq.as<float>(), 0.f, t->dq.as<float>(), s))) return rc; }
+      if ((rc = ip_wgrad_gathered_ex(t->opdZ(), t->opBank(), bank_rows, t->rowmap.as<int32_t>(), M, N, K, c.prec, c.regularization,
+                                     t->dW_parts.as<float>(), t->nsplit, 0, N, &f, s))) return rc;
+    } else {
+      if ((rc = ip_wgrad_ex(t->opdZ(), t->opX(), M, N, K, c.prec, c.regularization, t->dW_parts.as<float>(), t->nsplit,
+                            nullptr, 0, &f, s))) return rc;
+    }
+    t->toc(4);
+    if (use_p2p) {
+      t->tic(7);
+      DpExchange x;
+      x.G = c.world_size; x.rank = c.rank; x.seq = t->p2p.seq + 1;
+      x.parts = nullptr; x.nparts = 0; x.stride = NK; x.col_add = nullptr;       // phase A happened in the wgrad kernel
+      x.small_src = t->dbx.as<float>(); x.nsmall = N + 2; x.small_stride = t->p2p.small_stride;
+      x.hist = t->Wh.as<float>(); x.diff_out = t->dW_parts.as<float>(); x.count = NK; x.K = K; x.rows_per = t->p2p.rows_per;
+      x.rate_w = u.rate_w; x.decay_w = u.decay_w; x.momentum = c.momentum;
+      x.reg_type = c.reg_type; x.gscale = 1.f / float(c.world_size); x.prec = c.prec;
+      x.b = t->b.as<float>(); x.bh = t->bh.as<float>(); x.b_diff = t->dbx.as<float>(); x.nb = N;
+      x.rate_b = u.rate_b; x.decay_b = u.decay_b;
+      x.loss_out = t->loss_ptr(); x.viol_out = t->viol_ptr();
+      x.peers = t->p2p.peers;
+      if ((rc = dp_exchange_update(x, t->p2p.err_dev, t->p2p.replicate_master, s))) return rc;
+      t->p2p.seq += 1;
+      t->toc(7);
+    }
+    t->last_launches = launches_reset();
+    if (t->timing) ++t->timed_steps;
+    return VV_OK;
+  }
   t->tic(4);
   if (fused_gather) {
     const double reg = double(c.regularization) / 2;

@@ -117,8 +117,14 @@ extern "C" size_t vv_ip_wgrad_workspace_bytes(int M, int N, int K, int prec) {
 
 extern "C" int vv_ip_wgrad(vv_operand_t dZ, vv_operand_t X, int M, int N, int K, int prec, float regularization,
                            float* dW_parts, int nsplit, void* workspace, size_t workspace_bytes, vv_stream_t stream) {
+  return vv::ip_wgrad_ex(dZ, X, M, N, K, prec, regularization, dW_parts, nsplit, workspace, workspace_bytes, nullptr, stream);
+}
+int vv::ip_wgrad_ex(vv_operand_t dZ, vv_operand_t X, int M, int N, int K, int prec, float regularization,
+                    float* dW_parts, int nsplit, void* workspace, size_t workspace_bytes, const WgradFinish* finish, vv_stream_t stream) {
   VV_REQUIRE(dZ.hi && X.hi && dW_parts && M > 0 && N > 0 && K > 0 && nsplit >= 0, "ip_wgrad: bad arguments");
+  VV_REQUIRE(!finish || (nsplit >= 1 && prec != VV_PREC_FP32_SIMT), "ip_wgrad: the fused split-K finish needs explicit slabs and a tensor-core precision");
   GemmProblem g;
+  g.finish = finish;
   g.kind = GEMM_WGRAD; g.prec = prec; g.A = dZ; g.B = X; g.M = M; g.N = N; g.K = K; g.rowmap = nullptr; g.bank_rows = 0;
   int rc = fill_epilogue(nullptr, nullptr, nullptr, &g.epi);
   if (rc) return rc;
@@ -180,6 +186,11 @@ extern "C" int vv_ip_wgrad_gathered(vv_operand_t dZ, vv_operand_t bank, int64_t 
 extern "C" int vv_ip_wgrad_gathered_part(vv_operand_t dZ, vv_operand_t bank, int64_t bank_rows, const int32_t* rowmap, int M, int N,
                                          int K, int prec, float regularization, float* dW_parts, int nsplit, int n0, int ncols,
                                          vv_stream_t stream) {
+  return vv::ip_wgrad_gathered_ex(dZ, bank, bank_rows, rowmap, M, N, K, prec, regularization, dW_parts, nsplit, n0, ncols, nullptr, stream);
+}
+int vv::ip_wgrad_gathered_ex(vv_operand_t dZ, vv_operand_t bank, int64_t bank_rows, const int32_t* rowmap, int M, int N,
+                             int K, int prec, float regularization, float* dW_parts, int nsplit, int n0, int ncols,
+                             const WgradFinish* finish, vv_stream_t stream) {
   VV_REQUIRE(dZ.hi && bank.hi && rowmap && dW_parts && M > 0 && N > 0 && K > 0 && nsplit >= 1 && bank_rows > 0,
              "ip_wgrad_gathered: bad arguments");
   VV_REQUIRE(prec != VV_PREC_FP32_SIMT, "ip_wgrad_gathered needs a tensor-core precision");
@@ -193,5 +204,6 @@ extern "C" int vv_ip_wgrad_gathered_part(vv_operand_t dZ, vv_operand_t bank, int
   g.epi.out_scale = reg > 0 ? float(1.0 + reg) : 1.f;
   g.slab_stride = (long long)N * K; g.D = dW_parts; g.nsplit = nsplit;
   g.n0 = n0; g.ncols = ncols;
+  g.finish = finish;
   return gemm_tc_launch(g, stream);
 }

@@ -43,6 +43,7 @@ struct UpdateTail {
   float momentum; int reg_type; float gscale;
 };
 int sgd_update_tail(const UpdateTail& u, vv_stream_t stream);
+
 // vv_operand_rescale that also folds in n_extra recorded maxima (bit patterns) kept outside the operand's header
 int operand_rescale_ex(void* hi, int prec, int target_log2, const unsigned int* extra_bits, int n_extra, vv_stream_t stream);
 // vv_rank_loss_fused with the batch loss / violation reduction folded into the kernel (vv_rank_loss.cu)
@@ -50,7 +51,13 @@ int rank_loss_fused_counted(const float* H, const vv_rank_cfg_t* cfg, float loss
                             float dropout_scale, float* stats, float* target_score, float* neg_score,
                             float* item_loss, float* item_viol, float* loss, float* violations,
                             float* dZ, void* dZop_hi, void* dZop_lo, int prec, float* db_accum,
-                            const float* delta, float* dq_accum, unsigned int* done_counter, vv_stream_t stream);
+                            const float* delta, float* dq_accum, unsigned int* done_counter, vv_stream_t stream,
+                            void* workspace = nullptr, size_t workspace_bytes = 0);
+// Second-generation fused kernel (operand-only output, R <= 16, N <= 1024): with a workspace of rank_loss_workspace_bytes(N)
+// the bias / quirk column sums and the batch loss are reduced in a fixed order (no float atomics; db_accum / dq_accum are
+// then STORED, they need no zeroing) -- see rank_fused2_kernel in vv_rank_loss.cu.
+size_t rank_loss_workspace_bytes(int N);
+bool rank_loss_fused_v2_applies(const vv_rank_cfg_t* cfg, int prec, bool want_dz, bool want_scores);
 
 constexpr int kNumSMsB200 = 148;
 
@@ -133,6 +140,50 @@ __device__ __forceinline__ void f16_publish_absmax(const void* hi, float amax) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
   if ((threadIdx.x & 31) == 0 && amax > 0.f) atomicMax(&f16_hdr(hi)->absmax_bits, __float_as_uint(amax));
+}
+
+// K4's arithmetic for 4 consecutive weights (float4 index i of the [N,K] blob) given their summed gradient g: scale,
+// decay (L2 / L1), momentum, update, diff := history, W[:, K-1] saved, operand copy refreshed.  One definition for the
+// stand-alone update kernel and for the split-K finish inside the wgrad kernels, so both round identically
+// (ref: solver.cpp:534-568, net.cpp:837, blob.cpp:126-128).
+__device__ __forceinline__ void sgd_update4(const UpdateTail& u, long long i, float4 g, float scale, float& amax) {
+  const long long n4 = u.count / 4, k4 = u.K / 4;
+  const float rate = u.rate_w, momentum = u.momentum, decay = u.decay_w, gscale = u.gscale;
+  if (gscale != 1.f) { g.x *= gscale; g.y *= gscale; g.z *= gscale; g.w *= gscale; }
+  float4 w = reinterpret_cast<float4*>(u.W)[i];
+  if (decay != 0.f) {
+    if (u.reg_type == 2) {
+      g.x = fmaf(decay, w.x, g.x); g.y = fmaf(decay, w.y, g.y); g.z = fmaf(decay, w.z, g.z); g.w = fmaf(decay, w.w, g.w);
+    } else {
+      g.x += decay * float((0.f < w.x) - (w.x < 0.f)); g.y += decay * float((0.f < w.y) - (w.y < 0.f));
+      g.z += decay * float((0.f < w.z) - (w.z < 0.f)); g.w += decay * float((0.f < w.w) - (w.w < 0.f));
+    }
+  }
+  float4 h = reinterpret_cast<float4*>(u.hist)[i];
+  h.x = fmaf(rate, g.x, momentum * h.x); h.y = fmaf(rate, g.y, momentum * h.y);
+  h.z = fmaf(rate, g.z, momentum * h.z); h.w = fmaf(rate, g.w, momentum * h.w);
+  w.x -= h.x; w.y -= h.y; w.z -= h.z; w.w -= h.w;
+  reinterpret_cast<float4*>(u.hist)[i] = h;
+  reinterpret_cast<float4*>(u.W)[i] = w;
+  if (u.diff_out) reinterpret_cast<float4*>(u.diff_out)[i] = h;
+  if ((i % k4) == k4 - 1 && u.col_out) u.col_out[i / k4] = w.w;
+  float* hi = static_cast<float*>(u.Wop_hi);
+  if (u.prec == VV_PREC_TF32X3 && hi) {
+    store_x3(hi, u.Wop_lo, size_t(n4) * 4, size_t(i) * 4, w);
+  } else if (u.prec == VV_PREC_F16X3 && hi) {
+    store_f16x3(hi, u.Wop_lo, size_t(i) * 4, w, scale, amax);
+  } else if (u.prec == VV_PREC_BF16 && hi) {
+    reinterpret_cast<uint2*>(hi)[i] = make_uint2(pack_bf16x2(w.x, w.y), pack_bf16x2(w.z, w.w));
+  }
+}
+__device__ __forceinline__ void sgd_update_bias1(const UpdateTail& u, int i) {
+  float g = u.db[i];
+  if (u.gscale != 1.f) g *= u.gscale;
+  const float w = u.b[i];
+  if (u.decay_b != 0.f) g = (u.reg_type == 2) ? fmaf(u.decay_b, w, g) : g + u.decay_b * float((0.f < w) - (w < 0.f));
+  const float h = fmaf(u.rate_b, g, u.momentum * u.bh[i]);
+  u.bh[i] = h; u.b[i] = w - h;
+  if (u.b_diff) u.b_diff[i] = h;
 }
 
 // ----------------------------------------------------------------------------

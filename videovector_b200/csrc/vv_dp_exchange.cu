@@ -22,29 +22,33 @@ dp_exchange_update_kernel(const DpExchange x, const DpRun run) {
   const long long gstride = (long long)gridDim.x * T;
 
   // ---------------- phase A: local split-K sum -> push every row to its owner
-  for (long long i = blockIdx.x * (long long)T + tid; i < n4; i += gstride) {
-    float4 g = __ldcs(reinterpret_cast<const float4*>(x.parts) + i);
-    const long long row = i / k4;
-    if (x.col_add && (i - row * k4) == k4 - 1) g.w += x.col_add[row];     // .w is column K-1
-    for (int s = 1; s < x.nparts; ++s) {
-      const float4 t = __ldcs(reinterpret_cast<const float4*>(x.parts + s * x.stride) + i);
-      g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+  // (x.nparts == 0: the wgrad kernel's split-K finish already pushed the rows and raised dw_ready, vv_gemm.cuh)
+  if (x.nparts > 0) {
+    for (long long i = blockIdx.x * (long long)T + tid; i < n4; i += gstride) {
+      float4 g = __ldcs(reinterpret_cast<const float4*>(x.parts) + i);
+      const long long row = i / k4;
+      if (x.col_add && (i - row * k4) == k4 - 1) g.w += x.col_add[row];     // .w is column K-1
+      for (int s = 1; s < x.nparts; ++s) {
+        const float4 t = __ldcs(reinterpret_cast<const float4*>(x.parts + s * x.stride) + i);
+        g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+      }
+      const int o = int(row / x.rows_per);
+      const long long j = i - (long long)o * owned4;
+      reinterpret_cast<float4*>(x.peers.recv_dw[o])[(long long)x.rank * owned4 + j] = g;
     }
-    const int o = int(row / x.rows_per);
-    const long long j = i - (long long)o * owned4;
-    reinterpret_cast<float4*>(x.peers.recv_dw[o])[(long long)x.rank * owned4 + j] = g;
-  }
-  if (blockIdx.x == 0) {                                  // (db, loss, violations) to every rank
-    for (int d = 0; d < x.G; ++d)
-      for (int i = tid; i < x.nsmall; i += T) x.peers.recv_small[d][x.rank * x.small_stride + i] = x.small_src[i];
-  }
-  __syncthreads();
-  if (tid == 0) {
-    __threadfence_system();
-    const unsigned int prev = atomicAdd(&myflags[kDpFlagCtr], 1u);
-    if (prev + 1u == gridDim.x * x.seq) {                 // every CTA of this rank has pushed: tell the owners
+    if (blockIdx.x == 0) {                                  // (db, loss, violations) to every rank
+      for (int d = 0; d < x.G; ++d)
+        for (int i = tid; i < x.nsmall; i += T) x.peers.recv_small[d][x.rank * x.small_stride + i] = x.small_src[i];
+    }
+    __syncthreads();
+    if (tid == 0) {
       __threadfence_system();
-      for (int d = 0; d < x.G; ++d) dp_st_release_sys(&x.peers.flags[d][kDpFlagDwReady + x.rank], x.seq);
+      const unsigned int prev = atomicAdd(&myflags[kDpFlagCtr], 1u);
+      if (prev + 1u == gridDim.x) {                         // every CTA of this rank has pushed: tell the owners
+        myflags[kDpFlagCtr] = 0u;                           // (self-resetting: the next launch starts from zero)
+        __threadfence_system();
+        for (int d = 0; d < x.G; ++d) dp_st_release_sys(&x.peers.flags[d][kDpFlagDwReady + x.rank], x.seq);
+      }
     }
   }
   // ---------------- phase B: wait for all G contributions, update the owned rows, push them to every rank
@@ -129,7 +133,8 @@ dp_exchange_update_kernel(const DpExchange x, const DpRun run) {
   if (tid == 0) {
     __threadfence_system();
     const unsigned int prev = atomicAdd(&myflags[kDpFlagCtr + 1], 1u);
-    if (prev + 1u == gridDim.x * x.seq) {                 // the owned rows are in flight to every rank
+    if (prev + 1u == gridDim.x) {                         // the owned rows are in flight to every rank
+      myflags[kDpFlagCtr + 1] = 0u;
       __threadfence_system();
       if (x.prec == VV_PREC_F16X3) {
         const unsigned int bits = atomicExch(&myflags[kDpFlagCtr + 2], 0u);

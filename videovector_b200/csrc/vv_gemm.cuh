@@ -30,6 +30,27 @@ struct GemmEpilogue {
   const float* wlast;     // [N] = W[:, K-1]
 };
 
+// Split-K finish fused into the weight-gradient kernels (north star: "the momentum update is fused into the wgrad
+// epilogue").  Every (tile, split) unit leaves its partial tile in its slab and takes a ticket of its tile's counter; the
+// CTA that takes the last ticket re-reads the S partial tiles (fresh in L2) in slab order -- a fixed order, so the result
+// does not depend on which split finished last -- and finishes the tile:
+//   mode 1 (one GPU): g = sum_s slab_s (+ the K-1 quirk column); g += decay * W; h = momentum * h + rate * g; W -= h;
+//           diff = h; operand copy of W and W[:, K-1] refreshed -- the element-wise arithmetic of sgd_update_tail_kernel
+//           (ref: solver.cpp:534-568, net.cpp:837, blob.cpp:126-128); the CTA finishing the tile at feature offset 0 of an
+//           output block also updates that block of the bias.  No update launch, no second pass over the slabs.
+//   mode 2 (data parallel): the summed rows go straight to their owner rank's receive buffer (vv_dp_exchange.cuh); the CTA
+//           finishing the LAST tile pushes (db, loss, violations) and raises dw_ready on every rank.
+struct WgradFinish {
+  unsigned int* tickets = nullptr;      // one counter per output tile (+ one for the tiles finished), zero at launch; self-resetting
+  int mode = 0;
+  UpdateTail u;                          // mode 1 (u.parts / u.stride / u.nparts are taken from the GEMM problem)
+  // mode 2
+  int G = 0, rank = 0, rows_per = 0; unsigned int seq = 0;
+  const float* col_add = nullptr;       // [N] the quirk column's share (mode 2; mode 1 uses u.col_add)
+  const float* small_src = nullptr; int nsmall = 0, small_stride = 0;
+  DpPeers peers;
+};
+
 // D_rows x D_cols output (row pitch ldd), reduction length red.
 // nsplit slabs (split over the reduction) are written at D + s*slab_stride.
 struct GemmProblem {
@@ -47,6 +68,7 @@ struct GemmProblem {
   // data parallel: W (operand B of FWD / DGRAD) is being written by the owner ranks' update kernels; the TMA producer
   // lane waits for their w_ready flags right before its first W tile (flags == NULL: nothing to wait for)
   DpWait wait = {nullptr, 0, 0u, nullptr, 0ull};
+  const WgradFinish* finish = nullptr;   // WGRAD / WGRAD_T: fused split-K finish (NULL: slabs are left for the caller)
 };
 
 // vv_ip_forward / vv_ip_forward_gathered with the data-parallel wait (wait == NULL: the C-ABI entry points)
@@ -55,6 +77,12 @@ int ip_forward_ex(vv_operand_t X, vv_operand_t W, const float* bias, int M, int 
 int ip_forward_gathered_ex(vv_operand_t bank, int64_t bank_rows, const int32_t* rowmap, const float* delta,
                            const float* wlast, vv_operand_t W, const float* bias, int M, int N, int K, int prec,
                            const vv_act_t* act, float* Z, float* H, const DpWait* wait, vv_stream_t stream);
+// vv_ip_wgrad / vv_ip_wgrad_gathered_part with the fused split-K finish (finish == NULL: the C-ABI entry points)
+int ip_wgrad_ex(vv_operand_t dZ, vv_operand_t X, int M, int N, int K, int prec, float regularization,
+                float* dW_parts, int nsplit, void* workspace, size_t workspace_bytes, const WgradFinish* finish, vv_stream_t stream);
+int ip_wgrad_gathered_ex(vv_operand_t dZ, vv_operand_t bank, int64_t bank_rows, const int32_t* rowmap, int M, int N,
+                         int K, int prec, float regularization, float* dW_parts, int nsplit, int n0, int ncols,
+                         const WgradFinish* finish, vv_stream_t stream);
 int gemm_tc_launch(const GemmProblem& p, cudaStream_t stream);     // tcgen05 path (TF32X3 / TF32 / BF16)
 int gemm_simt_launch(const GemmProblem& p, cudaStream_t stream);   // exact fp32 path
 bool gemm_tc_supported(const GemmProblem& p, const char** why);

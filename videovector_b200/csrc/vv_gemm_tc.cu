@@ -41,6 +41,7 @@ struct TcParams {
   long long ga_pitch; int ga_cols; int rowmap_len;
   const float* inv_sa; const float* inv_sb;   // f16x3: 1/scale of the two operands (device, from their headers)
   DpWait wait;                  // data parallel: owner ranks' w_ready flags to wait for before the first B (= W) tile
+  WgradFinish fin;              // wgrad: fused split-K finish (fin.tickets == NULL: off)
   GemmEpilogue epi;
 };
 
@@ -84,6 +85,81 @@ struct Cfg {
   static_assert(smem_bytes <= 232448, "exceeds 227 KB of shared memory");
 };
 
+
+// The split-K finish of one work unit (see WgradFinish in vv_gemm.cuh), run by the 256 epilogue threads right after they
+// stored the unit's partial tile.  m0 / nt0: the tile's row / column offset in D; et: epilogue thread 0..255.
+template <class C>
+__device__ __forceinline__ void wgrad_finish_unit(const TcParams& p, int m0, int nt0, int et, unsigned int* s_last) {
+  if (m0 >= p.d_rows || nt0 >= p.d_cols) return;                 // the phantom tile of an odd pair (CTA-uniform)
+  // publish this unit's partial tile and take a ticket of the tile
+  __threadfence();
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  const int tile_id = (m0 / kBlockM) * p.tiles_n + nt0 / C::block_n;
+  if (et == 0) {
+    const unsigned int prev = atomicAdd(&p.fin.tickets[tile_id], 1u);
+    const bool last = prev + 1u == unsigned(p.nsplit);
+    if (last) p.fin.tickets[tile_id] = 0u;                       // ready for the next launch
+    *s_last = last ? 1u : 0u;
+  }
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  if (*s_last == 0u) return;
+  __threadfence();
+  // the tile as a region of dW [N, K] (row pitch p.ldd = K): WGRAD_T stores D transposed
+  int n_begin, n_count, k_begin, k_count;
+  if (C::trans_out) { n_begin = nt0; n_count = min(C::block_n, p.d_cols - nt0); k_begin = m0; k_count = min(kBlockM, p.d_rows - m0); }
+  else              { n_begin = m0;  n_count = min(kBlockM, p.d_rows - m0);    k_begin = nt0; k_count = min(C::block_n, p.d_cols - nt0); }
+  const int Kdim = p.ldd, k4c = k_count >> 2, total = n_count * k4c;
+  const float* col_add = p.fin.mode == 1 ? p.fin.u.col_add : p.fin.col_add;
+  float* hi = static_cast<float*>(p.fin.u.Wop_hi);
+  const float scale = (p.fin.mode == 1 && p.fin.u.prec == VV_PREC_F16X3 && hi) ? f16_hdr(hi)->scale : 1.f;
+  const long long owned4 = (long long)p.fin.rows_per * (Kdim >> 2);
+  float amax = 0.f;
+  for (int idx = et; idx < total; idx += 256) {
+    const int r = idx / k4c, c4 = idx - r * k4c;
+    const int n = n_begin + r, k = k_begin + c4 * 4;
+    const long long i = ((long long)n * Kdim + k) >> 2;                         // float4 index in [N, K]
+    float4 g = __ldcg(reinterpret_cast<const float4*>(p.D) + i);
+    if (col_add && k + 4 == Kdim) g.w += col_add[n];                            // .w is column K-1
+    for (int sp = 1; sp < p.nsplit; ++sp) {                                     // slab order: deterministic
+      const float4 t = __ldcg(reinterpret_cast<const float4*>(p.D + (long long)sp * p.slab_stride) + i);
+      g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+    }
+    if (p.fin.mode == 1) {
+      sgd_update4(p.fin.u, i, g, scale, amax);
+    } else {
+      const int o = n / p.fin.rows_per;                                         // owner rank of row n
+      reinterpret_cast<float4*>(p.fin.peers.recv_dw[o])[(long long)p.fin.rank * owned4 + (i - (long long)o * owned4)] = g;
+    }
+  }
+  if (p.fin.mode == 1) {
+    if (p.fin.u.prec == VV_PREC_F16X3 && hi) f16_publish_absmax(hi, amax);
+    if (k_begin == 0)                                                           // this block of the bias blob goes with feature tile 0
+      for (int j = et; j < n_count; j += 256) sgd_update_bias1(p.fin.u, n_begin + j);
+    return;
+  }
+  // data parallel: count the finished tiles; the CTA finishing the last one completes this rank's push
+  __threadfence_system();
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  const int ntiles = p.tiles_m * p.tiles_n;
+  if (et == 0) {
+    const unsigned int prev = atomicAdd(&p.fin.tickets[ntiles], 1u);
+    const bool last = prev + 1u == unsigned(ntiles);
+    if (last) p.fin.tickets[ntiles] = 0u;
+    *s_last = last ? 1u : 0u;
+  }
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  if (*s_last == 0u) return;
+  __threadfence();
+  for (int d = 0; d < p.fin.G; ++d)                                             // (db, loss, violations) to every rank
+    for (int i = et; i < p.fin.nsmall; i += 256) p.fin.peers.recv_small[d][p.fin.rank * p.fin.small_stride + i] = p.fin.small_src[i];
+  __threadfence_system();
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  if (et == 0) {
+    __threadfence_system();
+    for (int d = 0; d < p.fin.G; ++d) dp_st_release_sys(&p.fin.peers.flags[d][kDpFlagDwReady + p.fin.rank], p.fin.seq);
+  }
+}
+
 template <class C>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_hb,
@@ -98,6 +174,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   uint64_t* tmem_full = empty_bar + C::stages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  unsigned int* fin_last = tmem_slot + 1;          // split-K finish: "this CTA took the last ticket" (epilogue warps)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -493,6 +570,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             }
           }
         }
+        if (!C::fwd_epi && p.fin.tickets)
+          wgrad_finish_unit<C>(p, m0, (t % p.tiles_n) * C::block_n, int(threadIdx.x) - 128, fin_last);
       } else {
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
@@ -535,6 +614,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         acc ^= 1; if (acc == 0) acc_phase ^= 1u;
+        if (!C::fwd_epi && p.fin.tickets)
+          wgrad_finish_unit<C>(p, m0, (t % p.tiles_n) * C::block_n, int(threadIdx.x) - 128, fin_last);
       }
     }
   }
@@ -673,6 +754,13 @@ int launch_cfg(const GemmProblem& g, cudaStream_t stream) {
   p.D = g.D + (C::trans_out ? (long long)n0 * g.K : 0); p.slab_stride = g.slab_stride;
   p.act_N = g.N;
   p.wait = g.wait;
+  p.fin = WgradFinish();
+  if (g.finish && g.finish->tickets) {
+    if (g.kind != GEMM_WGRAD && g.kind != GEMM_WGRAD_T) { set_error("the split-K finish belongs to the weight-gradient kernels"); return VV_ERR_INVALID; }
+    if (n0 != 0 || ncols != g.N) { set_error("the split-K finish needs the whole output (no column slice)"); return VV_ERR_INVALID; }
+    if ((g.K % 4) != 0) { set_error("the split-K finish needs K %% 4 == 0"); return VV_ERR_INVALID; }
+    p.fin = *g.finish;
+  }
   p.epi = g.epi;
   p.rowmap = g.rowmap;
   p.ga0 = static_cast<const uint16_t*>(g.A.hi); p.ga1 = static_cast<const uint16_t*>(g.A.lo);

@@ -597,6 +597,310 @@ rank_fused_kernel(const float* __restrict__ H, const RankDev p, const float gsca
   }
 }
 
+// ---- K2+K3 in one pass, second generation ------------------------------------------------------------------
+// Same data flow as rank_fused_kernel (the R rows of an item in registers, one read of H, one write of the dZ operand)
+// for the trainer's hot case -- operand-only output (no fp32 dZ, no score blobs), nvec == 1, R <= 16 -- with the
+// instruction count cut to what the arithmetic needs (the first kernel is issue-bound at ~1 900 instructions per warp
+// and item):
+//   * packed fp32 pairs (FFMA2 / FMUL2 / FADD2, sm_100) for every element-wise product;
+//   * the operand scale and the dropout scale are folded into the per-row coefficients by the scalar chain, so a gradient
+//     element is fma2(A', cbar, B' * x) * gate and goes to the fp16 / bf16 conversion as it is; db, dq and max|dZ| are
+//     accumulated in the scaled domain and unscaled once per CTA (the operand scale is a power of two: exact);
+//   * the ReLU/dropout gate [H > 0] as a 0/1 float (one FSET per element) multiplied in packed form;
+//   * every warp evaluates the per-item scalar chain itself from the shared partial sums (no second barrier, no warp idles
+//     behind warp 0's sqrt / pow / divide chain);
+//   * db / dq without float atomics: every CTA leaves its column sums in a workspace, the last CTA of each group of
+//     kRankGroup CTAs adds its group's in CTA order, the last group adds the group sums in group order -> run-to-run
+//     deterministic like the reference's gemv (inner_product_layer.cpp:93-96).  The same final CTA adds up the batch loss.
+// Formulas, reduction trees and the order of operations that matters for rounding are those of rank_fused_kernel; the
+// folded scales change the last bit of individual gradient elements (both are within 1e-6 of the two-kernel path).
+constexpr int kRankGroup = 24;
+
+__device__ __forceinline__ float2 lo2(const float4& v) { return make_float2(v.x, v.y); }
+__device__ __forceinline__ float2 hi2(const float4& v) { return make_float2(v.z, v.w); }
+__device__ __forceinline__ float2 splat2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float dot4p(const float4& a, const float4& b) {          // (a.x b.x + a.z b.z) + (a.y b.y + a.w b.w)
+  const float2 t = __ffma2_rn(hi2(a), hi2(b), __fmul2_rn(lo2(a), lo2(b)));
+  return t.x + t.y;
+}
+// 1.0f where x > 0 else 0.0f (H is post-ReLU/dropout: never negative)
+__device__ __forceinline__ float gate1(float x) {
+  float g;
+  asm("set.gt.f32.f32 %0, %1, 0f00000000;" : "=f"(g) : "f"(x));
+  return g;
+}
+__device__ __forceinline__ float amax4(float m, const float4& v) {
+  return fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+}
+// operand store of 4 consecutive elements that are ALREADY scaled (F16X3) -- OUT: 2 TF32X3, 4 BF16, 8 F16X3
+template <int OUT>
+__device__ __forceinline__ void store_op4(const BwdOut& o, size_t off, const float4& v) {
+  if (OUT == 8) {
+    const uint32_t p01 = pack_f16x2_sat(v.x, v.y), p23 = pack_f16x2_sat(v.z, v.w);
+    const float2 f01 = unpack_f16x2(p01), f23 = unpack_f16x2(p23);
+    const float2 r01 = __fadd2_rn(lo2(v), make_float2(-f01.x, -f01.y)), r23 = __fadd2_rn(hi2(v), make_float2(-f23.x, -f23.y));
+    *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(o.hi) + off) = make_uint2(p01, p23);
+    *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(o.lo) + off) = make_uint2(pack_f16x2_sat(r01.x, r01.y), pack_f16x2_sat(r23.x, r23.y));
+  } else if (OUT == 4) {
+    *reinterpret_cast<uint2*>(o.bf + off) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  } else {
+    store_x3(o.hi, o.lo, o.count, off, v);
+  }
+}
+
+struct RankWs {            // deterministic column sums (db, dq): layout of the workspace, in floats
+  unsigned int* tickets;   // [groups + 1], zero at first use, self-resetting
+  float* cta_part;         // [grid][2][N]
+  float* grp_part;         // [groups][2][N]
+};
+
+template <int CT, int NNT, int OUT>
+__global__ void __launch_bounds__(256, 2)
+rank_fused2_kernel(const float* __restrict__ H, const RankDev p, const float gscale, const float dscale,
+                   const BwdOut out, float* __restrict__ db_accum, const float* __restrict__ delta,
+                   float* __restrict__ dq_accum, float* __restrict__ stats, float* __restrict__ item_loss,
+                   float* __restrict__ item_viol, const RankWs ws, unsigned int* __restrict__ done_counter,
+                   const float inv_count, float* __restrict__ loss_out, float* __restrict__ viol_out) {
+  constexpr int RMAX = 16;
+  extern __shared__ float sm[];
+  const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = T >> 5;
+  const int Cc = CT > 0 ? CT : p.C, Nn = NNT > 0 ? NNT : p.Nn;
+  const int J = 1 + Nn, R = Cc + Nn;
+  const int per = (2 * J + 1) * nw;                    // floats per partial-sum buffer (double buffered by item parity)
+  const bool col_ok = tid < p.N4;
+  const float oscale = (OUT == 8) ? f16_hdr(out.hi)->scale : 1.f;
+  const float osc = dscale * oscale;                   // what every stored gradient element is multiplied with
+  float4 dbacc = make_float4(0.f, 0.f, 0.f, 0.f), dqacc = make_float4(0.f, 0.f, 0.f, 0.f);
+  float amax = 0.f;
+  int parity = 0;
+  for (int b = blockIdx.x; b < p.B; b += gridDim.x, parity ^= 1) {
+    float* part = sm + parity * per;                   // [2J+1][nw]: (s_x, p_x) per branch, then s_c
+    // ---- one load phase: R independent 128-bit loads per thread
+    float4 x[RMAX];
+#pragma unroll
+    for (int r = 0; r < RMAX; ++r)
+      x[r] = (r < R && col_ok) ? ld4(H + (size_t(r) * p.B + b) * p.N + tid * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    // ---- context mean, bottom order (eltwise_layer.cpp:67-73)
+    float2 cl = make_float2(0.f, 0.f), ch = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int r = 1; r < RMAX; ++r) {
+      if (r < Cc) {
+        const float2 a = splat2(p.coeff[r - 1]);
+        cl = __ffma2_rn(a, lo2(x[r]), cl); ch = __ffma2_rn(a, hi2(x[r]), ch);
+      }
+    }
+    const float4 cbar = make_float4(cl.x, cl.y, ch.x, ch.y);
+    if (NNT > 0) {
+      constexpr int NV = 2 * (NNT > 0 ? 1 + NNT : 1) + 1;
+      float v[NV];
+#pragma unroll
+      for (int r = 0; r < RMAX; ++r) {
+        if (r < R && (r == 0 || r >= Cc)) {
+          const int j = (r == 0) ? 0 : r - Cc + 1;
+          v[2 * j] = dot4p(x[r], x[r]); v[2 * j + 1] = dot4p(cbar, x[r]);
+        }
+      }
+      v[NV - 1] = dot4p(cbar, cbar);
+      int e; bool ok;
+      warp_multi_sum<NV>(v, lane, e, ok);
+      if (ok) part[e * nw + warp] = v[0];
+    } else {
+      {
+        float s = warp_sum(dot4p(cbar, cbar));
+        if (lane == 0) part[2 * J * nw + warp] = s;
+      }
+#pragma unroll
+      for (int r = 0; r < RMAX; ++r) {
+        if (r < R && (r == 0 || r >= Cc)) {             // uniform branch
+          const int j = (r == 0) ? 0 : r - Cc + 1;
+          float sx = warp_sum(dot4p(x[r], x[r])), px = warp_sum(dot4p(cbar, x[r]));
+          if (lane == 0) { part[(j * 2 + 0) * nw + warp] = sx; part[(j * 2 + 1) * nw + warp] = px; }
+        }
+      }
+    }
+    __syncthreads();
+    // ---- per-item scalars, lane j = branch j, in EVERY warp (formulas of rank_fused_kernel); the coefficients carry
+    // the output scale: rA = A * osc, rB = B * osc, Fs/Fc likewise
+    float rA = 0.f, rB = 0.f, rE = 0.f, rD = 0.f, Fs, Fc;
+    {
+      float s_c = 0.f;
+      for (int w = 0; w < nw; ++w) s_c += part[2 * J * nw + w];
+      float sj = 0.f, pj = 0.f;
+      if (lane < J) {
+        for (int w = 0; w < nw; ++w) sj += part[(lane * 2 + 0) * nw + w];
+        for (int w = 0; w < nw; ++w) pj += part[(lane * 2 + 1) * nw + w];
+      }
+      if (stats && warp == 0) {
+        float* st = stats + size_t(b) * p.stride;
+        if (lane == 0) st[0] = s_c;
+        if (lane < J) { st[1 + 2 * lane] = sj; st[2 + 2 * lane] = pj; }
+      }
+      // normalization_layer.cpp:36-59: r = pow(s, .5) + eps ; y = x / r.  scores = <c^, x^>
+      const float nc = sqrtf(s_c) + p.eps;
+      const float nj = sqrtf(sj) + p.eps;
+      const float score = pj / (nc * nj);
+      const float score_t = __shfl_sync(0xffffffffu, score, 0);
+      const float dlt = score_t - score;                                  // caffe_sub :69
+      const float h = fmaxf(0.f, p.margin - dlt);
+      const bool neg = lane >= 1 && lane < J;
+      // max_margin_loss_layer.cpp:149-192: L2 g = h * (lw*2/count); L1 g = [h>0] * lw/count
+      float w = neg ? ((p.norm == 2) ? h * gscale : (h > 0.f ? gscale : 0.f)) : 0.f;
+      const float vterm = (neg && dlt < 0.f) ? 1.f : 0.f;
+      const float g = warp_sum(w);
+      if (warp == 0) {                                                    // the item's loss terms: once
+        const float loss = warp_sum(neg ? ((p.norm == 2) ? h * h : fabsf(h)) : 0.f);
+        const float viol = warp_sum(vterm);
+        if (lane == 0) { if (item_loss) item_loss[b] = loss; if (item_viol) item_viol[b] = viol; }
+      }
+      if (lane == 0) w = -g;                                              // d s+ = -1 * d s- (axpby, :210-212)
+      const float q = powf(sj, 1.5f) + p.eps;                             // normalization_layer.cpp:101-107
+      const float aj = w * pj / nc;
+      const float e = w / nj;
+      if (lane < J) {
+        rA = (sj * w / (nc * q)) * osc; rB = (-aj / q) * osc; rE = e;
+        rD = delta ? delta[size_t(lane == 0 ? 0 : Cc + lane - 1) * p.B + b] : 0.f;
+      }
+      const float ac = warp_sum(lane < J ? e * pj : 0.f);                 // a_c = <cbar, d c^>
+      const float qc = powf(s_c, 1.5f) + p.eps;
+      Fs = (s_c / qc) * osc; Fc = (-ac / qc) * osc;
+    }
+    // ---- target + negative rows: dx = (A cbar + B x) [H > 0]; D += E x
+    float2 Dl = make_float2(0.f, 0.f), Dh = make_float2(0.f, 0.f);
+    float2 dbl = lo2(dbacc), dbh = hi2(dbacc);
+#pragma unroll
+    for (int r = 0; r < RMAX; ++r) {
+      if (r < R && (r == 0 || r >= Cc)) {
+        const int j = (r == 0) ? 0 : r - Cc + 1;
+        const float a = __shfl_sync(0xffffffffu, rA, j), bb = __shfl_sync(0xffffffffu, rB, j), e = __shfl_sync(0xffffffffu, rE, j);
+        const float dl = __shfl_sync(0xffffffffu, rD, j);
+        if (col_ok) {
+          const float4 xv = x[r];
+          const float2 a2 = splat2(a), b2 = splat2(bb), e2 = splat2(e);
+          float2 ol = __ffma2_rn(a2, cl, __fmul2_rn(b2, lo2(xv))), oh = __ffma2_rn(a2, ch, __fmul2_rn(b2, hi2(xv)));
+          Dl = __ffma2_rn(e2, lo2(xv), Dl); Dh = __ffma2_rn(e2, hi2(xv), Dh);
+          ol = __fmul2_rn(ol, make_float2(gate1(xv.x), gate1(xv.y))); oh = __fmul2_rn(oh, make_float2(gate1(xv.z), gate1(xv.w)));
+          dbl = __fadd2_rn(dbl, ol); dbh = __fadd2_rn(dbh, oh);
+          const float4 o = make_float4(ol.x, ol.y, oh.x, oh.y);
+          if (dl != 0.f) {                                                // uniform; only rows hit by the K-1 copy quirk
+            dqacc.x = fmaf(dl, o.x, dqacc.x); dqacc.y = fmaf(dl, o.y, dqacc.y);
+            dqacc.z = fmaf(dl, o.z, dqacc.z); dqacc.w = fmaf(dl, o.w, dqacc.w);
+          }
+          if (OUT == 8) amax = amax4(amax, o);
+          store_op4<OUT>(out, (size_t(r) * p.B + b) * p.N + tid * 4, o);
+        }
+      }
+    }
+    // ---- context rows: d cbar = (s_c * d c^ - cbar * a_c) / q_c ; d c_i = coeff_i * d cbar
+    const float2 dcl = __ffma2_rn(splat2(Fs), Dl, __fmul2_rn(splat2(Fc), cl)), dch = __ffma2_rn(splat2(Fs), Dh, __fmul2_rn(splat2(Fc), ch));
+#pragma unroll
+    for (int r = 1; r < RMAX; ++r) {
+      if (r < Cc && col_ok) {
+        const float2 a2 = splat2(p.coeff[r - 1]);
+        const float4 xv = x[r];
+        const float2 ol = __fmul2_rn(__fmul2_rn(a2, dcl), make_float2(gate1(xv.x), gate1(xv.y)));
+        const float2 oh = __fmul2_rn(__fmul2_rn(a2, dch), make_float2(gate1(xv.z), gate1(xv.w)));
+        dbl = __fadd2_rn(dbl, ol); dbh = __fadd2_rn(dbh, oh);
+        const float4 o = make_float4(ol.x, ol.y, oh.x, oh.y);
+        if (OUT == 8) amax = amax4(amax, o);
+        store_op4<OUT>(out, (size_t(r) * p.B + b) * p.N + tid * 4, o);
+      }
+    }
+    dbacc = make_float4(dbl.x, dbl.y, dbh.x, dbh.y);
+    // no trailing barrier: the next item uses the other partial-sum buffer, and the barrier after ITS reductions orders
+    // this item's reads of `part` before the buffer is written again two items later
+  }
+  // back to the unscaled domain (oscale is a power of two: exact)
+  const float inv_os = 1.f / oscale;
+  dbacc.x *= inv_os; dbacc.y *= inv_os; dbacc.z *= inv_os; dbacc.w *= inv_os;
+  dqacc.x *= inv_os; dqacc.y *= inv_os; dqacc.z *= inv_os; dqacc.w *= inv_os;
+  if (OUT == 8) f16_publish_absmax(out.hi, amax * inv_os);
+  __shared__ unsigned int s_flag;
+  __shared__ float red[66];
+  if (ws.tickets == nullptr) {
+    // no workspace: atomics (order-dependent rounding), and the ticketed loss reduction of rank_fused_kernel
+    if (col_ok) {
+      if (db_accum) {
+        atomicAdd(db_accum + tid * 4 + 0, dbacc.x); atomicAdd(db_accum + tid * 4 + 1, dbacc.y);
+        atomicAdd(db_accum + tid * 4 + 2, dbacc.z); atomicAdd(db_accum + tid * 4 + 3, dbacc.w);
+      }
+      if (dq_accum) {
+        atomicAdd(dq_accum + tid * 4 + 0, dqacc.x); atomicAdd(dq_accum + tid * 4 + 1, dqacc.y);
+        atomicAdd(dq_accum + tid * 4 + 2, dqacc.z); atomicAdd(dq_accum + tid * 4 + 3, dqacc.w);
+      }
+    }
+    if (done_counter) {
+      __syncthreads();
+      last_cta_loss_reduce<false>(done_counter, item_loss, item_viol, p.B, inv_count, loss_out, viol_out, red, tid, T);
+    }
+    return;
+  }
+  // ---- deterministic column sums: CTA partials -> group sums (CTA order) -> totals (group order)
+  const int N4 = p.N4;
+  const int grp = blockIdx.x / kRankGroup, ngroups = (gridDim.x + kRankGroup - 1) / kRankGroup;
+  const int g0 = grp * kRankGroup, gsize = min(kRankGroup, int(gridDim.x) - g0);
+  if (col_ok) {
+    float4* mine = reinterpret_cast<float4*>(ws.cta_part) + size_t(blockIdx.x) * 2 * N4;
+    mine[tid] = dbacc; mine[N4 + tid] = dqacc;
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned int prev = atomicAdd(&ws.tickets[grp], 1u);
+    const bool last = prev + 1u == unsigned(gsize);
+    if (last) ws.tickets[grp] = 0u;
+    s_flag = last ? 1u : 0u;
+  }
+  __syncthreads();
+  if (s_flag == 0u) return;
+  __threadfence();
+  if (col_ok) {
+    const float4* base = reinterpret_cast<const float4*>(ws.cta_part) + size_t(g0) * 2 * N4;
+    float4 sb = make_float4(0.f, 0.f, 0.f, 0.f), sq = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+    for (int c = 0; c < gsize; ++c) {
+      const float4 a = __ldcg(base + size_t(c) * 2 * N4 + tid), q = __ldcg(base + size_t(c) * 2 * N4 + N4 + tid);
+      sb.x += a.x; sb.y += a.y; sb.z += a.z; sb.w += a.w; sq.x += q.x; sq.y += q.y; sq.z += q.z; sq.w += q.w;
+    }
+    float4* gp = reinterpret_cast<float4*>(ws.grp_part) + size_t(grp) * 2 * N4;
+    gp[tid] = sb; gp[N4 + tid] = sq;
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned int prev = atomicAdd(&ws.tickets[ngroups], 1u);
+    const bool last = prev + 1u == unsigned(ngroups);
+    if (last) ws.tickets[ngroups] = 0u;
+    s_flag = last ? 1u : 0u;
+  }
+  __syncthreads();
+  if (s_flag == 0u) return;
+  __threadfence();
+  if (col_ok) {
+    const float4* base = reinterpret_cast<const float4*>(ws.grp_part);
+    float4 sb = make_float4(0.f, 0.f, 0.f, 0.f), sq = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+    for (int c = 0; c < ngroups; ++c) {
+      const float4 a = __ldcg(base + size_t(c) * 2 * N4 + tid), q = __ldcg(base + size_t(c) * 2 * N4 + N4 + tid);
+      sb.x += a.x; sb.y += a.y; sb.z += a.z; sb.w += a.w; sq.x += q.x; sq.y += q.y; sq.z += q.z; sq.w += q.w;
+    }
+    if (db_accum) reinterpret_cast<float4*>(db_accum)[tid] = sb;
+    if (dq_accum) reinterpret_cast<float4*>(dq_accum)[tid] = sq;
+  }
+  if (loss_out || viol_out) {                           // the batch loss / violation count, fixed order (as last_cta_loss_reduce)
+    float a = 0.f, c = 0.f;
+    for (int i = tid; i < p.B; i += T) { a += __ldcg(item_loss + i); c += __ldcg(item_viol + i); }
+    a = warp_sum(a); c = warp_sum(c);
+    if ((tid & 31) == 0) { red[tid >> 5] = a; red[32 + (tid >> 5)] = c; }
+    __syncthreads();
+    if (tid == 0) {
+      a = 0.f; c = 0.f;
+      for (int w = 0; w < (T >> 5); ++w) { a += red[w]; c += red[32 + w]; }
+      if (loss_out) *loss_out = a * inv_count;
+      if (viol_out) *viol_out = c;
+    }
+  }
+}
+
 // ---- K2+K3 with the rows staged in shared memory by bulk async copies -----------------------------------------
 // Same math, reduction trees and outputs as rank_fused_kernel (bit-identical results), different data movement: a
 // producer warp streams whole items (R rows x N floats, one cp.async.bulk per row, mbarrier complete_tx) into a ring
@@ -921,16 +1225,31 @@ extern "C" int vv_rank_loss_fused(const float* H, const vv_rank_cfg_t* cfg, floa
                                   const float* delta, float* dq_accum, vv_stream_t stream) {
   return vv::rank_loss_fused_counted(H, cfg, loss_weight, act_fused, dropout_scale, stats, target_score, neg_score, item_loss,
                                      item_viol, loss, violations, dZ, dZop_hi, dZop_lo, prec, db_accum, delta, dq_accum,
-                                     nullptr, stream);
+                                     nullptr, stream, nullptr, 0);
 }
 
 // done_counter != NULL (a zeroed device word): the batch loss / violation sums are produced by the last CTA of the
 // fused kernel instead of a separate rank_loss_reduce_kernel launch (the trainer's path).
+// workspace of the second-generation kernel's deterministic column sums: tickets | per-CTA sums | per-group sums
+size_t vv::rank_loss_workspace_bytes(int N) {
+  const size_t grid = size_t(num_sms()) * 4, groups = (grid + kRankGroup - 1) / kRankGroup;
+  return 1024 + (grid + groups) * 2 * size_t(N) * sizeof(float);
+}
+bool vv::rank_loss_fused_v2_applies(const vv_rank_cfg_t* cfg, int prec, bool want_dz, bool want_scores) {
+  static const bool on = [] { const char* e = getenv("VV_RANK_V2"); return !(e && atoi(e) == 0); }();
+  const char* ring_e = getenv("VV_RANK_RING");
+  if (!on || (ring_e && atoi(ring_e) > 0)) return false;
+  if (!cfg || want_dz || want_scores) return false;
+  if (prec != VV_PREC_TF32X3 && prec != VV_PREC_BF16 && prec != VV_PREC_F16X3) return false;
+  return cfg->N % 4 == 0 && cfg->N <= 1024 && cfg->C + cfg->Nn <= 16 && cfg->Nn >= 1 && cfg->C >= 2;
+}
+
 int vv::rank_loss_fused_counted(const float* H, const vv_rank_cfg_t* cfg, float loss_weight, int act_fused,
                                 float dropout_scale, float* stats, float* target_score, float* neg_score,
                                 float* item_loss, float* item_viol, float* loss, float* violations,
                                 float* dZ, void* dZop_hi, void* dZop_lo, int prec, float* db_accum,
-                                const float* delta, float* dq_accum, unsigned int* done_counter, vv_stream_t stream) {
+                                const float* delta, float* dq_accum, unsigned int* done_counter, vv_stream_t stream,
+                                void* workspace, size_t workspace_bytes) {
   RankDev d; int T;
   int rc = make_dev(cfg, &d, &T);
   if (rc) return rc;
@@ -957,6 +1276,40 @@ int vv::rank_loss_fused_counted(const float* H, const vv_rank_cfg_t* cfg, float 
                    (o.prec == VV_PREC_F16X3 ? 8 : 0);
   unsigned int* cnt = (loss || violations) ? done_counter : nullptr;       // fold the batch reduction into the kernel
   const float inv_count = 1.f / float(d.B * d.Nn);
+  if (rank_loss_fused_v2_applies(cfg, o.prec, o.dZ != nullptr, target_score || neg_score) && dZop_hi) {
+    const int per2 = (T <= 128) ? 4 : 2;
+    const int grid2 = d.B < num_sms() * per2 ? d.B : num_sms() * per2;
+    const size_t smem2 = sizeof(float) * 2 * (2 * J + 1) * nw;
+    RankWs ws; ws.tickets = nullptr; ws.cta_part = nullptr; ws.grp_part = nullptr;
+    const bool want_sums = db_accum || dq_accum || loss || violations;
+    if (workspace && want_sums && (loss || violations ? (item_loss && item_viol) : true)) {
+      const size_t groups = (size_t(grid2) + kRankGroup - 1) / kRankGroup;
+      const size_t need = 1024 + (size_t(grid2) + groups) * 2 * size_t(d.N) * sizeof(float);
+      VV_REQUIRE(workspace_bytes >= need && groups + 1 <= 256, "rank_loss_fused: workspace too small (%zu bytes, need %zu)", workspace_bytes, need);
+      ws.tickets = static_cast<unsigned int*>(workspace);
+      ws.cta_part = reinterpret_cast<float*>(static_cast<char*>(workspace) + 1024);
+      ws.grp_part = ws.cta_part + size_t(grid2) * 2 * d.N;
+    }
+    const float ds = act_fused ? dropout_scale : 1.f;
+    VV_REQUIRE(act_fused, "rank_loss_fused: the operand-only fast kernel is the fused-activation form");
+#define VV_RANK_V2(CT, NNT, OUT)                                                                                        \
+    rank_fused2_kernel<CT, NNT, OUT><<<grid2, T, smem2, stream>>>(H, d, gscale, ds, o, db_accum, delta, dq_accum, stats,    \
+        item_loss, item_viol, ws, cnt, inv_count, loss, violations)
+    if (d.C == 5 && d.Nn == 10) {
+      if (mode == 8) VV_RANK_V2(5, 10, 8); else if (mode == 4) VV_RANK_V2(5, 10, 4); else VV_RANK_V2(5, 10, 2);
+    } else {
+      if (mode == 8) VV_RANK_V2(0, 0, 8); else if (mode == 4) VV_RANK_V2(0, 0, 4); else VV_RANK_V2(0, 0, 2);
+    }
+#undef VV_RANK_V2
+    VV_LAUNCH_CHECK();
+    count_launch();
+    if ((loss || violations) && !cnt && !ws.tickets) {
+      rank_loss_reduce_kernel<<<1, 1024, 0, stream>>>(item_loss, item_viol, d.B, inv_count, loss, violations);
+      VV_LAUNCH_CHECK();
+      count_launch();
+    }
+    return VV_OK;
+  }
   // ring variant (rows staged in shared memory by a producer warp): whenever two slots of R rows fit
   const char* ring_e = getenv("VV_RANK_RING");                      // 0 = register-resident kernel, n >= 2 = ring stages
   const int ring_env = ring_e ? atoi(ring_e) : -1;

@@ -244,21 +244,13 @@ __global__ void sgd_update_scalar_kernel(float* W, const float* parts, int npart
 __global__ void __launch_bounds__(256)
 sgd_update_tail_kernel(const UpdateTail u, const int main_blocks) {
   if (int(blockIdx.x) >= main_blocks) {            // ---- bias blob (scalar, nb elements)
-    for (int i = (blockIdx.x - main_blocks) * blockDim.x + threadIdx.x; i < u.nb; i += (gridDim.x - main_blocks) * blockDim.x) {
-      float g = u.db[i];
-      if (u.gscale != 1.f) g *= u.gscale;
-      const float w = u.b[i];
-      if (u.decay_b != 0.f) g = (u.reg_type == 2) ? fmaf(u.decay_b, w, g) : g + u.decay_b * float((0.f < w) - (w < 0.f));
-      const float h = fmaf(u.rate_b, g, u.momentum * u.bh[i]);
-      u.bh[i] = h; u.b[i] = w - h;
-      if (u.b_diff) u.b_diff[i] = h;
-    }
+    for (int i = (blockIdx.x - main_blocks) * blockDim.x + threadIdx.x; i < u.nb; i += (gridDim.x - main_blocks) * blockDim.x)
+      sgd_update_bias1(u, i);
     return;
   }
-  float* hi = static_cast<float*>(u.Wop_hi); float* lo = static_cast<float*>(u.Wop_lo);
+  float* hi = static_cast<float*>(u.Wop_hi);
   const float scale = (u.prec == VV_PREC_F16X3 && hi) ? f16_hdr(hi)->scale : 1.f;
   const long long n4 = u.count / 4, k4 = u.K / 4;
-  const float rate = u.rate_w, momentum = u.momentum, decay = u.decay_w, gscale = u.gscale;
   float amax = 0.f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)main_blocks * blockDim.x) {
     float4 g = reinterpret_cast<const float4*>(u.parts)[i];
@@ -268,31 +260,7 @@ sgd_update_tail_kernel(const UpdateTail u, const int main_blocks) {
       const float4 t = reinterpret_cast<const float4*>(u.parts + s * u.stride)[i];
       g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
     }
-    if (gscale != 1.f) { g.x *= gscale; g.y *= gscale; g.z *= gscale; g.w *= gscale; }
-    float4 w = reinterpret_cast<float4*>(u.W)[i];
-    if (decay != 0.f) {
-      if (u.reg_type == 2) {
-        g.x = fmaf(decay, w.x, g.x); g.y = fmaf(decay, w.y, g.y); g.z = fmaf(decay, w.z, g.z); g.w = fmaf(decay, w.w, g.w);
-      } else {
-        g.x += decay * float((0.f < w.x) - (w.x < 0.f)); g.y += decay * float((0.f < w.y) - (w.y < 0.f));
-        g.z += decay * float((0.f < w.z) - (w.z < 0.f)); g.w += decay * float((0.f < w.w) - (w.w < 0.f));
-      }
-    }
-    float4 h = reinterpret_cast<float4*>(u.hist)[i];
-    h.x = fmaf(rate, g.x, momentum * h.x); h.y = fmaf(rate, g.y, momentum * h.y);
-    h.z = fmaf(rate, g.z, momentum * h.z); h.w = fmaf(rate, g.w, momentum * h.w);
-    w.x -= h.x; w.y -= h.y; w.z -= h.z; w.w -= h.w;
-    reinterpret_cast<float4*>(u.hist)[i] = h;
-    reinterpret_cast<float4*>(u.W)[i] = w;
-    if (u.diff_out) reinterpret_cast<float4*>(u.diff_out)[i] = h;
-    if (last_col && u.col_out) u.col_out[i / k4] = w.w;
-    if (u.prec == VV_PREC_TF32X3 && hi) {
-      store_x3(hi, lo, size_t(n4) * 4, size_t(i) * 4, w);
-    } else if (u.prec == VV_PREC_F16X3 && hi) {
-      store_f16x3(hi, lo, size_t(i) * 4, w, scale, amax);
-    } else if (u.prec == VV_PREC_BF16 && hi) {
-      reinterpret_cast<uint2*>(hi)[i] = make_uint2(pack_bf16x2(w.x, w.y), pack_bf16x2(w.z, w.w));
-    }
+    sgd_update4(u, i, g, scale, amax);
   }
   if (u.prec == VV_PREC_F16X3 && hi) f16_publish_absmax(hi, amax);
 }
