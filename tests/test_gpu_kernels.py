@@ -333,6 +333,37 @@ def test_rank_loss_fused_equals_two_kernel_path(B, C, Nn, N, norm, prec, ring, m
     assert rel(dZ_b, dZ_ref) < 1e-5
 
 
+@pytest.mark.parametrize("B,C,Nn,N,norm", [(64, 5, 10, 512, 2), (33, 3, 4, 64, 1), (7, 5, 10, 1000, 2), (300, 7, 9, 256, 2),
+                                            (1, 5, 10, 512, 2), (700, 5, 10, 512, 2)])
+@pytest.mark.parametrize("prec", ["tf32x3", "f16x3", "bf16"])
+def test_rank_loss_fused_operand_only_form(B, C, Nn, N, norm, prec):
+    """The trainer's form of K2+K3 -- operand-only output, no score blobs -- runs the second-generation kernel (packed
+    fp32 pairs, output scales folded into the per-row coefficients, reciprocal-based scalar chain): against the float64
+    reference and the two-kernel path.  (700 items: more than one item per CTA and several CTA groups.)"""
+    R = C + Nn
+    g = torch.Generator(device="cuda").manual_seed(B + N)
+    H = torch.relu(torch.randn(R * B, N, device="cuda", generator=g))
+    H = (H * (torch.rand(R * B, N, device="cuda", generator=g) < 0.3) * 3.0).contiguous()
+    H[min(5, R * B - 1)] = 0.0
+    cfg = ops.rank_cfg(B, C, Nn, N, margin=2.0, norm=norm)
+    a = ops.rank_loss_forward(H, cfg)
+    b, dZ_none, op, db = ops.rank_loss_fused(H, cfg, 0.7, True, 10.0, prec=prec, want_dz=False, want_scores=False)
+    assert dZ_none is None
+    loss, viol, st, sn, dH_ref, dZ_ref = _rank_ref64(H, B, C, Nn, 2.0, norm, 0.7, 10.0)
+    assert rel(b["stats"], a["stats"]) < 1e-6
+    assert torch.equal(a["item_viol"], b["item_viol"]) and torch.equal(a["violations"], b["violations"])
+    assert abs(b["loss"].item() - loss) < 1e-5 * max(1, abs(loss)) and b["violations"].item() == viol
+    if prec == "f16x3":
+        got, tol = op.dequant(), 1e-5
+    elif prec == "bf16":
+        got, tol = op.hi.float(), 1e-2
+    else:
+        planes = op.lo.view(-1).view(torch.bfloat16).view(2, R * B, N)   # lo = planes [bf16(x) | bf16(x - hi)], hi = tf32(x)
+        got, tol = op.hi + planes[1].float(), 1e-5
+    assert rel(got, dZ_ref) < tol, rel(got, dZ_ref)
+    assert rel(db, dZ_ref.sum(0)) < 1e-5
+
+
 def test_rank_loss_fused_unsupported_shapes():
     assert not ops.rank_loss_fused_supported(ops.rank_cfg(8, 5, 30, 512))     # R > 32
     assert not ops.rank_loss_fused_supported(ops.rank_cfg(8, 5, 10, 2048))    # N > 1024

@@ -632,19 +632,25 @@ __device__ __forceinline__ float gate1(float x) {
 __device__ __forceinline__ float amax4(float m, const float4& v) {
   return fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
 }
-// operand store of 4 consecutive elements that are ALREADY scaled (F16X3) -- OUT: 2 TF32X3, 4 BF16, 8 F16X3
+// operand store of 4 consecutive elements that are ALREADY scaled (F16X3) -- OUT: 2 TF32X3, 4 BF16, 8 F16X3.
+// p_hi / p_lo: this thread's byte addresses in row 0 of the two planes; eoff: the row's element offset from there.
 template <int OUT>
-__device__ __forceinline__ void store_op4(const BwdOut& o, size_t off, const float4& v) {
+__device__ __forceinline__ void store_op4_at(const BwdOut& o, char* p_hi, char* p_lo, unsigned int eoff, const float4& v) {
   if (OUT == 8) {
     const uint32_t p01 = pack_f16x2_sat(v.x, v.y), p23 = pack_f16x2_sat(v.z, v.w);
     const float2 f01 = unpack_f16x2(p01), f23 = unpack_f16x2(p23);
     const float2 r01 = __fadd2_rn(lo2(v), make_float2(-f01.x, -f01.y)), r23 = __fadd2_rn(hi2(v), make_float2(-f23.x, -f23.y));
-    *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(o.hi) + off) = make_uint2(p01, p23);
-    *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(o.lo) + off) = make_uint2(pack_f16x2_sat(r01.x, r01.y), pack_f16x2_sat(r23.x, r23.y));
+    *reinterpret_cast<uint2*>(p_hi + size_t(eoff) * 2) = make_uint2(p01, p23);
+    *reinterpret_cast<uint2*>(p_lo + size_t(eoff) * 2) = make_uint2(pack_f16x2_sat(r01.x, r01.y), pack_f16x2_sat(r23.x, r23.y));
   } else if (OUT == 4) {
-    *reinterpret_cast<uint2*>(o.bf + off) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    *reinterpret_cast<uint2*>(p_hi + size_t(eoff) * 2) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
   } else {
-    store_x3(o.hi, o.lo, o.count, off, v);
+    float4 h;
+    h.x = to_tf32_rna(v.x); h.y = to_tf32_rna(v.y); h.z = to_tf32_rna(v.z); h.w = to_tf32_rna(v.w);
+    *reinterpret_cast<float4*>(p_hi + size_t(eoff) * 4) = h;
+    *reinterpret_cast<uint2*>(p_lo + size_t(eoff) * 2) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    *reinterpret_cast<uint2*>(p_lo + (size_t(eoff) + o.count) * 2) =
+        make_uint2(pack_bf16x2(v.x - h.x, v.y - h.y), pack_bf16x2(v.z - h.z, v.w - h.w));
   }
 }
 
@@ -654,7 +660,9 @@ struct RankWs {            // deterministic column sums (db, dq): layout of the 
   float* grp_part;         // [groups][2][N]
 };
 
-template <int CT, int NNT, int OUT>
+// FULL: blockDim.x == N/4 (every thread owns a column group: no bounds checks, no zero fill); NWT > 0: warps per CTA fixed
+// at compile time (4 = the N = 512 case: the per-branch partial sums are one 128-bit shared-memory load)
+template <int CT, int NNT, int OUT, bool FULL, int NWT>
 __global__ void __launch_bounds__(256, 2)
 rank_fused2_kernel(const float* __restrict__ H, const RankDev p, const float gscale, const float dscale,
                    const BwdOut out, float* __restrict__ db_accum, const float* __restrict__ delta,
@@ -662,24 +670,39 @@ rank_fused2_kernel(const float* __restrict__ H, const RankDev p, const float gsc
                    float* __restrict__ item_viol, const RankWs ws, unsigned int* __restrict__ done_counter,
                    const float inv_count, float* __restrict__ loss_out, float* __restrict__ viol_out) {
   constexpr int RMAX = 16;
-  extern __shared__ float sm[];
-  const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = T >> 5;
+  extern __shared__ __align__(16) float sm[];
+  const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = NWT > 0 ? NWT : (T >> 5);
   const int Cc = CT > 0 ? CT : p.C, Nn = NNT > 0 ? NNT : p.Nn;
   const int J = 1 + Nn, R = Cc + Nn;
   const int per = (2 * J + 1) * nw;                    // floats per partial-sum buffer (double buffered by item parity)
-  const bool col_ok = tid < p.N4;
+  const bool col_ok = FULL || tid < p.N4;
   const float oscale = (OUT == 8) ? f16_hdr(out.hi)->scale : 1.f;
   const float osc = dscale * oscale;                   // what every stored gradient element is multiplied with
+  // row r of item b starts at element (r * B + b) * N: 32-bit element offsets from per-item bases (the launcher checks
+  // that the blob has fewer than 2^31 elements), one IMAD.WIDE per row instead of a 64-bit multiply chain
+  const unsigned int rs = unsigned(p.B) * unsigned(p.N);
+  constexpr int kOpBytes = (OUT == 2) ? 4 : 2;         // element size of operand plane `hi`
   float4 dbacc = make_float4(0.f, 0.f, 0.f, 0.f), dqacc = make_float4(0.f, 0.f, 0.f, 0.f);
   float amax = 0.f;
   int parity = 0;
   for (int b = blockIdx.x; b < p.B; b += gridDim.x, parity ^= 1) {
     float* part = sm + parity * per;                   // [2J+1][nw]: (s_x, p_x) per branch, then s_c
+    const unsigned int e0 = unsigned(b) * unsigned(p.N) + unsigned(tid) * 4u;      // element offset of this thread in row 0
+    const float* hp = H + e0;
     // ---- one load phase: R independent 128-bit loads per thread
     float4 x[RMAX];
 #pragma unroll
-    for (int r = 0; r < RMAX; ++r)
-      x[r] = (r < R && col_ok) ? ld4(H + (size_t(r) * p.B + b) * p.N + tid * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < RMAX; ++r) {
+      if (r < R) {
+        if (FULL || col_ok) x[r] = ld4(hp + size_t(unsigned(r) * rs));
+        else x[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    // the NEXT item's rows on their way into L2 while this one is processed (one bulk prefetch per row, thread r takes row r)
+    if (FULL && tid < R && b + int(gridDim.x) < p.B) {
+      const float* nx = H + size_t(unsigned(tid) * rs) + size_t(unsigned(b + gridDim.x) * unsigned(p.N));
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(nx), "r"(unsigned(p.N) * 4u) : "memory");
+    }
     // ---- context mean, bottom order (eltwise_layer.cpp:67-73)
     float2 cl = make_float2(0.f, 0.f), ch = make_float2(0.f, 0.f);
 #pragma unroll
@@ -719,16 +742,27 @@ rank_fused2_kernel(const float* __restrict__ H, const RankDev p, const float gsc
       }
     }
     __syncthreads();
-    // ---- per-item scalars, lane j = branch j, in EVERY warp (formulas of rank_fused_kernel); the coefficients carry
-    // the output scale: rA = A * osc, rB = B * osc, Fs/Fc likewise
+    // ---- per-item scalars, lane j = branch j, in EVERY warp; the coefficients carry the output scale: rA = A * osc,
+    // rB = B * osc, Fs / Fc likewise.  Same formulas as rank_fused_kernel with the divisions as correctly rounded
+    // reciprocals times the numerator and pow(s, 1.5) as s * sqrt(s) (both within 1.5 ulp of the reference's libm values;
+    // the chain is evaluated by every warp, so its length is paid four times over).
     float rA = 0.f, rB = 0.f, rE = 0.f, rD = 0.f, Fs, Fc;
     {
-      float s_c = 0.f;
-      for (int w = 0; w < nw; ++w) s_c += part[2 * J * nw + w];
-      float sj = 0.f, pj = 0.f;
-      if (lane < J) {
-        for (int w = 0; w < nw; ++w) sj += part[(lane * 2 + 0) * nw + w];
-        for (int w = 0; w < nw; ++w) pj += part[(lane * 2 + 1) * nw + w];
+      float s_c = 0.f, sj = 0.f, pj = 0.f;
+      if (NWT == 4) {                                                     // [e][4]: one 128-bit load per value, warps in order
+        const float4 c4 = *reinterpret_cast<const float4*>(part + 2 * J * 4);
+        s_c = ((c4.x + c4.y) + c4.z) + c4.w;
+        if (lane < J) {
+          const float4 a4 = *reinterpret_cast<const float4*>(part + (lane * 2 + 0) * 4);
+          const float4 b4 = *reinterpret_cast<const float4*>(part + (lane * 2 + 1) * 4);
+          sj = ((a4.x + a4.y) + a4.z) + a4.w; pj = ((b4.x + b4.y) + b4.z) + b4.w;
+        }
+      } else {
+        for (int w = 0; w < nw; ++w) s_c += part[2 * J * nw + w];
+        if (lane < J) {
+          for (int w = 0; w < nw; ++w) sj += part[(lane * 2 + 0) * nw + w];
+          for (int w = 0; w < nw; ++w) pj += part[(lane * 2 + 1) * nw + w];
+        }
       }
       if (stats && warp == 0) {
         float* st = stats + size_t(b) * p.stride;
@@ -736,44 +770,56 @@ rank_fused2_kernel(const float* __restrict__ H, const RankDev p, const float gsc
         if (lane < J) { st[1 + 2 * lane] = sj; st[2 + 2 * lane] = pj; }
       }
       // normalization_layer.cpp:36-59: r = pow(s, .5) + eps ; y = x / r.  scores = <c^, x^>
-      const float nc = sqrtf(s_c) + p.eps;
-      const float nj = sqrtf(sj) + p.eps;
-      const float score = pj / (nc * nj);
-      const float score_t = __shfl_sync(0xffffffffu, score, 0);
+      const float rt_c = sqrtf(s_c), rt_j = sqrtf(sj);
+      const float inv_nc = __frcp_rn(rt_c + p.eps), inv_nj = __frcp_rn(rt_j + p.eps);
+      const float inv_q = __frcp_rn(sj * rt_j + p.eps);                   // 1 / (pow(s, 1.5) + eps), normalization_layer.cpp:101-107
+      const float inv_qc = __frcp_rn(s_c * rt_c + p.eps);
+      const float u = pj * inv_nj;                                        // <cbar, x^_j>
+      const float score = u * inv_nc;
+      const float score_t = __shfl_sync(0xffffffffu, score, 0), u0 = __shfl_sync(0xffffffffu, u, 0);
       const float dlt = score_t - score;                                  // caffe_sub :69
       const float h = fmaxf(0.f, p.margin - dlt);
       const bool neg = lane >= 1 && lane < J;
       // max_margin_loss_layer.cpp:149-192: L2 g = h * (lw*2/count); L1 g = [h>0] * lw/count
       float w = neg ? ((p.norm == 2) ? h * gscale : (h > 0.f ? gscale : 0.f)) : 0.f;
-      const float vterm = (neg && dlt < 0.f) ? 1.f : 0.f;
-      const float g = warp_sum(w);
-      if (warp == 0) {                                                    // the item's loss terms: once
-        const float loss = warp_sum(neg ? ((p.norm == 2) ? h * h : fabsf(h)) : 0.f);
-        const float viol = warp_sum(vterm);
-        if (lane == 0) { if (item_loss) item_loss[b] = loss; if (item_viol) item_viol[b] = viol; }
+      // g = sum_k w_k and sum_k w_k u_k as two interleaved butterflies (one dependent chain of 5 shuffles, not two):
+      // a_c = <cbar, d c^> = sum_j (w_j / n_j) p_j with w_0 = -g  =>  a_c = sum_{k>=1} w_k u_k - g u_0
+      float g = w, s1 = w * u;
+      if (warp == 0) {                                                    // the item's loss terms ride along: once per item
+        float ls = neg ? ((p.norm == 2) ? h * h : fabsf(h)) : 0.f, vs = (neg && dlt < 0.f) ? 1.f : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          g += __shfl_xor_sync(0xffffffffu, g, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+          ls += __shfl_xor_sync(0xffffffffu, ls, o); vs += __shfl_xor_sync(0xffffffffu, vs, o);
+        }
+        if (lane == 0) { if (item_loss) item_loss[b] = ls; if (item_viol) item_viol[b] = vs; }
+      } else {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { g += __shfl_xor_sync(0xffffffffu, g, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
       }
       if (lane == 0) w = -g;                                              // d s+ = -1 * d s- (axpby, :210-212)
-      const float q = powf(sj, 1.5f) + p.eps;                             // normalization_layer.cpp:101-107
-      const float aj = w * pj / nc;
-      const float e = w / nj;
+      const float ac = s1 - g * u0;
       if (lane < J) {
-        rA = (sj * w / (nc * q)) * osc; rB = (-aj / q) * osc; rE = e;
+        const float wn = w * inv_nc;
+        rA = (sj * wn * inv_q) * osc; rB = (-(wn * pj) * inv_q) * osc; rE = w * inv_nj;
         rD = delta ? delta[size_t(lane == 0 ? 0 : Cc + lane - 1) * p.B + b] : 0.f;
       }
-      const float ac = warp_sum(lane < J ? e * pj : 0.f);                 // a_c = <cbar, d c^>
-      const float qc = powf(s_c, 1.5f) + p.eps;
-      Fs = (s_c / qc) * osc; Fc = (-ac / qc) * osc;
+      Fs = (s_c * inv_qc) * osc; Fc = (-ac * inv_qc) * osc;
     }
+    const unsigned int qmask = __ballot_sync(0xffffffffu, rD != 0.f);     // branches hit by the K-1 copy quirk (rare)
     // ---- target + negative rows: dx = (A cbar + B x) [H > 0]; D += E x
     float2 Dl = make_float2(0.f, 0.f), Dh = make_float2(0.f, 0.f);
     float2 dbl = lo2(dbacc), dbh = hi2(dbacc);
+    char* const o_hi = reinterpret_cast<char*>(OUT == 4 ? static_cast<void*>(out.bf) : static_cast<void*>(out.hi)) + size_t(e0) * kOpBytes;
+    char* const o_lo = reinterpret_cast<char*>(out.lo) + size_t(e0) * 2;  // F16X3: h1 plane; TF32X3: bf16 plane 0 (plane 1 `count` elements on)
 #pragma unroll
     for (int r = 0; r < RMAX; ++r) {
       if (r < R && (r == 0 || r >= Cc)) {
         const int j = (r == 0) ? 0 : r - Cc + 1;
         const float a = __shfl_sync(0xffffffffu, rA, j), bb = __shfl_sync(0xffffffffu, rB, j), e = __shfl_sync(0xffffffffu, rE, j);
-        const float dl = __shfl_sync(0xffffffffu, rD, j);
-        if (col_ok) {
+        const bool hit = (qmask >> j) & 1u;                               // warp-uniform
+        const float dl = hit ? __shfl_sync(0xffffffffu, rD, j) : 0.f;     // every lane takes part (not under col_ok)
+        if (FULL || col_ok) {
           const float4 xv = x[r];
           const float2 a2 = splat2(a), b2 = splat2(bb), e2 = splat2(e);
           float2 ol = __ffma2_rn(a2, cl, __fmul2_rn(b2, lo2(xv))), oh = __ffma2_rn(a2, ch, __fmul2_rn(b2, hi2(xv)));
@@ -781,12 +827,12 @@ rank_fused2_kernel(const float* __restrict__ H, const RankDev p, const float gsc
           ol = __fmul2_rn(ol, make_float2(gate1(xv.x), gate1(xv.y))); oh = __fmul2_rn(oh, make_float2(gate1(xv.z), gate1(xv.w)));
           dbl = __fadd2_rn(dbl, ol); dbh = __fadd2_rn(dbh, oh);
           const float4 o = make_float4(ol.x, ol.y, oh.x, oh.y);
-          if (dl != 0.f) {                                                // uniform; only rows hit by the K-1 copy quirk
+          if (hit) {
             dqacc.x = fmaf(dl, o.x, dqacc.x); dqacc.y = fmaf(dl, o.y, dqacc.y);
             dqacc.z = fmaf(dl, o.z, dqacc.z); dqacc.w = fmaf(dl, o.w, dqacc.w);
           }
           if (OUT == 8) amax = amax4(amax, o);
-          store_op4<OUT>(out, (size_t(r) * p.B + b) * p.N + tid * 4, o);
+          store_op4_at<OUT>(out, o_hi, o_lo, unsigned(r) * rs, o);
         }
       }
     }
@@ -794,7 +840,7 @@ rank_fused2_kernel(const float* __restrict__ H, const RankDev p, const float gsc
     const float2 dcl = __ffma2_rn(splat2(Fs), Dl, __fmul2_rn(splat2(Fc), cl)), dch = __ffma2_rn(splat2(Fs), Dh, __fmul2_rn(splat2(Fc), ch));
 #pragma unroll
     for (int r = 1; r < RMAX; ++r) {
-      if (r < Cc && col_ok) {
+      if (r < Cc && (FULL || col_ok)) {
         const float2 a2 = splat2(p.coeff[r - 1]);
         const float4 xv = x[r];
         const float2 ol = __fmul2_rn(__fmul2_rn(a2, dcl), make_float2(gate1(xv.x), gate1(xv.y)));
@@ -802,7 +848,7 @@ rank_fused2_kernel(const float* __restrict__ H, const RankDev p, const float gsc
         dbl = __fadd2_rn(dbl, ol); dbh = __fadd2_rn(dbh, oh);
         const float4 o = make_float4(ol.x, ol.y, oh.x, oh.y);
         if (OUT == 8) amax = amax4(amax, o);
-        store_op4<OUT>(out, (size_t(r) * p.B + b) * p.N + tid * 4, o);
+        store_op4_at<OUT>(out, o_hi, o_lo, unsigned(r) * rs, o);
       }
     }
     dbacc = make_float4(dbl.x, dbl.y, dbh.x, dbh.y);
@@ -1241,6 +1287,7 @@ bool vv::rank_loss_fused_v2_applies(const vv_rank_cfg_t* cfg, int prec, bool wan
   if (!on || (ring_e && atoi(ring_e) > 0)) return false;
   if (!cfg || want_dz || want_scores) return false;
   if (prec != VV_PREC_TF32X3 && prec != VV_PREC_BF16 && prec != VV_PREC_F16X3) return false;
+  if (double(cfg->B) * (cfg->C + cfg->Nn) * cfg->N >= 2147483648.0) return false;     // the kernel uses 32-bit element offsets
   return cfg->N % 4 == 0 && cfg->N <= 1024 && cfg->C + cfg->Nn <= 16 && cfg->Nn >= 1 && cfg->C >= 2;
 }
 
@@ -1293,8 +1340,14 @@ int vv::rank_loss_fused_counted(const float* H, const vv_rank_cfg_t* cfg, float 
     const float ds = act_fused ? dropout_scale : 1.f;
     VV_REQUIRE(act_fused, "rank_loss_fused: the operand-only fast kernel is the fused-activation form");
 #define VV_RANK_V2(CT, NNT, OUT)                                                                                        \
-    rank_fused2_kernel<CT, NNT, OUT><<<grid2, T, smem2, stream>>>(H, d, gscale, ds, o, db_accum, delta, dq_accum, stats,    \
-        item_loss, item_viol, ws, cnt, inv_count, loss, violations)
+    do {                                                                                                                 \
+      if (T == d.N4 && T == 128) rank_fused2_kernel<CT, NNT, OUT, true, 4><<<grid2, T, smem2, stream>>>(H, d, gscale, ds, o, db_accum,  \
+          delta, dq_accum, stats, item_loss, item_viol, ws, cnt, inv_count, loss, violations);                             \
+      else if (T == d.N4) rank_fused2_kernel<CT, NNT, OUT, true, 0><<<grid2, T, smem2, stream>>>(H, d, gscale, ds, o, db_accum, delta,  \
+          dq_accum, stats, item_loss, item_viol, ws, cnt, inv_count, loss, violations);                                    \
+      else rank_fused2_kernel<CT, NNT, OUT, false, 0><<<grid2, T, smem2, stream>>>(H, d, gscale, ds, o, db_accum, delta, dq_accum,      \
+          stats, item_loss, item_viol, ws, cnt, inv_count, loss, violations);                                              \
+    } while (0)
     if (d.C == 5 && d.Nn == 10) {
       if (mode == 8) VV_RANK_V2(5, 10, 8); else if (mode == 4) VV_RANK_V2(5, 10, 4); else VV_RANK_V2(5, 10, 2);
     } else {

@@ -205,8 +205,10 @@ def rank_loss_fused_supported(cfg):
     return bool(_lib.load().vv_rank_loss_fused_supported(C.byref(cfg)))
 
 
-def rank_loss_fused(H, cfg, loss_weight=1.0, act_fused=True, dropout_scale=1.0, prec="fp32_simt", want_db=True):
-    """K2 + K3 in one pass.  Returns (forward dict as rank_loss_forward, dZ fp32, operand copies, db)."""
+def rank_loss_fused(H, cfg, loss_weight=1.0, act_fused=True, dropout_scale=1.0, prec="fp32_simt", want_db=True, want_dz=True,
+                    want_scores=True):
+    """K2 + K3 in one pass.  Returns (forward dict as rank_loss_forward, dZ fp32, operand copies, db).
+    want_dz=False, want_scores=False: operand-only output -- the trainer's form, served by the second-generation kernel."""
     dev = H.device
     B, Nn = cfg.B, cfg.Nn
     p = _prec(prec)
@@ -217,7 +219,9 @@ def rank_loss_fused(H, cfg, loss_weight=1.0, act_fused=True, dropout_scale=1.0, 
                item_viol=torch.empty((B,), dtype=torch.float32, device=dev),
                loss=torch.empty((1,), dtype=torch.float32, device=dev),
                violations=torch.empty((1,), dtype=torch.float32, device=dev))
-    dZ = torch.empty_like(H)
+    dZ = torch.empty_like(H) if want_dz else None
+    if not want_scores:
+        out["target_score"] = out["neg_score"] = None
     op = alloc_operand(H.shape, p, dev)
     db = torch.zeros((cfg.N,), dtype=torch.float32, device=dev) if want_db else None
     for _pass in range(2 if p == PREC["f16x3"] else 1):     # f16x3: a first pass measures max|dZ| for the scale
