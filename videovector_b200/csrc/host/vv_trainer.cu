@@ -121,6 +121,7 @@ struct vv_trainer {
   bool x_allocated = false;
   ncclComm_t comm = nullptr;
   DpP2P p2p;
+  unsigned int finish_epoch = 0;       // finishing wgrad launches so far (the tickets only grow)
   int last_launches = 0;
   // optional per-phase timing
   bool timing = false;
@@ -546,7 +547,7 @@ extern "C" int vv_trainer_step(vv_trainer_t* t, const float* bank, int64_t bank_
     if (use_p2p) { if ((rc = operand_rescale_ex(t->W_hi.p, c.prec, 10, t->p2p.peers.flags[c.rank] + kDpFlagAmax, c.world_size, s))) return rc; }
     else { if ((rc = vv_operand_rescale(t->W_hi.p, c.prec, 10, s))) return rc; }
     WgradFinish f;
-    f.tickets = t->tickets.as<unsigned int>();
+    f.tickets = t->tickets.as<unsigned int>(); f.epoch = ++t->finish_epoch;
     UpdateTail& u = f.u;
     u.W = t->W.as<float>(); u.parts = t->dW_parts.as<float>(); u.nparts = t->nsplit; u.stride = NK; u.hist = t->Wh.as<float>();
     u.diff_out = t->dW_parts.as<float>(); u.count = NK; u.K = K;

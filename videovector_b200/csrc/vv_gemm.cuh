@@ -31,17 +31,19 @@ struct GemmEpilogue {
 };
 
 // Split-K finish fused into the weight-gradient kernels (north star: "the momentum update is fused into the wgrad
-// epilogue").  Every (tile, split) unit leaves its partial tile in its slab and takes a ticket of its tile's counter; the
-// CTA that takes the last ticket re-reads the S partial tiles (fresh in L2) in slab order -- a fixed order, so the result
-// does not depend on which split finished last -- and finishes the tile:
+// epilogue").  Every (tile, split) unit leaves its partial tile in its slab and counts its arrival on the tile's ticket.
+// When a CTA has run out of units its epilogue warps DRAIN: the output tiles are cut into chunks that are dealt out over
+// all CTAs; a chunk waits for the nsplit arrivals of its tile, re-reads the S partial tiles in slab order -- a fixed order,
+// so the result does not depend on which split finished last -- and finishes its elements:
 //   mode 1 (one GPU): g = sum_s slab_s (+ the K-1 quirk column); g += decay * W; h = momentum * h + rate * g; W -= h;
 //           diff = h; operand copy of W and W[:, K-1] refreshed -- the element-wise arithmetic of sgd_update_tail_kernel
-//           (ref: solver.cpp:534-568, net.cpp:837, blob.cpp:126-128); the CTA finishing the tile at feature offset 0 of an
-//           output block also updates that block of the bias.  No update launch, no second pass over the slabs.
+//           (ref: solver.cpp:534-568, net.cpp:837, blob.cpp:126-128); chunks of feature tile 0 also update their rows of
+//           the bias.  No update launch.
 //   mode 2 (data parallel): the summed rows go straight to their owner rank's receive buffer (vv_dp_exchange.cuh); the CTA
-//           finishing the LAST tile pushes (db, loss, violations) and raises dw_ready on every rank.
+//           finishing the LAST chunk pushes (db, loss, violations) and raises dw_ready on every rank.
 struct WgradFinish {
-  unsigned int* tickets = nullptr;      // one counter per output tile (+ one for the tiles finished), zero at launch; self-resetting
+  unsigned int* tickets = nullptr;      // one counter per output tile (+ one for the chunks finished); they only grow:
+  unsigned int epoch = 0;               // 1, 2, ... = number of finishing launches on these tickets including this one
   int mode = 0;
   UpdateTail u;                          // mode 1 (u.parts / u.stride / u.nparts are taken from the GEMM problem)
   // mode 2

@@ -86,78 +86,125 @@ struct Cfg {
 };
 
 
-// The split-K finish of one work unit (see WgradFinish in vv_gemm.cuh), run by the 256 epilogue threads right after they
-// stored the unit's partial tile.  m0 / nt0: the tile's row / column offset in D; et: epilogue thread 0..255.
+// ---- the split-K finish (see WgradFinish in vv_gemm.cuh), run by the 256 epilogue threads ------------------------
+// (1) after a unit's partial tile is stored: publish it and count the arrival on the tile's ticket.
 template <class C>
-__device__ __forceinline__ void wgrad_finish_unit(const TcParams& p, int m0, int nt0, int et, unsigned int* s_last) {
+__device__ __forceinline__ void wgrad_arrive_unit(const TcParams& p, int m0, int nt0, int et) {
   if (m0 >= p.d_rows || nt0 >= p.d_cols) return;                 // the phantom tile of an odd pair (CTA-uniform)
-  // publish this unit's partial tile and take a ticket of the tile
   __threadfence();
   asm volatile("bar.sync 1, 256;" ::: "memory");
-  const int tile_id = (m0 / kBlockM) * p.tiles_n + nt0 / C::block_n;
-  if (et == 0) {
-    const unsigned int prev = atomicAdd(&p.fin.tickets[tile_id], 1u);
-    const bool last = prev + 1u == unsigned(p.nsplit);
-    if (last) p.fin.tickets[tile_id] = 0u;                       // ready for the next launch
-    *s_last = last ? 1u : 0u;
-  }
-  asm volatile("bar.sync 1, 256;" ::: "memory");
-  if (*s_last == 0u) return;
-  __threadfence();
-  // the tile as a region of dW [N, K] (row pitch p.ldd = K): WGRAD_T stores D transposed
-  int n_begin, n_count, k_begin, k_count;
-  if (C::trans_out) { n_begin = nt0; n_count = min(C::block_n, p.d_cols - nt0); k_begin = m0; k_count = min(kBlockM, p.d_rows - m0); }
-  else              { n_begin = m0;  n_count = min(kBlockM, p.d_rows - m0);    k_begin = nt0; k_count = min(C::block_n, p.d_cols - nt0); }
-  const int Kdim = p.ldd, k4c = k_count >> 2, total = n_count * k4c;
+  if (et == 0) atomicAdd(&p.fin.tickets[(m0 / kBlockM) * p.tiles_n + nt0 / C::block_n], 1u);
+}
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// (2) after the CTA's last unit: the drain.  Every output tile is cut into chunks of 1024 float4 (8 per full tile), chunk c
+// goes to CTA c % gridDim.x: ALL CTAs finish tiles, whoever computed them.  A chunk waits until its tile has collected the
+// arrivals of all nsplit units (tickets only grow: target = nsplit * epoch), then every thread takes 4 float4 elements with
+// all their loads in flight together: the S partial sums in slab order (fixed order: the result does not depend on which
+// split finished last), then the update (mode 1) or the push to the owner rank (mode 2).
+// No deadlock: a CTA drains only after its own units, and arrivals never wait for anything.
+template <class C>
+__device__ __forceinline__ void wgrad_drain(const TcParams& p, int et) {
+  const int ntiles = p.tiles_m * p.tiles_n;
+  constexpr int kChunk4 = 1024, kPer = kChunk4 / 256;            // float4 per chunk / per thread
+  constexpr int kTile4 = kBlockM * C::block_n / 4;
+  constexpr int kParts = kTile4 / kChunk4;                       // 8
+  const int Kdim = p.ldd;
+  const unsigned int target = unsigned(p.nsplit) * p.fin.epoch;
   const float* col_add = p.fin.mode == 1 ? p.fin.u.col_add : p.fin.col_add;
   float* hi = static_cast<float*>(p.fin.u.Wop_hi);
   const float scale = (p.fin.mode == 1 && p.fin.u.prec == VV_PREC_F16X3 && hi) ? f16_hdr(hi)->scale : 1.f;
   const long long owned4 = (long long)p.fin.rows_per * (Kdim >> 2);
   float amax = 0.f;
-  for (int idx = et; idx < total; idx += 256) {
-    const int r = idx / k4c, c4 = idx - r * k4c;
-    const int n = n_begin + r, k = k_begin + c4 * 4;
-    const long long i = ((long long)n * Kdim + k) >> 2;                         // float4 index in [N, K]
-    float4 g = __ldcg(reinterpret_cast<const float4*>(p.D) + i);
-    if (col_add && k + 4 == Kdim) g.w += col_add[n];                            // .w is column K-1
-    for (int sp = 1; sp < p.nsplit; ++sp) {                                     // slab order: deterministic
-      const float4 t = __ldcg(reinterpret_cast<const float4*>(p.D + (long long)sp * p.slab_stride) + i);
-      g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+  for (int c = blockIdx.x; c < ntiles * kParts; c += gridDim.x) {
+    const int tile = c / kParts, part = c - tile * kParts;
+    const int m0 = (tile / p.tiles_n) * kBlockM, nt0 = (tile % p.tiles_n) * C::block_n;
+    // the tile as a region of dW [N, K] (row pitch Kdim = K): WGRAD_T stores D transposed
+    int n_begin, n_count, k_begin, k_count;
+    if (C::trans_out) { n_begin = nt0; n_count = min(C::block_n, p.d_cols - nt0); k_begin = m0; k_count = min(kBlockM, p.d_rows - m0); }
+    else              { n_begin = m0;  n_count = min(kBlockM, p.d_rows - m0);    k_begin = nt0; k_count = min(C::block_n, p.d_cols - nt0); }
+    const int k4c = k_count >> 2, total = n_count * k4c;
+    if (part * kChunk4 >= total) continue;                       // ragged tile: this part is empty (uniform)
+    if (et == 0) { while (ld_acquire_gpu(&p.fin.tickets[tile]) < target) __nanosleep(64); }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    long long ii[kPer]; int nn[kPer]; bool ok[kPer], lastc[kPer];
+    float4 g[kPer];
+#pragma unroll
+    for (int e = 0; e < kPer; ++e) {
+      const int idx = part * kChunk4 + e * 256 + et;
+      ok[e] = idx < total;
+      const int r = ok[e] ? idx / k4c : 0, c4 = ok[e] ? idx - r * k4c : 0;
+      nn[e] = n_begin + r;
+      const int k = k_begin + c4 * 4;
+      lastc[e] = (k + 4 == Kdim);
+      ii[e] = ((long long)nn[e] * Kdim + k) >> 2;                // float4 index in [N, K]
+      g[e] = ok[e] ? __ldcg(reinterpret_cast<const float4*>(p.D) + ii[e]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int e = 0; e < kPer; ++e)
+      if (ok[e] && col_add && lastc[e]) g[e].w += col_add[nn[e]];                // .w is column K-1
+    for (int sp = 1; sp < p.nsplit; sp += 2) {                                   // slab order; two slabs x 4 elements in flight
+      const bool two = sp + 1 < p.nsplit;
+      float4 t0[kPer], t1[kPer];
+#pragma unroll
+      for (int e = 0; e < kPer; ++e) {
+        t0[e] = ok[e] ? __ldcg(reinterpret_cast<const float4*>(p.D + (long long)sp * p.slab_stride) + ii[e]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        t1[e] = (ok[e] && two) ? __ldcg(reinterpret_cast<const float4*>(p.D + (long long)(sp + 1) * p.slab_stride) + ii[e]) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int e = 0; e < kPer; ++e) {
+        g[e].x += t0[e].x; g[e].y += t0[e].y; g[e].z += t0[e].z; g[e].w += t0[e].w;
+        if (two) { g[e].x += t1[e].x; g[e].y += t1[e].y; g[e].z += t1[e].z; g[e].w += t1[e].w; }
+      }
     }
     if (p.fin.mode == 1) {
-      sgd_update4(p.fin.u, i, g, scale, amax);
+#pragma unroll
+      for (int e = 0; e < kPer; ++e) if (ok[e]) sgd_update4(p.fin.u, ii[e], g[e], scale, amax);
+      if (k_begin == 0) {                                        // this block of the bias blob goes with feature tile 0
+        // the rows whose first element lies in this chunk
+        const int r_lo = (part * kChunk4 + k4c - 1) / k4c, r_hi = min(n_count, ((part + 1) * kChunk4 + k4c - 1) / k4c);
+        for (int r = r_lo + et; r < r_hi; r += 256) sgd_update_bias1(p.fin.u, n_begin + r);
+      }
     } else {
-      const int o = n / p.fin.rows_per;                                         // owner rank of row n
-      reinterpret_cast<float4*>(p.fin.peers.recv_dw[o])[(long long)p.fin.rank * owned4 + (i - (long long)o * owned4)] = g;
+#pragma unroll
+      for (int e = 0; e < kPer; ++e) {
+        if (!ok[e]) continue;
+        const int o = nn[e] / p.fin.rows_per;                                     // owner rank of row n
+        reinterpret_cast<float4*>(p.fin.peers.recv_dw[o])[(long long)p.fin.rank * owned4 + (ii[e] - (long long)o * owned4)] = g[e];
+      }
+      // count the finished chunks; the CTA finishing the last one completes this rank's push
+      __threadfence_system();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      __shared__ unsigned int s_last;
+      if (et == 0) {
+        int nchunks = 0;                                         // non-empty chunks of this launch
+        for (int t2 = 0; t2 < ntiles; ++t2) {
+          const int mm = (t2 / p.tiles_n) * kBlockM, nn0 = (t2 % p.tiles_n) * C::block_n;
+          const int tot = C::trans_out ? min(C::block_n, p.d_cols - nn0) * (min(kBlockM, p.d_rows - mm) >> 2)
+                                       : min(kBlockM, p.d_rows - mm) * (min(C::block_n, p.d_cols - nn0) >> 2);
+          nchunks += (tot + kChunk4 - 1) / kChunk4;
+        }
+        const unsigned int prev = atomicAdd(&p.fin.tickets[ntiles], 1u);
+        s_last = (prev + 1u == unsigned(nchunks) * p.fin.epoch) ? 1u : 0u;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (s_last != 0u) {
+        __threadfence();
+        for (int d = 0; d < p.fin.G; ++d)                        // (db, loss, violations) to every rank
+          for (int i = et; i < p.fin.nsmall; i += 256) p.fin.peers.recv_small[d][p.fin.rank * p.fin.small_stride + i] = p.fin.small_src[i];
+        __threadfence_system();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (et == 0) {
+          __threadfence_system();
+          for (int d = 0; d < p.fin.G; ++d) dp_st_release_sys(&p.fin.peers.flags[d][kDpFlagDwReady + p.fin.rank], p.fin.seq);
+        }
+      }
     }
   }
-  if (p.fin.mode == 1) {
-    if (p.fin.u.prec == VV_PREC_F16X3 && hi) f16_publish_absmax(hi, amax);
-    if (k_begin == 0)                                                           // this block of the bias blob goes with feature tile 0
-      for (int j = et; j < n_count; j += 256) sgd_update_bias1(p.fin.u, n_begin + j);
-    return;
-  }
-  // data parallel: count the finished tiles; the CTA finishing the last one completes this rank's push
-  __threadfence_system();
-  asm volatile("bar.sync 1, 256;" ::: "memory");
-  const int ntiles = p.tiles_m * p.tiles_n;
-  if (et == 0) {
-    const unsigned int prev = atomicAdd(&p.fin.tickets[ntiles], 1u);
-    const bool last = prev + 1u == unsigned(ntiles);
-    if (last) p.fin.tickets[ntiles] = 0u;
-    *s_last = last ? 1u : 0u;
-  }
-  asm volatile("bar.sync 1, 256;" ::: "memory");
-  if (*s_last == 0u) return;
-  __threadfence();
-  for (int d = 0; d < p.fin.G; ++d)                                             // (db, loss, violations) to every rank
-    for (int i = et; i < p.fin.nsmall; i += 256) p.fin.peers.recv_small[d][p.fin.rank * p.fin.small_stride + i] = p.fin.small_src[i];
-  __threadfence_system();
-  asm volatile("bar.sync 1, 256;" ::: "memory");
-  if (et == 0) {
-    __threadfence_system();
-    for (int d = 0; d < p.fin.G; ++d) dp_st_release_sys(&p.fin.peers.flags[d][kDpFlagDwReady + p.fin.rank], p.fin.seq);
-  }
+  if (p.fin.mode == 1 && p.fin.u.prec == VV_PREC_F16X3 && hi) f16_publish_absmax(hi, amax);
 }
 
 template <class C>
@@ -174,7 +221,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   uint64_t* tmem_full = empty_bar + C::stages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  unsigned int* fin_last = tmem_slot + 1;          // split-K finish: "this CTA took the last ticket" (epilogue warps)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -570,8 +616,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             }
           }
         }
-        if (!C::fwd_epi && p.fin.tickets)
-          wgrad_finish_unit<C>(p, m0, (t % p.tiles_n) * C::block_n, int(threadIdx.x) - 128, fin_last);
+        if (!C::fwd_epi && p.fin.tickets) wgrad_arrive_unit<C>(p, m0, (t % p.tiles_n) * C::block_n, int(threadIdx.x) - 128);
       } else {
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
@@ -614,10 +659,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         acc ^= 1; if (acc == 0) acc_phase ^= 1u;
-        if (!C::fwd_epi && p.fin.tickets)
-          wgrad_finish_unit<C>(p, m0, (t % p.tiles_n) * C::block_n, int(threadIdx.x) - 128, fin_last);
+        if (!C::fwd_epi && p.fin.tickets) wgrad_arrive_unit<C>(p, m0, (t % p.tiles_n) * C::block_n, int(threadIdx.x) - 128);
       }
     }
+    if (!C::fwd_epi && p.fin.tickets) wgrad_drain<C>(p, int(threadIdx.x) - 128);
   }
 
   tc_fence_before();

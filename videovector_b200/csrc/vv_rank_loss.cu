@@ -676,7 +676,10 @@ rank_fused2_kernel(const float* __restrict__ H, const RankDev p, const float gsc
   const int J = 1 + Nn, R = Cc + Nn;
   const int per = (2 * J + 1) * nw;                    // floats per partial-sum buffer (double buffered by item parity)
   const bool col_ok = FULL || tid < p.N4;
-  const float oscale = (OUT == 8) ? f16_hdr(out.hi)->scale : 1.f;
+  // F16X3: the operand's power-of-two scale; a header that was never set (0) measures with scale 1 (the first, measuring
+  // pass of a fresh operand: what it stores is overwritten by the pass that follows vv_operand_rescale)
+  const float hdr_scale = (OUT == 8) ? f16_hdr(out.hi)->scale : 1.f;
+  const float oscale = hdr_scale > 0.f ? hdr_scale : 1.f;
   const float osc = dscale * oscale;                   // what every stored gradient element is multiplied with
   // row r of item b starts at element (r * B + b) * N: 32-bit element offsets from per-item bases (the launcher checks
   // that the blob has fewer than 2^31 elements), one IMAD.WIDE per row instead of a 64-bit multiply chain
