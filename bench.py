@@ -433,6 +433,10 @@ def training_kernels(c, prec, out, args, pk):
                 "note": "ONE kernel: split-K sum -> rows pushed to their owner rank over NVLink -> owner adds the G contributions, "
                         "updates its N/G rows -> pushes the new operand rows to every rank; includes waiting for the slowest rank",
                 "nvlink_bytes_out": (out["world"] - 1) * (N * K // out["world"]) * (4 + opw)})
+    if phase["sgd_update"] <= 0 or p2p:
+        kern["wgrad"]["note"] = ("includes the split-K finish in the kernel's drain phase: the %d partial slabs summed in slab order, then "
+                                 "%s (no separate update launch)" % (out["nsplit"], "the rows pushed to their owner ranks over NVLink" if p2p
+                                                                      else "decay + momentum + update + operand refresh of W and the bias update"))
     if fg and phase["gather"] > 0:
         kern["gather_plan"] = {"ms": phase["gather"], "bound": "latency (index traffic only; not graded)", "frac": None}
     if phase.get("allreduce", 0) > 0:

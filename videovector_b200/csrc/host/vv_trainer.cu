@@ -114,7 +114,8 @@ struct vv_trainer {
   // activations / gradients
   DevBuf Xf, X_hi, X_lo, Zf, H, stats, item_loss, item_viol, dZf, dZ_hi, dZ_lo, dW_parts, dbx, dX;
   // gather-fused path: operand copies of the registered bank, per-step gather plan, quirk corrections
-  DevBuf bank_hi, bank_lo, rowmap, delta, wlast, dq, tickets, rank_ws;
+  DevBuf bank_hi, bank_lo, rowmap, delta, wlast, dq, tickets, rank_ws, tail_ws, tail_flags;
+  unsigned int tail_epoch = 0;
   const float* bank_reg = nullptr; int64_t bank_reg_rows = 0;
   // F16X3: the X scale is fixed from max|bank| (gathered rows are a subset), the dZ scale trails the previous step
   const float* scaled_bank = nullptr; int64_t scaled_bank_rows = 0; bool dz_scale_ready = false;
@@ -159,6 +160,8 @@ struct vv_trainer {
     if ((rc = alloc_operand(dZ_hi, dZ_lo, MN, cfg.prec))) return rc;
     if (f32op || cfg.keep_blobs) { A(dZf, MN * 4); }
     A(wlast, size_t(cfg.N) * 4);
+    // forward tail split: at most (clusters / 2) units x 2 CTAs x one 128 x 256 fp32 partial tile, + one flag per tail CTA
+    A(tail_ws, size_t(kNumSMsB200 / 2) * 128 * 256 * 4); A(tail_flags, 1024);
     A(rank_ws, rank_loss_workspace_bytes(cfg.N));       // deterministic db / dq / loss sums of the fused rank-loss kernel
     // split-K finish: one ticket counter per wgrad output tile (+ one for the tiles finished), zeroed here, self-resetting
     A(tickets, (size_t((cfg.K + 127) / 128 + 1) * size_t((cfg.N + 127) / 128 + 1) + 1) * 4);
@@ -225,7 +228,7 @@ struct vv_trainer {
     if (p2p.err_host) cudaFreeHost(p2p.err_host);
     if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
     DevBuf* all[] = {&W, &b, &Wh, &bh, &W_hi, &W_lo, &Xf, &X_hi, &X_lo, &Zf, &H, &stats, &item_loss, &item_viol,
-                     &dZf, &dZ_hi, &dZ_lo, &dW_parts, &dbx, &dX, &bank_hi, &bank_lo, &rowmap, &delta, &wlast, &dq, &tickets, &rank_ws};
+                     &dZf, &dZ_hi, &dZ_lo, &dW_parts, &dbx, &dX, &bank_hi, &bank_lo, &rowmap, &delta, &wlast, &dq, &tickets, &rank_ws, &tail_ws, &tail_flags};
     for (DevBuf* d : all) d->release();
     for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
     if (ev_grad) cudaEventDestroy(ev_grad);
@@ -471,12 +474,16 @@ extern "C" int vv_trainer_step(vv_trainer_t* t, const float* bank, int64_t bank_
     }
     t->p2p.waited = t->p2p.seq;
   }
+  // the last, partial wave of the persistent forward runs as K halves (VV_FWD_TAIL=0: whole units only)
+  static const bool want_tail = [] { const char* e = getenv("VV_FWD_TAIL"); return !(e && atoi(e) == 0); }();
+  FwdTail tail = {t->tail_ws.as<float>(), t->tail_ws.bytes, t->tail_flags.as<unsigned int>(), t->tail_flags.bytes / 4, ++t->tail_epoch};
+  const FwdTail* tailp = (want_tail && c.prec != VV_PREC_FP32_SIMT) ? &tail : nullptr;
   if (fused_gather) {
     if ((rc = ip_forward_gathered_ex(t->opBank(), bank_rows, t->rowmap.as<int32_t>(), t->delta.as<float>(), t->wlast.as<float>(),
-                                     t->opW(), t->b.as<float>(), M, N, K, c.prec, &act, nullptr, t->H.as<float>(), wait, s))) return rc;
+                                     t->opW(), t->b.as<float>(), M, N, K, c.prec, &act, nullptr, t->H.as<float>(), wait, s, tailp))) return rc;
   } else {
     if ((rc = ip_forward_ex(t->opX(), t->opW(), t->b.as<float>(), M, N, K, c.prec, &act, t->Zf.as<float>(),
-                            t->H.as<float>(), wait, s))) return rc;
+                            t->H.as<float>(), wait, s, tailp))) return rc;
   }
   t->toc(1);
   const float dscale = has_dropout ? dropout_scale(c.dropout_ratio) : 1.f;

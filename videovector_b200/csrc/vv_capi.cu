@@ -76,10 +76,11 @@ extern "C" int vv_ip_forward(vv_operand_t X, vv_operand_t W, const float* bias, 
   return vv::ip_forward_ex(X, W, bias, M, N, K, prec, act, Z, H, nullptr, stream);
 }
 int vv::ip_forward_ex(vv_operand_t X, vv_operand_t W, const float* bias, int M, int N, int K, int prec,
-                      const vv_act_t* act, float* Z, float* H, const DpWait* wait, vv_stream_t stream) {
+                      const vv_act_t* act, float* Z, float* H, const DpWait* wait, vv_stream_t stream, const FwdTail* tail) {
   VV_REQUIRE(X.hi && W.hi && H && M > 0 && N > 0 && K > 0, "ip_forward: bad arguments");
   GemmProblem g;
   if (wait) g.wait = *wait;
+  if (tail) { g.tail_ws = tail->ws; g.tail_ws_bytes = tail->ws_bytes; g.tail_flags = tail->flags; g.tail_flags_count = tail->flags_count; g.tail_epoch = tail->epoch; }
   g.kind = GEMM_FWD; g.prec = prec; g.A = X; g.B = W; g.M = M; g.N = N; g.K = K;
   g.D = H; g.slab_stride = 0; g.nsplit = 1; g.rowmap = nullptr; g.bank_rows = 0;
   int rc = fill_epilogue(act, bias, Z, &g.epi);
@@ -164,7 +165,7 @@ extern "C" int vv_ip_forward_gathered(vv_operand_t bank, int64_t bank_rows, cons
 }
 int vv::ip_forward_gathered_ex(vv_operand_t bank, int64_t bank_rows, const int32_t* rowmap, const float* delta,
                                const float* wlast, vv_operand_t W, const float* bias, int M, int N, int K, int prec,
-                               const vv_act_t* act, float* Z, float* H, const DpWait* wait, vv_stream_t stream) {
+                               const vv_act_t* act, float* Z, float* H, const DpWait* wait, vv_stream_t stream, const FwdTail* tail) {
   VV_REQUIRE(bank.hi && rowmap && W.hi && H && M > 0 && N > 0 && K > 0 && bank_rows > 0, "ip_forward_gathered: bad arguments");
   VV_REQUIRE(prec != VV_PREC_FP32_SIMT, "ip_forward_gathered needs a tensor-core precision");
   VV_REQUIRE(!delta || wlast, "ip_forward_gathered: delta needs wlast");
@@ -172,6 +173,7 @@ int vv::ip_forward_gathered_ex(vv_operand_t bank, int64_t bank_rows, const int32
   g.kind = GEMM_FWD; g.prec = prec; g.A = bank; g.B = W; g.M = M; g.N = N; g.K = K;
   g.D = H; g.slab_stride = 0; g.nsplit = 1; g.rowmap = rowmap; g.bank_rows = bank_rows;
   if (wait) g.wait = *wait;
+  if (tail) { g.tail_ws = tail->ws; g.tail_ws_bytes = tail->ws_bytes; g.tail_flags = tail->flags; g.tail_flags_count = tail->flags_count; g.tail_epoch = tail->epoch; }
   int rc = fill_epilogue(act, bias, Z, &g.epi);
   if (rc) return rc;
   if (!act) g.epi.Z = nullptr;

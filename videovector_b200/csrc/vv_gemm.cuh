@@ -71,14 +71,21 @@ struct GemmProblem {
   // lane waits for their w_ready flags right before its first W tile (flags == NULL: nothing to wait for)
   DpWait wait = {nullptr, 0, 0u, nullptr, 0ull};
   const WgradFinish* finish = nullptr;   // WGRAD / WGRAD_T: fused split-K finish (NULL: slabs are left for the caller)
+  // FWD: workspace for splitting the units of the last, partial wave of the persistent kernel in two along K (the first
+  // half's fp32 partial tile travels through it; NULL: whole units only).  tail_flags: one word per tail CTA, zero at
+  // first use; tail_epoch: 1, 2, ... per launch on these flags.
+  float* tail_ws = nullptr; size_t tail_ws_bytes = 0; unsigned int* tail_flags = nullptr; size_t tail_flags_count = 0;
+  unsigned int tail_epoch = 0;
 };
+struct FwdTail { float* ws; size_t ws_bytes; unsigned int* flags; size_t flags_count; unsigned int epoch; };
 
 // vv_ip_forward / vv_ip_forward_gathered with the data-parallel wait (wait == NULL: the C-ABI entry points)
 int ip_forward_ex(vv_operand_t X, vv_operand_t W, const float* bias, int M, int N, int K, int prec,
-                  const vv_act_t* act, float* Z, float* H, const DpWait* wait, vv_stream_t stream);
+                  const vv_act_t* act, float* Z, float* H, const DpWait* wait, vv_stream_t stream, const FwdTail* tail = nullptr);
 int ip_forward_gathered_ex(vv_operand_t bank, int64_t bank_rows, const int32_t* rowmap, const float* delta,
                            const float* wlast, vv_operand_t W, const float* bias, int M, int N, int K, int prec,
-                           const vv_act_t* act, float* Z, float* H, const DpWait* wait, vv_stream_t stream);
+                           const vv_act_t* act, float* Z, float* H, const DpWait* wait, vv_stream_t stream,
+                           const FwdTail* tail = nullptr);
 // vv_ip_wgrad / vv_ip_wgrad_gathered_part with the fused split-K finish (finish == NULL: the C-ABI entry points)
 int ip_wgrad_ex(vv_operand_t dZ, vv_operand_t X, int M, int N, int K, int prec, float regularization,
                 float* dW_parts, int nsplit, void* workspace, size_t workspace_bytes, const WgradFinish* finish, vv_stream_t stream);

@@ -42,8 +42,30 @@ struct TcParams {
   const float* inv_sa; const float* inv_sb;   // f16x3: 1/scale of the two operands (device, from their headers)
   DpWait wait;                  // data parallel: owner ranks' w_ready flags to wait for before the first B (= W) tile
   WgradFinish fin;              // wgrad: fused split-K finish (fin.tickets == NULL: off)
+  // FWD tail split: the units of the last, partial wave are cut in two along K (tail_first < 0: off).  Virtual unit
+  // tail_first + 2 i is the first K half of unit tail_first + i, tail_first + 2 i + 1 the second; the first half leaves its
+  // raw fp32 partial in tail_ws, the second adds it in front of the bias / activation epilogue.
+  int tail_first, tail_count, tail_kb;      // tail_kb: k-blocks of the first half
+  float* tail_ws; unsigned int* tail_flags; unsigned int tail_epoch;
   GemmEpilogue epi;
 };
+
+// what a (virtual) work unit is
+struct UnitInfo { int t, split, kb0, kb1, half /*0 whole, 1 first K half, 2 second*/, tail_idx; };
+__device__ __forceinline__ UnitInfo decode_unit(const TcParams& p, int u, int tiles_mn) {
+  UnitInfo ui;
+  if (p.tail_first < 0 || u < p.tail_first) {
+    ui.split = u / tiles_mn; ui.t = u - ui.split * tiles_mn;
+    ui.kb0 = ui.split * p.kb_per_split; ui.kb1 = min(ui.kb0 + p.kb_per_split, p.num_kb);
+    ui.half = 0; ui.tail_idx = 0;
+  } else {
+    const int v = u - p.tail_first;
+    ui.tail_idx = v >> 1; ui.half = 1 + (v & 1);
+    ui.split = 0; ui.t = p.tail_first + ui.tail_idx;               // the tail split exists for nsplit == 1 only
+    ui.kb0 = (ui.half == 1) ? 0 : p.tail_kb; ui.kb1 = (ui.half == 1) ? p.tail_kb : p.num_kb;
+  }
+  return ui;
+}
 
 template <bool kTF32, bool kAMN, bool kBMN, int kNProd, int kBlockN, int kStages, bool kFwdEpi, bool kGather = false,
           bool kF16 = false, bool kTransOut = false>
@@ -94,6 +116,9 @@ __device__ __forceinline__ void wgrad_arrive_unit(const TcParams& p, int m0, int
   __threadfence();
   asm volatile("bar.sync 1, 256;" ::: "memory");
   if (et == 0) atomicAdd(&p.fin.tickets[(m0 / kBlockM) * p.tiles_n + nt0 / C::block_n], 1u);
+}
+__device__ __forceinline__ void st_release_gpu(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
   unsigned int v;
@@ -247,7 +272,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   const int cta_rank = (C::cluster > 1) ? int(cluster_ctarank()) : 0;
   const int tiles_mp = (p.tiles_m + C::cluster - 1) / C::cluster;
   const int tiles_mn = tiles_mp * p.tiles_n;
-  const int total_units = tiles_mn * p.nsplit;
+  const int total_units = p.tail_first < 0 ? tiles_mn * p.nsplit : tiles_mn + p.tail_count;
   const int unit0 = blockIdx.x / C::cluster, unit_stride = gridDim.x / C::cluster;
 
   if (warp == 0) {
@@ -263,12 +288,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         asm volatile("fence.proxy.async;" ::: "memory");   // peer stores (generic proxy) -> TMA reads (async proxy)
       }
       for (int u = unit0; u < total_units; u += unit_stride) {
-        const int split = u / tiles_mn;
-        const int t = u - split * tiles_mn;
+        const UnitInfo ui = decode_unit(p, u, tiles_mn);
+        const int t = ui.t;
         const int m0 = ((t / p.tiles_n) * C::cluster + cta_rank) * kBlockM;
         const int n0 = (t % p.tiles_n) * C::block_n;
-        const int kb0 = split * p.kb_per_split;
-        const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
+        const int kb0 = ui.kb0, kb1 = ui.kb1;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           mbar_arrive_expect_tx(&full_bar[stage], kTmaBytes);
@@ -385,9 +409,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int u = unit0; u < total_units; u += unit_stride) {
-        const int split = u / tiles_mn;
-        const int kb0 = split * p.kb_per_split;
-        const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
+        const UnitInfo ui = decode_unit(p, u, tiles_mn);
+        const int kb0 = ui.kb0, kb1 = ui.kb1;
         // The k-range is issued in chunks of p.chunk_kb k-blocks, each into its own TMEM buffer
         // (accumulate = 0 at the chunk start): the epilogue warps sum the chunks in fp32 registers.
         // Non-promoting configurations use one chunk per unit.
@@ -464,11 +487,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     const long long h1d = il ? 64 : (kPlanes == 2 ? (long long)(p.ga1 - p.ga0) : 0);
     int stage = 0; uint32_t phase = 0;
     for (int u = unit0; u < total_units; u += unit_stride) {
-      const int split = u / tiles_mn;
-      const int t = u - split * tiles_mn;
+      const UnitInfo ui = decode_unit(p, u, tiles_mn);
+      const int t = ui.t;
       const int m0 = ((t / p.tiles_n) * C::cluster + cta_rank) * kBlockM;
-      const int kb0 = split * p.kb_per_split;
-      const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
+      const int kb0 = ui.kb0, kb1 = ui.kb1;
       if (!C::a_mn) {
         // FWD: A tile = [128 X rows x 128 B of K]; this lane's 16 rows are fixed for the whole unit
         long long rowoff[16];
@@ -537,12 +559,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     constexpr int kColsPerWarp = C::block_n / 2;
     int acc = 0; uint32_t acc_phase = 0;
     for (int u = unit0; u < total_units; u += unit_stride) {
-      const int split = u / tiles_mn;
-      const int t = u - split * tiles_mn;
+      const UnitInfo ui = decode_unit(p, u, tiles_mn);
+      const int split = ui.split, t = ui.t;
       const int m0 = ((t / p.tiles_n) * C::cluster + cta_rank) * kBlockM;
       const int n0 = (t % p.tiles_n) * C::block_n + half * kColsPerWarp;
-      const int kb0 = split * p.kb_per_split;
-      const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
+      const int kb0 = ui.kb0, kb1 = ui.kb1;
+      // FWD tail split: this thread's slice of the partial tile in the workspace is float4 j of thread et at [j * 256 + et]
+      // (the pointers are formed where they are used: the promoting epilogue has no registers to spare)
+#define VV_TAIL_ET (int(threadIdx.x) - 128)
+#define VV_TAIL_PART (reinterpret_cast<float4*>(p.tail_ws) + (size_t(ui.tail_idx) * C::cluster + cta_rank) * (kBlockM * C::block_n / 4) + VV_TAIL_ET)
+#define VV_TAIL_FLAG (p.tail_flags + ui.tail_idx * C::cluster + cta_rank)
       const int row = m0 + q * 32 + lane;
       const bool row_ok = row < p.d_rows;
       float* drow = p.D + (long long)split * p.slab_stride + (long long)row * p.ldd;
@@ -568,6 +594,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           __syncwarp();
           if (lane == 0) mbar_arrive(&tmem_empty[acc]);
           acc ^= 1; if (acc == 0) acc_phase ^= 1u;
+        }
+        if (C::fwd_epi && ui.half == 1) {
+          // first K half of a tail unit: the raw partial sums go to the workspace, the second half finishes the tile
+#pragma unroll
+          for (int j = 0; j < kColsPerWarp / 4; ++j)
+            VV_TAIL_PART[j * 256] = make_float4(accr[4 * j], accr[4 * j + 1], accr[4 * j + 2], accr[4 * j + 3]);
+          __threadfence();
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (VV_TAIL_ET == 0) st_release_gpu(VV_TAIL_FLAG, p.tail_epoch);
+          continue;
+        }
+        if (C::fwd_epi && ui.half == 2) {
+          if (VV_TAIL_ET == 0) { while (ld_acquire_gpu(VV_TAIL_FLAG) < p.tail_epoch) __nanosleep(32); }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < kColsPerWarp / 4; ++j) {               // first half + second half, in that order
+            const float4 pv = __ldcg(VV_TAIL_PART + j * 256);
+            accr[4 * j] = pv.x + accr[4 * j]; accr[4 * j + 1] = pv.y + accr[4 * j + 1];
+            accr[4 * j + 2] = pv.z + accr[4 * j + 2]; accr[4 * j + 3] = pv.w + accr[4 * j + 3];
+          }
         }
         // f16x3: undo the operands' power-of-two scales (exact)
         const float unscale = C::split16 ? __ldg(p.inv_sa) * __ldg(p.inv_sb) : 1.f;
@@ -618,6 +664,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         }
         if (!C::fwd_epi && p.fin.tickets) wgrad_arrive_unit<C>(p, m0, (t % p.tiles_n) * C::block_n, int(threadIdx.x) - 128);
       } else {
+        if (C::fwd_epi && ui.half == 2) {                              // second K half of a tail unit: the first half's partial
+          if (VV_TAIL_ET == 0) { while (ld_acquire_gpu(VV_TAIL_FLAG) < p.tail_epoch) __nanosleep(32); }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * C::block_n + half * kColsPerWarp);
@@ -627,6 +677,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           tmem_ld_32x32(taddr + c * 32, r);
           tmem_ld_wait();
           const int col0 = n0 + c * 32;
+          if (C::fwd_epi && ui.half == 1) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              VV_TAIL_PART[(c * 8 + j) * 256] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                                         __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+            continue;
+          }
+          if (C::fwd_epi && ui.half == 2) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 pv = __ldcg(VV_TAIL_PART + (c * 8 + j) * 256);
+              r[4 * j] = __float_as_uint(pv.x + __uint_as_float(r[4 * j])); r[4 * j + 1] = __float_as_uint(pv.y + __uint_as_float(r[4 * j + 1]));
+              r[4 * j + 2] = __float_as_uint(pv.z + __uint_as_float(r[4 * j + 2])); r[4 * j + 3] = __float_as_uint(pv.w + __uint_as_float(r[4 * j + 3]));
+            }
+          }
           if (row_ok) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -659,10 +724,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         acc ^= 1; if (acc == 0) acc_phase ^= 1u;
+        if (C::fwd_epi && ui.half == 1) {
+          __threadfence();
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (VV_TAIL_ET == 0) st_release_gpu(VV_TAIL_FLAG, p.tail_epoch);
+        }
         if (!C::fwd_epi && p.fin.tickets) wgrad_arrive_unit<C>(p, m0, (t % p.tiles_n) * C::block_n, int(threadIdx.x) - 128);
       }
     }
     if (!C::fwd_epi && p.fin.tickets) wgrad_drain<C>(p, int(threadIdx.x) - 128);
+#undef VV_TAIL_ET
+#undef VV_TAIL_PART
+#undef VV_TAIL_FLAG
   }
 
   tc_fence_before();
@@ -799,6 +872,21 @@ int launch_cfg(const GemmProblem& g, cudaStream_t stream) {
   p.D = g.D + (C::trans_out ? (long long)n0 * g.K : 0); p.slab_stride = g.slab_stride;
   p.act_N = g.N;
   p.wait = g.wait;
+  // FWD tail split (see TcParams): only with a workspace, one K range per unit, and when the last wave is at most half full
+  p.tail_first = -1; p.tail_count = 0; p.tail_kb = 0; p.tail_ws = nullptr; p.tail_flags = nullptr; p.tail_epoch = 0;
+  if (g.kind == GEMM_FWD && g.tail_ws && nsplit == 1) {
+    const int units = ((p.tiles_m + C::cluster - 1) / C::cluster) * p.tiles_n;
+    const int ncl = num_sms() / C::cluster;
+    const int rem = units % ncl;
+    // whole promotion chunks in the first half (the non-promoting kernels accumulate a unit's whole K range in TMEM)
+    const int half_kb = C::promote ? ((p.num_kb / 2 + p.chunk_kb - 1) / p.chunk_kb) * p.chunk_kb : p.num_kb / 2;
+    const size_t need = size_t(rem) * C::cluster * kBlockM * C::block_n * sizeof(float);
+    if (units > ncl && rem > 0 && 2 * rem <= ncl && half_kb > 0 && half_kb < p.num_kb && need <= g.tail_ws_bytes &&
+        size_t(rem) * C::cluster <= g.tail_flags_count) {
+      p.tail_first = units - rem; p.tail_count = rem; p.tail_kb = half_kb;
+      p.tail_ws = g.tail_ws; p.tail_flags = g.tail_flags; p.tail_epoch = g.tail_epoch;
+    }
+  }
   p.fin = WgradFinish();
   if (g.finish && g.finish->tickets) {
     if (g.kind != GEMM_WGRAD && g.kind != GEMM_WGRAD_T) { set_error("the split-K finish belongs to the weight-gradient kernels"); return VV_ERR_INVALID; }
@@ -815,7 +903,7 @@ int launch_cfg(const GemmProblem& g, cudaStream_t stream) {
     VV_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::smem_bytes));
     attr_set = true;
   }
-  const int total = ((p.tiles_m + C::cluster - 1) / C::cluster) * p.tiles_n * p.nsplit;     // units (per cluster)
+  const int total = ((p.tiles_m + C::cluster - 1) / C::cluster) * p.tiles_n * p.nsplit + p.tail_count;     // (virtual) units per cluster
   int nclusters = num_sms() / C::cluster;
   if (total < nclusters) nclusters = total;
   cudaLaunchConfig_t lc = {};
