@@ -216,7 +216,7 @@ def sampler_streams(args, world):
     if args.sampler_streams > 0:
         return args.sampler_streams
     per_rank = max(1, host_cores() // max(world, 1))
-    return max(1, min(4, per_rank // 2))
+    return max(1, min(4, per_rank - 1))          # one core stays with the rank's main thread
 
 
 def workload_config(args, world, c=None, prec=None, name="BASELINE configs[1] per GPU", streams=None):
@@ -339,6 +339,15 @@ def run_training(c, prec, args, steps, warmup, world, rank, stream, pk, want_e2e
         out["phase"], _ = tr.phase_ms()
         tr.set_timing(False)
         out["nsplit"] = tr._lib.vv_ip_wgrad_auto_nsplit(R * B, N, K, ops.PREC[prec])
+        # how evenly the ranks run: every rank's own compute per step (everything before the exchange).  In a synchronous
+        # step the exchange ends when the slowest rank arrives, so the spread shows up as waiting inside the exchange kernel
+        comp = sum(out["phase"][k] for k in ("gather", "fc7_forward", "rank_loss_forward", "rank_loss_backward", "wgrad"))
+        if world > 1:
+            allc = [torch.zeros(1, device="cuda", dtype=torch.float64) for _ in range(world)]
+            dist.all_gather(allc, torch.tensor([comp], device="cuda", dtype=torch.float64))
+            out["rank_compute_ms"] = [float(x.item()) for x in allc]
+        else:
+            out["rank_compute_ms"] = [comp]
 
         # ---- leg 3: `e2e` -- the public API with HOST buffers: sampler (prefetch threads, as the reference's
         # prefetching data layer) -> pinned host indices -> H2D -> step -> D2H loss, all inside the timed region
@@ -586,6 +595,11 @@ def run_gpu(args):
                             "of one full-rate 16-bit MMA); tensor_pipe_frac = frac x units is the pipe's utilisation"}
         cfgd = workload_config(args, world, streams=out["streams"])
         cfgd["dp_mode"] = out["dp_mode"]
+        rc = out["rank_compute_ms"]
+        skew = {"compute_ms_per_rank": [round(x, 4) for x in rc], "slowest_minus_fastest_ms": max(rc) - min(rc),
+                "slowest_over_rank0": max(rc) / rc[0] if rc[0] > 0 else None,
+                "note": "per-rank device time of gather plan + forward + rank loss + wgrad (in-step CUDA events): a synchronous "
+                        "step runs at the pace of the slowest rank (per-GPU power capping), the others wait inside the exchange"}
         line = {
             "metric": METRIC, "value": value, "unit": "triplets/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -598,7 +612,7 @@ def run_gpu(args):
                             "D2H loss; the feature bank is resident in HBM (uploaded once, like opening the LMDB); the clock stops "
                             "only when the sampler is as far ahead as it was when the clock started"},
             "roofline": roofline, "kernels": kern, "loss": out["loss"],
-            "hinge_terms_per_s": value * Nn,
+            "hinge_terms_per_s": value * Nn, "rank_skew": skew,
         }
 
     # ---- the other BASELINE configurations, same run (each with value, ms_per_step, roofline.frac, e2e)

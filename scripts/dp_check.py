@@ -64,8 +64,13 @@ mode = tr.dp_mode
 ref = make(1, 0, B * world) if rank == 0 else None
 smp = ops.Sampler(vid, off, sid, B * world, C, Nn, 500, 50, 6, 100, rand_seed=1)     # global stream, same on every rank
 mrng = np.random.RandomState(3)
-worst = 0.0
-for it in range(steps):
+worst = 0.0          # strict bound (1e-5 for the fp32-parity modes): every step that starts from identical state
+drift = 0.0          # free-running steps: the runs may part at ReLU gates (see below)
+
+
+def one_step(it, strict):
+    """One update step on the G ranks and on the 1-rank reference (global batch), compared on rank 0."""
+    global worst, drift
     gidx, gq = smp.next()
     gmask = (mrng.uniform(0, 1, (R, B * world, N)) > 0.5).astype(np.int32)
     idx, quirk = dp.shard_batch(gidx, gq, rank, world)
@@ -79,9 +84,40 @@ for it in range(steps):
         eW, eH, eb = rel("W"), rel("W_hist"), rel("b")
         eL = abs(tr.tensor("loss").item() - ref.tensor("loss").item())
         eV = abs(tr.tensor("violations").item() - ref.tensor("violations").item())
-        worst = max(worst, eW, eH, eb, eL, 1.0 if eV != 0 else 0.0)
-        print("iter %d: relerr W %.2e hist %.2e b %.2e loss %.2e viol %g" % (it, eW, eH, eb, eL, eV))
+        if strict:
+            worst = max(worst, eW, eH, eb, eL, 1.0 if eV != 0 else 0.0)
+        else:
+            drift = max(drift, eW, eL)
+        print("iter %d (%s): relerr W %.2e hist %.2e b %.2e loss %.2e viol %g" % (it, "strict" if strict else "free", eW, eH, eb, eL, eV))
+
+
+def resync():
+    """Every rank (and nothing else changes) restarts from the reference's exact state: W, b and both histories."""
+    bufs = [torch.empty((N, K), device="cuda"), torch.empty(N, device="cuda"), torch.empty((N, K), device="cuda"), torch.empty(N, device="cuda")]
+    if rank == 0:
+        for t_, name in zip(bufs, ("W", "b", "W_hist", "b_hist")):
+            t_.copy_(ref.tensor(name))
+    for t_ in bufs:
+        dist.broadcast(t_, 0)
+    tr.tensor("W_hist").copy_(bufs[2]); tr.tensor("b_hist").copy_(bufs[3])
+    tr.set_weights(bufs[0], bufs[1])
+    torch.cuda.synchronize()
+    dist.barrier()
+
+
+# (a) step 0 starts from identical state on both sides: strict.  (b) free-running steps: once the weights differ in the
+# last bit, a pre-activation within rounding of zero may take the other side of its ReLU gate (with 15*B*G*N of them per
+# step that happens every few steps; it changes a gradient row by its whole magnitude, ~1e-3 of max|dW|) -- the loss stays
+# within 1e-5, the weights within 2e-3.  (c) strict again: every step restarts from the reference's exact state.
+one_step(0, True)
+for it in range(1, steps):
+    one_step(it, False)
+for it in range(steps, steps + 3):
+    resync()
+    one_step(it, True)
+steps += 3
 # one forward/backward-only step (the NCCL path in both modes): loss is the mean over ranks, gradients all-reduced
+resync()
 gidx, gq = smp.next()
 gmask = (mrng.uniform(0, 1, (R, B * world, N)) > 0.5).astype(np.int32)
 idx, quirk = dp.shard_batch(gidx, gq, rank, world)
@@ -110,9 +146,9 @@ torch.cuda.synchronize()
 masks_differ = not same_everywhere((th.tensor("H") != 0).to(torch.int32))
 if rank == 0:
     tol = 1e-5 if prec in ("tf32x3", "f16x3", "fp32_simt") else 5e-2
-    ok = worst < tol and same and masks_differ
-    print("DP_CHECK %s world=%d prec=%s mode=%s%s fused_gather=%s worst=%.2e replicas_identical=%s hash_masks_differ=%s" % (
-        "OK" if ok else "FAIL", world, prec, mode, (" (" + tr.dp_mode_reason + ")") if tr.dp_mode_reason else "", fused, worst, same,
+    ok = worst < tol and drift < max(2e-3, tol) and same and masks_differ
+    print("DP_CHECK %s world=%d prec=%s mode=%s%s fused_gather=%s worst=%.2e free_running_drift=%.2e replicas_identical=%s hash_masks_differ=%s" % (
+        "OK" if ok else "FAIL", world, prec, mode, (" (" + tr.dp_mode_reason + ")") if tr.dp_mode_reason else "", fused, worst, drift, same,
         masks_differ))
 dist.barrier()
 th.close(); tr.close()

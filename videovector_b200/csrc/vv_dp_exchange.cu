@@ -20,6 +20,7 @@ dp_exchange_update_kernel(const DpExchange x, const DpRun run) {
   const long long owned4 = (long long)x.rows_per * k4;
   unsigned int* myflags = x.peers.flags[x.rank];
   const long long gstride = (long long)gridDim.x * T;
+  __shared__ unsigned int s_last, s_bits;
 
   // ---------------- phase A: local split-K sum -> push every row to its owner
   // (x.nparts == 0: the wgrad kernel's split-K finish already pushed the rows and raised dw_ready, vv_gemm.cuh)
@@ -44,12 +45,12 @@ dp_exchange_update_kernel(const DpExchange x, const DpRun run) {
     if (tid == 0) {
       __threadfence_system();
       const unsigned int prev = atomicAdd(&myflags[kDpFlagCtr], 1u);
-      if (prev + 1u == gridDim.x) {                         // every CTA of this rank has pushed: tell the owners
-        myflags[kDpFlagCtr] = 0u;                           // (self-resetting: the next launch starts from zero)
-        __threadfence_system();
-        for (int d = 0; d < x.G; ++d) dp_st_release_sys(&x.peers.flags[d][kDpFlagDwReady + x.rank], x.seq);
-      }
+      s_last = (prev + 1u == gridDim.x) ? 1u : 0u;          // every CTA of this rank has pushed: tell the owners
+      if (s_last) myflags[kDpFlagCtr] = 0u;                 // (self-resetting: the next launch starts from zero)
     }
+    __syncthreads();
+    // one thread per destination: the G release stores (each a system-scope fence + a store over NVLink) run side by side
+    if (s_last != 0u && tid < x.G) { __threadfence_system(); dp_st_release_sys(&x.peers.flags[tid][kDpFlagDwReady + x.rank], x.seq); }
   }
   // ---------------- phase B: wait for all G contributions, update the owned rows, push them to every rank
   if (tid < x.G) dp_spin_wait_flag(&myflags[kDpFlagDwReady + tid], x.seq, run.timeout_ns, run.err, 1u);
@@ -133,16 +134,14 @@ dp_exchange_update_kernel(const DpExchange x, const DpRun run) {
   if (tid == 0) {
     __threadfence_system();
     const unsigned int prev = atomicAdd(&myflags[kDpFlagCtr + 1], 1u);
-    if (prev + 1u == gridDim.x) {                         // the owned rows are in flight to every rank
-      myflags[kDpFlagCtr + 1] = 0u;
-      __threadfence_system();
-      if (x.prec == VV_PREC_F16X3) {
-        const unsigned int bits = atomicExch(&myflags[kDpFlagCtr + 2], 0u);
-        for (int d = 0; d < x.G; ++d) *reinterpret_cast<volatile unsigned int*>(&x.peers.flags[d][kDpFlagAmax + x.rank]) = bits;
-        __threadfence_system();
-      }
-      for (int d = 0; d < x.G; ++d) dp_st_release_sys(&x.peers.flags[d][kDpFlagWReady + x.rank], x.seq);
-    }
+    s_last = (prev + 1u == gridDim.x) ? 1u : 0u;          // the owned rows are in flight to every rank
+    if (s_last) { myflags[kDpFlagCtr + 1] = 0u; s_bits = atomicExch(&myflags[kDpFlagCtr + 2], 0u); }
+  }
+  __syncthreads();
+  if (s_last != 0u && tid < x.G) {                        // one thread per destination rank, side by side
+    __threadfence_system();
+    if (x.prec == VV_PREC_F16X3) *reinterpret_cast<volatile unsigned int*>(&x.peers.flags[tid][kDpFlagAmax + x.rank]) = s_bits;
+    dp_st_release_sys(&x.peers.flags[tid][kDpFlagWReady + x.rank], x.seq);      // release: ordered after the amax word
   }
 }
 

@@ -222,10 +222,8 @@ __device__ __forceinline__ void wgrad_drain(const TcParams& p, int et) {
           for (int i = et; i < p.fin.nsmall; i += 256) p.fin.peers.recv_small[d][p.fin.rank * p.fin.small_stride + i] = p.fin.small_src[i];
         __threadfence_system();
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (et == 0) {
-          __threadfence_system();
-          for (int d = 0; d < p.fin.G; ++d) dp_st_release_sys(&p.fin.peers.flags[d][kDpFlagDwReady + p.fin.rank], p.fin.seq);
-        }
+        // one thread per destination rank: the G release stores (system fence + store over NVLink each) run side by side
+        if (et < p.fin.G) { __threadfence_system(); dp_st_release_sys(&p.fin.peers.flags[et][kDpFlagDwReady + p.fin.rank], p.fin.seq); }
       }
     }
   }
