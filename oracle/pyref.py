@@ -23,6 +23,24 @@ def lib():
     return _lib
 
 
+DROPIN_SO = os.path.join(_HERE, "_ref", "libvv_dropin.so")
+_dropin = None
+
+
+def dropin_available():
+    return os.path.exists(DROPIN_SO)
+
+
+def dropin_lib():
+    """oracle/_ref/libvv_dropin.so: the same reference sources compiled in Caffe GPU mode, their device side (the layers'
+    Forward_gpu / Backward_gpu, caffe_gpu_*) supplied by oracle/ref_shim/dropin_gpu.cpp = calls into libvv_b200.so's C-ABI.
+    Same C entry points as libvv_ref.so; ref_solver_create runs the reference's Net / SGDSolver in GPU mode."""
+    global _dropin
+    if _dropin is None:
+        _dropin = C.CDLL(DROPIN_SO)
+    return _dropin
+
+
 def _p(a):
     return C.c_void_p(a.ctypes.data) if a is not None else None
 
@@ -161,10 +179,10 @@ class Solver:
     def __init__(self, video_id, shot_off, shot_ids, feat, W0, b0, batch_size, context_size=5, num_negative_samples=10,
                  max_buffer_size=5000, negative_swap_percentage=50, max_same_video_negs=6, context_type=1, margin=2.0,
                  norm=2, base_lr=0.001, momentum=0.9, weight_decay=0.0005, lr_policy="inv", gamma=0.001, power=0.75,
-                 stepsize=1, seed=1, dropout_ratio=0.0, test=None, reg_type=2):
+                 stepsize=1, seed=1, dropout_ratio=0.0, test=None, reg_type=2, library=None):
         """test = dict(data=[n, frames, K], video_id=[n], batch=.., id_to_class_file=path, exclude_same=True): adds the shipped
         file's TEST-phase graph (TestVideoShotWindows records on a second fake LMDB); see test()."""
-        L = lib()
+        L = self._L = library if library is not None else lib()      # library=dropin_lib(): the GPU-mode build
         L.ref_solver_create.restype = C.c_void_p
         L.ref_solver_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.ref_solver_get.argtypes = [C.c_void_p] + [C.c_void_p] * 5
@@ -200,32 +218,32 @@ class Solver:
 
     def step(self):
         loss, viol = C.c_float(0), C.c_float(0)
-        assert lib().ref_solver_step(self._h, C.addressof(loss), C.addressof(viol)) == 0
+        assert self._L.ref_solver_step(self._h, C.addressof(loss), C.addressof(viol)) == 0
         return loss.value, viol.value
 
     def state(self, want_data=False):
         W = np.empty((self.N, self.K), np.float32); b = np.empty(self.N, np.float32)
         hW = np.empty_like(W); hb = np.empty_like(b)
         data = np.empty((self.B, self.R, self.K), np.float32) if want_data else None
-        assert lib().ref_solver_get(self._h, _p(W), _p(b), _p(hW), _p(hb), _p(data)) == 0
+        assert self._L.ref_solver_get(self._h, _p(W), _p(b), _p(hW), _p(hb), _p(data)) == 0
         return dict(W=W, b=b, hW=hW, hb=hb, data=data)
 
     def layer_names(self):
-        return [lib().ref_solver_layer_name(self._h, i).decode() for i in range(lib().ref_solver_num_layers(self._h))]
+        return [self._L.ref_solver_layer_name(self._h, i).decode() for i in range(self._L.ref_solver_num_layers(self._h))]
 
     def test(self, iters):
         """Solver::Test's loop on the TEST net (weights shared with the TRAIN net): mean (mAP, hit@1, hit@5) over iters."""
         out = np.zeros(3, np.float32)
-        assert lib().ref_solver_test(self._h, iters, _p(out)) == 0
+        assert self._L.ref_solver_test(self._h, iters, _p(out)) == 0
         return out
 
     def test_output_names(self):
         """in the order the reference's Net reports its outputs (Net::Init's std::set of blob names: lexicographic)"""
-        return [lib().ref_solver_test_output_name(self._h, j).decode() for j in range(3)]
+        return [self._L.ref_solver_test_output_name(self._h, j).decode() for j in range(3)]
 
     def test_layer_names(self):
-        return [lib().ref_solver_test_layer_name(self._h, i).decode() for i in range(lib().ref_solver_test_num_layers(self._h))]
+        return [self._L.ref_solver_test_layer_name(self._h, i).decode() for i in range(self._L.ref_solver_test_num_layers(self._h))]
 
     def close(self):
         if self._h:
-            lib().ref_solver_destroy(self._h); self._h = None
+            self._L.ref_solver_destroy(self._h); self._h = None

@@ -50,3 +50,32 @@ g++ $CXXFLAGS -c "$HERE/ref_driver.cpp" -o "$OUT/obj/ref_driver.o"
 # link the SciPy wheel's OpenBLAS in place (same image, hence same path, on the GPU box)
 g++ -shared -o "$OUT/libvv_ref.so" $OBJS "$OUT/obj/ref_driver.o" "$BLAS" -Wl,-Bsymbolic -Wl,-rpath,"$(dirname "$BLAS")" -lpthread
 echo "built $OUT/libvv_ref.so"
+
+# ---- the drop-in proof: the same reference sources in GPU mode (no CPU_ONLY), their device side supplied by
+# dropin_gpu.cpp = calls into the product's C-ABI.  Needs the product library (make all) and the CUDA headers.
+VVLIB="$ROOT/videovector_b200/lib/libvv_b200.so"
+CUDA="${CUDA_HOME:-/usr/local/cuda}"
+if [ -f "$VVLIB" ] && [ -f "$CUDA/include/cuda_runtime_api.h" ]; then
+  mkdir -p "$OUT/obj_gpu"
+  GPUFLAGS="${CXXFLAGS/-DCPU_ONLY/} -DVV_DROPIN_GPU -I$CUDA/include -I$ROOT/include"
+  GOBJS=""
+  pids=""
+  for s in $SRCS; do
+    o="$OUT/obj_gpu/$(basename $s).o"
+    if [ ! -f "$o" ] || [ "$REF/src/caffe/$s.cpp" -nt "$o" ] || [ "$NEWEST_HDR" -nt "$o" ]; then
+      g++ $GPUFLAGS -c "$REF/src/caffe/$s.cpp" -o "$o" &
+      pids="$pids $!"
+      while [ "$(jobs -rp | wc -l)" -ge "$JOBS" ]; do sleep 0.2; done
+    fi
+    GOBJS="$GOBJS $o"
+  done
+  for p in $pids; do wait "$p"; done
+  g++ $GPUFLAGS -c "$HERE/ref_driver.cpp" -o "$OUT/obj_gpu/ref_driver.o"
+  g++ $GPUFLAGS -c "$HERE/dropin_gpu.cpp" -o "$OUT/obj_gpu/dropin_gpu.o"
+  g++ -shared -o "$OUT/libvv_dropin.so" $GOBJS "$OUT/obj_gpu/ref_driver.o" "$OUT/obj_gpu/dropin_gpu.o" "$BLAS" "$VVLIB" \
+      -L"$CUDA/lib64" -lcudart -Wl,-Bsymbolic -Wl,--no-undefined \
+      -Wl,-rpath,"$(dirname "$BLAS")" -Wl,-rpath,'$ORIGIN/../../videovector_b200/lib' -Wl,-rpath,"$CUDA/lib64" -lpthread
+  echo "built $OUT/libvv_dropin.so"
+else
+  echo "product library or CUDA headers absent: skipping the drop-in build"
+fi

@@ -493,7 +493,11 @@ REF_API void* ref_solver_create(int V, int K, const int* video_id, const int* sh
                                 int n_test, int frames, const float* test_data /*[n_test, frames, K]*/, const int* test_video_id,
                                 int test_batch, const char* id_to_class_file, int exclude_same_video_shots, int reg_type) {
   try {
+#ifdef VV_DROPIN_GPU      // the drop-in build (dropin_gpu.cpp): the same solver in Caffe GPU mode, device bodies = the C-ABI
+    Caffe::set_mode(Caffe::GPU);
+#else
     Caffe::set_mode(Caffe::CPU);
+#endif
     Caffe::set_phase(Caffe::TRAIN);
     RefSolver* s = new RefSolver();
     for (int v = 0; v < V; ++v) {
