@@ -231,6 +231,20 @@ class Solver:
     def layer_names(self):
         return [self._L.ref_solver_layer_name(self._h, i).decode() for i in range(self._L.ref_solver_num_layers(self._h))]
 
+    def blob_names(self):
+        self._L.ref_solver_blob_name.restype = C.c_char_p; self._L.ref_solver_blob_name.argtypes = [C.c_void_p, C.c_int]
+        self._L.ref_solver_num_blobs.argtypes = [C.c_void_p]
+        return [self._L.ref_solver_blob_name(self._h, i).decode() for i in range(self._L.ref_solver_num_blobs(self._h))]
+
+    def blob(self, name, diff=False):
+        """A blob of the TRAIN net as the host sees it after the last step (data or diff)."""
+        self._L.ref_solver_blob.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p, C.c_int]
+        n = self._L.ref_solver_blob(self._h, name.encode(), int(diff), None, 0)
+        assert n >= 0, name
+        out = np.empty(n, np.float32)
+        assert self._L.ref_solver_blob(self._h, name.encode(), int(diff), _p(out), n) == n
+        return out
+
     def test(self, iters):
         """Solver::Test's loop on the TEST net (weights shared with the TRAIN net): mean (mAP, hit@1, hit@5) over iters."""
         out = np.zeros(3, np.float32)

@@ -655,6 +655,19 @@ REF_API int ref_solver_get(void* h, float* W, float* b, float* hW, float* hb, fl
     return 0;
   } catch (const std::exception& e) { fprintf(stderr, "ref_driver: %s\n", e.what()); return -1; }
 }
+// any blob of the TRAIN net by name (data, or diff with diff != 0), as the host sees it; returns its count (or < 0)
+REF_API int ref_solver_blob(void* h, const char* name, int diff, float* out, int cap) {
+  try {
+    RefSolver* s = static_cast<RefSolver*>(h);
+    if (!s->solver->net()->has_blob(name)) return -2;
+    const shared_ptr<Blob<float> > b = s->solver->net()->blob_by_name(name);
+    const int n = b->count();
+    if (out && cap >= n) memcpy(out, diff ? b->cpu_diff() : b->cpu_data(), sizeof(float) * n);
+    return n;
+  } catch (const std::exception& e) { fprintf(stderr, "ref_driver: %s\n", e.what()); return -1; }
+}
+REF_API int ref_solver_num_blobs(void* h) { return int(static_cast<RefSolver*>(h)->solver->net()->blob_names().size()); }
+REF_API const char* ref_solver_blob_name(void* h, int i) { return static_cast<RefSolver*>(h)->solver->net()->blob_names()[i].c_str(); }
 // Solver::Test's loop (solver.cpp:252-317) on test net 0: weights shared with the train net, `iters` forward passes,
 // mean of the three outputs (test_map, test_hit_at_1, test_hit_at_5)
 REF_API int ref_solver_test(void* h, int iters, float* out3) {
