@@ -78,6 +78,15 @@ __attribute__((visibility("hidden"))) curandStatus_t curandSetPseudoRandomGenera
 __attribute__((visibility("hidden"))) curandStatus_t curandSetGeneratorOffset(curandGenerator_t, unsigned long long) { return CURAND_STATUS_SUCCESS; }
 }
 
+// ---- the data layer's rand() / srand() / std::random_shuffle stream, private to this library.  libc's generator is
+// process-global state, and in a GPU process other libraries draw from it too (the sampled rows then differ from run to
+// run); the product's bit-exact glibc generator (vv_glibc_rand_*, tested equal to libc's) serves this library's calls.
+extern "C" {
+static vv_glibc_rand_t* g_rand = nullptr;
+__attribute__((visibility("hidden"))) int rand(void) { if (!g_rand) g_rand = vv_glibc_rand_create(1u); return vv_glibc_rand_next(g_rand); }
+__attribute__((visibility("hidden"))) void srand(unsigned int seed) { if (g_rand) vv_glibc_rand_destroy(g_rand); g_rand = vv_glibc_rand_create(seed); }
+}
+
 namespace caffe {
 
 // ---- util/math_functions.cu, the subset Blob / Layer / SGDSolver use (ref: math_functions.cu:15-143, 470-512) --------
