@@ -225,8 +225,12 @@ void DropoutLayer<Dtype>::Backward_gpu(const vector<Blob<Dtype>*>& top, const ve
 template <typename Dtype>
 void SliceLayer<Dtype>::Forward_gpu(const vector<Blob<Dtype>*>& bottom, vector<Blob<Dtype>*>* top) {
   FLOAT_ONLY();
+  // (the reference's Reshape leaves num_ / channels_ holding the PER-TOP extent when no slice points are given,
+  // slice_layer.cpp:59-71: the bottom's own shape gives the source pitch)
   const float* src = FP(bottom[0]->gpu_data());
-  const int64_t inner = int64_t(height_) * width_;
+  const int64_t inner = int64_t(bottom[0]->height()) * bottom[0]->width();
+  const int64_t src_pitch = bottom[0]->channels() * inner;
+  const int rows = bottom[0]->num();
   int64_t off = 0;
   for (size_t i = 0; i < top->size(); ++i) {
     Blob<Dtype>* t = (*top)[i];
@@ -235,7 +239,7 @@ void SliceLayer<Dtype>::Forward_gpu(const vector<Blob<Dtype>*>& bottom, vector<B
       off += t->count();
     } else {
       const int64_t cols = t->channels() * inner;
-      VV(vv_copy_strided(src + off, channels_ * inner, FPM(t->mutable_gpu_data()), cols, num_, cols, kStream));
+      VV(vv_copy_strided(src + off, src_pitch, FPM(t->mutable_gpu_data()), cols, rows, cols, kStream));
       off += cols;
     }
   }
@@ -245,7 +249,9 @@ void SliceLayer<Dtype>::Backward_gpu(const vector<Blob<Dtype>*>& top, const vect
   FLOAT_ONLY();
   if (!propagate_down[0]) return;
   float* dst = FPM((*bottom)[0]->mutable_gpu_diff());
-  const int64_t inner = int64_t(height_) * width_;
+  const int64_t inner = int64_t((*bottom)[0]->height()) * (*bottom)[0]->width();
+  const int64_t dst_pitch = (*bottom)[0]->channels() * inner;
+  const int rows = (*bottom)[0]->num();
   int64_t off = 0;
   for (size_t i = 0; i < top.size(); ++i) {
     Blob<Dtype>* t = top[i];
@@ -254,7 +260,7 @@ void SliceLayer<Dtype>::Backward_gpu(const vector<Blob<Dtype>*>& top, const vect
       off += t->count();
     } else {
       const int64_t cols = t->channels() * inner;
-      VV(vv_copy_strided(FP(t->gpu_diff()), cols, dst + off, channels_ * inner, num_, cols, kStream));
+      VV(vv_copy_strided(FP(t->gpu_diff()), cols, dst + off, dst_pitch, rows, cols, kStream));
       off += cols;
     }
   }
