@@ -21,11 +21,12 @@ inline void InstallFailureSignalHandler() {}
 #define LOG_FATAL ::google::LogMessageFatal(__FILE__, __LINE__).stream()
 #define LOG(sev) LOG_##sev
 #define DLOG(sev) ::google::NullStream()
-#define LOG_IF(sev, cond) if (cond) LOG_##sev
+#define LOG_IF(sev, cond) if (!(cond)) ; else LOG_##sev
 #define VLOG(n) ::google::NullStream()
 #define LOG_EVERY_N(sev, n) LOG_##sev
-#define CHECK(c) if (!(c)) LOG_FATAL << "Check failed: " #c " "
-#define CHECK_OP_(a, b, op) if (!((a) op (b))) LOG_FATAL << "Check failed: " #a " " #op " " #b " (" << (a) << " vs. " << (b) << ") "
+// (if (ok) ; else ...: safe inside an unbraced if / else, like glog's own macros)
+#define CHECK(c) if (c) ; else LOG_FATAL << "Check failed: " #c " "
+#define CHECK_OP_(a, b, op) if ((a) op (b)) ; else LOG_FATAL << "Check failed: " #a " " #op " " #b " (" << (a) << " vs. " << (b) << ") "
 #define CHECK_EQ(a, b) CHECK_OP_(a, b, ==)
 #define CHECK_NE(a, b) CHECK_OP_(a, b, !=)
 #define CHECK_LE(a, b) CHECK_OP_(a, b, <=)
