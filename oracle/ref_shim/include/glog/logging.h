@@ -24,9 +24,9 @@ inline void InstallFailureSignalHandler() {}
 #define LOG_IF(sev, cond) if (!(cond)) ; else LOG_##sev
 #define VLOG(n) ::google::NullStream()
 #define LOG_EVERY_N(sev, n) LOG_##sev
-// (if (ok) ; else ...: safe inside an unbraced if / else, like glog's own macros)
-#define CHECK(c) if (c) ; else LOG_FATAL << "Check failed: " #c " "
-#define CHECK_OP_(a, b, op) if ((a) op (b)) ; else LOG_FATAL << "Check failed: " #a " " #op " " #b " (" << (a) << " vs. " << (b) << ") "
+// (if (ok) ; else ...: safe inside an unbraced if / else, and quiet under -Wdangling-else, like glog's own macros)
+#define CHECK(c) switch (0) case 0: default: if (c) ; else LOG_FATAL << "Check failed: " #c " "
+#define CHECK_OP_(a, b, op) switch (0) case 0: default: if ((a) op (b)) ; else LOG_FATAL << "Check failed: " #a " " #op " " #b " (" << (a) << " vs. " << (b) << ") "
 #define CHECK_EQ(a, b) CHECK_OP_(a, b, ==)
 #define CHECK_NE(a, b) CHECK_OP_(a, b, !=)
 #define CHECK_LE(a, b) CHECK_OP_(a, b, <=)

@@ -32,8 +32,9 @@ struct CheckFail {
   [[noreturn]] ~CheckFail() noexcept(false) { throw FatalError(os.str()); }
   template <class T> CheckFail& operator<<(const T& v) { os << v; return *this; }
 };
-#define CHECK(cond) if (!(cond)) ::caffe::CheckFail(__FILE__, __LINE__, #cond)
-#define CHECK_OP(a, b, op) if (!((a) op (b))) ::caffe::CheckFail(__FILE__, __LINE__, #a " " #op " " #b) << "(" << (a) << " vs " << (b) << ") "
+// `if (ok) ; else fail`: safe inside an unbraced if / else, and quiet under -Wdangling-else (the shape glog's own macros have)
+#define CHECK(cond) switch (0) case 0: default: if (cond) ; else ::caffe::CheckFail(__FILE__, __LINE__, #cond)
+#define CHECK_OP(a, b, op) switch (0) case 0: default: if ((a) op (b)) ; else ::caffe::CheckFail(__FILE__, __LINE__, #a " " #op " " #b) << "(" << (a) << " vs " << (b) << ") "
 #define CHECK_EQ(a, b) CHECK_OP(a, b, ==)
 #define CHECK_NE(a, b) CHECK_OP(a, b, !=)
 #define CHECK_LE(a, b) CHECK_OP(a, b, <=)
