@@ -33,6 +33,9 @@ struct CheckFail {
   template <class T> CheckFail& operator<<(const T& v) { os << v; return *this; }
 };
 // `if (ok) ; else fail`: safe inside an unbraced if / else, and quiet under -Wdangling-else (the shape glog's own macros have)
+#if defined(__GNUC__)
+#pragma GCC diagnostic ignored "-Wdangling-else"   // `if (x) CHECK(...)`: the else inside the macro is the intended binding
+#endif
 #define CHECK(cond) switch (0) case 0: default: if (cond) ; else ::caffe::CheckFail(__FILE__, __LINE__, #cond)
 #define CHECK_OP(a, b, op) switch (0) case 0: default: if ((a) op (b)) ; else ::caffe::CheckFail(__FILE__, __LINE__, #a " " #op " " #b) << "(" << (a) << " vs " << (b) << ") "
 #define CHECK_EQ(a, b) CHECK_OP(a, b, ==)
