@@ -183,6 +183,11 @@ int vv_ip_dgrad(vv_operand_t dZ, vv_operand_t W, int M, int N, int K, int prec,
  *           (X^T dZ)^T so that the gathered operand is again operand A.  2-byte operand formats only (BF16, F16X3). */
 int vv_gather_plan(const float* bank, int K, const int32_t* idx, const int32_t* quirk, int B, int R,
                    int32_t* rowmap, float* delta, vv_stream_t stream);
+/* Same, with the indices checked against the bank: a row (or quirk row) outside [0, bank_rows) is planned as row 0 and
+ * *bad_flag (device-visible word, e.g. host-mapped; may be NULL) gets bit 0 set -- vv_trainer_step uses this and reports
+ * the error on the next call.  bank_rows = 0 skips the check. */
+int vv_gather_plan_checked(const float* bank, int64_t bank_rows, int K, const int32_t* idx, const int32_t* quirk, int B, int R,
+                           int32_t* rowmap, float* delta, uint32_t* bad_flag, vv_stream_t stream);
 int vv_ip_forward_gathered(vv_operand_t bank, int64_t bank_rows, const int32_t* rowmap, const float* delta,
                            const float* wlast, vv_operand_t W, const float* bias, int M, int N, int K, int prec,
                            const vv_act_t* act, float* Z, float* H, vv_stream_t stream);

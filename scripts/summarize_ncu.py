@@ -67,6 +67,8 @@ def launches(src, out, tag):
 if __name__ == "__main__":
     rnd = sys.argv[1] if len(sys.argv) > 1 else "r01"
     go = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(os.path.join(go, rnd)):            # later rounds keep their captures in gpurun_out/<round>/
+        go = os.path.join(go, rnd)
     pr = os.path.join(ROOT, "profiles")
     for p in ("f16x3", "tf32x3", "bf16"):
         if os.path.exists(os.path.join(go, "launches_%s.csv" % p)):
@@ -74,7 +76,7 @@ if __name__ == "__main__":
                      "launch list, `python scripts/profile_step.py --precision %s --steps 4` (B=4096, K=4096, N=512, C=5, Nn=10)" % p)
     if os.path.exists(os.path.join(go, "launches_bench.csv")):
         launches(os.path.join(go, "launches_bench.csv"), os.path.join(pr, "%s_launches_bench.txt" % rnd),
-                 "launch list of the bench command itself: `python bench.py --steps 2 --warmup 1 --no-cpu-baseline` (value leg, per-kernel leg, e2e leg)")
+                 "launch list of the bench command itself: `python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extra-configs` (value leg, per-kernel leg, e2e leg)")
     tr = {}
     for key, rep in (("f16x3_gathered", "prof_gemm_f16x3"), ("bf16_gathered", "prof_gemm_bf16")):
         p = os.path.join(go, rep + ".ncu-rep")

@@ -301,3 +301,22 @@ def test_other_context_types_train_step_matches_oracle(oracle, mode, C):
         assert rel(tr.tensor("dW_raw"), ref["dW"]) < 2e-5 and rel(tr.tensor("db_raw"), ref["db"]) < 2e-5
     oracle.use_builtin_blas()
     tr.close(); smp.close()
+
+
+def test_out_of_range_bank_rows_are_reported_not_read():
+    """A sampler / bank mismatch (or a user-fed index) must not become an out-of-bounds read in the GEMM's gather producers:
+    the gather plan clamps the row and raises a flag, the next step fails loudly."""
+    from videovector_b200._lib import VVError
+    B, C, Nn, K, N = 16, 5, 10, 256, 64
+    bank, smp, W0, b0 = setup_problem(B, C, Nn, K, N)
+    tr = ops.Trainer(ops.trainer_cfg(B, C, Nn, K, N, dropout_ratio=0.0, prec="f16x3"))
+    tr.set_weights(torch.as_tensor(W0).cuda(), torch.as_tensor(b0).cuda())
+    tr.set_bank(bank)
+    idx, quirk = smp.next()
+    bad = idx.copy(); bad[3, 7] = bank.shape[0] + 5
+    tr.step(bank, torch.as_tensor(bad).cuda(), torch.as_tensor(quirk).cuda(), None, it=0)      # planned as row 0, flagged
+    torch.cuda.synchronize()
+    assert torch.isfinite(tr.tensor("loss")).all()
+    with pytest.raises(VVError, match="outside"):
+        tr.step(bank, torch.as_tensor(idx).cuda(), torch.as_tensor(quirk).cuda(), None, it=1)
+    tr.close(); smp.close()

@@ -73,6 +73,7 @@ SIGNATURES = {
     "vv_ip_dgrad": (_i, [Operand, Operand, _i, _i, _i, _i, _P, _P]),
     "vv_reduce_parts": (_i, [_P, _i, _i64, _i64, _P, _P]),
     "vv_gather_plan": (_i, [_P, _i, _P, _P, _i, _i, _P, _P, _P]),
+    "vv_gather_plan_checked": (_i, [_P, _i64, _i, _P, _P, _i, _i, _P, _P, _P, _P]),
     "vv_ip_forward_gathered": (_i, [Operand, _i64, _P, _P, _P, Operand, _P, _i, _i, _i, _i, C.POINTER(Act), _P, _P, _P]),
     "vv_ip_wgrad_gathered": (_i, [Operand, Operand, _i64, _P, _i, _i, _i, _i, _f, _P, _i, _P]),
     "vv_ip_wgrad_gathered_part": (_i, [Operand, Operand, _i64, _P, _i, _i, _i, _i, _f, _P, _i, _i, _i, _P]),

@@ -123,6 +123,7 @@ struct vv_trainer {
   ncclComm_t comm = nullptr;
   DpP2P p2p;
   unsigned int finish_epoch = 0;       // finishing wgrad launches so far (the tickets only grow)
+  unsigned int* bad_idx_host = nullptr; unsigned int* bad_idx_dev = nullptr;   // host-mapped: a gather plan saw an index outside the bank
   int last_launches = 0;
   // optional per-phase timing
   bool timing = false;
@@ -178,6 +179,10 @@ struct vv_trainer {
     dq.p = dbx.as<float>() + cfg.N + 4; dq.bytes = size_t(cfg.N) * 4; dq.base = nullptr;
     if (cfg.compute_dgrad) { A(dX, MK * 4); }
 #undef A
+    if (cudaHostAlloc(reinterpret_cast<void**>(&bad_idx_host), sizeof(unsigned int), cudaHostAllocMapped) == cudaSuccess) {
+      *bad_idx_host = 0u;
+      if (cudaHostGetDevicePointer(reinterpret_cast<void**>(&bad_idx_dev), bad_idx_host, 0) != cudaSuccess) bad_idx_dev = nullptr;
+    } else { bad_idx_host = nullptr; cudaGetLastError(); }
     memset(&rank, 0, sizeof(rank));
     rank.B = cfg.B; rank.C = cfg.C; rank.Nn = cfg.Nn; rank.N = cfg.N;
     bool any = false;
@@ -226,6 +231,7 @@ struct vv_trainer {
     for (int i = 0; i < p2p.n_opened; ++i) cudaIpcCloseMemHandle(p2p.opened[i]);
     if (p2p.region) { if (wlast.p && !wlast.base) wlast.p = nullptr; cudaFree(p2p.region); }
     if (p2p.err_host) cudaFreeHost(p2p.err_host);
+    if (bad_idx_host) cudaFreeHost(bad_idx_host);
     if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
     DevBuf* all[] = {&W, &b, &Wh, &bh, &W_hi, &W_lo, &Xf, &X_hi, &X_lo, &Zf, &H, &stats, &item_loss, &item_viol,
                      &dZf, &dZ_hi, &dZ_lo, &dW_parts, &dbx, &dX, &bank_hi, &bank_lo, &rowmap, &delta, &wlast, &dq, &tickets, &rank_ws, &tail_ws, &tail_flags};
@@ -432,7 +438,13 @@ extern "C" int vv_trainer_step(vv_trainer_t* t, const float* bank, int64_t bank_
   const bool fused_gather = t->bank_reg != nullptr && bank == t->bank_reg && bank_rows == t->bank_reg_rows;
   t->tic(0);
   if (fused_gather) {
-    if ((rc = vv_gather_plan(bank, K, idx, quirk, c.B, t->R, t->rowmap.as<int32_t>(), t->delta.as<float>(), s))) return rc;
+    if (t->bad_idx_host && *t->bad_idx_host) {
+      set_error("an earlier step's indices named bank rows outside [0, %lld): the bank and the sampler do not belong together",
+                (long long)t->bank_reg_rows);
+      return VV_ERR_INVALID;
+    }
+    if ((rc = vv_gather_plan_checked(bank, bank_rows, K, idx, quirk, c.B, t->R, t->rowmap.as<int32_t>(), t->delta.as<float>(),
+                                     t->bad_idx_dev, s))) return rc;
   } else {
     if ((rc = t->alloc_x())) return rc;
     if (c.prec == VV_PREC_F16X3 && (bank != t->scaled_bank || bank_rows != t->scaled_bank_rows)) {

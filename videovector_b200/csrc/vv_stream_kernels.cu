@@ -89,9 +89,12 @@ gather_rows_kernel(const float* __restrict__ bank, const int* __restrict__ idx, 
 // Gather plan for the gather-fused GEMMs: rowmap[m] = bank row of X row m = j*B+b (0 in the padding), and
 // delta[m] = (value element K-1 should have) - (value the bank row has there): the K-1 copy quirk
 // (ref: video_sampled_shots_data_layer.cpp:492) expressed as a correction of the last feature only.
+// bank_rows > 0: indices are checked -- a row (or quirk row) outside [0, bank_rows) is replaced by row 0 and reported
+// through *bad (a mismatched bank / sampler pair must not become a silent out-of-bounds read in the GEMM producers)
 __global__ void __launch_bounds__(256)
 gather_plan_kernel(const float* __restrict__ bank, const int* __restrict__ idx, const int* __restrict__ quirk,
-                   int B, int R, int K, int Mpad, int* __restrict__ rowmap, float* __restrict__ delta) {
+                   int B, int R, int K, int Mpad, int* __restrict__ rowmap, float* __restrict__ delta,
+                   long long bank_rows, unsigned int* __restrict__ bad) {
   const int M = B * R;
   for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < Mpad; m += gridDim.x * blockDim.x) {
     int row = 0; float d = 0.f;
@@ -99,7 +102,11 @@ gather_plan_kernel(const float* __restrict__ bank, const int* __restrict__ idx, 
       const int j = m / B, b = m - j * B;
       const int slot = b * R + j;
       row = idx[slot];
-      const int qk = quirk ? quirk[slot] : -2;
+      int qk = quirk ? quirk[slot] : -2;
+      if (bank_rows > 0 && (row < 0 || row >= bank_rows || qk >= bank_rows || qk < -2)) {
+        if (bad) atomicOr(bad, 1u);
+        row = 0; qk = -2;
+      }
       if (qk != -2) d = (qk >= 0 ? bank[(long long)qk * K + (K - 1)] : 0.f) - bank[(long long)row * K + (K - 1)];
     }
     rowmap[m] = row;
@@ -456,9 +463,13 @@ extern "C" int vv_gather_rows(const float* bank, int64_t bank_rows, int K, const
 
 extern "C" int vv_gather_plan(const float* bank, int K, const int32_t* idx, const int32_t* quirk, int B, int R,
                               int32_t* rowmap, float* delta, vv_stream_t stream) {
-  VV_REQUIRE(bank && idx && rowmap && B > 0 && R > 0 && K > 0, "gather_plan: bad arguments");
+  return vv_gather_plan_checked(bank, 0, K, idx, quirk, B, R, rowmap, delta, nullptr, stream);
+}
+extern "C" int vv_gather_plan_checked(const float* bank, int64_t bank_rows, int K, const int32_t* idx, const int32_t* quirk, int B, int R,
+                                      int32_t* rowmap, float* delta, uint32_t* bad_flag, vv_stream_t stream) {
+  VV_REQUIRE(bank && idx && rowmap && B > 0 && R > 0 && K > 0 && bank_rows >= 0, "gather_plan: bad arguments");
   const int M = B * R, Mpad = ((M + 127) / 128) * 128;
-  gather_plan_kernel<<<stream_grid(Mpad, 256), 256, 0, stream>>>(bank, idx, quirk, B, R, K, Mpad, rowmap, delta);
+  gather_plan_kernel<<<stream_grid(Mpad, 256), 256, 0, stream>>>(bank, idx, quirk, B, R, K, Mpad, rowmap, delta, bank_rows, bad_flag);
   VV_LAUNCH_CHECK();
   count_launch();
   return VV_OK;
