@@ -504,8 +504,12 @@ extern "C" int vv_trainer_step(vv_trainer_t* t, const float* bank, int64_t bank_
     if (vv_rank_loss_fused_supported(&t->rank) && !c.split_rank_loss) {
       // K2 + K3 in one pass over H (+ bias gradient); timed as phase 3, phase 2 stays 0
       t->tic(3);
-      VV_CUDA(cudaMemsetAsync(t->dbx.p, 0, size_t(2 * N + 4) * 4, t->stream));      // db, loss, viol, ticket, dq
-      count_launch();
+      // the second-generation kernel STORES db, dq, loss and violations (fixed-order sums through its workspace); the
+      // first-generation one accumulates with atomics into zeroed words
+      if (!rank_loss_fused_v2_applies(&t->rank, c.prec, t->dZf.p != nullptr, false)) {
+        VV_CUDA(cudaMemsetAsync(t->dbx.p, 0, size_t(2 * N + 4) * 4, t->stream));    // db, loss, viol, ticket, dq
+        count_launch();
+      }
       if ((rc = rank_loss_fused_counted(t->H.as<float>(), &t->rank, c.loss_weight, 1, dscale, t->stats.as<float>(), nullptr, nullptr,
                                         t->item_loss.as<float>(), t->item_viol.as<float>(), t->loss_ptr(), t->viol_ptr(),
                                         t->dZf.as<float>(), t->dZ_hi.p, t->dZ_lo.p, c.prec, t->dbx.as<float>(),
