@@ -662,8 +662,9 @@ struct RankWs {            // deterministic column sums (db, dq): layout of the 
 
 // FULL: blockDim.x == N/4 (every thread owns a column group: no bounds checks, no zero fill); NWT > 0: warps per CTA fixed
 // at compile time (4 = the N = 512 case: the per-branch partial sums are one 128-bit shared-memory load)
-template <int CT, int NNT, int OUT, bool FULL, int NWT>
-__global__ void __launch_bounds__(256, 2)
+// OCC: resident CTAs per SM the 128-thread specialisation is compiled for (4: 128 registers, 5: 96, 6: 80 with spills)
+template <int CT, int NNT, int OUT, bool FULL, int NWT, int OCC = 4>
+__global__ void __launch_bounds__(NWT == 4 ? 128 : 256, NWT == 4 ? OCC : 2)
 rank_fused2_kernel(const float* __restrict__ H, const RankDev p, const float gscale, const float dscale,
                    const BwdOut out, float* __restrict__ db_accum, const float* __restrict__ delta,
                    float* __restrict__ dq_accum, float* __restrict__ stats, float* __restrict__ item_loss,
@@ -1281,7 +1282,7 @@ extern "C" int vv_rank_loss_fused(const float* H, const vv_rank_cfg_t* cfg, floa
 // fused kernel instead of a separate rank_loss_reduce_kernel launch (the trainer's path).
 // workspace of the second-generation kernel's deterministic column sums: tickets | per-CTA sums | per-group sums
 size_t vv::rank_loss_workspace_bytes(int N) {
-  const size_t grid = size_t(num_sms()) * 4, groups = (grid + kRankGroup - 1) / kRankGroup;
+  const size_t grid = size_t(num_sms()) * 6, groups = (grid + kRankGroup - 1) / kRankGroup;     // up to 6 resident CTAs per SM
   return 1024 + (grid + groups) * 2 * size_t(N) * sizeof(float);
 }
 bool vv::rank_loss_fused_v2_applies(const vv_rank_cfg_t* cfg, int prec, bool want_dz, bool want_scores) {
@@ -1327,7 +1328,9 @@ int vv::rank_loss_fused_counted(const float* H, const vv_rank_cfg_t* cfg, float 
   unsigned int* cnt = (loss || violations) ? done_counter : nullptr;       // fold the batch reduction into the kernel
   const float inv_count = 1.f / float(d.B * d.Nn);
   if (rank_loss_fused_v2_applies(cfg, o.prec, o.dZ != nullptr, target_score || neg_score) && dZop_hi) {
-    const int per2 = (T <= 128) ? 4 : 2;
+    static const int occ_env = [] { const char* e = getenv("VV_RANK2_CTAS"); const int v = e ? atoi(e) : 4; return v < 4 ? 4 : (v > 6 ? 6 : v); }();
+    const bool hot = (T == d.N4 && T == 128 && d.C == 5 && d.Nn == 10);       // the occupancy variants exist for the shipped shape
+    const int per2 = (T <= 128) ? (hot ? occ_env : 4) : 2;
     const int grid2 = d.B < num_sms() * per2 ? d.B : num_sms() * per2;
     const size_t smem2 = sizeof(float) * 2 * (2 * J + 1) * nw;
     RankWs ws; ws.tickets = nullptr; ws.cta_part = nullptr; ws.grp_part = nullptr;
@@ -1344,7 +1347,11 @@ int vv::rank_loss_fused_counted(const float* H, const vv_rank_cfg_t* cfg, float 
     VV_REQUIRE(act_fused, "rank_loss_fused: the operand-only fast kernel is the fused-activation form");
 #define VV_RANK_V2(CT, NNT, OUT)                                                                                        \
     do {                                                                                                                 \
-      if (T == d.N4 && T == 128) rank_fused2_kernel<CT, NNT, OUT, true, 4><<<grid2, T, smem2, stream>>>(H, d, gscale, ds, o, db_accum,  \
+      if (T == d.N4 && T == 128 && CT == 5 && per2 == 5) rank_fused2_kernel<CT, NNT, OUT, true, 4, (CT == 5 ? 5 : 4)><<<grid2, T, smem2, stream>>>(H, d, gscale, ds, o, db_accum,  \
+          delta, dq_accum, stats, item_loss, item_viol, ws, cnt, inv_count, loss, violations);                             \
+      else if (T == d.N4 && T == 128 && CT == 5 && per2 == 6) rank_fused2_kernel<CT, NNT, OUT, true, 4, (CT == 5 ? 6 : 4)><<<grid2, T, smem2, stream>>>(H, d, gscale, ds, o, db_accum,  \
+          delta, dq_accum, stats, item_loss, item_viol, ws, cnt, inv_count, loss, violations);                             \
+      else if (T == d.N4 && T == 128) rank_fused2_kernel<CT, NNT, OUT, true, 4><<<grid2, T, smem2, stream>>>(H, d, gscale, ds, o, db_accum,  \
           delta, dq_accum, stats, item_loss, item_viol, ws, cnt, inv_count, loss, violations);                             \
       else if (T == d.N4) rank_fused2_kernel<CT, NNT, OUT, true, 0><<<grid2, T, smem2, stream>>>(H, d, gscale, ds, o, db_accum, delta,  \
           dq_accum, stats, item_loss, item_viol, ws, cnt, inv_count, loss, violations);                                    \
