@@ -19,6 +19,7 @@
 // and f16x3 = scaled operands s*x = h0 + h1 in fp16 with the three products h1*h0' + h0*h1' + h0*h0' on the f16
 // pipe (3 MMA units, 4 bytes per element), unscaled by 1/(s s') in the epilogue.
 #include <cuda.h>
+#include <stdlib.h>
 #include "vv_gemm.cuh"
 
 namespace vv {
@@ -68,8 +69,15 @@ __device__ __forceinline__ UnitInfo decode_unit(const TcParams& p, int u, int ti
 }
 
 template <bool kTF32, bool kAMN, bool kBMN, int kNProd, int kBlockN, int kStages, bool kFwdEpi, bool kGather = false,
-          bool kF16 = false, bool kTransOut = false>
+          bool kF16 = false, bool kTransOut = false, bool kTwoCta = false>
 struct Cfg {
+  // kTwoCta: ONE tcgen05.mma.cta_group::2 per k-step over the CTA pair (M = 256: each CTA holds 128 rows of A and of D in
+  // its own smem / TMEM) and each CTA stages only ITS half of the B tile (128 of the 256 W rows, no multicast): the smem
+  // fill per CTA and k-block drops from A + B to A + B/2 and a stage shrinks by a third.  Only the leader CTA (rank 0)
+  // issues MMAs; the peer's TMA credits its bytes to the leader's full barrier, its gather producers complete on a local
+  // barrier that the peer's (otherwise idle) MMA warp relays to the leader.  Built for the gathered forward (K-major, 2-byte).
+  static constexpr bool two_cta = kTwoCta;
+  static_assert(!kTwoCta || (kGather && !kAMN && !kBMN && !kTF32 && kFwdEpi && (kNProd == 1 || kF16)), "cta_group::2 variant: gathered forward only");
   static constexpr bool f16 = kF16;                    // fp16 elements (kind::f16 with F16 formats) instead of bf16
   static_assert(!(kF16 && kTF32), "f16 and tf32 exclude each other");
   // kGather: operand A (X: the rows of FWD, the k-rows of WGRAD_T) is gathered row-wise from the bank's operand copy by
@@ -95,14 +103,15 @@ struct Cfg {
   static constexpr int ksteps = bk / umma_k;           // 4
   static constexpr int chunk = kRowBytes / elem_bytes; // MN elements per 128B row (MN-major)
   static constexpr int a_bytes = kBlockM * kRowBytes;  // 16 KB: the main (hi) tile
-  static constexpr int b_bytes = kBlockN * kRowBytes;  // 32 KB (BLOCK_N = 256)
+  static constexpr int b_bytes = (kBlockN / (kTwoCta ? 2 : 1)) * kRowBytes;  // 32 KB (BLOCK_N = 256); cta_group::2: this CTA's half
   // mixed mode: two extra bf16 tiles per operand (bf16(x) and bf16(lo)) covering the same bk = 32 reduction
   // elements: K-major = rows of 64 B (SWIZZLE_64B); MN-major = 64-element chunks of [32 k-rows x 128 B] (SWIZZLE_128B)
   static constexpr int a_half = a_bytes / 2, b_half = b_bytes / 2;
   // split16: a second full-size tile per operand (the h1 plane), stage = [A_h0][A_h1][B_h0][B_h1]
   static constexpr int stage_bytes = (mixed || split16) ? 2 * (a_bytes + b_bytes) : (a_bytes + b_bytes);
   static constexpr int tmem_cols = 2 * kBlockN;
-  static constexpr int smem_bytes = stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int smem_bytes = stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers: (3 * stages + 4) * 8 + 8 bytes*/;
+  static_assert((3 * kStages + 4) * 8 + 8 <= 256, "barrier area");
   static_assert(tmem_cols == 256 || tmem_cols == 512, "TMEM allocation must be a power of two");
   static_assert(smem_bytes <= 232448, "exceeds 227 KB of shared memory");
 };
@@ -243,7 +252,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   uint64_t* empty_bar = full_bar + C::stages;
   uint64_t* tmem_full = empty_bar + C::stages;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* gfull_bar = tmem_empty + 2;            // cta_group::2, peer CTA: its gather producers' completion (relayed to the leader)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gfull_bar + C::stages);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -255,11 +265,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   }
   if (warp == 1 && lane == 0) {
     // full: the TMA lane's arrive.expect_tx (+ one cp.async-completion arrival per gather lane, 2 warps)
-    for (int s = 0; s < C::stages; ++s) { mbar_init(&full_bar[s], C::gather ? 1 + 64 : 1); mbar_init(&empty_bar[s], C::cluster); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 8); }
+    if (C::two_cta) {
+      // leader's full: its TMA lane's arrive.expect_tx (bytes of BOTH CTAs) + its 64 gather lanes + the peer's relay;
+      // empty / tmem_full: one multicast commit of the single MMA issuer; leader's tmem_empty: 8 local + 8 remote epilogue warps
+      for (int s = 0; s < C::stages; ++s) { mbar_init(&full_bar[s], 1 + 64 + 1); mbar_init(&empty_bar[s], 1); mbar_init(&gfull_bar[s], 64); }
+      for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 16); }
+    } else {
+      for (int s = 0; s < C::stages; ++s) { mbar_init(&full_bar[s], C::gather ? 1 + 64 : 1); mbar_init(&empty_bar[s], C::cluster); }
+      for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 8); }
+    }
     fence_barrier_init();
   }
-  if (warp == 2) { tmem_alloc(tmem_slot, C::tmem_cols); tmem_relinquish(); }
+  if (warp == 2) {
+    if (C::two_cta) { tmem_alloc2(tmem_slot, C::tmem_cols); tmem_relinquish2(); }
+    else { tmem_alloc(tmem_slot, C::tmem_cols); tmem_relinquish(); }
+  }
   tc_fence_before();
   if (C::cluster > 1) cluster_sync_all(); else __syncthreads();   // barrier inits visible to the peer before any remote arrive
   tc_fence_after();
@@ -293,11 +313,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const int kb0 = ui.kb0, kb1 = ui.kb1;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
-          mbar_arrive_expect_tx(&full_bar[stage], kTmaBytes);
           // stage layout: [A_hi][A_hb][A_lb][B_hi][B_hb][B_lb]  (the extra tiles only in the split modes)
           uint8_t* sa = smem + stage * C::stage_bytes;
           uint8_t* sb = sa + ((C::mixed || C::split16) ? 2 * C::a_bytes : C::a_bytes);
           const int k0 = kb * C::bk;
+          if (C::two_cta) {
+            // this CTA's half of the W tile (rows n0 + 128 * rank), into its own smem; the bytes of both CTAs complete on the
+            // leader's barrier, which the leader arms for the pair
+            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * kTmaBytes);
+            tma_load_2d_2cta(sb, &tmB_hi, &full_bar[stage], k0, n0 + cta_rank * (C::block_n / 2));
+            if (C::split16) tma_load_2d_2cta(sb + C::b_bytes, &tmB_hb, &full_bar[stage], k0, n0 + cta_rank * (C::block_n / 2));
+            if (++stage == C::stages) { stage = 0; phase ^= 1u; }
+            continue;
+          }
+          mbar_arrive_expect_tx(&full_bar[stage], kTmaBytes);
           if (!C::gather) {
             if (!C::a_mn) {
               tma_load_2d(sa, &tmA_hi, &full_bar[stage], k0, m0);
@@ -390,8 +419,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
+    if (C::two_cta && cta_rank != 0) {
+      // cta_group::2, peer CTA: no MMAs to issue.  This warp relays the completion of the peer's row gathers (cp.async into
+      // the peer's own smem, counted on its local barrier) to the leader's full barrier, stage by stage, in the order
+      // the leader consumes them.
+      if (lane == 0) {
+        int stage = 0; uint32_t phase = 0;
+        for (int u = unit0; u < total_units; u += unit_stride) {
+          const UnitInfo ui = decode_unit(p, u, tiles_mn);
+          for (int kb = ui.kb0; kb < ui.kb1; ++kb) {
+            mbar_wait(&gfull_bar[stage], phase);
+            fence_proxy_async();                    // the gathered tile (generic-proxy writes) before the leader's MMA reads it
+            mbar_arrive_cluster(&full_bar[stage], 0);
+            if (++stage == C::stages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    } else
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(C::tf32 ? 2 : (C::f16 ? 0 : 1), C::a_mn ? 1 : 0, C::b_mn ? 1 : 0, kBlockM, C::block_n);
+      constexpr uint32_t idesc = make_idesc(C::tf32 ? 2 : (C::f16 ? 0 : 1), C::a_mn ? 1 : 0, C::b_mn ? 1 : 0,
+                                            C::two_cta ? 2 * kBlockM : kBlockM, C::block_n);
       // K-major : rows of 128 B, 8-row atoms 1024 B apart (SBO); LBO unused (1)
       // MN-major: 128 B of MN contiguous, k-rows 128 B apart, 8-row atoms 1024 B apart (SBO),
       //           next MN chunk bk*128 B away (LBO)
@@ -414,12 +461,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         // Non-promoting configurations use one chunk per unit.
         for (int c0 = kb0; c0 < kb1; c0 += p.chunk_kb) {
           const int c1 = min(c0 + p.chunk_kb, kb1);
-          mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+          if (C::two_cta) mbar_wait_cluster(&tmem_empty[acc], acc_phase ^ 1u);      // both CTAs' epilogues have drained the buffer
+          else mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + uint32_t(acc * C::block_n);
           uint32_t accumulate = 0;
           for (int kb = c0; kb < c1; ++kb) {
-            mbar_wait(&full_bar[stage], phase);
+            if (C::two_cta) mbar_wait_cluster(&full_bar[stage], phase); else mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
             if (C::gather) fence_proxy_async();     // A was written by cp.async (generic proxy); the MMA reads through the async proxy
             const uint32_t sa = smem_u32(smem + stage * C::stage_bytes);
@@ -451,14 +499,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 // cross terms first (small magnitude): h1*h0' + h0*h1', then h0*h0'
                 const uint64_t a_h1 = make_smem_desc(sa + C::a_bytes + k * kadv_a, lbo_a, sbo_a, lay_a);
                 const uint64_t b_h1 = make_smem_desc(sb + C::b_bytes + k * kadv_b, lbo_b, sbo_b, lay_b);
-                umma_ss<false>(d_tmem, a_h1, b_hi, idesc, accumulate);
-                umma_ss<false>(d_tmem, a_hi, b_h1, idesc, 1u);
+                if (C::two_cta) { umma2_ss_f16(d_tmem, a_h1, b_hi, idesc, accumulate); umma2_ss_f16(d_tmem, a_hi, b_h1, idesc, 1u); }
+                else { umma_ss<false>(d_tmem, a_h1, b_hi, idesc, accumulate); umma_ss<false>(d_tmem, a_hi, b_h1, idesc, 1u); }
                 accumulate = 1u;
               }
-              umma_ss<C::tf32>(d_tmem, a_hi, b_hi, idesc, accumulate);
+              if (C::two_cta) umma2_ss_f16(d_tmem, a_hi, b_hi, idesc, accumulate);
+              else umma_ss<C::tf32>(d_tmem, a_hi, b_hi, idesc, accumulate);
               accumulate = 1u;
             }
             // frees the smem stage when these MMAs retire -- in BOTH CTAs of a cluster (the peer multicasts into it)
+            if (C::two_cta) {
+              umma2_commit_mc(&empty_bar[stage], 0x3);
+              if (kb == c1 - 1) umma2_commit_mc(&tmem_full[acc], 0x3);        // the accumulator halves of both CTAs are ready
+              if (++stage == C::stages) { stage = 0; phase ^= 1u; }
+              continue;
+            }
             if (C::cluster > 1) umma_commit_mc(&empty_bar[stage], 0x3); else umma_commit(&empty_bar[stage]);
             if (kb == c1 - 1) umma_commit(&tmem_full[acc]);
             if (++stage == C::stages) { stage = 0; phase ^= 1u; }
@@ -511,7 +566,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             cp_async16_l2_256(dst, src, nb);
             if (kPlanes == 2) cp_async16_l2_256(dst + C::a_bytes, src + h1d, nb);
           }
-          cp_async_mbar_arrive_noinc(&full_bar[stage]);
+          cp_async_mbar_arrive_noinc((C::two_cta && cta_rank != 0) ? &gfull_bar[stage] : &full_bar[stage]);
           if (++stage == C::stages) { stage = 0; phase ^= 1u; }
         }
       } else {
@@ -590,7 +645,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           }
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          if (lane == 0) { if (C::two_cta && cta_rank != 0) mbar_arrive_cluster(&tmem_empty[acc], 0); else mbar_arrive(&tmem_empty[acc]); }
           acc ^= 1; if (acc == 0) acc_phase ^= 1u;
         }
         if (C::fwd_epi && ui.half == 1) {
@@ -720,7 +775,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        if (lane == 0) { if (C::two_cta && cta_rank != 0) mbar_arrive_cluster(&tmem_empty[acc], 0); else mbar_arrive(&tmem_empty[acc]); }
         acc ^= 1; if (acc == 0) acc_phase ^= 1u;
         if (C::fwd_epi && ui.half == 1) {
           __threadfence();
@@ -738,7 +793,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 
   tc_fence_before();
   if (C::cluster > 1) cluster_sync_all(); else __syncthreads();   // the peer may still arrive on / multicast into this CTA
-  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, C::tmem_cols); }
+  if (warp == 2) { tc_fence_after(); if (C::two_cta) tmem_dealloc2(tmem_base, C::tmem_cols); else tmem_dealloc(tmem_base, C::tmem_cols); }
 #endif
 }
 
@@ -935,6 +990,12 @@ int gemm_tc_launch(const GemmProblem& g, cudaStream_t stream) {
   if (gat != (g.kind == GEMM_WGRAD_T) && g.kind != GEMM_FWD) { set_error("only FWD and WGRAD_T take a gathered operand"); return VV_ERR_INVALID; }
   if (gat && g.prec != VV_PREC_BF16 && g.prec != VV_PREC_F16X3) {
     set_error("the gather-fused variants are built for the 2-byte operand formats (bf16, f16x3)"); return VV_ERR_UNSUPPORTED;
+  }
+  // cta_group::2 forward (gathered, 2-byte operands): VV_GEMM_2CTA=1
+  static const bool two_cta = [] { const char* e = getenv("VV_GEMM_2CTA"); return e && atoi(e) != 0; }();
+  if (two_cta && gat && g.kind == GEMM_FWD && (g.N % 256) == 0) {
+    if (g.prec == VV_PREC_BF16)  return launch_cfg<Cfg<false, false, false, 1, 256, 6, true, true, false, false, true>>(g, stream);
+    if (g.prec == VV_PREC_F16X3) return launch_cfg<Cfg<false, false, false, 3, 256, 3, true, true, true,  false, true>>(g, stream);
   }
   if (g.prec == VV_PREC_BF16) {
     switch (g.kind) {
