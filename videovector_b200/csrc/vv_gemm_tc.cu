@@ -423,16 +423,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       // cta_group::2, peer CTA: no MMAs to issue.  This warp relays the completion of the peer's row gathers (cp.async into
       // the peer's own smem, counted on its local barrier) to the leader's full barrier, stage by stage, in the order
       // the leader consumes them.
-      if (lane == 0) {
-        int stage = 0; uint32_t phase = 0;
-        for (int u = unit0; u < total_units; u += unit_stride) {
-          const UnitInfo ui = decode_unit(p, u, tiles_mn);
-          for (int kb = ui.kb0; kb < ui.kb1; ++kb) {
-            mbar_wait(&gfull_bar[stage], phase);
-            fence_proxy_async();                    // the gathered tile (generic-proxy writes) before the leader's MMA reads it
-            mbar_arrive_cluster(&full_bar[stage], 0);
-            if (++stage == C::stages) { stage = 0; phase ^= 1u; }
-          }
+      // One lane per stage (lane s relays stage s, phase after phase): the waits, proxy fences and remote arrivals of
+      // different stages overlap -- a single relay thread's wait + fence + NVLink-free but cluster-wide arrive per k-block
+      // is slower than one bf16 k-block of MMAs.
+      if (lane < C::stages) {
+        long long total_kb = 0;
+        for (int u = unit0; u < total_units; u += unit_stride) { const UnitInfo ui = decode_unit(p, u, tiles_mn); total_kb += ui.kb1 - ui.kb0; }
+        uint32_t phase = 0;
+        for (long long i = lane; i < total_kb; i += C::stages, phase ^= 1u) {
+          mbar_wait(&gfull_bar[lane], phase);
+          fence_proxy_async();                      // the gathered tile (generic-proxy writes) before the leader's MMA reads it
+          mbar_arrive_cluster(&full_bar[lane], 0);
         }
       }
     } else
@@ -991,11 +992,13 @@ int gemm_tc_launch(const GemmProblem& g, cudaStream_t stream) {
   if (gat && g.prec != VV_PREC_BF16 && g.prec != VV_PREC_F16X3) {
     set_error("the gather-fused variants are built for the 2-byte operand formats (bf16, f16x3)"); return VV_ERR_UNSUPPORTED;
   }
-  // cta_group::2 forward (gathered, 2-byte operands): VV_GEMM_2CTA=1
-  static const bool two_cta = [] { const char* e = getenv("VV_GEMM_2CTA"); return e && atoi(e) != 0; }();
+  // cta_group::2 forward (gathered, 2-byte operands). Measured (profiles/r02_2cta_forward.md): f16x3 forward 0.622 ms vs
+  // 0.641 with the 1-CTA multicast kernel, bf16 0.267 vs 0.246 -- so it is the default for f16x3 only.
+  // VV_GEMM_2CTA=0 turns it off, =1 also takes it for bf16.
+  static const int two_cta = [] { const char* e = getenv("VV_GEMM_2CTA"); return e ? (atoi(e) != 0 ? 2 : 0) : 1; }();
   if (two_cta && gat && g.kind == GEMM_FWD && (g.N % 256) == 0) {
-    if (g.prec == VV_PREC_BF16)  return launch_cfg<Cfg<false, false, false, 1, 256, 6, true, true, false, false, true>>(g, stream);
-    if (g.prec == VV_PREC_F16X3) return launch_cfg<Cfg<false, false, false, 3, 256, 3, true, true, true,  false, true>>(g, stream);
+    if (g.prec == VV_PREC_BF16 && two_cta == 2) return launch_cfg<Cfg<false, false, false, 1, 256, 6, true, true, false, false, true>>(g, stream);
+    if (g.prec == VV_PREC_F16X3)                return launch_cfg<Cfg<false, false, false, 3, 256, 3, true, true, true,  false, true>>(g, stream);
   }
   if (g.prec == VV_PREC_BF16) {
     switch (g.kind) {
