@@ -2,7 +2,7 @@
 into the GEMMs, persistent multi-wave forward: 480 cluster tiles on 74 clusters) against the oracle's whole TRAIN net
 (ref: inner_product_layer.cpp:61-106, relu_layer.cpp:10-36, dropout_layer.cpp:13-68, eltwise / normalization / sum /
 split layers, max_margin_loss_layer.cpp:54-214) on identical inputs with an explicit dropout mask, and of configs[3]'s
-shape (C = 17, Nn = 50, N = 1024: the two-kernel rank loss) at B = 512."""
+shape (C = 17, Nn = 50, N = 1024: the wide rank-loss kernel, two phases per item) at B = 512."""
 import numpy as np
 import pytest
 import torch
@@ -72,6 +72,10 @@ def run_case(oracle, prec, B, C, Nn, K, N, V, S, tol, update_check):
         assert rel_l2(tr.dZ_from_operand(), ref["dZ"]) < 10 * tol
         assert rel_l2(tr.tensor("dW_raw"), ref["dW"]) < 10 * tol
         assert rel_l2(tr.tensor("db_raw"), ref["db"]) < 10 * tol
+    # the same step again: loss and the bias gradient (column sums of dZ) are summed in a fixed order -> bit-identical
+    db_first, loss_first = tr.tensor("db_raw").clone(), tr.tensor("loss").clone()
+    tr.step(bank, di, dq, dm, it=0, do_update=False)
+    assert torch.equal(tr.tensor("db_raw"), db_first) and torch.equal(tr.tensor("loss"), loss_first)
     if update_check:
         # one update on top (K4 / the fused update): W, b and both histories against the oracle's SGD step
         tr.step(bank, di, dq, dm, it=0, do_update=True)

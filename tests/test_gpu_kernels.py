@@ -364,9 +364,46 @@ def test_rank_loss_fused_operand_only_form(B, C, Nn, N, norm, prec):
     assert rel(db, dZ_ref.sum(0)) < 1e-5
 
 
-def test_rank_loss_fused_unsupported_shapes():
-    assert not ops.rank_loss_fused_supported(ops.rank_cfg(8, 5, 30, 512))     # R > 32
+def test_rank_loss_fused_unsupported_shapes(monkeypatch):
+    assert ops.rank_loss_fused_supported(ops.rank_cfg(8, 5, 30, 512))         # R > 32: the wide (two-phase) kernel
     assert not ops.rank_loss_fused_supported(ops.rank_cfg(8, 5, 10, 2048))    # N > 1024
+    assert not ops.rank_loss_fused_supported(ops.rank_cfg(8, 5, 256, 512))    # more negatives than the wide kernel's scalar stage takes
+
+
+@pytest.mark.parametrize("B,C,Nn,N,norm", [(37, 17, 50, 1024, 2), (9, 9, 40, 512, 1), (5, 3, 33, 100, 2), (700, 5, 30, 256, 2),
+                                            (1, 17, 50, 1024, 2)])
+@pytest.mark.parametrize("prec", ["fp32_simt", "tf32x3", "f16x3", "bf16"])
+def test_rank_loss_wide_equals_two_kernel_path(B, C, Nn, N, norm, prec):
+    """Items with more than 32 rows (the large-window configuration: 16 context shots + 50 negatives): one launch, two
+    phases per item, the second reading the rows back from L2.  Same formulas, trees and orders as the forward +
+    backward kernels: everything but the column sums (db, fixed order here, atomics there) must be bit-identical."""
+    R = C + Nn
+    g = torch.Generator(device="cuda").manual_seed(B + N)
+    H = torch.relu(torch.randn(R * B, N, device="cuda", generator=g))
+    H = (H * (torch.rand(R * B, N, device="cuda", generator=g) < 0.3) * 3.0).contiguous()
+    H[min(5, R * B - 1)] = 0.0
+    cfg = ops.rank_cfg(B, C, Nn, N, margin=2.0, norm=norm)
+    assert ops.rank_loss_fused_supported(cfg)
+    a = ops.rank_loss_forward(H, cfg)
+    dZ_a, op_a, db_a = ops.rank_loss_backward(H, cfg, a["stats"], 0.7, True, 10.0, prec=prec)
+    b, dZ_b, op_b, db_b = ops.rank_loss_fused(H, cfg, 0.7, True, 10.0, prec=prec)
+    for k in ("stats", "target_score", "neg_score", "item_viol", "violations", "item_loss"):
+        assert torch.equal(a[k], b[k]), k
+    assert rel(b["loss"], a["loss"]) < 1e-6
+    assert torch.equal(dZ_a, dZ_b)
+    assert rel(db_b, db_a) < 1e-5
+    if prec != "fp32_simt":
+        assert torch.equal(op_a.hi, op_b.hi) and (op_a.lo is None or torch.equal(op_a.lo, op_b.lo))
+    loss, viol, st, sn, dH_ref, dZ_ref = _rank_ref64(H, B, C, Nn, 2.0, norm, 0.7, 10.0)
+    assert abs(b["loss"].item() - loss) < 1e-5 * max(1, abs(loss)) and b["violations"].item() == viol
+    assert rel(dZ_b, dZ_ref) < 1e-5
+    assert rel(db_b, dZ_ref.sum(0)) < 1e-5
+    # operand-only form (what the trainer asks for; there the column sums go through a workspace in a fixed order --
+    # tests/test_gpu_fullsize.py checks that they repeat bit for bit)
+    c1, _, op_c, db_c1 = ops.rank_loss_fused(H, cfg, 0.7, True, 10.0, prec=prec, want_dz=(prec == "fp32_simt"), want_scores=False)
+    assert torch.equal(c1["loss"], b["loss"]) and rel(db_c1, db_b) < 1e-5
+    if prec != "fp32_simt":
+        assert torch.equal(op_c.hi, op_b.hi)
 
 
 @pytest.mark.parametrize("prec", ["tf32x3", "f16x3", "bf16"])

@@ -660,6 +660,81 @@ struct RankWs {            // deterministic column sums (db, dq): layout of the 
   float* grp_part;         // [groups][2][N]
 };
 
+// Deterministic column sums (db, dq) and batch loss of a rank kernel with one float4 column group per thread: every CTA
+// stores its partials, the last CTA of each group of kRankGroup sums them in CTA order, the last group sums the groups
+// in group order and then the item losses in a fixed order.  Tickets reset themselves.  Called by all T threads.
+__device__ __forceinline__ void column_sums_finish(const RankWs& ws, const RankDev& p, const float4& dbacc, const float4& dqacc,
+                                                   bool col_ok, float* db_accum, float* dq_accum, const float* item_loss,
+                                                   const float* item_viol, float inv_count, float* loss_out, float* viol_out,
+                                                   int tid, int T) {
+  __shared__ unsigned int s_flag;
+  __shared__ float red[66];
+  const int N4 = p.N4;
+  const int grp = blockIdx.x / kRankGroup, ngroups = (gridDim.x + kRankGroup - 1) / kRankGroup;
+  const int g0 = grp * kRankGroup, gsize = min(kRankGroup, int(gridDim.x) - g0);
+  if (col_ok) {
+    float4* mine = reinterpret_cast<float4*>(ws.cta_part) + size_t(blockIdx.x) * 2 * N4;
+    mine[tid] = dbacc; mine[N4 + tid] = dqacc;
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned int prev = atomicAdd(&ws.tickets[grp], 1u);
+    const bool last = prev + 1u == unsigned(gsize);
+    if (last) ws.tickets[grp] = 0u;
+    s_flag = last ? 1u : 0u;
+  }
+  __syncthreads();
+  if (s_flag == 0u) return;
+  __threadfence();
+  if (col_ok) {
+    const float4* base = reinterpret_cast<const float4*>(ws.cta_part) + size_t(g0) * 2 * N4;
+    float4 sb = make_float4(0.f, 0.f, 0.f, 0.f), sq = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+    for (int c = 0; c < gsize; ++c) {
+      const float4 a = __ldcg(base + size_t(c) * 2 * N4 + tid), q = __ldcg(base + size_t(c) * 2 * N4 + N4 + tid);
+      sb.x += a.x; sb.y += a.y; sb.z += a.z; sb.w += a.w; sq.x += q.x; sq.y += q.y; sq.z += q.z; sq.w += q.w;
+    }
+    float4* gp = reinterpret_cast<float4*>(ws.grp_part) + size_t(grp) * 2 * N4;
+    gp[tid] = sb; gp[N4 + tid] = sq;
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned int prev = atomicAdd(&ws.tickets[ngroups], 1u);
+    const bool last = prev + 1u == unsigned(ngroups);
+    if (last) ws.tickets[ngroups] = 0u;
+    s_flag = last ? 1u : 0u;
+  }
+  __syncthreads();
+  if (s_flag == 0u) return;
+  __threadfence();
+  if (col_ok) {
+    const float4* base = reinterpret_cast<const float4*>(ws.grp_part);
+    float4 sb = make_float4(0.f, 0.f, 0.f, 0.f), sq = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+    for (int c = 0; c < ngroups; ++c) {
+      const float4 a = __ldcg(base + size_t(c) * 2 * N4 + tid), q = __ldcg(base + size_t(c) * 2 * N4 + N4 + tid);
+      sb.x += a.x; sb.y += a.y; sb.z += a.z; sb.w += a.w; sq.x += q.x; sq.y += q.y; sq.z += q.z; sq.w += q.w;
+    }
+    if (db_accum) reinterpret_cast<float4*>(db_accum)[tid] = sb;
+    if (dq_accum) reinterpret_cast<float4*>(dq_accum)[tid] = sq;
+  }
+  if (loss_out || viol_out) {                           // the batch loss / violation count, fixed order (as last_cta_loss_reduce)
+    float a = 0.f, c = 0.f;
+    for (int i = tid; i < p.B; i += T) { a += __ldcg(item_loss + i); c += __ldcg(item_viol + i); }
+    a = warp_sum(a); c = warp_sum(c);
+    if ((tid & 31) == 0) { red[tid >> 5] = a; red[32 + (tid >> 5)] = c; }
+    __syncthreads();
+    if (tid == 0) {
+      a = 0.f; c = 0.f;
+      for (int w = 0; w < (T >> 5); ++w) { a += red[w]; c += red[32 + w]; }
+      if (loss_out) *loss_out = a * inv_count;
+      if (viol_out) *viol_out = c;
+    }
+  }
+}
+
 // FULL: blockDim.x == N/4 (every thread owns a column group: no bounds checks, no zero fill); NWT > 0: warps per CTA fixed
 // at compile time (4 = the N = 512 case: the per-branch partial sums are one 128-bit shared-memory load)
 // OCC: resident CTAs per SM the 128-thread specialisation is compiled for (4: 128 registers, 5: 96, 6: 80 with spills)
@@ -864,9 +939,8 @@ rank_fused2_kernel(const float* __restrict__ H, const RankDev p, const float gsc
   dbacc.x *= inv_os; dbacc.y *= inv_os; dbacc.z *= inv_os; dbacc.w *= inv_os;
   dqacc.x *= inv_os; dqacc.y *= inv_os; dqacc.z *= inv_os; dqacc.w *= inv_os;
   if (OUT == 8) f16_publish_absmax(out.hi, amax * inv_os);
-  __shared__ unsigned int s_flag;
-  __shared__ float red[66];
   if (ws.tickets == nullptr) {
+    __shared__ float red[66];
     // no workspace: atomics (order-dependent rounding), and the ticketed loss reduction of rank_fused_kernel
     if (col_ok) {
       if (db_accum) {
@@ -884,71 +958,250 @@ rank_fused2_kernel(const float* __restrict__ H, const RankDev p, const float gsc
     }
     return;
   }
-  // ---- deterministic column sums: CTA partials -> group sums (CTA order) -> totals (group order)
-  const int N4 = p.N4;
-  const int grp = blockIdx.x / kRankGroup, ngroups = (gridDim.x + kRankGroup - 1) / kRankGroup;
-  const int g0 = grp * kRankGroup, gsize = min(kRankGroup, int(gridDim.x) - g0);
-  if (col_ok) {
-    float4* mine = reinterpret_cast<float4*>(ws.cta_part) + size_t(blockIdx.x) * 2 * N4;
-    mine[tid] = dbacc; mine[N4 + tid] = dqacc;
-  }
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) {
-    const unsigned int prev = atomicAdd(&ws.tickets[grp], 1u);
-    const bool last = prev + 1u == unsigned(gsize);
-    if (last) ws.tickets[grp] = 0u;
-    s_flag = last ? 1u : 0u;
-  }
-  __syncthreads();
-  if (s_flag == 0u) return;
-  __threadfence();
-  if (col_ok) {
-    const float4* base = reinterpret_cast<const float4*>(ws.cta_part) + size_t(g0) * 2 * N4;
-    float4 sb = make_float4(0.f, 0.f, 0.f, 0.f), sq = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 8
-    for (int c = 0; c < gsize; ++c) {
-      const float4 a = __ldcg(base + size_t(c) * 2 * N4 + tid), q = __ldcg(base + size_t(c) * 2 * N4 + N4 + tid);
-      sb.x += a.x; sb.y += a.y; sb.z += a.z; sb.w += a.w; sq.x += q.x; sq.y += q.y; sq.z += q.z; sq.w += q.w;
+  column_sums_finish(ws, p, dbacc, dqacc, col_ok, db_accum, dq_accum, item_loss, item_viol, inv_count, loss_out, viol_out, tid, T);
+}
+
+// ---- K2+K3 for wide items (R > 32 rows: the large-window configuration, 16 context shots + 50 negatives) ------------
+// One launch, one CTA per item, two phases over the item's rows.  Phase 1 streams the rows once from HBM (context mean,
+// then |x|^2 and <cbar, x> of the target and every negative) and asks L2 to keep them (evict_last); the per-item scalar
+// chain of rank_fwd_kernel / rank_bwd_kernel follows in shared memory; phase 2 reads the rows again -- 2 CTAs per SM x
+// R*N*4 bytes = 81 MB in flight at R = 67, N = 1024, inside the 126 MB L2 -- and writes the gradient rows.  HBM traffic
+// is R*N*4 read + the dZ operand write, as for the register-resident kernels; the two-kernel path read H twice from HBM
+// and re-read the context rows a third time.  Formulas, reduction trees and summation orders are those of
+// rank_fwd_kernel / rank_bwd_kernel (their results agree bit for bit except db / dq, which are summed in a fixed order
+// here).  Needs nvec == 1 (N <= 1024).
+// OCC: resident CTAs per SM the kernel is compiled for; rows in flight per thread follow from the register budget
+
+__device__ __forceinline__ float4 ld4_keep(const float* p) {
+  float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+#if defined(__CUDA_ARCH__)
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p), "l"(kEvictLast));
+#endif
+  return r;
+}
+__device__ __forceinline__ float4 ld4_last_use(const float* p) {
+  float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+#if defined(__CUDA_ARCH__)
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p), "l"(kEvictFirst));
+#endif
+  return r;
+}
+
+template <int OUT, int OCC>
+__global__ void __launch_bounds__(256, OCC)
+rank_wide_kernel(const float* __restrict__ H, const RankDev p, const float gscale, const int act_fused,
+                 const float dscale, const BwdOut out, float* __restrict__ db_accum,
+                 const float* __restrict__ delta, float* __restrict__ dq_accum,
+                 float* __restrict__ stats, float* __restrict__ tscore, float* __restrict__ nscore,
+                 float* __restrict__ item_loss, float* __restrict__ item_viol, const RankWs ws,
+                 unsigned int* __restrict__ done_counter, const float inv_count, float* __restrict__ loss_out,
+                 float* __restrict__ viol_out, const int prefetch_next) {
+  constexpr int kWideBatch = OCC <= 2 ? 8 : 4;
+  extern __shared__ __align__(16) float sm[];
+  const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = T >> 5;
+  const int J = 1 + p.Nn;
+  float* part = sm;                        // [2J + 1][nw]: (s_x, p_x) per branch, then s_c
+  float* s_s = part + (2 * J + 1) * nw;    // [J] |x|^2
+  float* s_p = s_s + J;                    // [J] <cbar, x>
+  float* s_w = s_p + J;                    // [J] weight of branch j on c^ : w_0 = -sum g, w_k = g_k
+  float* cA = s_w + J;                     // [J] coefficient on cbar
+  float* cB = cA + J;                      // [J] coefficient on x
+  float* cE = cB + J;                      // [J] w_j / n_j   (d c^ = sum_j cE_j x_j)
+  float* s_l = cE + J;                     // [J] loss term of negative k
+  float* s_v = s_l + J;                    // [J] violation of negative k
+  float* sc = s_v + J;                     // [4] s_c, nc, Fs, Fc
+  const bool col_ok = tid < p.N4;
+  const size_t rs = size_t(p.B) * p.N;     // row stride of the blob, in elements
+  const float hdr_scale = (out.prec == VV_PREC_F16X3) ? f16_hdr(out.hi)->scale : 1.f;
+  const float oscale = hdr_scale > 0.f ? hdr_scale : 1.f;     // a header that was never set measures with scale 1
+  float4 dbacc = make_float4(0.f, 0.f, 0.f, 0.f), dqacc = make_float4(0.f, 0.f, 0.f, 0.f);
+  float amax = 0.f;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
+    const size_t e0 = size_t(b) * p.N + size_t(tid) * 4;
+    const float* hp = H + e0;
+    // ================= phase 1: one pass over the rows =================
+    // c-bar = sum_i coeff_i * ctx_i, bottom order (eltwise_layer.cpp:67-73)
+    float4 cbar = zero4;
+    for (int i0 = 1; i0 < p.C; i0 += kWideBatch) {
+      float4 x[kWideBatch];
+#pragma unroll
+      for (int r = 0; r < kWideBatch; ++r) x[r] = (i0 + r < p.C && col_ok) ? ld4_keep(hp + size_t(i0 + r) * rs) : zero4;
+#pragma unroll
+      for (int r = 0; r < kWideBatch; ++r) {
+        if (i0 + r < p.C) {
+          const float a = p.coeff[i0 + r - 1];
+          cbar.x = fmaf(a, x[r].x, cbar.x); cbar.y = fmaf(a, x[r].y, cbar.y);
+          cbar.z = fmaf(a, x[r].z, cbar.z); cbar.w = fmaf(a, x[r].w, cbar.w);
+        }
+      }
     }
-    float4* gp = reinterpret_cast<float4*>(ws.grp_part) + size_t(grp) * 2 * N4;
-    gp[tid] = sb; gp[N4 + tid] = sq;
-  }
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) {
-    const unsigned int prev = atomicAdd(&ws.tickets[ngroups], 1u);
-    const bool last = prev + 1u == unsigned(ngroups);
-    if (last) ws.tickets[ngroups] = 0u;
-    s_flag = last ? 1u : 0u;
-  }
-  __syncthreads();
-  if (s_flag == 0u) return;
-  __threadfence();
-  if (col_ok) {
-    const float4* base = reinterpret_cast<const float4*>(ws.grp_part);
-    float4 sb = make_float4(0.f, 0.f, 0.f, 0.f), sq = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 8
-    for (int c = 0; c < ngroups; ++c) {
-      const float4 a = __ldcg(base + size_t(c) * 2 * N4 + tid), q = __ldcg(base + size_t(c) * 2 * N4 + N4 + tid);
-      sb.x += a.x; sb.y += a.y; sb.z += a.z; sb.w += a.w; sq.x += q.x; sq.y += q.y; sq.z += q.z; sq.w += q.w;
+    {
+      const float s = warp_sum(dot4(cbar, cbar));
+      if (lane == 0) part[2 * J * nw + warp] = s;
     }
-    if (db_accum) reinterpret_cast<float4*>(db_accum)[tid] = sb;
-    if (dq_accum) reinterpret_cast<float4*>(dq_accum)[tid] = sq;
-  }
-  if (loss_out || viol_out) {                           // the batch loss / violation count, fixed order (as last_cta_loss_reduce)
-    float a = 0.f, c = 0.f;
-    for (int i = tid; i < p.B; i += T) { a += __ldcg(item_loss + i); c += __ldcg(item_viol + i); }
-    a = warp_sum(a); c = warp_sum(c);
-    if ((tid & 31) == 0) { red[tid >> 5] = a; red[32 + (tid >> 5)] = c; }
+    for (int j0 = 0; j0 < J; j0 += kWideBatch) {
+      float v[2 * kWideBatch];
+      {
+        float4 x[kWideBatch];
+#pragma unroll
+        for (int r = 0; r < kWideBatch; ++r) {
+          const int j = j0 + r;
+          const int row = (j == 0) ? 0 : p.C + j - 1;
+          x[r] = (j < J && col_ok) ? ld4_keep(hp + size_t(row) * rs) : zero4;
+        }
+#pragma unroll
+        for (int r = 0; r < kWideBatch; ++r) { v[2 * r] = dot4(x[r], x[r]); v[2 * r + 1] = dot4(cbar, x[r]); }
+      }
+      int e; bool ok;
+      warp_multi_sum<2 * kWideBatch>(v, lane, e, ok);        // same butterfly per value as warp_sum
+      if (ok && 2 * j0 + e < 2 * J) part[(2 * j0 + e) * nw + warp] = v[0];
+    }
+    __syncthreads();
+    for (int e = tid; e < 2 * J + 1; e += T) {
+      float s = 0.f;
+      for (int w = 0; w < nw; ++w) s += part[e * nw + w];
+      if (e < 2 * J) { if (e & 1) s_p[e >> 1] = s; else s_s[e >> 1] = s; }
+      else { sc[0] = s; sc[1] = sqrtf(s) + p.eps; }
+      // stats layout: [s_c, s_t, p_t, s_n1, p_n1, ...]
+      if (stats) stats[size_t(b) * p.stride + (e < 2 * J ? 1 + e : 0)] = s;
+    }
+    __syncthreads();
+    // ---- scores, hinge, loss terms (normalization_layer.cpp:36-59, max_margin_loss_layer.cpp:54-214), one thread per negative
+    const float nc = sc[1];
+    const float score_t = s_p[0] / (nc * (sqrtf(s_s[0]) + p.eps));
+    for (int k = 1 + tid; k < J; k += T) {
+      const float sn = s_p[k] / (nc * (sqrtf(s_s[k]) + p.eps));
+      const float dlt = score_t - sn;                        // caffe_sub :69
+      const float h = fmaxf(0.f, p.margin - dlt);
+      // :149-192: L2 g = h * (lw*2/count); L1 g = [h>0] * lw/count
+      s_w[k] = (p.norm == 2) ? h * gscale : (h > 0.f ? gscale : 0.f);
+      s_l[k] = (p.norm == 2) ? h * h : fabsf(h);
+      s_v[k] = dlt < 0.f ? 1.f : 0.f;
+      if (tscore) tscore[size_t(b) * p.Nn + k - 1] = score_t;  // sum_true replicates to Nn columns
+      if (nscore) nscore[size_t(b) * p.Nn + k - 1] = sn;
+    }
     __syncthreads();
     if (tid == 0) {
-      a = 0.f; c = 0.f;
-      for (int w = 0; w < (T >> 5); ++w) { a += red[w]; c += red[32 + w]; }
-      if (loss_out) *loss_out = a * inv_count;
-      if (viol_out) *viol_out = c;
+      float g = 0.f, l = 0.f, vi = 0.f;                      // sum_layer.cpp:65-68 gemv over the Nn replicated columns
+      for (int k = 1; k < J; ++k) { g += s_w[k]; l += s_l[k]; vi += s_v[k]; }
+      s_w[0] = -g;                                           // d s+ = -1 * d s- (axpby, :210-212)
+      if (item_loss) item_loss[b] = l;
+      if (item_viol) item_viol[b] = vi;
     }
+    __syncthreads();
+    for (int j = tid; j < J; j += T) {
+      const float s = s_s[j], pj = s_p[j], w = s_w[j];
+      const float nj = sqrtf(s) + p.eps;
+      const float q = powf(s, 1.5f) + p.eps;                 // normalization_layer.cpp:101-107
+      const float aj = w * pj / nc;                          // a = <x, w c^>
+      cA[j] = s * w / (nc * q);                              // (s * w c^) / q, c^ = cbar / nc
+      cB[j] = -aj / q;
+      cE[j] = w / nj;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      float ac = 0.f;                                        // a_c = <cbar, d c^> = sum_j cE_j p_j (split order: true, neg_1..)
+      for (int j = 0; j < J; ++j) ac += cE[j] * s_p[j];
+      const float s = sc[0];
+      const float q = powf(s, 1.5f) + p.eps;
+      sc[2] = s / q; sc[3] = -ac / q;
+    }
+    // ================= phase 2: the rows again (L2), gradients out =================
+    // the NEXT item's rows on their way into L2 meanwhile (one bulk prefetch per row, thread r takes row r)
+    if (prefetch_next && b + int(gridDim.x) < p.B && (p.N & 3) == 0) {
+      for (int r = tid; r < p.C + p.Nn; r += T) {
+        const float* nx = H + size_t(r) * rs + size_t(b + gridDim.x) * p.N;
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(nx), "r"(unsigned(p.N) * 4u) : "memory");
+      }
+    }
+    // target + negative rows: dx = cA*cbar + cB*x ; D += cE*x
+    float4 D = zero4;
+    for (int j0 = 0; j0 < J; j0 += kWideBatch) {
+      float4 x[kWideBatch];
+#pragma unroll
+      for (int r = 0; r < kWideBatch; ++r) {
+        const int j = j0 + r;
+        const int row = (j == 0) ? 0 : p.C + j - 1;
+        x[r] = (j < J && col_ok) ? ld4_last_use(hp + size_t(row) * rs) : zero4;
+      }
+#pragma unroll
+      for (int r = 0; r < kWideBatch; ++r) {
+        const int j = j0 + r;
+        if (j < J && col_ok) {
+          const int row = (j == 0) ? 0 : p.C + j - 1;
+          const float a = cA[j], bb = cB[j], e = cE[j];
+          const float dl = delta ? delta[size_t(row) * p.B + b] : 0.f;
+          const float4 xv = x[r];
+          float4 o;
+          o.x = fmaf(a, cbar.x, bb * xv.x); o.y = fmaf(a, cbar.y, bb * xv.y);
+          o.z = fmaf(a, cbar.z, bb * xv.z); o.w = fmaf(a, cbar.w, bb * xv.w);
+          D.x = fmaf(e, xv.x, D.x); D.y = fmaf(e, xv.y, D.y); D.z = fmaf(e, xv.z, D.z); D.w = fmaf(e, xv.w, D.w);
+          if (act_fused) {   // dZ = dH * mask*scale * [Z>0]  <=>  dH * scale * [H>0]
+            o.x = xv.x > 0.f ? o.x * dscale : 0.f; o.y = xv.y > 0.f ? o.y * dscale : 0.f;
+            o.z = xv.z > 0.f ? o.z * dscale : 0.f; o.w = xv.w > 0.f ? o.w * dscale : 0.f;
+          }
+          dbacc.x += o.x; dbacc.y += o.y; dbacc.z += o.z; dbacc.w += o.w;
+          dqacc.x = fmaf(dl, o.x, dqacc.x); dqacc.y = fmaf(dl, o.y, dqacc.y);
+          dqacc.z = fmaf(dl, o.z, dqacc.z); dqacc.w = fmaf(dl, o.w, dqacc.w);
+          store_row4_t<OUT>(out, e0 + size_t(row) * rs, o, oscale, amax);
+        }
+      }
+    }
+    __syncthreads();   // sc[2], sc[3] visible
+    // context rows: d cbar = (s_c * d c^ - cbar * a_c) / q_c ; d c_i = coeff_i * d cbar
+    const float Fs = sc[2], Fc = sc[3];
+    float4 dcb;
+    dcb.x = fmaf(Fs, D.x, Fc * cbar.x); dcb.y = fmaf(Fs, D.y, Fc * cbar.y);
+    dcb.z = fmaf(Fs, D.z, Fc * cbar.z); dcb.w = fmaf(Fs, D.w, Fc * cbar.w);
+    for (int i0 = 1; i0 < p.C; i0 += kWideBatch) {
+      float4 x[kWideBatch];
+      if (act_fused) {       // the ReLU / dropout gate of these rows
+#pragma unroll
+        for (int r = 0; r < kWideBatch; ++r) x[r] = (i0 + r < p.C && col_ok) ? ld4_last_use(hp + size_t(i0 + r) * rs) : zero4;
+      }
+#pragma unroll
+      for (int r = 0; r < kWideBatch; ++r) {
+        const int i = i0 + r;
+        if (i < p.C && col_ok) {
+          const float a = p.coeff[i - 1];
+          float4 o = make_float4(a * dcb.x, a * dcb.y, a * dcb.z, a * dcb.w);
+          if (act_fused) {
+            const float4 xv = x[r];
+            o.x = xv.x > 0.f ? o.x * dscale : 0.f; o.y = xv.y > 0.f ? o.y * dscale : 0.f;
+            o.z = xv.z > 0.f ? o.z * dscale : 0.f; o.w = xv.w > 0.f ? o.w * dscale : 0.f;
+          }
+          dbacc.x += o.x; dbacc.y += o.y; dbacc.z += o.z; dbacc.w += o.w;
+          store_row4_t<OUT>(out, e0 + size_t(i) * rs, o, oscale, amax);
+        }
+      }
+    }
+    __syncthreads();   // shared-memory coefficients are rewritten by the next item
   }
+  if (out.prec == VV_PREC_F16X3) f16_publish_absmax(out.hi, amax);
+  if (ws.tickets == nullptr) {
+    // no workspace: atomics (order-dependent rounding) into zeroed words, and the ticketed loss reduction
+    __shared__ float red[66];
+    if (col_ok) {
+      if (db_accum) {
+        atomicAdd(db_accum + tid * 4 + 0, dbacc.x); atomicAdd(db_accum + tid * 4 + 1, dbacc.y);
+        atomicAdd(db_accum + tid * 4 + 2, dbacc.z); atomicAdd(db_accum + tid * 4 + 3, dbacc.w);
+      }
+      if (dq_accum) {
+        atomicAdd(dq_accum + tid * 4 + 0, dqacc.x); atomicAdd(dq_accum + tid * 4 + 1, dqacc.y);
+        atomicAdd(dq_accum + tid * 4 + 2, dqacc.z); atomicAdd(dq_accum + tid * 4 + 3, dqacc.w);
+      }
+    }
+    if (done_counter) {
+      __syncthreads();
+      last_cta_loss_reduce<false>(done_counter, item_loss, item_viol, p.B, inv_count, loss_out, viol_out, red, tid, T);
+    }
+    return;
+  }
+  column_sums_finish(ws, p, dbacc, dqacc, col_ok, db_accum, dq_accum, item_loss, item_viol, inv_count, loss_out, viol_out, tid, T);
 }
 
 // ---- K2+K3 with the rows staged in shared memory by bulk async copies -----------------------------------------
@@ -1264,8 +1517,12 @@ extern "C" int vv_rank_loss_backward_ex(const float* H, const vv_rank_cfg_t* cfg
   return VV_OK;
 }
 
+// register-resident kernels: R <= 32 rows per item; wide kernel (two phases, second one out of L2): any R with Nn <= 255
+static bool rank_narrow(const vv_rank_cfg_t* cfg) { return cfg->C + cfg->Nn <= 32 && 1 + cfg->Nn <= 32; }
 extern "C" int vv_rank_loss_fused_supported(const vv_rank_cfg_t* cfg) {
-  return cfg && cfg->N % 4 == 0 && cfg->N <= 1024 && cfg->C + cfg->Nn <= 32 && 1 + cfg->Nn <= 32 && cfg->Nn >= 1 && cfg->C >= 2;
+  static const bool wide_on = [] { const char* e = getenv("VV_RANK_WIDE"); return !(e && atoi(e) == 0); }();
+  return cfg && cfg->N % 4 == 0 && cfg->N <= 1024 && cfg->Nn >= 1 && cfg->C >= 2 && cfg->C - 1 <= VV_MAX_CONTEXT &&
+         (rank_narrow(cfg) || (wide_on && cfg->Nn <= 255));
 }
 
 extern "C" int vv_rank_loss_fused(const float* H, const vv_rank_cfg_t* cfg, float loss_weight, int act_fused,
@@ -1304,7 +1561,7 @@ int vv::rank_loss_fused_counted(const float* H, const vv_rank_cfg_t* cfg, float 
   RankDev d; int T;
   int rc = make_dev(cfg, &d, &T);
   if (rc) return rc;
-  VV_REQUIRE(vv_rank_loss_fused_supported(cfg), "rank_loss_fused: needs N <= 1024, C + Nn <= 32 (use forward + backward)");
+  VV_REQUIRE(vv_rank_loss_fused_supported(cfg), "rank_loss_fused: needs N <= 1024 and Nn <= 255 (use forward + backward)");
   VV_REQUIRE(H, "H must be non-NULL");
   VV_REQUIRE(!(loss || violations) || (item_loss && item_viol), "loss/violations need item_loss and item_viol scratch [B]");
   BwdOut o; o.dZ = dZ; o.hi = nullptr; o.lo = nullptr; o.bf = nullptr; o.prec = VV_PREC_FP32_SIMT;
@@ -1327,6 +1584,41 @@ int vv::rank_loss_fused_counted(const float* H, const vv_rank_cfg_t* cfg, float 
                    (o.prec == VV_PREC_F16X3 ? 8 : 0);
   unsigned int* cnt = (loss || violations) ? done_counter : nullptr;       // fold the batch reduction into the kernel
   const float inv_count = 1.f / float(d.B * d.Nn);
+  if (!rank_narrow(cfg)) {
+    // wide items: one launch, two phases per item (rank_wide_kernel)
+    static const int wocc = [] { const char* e = getenv("VV_RANK_WIDE_CTAS"); const int v = e ? atoi(e) : 2; return v < 2 ? 2 : (v > 4 ? 4 : v); }();
+    static const int wpf = [] { const char* e = getenv("VV_RANK_WIDE_PREFETCH"); return e ? atoi(e) : 0; }();
+    const int wgrid = d.B < num_sms() * wocc ? d.B : num_sms() * wocc;
+    const size_t wsmem = sizeof(float) * ((2 * J + 1) * nw + 8 * J + 4);
+    RankWs ws; ws.tickets = nullptr; ws.cta_part = nullptr; ws.grp_part = nullptr;
+    if (workspace && (loss || violations ? (item_loss && item_viol) : true)) {
+      const size_t groups = (size_t(wgrid) + kRankGroup - 1) / kRankGroup;
+      const size_t need = 1024 + (size_t(wgrid) + groups) * 2 * size_t(d.N) * sizeof(float);
+      VV_REQUIRE(workspace_bytes >= need && groups + 1 <= 256, "rank_loss_fused: workspace too small (%zu bytes, need %zu)", workspace_bytes, need);
+      ws.tickets = static_cast<unsigned int*>(workspace);
+      ws.cta_part = reinterpret_cast<float*>(static_cast<char*>(workspace) + 1024);
+      ws.grp_part = ws.cta_part + size_t(wgrid) * 2 * d.N;
+    }
+#define VV_RANK_WIDE(OUT)                                                                                              \
+    do {                                                                                                               \
+      if (wocc == 2) rank_wide_kernel<OUT, 2><<<wgrid, T, wsmem, stream>>>(H, d, gscale, act_fused, dropout_scale, o, db_accum, delta, dq_accum, \
+          stats, target_score, neg_score, item_loss, item_viol, ws, cnt, inv_count, loss, violations, wpf);            \
+      else if (wocc == 3) rank_wide_kernel<OUT, 3><<<wgrid, T, wsmem, stream>>>(H, d, gscale, act_fused, dropout_scale, o, db_accum, delta, dq_accum, \
+          stats, target_score, neg_score, item_loss, item_viol, ws, cnt, inv_count, loss, violations, wpf);            \
+      else rank_wide_kernel<OUT, 4><<<wgrid, T, wsmem, stream>>>(H, d, gscale, act_fused, dropout_scale, o, db_accum, delta, dq_accum, \
+          stats, target_score, neg_score, item_loss, item_viol, ws, cnt, inv_count, loss, violations, wpf);            \
+    } while (0)
+    if (mode == 8) VV_RANK_WIDE(8); else if (mode == 4) VV_RANK_WIDE(4); else if (mode == 2) VV_RANK_WIDE(2); else VV_RANK_WIDE(-1);
+#undef VV_RANK_WIDE
+    VV_LAUNCH_CHECK();
+    count_launch();
+    if ((loss || violations) && !cnt && !ws.tickets) {
+      rank_loss_reduce_kernel<<<1, 1024, 0, stream>>>(item_loss, item_viol, d.B, inv_count, loss, violations);
+      VV_LAUNCH_CHECK();
+      count_launch();
+    }
+    return VV_OK;
+  }
   if (rank_loss_fused_v2_applies(cfg, o.prec, o.dZ != nullptr, target_score || neg_score) && dZop_hi) {
     static const int occ_env = [] { const char* e = getenv("VV_RANK2_CTAS"); const int v = e ? atoi(e) : 4; return v < 4 ? 4 : (v > 6 ? 6 : v); }();
     const bool hot = (T == d.N4 && T == 128 && d.C == 5 && d.Nn == 10);       // the occupancy variants exist for the shipped shape
