@@ -305,6 +305,17 @@ int vv_max_margin_forward(const float* s_true, const float* s_bogus, int count, 
                           float* hinge_tmp, float* loss, float* violations, vv_stream_t s);         /* max_margin_loss_layer.cpp:54-127 */
 int vv_max_margin_backward(const float* s_true, const float* s_bogus, int count, float margin, int norm,
                            float loss_weight, float* d_true, float* d_bogus, vv_stream_t s);        /* :130-214 */
+/* Per-element loss weights (the layer's optional third bottom, max_margin_loss_layer.cpp:18-39,79-97,150-186):
+ * `weights` [count] on the device, NULL = unweighted.  Forward term: sqrt(w)*h (L2) or w*h (L1); backward: w*h, and
+ * for L1 the sign step becomes w -- the reference's own asymmetry, kept.  With use_direct_weight the blob IS `weights`;
+ * otherwise it holds video ids and vv_id_to_weight maps them through the id_to_weight_file table (ids ascending; an id
+ * that is not in the table weighs 0, as std::map::operator[] gives the reference). */
+int vv_max_margin_forward_w(const float* s_true, const float* s_bogus, const float* weights, int count, float margin, int norm,
+                            float* hinge_tmp, float* loss, float* violations, vv_stream_t s);
+int vv_max_margin_backward_w(const float* s_true, const float* s_bogus, const float* weights, int count, float margin, int norm,
+                             float loss_weight, float* d_true, float* d_bogus, vv_stream_t s);
+int vv_id_to_weight(const float* video_ids, int count, const int* table_ids, const float* table_weights, int table_size,
+                    float* weights, vv_stream_t s);
 
 /* ------------------------------------------------------------------------- */
 /* Synthetic feature bank (benchmarks): value(row, col) = relu(approx N(0,1))   */

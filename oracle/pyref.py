@@ -80,6 +80,16 @@ def max_margin(s_true, s_bogus, margin=1.0, norm=1, loss_weight=1.0):
     return float(loss[0]), float(viol[0]), dt, dbg
 
 
+def max_margin_weighted(s_true, s_bogus, third, direct, id_to_weight_file="", margin=1.0, norm=1, loss_weight=1.0):
+    """The reference layer with its third bottom: per-element weights (direct) or video ids + an "id,weight" file."""
+    a, b, c = f32(s_true), f32(s_bogus), f32(third)
+    loss = np.zeros(1, np.float32); viol = np.zeros(1, np.float32); dt = np.empty_like(a); dbg = np.empty_like(a)
+    assert lib().ref_max_margin_w(a.shape[0], a.size // a.shape[0], _p(a), _p(b), _p(c), int(bool(direct)),
+                                  id_to_weight_file.encode(), C.c_float(margin), norm, C.c_float(loss_weight),
+                                  _p(loss), _p(viol), _p(dt), _p(dbg)) == 0
+    return float(loss[0]), float(viol[0]), dt, dbg
+
+
 def inner_product(X, W, b, dZ, regularization=0.0):
     X, W, b, dZ = f32(X), f32(W), f32(b), f32(dZ)
     M, K = X.shape; N = W.shape[0]

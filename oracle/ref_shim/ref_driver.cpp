@@ -182,6 +182,33 @@ REF_API int ref_max_margin(int num, int ch, const float* s_true, const float* s_
     return 0;
   } catch (const std::exception& e) { fprintf(stderr, "ref_driver: %s\n", e.what()); return -1; }
 }
+// MaxMarginLossLayer with its optional third bottom (max_margin_loss_layer.cpp:18-39,79-97,150-186): `third` holds the
+// per-element weights (direct != 0) or video ids looked up in the "id,weight" file
+REF_API int ref_max_margin_w(int num, int ch, const float* s_true, const float* s_bogus, const float* third, int direct,
+                             const char* id_to_weight_file, float margin, int norm, float loss_weight,
+                             float* loss, float* viol, float* d_true, float* d_bogus) {
+  try {
+    Caffe::set_mode(Caffe::CPU);
+    Blob<float> a(num, ch, 1, 1), b(num, ch, 1, 1), c(num, ch, 1, 1), l, v;
+    memcpy(a.mutable_cpu_data(), s_true, sizeof(float) * num * ch);
+    memcpy(b.mutable_cpu_data(), s_bogus, sizeof(float) * num * ch);
+    memcpy(c.mutable_cpu_data(), third, sizeof(float) * num * ch);
+    LayerParameter p; p.add_loss_weight(loss_weight); p.add_loss_weight(0.f);
+    p.mutable_max_margin_loss_param()->set_margin(margin);
+    p.mutable_max_margin_loss_param()->set_norm(norm == 2 ? MaxMarginLossParameter_Norm_L2 : MaxMarginLossParameter_Norm_L1);
+    p.mutable_max_margin_loss_param()->set_use_direct_weight(direct != 0);
+    if (id_to_weight_file && *id_to_weight_file) p.mutable_max_margin_loss_param()->set_id_to_weight_file(id_to_weight_file);
+    MaxMarginLossLayer<float> layer(p);
+    BV bv{&a, &b, &c}, tv{&l, &v};
+    layer.SetUp(bv, &tv);
+    layer.Forward(bv, &tv);
+    *loss = l.cpu_data()[0]; *viol = v.cpu_data()[0];
+    layer.Backward(tv, {true, true, false}, &bv);
+    memcpy(d_true, a.cpu_diff(), sizeof(float) * num * ch);
+    memcpy(d_bogus, b.cpu_diff(), sizeof(float) * num * ch);
+    return 0;
+  } catch (const std::exception& e) { fprintf(stderr, "ref_driver: %s\n", e.what()); return -1; }
+}
 REF_API int ref_inner_product(int M, int N, int K, const float* X, const float* W, const float* bias, const float* dZ, float reg,
                       float* Z, float* dW, float* db, float* dX) {
   try {

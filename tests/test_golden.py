@@ -52,6 +52,27 @@ def test_oracle_reproduces_reference_layers(oracle):
     assert rel(Z, g["ip_Z"]) < 1e-6 and rel(dW, g["ip_dW"]) < 1e-6 and rel(db, g["ip_db"]) < 1e-6 and rel(dX, g["ip_dX"]) < 1e-6
 
 
+def mm_table_weights(g):
+    """id -> weight as the reference's map holds it: first line of an id wins, unknown ids weigh 0."""
+    table = {}
+    for i, w in zip(g["table_ids"], g["table_w"]):
+        table.setdefault(int(i), float(w))
+    return np.vectorize(lambda i: table.get(int(i), 0.0))(g["ids"]).astype(np.float32)
+
+
+def test_oracle_reproduces_reference_weighted_max_margin(oracle):
+    """MaxMarginLoss with its third bottom (per-video weights), both forms, against the compiled reference layer
+    (tests/golden/mm_weights.npz <- make_mm_weights_golden.py; ref: max_margin_loss_layer.cpp:18-39,79-97,150-186)."""
+    g = np.load(os.path.join(GOLD, "mm_weights.npz"))
+    margin, lw = float(g["margin"]), float(g["loss_weight"])
+    for form, w in (("direct", g["w"]), ("table", mm_table_weights(g))):
+        for norm in (1, 2):
+            loss, viol, _ = oracle.max_margin_forward(g["t"], g["s"], margin=margin, norm=norm, weights=w)
+            dt, dbg = oracle.max_margin_backward(g["t"], g["s"], margin=margin, norm=norm, loss_weight=lw, weights=w)
+            assert abs(loss - float(g["%s_loss%d" % (form, norm)])) < 1e-6 * max(1, loss) and viol == float(g["%s_viol%d" % (form, norm)])
+            assert rel(dt, g["%s_dt%d" % (form, norm)]) < 1e-6 and rel(dbg, g["%s_db%d" % (form, norm)]) < 1e-6
+
+
 def test_live_reference_agrees_with_fixtures_and_oracle(oracle):
     """Only where oracle/_ref was built (needs /root/reference at build time)."""
     from oracle import pyref

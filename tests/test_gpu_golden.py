@@ -61,6 +61,49 @@ def test_layer_kernels_reproduce_reference(vvlib):
         assert rel(H[:, :10], g["ip_Z"]) < tol
 
 
+def test_weighted_max_margin_reproduces_reference(vvlib, tmp_path):
+    """MaxMarginLoss with per-video weights (third bottom): the C-ABI kernels and the reference-interface layer
+    (MaxMarginLossLayer<float> of caffe_compat, built from a `layers { }` entry and driven like the reference's per-layer
+    tests) against the compiled reference layer's outputs -- tests/golden/mm_weights.npz, both forms: direct weights and
+    video ids through an id_to_weight_file (ref: max_margin_loss_layer.cpp:18-39,79-97,150-186)."""
+    from videovector_b200 import caffe_host
+    from videovector_b200.ops import _ptr, _stream
+    from videovector_b200._lib import check
+    g = np.load(os.path.join(GOLD, "mm_weights.npz"))
+    margin, lw = float(g["margin"]), float(g["loss_weight"])
+    t = torch.as_tensor(g["t"]).cuda(); s = torch.as_tensor(g["s"]).cuda()
+    count = t.numel()
+    # the table as the layer uploads it: ascending ids, first line of an id wins
+    table = {}
+    for i, w in zip(g["table_ids"], g["table_w"]):
+        table.setdefault(int(i), float(w))
+    tid = torch.as_tensor(np.array(sorted(table), np.int32)).cuda()
+    tw = torch.as_tensor(np.array([table[i] for i in sorted(table)], np.float32)).cuda()
+    w_table = torch.empty_like(t)
+    check(vvlib.vv_id_to_weight(_ptr(torch.as_tensor(g["ids"]).cuda()), count, _ptr(tid), _ptr(tw), tid.numel(), _ptr(w_table), _stream()))
+    assert (w_table[3] == 0).all()                                     # id 1000 is not in the table
+    path = tmp_path / "id2w.txt"
+    path.write_text("".join("%d,%.9g\n" % (int(i), float(w)) for i, w in zip(g["table_ids"], g["table_w"])))
+    caffe_host.set_device(0)
+    for form, w, third, extra in (("direct", torch.as_tensor(g["w"]).cuda(), g["w"], "use_direct_weight: true"),
+                                  ("table", w_table, g["ids"], 'id_to_weight_file: "%s"' % path)):
+        for norm in (1, 2):
+            hinge = torch.empty_like(t); loss = torch.zeros(1, device="cuda"); viol = torch.zeros(1, device="cuda")
+            dt = torch.empty_like(t); dbg = torch.empty_like(t)
+            check(vvlib.vv_max_margin_forward_w(_ptr(t), _ptr(s), _ptr(w), count, margin, norm, _ptr(hinge), _ptr(loss), _ptr(viol), _stream()))
+            check(vvlib.vv_max_margin_backward_w(_ptr(t), _ptr(s), _ptr(w), count, margin, norm, lw, _ptr(dt), _ptr(dbg), _stream()))
+            want = float(g["%s_loss%d" % (form, norm)])
+            assert abs(loss.item() - want) < 2e-6 * max(1, want) and viol.item() == float(g["%s_viol%d" % (form, norm)])
+            assert rel(dt, g["%s_dt%d" % (form, norm)]) < 1e-6 and rel(dbg, g["%s_db%d" % (form, norm)]) < 1e-6
+            # the layer, through the reference's interface
+            text = ('layers { name: "loss" type: MAX_MARGIN_LOSS bottom: "t" bottom: "s" bottom: "v" top: "l" top: "nv" '
+                    'loss_weight: %g loss_weight: 0 max_margin_loss_param { norm: %s margin: %g %s } }' % (lw, "L2" if norm == 2 else "L1", margin, extra))
+            lval, tops, diffs = caffe_host.run_layer(text, [g["t"], g["s"], third], 2, propagate_down=[True, True, False])
+            assert abs(tops[0][0] - want) < 2e-6 * max(1, want) and tops[1][0] == float(g["%s_viol%d" % (form, norm)])
+            assert abs(lval - lw * want) < 2e-6 * max(1, want)
+            assert rel(diffs[0], g["%s_dt%d" % (form, norm)]) < 1e-6 and rel(diffs[1], g["%s_db%d" % (form, norm)]) < 1e-6 and diffs[2] is None
+
+
 def test_device_eval_kernels_reproduce_reference_fixtures():
     """vv_retrieval_stats / vv_id_lookup_* against the compiled reference's outputs (tests/golden/eval_layers.npz)."""
     import torch

@@ -104,6 +104,9 @@ SIGNATURES = {
     "vv_copy_strided": (_i, [_P, _i64, _P, _i64, _i64, _i64, _P]),
     "vv_max_margin_forward": (_i, [_P, _P, _i, _f, _i, _P, _P, _P, _P]),
     "vv_max_margin_backward": (_i, [_P, _P, _i, _f, _i, _f, _P, _P, _P]),
+    "vv_max_margin_forward_w": (_i, [_P, _P, _P, _i, _f, _i, _P, _P, _P, _P]),
+    "vv_max_margin_backward_w": (_i, [_P, _P, _P, _i, _f, _i, _f, _P, _P, _P]),
+    "vv_id_to_weight": (_i, [_P, _i, _P, _P, _i, _P, _P]),
     "vv_fill_bank": (_i, [_P, _i64, _i, _u64, _P]),
     "vv_bank_value_host": (_f, [_u64, _i64, _i, _i]),
     "vv_id_lookup_forward": (_i, [_P, _i, _i, _P, _i, _P, _P]),

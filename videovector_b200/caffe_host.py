@@ -81,6 +81,35 @@ def set_precision(prec):
     _l().vvc_set_precision(PREC[prec] if isinstance(prec, str) else prec)
 
 
+def run_layer(layer_prototxt, bottoms, n_top, propagate_down=None, top_diffs=None, cap=1 << 20):
+    """One layer by itself, as the reference's per-layer tests drive it (src/caffe/test/test_*_layer.cpp): `bottoms` are
+    float32 arrays with up to 4 dims (num, channels, height, width), `layer_prototxt` a `layers { ... }` entry.
+    Returns (loss, [top data], [bottom diff or None])."""
+    lib = _l()
+    nb = len(bottoms)
+    arrs = [np.ascontiguousarray(b, np.float32) for b in bottoms]
+    shapes = (C.c_int * (4 * nb))(*[d for a in arrs for d in (list(a.shape) + [1, 1, 1, 1])[:4]])
+    bptr = (_P * nb)(*[a.ctypes.data for a in arrs])
+    tops = [np.zeros(cap, np.float32) for _ in range(n_top)]
+    tptr = (_P * n_top)(*[t.ctypes.data for t in tops])
+    counts = (C.c_int * n_top)()
+    tdiff = None
+    if top_diffs is not None:
+        td = [None if d is None else np.ascontiguousarray(d, np.float32) for d in top_diffs]
+        tdiff = (_P * n_top)(*[None if d is None else d.ctypes.data for d in td])
+    pd = bd = None
+    bdiffs = [None] * nb
+    if propagate_down is not None:
+        pd = (C.c_int * nb)(*[int(bool(x)) for x in propagate_down])
+        bdiffs = [np.zeros(a.size, np.float32) if propagate_down[i] else None for i, a in enumerate(arrs)]
+        bd = (_P * nb)(*[None if d is None else d.ctypes.data for d in bdiffs])
+    loss = C.c_float(0)
+    lib.vvc_layer_run.argtypes = [C.c_char_p, C.c_int, _P, _P, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P]
+    _check(lib.vvc_layer_run(layer_prototxt.encode(), nb, shapes, bptr, n_top, cap, tptr, counts, tdiff, pd, bd, C.byref(loss)))
+    return (loss.value, [t[:counts[i]].copy() for i, t in enumerate(tops)],
+            [None if d is None else d.reshape(arrs[i].shape) for i, d in enumerate(bdiffs)])
+
+
 def transform_net(prototxt, phase="TRAIN"):
     """FilterNet(phase) + InsertSplits on prototxt text (host only, no GPU needed)."""
     buf = C.create_string_buffer(1 << 22)

@@ -197,8 +197,12 @@ class MaxMarginLossLayer : public Layer<Dtype> {
  protected:
   virtual void Forward_gpu(const vector<Blob<Dtype>*>& bottom, vector<Blob<Dtype>*>* top);
   virtual void Backward_gpu(const vector<Blob<Dtype>*>& top, const vector<bool>& propagate_down, vector<Blob<Dtype>*>* bottom);
+  const Dtype* Weights(const vector<Blob<Dtype>*>& bottom);
   float margin_;
+  bool use_direct_weight_ = false;
+  int table_size_ = 0;
   Blob<Dtype> scratch_;   // loss, violations on the device
+  Blob<Dtype> table_ids_, table_w_, weights_;   // id_to_weight_file (ids as raw ints, ascending) and the looked-up weights
 };
 // ref: data_layers.hpp:223-286, video_sampled_shots_data_layer.cpp.  The DB reader is out of scope (no lmdb
 // here): `source` is "synthetic://videos=V&shots=S&dim=K&seed=s", a resident feature bank filled on the

@@ -28,6 +28,50 @@ int vvc_transform_net(const char* prototxt_text, int phase, char* out, int out_l
         memcpy(out, s.c_str(), s.size() + 1); return int(s.size());)
 }
 
+// One layer by itself, the way the reference's per-layer tests drive a layer (src/caffe/test/test_*_layer.cpp): bottoms
+// filled from host arrays, SetUp, Forward, Backward.  net_text: a NetParameter with one `layers { }` entry.
+// bottom_shapes: 4 ints per bottom; top_data / bottom_diff: host buffers of at least `cap` floats each (entries may be
+// NULL); top_diff: what to seed the top diffs with before Backward (NULL: what SetUp left there, i.e. the loss weights).
+int vvc_layer_run(const char* net_text, int n_bottom, const int* bottom_shapes, const float* const* bottom_data, int n_top,
+                  int cap, float* const* top_data, int* top_counts, const float* const* top_diff, const int* propagate_down,
+                  float* const* bottom_diff, float* loss) {
+  try {
+    const NetParameter np(ParseTextFormat(net_text));
+    CHECK_EQ(np.layers_size(), 1) << "vvc_layer_run takes exactly one layer";
+    shared_ptr<Layer<float> > layer(GetLayer<float>(np.layers(0)));
+    vector<shared_ptr<Blob<float> > > hold;
+    vector<Blob<float>*> bottom, top;
+    for (int i = 0; i < n_bottom; ++i) {
+      const int* sh = bottom_shapes + 4 * i;
+      hold.push_back(shared_ptr<Blob<float> >(new Blob<float>(sh[0], sh[1], sh[2], sh[3])));
+      memcpy(hold.back()->mutable_cpu_data(), bottom_data[i], sizeof(float) * hold.back()->count());
+      bottom.push_back(hold.back().get());
+    }
+    for (int i = 0; i < n_top; ++i) { hold.push_back(shared_ptr<Blob<float> >(new Blob<float>())); top.push_back(hold.back().get()); }
+    layer->SetUp(bottom, &top);
+    const float l = layer->Forward(bottom, &top);
+    if (loss) *loss = l;
+    for (int i = 0; i < n_top; ++i) {
+      CHECK_LE(top[i]->count(), cap) << "top " << i << " does not fit the output buffer";
+      if (top_counts) top_counts[i] = top[i]->count();
+      if (top_data && top_data[i]) memcpy(top_data[i], top[i]->cpu_data(), sizeof(float) * top[i]->count());
+      if (top_diff && top_diff[i]) memcpy(top[i]->mutable_cpu_diff(), top_diff[i], sizeof(float) * top[i]->count());
+    }
+    if (propagate_down) {
+      vector<bool> pd(n_bottom);
+      for (int i = 0; i < n_bottom; ++i) pd[i] = propagate_down[i] != 0;
+      layer->Backward(top, pd, &bottom);
+      for (int i = 0; i < n_bottom; ++i) {
+        if (!(bottom_diff && bottom_diff[i] && pd[i])) continue;
+        CHECK_LE(bottom[i]->count(), cap) << "bottom " << i << " does not fit the output buffer";
+        memcpy(bottom_diff[i], bottom[i]->cpu_diff(), sizeof(float) * bottom[i]->count());
+      }
+    }
+    cudaDeviceSynchronize();
+    return 0;
+  } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+
 void* vvc_net_create(const char* prototxt_text, int phase) {
   GUARDP(return new Net<float>(NetParameter(ParseTextFormat(prototxt_text)), phase == 1 ? Caffe::TEST : Caffe::TRAIN);)
 }

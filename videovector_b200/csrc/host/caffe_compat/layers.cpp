@@ -405,8 +405,36 @@ template <typename Dtype>
 void MaxMarginLossLayer<Dtype>::LayerSetUp(const vector<Blob<Dtype>*>& bottom, vector<Blob<Dtype>*>* top) {
   // LossLayer::LayerSetUp: a loss layer's first top has loss_weight 1 unless specified (ref: loss_layer.cpp:13-20)
   if (this->layer_param_.loss_weight_size() == 0) this->layer_param_.add_loss_weight(Dtype(1));
-  CHECK(this->layer_param_.max_margin_loss_param().id_to_weight_file() == "" && bottom.size() == 2)
-      << "per-video loss weights (3rd bottom / id_to_weight_file) are not used by the shipped net and not built for B200";
+  // per-video loss weights (ref: max_margin_loss_layer.cpp:18-39): "video_id,weight" lines; the table goes to the device
+  // sorted by id, the lookup runs there (vv_id_to_weight)
+  const string file = this->layer_param_.max_margin_loss_param().id_to_weight_file();
+  if (file != "") {
+    std::ifstream in(file.c_str());
+    std::map<int, float> table;
+    string line;
+    while (std::getline(in, line)) {
+      const size_t comma = line.find(',');
+      CHECK(comma != string::npos && line.find(',', comma + 1) == string::npos) << "Line: " << line;
+      char* end = nullptr;
+      const string a = line.substr(0, comma), b = line.substr(comma + 1);
+      const long id = strtol(a.c_str(), &end, 10);
+      CHECK(end == a.c_str() + a.size() && !a.empty()) << "Line: " << line;
+      const float w = strtof(b.c_str(), &end);
+      CHECK(end == b.c_str() + b.size() && !b.empty()) << "Line: " << line;
+      CHECK_GE(w, 0) << "All weights should be greater than 0";
+      table.insert(std::make_pair(int(id), w));            // first occurrence wins, as map::insert does
+    }
+    if (!table.empty()) {
+      table_ids_.Reshape(1, 1, 1, int(table.size())); table_w_.Reshape(1, 1, 1, int(table.size()));
+      // ids travel as raw ints inside a float blob's storage (never used as floats)
+      int* ids = reinterpret_cast<int*>(table_ids_.mutable_cpu_data());
+      float* ws = reinterpret_cast<float*>(table_w_.mutable_cpu_data());
+      size_t i = 0;
+      for (const auto& kv : table) { ids[i] = kv.first; ws[i] = kv.second; ++i; }
+    }
+    table_size_ = int(table.size());
+  }
+  use_direct_weight_ = this->layer_param_.max_margin_loss_param().use_direct_weight();
   margin_ = this->layer_param_.max_margin_loss_param().margin();
 }
 template <typename Dtype>
@@ -416,15 +444,29 @@ void MaxMarginLossLayer<Dtype>::Reshape(const vector<Blob<Dtype>*>& bottom, vect
   (*top)[0]->Reshape(1, 1, 1, 1);
   if (top->size() >= 2) (*top)[1]->Reshape(1, 1, 1, 1);
   scratch_.Reshape(1, 1, 1, 2);
+  if (bottom.size() == 3) {
+    CHECK_EQ(bottom[2]->count(), bottom[0]->count()) << "one weight / video id per score";
+    if (!use_direct_weight_) weights_.Reshape(1, 1, 1, bottom[0]->count());
+  }
+}
+// the third bottom as per-element weights: itself (use_direct_weight) or its video ids through the table
+template <typename Dtype>
+const Dtype* MaxMarginLossLayer<Dtype>::Weights(const vector<Blob<Dtype>*>& bottom) {
+  if (bottom.size() != 3) return nullptr;
+  if (use_direct_weight_) return bottom[2]->gpu_data();
+  VV_CHECK(vv_id_to_weight(bottom[2]->gpu_data(), bottom[2]->count(),
+                           table_size_ ? reinterpret_cast<const int*>(table_ids_.gpu_data()) : nullptr,
+                           table_size_ ? table_w_.gpu_data() : nullptr, table_size_, weights_.mutable_gpu_data(), Caffe::stream()));
+  return weights_.gpu_data();
 }
 template <typename Dtype>
 void MaxMarginLossLayer<Dtype>::Forward_gpu(const vector<Blob<Dtype>*>& bottom, vector<Blob<Dtype>*>* top) {
   const int count = bottom[0]->count();
   const int norm = this->layer_param_.max_margin_loss_param().norm() == MaxMarginLossParameter_Norm_L2 ? 2 : 1;
   // the reference uses bottom[0].diff as the hinge scratch (max_margin_loss_layer.cpp:62-69); kept for blob parity
-  VV_CHECK(vv_max_margin_forward(bottom[0]->gpu_data(), bottom[1]->gpu_data(), count, margin_, norm,
-                                 bottom[0]->mutable_gpu_diff(), (*top)[0]->mutable_gpu_data(),
-                                 top->size() > 1 ? (*top)[1]->mutable_gpu_data() : scratch_.mutable_gpu_data() + 1, Caffe::stream()));
+  VV_CHECK(vv_max_margin_forward_w(bottom[0]->gpu_data(), bottom[1]->gpu_data(), Weights(bottom), count, margin_, norm,
+                                   bottom[0]->mutable_gpu_diff(), (*top)[0]->mutable_gpu_data(),
+                                   top->size() > 1 ? (*top)[1]->mutable_gpu_data() : scratch_.mutable_gpu_data() + 1, Caffe::stream()));
 }
 template <typename Dtype>
 void MaxMarginLossLayer<Dtype>::Backward_gpu(const vector<Blob<Dtype>*>& top, const vector<bool>& propagate_down, vector<Blob<Dtype>*>* bottom) {
@@ -432,9 +474,9 @@ void MaxMarginLossLayer<Dtype>::Backward_gpu(const vector<Blob<Dtype>*>& top, co
   const int count = (*bottom)[0]->count();
   const int norm = this->layer_param_.max_margin_loss_param().norm() == MaxMarginLossParameter_Norm_L2 ? 2 : 1;
   const Dtype loss_weight = top[0]->cpu_diff()[0];
-  VV_CHECK(vv_max_margin_backward((*bottom)[0]->gpu_data(), (*bottom)[1]->gpu_data(), count, margin_, norm, loss_weight,
-                                  propagate_down[0] ? (*bottom)[0]->mutable_gpu_diff() : nullptr,
-                                  (*bottom)[1]->mutable_gpu_diff(), Caffe::stream()));
+  VV_CHECK(vv_max_margin_backward_w((*bottom)[0]->gpu_data(), (*bottom)[1]->gpu_data(), Weights(*bottom), count, margin_, norm, loss_weight,
+                                    propagate_down[0] ? (*bottom)[0]->mutable_gpu_diff() : nullptr,
+                                    (*bottom)[1]->mutable_gpu_diff(), Caffe::stream()));
 }
 
 // =================================== VideoSampledShotsData ===================================

@@ -401,15 +401,18 @@ __global__ void rowsum_bwd_kernel(const float* dy, int num, int dim, int nout, f
 __global__ void copy_strided_kernel(const float* src, long long ss, float* dst, long long ds, long long rows, long long cols) {
   GS_LOOP(i, rows * cols) { const long long r = i / cols, c = i - r * cols; dst[r * ds + c] = src[r * ss + c]; }
 }
-// single block: hinge terms, loss, violations (max_margin_loss_layer.cpp:54-127)
+// single block: hinge terms, loss, violations (max_margin_loss_layer.cpp:54-127).  w: optional per-element weights (the
+// layer's third bottom with use_direct_weight, or video ids mapped through id_to_weight_file): the forward term is
+// sqrt(w) * h for L2 and w * h for L1 (:84-97)
 __global__ void __launch_bounds__(1024)
-max_margin_fwd_kernel(const float* st, const float* sb, int count, float margin, int norm, float* hinge, float* loss, float* viol) {
+max_margin_fwd_kernel(const float* st, const float* sb, const float* w, int count, float margin, int norm, float* hinge, float* loss, float* viol) {
   __shared__ float s1[32], s2[32];
   float a = 0.f, v = 0.f;
   for (int i = threadIdx.x; i < count; i += blockDim.x) {
     const float d = st[i] - sb[i];
     if (d < 0.f) v += 1.f;
-    const float h = fmaxf(0.f, margin - d);
+    float h = fmaxf(0.f, margin - d);
+    if (w) h = (norm == 2 ? sqrtf(w[i]) : w[i]) * h;
     if (hinge) hinge[i] = h;
     a += (norm == 2) ? h * h : fabsf(h);
   }
@@ -422,12 +425,26 @@ max_margin_fwd_kernel(const float* st, const float* sb, int count, float margin,
     if (threadIdx.x == 0) { if (loss) *loss = a / count; if (viol) *viol = v; }
   }
 }
-__global__ void max_margin_bwd_kernel(const float* st, const float* sb, int count, float margin, int norm, float gs, float* dt, float* dbg) {
+// :130-214.  Weighted: t = w * h (NOT sqrt(w): the reference's forward / backward asymmetry, :154); L2 g = t * lw*2/count,
+// L1 g = [t > 0] * w * lw/count (:178-184)
+__global__ void max_margin_bwd_kernel(const float* st, const float* sb, const float* w, int count, float margin, int norm, float gs, float* dt, float* dbg) {
   GS_LOOP(i, count) {
-    const float h = fmaxf(0.f, margin - (st[i] - sb[i]));
-    const float g = (norm == 2) ? h * gs : (h > 0.f ? gs : 0.f);
+    float h = fmaxf(0.f, margin - (st[i] - sb[i]));
+    const float wi = w ? w[i] : 1.f;
+    if (w) h = wi * h;
+    const float g = (norm == 2) ? h * gs : (h > 0.f ? wi * gs : 0.f);
     if (dbg) dbg[i] = g;
     if (dt) dt[i] = -1.f * g;
+  }
+}
+// weight of element i = table[video id], ids as floats (the blob's type); ids absent from the table weigh 0, as the
+// reference's std::map::operator[] default-inserts (:93-95).  table_ids ascending.
+__global__ void id_to_weight_kernel(const float* ids, int count, const int* table_ids, const float* table_w, int n, float* out) {
+  GS_LOOP(i, count) {
+    const int id = static_cast<int>(ids[i]);
+    int lo = 0, hi = n;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (table_ids[mid] < id) lo = mid + 1; else hi = mid; }
+    out[i] = (lo < n && table_ids[lo] == id) ? table_w[lo] : 0.f;
   }
 }
 
@@ -715,17 +732,30 @@ extern "C" int vv_copy_strided(const float* src, int64_t ss, float* dst, int64_t
   VV_REQUIRE(src && dst && rows > 0 && cols > 0, "copy_strided: bad arguments");
   VV_SIMPLE_LAUNCH(copy_strided_kernel, rows * cols, src, ss, dst, ds, rows, cols);
 }
-extern "C" int vv_max_margin_forward(const float* st, const float* sb, int count, float margin, int norm, float* hinge,
-                                     float* loss, float* viol, vv_stream_t s) {
+extern "C" int vv_max_margin_forward_w(const float* st, const float* sb, const float* weights, int count, float margin, int norm,
+                                       float* hinge, float* loss, float* viol, vv_stream_t s) {
   VV_REQUIRE(st && sb && count > 0 && (norm == 1 || norm == 2), "max_margin_forward: bad arguments");
-  max_margin_fwd_kernel<<<1, 1024, 0, s>>>(st, sb, count, margin, norm, hinge, loss, viol);
+  max_margin_fwd_kernel<<<1, 1024, 0, s>>>(st, sb, weights, count, margin, norm, hinge, loss, viol);
   VV_LAUNCH_CHECK();
   count_launch();
   return VV_OK;
 }
-extern "C" int vv_max_margin_backward(const float* st, const float* sb, int count, float margin, int norm, float lw,
-                                      float* d_true, float* d_bogus, vv_stream_t s) {
+extern "C" int vv_max_margin_forward(const float* st, const float* sb, int count, float margin, int norm, float* hinge,
+                                     float* loss, float* viol, vv_stream_t s) {
+  return vv_max_margin_forward_w(st, sb, nullptr, count, margin, norm, hinge, loss, viol, s);
+}
+extern "C" int vv_max_margin_backward_w(const float* st, const float* sb, const float* weights, int count, float margin, int norm,
+                                        float lw, float* d_true, float* d_bogus, vv_stream_t s) {
   VV_REQUIRE(st && sb && count > 0 && (norm == 1 || norm == 2), "max_margin_backward: bad arguments");
   const float gs = (norm == 2) ? lw * 2 / count : lw / count;
-  VV_SIMPLE_LAUNCH(max_margin_bwd_kernel, count, st, sb, count, margin, norm, gs, d_true, d_bogus);
+  VV_SIMPLE_LAUNCH(max_margin_bwd_kernel, count, st, sb, weights, count, margin, norm, gs, d_true, d_bogus);
+}
+extern "C" int vv_max_margin_backward(const float* st, const float* sb, int count, float margin, int norm, float lw,
+                                      float* d_true, float* d_bogus, vv_stream_t s) {
+  return vv_max_margin_backward_w(st, sb, nullptr, count, margin, norm, lw, d_true, d_bogus, s);
+}
+extern "C" int vv_id_to_weight(const float* ids, int count, const int* table_ids, const float* table_w, int table_size,
+                               float* weights, vv_stream_t s) {
+  VV_REQUIRE(ids && weights && count > 0 && table_size >= 0 && (table_size == 0 || (table_ids && table_w)), "id_to_weight: bad arguments");
+  VV_SIMPLE_LAUNCH(id_to_weight_kernel, count, ids, count, table_ids, table_w, table_size, weights);
 }
