@@ -77,7 +77,9 @@ struct Cfg {
   // issues MMAs; the peer's TMA credits its bytes to the leader's full barrier, its gather producers complete on a local
   // barrier that the peer's (otherwise idle) MMA warp relays to the leader.  Built for the gathered forward (K-major, 2-byte).
   static constexpr bool two_cta = kTwoCta;
-  static_assert(!kTwoCta || (kGather && !kAMN && !kBMN && !kTF32 && kFwdEpi && (kNProd == 1 || kF16)), "cta_group::2 variant: gathered forward only");
+  static_assert(!kTwoCta || (kGather && !kTF32 && (kNProd == 1 || kF16) &&
+                             ((!kAMN && !kBMN && kFwdEpi) || (kAMN && kBMN && kTransOut && !kFwdEpi))),
+                "cta_group::2 variant: the gathered forward and the gathered (transposed) weight gradient");
   static constexpr bool f16 = kF16;                    // fp16 elements (kind::f16 with F16 formats) instead of bf16
   static_assert(!(kF16 && kTF32), "f16 and tf32 exclude each other");
   // kGather: operand A (X: the rows of FWD, the k-rows of WGRAD_T) is gathered row-wise from the bank's operand copy by
@@ -321,8 +323,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             // this CTA's half of the W tile (rows n0 + 128 * rank), into its own smem; the bytes of both CTAs complete on the
             // leader's barrier, which the leader arms for the pair
             if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * kTmaBytes);
-            tma_load_2d_2cta(sb, &tmB_hi, &full_bar[stage], k0, n0 + cta_rank * (C::block_n / 2));
-            if (C::split16) tma_load_2d_2cta(sb + C::b_bytes, &tmB_hb, &full_bar[stage], k0, n0 + cta_rank * (C::block_n / 2));
+            if (!C::b_mn) {
+              tma_load_2d_2cta(sb, &tmB_hi, &full_bar[stage], k0, n0 + cta_rank * (C::block_n / 2));
+              if (C::split16) tma_load_2d_2cta(sb + C::b_bytes, &tmB_hb, &full_bar[stage], k0, n0 + cta_rank * (C::block_n / 2));
+            } else {
+              // MN-major B (the weight gradient's dZ tile): this CTA's half = kHalf chunks of [bk k-rows x 128 B of n]
+              constexpr int kHalf = C::block_n / C::chunk / 2;
+#pragma unroll
+              for (int c = 0; c < kHalf; ++c) {
+                tma_load_2d_2cta(sb + c * (C::bk * kRowBytes), &tmB_hi, &full_bar[stage], n0 + (cta_rank * kHalf + c) * C::chunk, k0);
+                if (C::split16) tma_load_2d_2cta(sb + C::b_bytes + c * (C::bk * kRowBytes), &tmB_hb, &full_bar[stage],
+                                                 n0 + (cta_rank * kHalf + c) * C::chunk, k0);
+              }
+            }
             if (++stage == C::stages) { stage = 0; phase ^= 1u; }
             continue;
           }
@@ -600,7 +613,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
               if (kPlanes == 2) cp_async16_l2_256(dst + C::a_bytes, src + h1d, nb);
             }
           }
-          cp_async_mbar_arrive_noinc(&full_bar[stage]);
+          cp_async_mbar_arrive_noinc((C::two_cta && cta_rank != 0) ? &gfull_bar[stage] : &full_bar[stage]);
           if (++stage == C::stages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -999,6 +1012,13 @@ int gemm_tc_launch(const GemmProblem& g, cudaStream_t stream) {
   if (two_cta && gat && g.kind == GEMM_FWD && (g.N % 256) == 0) {
     if (g.prec == VV_PREC_BF16 && two_cta == 2) return launch_cfg<Cfg<false, false, false, 1, 256, 6, true, true, false, false, true>>(g, stream);
     if (g.prec == VV_PREC_F16X3)                return launch_cfg<Cfg<false, false, false, 3, 256, 3, true, true, true,  false, true>>(g, stream);
+  }
+  // cta_group::2 weight gradient (gathered, transposed).  Measured (profiles/r02_2cta_forward.md): f16x3 0.587-0.593 ms vs
+  // 0.610-0.620, bf16 0.308 vs 0.299 -- the default for f16x3 only, as for the forward.  VV_GEMM_2CTA_WGRAD=0 off, =1 bf16 too.
+  static const int two_cta_w = [] { const char* e = getenv("VV_GEMM_2CTA_WGRAD"); return e ? (atoi(e) != 0 ? 2 : 0) : 1; }();
+  if (two_cta_w && gat && g.kind == GEMM_WGRAD_T && (g.N % 256) == 0 && g.n0 == 0 && (g.ncols <= 0 || g.ncols == g.N)) {
+    if (g.prec == VV_PREC_BF16 && two_cta_w == 2) return launch_cfg<Cfg<false, true, true, 1, 256, 6, false, true, false, true, true>>(g, stream);
+    if (g.prec == VV_PREC_F16X3)                  return launch_cfg<Cfg<false, true, true, 3, 256, 3, false, true, true,  true, true>>(g, stream);
   }
   if (g.prec == VV_PREC_BF16) {
     switch (g.kind) {
