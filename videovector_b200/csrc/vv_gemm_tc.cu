@@ -257,7 +257,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   uint64_t* gfull_bar = tmem_empty + 2;            // cta_group::2, peer CTA: its gather producers' completion (relayed to the leader)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gfull_bar + C::stages);
 
+#if defined(VV_WARP_PLAIN)
   const int warp = threadIdx.x >> 5;
+#else
+  const int warp = __shfl_sync(0xffffffffu, int(threadIdx.x >> 5), 0);   // warp-uniform for the compiler: role branches do not diverge
+#endif
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -449,8 +453,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           mbar_arrive_cluster(&full_bar[lane], 0);
         }
       }
-    } else
-    if (lane == 0) {
+    } else {
+      // The whole warp runs this loop converged (every lane polls the barriers) and ONE elected lane issues the MMAs and
+      // commits: with warp-uniform control flow and operands the compiler keeps descriptors, addresses and predicates in
+      // uniform registers and feeds UTCHMMA directly.  Under `if (lane == 0)` every tcgen05.mma was wrapped in a
+      // vote / elect / 5 x R2UR waterfall and every descriptor was rebuilt from scratch: ~110 instructions per bf16
+      // k-block on a single thread, i.e. as long as the k-block's MMAs themselves (ncu: tensor pipe 59 % active).
       constexpr uint32_t idesc = make_idesc(C::tf32 ? 2 : (C::f16 ? 0 : 1), C::a_mn ? 1 : 0, C::b_mn ? 1 : 0,
                                             C::two_cta ? 2 * kBlockM : kBlockM, C::block_n);
       // K-major : rows of 128 B, 8-row atoms 1024 B apart (SBO); LBO unused (1)
@@ -465,6 +473,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       constexpr uint32_t lay_b = (C::tf32 && C::b_mn) ? kLayoutSw128Base32 : kLayoutSw128;
       constexpr uint32_t sbo_a = (C::tf32 && C::a_mn) ? 512 : 1024;
       constexpr uint32_t sbo_b = (C::tf32 && C::b_mn) ? 512 : 1024;
+      // shared-memory descriptors = constant high word | (constant LBO field + address / 16): one add per descriptor
+      // (the 14-bit address field cannot carry: shared memory ends below 256 KB).  The mask matters: in a cluster the
+      // shared-window address of the rank-1 CTA carries its rank in bit 24, which would land in the LBO field.
+      constexpr uint32_t dhi_a = ((sbo_a >> 4) & 0x3FFFu) | (1u << 14) | (lay_a << 29);
+      constexpr uint32_t dhi_b = ((sbo_b >> 4) & 0x3FFFu) | (1u << 14) | (lay_b << 29);
+      const uint32_t dlo_a = (((lbo_a >> 4) & 0x3FFFu) << 16) + ((smem_u32(smem) >> 4) & 0x3FFFu);
+      const uint32_t dlo_b = (((lbo_b >> 4) & 0x3FFFu) << 16) + ((smem_u32(smem) >> 4) & 0x3FFFu);
+      constexpr uint32_t kBOff = ((C::mixed || C::split16) ? 2 * C::a_bytes : C::a_bytes) >> 4;   // B tiles behind the A tiles, in 16-byte units
+#define VV_DESC(hi, lo) ((uint64_t(hi) << 32) | uint64_t(lo))
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int u = unit0; u < total_units; u += unit_stride) {
@@ -481,60 +498,67 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           const uint32_t d_tmem = tmem_base + uint32_t(acc * C::block_n);
           uint32_t accumulate = 0;
           for (int kb = c0; kb < c1; ++kb) {
-            if (C::two_cta) mbar_wait_cluster(&full_bar[stage], phase); else mbar_wait(&full_bar[stage], phase);
-            tc_fence_after();
-            if (C::gather) fence_proxy_async();     // A was written by cp.async (generic proxy); the MMA reads through the async proxy
-            const uint32_t sa = smem_u32(smem + stage * C::stage_bytes);
-            const uint32_t sb = sa + ((C::mixed || C::split16) ? 2 * C::a_bytes : C::a_bytes);
-            if (C::mixed) {
-              // cross terms first (small magnitude), on the bf16 pipe: bf16(a)*bf16(b_lo) + bf16(a_lo)*bf16(b)
-              constexpr uint32_t idesc16 = make_idesc(1, C::a_mn ? 1 : 0, C::b_mn ? 1 : 0, kBlockM, C::block_n);
-              constexpr uint32_t lay16_a = C::a_mn ? kLayoutSw128 : kLayoutSw64, lay16_b = C::b_mn ? kLayoutSw128 : kLayoutSw64;
-              constexpr uint32_t sbo16_a = C::a_mn ? 1024 : 512, sbo16_b = C::b_mn ? 1024 : 512;
-              constexpr uint32_t kadv16_a = C::a_mn ? 16 * kRowBytes : 32, kadv16_b = C::b_mn ? 16 * kRowBytes : 32;
-              const uint32_t a_hb = sa + C::a_bytes, a_lb = a_hb + C::a_half;
-              const uint32_t b_hb = sb + C::b_bytes, b_lb = b_hb + C::b_half;
+            // (cta_group::2: the peer's arrivals are release.cluster; the operands they announce are read by the tensor core
+            // through the async proxy, never through this SM's L1, so the default acquire is enough -- as in CUTLASS' pipelines)
+            mbar_wait(&full_bar[stage], phase);
+            if (elect_one()) {
+              if (C::gather) fence_proxy_async();     // A was written by cp.async (generic proxy); the MMA reads through the async proxy
+              uint32_t accf = accumulate;
+              const uint32_t so = uint32_t(stage) * uint32_t(C::stage_bytes >> 4);     // this stage, in 16-byte units
+              if (C::mixed) {
+                // cross terms first (small magnitude), on the bf16 pipe: bf16(a)*bf16(b_lo) + bf16(a_lo)*bf16(b)
+                const uint32_t sa = smem_u32(smem + stage * C::stage_bytes);
+                const uint32_t sb = sa + 2 * C::a_bytes;
+                constexpr uint32_t idesc16 = make_idesc(1, C::a_mn ? 1 : 0, C::b_mn ? 1 : 0, kBlockM, C::block_n);
+                constexpr uint32_t lay16_a = C::a_mn ? kLayoutSw128 : kLayoutSw64, lay16_b = C::b_mn ? kLayoutSw128 : kLayoutSw64;
+                constexpr uint32_t sbo16_a = C::a_mn ? 1024 : 512, sbo16_b = C::b_mn ? 1024 : 512;
+                constexpr uint32_t kadv16_a = C::a_mn ? 16 * kRowBytes : 32, kadv16_b = C::b_mn ? 16 * kRowBytes : 32;
+                const uint32_t a_hb = sa + C::a_bytes, a_lb = a_hb + C::a_half;
+                const uint32_t b_hb = sb + C::b_bytes, b_lb = b_hb + C::b_half;
 #pragma unroll
-              for (int k = 0; k < 2; ++k) {      // 32 reduction elements = 2 bf16 k-steps of 16
-                const uint64_t d_ahb = make_smem_desc(a_hb + k * kadv16_a, lbo_a, sbo16_a, lay16_a);
-                const uint64_t d_alb = make_smem_desc(a_lb + k * kadv16_a, lbo_a, sbo16_a, lay16_a);
-                const uint64_t d_bhb = make_smem_desc(b_hb + k * kadv16_b, lbo_b, sbo16_b, lay16_b);
-                const uint64_t d_blb = make_smem_desc(b_lb + k * kadv16_b, lbo_b, sbo16_b, lay16_b);
-                umma_ss<false>(d_tmem, d_alb, d_bhb, idesc16, accumulate);
-                umma_ss<false>(d_tmem, d_ahb, d_blb, idesc16, 1u);
-                accumulate = 1u;
+                for (int k = 0; k < 2; ++k) {      // 32 reduction elements = 2 bf16 k-steps of 16
+                  const uint64_t d_ahb = make_smem_desc(a_hb + k * kadv16_a, lbo_a, sbo16_a, lay16_a);
+                  const uint64_t d_alb = make_smem_desc(a_lb + k * kadv16_a, lbo_a, sbo16_a, lay16_a);
+                  const uint64_t d_bhb = make_smem_desc(b_hb + k * kadv16_b, lbo_b, sbo16_b, lay16_b);
+                  const uint64_t d_blb = make_smem_desc(b_lb + k * kadv16_b, lbo_b, sbo16_b, lay16_b);
+                  umma_ss<false>(d_tmem, d_alb, d_bhb, idesc16, accf);
+                  umma_ss<false>(d_tmem, d_ahb, d_blb, idesc16, 1u);
+                  accf = 1u;
+                }
+              }
+#pragma unroll
+              for (int k = 0; k < C::ksteps; ++k) {
+                const uint64_t a_hi = VV_DESC(dhi_a, dlo_a + so + uint32_t(k * kadv_a >> 4));
+                const uint64_t b_hi = VV_DESC(dhi_b, dlo_b + so + kBOff + uint32_t(k * kadv_b >> 4));
+                if (C::split16) {
+                  // cross terms first (small magnitude): h1*h0' + h0*h1', then h0*h0'
+                  const uint64_t a_h1 = VV_DESC(dhi_a, dlo_a + so + uint32_t((C::a_bytes + k * kadv_a) >> 4));
+                  const uint64_t b_h1 = VV_DESC(dhi_b, dlo_b + so + kBOff + uint32_t((C::b_bytes + k * kadv_b) >> 4));
+                  if (C::two_cta) { umma2_ss_f16(d_tmem, a_h1, b_hi, idesc, accf); umma2_ss_f16(d_tmem, a_hi, b_h1, idesc, 1u); }
+                  else { umma_ss<false>(d_tmem, a_h1, b_hi, idesc, accf); umma_ss<false>(d_tmem, a_hi, b_h1, idesc, 1u); }
+                  accf = 1u;
+                }
+                if (C::two_cta) umma2_ss_f16(d_tmem, a_hi, b_hi, idesc, accf);
+                else umma_ss<C::tf32>(d_tmem, a_hi, b_hi, idesc, accf);
+                accf = 1u;
+              }
+              // frees the smem stage when these MMAs retire -- in BOTH CTAs of a cluster (the peer multicasts into it)
+              if (C::two_cta) {
+                umma2_commit_mc(&empty_bar[stage], 0x3);
+                if (kb == c1 - 1) umma2_commit_mc(&tmem_full[acc], 0x3);        // the accumulator halves of both CTAs are ready
+              } else {
+                if (C::cluster > 1) umma_commit_mc(&empty_bar[stage], 0x3); else umma_commit(&empty_bar[stage]);
+                if (kb == c1 - 1) umma_commit(&tmem_full[acc]);
               }
             }
-#pragma unroll
-            for (int k = 0; k < C::ksteps; ++k) {
-              const uint64_t a_hi = make_smem_desc(sa + k * kadv_a, lbo_a, sbo_a, lay_a);
-              const uint64_t b_hi = make_smem_desc(sb + k * kadv_b, lbo_b, sbo_b, lay_b);
-              if (C::split16) {
-                // cross terms first (small magnitude): h1*h0' + h0*h1', then h0*h0'
-                const uint64_t a_h1 = make_smem_desc(sa + C::a_bytes + k * kadv_a, lbo_a, sbo_a, lay_a);
-                const uint64_t b_h1 = make_smem_desc(sb + C::b_bytes + k * kadv_b, lbo_b, sbo_b, lay_b);
-                if (C::two_cta) { umma2_ss_f16(d_tmem, a_h1, b_hi, idesc, accumulate); umma2_ss_f16(d_tmem, a_hi, b_h1, idesc, 1u); }
-                else { umma_ss<false>(d_tmem, a_h1, b_hi, idesc, accumulate); umma_ss<false>(d_tmem, a_hi, b_h1, idesc, 1u); }
-                accumulate = 1u;
-              }
-              if (C::two_cta) umma2_ss_f16(d_tmem, a_hi, b_hi, idesc, accumulate);
-              else umma_ss<C::tf32>(d_tmem, a_hi, b_hi, idesc, accumulate);
-              accumulate = 1u;
-            }
-            // frees the smem stage when these MMAs retire -- in BOTH CTAs of a cluster (the peer multicasts into it)
-            if (C::two_cta) {
-              umma2_commit_mc(&empty_bar[stage], 0x3);
-              if (kb == c1 - 1) umma2_commit_mc(&tmem_full[acc], 0x3);        // the accumulator halves of both CTAs are ready
-              if (++stage == C::stages) { stage = 0; phase ^= 1u; }
-              continue;
-            }
-            if (C::cluster > 1) umma_commit_mc(&empty_bar[stage], 0x3); else umma_commit(&empty_bar[stage]);
-            if (kb == c1 - 1) umma_commit(&tmem_full[acc]);
+            __syncwarp();
+            accumulate = 1u;
             if (++stage == C::stages) { stage = 0; phase ^= 1u; }
           }
           acc ^= 1; if (acc == 0) acc_phase ^= 1u;
         }
       }
+#undef VV_DESC
     }
   } else if (C::gather && (warp == 2 || warp == 3)) {
     // ===================== cp.async gather producers of operand A (2 warps) =====================
