@@ -3,7 +3,7 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 N=${1:-2}
-timeout -k 5 400 python -m pytest tests/test_gpu_dp.py -q -x --timeout 150 2>&1 | tail -4
+[ "$2" = nopytest ] || timeout -k 5 400 python -m pytest tests/test_gpu_dp.py -q -x --timeout 150 2>&1 | tail -4
 for mode in p2p nccl; do
   VV_DP_MODE=$mode VV_DP_TIMEOUT_MS=5000 timeout -k 5 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
     scripts/dp_check.py f16x3 2>&1 | grep -E "DP_CHECK|Error|error|Traceback" | tail -4 | tee -a gpurun_out/dp_check_${N}_b.log
