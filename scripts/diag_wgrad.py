@@ -1,3 +1,6 @@
+"""Bring-up probe for the weight-gradient GEMMs (materialised operands): relative error and, when it is large, the error per
+128 x 256 output tile, for every tensor-core precision at one tile, a few tiles and cfg-1's shape, with 1 and 2 split-K slabs.
+(Found the cluster-rank bit leaking into the MN-major descriptors' LBO field, DESIGN.md section 3, "The MMA issuer".)"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch

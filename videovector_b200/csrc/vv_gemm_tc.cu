@@ -257,11 +257,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   uint64_t* gfull_bar = tmem_empty + 2;            // cta_group::2, peer CTA: its gather producers' completion (relayed to the leader)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gfull_bar + C::stages);
 
-#if defined(VV_WARP_PLAIN)
-  const int warp = threadIdx.x >> 5;
-#else
   const int warp = __shfl_sync(0xffffffffu, int(threadIdx.x >> 5), 0);   // warp-uniform for the compiler: role branches do not diverge
-#endif
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
