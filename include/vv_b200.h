@@ -390,6 +390,23 @@ vv_sampler_t* vv_sampler_create_ex(int num_videos, const int32_t* video_id,
                                    int max_buffer_size, int negative_swap_percentage,
                                    int max_same_video_negs, int max_tries_for_negs,
                                    unsigned int rand_seed, int context_type);
+/* The data layer's two remaining options (video_sampled_shots_data_layer.cpp:104-153, 157-180, 253-284, 324-338):
+ *   start_skip  = rand_skip: the record cursor starts `start_skip` records in (wrapping).  The reference draws it as
+ *                 caffe_rng_rand() % rand_skip -- the first output of an mt19937 seeded with the Caffe seed -- the caller
+ *                 passes the value (the compat data layer computes it the same way);
+ *   neg_*       = negative_dataset: a second set of VideoShots records (same table layout) whose rows live at
+ *                 [neg_row_base, ...) of the resident bank.  The negative buffer then starts with EVERY shot of these
+ *                 records in order -- no rand() is drawn and the main cursor does not move -- and, as in the reference
+ *                 (unchecked copy + CHECK_EQ :346), max_buffer_size must be reached exactly at a record boundary
+ *                 (NULL otherwise).  Swaps during training still come from the main data.  neg_num_videos = 0: none. */
+vv_sampler_t* vv_sampler_create_ex2(int num_videos, const int32_t* video_id,
+                                    const int32_t* shot_off /*[V+1]*/, const int32_t* shot_ids,
+                                    int batch_size, int context_size, int num_negative_samples,
+                                    int max_buffer_size, int negative_swap_percentage,
+                                    int max_same_video_negs, int max_tries_for_negs,
+                                    unsigned int rand_seed, int context_type, int start_skip,
+                                    int neg_num_videos, const int32_t* neg_video_id,
+                                    const int32_t* neg_shot_off, const int32_t* neg_shot_ids, int32_t neg_row_base);
 void vv_sampler_destroy(vv_sampler_t* s);
 /* idx, quirk: host [B,R] int32 (see vv_gather_rows).  Returns 0 or <0. */
 int vv_sampler_next(vv_sampler_t* s, int32_t* idx, int32_t* quirk);

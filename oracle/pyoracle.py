@@ -50,6 +50,8 @@ def lib():
         _lib.orc_sampler_create.argtypes = [_i, _i, _P, _P, _P, _P, _i, _i, _i, _i, _i, _i, _i]
         _lib.orc_sampler_create_mode.restype = _P
         _lib.orc_sampler_create_mode.argtypes = [_i, _i, _P, _P, _P, _P, _i, _i, _i, _i, _i, _i, _i, _i]
+        _lib.orc_sampler_create_opts.restype = _P
+        _lib.orc_sampler_create_opts.argtypes = [_i, _i, _P, _P, _P, _P, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _P, _P, _P, _P, _i]
         _lib.orc_sampler_next.argtypes = [_P, _P, _P, _P]
         _lib.orc_sampler_destroy.argtypes = [_P]
         _lib.orc_sampler_cursor.argtypes = [_P]
@@ -238,16 +240,24 @@ class Sampler:
 
     def __init__(self, video_id, shot_off, shot_ids, feat, K, batch_size, context_size=5, num_negative_samples=10,
                  max_buffer_size=5000, negative_swap_percentage=50, max_same_video_negs=6, max_tries_for_negs=100,
-                 seed=1, context_type=1):
+                 seed=1, context_type=1, start_skip=0, negative_dataset=None):
+        """start_skip: the value of the data layer's rand_skip draw; negative_dataset: (video_id, shot_off, shot_ids, feat,
+        row_base) -- indices of its shots come out as row_base + position in that set."""
         self.video_id = np.ascontiguousarray(video_id, np.int32)
         self.shot_off = np.ascontiguousarray(shot_off, np.int32)
         self.shot_ids = np.ascontiguousarray(shot_ids, np.int32)
         self.feat = f32(feat) if feat is not None else None
         self.B, self.R, self.K = batch_size, context_size + num_negative_samples, K
         lib().orc_srand(seed)
-        self._h = lib().orc_sampler_create_mode(len(self.video_id), K, _p(self.video_id), _p(self.shot_off), _p(self.shot_ids),
+        nv, neg, nbase = 0, [None] * 4, 0
+        if negative_dataset is not None:
+            neg = [np.ascontiguousarray(a, np.int32) for a in negative_dataset[:3]] + [f32(negative_dataset[3]) if negative_dataset[3] is not None else None]
+            nv, nbase = len(neg[0]), int(negative_dataset[4])
+        self._neg = neg
+        self._h = lib().orc_sampler_create_opts(len(self.video_id), K, _p(self.video_id), _p(self.shot_off), _p(self.shot_ids),
                                                 _p(self.feat), batch_size, context_size, num_negative_samples, max_buffer_size,
-                                                negative_swap_percentage, max_same_video_negs, max_tries_for_negs, context_type)
+                                                negative_swap_percentage, max_same_video_negs, max_tries_for_negs, context_type,
+                                                int(start_skip), nv, _p(neg[0]), _p(neg[1]), _p(neg[2]), _p(neg[3]), nbase)
         if not self._h:
             raise RuntimeError("oracle sampler: could not fill the negative buffer")
 

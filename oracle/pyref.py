@@ -124,18 +124,28 @@ class Sampler:
     process-global libc rand() like the oracle's sampler does: run one of them to completion before the other."""
 
     def __init__(self, video_id, shot_off, shot_ids, feat, K, batch_size, context_size=5, num_negative_samples=10,
-                 max_buffer_size=5000, negative_swap_percentage=50, max_same_video_negs=6, seed=1, context_type=1):
+                 max_buffer_size=5000, negative_swap_percentage=50, max_same_video_negs=6, seed=1, context_type=1,
+                 rand_skip=0, caffe_seed=0, negative_dataset=None):
+        """rand_skip / caffe_seed: the layer draws its skip from caffe_rng_rand() right after Caffe::set_random_seed(caffe_seed);
+        negative_dataset: (video_id, shot_off, shot_ids, feat) served as a second fake LMDB."""
         L = lib()
         L.ref_sampler_create.restype = C.c_void_p
+        L.ref_sampler_create_opts.restype = C.c_void_p
         L.ref_sampler_next.argtypes = [C.c_void_p, C.c_void_p]
         L.ref_sampler_rows.argtypes = [C.c_void_p]
         L.ref_sampler_destroy.argtypes = [C.c_void_p]
         self.vid = np.ascontiguousarray(video_id, np.int32); self.off = np.ascontiguousarray(shot_off, np.int32)
         self.sid = np.ascontiguousarray(shot_ids, np.int32); self.feat = f32(feat)
         L.ref_srand(C.c_uint(seed))
-        self._h = L.ref_sampler_create(len(self.vid), K, _p(self.vid), _p(self.off), _p(self.sid), _p(self.feat), batch_size,
-                                       context_size, num_negative_samples, max_buffer_size, negative_swap_percentage,
-                                       max_same_video_negs, context_type)
+        nv, neg = 0, [None] * 4
+        if negative_dataset is not None:
+            neg = [np.ascontiguousarray(a, np.int32) for a in negative_dataset[:3]] + [f32(negative_dataset[3])]
+            nv = len(neg[0])
+        self._neg = neg
+        self._h = L.ref_sampler_create_opts(len(self.vid), K, _p(self.vid), _p(self.off), _p(self.sid), _p(self.feat), batch_size,
+                                            context_size, num_negative_samples, max_buffer_size, negative_swap_percentage,
+                                            max_same_video_negs, context_type, int(rand_skip), C.c_uint(caffe_seed), nv,
+                                            *[(_p(a) if a is not None else None) for a in neg])
         if not self._h:
             raise RuntimeError("reference data layer failed to set up")
         self.B, self.R, self.K = batch_size, L.ref_sampler_rows(self._h), K

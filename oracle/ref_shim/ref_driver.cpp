@@ -297,6 +297,7 @@ typedef video_shot_sentences::TestVideoShotWindows TestVideoShotWindows;
 struct FakeDb { std::vector<std::shared_ptr<void> > records; };      // live VideoShots / TestVideoShotWindows messages
 FakeDb* g_fake_db = nullptr;          // the dataset the next mdb_env_open serves ...
 FakeDb* g_fake_db_test = nullptr;     // ... unless the source names the TEST database
+FakeDb* g_fake_db_neg = nullptr;      // ... or the negative_dataset
 }  // namespace
 struct MDB_env { FakeDb* db; };
 struct MDB_txn { MDB_env* env; };
@@ -305,7 +306,7 @@ extern "C" {
 int mdb_env_create(MDB_env** env) { *env = new MDB_env{nullptr}; return MDB_SUCCESS; }
 int mdb_env_set_mapsize(MDB_env*, size_t) { return MDB_SUCCESS; }
 int mdb_env_open(MDB_env* env, const char* path, unsigned int, mdb_mode_t) {
-  env->db = (path && strstr(path, "fake-lmdb-test")) ? g_fake_db_test : g_fake_db;
+  env->db = (path && strstr(path, "fake-lmdb-test")) ? g_fake_db_test : (path && strstr(path, "fake-lmdb-neg")) ? g_fake_db_neg : g_fake_db;
   return env->db ? MDB_SUCCESS : -1;
 }
 int mdb_txn_begin(MDB_env* env, MDB_txn*, unsigned int, MDB_txn** txn) { *txn = new MDB_txn{env}; return MDB_SUCCESS; }
@@ -328,7 +329,7 @@ void mdb_env_close(MDB_env* e) { delete e; }
 
 namespace {
 struct RefSampler {
-  FakeDb db;
+  FakeDb db, neg_db;
   std::unique_ptr<VideoSampledShotsDataLayer<float> > layer;
   Blob<float> top;
   int B, R, K;
@@ -339,22 +340,42 @@ extern "C" {
 // Dataset as in the oracle's sampler: videos [V] with shots [shot_off[v], shot_off[v+1]) of `feat` [total, K].
 // context_type: 0 PAIRWISE, 1 WINDOW, 2 PAST, 3 PAST_CONTINUOUS, 4 PAST_CONTINUOUS_FIXED.  Call srand(seed) first: the
 // layer draws from the process-global rand() (from its prefetch thread; one batch is always prefetched ahead).
+static void FillFakeDb(FakeDb* db, int V, int K, const int* video_id, const int* shot_off, const int* shot_ids, const float* feat) {
+  for (int v = 0; v < V; ++v) {
+    std::shared_ptr<VideoShots> rec(new VideoShots());
+    rec->set_video_id(video_id[v]);
+    for (int g = shot_off[v]; g < shot_off[v + 1]; ++g) {
+      rec->add_shot_ids(shot_ids[g]);
+      Datum* d = rec->add_shot_words();
+      for (int k = 0; k < K; ++k) d->add_float_data(feat[size_t(g) * K + k]);
+    }
+    db->records.push_back(rec);
+  }
+}
+REF_API void* ref_sampler_create_opts(int V, int K, const int* video_id, const int* shot_off, const int* shot_ids, const float* feat,
+                                      int batch_size, int context_size, int num_negative_samples, int max_buffer_size,
+                                      int negative_swap_percentage, int max_same_video_negs, int context_type,
+                                      int rand_skip, unsigned caffe_seed, int negV, const int* neg_video_id,
+                                      const int* neg_shot_off, const int* neg_shot_ids, const float* neg_feat);
 REF_API void* ref_sampler_create(int V, int K, const int* video_id, const int* shot_off, const int* shot_ids, const float* feat,
                                  int batch_size, int context_size, int num_negative_samples, int max_buffer_size,
                                  int negative_swap_percentage, int max_same_video_negs, int context_type) {
+  return ref_sampler_create_opts(V, K, video_id, shot_off, shot_ids, feat, batch_size, context_size, num_negative_samples,
+                                 max_buffer_size, negative_swap_percentage, max_same_video_negs, context_type,
+                                 0, 0, 0, nullptr, nullptr, nullptr, nullptr);
+}
+// + rand_skip (drawn by the layer from caffe_rng_rand() right after Caffe::set_random_seed(caffe_seed)) and
+// negative_dataset (a second fake LMDB) -- video_sampled_shots_data_layer.cpp:137-153, 157-180
+REF_API void* ref_sampler_create_opts(int V, int K, const int* video_id, const int* shot_off, const int* shot_ids, const float* feat,
+                                      int batch_size, int context_size, int num_negative_samples, int max_buffer_size,
+                                      int negative_swap_percentage, int max_same_video_negs, int context_type,
+                                      int rand_skip, unsigned caffe_seed, int negV, const int* neg_video_id,
+                                      const int* neg_shot_off, const int* neg_shot_ids, const float* neg_feat) {
   try {
     Caffe::set_mode(Caffe::CPU);
     RefSampler* s = new RefSampler();
-    for (int v = 0; v < V; ++v) {
-      std::shared_ptr<VideoShots> rec(new VideoShots());
-      rec->set_video_id(video_id[v]);
-      for (int g = shot_off[v]; g < shot_off[v + 1]; ++g) {
-        rec->add_shot_ids(shot_ids[g]);
-        Datum* d = rec->add_shot_words();
-        for (int k = 0; k < K; ++k) d->add_float_data(feat[size_t(g) * K + k]);
-      }
-      s->db.records.push_back(rec);
-    }
+    FillFakeDb(&s->db, V, K, video_id, shot_off, shot_ids, feat);
+    if (negV > 0) FillFakeDb(&s->neg_db, negV, K, neg_video_id, neg_shot_off, neg_shot_ids, neg_feat);
     LayerParameter p;
     VideoSampledShotsDataParameter* vp = p.mutable_video_sampled_shots_data_param();
     vp->set_source("mem://fake-lmdb"); vp->set_backend(VideoSampledShotsDataParameter_DB_LMDB);
@@ -362,11 +383,13 @@ REF_API void* ref_sampler_create(int V, int K, const int* video_id, const int* s
     vp->set_max_buffer_size(max_buffer_size); vp->set_negative_swap_percentage(negative_swap_percentage);
     vp->set_max_same_video_negs(max_same_video_negs);
     vp->set_context_type(VideoSampledShotsDataParameter_CONTEXT(context_type));
-    g_fake_db = &s->db;
+    if (rand_skip > 0) { vp->set_rand_skip(rand_skip); Caffe::set_random_seed(caffe_seed); }
+    if (negV > 0) vp->set_negative_dataset("mem://fake-lmdb-neg");
+    g_fake_db = &s->db; g_fake_db_neg = negV > 0 ? &s->neg_db : nullptr;
     s->layer.reset(new VideoSampledShotsDataLayer<float>(p));
     BV bottom, tv{&s->top};
     s->layer->SetUp(bottom, &tv);            // DataLayerSetUp (negative buffer init) + first prefetch
-    g_fake_db = nullptr;
+    g_fake_db = nullptr; g_fake_db_neg = nullptr;
     s->B = batch_size; s->R = s->top.channels(); s->K = K;
     return s;
   } catch (const std::exception& e) { fprintf(stderr, "ref_driver: %s\n", e.what()); return nullptr; }

@@ -684,6 +684,13 @@ void* orc_sampler_create(int V, int K, const int* video_id, const int* shot_off,
   return orc_sampler_create_mode(V, K, video_id, shot_off, shot_ids, feat, batch_size, context_size, num_negative_samples,
                                  max_buffer_size, negative_swap_percentage, max_same_video_negs, max_tries_for_negs, 1);
 }
+void* orc_sampler_create_opts(int V, int K, const int* video_id, const int* shot_off,
+                              const int* shot_ids, const float* feat,
+                              int batch_size, int context_size, int num_negative_samples,
+                              int max_buffer_size, int negative_swap_percentage,
+                              int max_same_video_negs, int max_tries_for_negs, int context_type,
+                              int start_skip, int negV, const int* neg_video_id, const int* neg_shot_off,
+                              const int* neg_shot_ids, const float* neg_feat, int neg_row_base);
 // context_type: VideoSampledShotsDataParameter.CONTEXT (caffe.proto:598-604): 0 PAIRWISE, 1 WINDOW, 2 PAST,
 // 3 PAST_CONTINUOUS, 4 PAST_CONTINUOUS_FIXED
 void* orc_sampler_create_mode(int V, int K, const int* video_id, const int* shot_off,
@@ -691,6 +698,20 @@ void* orc_sampler_create_mode(int V, int K, const int* video_id, const int* shot
                               int batch_size, int context_size, int num_negative_samples,
                               int max_buffer_size, int negative_swap_percentage,
                               int max_same_video_negs, int max_tries_for_negs, int context_type) {
+  return orc_sampler_create_opts(V, K, video_id, shot_off, shot_ids, feat, batch_size, context_size, num_negative_samples,
+                                 max_buffer_size, negative_swap_percentage, max_same_video_negs, max_tries_for_negs, context_type,
+                                 0, 0, nullptr, nullptr, nullptr, nullptr, 0);
+}
+// + the data layer's rand_skip (:157-180; start_skip = the value drawn, caffe_rng_rand() % rand_skip) and
+// negative_dataset (:137-153, 273-284, 324-338): a second record set whose shots -- ALL of them, record after record, no
+// rand() -- seed the negative buffer; emitted indices of those shots are neg_row_base + their index in that set
+void* orc_sampler_create_opts(int V, int K, const int* video_id, const int* shot_off,
+                              const int* shot_ids, const float* feat,
+                              int batch_size, int context_size, int num_negative_samples,
+                              int max_buffer_size, int negative_swap_percentage,
+                              int max_same_video_negs, int max_tries_for_negs, int context_type,
+                              int start_skip, int negV, const int* neg_video_id, const int* neg_shot_off,
+                              const int* neg_shot_ids, const float* neg_feat, int neg_row_base) {
   if (max_same_video_negs > num_negative_samples) return nullptr;   // undefined in the reference (slot overflow)
   if (context_type < 0 || context_type > 4) return nullptr;
   if (context_type == 0 && context_size != 2) return nullptr;       // PAIRWISE fills channels 0 and 1 only (:396-404)
@@ -700,7 +721,7 @@ void* orc_sampler_create_mode(int V, int K, const int* video_id, const int* shot
   s->P = num_negative_samples > 0 ? max_buffer_size : 0;
   s->swap_pct = negative_swap_percentage; s->max_same = max_same_video_negs;
   s->video_id = video_id; s->shot_off = shot_off; s->shot_ids = shot_ids; s->feat = feat;
-  s->cursor = 0;
+  s->cursor = start_skip % V;                                           // rand_skip: MDB_NEXT x skip, wrapping (:161-178)
   const int R = s->C + s->Nn;
   for (int i = 0; i < s->P; ++i) s->buffer_ids.push_back(i);            // :81-83
   if (feat) { s->prefetch.assign((size_t)s->B * R * K, 0.f); s->negatives.assign((size_t)s->P * K, 0.f); }
@@ -708,7 +729,26 @@ void* orc_sampler_create_mode(int V, int K, const int* video_id, const int* shot
   s->neg_shot.assign(s->P, -1);
   // negative buffer init :245-344 : one rand()%num_shots per record visited
   int added = 0;
-  for (long nid = 0; nid < (long)max_tries_for_negs * s->P; ++nid) {
+  int ncur = 0;
+  for (long nid = 0; negV > 0 && nid < (long)max_tries_for_negs * s->P; ++nid) {
+    // negative_dataset: every shot of the record at the negative cursor (:324-338); the reference copies without a
+    // bound check, so running past max_buffer_size inside a record is a buffer overflow there -- an error here
+    const int v = ncur;
+    ncur = (ncur + 1) % negV;
+    for (int g = neg_shot_off[v]; g < neg_shot_off[v + 1]; ++g) {
+      const std::string key = orc_key(neg_video_id[v], neg_shot_ids[g]);
+      if (s->key_set.find(key) == s->key_set.end()) {
+        if (added >= s->P) { delete s; return nullptr; }
+        if (feat && neg_feat) memcpy(&s->negatives[(size_t)added * K], neg_feat + (size_t)g * K, K * sizeof(float));
+        s->neg_shot[added] = neg_row_base + g;
+        s->id_to_key.push_back(key);
+        s->key_set.insert(key);
+        added++;
+      }
+    }
+    if (added >= s->P) break;
+  }
+  for (long nid = 0; negV == 0 && nid < (long)max_tries_for_negs * s->P; ++nid) {
     const int v = s->cursor;
     s->cursor = (s->cursor + 1) % V;                                     // MDB_NEXT / wrap
     const int num_shots = shot_off[v + 1] - shot_off[v];

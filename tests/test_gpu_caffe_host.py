@@ -368,6 +368,33 @@ def test_net_trains_from_video_shots_records(tmp_path, oracle, container):
     assert rel(net2.param(0, diff=True).reshape(N, K), ref["dW"]) < 1e-5
 
 
+@pytest.mark.parametrize("name", ["skip_window", "neg_window", "skip_neg_past"])
+def test_data_layer_rand_skip_and_negative_dataset(tmp_path, name):
+    """The data layer's `rand_skip` and `negative_dataset` (video_sampled_shots_data_layer.cpp:104-180, 253-338) through the
+    reference's interface: VideoSampledShotsDataLayer<float> of caffe_compat, built from a `layers { }` entry over two
+    record files, must serve the data blobs the compiled reference layer served (tests/golden/sampler_opts_ref.npz)."""
+    import records_util
+    g = np.load(os.path.join(ROOT, "tests", "golden", "sampler_opts_ref.npz"))
+    mode, B, C, Nn, P, swap, max_same, rand_skip, cseed, with_neg = [int(x) for x in g["cfg_" + name]]
+    ref = g["blobs_" + name]
+    src = records_util.write_vvrs(tmp_path / "main.vvrs", records_util.video_shots_records(g["vid"], g["off"], g["sid"], g["feat"]))
+    extra = ""
+    if with_neg:
+        extra += ' negative_dataset: "%s"' % records_util.write_vvrs(
+            tmp_path / "neg.vvrs", records_util.video_shots_records(g["nvid"], g["noff"], g["nsid"], g["nfeat"]))
+    if rand_skip:
+        extra += " rand_skip: %d" % rand_skip
+    ctx = ["PAIRWISE", "WINDOW", "PAST", "PAST_CONTINUOUS", "PAST_CONTINUOUS_FIXED"][mode]
+    text = ('layers { name: "shot_windows" type: VIDEO_SAMPLED_SHOTS_DATA top: "data" video_sampled_shots_data_param { '
+            'source: "%s" backend: LMDB batch_size: %d num_negative_samples: %d max_buffer_size: %d negative_swap_percentage: %d '
+            'max_same_video_negs: %d context_type: %s context_size: %d%s } }' % (src, B, Nn, P, swap, max_same, ctx, C, extra))
+    caffe_host.set_device(0)
+    caffe_host.set_seed(cseed)
+    for batch in (0, 2, 7):
+        _, tops, _ = caffe_host.run_layer(text, [], 1, forwards=batch + 1)
+        assert np.array_equal(tops[0].reshape(ref[batch].shape), ref[batch]), "batch %d differs from the reference data layer" % batch
+
+
 def test_test_net_reads_test_window_records(tmp_path):
     """TEST-phase data layer on TestVideoShotWindows records: items in DB order, label = video_id, wrap at the end
     (video_shot_window_test_data_layer.cpp:160-262)."""

@@ -193,6 +193,61 @@ def test_sampler_reproduces_reference_data_layer_fixtures(vvlib, oracle, name):
     psmp.close()
 
 
+def mt19937_first(seed):
+    """First 32-bit output of mt19937 seeded with an integer (boost::mt19937 = std::mt19937): what caffe_rng_rand() returns
+    right after Caffe::set_random_seed(seed) (ref: common.cpp:47-50, math_functions.cpp:265-267)."""
+    mt = [0] * 624
+    mt[0] = seed & 0xFFFFFFFF
+    for i in range(1, 624):
+        mt[i] = (1812433253 * (mt[i - 1] ^ (mt[i - 1] >> 30)) + i) & 0xFFFFFFFF
+    for i in range(624):                                   # one twist
+        y = (mt[i] & 0x80000000) | (mt[(i + 1) % 624] & 0x7FFFFFFF)
+        mt[i] = mt[(i + 397) % 624] ^ (y >> 1) ^ (0x9908B0DF if y & 1 else 0)
+    y = mt[0]
+    y ^= y >> 11; y ^= (y << 7) & 0x9D2C5680; y ^= (y << 15) & 0xEFC60000; y ^= y >> 18
+    return y & 0xFFFFFFFF
+
+
+GOLD_SAMPLER_OPTS = GOLD_SAMPLER.replace("sampler_ref.npz", "sampler_opts_ref.npz")
+
+
+@pytest.mark.parametrize("name", ["skip_window", "neg_window", "skip_neg_past"])
+def test_sampler_options_reproduce_reference_data_layer(vvlib, oracle, name):
+    """rand_skip and negative_dataset (video_sampled_shots_data_layer.cpp:137-153, 157-180, 273-284, 324-338): the data blobs
+    the reference's data layer produced with them (tests/golden/sampler_opts_ref.npz <- make_sampler_opts_golden.py: two
+    fake LMDBs, skip drawn from caffe_rng_rand()) rebuilt bit for bit by the oracle's sampler and by the product's index
+    stream over a bank that holds the negative set's rows behind the main set's."""
+    g = np.load(GOLD_SAMPLER_OPTS)
+    mode, B, C, Nn, P, swap, max_same, rand_skip, cseed, with_neg = [int(x) for x in g["cfg_" + name]]
+    ref = g["blobs_" + name]
+    skip = mt19937_first(cseed) % rand_skip if rand_skip else 0
+    bank = np.concatenate([g["feat"], g["nfeat"]]) if with_neg else g["feat"]
+    base = len(g["feat"])
+    oneg = (g["nvid"], g["noff"], g["nsid"], g["nfeat"], base) if with_neg else None
+    osmp = oracle.Sampler(g["vid"], g["off"], g["sid"], g["feat"], 5, B, C, Nn, P, swap, max_same, 100, seed=1, context_type=mode,
+                          start_skip=skip, negative_dataset=oneg)
+    for i in range(ref.shape[0]):
+        idx, quirk, data = osmp.next()
+        assert np.array_equal(data, ref[i]), "oracle differs from the reference data layer at batch %d" % i
+        assert np.array_equal(_blob_from_indices(bank, idx, quirk), ref[i])
+    osmp.close()
+    pneg = (g["nvid"], g["noff"], g["nsid"], base) if with_neg else None
+    psmp = ops.Sampler(g["vid"], g["off"], g["sid"], B, C, Nn, P, swap, max_same, 100, rand_seed=1, context_type=mode,
+                       start_skip=skip, negative_dataset=pneg)
+    for i in range(ref.shape[0]):
+        idx, quirk = psmp.next()
+        assert np.array_equal(_blob_from_indices(bank, idx, quirk), ref[i]), "product differs at batch %d" % i
+    psmp.close()
+    if with_neg:
+        # the reference CHECKs that the buffer fills exactly at a record boundary (:346): one slot less is an error
+        with pytest.raises(Exception):
+            ops.Sampler(g["vid"], g["off"], g["sid"], B, C, Nn, P - 1, swap, max_same, 100, rand_seed=1, context_type=mode,
+                        negative_dataset=pneg)
+        with pytest.raises(Exception):
+            oracle.Sampler(g["vid"], g["off"], g["sid"], g["feat"], 5, B, C, Nn, P - 1, swap, max_same, 100, seed=1,
+                           context_type=mode, negative_dataset=oneg)
+
+
 @pytest.mark.parametrize("mode,C", [(1, 5), (2, 6), (3, 4), (4, 5), (0, 2)])
 def test_live_reference_data_layer(vvlib, oracle, mode, C):
     """Where oracle/_ref was built: the reference's data layer run live on a fresh dataset against the product sampler."""

@@ -124,6 +124,7 @@ SIGNATURES = {
     "vv_record_set_upload": (_i, [_P, _P, _P]),
     "vv_sampler_create": (_P, [_i, _P, _P, _P, _i, _i, _i, _i, _i, _i, _i, C.c_uint]),
     "vv_sampler_create_ex": (_P, [_i, _P, _P, _P, _i, _i, _i, _i, _i, _i, _i, C.c_uint, _i]),
+    "vv_sampler_create_ex2": (_P, [_i, _P, _P, _P, _i, _i, _i, _i, _i, _i, _i, C.c_uint, _i, _i, _i, _P, _P, _P, _i]),
     "vv_sampler_destroy": (None, [_P]),
     "vv_sampler_next": (_i, [_P, _P, _P]),
     "vv_sampler_cursor": (_i, [_P]),

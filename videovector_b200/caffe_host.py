@@ -81,9 +81,10 @@ def set_precision(prec):
     _l().vvc_set_precision(PREC[prec] if isinstance(prec, str) else prec)
 
 
-def run_layer(layer_prototxt, bottoms, n_top, propagate_down=None, top_diffs=None, cap=1 << 20):
+def run_layer(layer_prototxt, bottoms, n_top, propagate_down=None, top_diffs=None, cap=1 << 20, forwards=1):
     """One layer by itself, as the reference's per-layer tests drive it (src/caffe/test/test_*_layer.cpp): `bottoms` are
     float32 arrays with up to 4 dims (num, channels, height, width), `layer_prototxt` a `layers { ... }` entry.
+    forwards: Forward is run that many times before the tops are read (the n-th batch of a data layer).
     Returns (loss, [top data], [bottom diff or None])."""
     lib = _l()
     nb = len(bottoms)
@@ -104,8 +105,9 @@ def run_layer(layer_prototxt, bottoms, n_top, propagate_down=None, top_diffs=Non
         bdiffs = [np.zeros(a.size, np.float32) if propagate_down[i] else None for i, a in enumerate(arrs)]
         bd = (_P * nb)(*[None if d is None else d.ctypes.data for d in bdiffs])
     loss = C.c_float(0)
-    lib.vvc_layer_run.argtypes = [C.c_char_p, C.c_int, _P, _P, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P]
-    _check(lib.vvc_layer_run(layer_prototxt.encode(), nb, shapes, bptr, n_top, cap, tptr, counts, tdiff, pd, bd, C.byref(loss)))
+    lib.vvc_layer_run.argtypes = [C.c_char_p, C.c_int, _P, _P, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, C.c_int]
+    _check(lib.vvc_layer_run(layer_prototxt.encode(), nb, shapes, bptr, n_top, cap, tptr, counts, tdiff, pd, bd, C.byref(loss),
+                             int(forwards)))
     return (loss.value, [t[:counts[i]].copy() for i, t in enumerate(tops)],
             [None if d is None else d.reshape(arrs[i].shape) for i, d in enumerate(bdiffs)])
 

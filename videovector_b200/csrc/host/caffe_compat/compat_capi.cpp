@@ -30,11 +30,12 @@ int vvc_transform_net(const char* prototxt_text, int phase, char* out, int out_l
 
 // One layer by itself, the way the reference's per-layer tests drive a layer (src/caffe/test/test_*_layer.cpp): bottoms
 // filled from host arrays, SetUp, Forward, Backward.  net_text: a NetParameter with one `layers { }` entry.
+// forwards: how many times Forward runs before the tops are read (a data layer's n-th batch).
 // bottom_shapes: 4 ints per bottom; top_data / bottom_diff: host buffers of at least `cap` floats each (entries may be
 // NULL); top_diff: what to seed the top diffs with before Backward (NULL: what SetUp left there, i.e. the loss weights).
 int vvc_layer_run(const char* net_text, int n_bottom, const int* bottom_shapes, const float* const* bottom_data, int n_top,
                   int cap, float* const* top_data, int* top_counts, const float* const* top_diff, const int* propagate_down,
-                  float* const* bottom_diff, float* loss) {
+                  float* const* bottom_diff, float* loss, int forwards) {
   try {
     const NetParameter np(ParseTextFormat(net_text));
     CHECK_EQ(np.layers_size(), 1) << "vvc_layer_run takes exactly one layer";
@@ -49,7 +50,8 @@ int vvc_layer_run(const char* net_text, int n_bottom, const int* bottom_shapes, 
     }
     for (int i = 0; i < n_top; ++i) { hold.push_back(shared_ptr<Blob<float> >(new Blob<float>())); top.push_back(hold.back().get()); }
     layer->SetUp(bottom, &top);
-    const float l = layer->Forward(bottom, &top);
+    float l = 0.f;
+    for (int f = 0; f < (forwards < 1 ? 1 : forwards); ++f) l = layer->Forward(bottom, &top);   // data layers: the f-th batch
     if (loss) *loss = l;
     for (int i = 0; i < n_top; ++i) {
       CHECK_LE(top[i]->count(), cap) << "top " << i << " does not fit the output buffer";

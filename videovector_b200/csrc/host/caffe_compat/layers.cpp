@@ -487,50 +487,80 @@ static long UrlParam(const string& src, const string& key, long dflt) {
 }
 template <typename Dtype>
 VideoSampledShotsDataLayer<Dtype>::~VideoSampledShotsDataLayer() { if (sampler_) vv_sampler_destroy(sampler_); }
+namespace {
+// One `source` / `negative_dataset` of the data layer: its tables now, its rows into the bank later (one allocation holds
+// the main set's rows followed by the negative set's).
+struct ShotSource {
+  int V = 0, K = 0; int64_t rows = 0;
+  vector<int32_t> vid, off, ids;
+  vv_record_set_t* rs = nullptr;        // record-file sources
+  uint64_t seed = 0;                    // synthetic:// sources
+  ~ShotSource() { if (rs) vv_record_set_destroy(rs); }
+  void Open(const string& src) {
+    if (src.compare(0, 12, "synthetic://") == 0) {
+      V = int(UrlParam(src, "videos", 2048));
+      const int S = int(UrlParam(src, "shots", 32));
+      K = int(UrlParam(src, "dim", 4096));
+      seed = uint64_t(UrlParam(src, "seed", 1234));
+      CHECK_GE(K, 1);
+      rows = int64_t(V) * S;
+      vid.resize(V); off.resize(V + 1); ids.resize(size_t(V) * S);
+      for (int v = 0; v < V; ++v) { vid[v] = v; off[v] = v * S; for (int s2 = 0; s2 < S; ++s2) ids[size_t(v) * S + s2] = s2; }
+      off[V] = V * S;
+      return;
+    }
+    // the reference's `source`: an LMDB environment of VideoShots records (:121-135), or a VVRS / mdb_dump file of them;
+    // every record is decoded once into the resident device bank, the cursor loop becomes the sampler's index stream
+    rs = vv_record_set_create(VV_RECORD_VIDEO_SHOTS, 1, 1);
+    CHECK(rs) << vv_last_error();
+    const int rc = vv_record_set_load_file(rs, src.c_str());
+    if (rc != 0) { const string e = vv_last_error(); LOG_FATAL << "cannot read VideoShots records from '" << src << "': " << e; }
+    int64_t records = 0; int32_t k = 0;
+    VV_CHECK(vv_record_set_info(rs, &records, &rows, &k, nullptr));
+    if (records < 1 || rows < 1) LOG_FATAL << "no VideoShots records in '" << src << "'";
+    V = int(records); K = k;
+    vid.resize(V); off.resize(V + 1); ids.resize(size_t(rows));
+    VV_CHECK(vv_record_set_tables(rs, vid.data(), off.data(), ids.data()));
+    LogInfo("VideoShots records: " + std::to_string(records) + " videos, " + std::to_string(rows) + " shots, feature size " + std::to_string(K));
+  }
+  void Upload(float* dst) {
+    if (rs) { VV_CHECK(vv_record_set_upload(rs, dst, Caffe::stream())); }
+    else VV_CHECK(vv_fill_bank(dst, rows, K, seed, Caffe::stream()));
+  }
+};
+}  // namespace
 template <typename Dtype>
 void VideoSampledShotsDataLayer<Dtype>::LayerSetUp(const vector<Blob<Dtype>*>& bottom, vector<Blob<Dtype>*>* top) {
   const VideoSampledShotsDataParameter p = this->layer_param_.video_sampled_shots_data_param();
-  const string src = p.source();
   batch_size_ = p.batch_size(); context_size_ = p.context_size(); num_negative_samples_ = p.num_negative_samples();
-  CHECK(p.negative_dataset().empty()) << "negative_dataset is not built";
-  CHECK_EQ(p.rand_skip(), 0) << "rand_skip is not built";
-  int V = 0;
-  vector<int32_t> vid, off, ids;
-  if (src.compare(0, 12, "synthetic://") == 0) {
-    V = int(UrlParam(src, "videos", 2048));
-    const int S = int(UrlParam(src, "shots", 32));
-    feature_size_ = int(UrlParam(src, "dim", 4096));
-    const uint64_t seed = uint64_t(UrlParam(src, "seed", 1234));
-    CHECK_GE(feature_size_, 1);
-    bank_rows_ = int64_t(V) * S;
-    bank_ptr_ = static_cast<float*>(bank_.get(size_t(bank_rows_) * feature_size_ * sizeof(float)));
-    VV_CHECK(vv_fill_bank(bank_ptr_, bank_rows_, feature_size_, seed, Caffe::stream()));
-    vid.resize(V); off.resize(V + 1); ids.resize(size_t(V) * S);
-    for (int v = 0; v < V; ++v) { vid[v] = v; off[v] = v * S; for (int s = 0; s < S; ++s) ids[size_t(v) * S + s] = s; }
-    off[V] = V * S;
-  } else {
-    // the reference's `source`: an LMDB environment of VideoShots records (:121-135), or a VVRS / mdb_dump file of them;
-    // every record is decoded once into the resident device bank, the cursor loop becomes the sampler's index stream
-    vv_record_set_t* rs = vv_record_set_create(VV_RECORD_VIDEO_SHOTS, 1, 1);
-    CHECK(rs) << vv_last_error();
-    const int rc = vv_record_set_load_file(rs, src.c_str());
-    if (rc != 0) { const string e = vv_last_error(); vv_record_set_destroy(rs); LOG_FATAL << "cannot read VideoShots records from '" << src << "': " << e; }
-    int64_t records = 0, rows = 0; int32_t K = 0;
-    VV_CHECK(vv_record_set_info(rs, &records, &rows, &K, nullptr));
-    if (records < 1 || rows < 1) { vv_record_set_destroy(rs); LOG_FATAL << "no VideoShots records in '" << src << "'"; }
-    V = int(records); feature_size_ = K; bank_rows_ = rows;
-    vid.resize(V); off.resize(V + 1); ids.resize(size_t(rows));
-    VV_CHECK(vv_record_set_tables(rs, vid.data(), off.data(), ids.data()));
-    bank_ptr_ = static_cast<float*>(bank_.get(size_t(rows) * K * sizeof(float)));
-    const int urc = vv_record_set_upload(rs, bank_ptr_, Caffe::stream());
-    vv_record_set_destroy(rs);
-    VV_CHECK(urc);
-    LogInfo("VideoShots records: " + std::to_string(records) + " videos, " + std::to_string(rows) + " shots, feature size " + std::to_string(K));
+  ShotSource main_src, neg_src;
+  main_src.Open(p.source());
+  // negative_dataset (ref: :104-153): a second record set that seeds the negative buffer; its rows follow the main set's
+  const bool has_neg = !p.negative_dataset().empty();
+  if (has_neg) {
+    neg_src.Open(p.negative_dataset());
+    CHECK_EQ(neg_src.K, main_src.K) << "negative_dataset has another feature size";
   }
+  feature_size_ = main_src.K;
+  bank_rows_ = main_src.rows + (has_neg ? neg_src.rows : 0);
+  bank_ptr_ = static_cast<float*>(bank_.get(size_t(bank_rows_) * feature_size_ * sizeof(float)));
+  main_src.Upload(bank_ptr_);
+  if (has_neg) neg_src.Upload(bank_ptr_ + size_t(main_src.rows) * feature_size_);
   CHECK_GE(feature_size_, 1); CHECK_GE(context_size_, 2); CHECK_GE(batch_size_, 1);
-  sampler_ = vv_sampler_create_ex(V, vid.data(), off.data(), ids.data(), batch_size_, context_size_, num_negative_samples_,
-                                  p.max_buffer_size(), p.negative_swap_percentage(), p.max_same_video_negs(), 100,
-                                  1 /* rand() is never seeded */, int(p.context_type()));
+  // rand_skip (ref: :157-180): skip = caffe_rng_rand() % rand_skip records, caffe_rng_rand() being the next output of the
+  // mt19937 that Caffe::set_random_seed seeded -- its first output here, nothing else has drawn from it at set-up
+  int skip = 0;
+  if (p.rand_skip() > 0) {
+    std::mt19937 gen(unsigned(Caffe::rng_seed()));
+    skip = int(gen() % unsigned(p.rand_skip()));
+    LogInfo("Skipping first " + std::to_string(skip) + " data points.");
+  }
+  sampler_ = vv_sampler_create_ex2(main_src.V, main_src.vid.data(), main_src.off.data(), main_src.ids.data(), batch_size_,
+                                   context_size_, num_negative_samples_, p.max_buffer_size(), p.negative_swap_percentage(),
+                                   p.max_same_video_negs(), 100, 1 /* rand() is never seeded */, int(p.context_type()), skip,
+                                   has_neg ? neg_src.V : 0, has_neg ? neg_src.vid.data() : nullptr,
+                                   has_neg ? neg_src.off.data() : nullptr, has_neg ? neg_src.ids.data() : nullptr,
+                                   int32_t(main_src.rows));
   CHECK(sampler_) << "Could not add requested number of negatives (or an invalid context_size for this context_type)";
   VV_CHECK(vv_sampler_prefetch(sampler_, 3));      // BasePrefetchingDataLayer: the next batches are drawn on a thread
   const int R = context_size_ + num_negative_samples_;

@@ -229,6 +229,30 @@ struct vv_sampler {
     }
     return added == P;
   }
+  // negative_dataset (video_sampled_shots_data_layer.cpp:137-153, 273-284, 324-338): the buffer starts with EVERY shot of
+  // the second dataset's records in order (no rand() drawn, the main cursor untouched), keys shared with the main data.
+  // The reference copies without a bound check and then CHECKs that exactly max_buffer_size negatives were added (:346),
+  // so the fill must end exactly on a record boundary: anything else is an error there and here.
+  bool has_neg_dataset = false;
+  bool init_from(int max_tries, int negV, const int32_t* noff, const int32_t* nkey, int32_t row0) {
+    int added = 0, ncur = 0;
+    for (long nid = 0; nid < (long)max_tries * P; ++nid) {
+      const int v = ncur;
+      ncur = (ncur + 1) % negV;
+      for (int g = noff[v]; g < noff[v + 1]; ++g) {
+        const int32_t key = nkey[g];
+        if (!in_set[key]) {
+          if (added >= P) return false;                   // the reference would write past its buffer here
+          in_set[key] = 1;
+          neg_row[added] = row0 + g;
+          slot_key[added] = key;
+          ++added;
+        }
+      }
+      if (added >= P) break;
+    }
+    return added == P;
+  }
   int next(int32_t* idx, int32_t* quirk) {
     const int R = C + Nn;
     int item = 0; long guard = 0;
@@ -359,6 +383,18 @@ extern "C" vv_sampler_t* vv_sampler_create_ex(int num_videos, const int32_t* vid
                                               int num_negative_samples, int max_buffer_size,
                                               int negative_swap_percentage, int max_same_video_negs,
                                               int max_tries_for_negs, unsigned int rand_seed, int context_type) {
+  return vv_sampler_create_ex2(num_videos, video_id, shot_off, shot_ids, batch_size, context_size, num_negative_samples,
+                               max_buffer_size, negative_swap_percentage, max_same_video_negs, max_tries_for_negs, rand_seed,
+                               context_type, 0, 0, nullptr, nullptr, nullptr, 0);
+}
+extern "C" vv_sampler_t* vv_sampler_create_ex2(int num_videos, const int32_t* video_id, const int32_t* shot_off,
+                                               const int32_t* shot_ids, int batch_size, int context_size,
+                                               int num_negative_samples, int max_buffer_size,
+                                               int negative_swap_percentage, int max_same_video_negs,
+                                               int max_tries_for_negs, unsigned int rand_seed, int context_type,
+                                               int start_skip, int neg_num_videos, const int32_t* neg_video_id,
+                                               const int32_t* neg_shot_off, const int32_t* neg_shot_ids, int32_t neg_row_base) {
+  if (start_skip < 0 || neg_num_videos < 0 || (neg_num_videos > 0 && (!neg_video_id || !neg_shot_off || !neg_shot_ids))) return nullptr;
   if (context_type < VV_CONTEXT_PAIRWISE || context_type > VV_CONTEXT_PAST_CONTINUOUS_FIXED) return nullptr;
   // WINDOW takes the temporal median as target (odd window); PAIRWISE fills exactly two slots
   if (context_type == VV_CONTEXT_WINDOW && (context_size % 2) != 1) return nullptr;
@@ -395,13 +431,30 @@ extern "C" vv_sampler_t* vv_sampler_create_ex(int num_videos, const int32_t* vid
         auto it = ids.emplace(shot_key(video_id[v], shot_ids[g]), int32_t(ids.size()));
         s->key_of[g] = it.first->second;
       }
+    // the negative dataset's shots share the key space ("video_id:shot_id" strings in the reference)
+    std::vector<int32_t> neg_key;
+    if (neg_num_videos > 0) {
+      neg_key.resize(neg_shot_off[neg_num_videos]);
+      for (int v = 0; v < neg_num_videos; ++v)
+        for (int g = neg_shot_off[v]; g < neg_shot_off[v + 1]; ++g) {
+          auto it = ids.emplace(shot_key(neg_video_id[v], neg_shot_ids[g]), int32_t(ids.size()));
+          neg_key[g] = it.first->second;
+        }
+    }
     s->in_set.assign(ids.size() + 1, 0);     // + one dummy key for the branch-free swap loop
     // the dummy slot P must hold the dummy key from the start: the swap loop clears in_set[slot_key[pos]] before it
     // stores, and a zero-initialised dummy slot would name key 0 -- a real shot (found by the reference-pinned fixtures)
     s->slot_key[s->P] = int32_t(ids.size());
+    s->last_full.assign((size_t)batch_size * (context_size + num_negative_samples), -1);
+    // rand_skip (:157-180): the record cursor starts `start_skip` records in (wrapping), before anything else reads it
+    s->cursor = start_skip % num_videos;
+    if (s->P > 0) {
+      const bool ok = neg_num_videos > 0 ? s->init_from(max_tries_for_negs, neg_num_videos, neg_shot_off, neg_key.data(), neg_row_base)
+                                         : s->init(max_tries_for_negs);
+      if (!ok) { delete s; return nullptr; }
+    }
+    s->has_neg_dataset = neg_num_videos > 0;
   }
-  s->last_full.assign((size_t)batch_size * (context_size + num_negative_samples), -1);
-  if (s->P > 0 && !s->init(max_tries_for_negs)) { delete s; return nullptr; }
   return s;
 }
 extern "C" void vv_sampler_destroy(vv_sampler_t* s) { if (s) { s->stop_prefetch(); delete s->ring; s->ring = nullptr; } delete s; }
@@ -420,6 +473,7 @@ extern "C" int vv_sampler_next(vv_sampler_t* s, int32_t* idx, int32_t* quirk) {
 }
 extern "C" int vv_sampler_set_row_base(vv_sampler_t* s, int32_t row_base) {
   if (!s || row_base < 0) return VV_ERR_INVALID;
+  if (s->has_neg_dataset && row_base != 0) return VV_ERR_INVALID;   // the negative dataset's rows are absolute bank rows
   s->row_base = row_base;
   return 0;
 }

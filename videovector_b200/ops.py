@@ -355,17 +355,24 @@ class Sampler:
 
     def __init__(self, video_id, shot_off, shot_ids, batch_size, context_size=5, num_negative_samples=10,
                  max_buffer_size=5000, negative_swap_percentage=50, max_same_video_negs=6,
-                 max_tries_for_negs=100, rand_seed=1, context_type="window"):
+                 max_tries_for_negs=100, rand_seed=1, context_type="window", start_skip=0, negative_dataset=None):
+        """start_skip: the data layer's rand_skip draw (the record cursor starts that many records in);
+        negative_dataset: (video_id, shot_off, shot_ids, row_base) of a second record set whose shots seed the
+        negative buffer, its rows living at [row_base, ...) of the bank."""
         self._lib = _lib.load()
         self.video_id = np.ascontiguousarray(video_id, dtype=np.int32)
         self.shot_off = np.ascontiguousarray(shot_off, dtype=np.int32)
         self.shot_ids = np.ascontiguousarray(shot_ids, dtype=np.int32)
         self.B, self.R = batch_size, context_size + num_negative_samples
         ct = _lib.CONTEXT[context_type] if isinstance(context_type, str) else int(context_type)
-        self._h = self._lib.vv_sampler_create_ex(len(self.video_id), self.video_id.ctypes.data, self.shot_off.ctypes.data,
-                                                 self.shot_ids.ctypes.data, batch_size, context_size, num_negative_samples,
-                                                 max_buffer_size, negative_swap_percentage, max_same_video_negs,
-                                                 max_tries_for_negs, rand_seed, ct)
+        nv, nvid, noff, nsid, nbase = 0, None, None, None, 0
+        if negative_dataset is not None:
+            self._neg = [np.ascontiguousarray(a, dtype=np.int32) for a in negative_dataset[:3]]
+            nv, nvid, noff, nsid, nbase = len(self._neg[0]), self._neg[0].ctypes.data, self._neg[1].ctypes.data, self._neg[2].ctypes.data, int(negative_dataset[3])
+        self._h = self._lib.vv_sampler_create_ex2(len(self.video_id), self.video_id.ctypes.data, self.shot_off.ctypes.data,
+                                                  self.shot_ids.ctypes.data, batch_size, context_size, num_negative_samples,
+                                                  max_buffer_size, negative_swap_percentage, max_same_video_negs,
+                                                  max_tries_for_negs, rand_seed, ct, int(start_skip), nv, nvid, noff, nsid, nbase)
         if not self._h:
             raise VVError("vv_sampler_create failed (bad parameters, or could not fill the negative buffer)")
 
