@@ -442,6 +442,14 @@ size_t vv_retrieval_stats_workspace_bytes(int B);
 int vv_retrieval_stats(const float* E, int B, int N, const int32_t* video_ids, const int32_t* labels,
                        int exclude_same_video_shots, const float* gram_given, void* workspace, size_t workspace_bytes,
                        double* out3, double* per_query, vv_stream_t stream);
+/* + top5 (device, [B,5] int32, optional): per query the first five ranked items of ANOTHER video -- the "ret_id_1..5" of
+ * the layer's per-query CSV (stats_output_file, retrieval_stats_layer.cpp:306-333); -1 where fewer exist / unscored. */
+int vv_retrieval_stats_ex(const float* E, int B, int N, const int32_t* video_ids, const int32_t* labels,
+                          int exclude_same_video_shots, const float* gram_given, void* workspace, size_t workspace_bytes,
+                          double* out3, double* per_query, int32_t* top5, vv_stream_t stream);
+/* video_level_retrieval (:160-206): out[v,:] = mean of the batch's embeddings E[i,:] with group[i] == v (group [B] int32 in
+ * [0,V)), accumulated in increasing i; the stats then run on out [V,N] with one id / label per video. */
+int vv_video_mean_rows(const float* E, int B, int N, const int32_t* group, int V, float* out, vv_stream_t stream);
 
 /* IdToWeightMapping: a per-id embedding table (ref: id_to_weight_mapping_layer.cpp:61-148; CPU loops in the reference).
  *  forward : top[i,:] = table[ids[i],:]        ids [M] floats holding integers (a Caffe blob), table [rows, N]

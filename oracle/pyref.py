@@ -107,6 +107,18 @@ def retrieval_stats(E, video_ids, id_to_class_file, exclude_same_video_shots=Tru
     return out
 
 
+def retrieval_stats_ex(E, video_ids, id_to_class_file, exclude_same_video_shots=True, video_level=False, max_num_videos=0,
+                       stats_output_file=""):
+    """The reference's RetrievalStatsLayer with video_level_retrieval / stats_output_file.  Returns (mAP, hit@1, hit@5)."""
+    E = f32(E); ids = f32(video_ids)
+    out = np.zeros(3, np.float32)
+    rc = lib().ref_retrieval_stats_ex(E.shape[0], E.shape[1], _p(E), _p(ids), str(id_to_class_file).encode(),
+                                      int(exclude_same_video_shots), int(video_level), int(max_num_videos),
+                                      str(stats_output_file).encode(), _p(out))
+    assert rc == 0
+    return out
+
+
 def id_to_weight(table, ids, top_diff=None):
     """The reference's IdToWeightMappingLayer: (top, table_diff or None)."""
     table = f32(table); ids = f32(ids)

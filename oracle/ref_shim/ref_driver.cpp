@@ -254,6 +254,31 @@ REF_API int ref_retrieval_stats(int B, int N, const float* E, const float* video
     return 0;
   } catch (const std::exception& e) { fprintf(stderr, "ref_driver: %s\n", e.what()); return -1; }
 }
+// + video_level_retrieval (shots of a video averaged first, :160-206; max_num_videos must equal the number of distinct
+// videos in the batch) and stats_output_file (the per-query CSV, :146-151, 306-340)
+REF_API int ref_retrieval_stats_ex(int B, int N, const float* E, const float* video_ids, const char* id_to_class_file,
+                                   int exclude_same_video_shots, int video_level, int max_num_videos,
+                                   const char* stats_output_file, float* out3) {
+  try {
+    Caffe::set_mode(Caffe::CPU);
+    Blob<float> e(B, N, 1, 1), ids(B, 1, 1, 1), t0, t1, t2;
+    memcpy(e.mutable_cpu_data(), E, sizeof(float) * size_t(B) * N);
+    memcpy(ids.mutable_cpu_data(), video_ids, sizeof(float) * B);
+    LayerParameter p;
+    p.mutable_retrieval_stats_param()->set_id_to_class_file(id_to_class_file);
+    p.mutable_retrieval_stats_param()->set_exclude_same_video_shots(exclude_same_video_shots != 0);
+    if (video_level) {
+      p.mutable_retrieval_stats_param()->set_video_level_retrieval(true);
+      p.mutable_retrieval_stats_param()->set_max_num_videos(max_num_videos);
+    }
+    if (stats_output_file && *stats_output_file) p.mutable_retrieval_stats_param()->set_stats_output_file(stats_output_file);
+    RetrievalStatsLayer<float> l(p);
+    BV bv{&e, &ids}, tv{&t0, &t1, &t2};
+    l.SetUp(bv, &tv); l.Forward(bv, &tv);
+    out3[0] = t0.cpu_data()[0]; out3[1] = t1.cpu_data()[0]; out3[2] = t2.cpu_data()[0];
+    return 0;
+  } catch (const std::exception& e) { fprintf(stderr, "ref_driver: %s\n", e.what()); return -1; }
+}
 // IdToWeightMappingLayer (id_to_weight_mapping_layer.cpp): table [rows,N], ids [M]; top [M,N] and the table gradient for top_diff
 REF_API int ref_id_to_weight(int M, int N, int rows, const float* table, const float* ids, const float* top_diff,
                              float* top, float* table_diff) {

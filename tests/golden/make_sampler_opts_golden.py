@@ -15,7 +15,7 @@ from oracle import pyref  # noqa: E402
 assert pyref.available(), "build oracle/_ref first: bash oracle/ref_shim/build_ref.sh"
 OUT = os.path.dirname(os.path.abspath(__file__))
 rng = np.random.RandomState(77)
-K = 5
+K = 8                                            # the device gather takes feature sizes that are multiples of 4
 
 
 def dataset(V, lo, hi, vid0):

@@ -104,6 +104,68 @@ def test_weighted_max_margin_reproduces_reference(vvlib, tmp_path):
             assert rel(diffs[0], g["%s_dt%d" % (form, norm)]) < 1e-6 and rel(diffs[1], g["%s_db%d" % (form, norm)]) < 1e-6 and diffs[2] is None
 
 
+def _csv_rows(text):
+    rows = []
+    for line in text.strip().splitlines():
+        if line.startswith("#"):
+            rows.append(line)
+        else:
+            f = line.split(",")
+            rows.append((int(f[0]), int(f[1]), float(f[2]), float(f[3]), float(f[4])) + tuple(int(x) for x in f[5:]))
+    return rows
+
+
+def _csv_equal(a, b):
+    if len(a) != len(b):
+        return False
+    for x, y in zip(a, b):
+        if isinstance(x, str) or isinstance(y, str):
+            if x != y:
+                return False
+        elif x[:2] != y[:2] or x[5:] != y[5:] or any(abs(p - q) > 2e-6 for p, q in zip(x[2:5], y[2:5])):
+            return False
+    return True
+
+
+@pytest.mark.parametrize("excl", [0, 1])
+def test_retrieval_stats_video_level_and_csv_reproduce_reference(vvlib, tmp_path, excl):
+    """RetrievalStatsLayer's `video_level_retrieval` and `stats_output_file` (retrieval_stats_layer.cpp:146-206, 306-340)
+    through the reference's interface (caffe_compat's layer, driven alone) against the compiled reference layer's outputs
+    and CSV files (tests/golden/retrieval_opts.npz <- make_retrieval_opts_golden.py).  Video-level CSV lines come in the
+    reference's hash-map order there and in ascending video id here: compared as sets."""
+    from videovector_b200 import caffe_host
+    from videovector_b200.ops import _ptr, _stream
+    from videovector_b200._lib import check
+    g = np.load(os.path.join(GOLD, "retrieval_opts.npz"))
+    E, vids = g["E"], g["vids"]
+    B, N = E.shape
+    idf = tmp_path / "id2class.txt"
+    idf.write_text("".join("%d,%d\n" % (int(a), int(b)) for a, b in zip(g["map_ids"], g["map_cls"])))
+    # the mean embeddings themselves
+    uniq = sorted(set(int(v) for v in vids))
+    group = torch.as_tensor(np.array([uniq.index(int(v)) for v in vids], np.int32)).cuda()
+    Ed = torch.as_tensor(E).cuda()
+    mean = torch.empty((len(uniq), N), device="cuda")
+    check(vvlib.vv_video_mean_rows(_ptr(Ed), B, N, _ptr(group), len(uniq), _ptr(mean), _stream()))
+    want = np.stack([E[vids == v].astype(np.float64).mean(0) for v in uniq])
+    assert rel(mean, want) < 1e-6
+    caffe_host.set_device(0)
+    for level, key in ((False, "shot"), (True, "video")):
+        csv = tmp_path / ("%s_%d.csv" % (key, excl))
+        text = ('layers { name: "retrieval_stats" type: RETRIEVAL_STATS bottom: "e" bottom: "ids" top: "map" top: "hit1" top: "hit5" '
+                'retrieval_stats_param { id_to_class_file: "%s" stats_output_file: "%s" exclude_same_video_shots: %s%s } }'
+                % (idf, csv, "true" if excl else "false",
+                   (" video_level_retrieval: true max_num_videos: %d" % int(g["max_num_videos"])) if level else ""))
+        _, tops, _ = caffe_host.run_layer(text, [E.reshape(B, N, 1, 1), vids.reshape(B, 1, 1, 1)], 3)
+        got = np.array([t[0] for t in tops])
+        assert np.abs(got - g["%s_out_%d" % (key, excl)]).max() < 2e-6, (key, got, g["%s_out_%d" % (key, excl)])
+        ours = _csv_rows(csv.read_text())
+        ref = _csv_rows(bytes(g["%s_csv_%d" % (key, excl)]).decode())
+        if level:
+            ours = [ours[0]] + sorted(ours[1:]); ref = [ref[0]] + sorted(ref[1:])
+        assert _csv_equal(ours, ref), (key, ours[:3], ref[:3])
+
+
 def test_device_eval_kernels_reproduce_reference_fixtures():
     """vv_retrieval_stats / vv_id_lookup_* against the compiled reference's outputs (tests/golden/eval_layers.npz)."""
     import torch

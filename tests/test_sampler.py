@@ -224,8 +224,8 @@ def test_sampler_options_reproduce_reference_data_layer(vvlib, oracle, name):
     bank = np.concatenate([g["feat"], g["nfeat"]]) if with_neg else g["feat"]
     base = len(g["feat"])
     oneg = (g["nvid"], g["noff"], g["nsid"], g["nfeat"], base) if with_neg else None
-    osmp = oracle.Sampler(g["vid"], g["off"], g["sid"], g["feat"], 5, B, C, Nn, P, swap, max_same, 100, seed=1, context_type=mode,
-                          start_skip=skip, negative_dataset=oneg)
+    osmp = oracle.Sampler(g["vid"], g["off"], g["sid"], g["feat"], g["feat"].shape[1], B, C, Nn, P, swap, max_same, 100, seed=1,
+                          context_type=mode, start_skip=skip, negative_dataset=oneg)
     for i in range(ref.shape[0]):
         idx, quirk, data = osmp.next()
         assert np.array_equal(data, ref[i]), "oracle differs from the reference data layer at batch %d" % i
@@ -244,7 +244,7 @@ def test_sampler_options_reproduce_reference_data_layer(vvlib, oracle, name):
             ops.Sampler(g["vid"], g["off"], g["sid"], B, C, Nn, P - 1, swap, max_same, 100, rand_seed=1, context_type=mode,
                         negative_dataset=pneg)
         with pytest.raises(Exception):
-            oracle.Sampler(g["vid"], g["off"], g["sid"], g["feat"], 5, B, C, Nn, P - 1, swap, max_same, 100, seed=1,
+            oracle.Sampler(g["vid"], g["off"], g["sid"], g["feat"], g["feat"].shape[1], B, C, Nn, P - 1, swap, max_same, 100, seed=1,
                            context_type=mode, negative_dataset=oneg)
 
 

@@ -114,6 +114,8 @@ SIGNATURES = {
     "vv_gather_mean_rows": (_i, [_P, _i64, _i, _P, _i, _i, _P, _P, _P]),
     "vv_retrieval_stats_workspace_bytes": (C.c_size_t, [_i]),
     "vv_retrieval_stats": (_i, [_P, _i, _i, _P, _P, _i, _P, _P, C.c_size_t, _P, _P, _P]),
+    "vv_retrieval_stats_ex": (_i, [_P, _i, _i, _P, _P, _i, _P, _P, C.c_size_t, _P, _P, _P, _P]),
+    "vv_video_mean_rows": (_i, [_P, _i, _i, _P, _i, _P, _P]),
     "vv_record_set_create": (_P, [_i, _i, _i]),
     "vv_record_set_destroy": (None, [_P]),
     "vv_record_set_add": (_i, [_P, C.c_char_p, C.c_size_t]),

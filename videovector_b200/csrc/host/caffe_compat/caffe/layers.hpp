@@ -296,7 +296,10 @@ class RetrievalStatsLayer : public Layer<Dtype> {
   virtual void Backward_gpu(const vector<Blob<Dtype>*>& top, const vector<bool>& propagate_down, vector<Blob<Dtype>*>* bottom) {}
   std::map<int, int> video_id_to_class_;
   bool exclude_same_video_shots_ = true;
-  DeviceBuffer ids_dev_, labels_dev_, work_, out_dev_;
+  bool video_level_ = false;            // video_level_retrieval: rank per-video mean embeddings (ref: :160-206)
+  int max_num_videos_ = 0;
+  string stats_output_file_;            // per-query CSV (ref: :146-151, 306-340)
+  DeviceBuffer ids_dev_, labels_dev_, work_, out_dev_, group_dev_, mean_dev_, top5_dev_;
 };
 
 }  // namespace caffe

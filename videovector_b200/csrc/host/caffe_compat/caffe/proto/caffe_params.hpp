@@ -132,6 +132,7 @@ struct RetrievalStatsParameter : ParamBase {
   string stats_output_file() const { return m->str("stats_output_file", ""); }
   bool exclude_same_video_shots() const { return m->boolean("exclude_same_video_shots", true); }
   bool video_level_retrieval() const { return m->boolean("video_level_retrieval", false); }
+  int max_num_videos() const { return int(m->num("max_num_videos", 0)); }
 };
 struct NetStateRule : ParamBase { using ParamBase::ParamBase; bool has_phase() const { return m->has("phase"); } Caffe::Phase phase() const { return m->str("phase") == "TEST" ? Caffe::TEST : Caffe::TRAIN; } };
 

@@ -689,8 +689,10 @@ void VideoShotWindowTestDataLayer<Dtype>::Forward_gpu(const vector<Blob<Dtype>*>
 template <typename Dtype>
 void RetrievalStatsLayer<Dtype>::LayerSetUp(const vector<Blob<Dtype>*>& bottom, vector<Blob<Dtype>*>* top) {
   const RetrievalStatsParameter p = this->layer_param_.retrieval_stats_param();
-  CHECK(!p.video_level_retrieval()) << "video_level_retrieval is not built";
-  CHECK(p.stats_output_file().empty()) << "stats_output_file is not built";
+  video_level_ = p.video_level_retrieval();
+  max_num_videos_ = p.max_num_videos();
+  if (video_level_) CHECK_GE(max_num_videos_, 1) << "To do video level retrieval ... need min 1 video";
+  stats_output_file_ = p.stats_output_file();
   exclude_same_video_shots_ = p.exclude_same_video_shots();
   std::ifstream f(p.id_to_class_file().c_str());
   CHECK(f.good()) << "cannot open id_to_class_file " << p.id_to_class_file();
@@ -716,24 +718,69 @@ template <typename Dtype>
 void RetrievalStatsLayer<Dtype>::Forward_gpu(const vector<Blob<Dtype>*>& bottom, vector<Blob<Dtype>*>* top) {
   const int B = bottom[0]->num(), N = bottom[0]->count() / bottom[0]->num();
   const Dtype* vids = bottom[1]->cpu_data();
-  vector<int32_t> ids(B), labels(B);
-  for (int b = 0; b < B; ++b) {
-    ids[b] = static_cast<int>(vids[b]);
-    labels[b] = video_id_to_class_[ids[b]];        // operator[]: an unlisted video gets class 0, as in the reference (:249-253)
-  }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(Caffe::stream());
-  int32_t* d_ids = static_cast<int32_t*>(ids_dev_.get(sizeof(int32_t) * B));
-  int32_t* d_lab = static_cast<int32_t*>(labels_dev_.get(sizeof(int32_t) * B));
-  CHECK_EQ(int(cudaMemcpyAsync(d_ids, ids.data(), sizeof(int32_t) * B, cudaMemcpyHostToDevice, s)), 0);
-  CHECK_EQ(int(cudaMemcpyAsync(d_lab, labels.data(), sizeof(int32_t) * B, cudaMemcpyHostToDevice, s)), 0);
-  const size_t ws = vv_retrieval_stats_workspace_bytes(B);
-  double* out = static_cast<double*>(out_dev_.get(3 * sizeof(double)));
-  VV_CHECK(vv_retrieval_stats(bottom[0]->gpu_data(), B, N, d_ids, d_lab, exclude_same_video_shots_ ? 1 : 0, nullptr, work_.get(ws), ws,
-                              out, nullptr, Caffe::stream()));
-  double host[3];
-  CHECK_EQ(int(cudaMemcpyAsync(host, out, sizeof(host), cudaMemcpyDeviceToHost, s)), 0);
+  // the items that are ranked: the batch's shots, or -- video_level_retrieval (ref: :160-206) -- one mean embedding per
+  // video (the reference enumerates the videos in its hash map's order; ascending id here: the statistics do not depend
+  // on it, the CSV's line order does)
+  int Q = B;
+  vector<int32_t> ids(B), labels;
+  for (int b = 0; b < B; ++b) ids[b] = static_cast<int>(vids[b]);
+  const Dtype* E = bottom[0]->gpu_data();
+  if (video_level_) {
+    std::map<int, int> index;
+    for (int b = 0; b < B; ++b) index.insert(std::make_pair(ids[b], 0));
+    CHECK_EQ(int(index.size()), max_num_videos_);
+    vector<int32_t> vid_of;
+    for (auto& kv : index) { kv.second = int(vid_of.size()); vid_of.push_back(kv.first); }
+    vector<int32_t> group(B);
+    for (int b = 0; b < B; ++b) group[b] = index[ids[b]];
+    Q = int(vid_of.size());
+    int32_t* d_group = static_cast<int32_t*>(group_dev_.get(sizeof(int32_t) * B));
+    CHECK_EQ(int(cudaMemcpyAsync(d_group, group.data(), sizeof(int32_t) * B, cudaMemcpyHostToDevice, s)), 0);
+    float* mean = static_cast<float*>(mean_dev_.get(sizeof(float) * size_t(Q) * N));
+    VV_CHECK(vv_video_mean_rows(E, B, N, d_group, Q, mean, Caffe::stream()));
+    CHECK_EQ(int(cudaStreamSynchronize(s)), 0);          // `group` is a local
+    E = mean;
+    ids = vid_of;
+  }
+  CHECK_GT(Q, 1) << "retrieval statistics need at least two items";
+  labels.resize(Q);
+  for (int q = 0; q < Q; ++q) labels[q] = video_id_to_class_[ids[q]];   // operator[]: an unlisted video gets class 0, as in the reference (:249-253)
+  int32_t* d_ids = static_cast<int32_t*>(ids_dev_.get(sizeof(int32_t) * Q));
+  int32_t* d_lab = static_cast<int32_t*>(labels_dev_.get(sizeof(int32_t) * Q));
+  CHECK_EQ(int(cudaMemcpyAsync(d_ids, ids.data(), sizeof(int32_t) * Q, cudaMemcpyHostToDevice, s)), 0);
+  CHECK_EQ(int(cudaMemcpyAsync(d_lab, labels.data(), sizeof(int32_t) * Q, cudaMemcpyHostToDevice, s)), 0);
+  const size_t ws = vv_retrieval_stats_workspace_bytes(Q);
+  const bool csv = !stats_output_file_.empty();
+  double* out = static_cast<double*>(out_dev_.get((3 + (csv ? 3 * size_t(Q) : 0)) * sizeof(double)));
+  double* d_pq = csv ? out + 3 : nullptr;
+  int32_t* d_top5 = csv ? static_cast<int32_t*>(top5_dev_.get(sizeof(int32_t) * 5 * Q)) : nullptr;
+  VV_CHECK(vv_retrieval_stats_ex(E, Q, N, d_ids, d_lab, exclude_same_video_shots_ ? 1 : 0, nullptr, work_.get(ws), ws,
+                                 out, d_pq, d_top5, Caffe::stream()));
+  vector<double> host(3 + (csv ? 3 * size_t(Q) : 0));
+  vector<int32_t> top5(csv ? 5 * size_t(Q) : 0);
+  CHECK_EQ(int(cudaMemcpyAsync(host.data(), out, host.size() * sizeof(double), cudaMemcpyDeviceToHost, s)), 0);
+  if (csv) CHECK_EQ(int(cudaMemcpyAsync(top5.data(), d_top5, top5.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, s)), 0);
   CHECK_EQ(int(cudaStreamSynchronize(s)), 0);
   for (int i = 0; i < 3; ++i) (*top)[i]->mutable_cpu_data()[0] = Dtype(host[i]);
+  if (csv) {
+    // the per-query CSV (ref: :146-151, 306-340): scored queries only, in item order; default ostream formatting
+    std::ofstream f(stats_output_file_.c_str());
+    f << "#video_id,class_id,ap,acc@1,acc@5" << ",ret_id_1,ret_id_2,ret_id_3,ret_id_4,ret_id_5"
+      << ",class_id_1,class_id_2,class_id_3,class_id_4,class_id_5" << std::endl;
+    int t5[5] = {0, 0, 0, 0, 0};              // the reference's vector outlives the loop: a missing entry keeps its last value
+    for (int q = 0; q < Q; ++q) {
+      if (labels[q] < 0) continue;
+      const double ap = host[3 + 3 * q], a1 = host[3 + 3 * q + 1], a5 = host[3 + 3 * q + 2];
+      f << ids[q] << "," << labels[q] << "," << ap << "," << a1 << "," << a5;
+      if (!video_level_) {
+        for (int k = 0; k < 5; ++k) if (top5[5 * size_t(q) + k] >= 0) t5[k] = top5[5 * size_t(q) + k];
+        for (int k = 0; k < 5; ++k) f << "," << t5[k];
+        for (int k = 0; k < 5; ++k) f << "," << video_id_to_class_[ids[t5[k]]];
+      }
+      f << std::endl;
+    }
+  }
 }
 
 // =================================== factory ===================================

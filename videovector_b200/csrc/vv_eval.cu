@@ -41,7 +41,8 @@ gather_mean_kernel(const float* __restrict__ bank, const int* __restrict__ idx, 
 // hit@5 = (#relevant with val <= 5) / 5.  per_query[i] = {ap, hit1, hit5} or -1s when labels[i] < 0 (:256-258).
 __global__ void __launch_bounds__(256)
 retrieval_stats_kernel(const float* __restrict__ G, int B, int n2, const int* __restrict__ video_ids,
-                       const int* __restrict__ labels, int exclude_same, double* __restrict__ per_query) {
+                       const int* __restrict__ labels, int exclude_same, double* __restrict__ per_query,
+                       int* __restrict__ top5) {
   extern __shared__ unsigned char sm_raw[];
   float* key = reinterpret_cast<float*>(sm_raw);
   int* id = reinterpret_cast<int*>(key + n2);
@@ -50,6 +51,7 @@ retrieval_stats_kernel(const float* __restrict__ G, int B, int n2, const int* __
   const int i = blockIdx.x, T = blockDim.x, tid = threadIdx.x;
   if (labels[i] < 0) {
     if (tid < 3) per_query[3 * i + tid] = -1.0;
+    if (top5 && tid < 5) top5[5 * i + tid] = -1;
     return;
   }
   for (int j = tid; j < n2; j += T) {
@@ -72,8 +74,18 @@ retrieval_stats_kernel(const float* __restrict__ G, int B, int n2, const int* __
       __syncthreads();
     }
   }
-  // scan positions 1..B-1 in chunks of consecutive positions per thread
   const int vi = video_ids[i], li = labels[i];
+  // the CSV's "ret_id_1..5" (:309-316): the first five ranked items of ANOTHER video, whatever exclude_same says
+  // (-1 where fewer exist: the reference leaves the previous query's value there, the host side mimics that)
+  if (top5 && tid == 0) {
+    int found = 0;
+    for (int k = 0; k < B && found < 5; ++k) {
+      const int j = id[k];
+      if (video_ids[j] != vi) top5[5 * i + found++] = j;
+    }
+    for (; found < 5; ++found) top5[5 * i + found] = -1;
+  }
+  // scan positions 1..B-1 in chunks of consecutive positions per thread
   const int per = (B + T - 1) / T;
   const int p0 = tid * per, p1 = min(B, p0 + per);
   int nval = 0, nrel = 0;
@@ -108,6 +120,23 @@ retrieval_stats_kernel(const float* __restrict__ G, int B, int n2, const int* __
     per_query[3 * i] = total_ret > 0 ? sap / double(total_ret) : 0.0;
     per_query[3 * i + 1] = s1;
     per_query[3 * i + 2] = s5 / 5.0;
+  }
+}
+
+// video_level_retrieval (:160-206): out[v,:] = sum over the batch items i of video v, in increasing i, of (1/n_v) * E[i,:]
+// -- the reference's GEMM with the [V,B] matrix of 1/n_v entries.  group[i] in [0,V): the item's video.  One CTA per video.
+__global__ void __launch_bounds__(256)
+video_mean_kernel(const float* __restrict__ E, const int* __restrict__ group, int B, int N, float* __restrict__ out) {
+  __shared__ int s_n;
+  const int v = blockIdx.x;
+  if (threadIdx.x == 0) { int n = 0; for (int i = 0; i < B; ++i) n += group[i] == v; s_n = n; }
+  __syncthreads();
+  const float w = float(1.0 / double(s_n > 0 ? s_n : 1));
+  for (int c = threadIdx.x; c < N; c += blockDim.x) {
+    float acc = 0.f;
+    for (int i = 0; i < B; ++i)
+      if (group[i] == v) acc = fmaf(w, E[(size_t)i * N + c], acc);
+    out[(size_t)v * N + c] = acc;
   }
 }
 
@@ -174,9 +203,24 @@ extern "C" size_t vv_retrieval_stats_workspace_bytes(int B) {
   return ((size_t(B) * B * sizeof(float) + 7) & ~size_t(7)) + size_t(B) * 3 * sizeof(double);
 }
 
+extern "C" int vv_video_mean_rows(const float* E, int B, int N, const int32_t* group, int V, float* out, vv_stream_t stream) {
+  VV_REQUIRE(E && group && out && B > 0 && N > 0 && V > 0, "video_mean_rows: bad arguments");
+  video_mean_kernel<<<V, 256, 0, stream>>>(E, group, B, N, out);
+  VV_LAUNCH_CHECK();
+  count_launch();
+  return VV_OK;
+}
+
 extern "C" int vv_retrieval_stats(const float* E, int B, int N, const int32_t* video_ids, const int32_t* labels,
                                   int exclude_same_video_shots, const float* gram_given, void* workspace,
                                   size_t workspace_bytes, double* out3, double* per_query_out, vv_stream_t stream) {
+  return vv_retrieval_stats_ex(E, B, N, video_ids, labels, exclude_same_video_shots, gram_given, workspace, workspace_bytes,
+                               out3, per_query_out, nullptr, stream);
+}
+extern "C" int vv_retrieval_stats_ex(const float* E, int B, int N, const int32_t* video_ids, const int32_t* labels,
+                                     int exclude_same_video_shots, const float* gram_given, void* workspace,
+                                     size_t workspace_bytes, double* out3, double* per_query_out, int32_t* top5,
+                                     vv_stream_t stream) {
   VV_REQUIRE((E || gram_given) && video_ids && labels && out3 && B > 1 && N > 0, "retrieval_stats: bad arguments");
   VV_REQUIRE(workspace && workspace_bytes >= vv_retrieval_stats_workspace_bytes(B), "retrieval_stats: workspace too small");
   int n2 = 1; while (n2 < B) n2 <<= 1;
@@ -198,7 +242,7 @@ extern "C" int vv_retrieval_stats(const float* E, int B, int N, const int32_t* v
   const int T = 256;
   const size_t smem = size_t(n2) * 8 + size_t(2 * T) * 4 + size_t(3 * T) * 8 + 8;
   if (smem > 48 * 1024) VV_CUDA(cudaFuncSetAttribute(retrieval_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-  retrieval_stats_kernel<<<B, T, smem, stream>>>(Guse, B, n2, video_ids, labels, exclude_same_video_shots, pq);
+  retrieval_stats_kernel<<<B, T, smem, stream>>>(Guse, B, n2, video_ids, labels, exclude_same_video_shots, pq, top5);
   VV_LAUNCH_CHECK();
   retrieval_mean_kernel<<<1, 32, 0, stream>>>(pq, labels, B, out3);
   VV_LAUNCH_CHECK();
