@@ -2,7 +2,9 @@
 //
 // One persistent, warp-specialised kernel template for sm_100a:
 //   warp 0   : TMA producer  (cp.async.bulk.tensor 2D tiles, SWIZZLE_128B, mbarrier tx)
-//   warp 1   : MMA issuer    (tcgen05.mma cta_group::1, 128 x BLOCK_N x (32 B of K), fp32 accum in TMEM)
+//   warp 1   : MMA issuer    (tcgen05.mma, fp32 accum in TMEM; the warp runs converged and one elected lane issues:
+//              cta_group::1, 128 x BLOCK_N x (32 B of K) per CTA -- or, Cfg::two_cta, cta_group::2: 256 x BLOCK_N per CTA
+//              PAIR, issued by the leader CTA, each CTA staging its own A rows and half of the B tile)
 //   warp 2   : TMEM allocator; warps 2-3: cp.async row-gather producers of operand A in the gather-fused variants
 //   warps 4-11: epilogue     (tcgen05.ld 32x32b -> bias / ReLU / dropout / scale -> global)
 // Two TMEM accumulator buffers (2 x BLOCK_N columns) let the epilogue of tile i
