@@ -238,6 +238,9 @@ def workload_config(args, world, c=None, prec=None, name="BASELINE configs[1] pe
                             "%s stream(s) per rank, batches round-robin" % (streams if streams is not None else "?"),
             "gather": "fused into the GEMMs (cp.async row gather of the bank's operand copy by two producer warps)"
                       if fused_gather_for(prec, args) else "materialised X (K0 kernel)",
+            "gemm": ("tcgen05.mma cta_group::2: one MMA per CTA pair, each CTA stages its own A rows and half of B"
+                     if (prec == "f16x3" and fused_gather_for(prec, args) and os.environ.get("VV_GEMM_2CTA", "1") != "0")
+                     else "tcgen05.mma cta_group::1, 2-CTA clusters with B multicast") if prec != "fp32_simt" else "fp32 SIMT",
             "l2": "inputs larger than L2: every GEMM streams %.2f GB of gathered operand rows (> 126 MB L2)" % (
                 (c["C"] + c["Nn"]) * c["B"] * c["K"] * OPERAND_BYTES[prec] / 1e9)}
 
