@@ -248,6 +248,28 @@ def test_sampler_options_reproduce_reference_data_layer(vvlib, oracle, name):
                            context_type=mode, negative_dataset=oneg)
 
 
+def test_sampler_option_arguments_are_checked(vvlib):
+    """start_skip wraps around the record count; a negative dataset excludes sub-shard row offsets (its rows are absolute
+    bank rows); malformed option arguments are refused."""
+    g = np.load(GOLD_SAMPLER_OPTS)
+    mode, B, C, Nn, P = [int(x) for x in g["cfg_neg_window"][:5]]
+    V = len(g["vid"])
+    a = ops.Sampler(g["vid"], g["off"], g["sid"], B, C, Nn, 40, 50, 4, 100, rand_seed=1, start_skip=3)
+    b = ops.Sampler(g["vid"], g["off"], g["sid"], B, C, Nn, 40, 50, 4, 100, rand_seed=1, start_skip=3 + 2 * V)
+    for _ in range(3):
+        ia, qa = a.next(); ib, qb = b.next()
+        assert np.array_equal(ia, ib) and np.array_equal(qa, qb)
+    a.close(); b.close()
+    with pytest.raises(Exception):
+        ops.Sampler(g["vid"], g["off"], g["sid"], B, C, Nn, 40, 50, 4, 100, rand_seed=1, start_skip=-1)
+    neg = (g["nvid"], g["noff"], g["nsid"], len(g["feat"]))
+    s = ops.Sampler(g["vid"], g["off"], g["sid"], B, C, Nn, P, 50, 4, 100, rand_seed=1, negative_dataset=neg)
+    assert vvlib.vv_sampler_set_row_base(s._h, 128) != 0 and vvlib.vv_sampler_set_row_base(s._h, 0) == 0
+    idx, _ = s.next()
+    assert (idx[:, C:] >= len(g["feat"])).any()          # buffer negatives of the first batch come from the negative set's rows
+    s.close()
+
+
 @pytest.mark.parametrize("mode,C", [(1, 5), (2, 6), (3, 4), (4, 5), (0, 2)])
 def test_live_reference_data_layer(vvlib, oracle, mode, C):
     """Where oracle/_ref was built: the reference's data layer run live on a fresh dataset against the product sampler."""
